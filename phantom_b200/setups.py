@@ -1,0 +1,397 @@
+"""Synthetic initial conditions restating the reference's IC generators.
+
+The reference builds its ICs with `phantomsetup` (src/setup/); it cannot be
+compiled here, so the generators used by BASELINE.json's configs and by the
+reference's own unit tests are restated in numpy:
+
+  set_unifdis  cubic / closepacked / random   src/setup/set_unifdis.f90:181-233, :354-518, :520-560
+  ran2 / get_random (L'Ecuyer 1988)            src/main/random.f90:38-114
+  test_derivs velocity / energy fields          src/tests/test_derivs.f90:1216-1240, :1604-1613
+  Sod shock tube                                src/setup/set_shock.f90:35-140, setup_shock.f90:497-499
+  MHD blast / Orszag-Tang                       src/setup/setup_mhdblast.f90:70-123, setup_orstang.f90:88-125
+
+Everything returns plain numpy arrays in the Fortran layout the hot-path
+interfaces take: xyzh(4,N) is a C-contiguous (N,4) array, etc.
+"""
+import math
+import numpy as np
+
+from .params import default_params, IGAS, IBOUNDARY, KERNEL_CUBIC, KERNEL_QUINTIC
+
+_M1, _M2 = 2147483563, 2147483399
+_A1, _A2 = 40014, 40692
+EPS = np.finfo(np.float64).eps
+
+
+class Ran2:
+    """ran2(iseed) of src/main/random.f90: two int32 LCG states; a negative seed resets the second."""
+
+    def __init__(self, iseed=-43587):
+        self.s1 = int(iseed)
+        self.s2 = 123456789
+
+    def draw(self, n):
+        """n successive deviates, vectorised: s_k = s_0 * a^k mod m (Schrage's trick in the
+        reference only avoids int32 overflow; the recurrence is a plain modular product)."""
+        if self.s1 < 0:
+            self.s2 = 123456789
+        out = np.empty(n, dtype=np.float64)
+        B = 1 << 15
+        p1 = np.empty(B, dtype=np.uint64)
+        p2 = np.empty(B, dtype=np.uint64)
+        a1 = a2 = 1
+        for k in range(B):
+            a1 = (a1 * _A1) % _M1
+            a2 = (a2 * _A2) % _M2
+            p1[k] = a1
+            p2[k] = a2
+        s1 = self.s1 % _M1
+        s2 = self.s2 % _M2
+        done = 0
+        while done < n:
+            m = min(B, n - done)
+            v1 = (np.uint64(s1) * p1[:m]) % np.uint64(_M1)
+            v2 = (np.uint64(s2) * p2[:m]) % np.uint64(_M2)
+            z = v1.astype(np.int64) - v2.astype(np.int64)
+            z[z < 1] += 2147483562
+            out[done:done + m] = z / 2147483563.0
+            s1, s2 = int(v1[-1]), int(v2[-1])
+            done += m
+        self.s1, self.s2 = s1, s2
+        return out
+
+
+def _nint(x):
+    return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+
+def unifdis_cubic(xmin, xmax, ymin, ymax, zmin, zmax, delta, hfact):
+    """set_unifdis 'cubic' (set_unifdis.f90:181-233): ids run x fastest, then y, then z."""
+    dxb, dyb, dzb = xmax - xmin, ymax - ymin, zmax - zmin
+    nx, ny, nz = _nint(dxb / delta), _nint(dyb / delta), _nint(dzb / delta)
+    dx, dy, dz = dxb / nx, dyb / ny, dzb / nz
+    x = xmin + (np.arange(1, nx + 1) - 0.5) * dx
+    y = ymin + (np.arange(1, ny + 1) - 0.5) * dy
+    z = zmin + (np.arange(1, nz + 1) - 0.5) * dz
+    xyzh = np.empty((nz, ny, nx, 4))
+    xyzh[..., 0] = x[None, None, :]
+    xyzh[..., 1] = y[None, :, None]
+    xyzh[..., 2] = z[:, None, None]
+    xyzh[..., 3] = hfact * dx
+    return np.ascontiguousarray(xyzh.reshape(-1, 4))
+
+
+def closepacked_ny_nz(delta, ymin, ymax, zmin, zmax, periodic=True):
+    dyb, dzb = ymax - ymin, zmax - zmin
+    deltay = delta * math.sqrt(3. / 4.)
+    deltaz = delta * math.sqrt(6.) / 3.
+    ny = int((1. - EPS) * dyb / deltay) + 1
+    nz = int((1. - EPS) * dzb / deltaz) + 1
+    if periodic:
+        ny = 2 * (ny // 2)
+        nz = 3 * (nz // 3)
+    return ny, nz
+
+
+def unifdis_closepacked(xmin, xmax, ymin, ymax, zmin, zmax, delta, hfact, periodic=True, npy=0, npz=0):
+    """set_unifdis 'closepacked' (set_unifdis.f90:354-518), ABC stacking."""
+    dxb, dyb, dzb = xmax - xmin, ymax - ymin, zmax - zmin
+    deltax = delta
+    deltay = delta * math.sqrt(3. / 4.)
+    deltaz = delta * math.sqrt(6.) / 3.
+    delx = 0.5 * delta
+    dely = 1. / 3. * deltay
+    nx = int((1. - EPS) * dxb / deltax) + 1
+    ny = int((1. - EPS) * dyb / deltay) + 1
+    nz = int((1. - EPS) * dzb / deltaz) + 1
+    if npy > 0:
+        ny = npy
+    if npz > 0:
+        nz = npz
+    if periodic:
+        ny = 2 * (ny // 2)
+        nz = 3 * (nz // 3)
+        if npy <= 0:
+            deltax = dxb / float(nx)
+        deltay = dyb / float(ny)
+        deltaz = dzb / float(nz)
+        dely = 1. / 3. * deltay
+    k = np.arange(1, nx + 1)[None, None, :]
+    l = np.arange(1, ny + 1)[None, :, None]
+    m = np.arange(1, nz + 1)[:, None, None]
+    jy = l % 2
+    jz = m % 3
+    xstart = np.full((nz, ny, 1), xmin + 0.5 * delx)
+    ystart = np.full((nz, ny, 1), ymin + 0.5 * dely)
+    zstart = zmin + 0.5 * deltaz
+    jyb = np.broadcast_to(jy, (nz, ny, 1))
+    jzb = np.broadcast_to(jz, (nz, ny, 1))
+    third = (jzb == 0)
+    second = (jzb == 2)
+    first = (jzb == 1)
+    ystart = ystart + np.where(third, 2. * dely, 0.) + np.where(second, dely, 0.)
+    xstart = xstart + np.where(third & (jyb == 0), delx, 0.) + np.where(second & (jyb == 1), delx, 0.) \
+        + np.where(first & (jyb == 0), delx, 0.)
+    xyzh = np.empty((nz, ny, nx, 4))
+    xyzh[..., 0] = xstart + (k - 1.0) * deltax
+    xyzh[..., 1] = ystart + (l - 1.0) * deltay
+    xyzh[..., 2] = zstart + (m - 1.0) * deltaz
+    xyzh[..., 3] = hfact * deltax
+    return np.ascontiguousarray(xyzh.reshape(-1, 4))
+
+
+def unifdis_random(xmin, xmax, ymin, ymax, zmin, zmax, delta, hfact, iseed=-43587, npnew=None, rmax=None):
+    """set_unifdis 'random' (set_unifdis.f90:520-560); rmax trims to a sphere (in_range on rr2)."""
+    dxb, dyb, dzb = xmax - xmin, ymax - ymin, zmax - zmin
+    if npnew is None:
+        npnew = _nint(dxb / delta) * _nint(dyb / delta) * _nint(dzb / delta)
+    rng = Ran2(iseed)
+    got = []
+    ngot = 0
+    while ngot < npnew:
+        ntry = max(1024, int((npnew - ngot) * (2.0 if rmax else 1.0)))
+        r = rng.draw(3 * ntry).reshape(ntry, 3)
+        pts = np.empty((ntry, 3))
+        pts[:, 0] = xmin + r[:, 0] * dxb
+        pts[:, 1] = ymin + r[:, 1] * dyb
+        pts[:, 2] = zmin + r[:, 2] * dzb
+        if rmax is not None:
+            rr2 = pts[:, 0] * pts[:, 0] + pts[:, 1] * pts[:, 1] + pts[:, 2] * pts[:, 2]
+            pts = pts[rr2 < rmax * rmax]
+        got.append(pts)
+        ngot += len(pts)
+    pts = np.concatenate(got)[:npnew]
+    xyzh = np.empty((npnew, 4))
+    xyzh[:, :3] = pts
+    xyzh[:, 3] = hfact * delta
+    return xyzh
+
+
+# ---------------------------------------------------------------------------------------------
+#  a bundle of particle arrays in the layouts the hot-path interfaces take
+# ---------------------------------------------------------------------------------------------
+class Particles:
+    """Host mirror of the slice of part.F90 (src/main/part.F90:47-416) that the hot path touches."""
+
+    def __init__(self, params, xyzh, iphase=None):
+        n = len(xyzh)
+        p = params
+        nvu = p.maxvxyzu
+        self.params = p
+        self.npart = n
+        self.xyzh = np.ascontiguousarray(xyzh, dtype=np.float64)
+        self.vxyzu = np.zeros((n, nvu))
+        self.fxyzu = np.zeros((n, nvu))
+        self.fext = np.zeros((n, 3))
+        self.Bevol = np.zeros((n, 4))
+        self.dBevol = np.zeros((n, 4))
+        self.iphase = np.full(n, IGAS, dtype=np.int8) if iphase is None else np.ascontiguousarray(iphase, dtype=np.int8)
+        self.divcurlv = np.zeros((n, 1), dtype=np.float32)
+        self.divcurlB = np.zeros((n, 4), dtype=np.float32)
+        self.alphaind = np.zeros((n, 3), dtype=np.float32)
+        self.gradh = np.zeros((n, p.ngradh), dtype=np.float32)
+        self.dvdx = np.zeros((n, 9), dtype=np.float32)
+        self.eos_vars = np.zeros((n, 7))
+        self.Bxyz = np.zeros((n, 3))
+        self.poten = np.zeros(n, dtype=np.float32)
+        self.divBsymm = np.zeros(n, dtype=np.float32)
+        self.dustfrac = np.zeros(n)
+        self.tstop = np.zeros(n)
+        self.ibin = np.zeros(n, dtype=np.int8)
+        self.ibin_old = np.zeros(n, dtype=np.int8)
+        self.ibin_wake = np.zeros(n, dtype=np.int8)
+
+    def copy(self):
+        q = Particles.__new__(Particles)
+        q.params = self.params.copy()
+        q.npart = self.npart
+        for k, v in self.__dict__.items():
+            if isinstance(v, np.ndarray):
+                setattr(q, k, v.copy())
+        return q
+
+
+# ---------------------------------------------------------------------------------------------
+#  the reference's test_derivs configuration (src/tests/test_derivs.f90:128-163)
+# ---------------------------------------------------------------------------------------------
+def test_derivs_fields(xyzh, p):
+    """vx,vy,vz (test_derivs.f90:1216-1240) and utherm (:1604-1613)."""
+    dxb, dyb, dzb = p.xmax - p.xmin, p.ymax - p.ymin, p.zmax - p.zmin
+    x, y, z = xyzh[:, 0], xyzh[:, 1], xyzh[:, 2]
+    pi = math.pi
+    vx = 0.5 / pi * dxb * np.sin(2. * pi * (x - p.xmin) / dxb)
+    vy = 0.5 / pi * dxb * np.sin(2. * pi * (x - p.xmin) / dxb) - 0.5 / pi * dzb * np.sin(2. * pi * (z - p.zmin) / dzb)
+    vz = 0.05 / pi * dyb * np.cos(4. * pi * (y - p.ymin) / dyb)
+    u = 0.5 / pi * (3. + np.sin(2. * pi * (x - p.xmin) / dxb) + np.cos(2. * pi * (y - p.ymin) / dyb)
+                    + np.sin(2. * pi * (z - p.zmin) / dzb))
+    return vx, vy, vz, u
+
+
+def setup_test_derivs(nx=100, rhozero=5.0, tolh=1.e-5, lattice="cubic", isothermal=False, mhd=False, iseed=-43587,
+                      dissipation=True, **kw):
+    """test_derivs.f90:128-163; dissipation=False restates reset_dissipation_to_zero (:989-1003)."""
+    if not dissipation:
+        kw = dict(alpha=0., alphau=0., alphaB=0., beta=0., **kw)
+    p = default_params(tolh=tolh, isothermal=int(isothermal), mhd=int(mhd), ieos=1 if isothermal else 2, **kw)
+    if isothermal:
+        p.polyk, p.gamma = 3.0, 1.0
+    dxb = p.xmax - p.xmin
+    psep = dxb / nx
+    if lattice == "cubic":
+        xyzh = unifdis_cubic(p.xmin, p.xmax, p.ymin, p.ymax, p.zmin, p.zmax, psep, p.hfact)
+    elif lattice == "closepacked":
+        xyzh = unifdis_closepacked(p.xmin, p.xmax, p.ymin, p.ymax, p.zmin, p.zmax, psep, p.hfact, periodic=bool(p.periodic))
+    else:
+        xyzh = unifdis_random(p.xmin, p.xmax, p.ymin, p.ymax, p.zmin, p.zmax, psep, p.hfact, iseed=iseed)
+    n = len(xyzh)
+    totmass = rhozero * dxb * (p.ymax - p.ymin) * (p.zmax - p.zmin)
+    p.massoftype[IGAS] = totmass / n
+    part = Particles(p, xyzh)
+    vx, vy, vz, u = test_derivs_fields(xyzh, p)
+    part.vxyzu[:, 0], part.vxyzu[:, 1], part.vxyzu[:, 2] = vx, vy, vz
+    if not isothermal:
+        part.vxyzu[:, 3] = u
+    if mhd:
+        # a smooth divergence-free test field, stored as B/rho
+        x, y, z = xyzh[:, 0], xyzh[:, 1], xyzh[:, 2]
+        pi = math.pi
+        Bx = 0.5 * np.sin(2 * pi * (y - p.ymin)) + 0.3
+        By = 0.4 * np.sin(2 * pi * (z - p.zmin))
+        Bz = 0.6 * np.cos(2 * pi * (x - p.xmin)) - 0.2
+        part.Bevol[:, 0], part.Bevol[:, 1], part.Bevol[:, 2] = Bx / rhozero, By / rhozero, Bz / rhozero
+        part.Bevol[:, 3] = 0.05 * np.sin(2 * pi * (x - p.xmin)) * np.cos(2 * pi * (y - p.ymin))
+    hzero = p.hfact * (p.massoftype[IGAS] / rhozero) ** (1. / 3.)
+    return part, hzero
+
+
+# ---------------------------------------------------------------------------------------------
+#  BASELINE.json configs
+# ---------------------------------------------------------------------------------------------
+def _solenoidal_field(xyzh, box, seed, mach, cs, kmin=1, kmax=3):
+    """Seeded solenoidal Gaussian velocity field, k in [kmin,kmax]*2pi/L, rms Mach `mach`
+    (substitute for the OU-driven state; data/forcing/forcing.dat is not shipped)."""
+    rng = np.random.RandomState(seed)
+    xmin, L = box
+    x = (xyzh[:, :3] - xmin) / L
+    v = np.zeros((len(xyzh), 3))
+    for kx in range(-kmax, kmax + 1):
+        for ky in range(-kmax, kmax + 1):
+            for kz in range(0, kmax + 1):
+                k2 = kx * kx + ky * ky + kz * kz
+                if k2 < kmin * kmin or k2 > kmax * kmax:
+                    continue
+                kv = np.array([kx, ky, kz], dtype=float)
+                a = rng.normal(size=3) * k2 ** (-1.0)
+                b = rng.normal(size=3) * k2 ** (-1.0)
+                a -= kv * (a @ kv) / k2          # project out the compressive part
+                b -= kv * (b @ kv) / k2
+                ph = 2. * math.pi * (x @ kv)
+                v += np.outer(np.cos(ph), a) + np.outer(np.sin(ph), b)
+    vrms = math.sqrt(np.mean(np.sum(v * v, axis=1)))
+    return v * (mach * cs / vrms)
+
+
+def setup_turb(nx=128, mach=5.0, seed=1234, ind_timesteps=False):
+    """C2: SETUP=turb -- isothermal periodic box [0,1]^3, cubic lattice nx^3, cs=1, rho0=1
+    (setup_turb.f90:101-176)."""
+    p = default_params(isothermal=1, ieos=1, polyk=1.0, gamma=1.0, ind_timesteps=int(ind_timesteps),
+                       xmin=0., xmax=1., ymin=0., ymax=1., zmin=0., zmax=1., dtmax=0.025 if ind_timesteps else 1e29)
+    xyzh = unifdis_cubic(0., 1., 0., 1., 0., 1., 1.0 / nx, p.hfact)
+    p.massoftype[IGAS] = 1.0 / len(xyzh)
+    part = Particles(p, xyzh)
+    part.vxyzu[:, :3] = _solenoidal_field(xyzh, (0.0, 1.0), seed, mach, 1.0)
+    return part
+
+
+def setup_shock(nx=256, gamma=5. / 3.):
+    """C1: SETUP=shock -- 3D Sod tube, quintic kernel, adiabatic, closepacked, periodic in y,z
+    (setup_shock.f90:497-499 states; set_shock.f90:35-140; adjust_shock_boundaries :180-209)."""
+    rhoL, rhoR, prL, prR = 1.0, 0.125, 1.0, 0.1
+    radkern, hfact = 3.0, 1.0
+    xleft, xright, xshock = -0.5, 0.5, 0.0
+    dxleft = (xshock - xleft) / nx          # nx particles across the left half (nx=256 -> 1/512)
+    dxright = dxleft * (rhoL / rhoR) ** (1. / 3.)
+    fac = -6. * (int(1.99 * radkern / 6.) + 1) * max(dxleft, dxright)
+    ymin, zmin = fac * math.sqrt(0.75), fac * math.sqrt(6.) / 3.
+    ymax, zmax = -ymin, -zmin
+    p = default_params(kernel=KERNEL_QUINTIC, hfact=hfact, gamma=gamma, ieos=2, isothermal=0,
+                       xmin=xleft - 1000. * dxleft, xmax=xright + 1000. * dxright, ymin=ymin, ymax=ymax, zmin=zmin, zmax=zmax)
+    left = unifdis_closepacked(xleft, xshock, ymin, ymax, zmin, zmax, dxleft, hfact, periodic=True)
+    massgas = (xshock - xleft) * (ymax - ymin) * (zmax - zmin) * rhoL / len(left)
+    ny, nz = closepacked_ny_nz(dxright, ymin, ymax, zmin, zmax)
+    totmassR = (xright - xshock) * (ymax - ymin) * (zmax - zmin) * rhoR
+    dxright = (xright - xshock) / ((totmassR / massgas) / (ny * nz))
+    right = unifdis_closepacked(xshock, xright, ymin, ymax, zmin, zmax, dxright, hfact, periodic=True, npy=ny, npz=nz)
+    xyzh = np.concatenate([left, right])
+    n = len(xyzh)
+    p.massoftype[IGAS] = massgas
+    p.massoftype[IBOUNDARY] = massgas
+    isleft = xyzh[:, 0] < xshock
+    rho = np.where(isleft, rhoL, rhoR)
+    pr = np.where(isleft, prL, prR)
+    xyzh[:, 3] = hfact * (massgas / rho) ** (1. / 3.)
+    # boundary particles within nbpts spacings of the x ends (setup_shock.f90:233-250)
+    nbpts = _nint(2.01 * radkern * hfact)
+    iphase = np.full(n, IGAS, dtype=np.int8)
+    iphase[(xyzh[:, 0] < xleft + nbpts * dxleft) | (xyzh[:, 0] > xright - nbpts * dxright)] = IBOUNDARY
+    part = Particles(p, xyzh, iphase)
+    part.vxyzu[:, 3] = pr / ((gamma - 1.) * rho)
+    return part
+
+
+def setup_mhdblast(nx=64):
+    """C3(i): SETUP=mhdblast (setup_mhdblast.f90:70-123): closepacked in [-0.5,0.5]^3, gamma=1.4,
+    rho=1, B=(10/sqrt2, 0, 10/sqrt2), P=100 inside r<0.125 else 1."""
+    gamma = 1.4
+    p = default_params(mhd=1, gamma=gamma, ieos=2)
+    xyzh = unifdis_closepacked(p.xmin, p.xmax, p.ymin, p.ymax, p.zmin, p.zmax, 1.0 / nx, p.hfact, periodic=True)
+    n = len(xyzh)
+    p.massoftype[IGAS] = 1.0 / n
+    part = Particles(p, xyzh)
+    r = np.sqrt(np.sum(xyzh[:, :3] ** 2, axis=1))
+    pr = np.where(r < 0.125, 100.0, 1.0)
+    part.vxyzu[:, 3] = pr / ((gamma - 1.) * 1.0)
+    B0 = 10. / math.sqrt(2.)
+    part.Bevol[:, 0] = B0 / 1.0
+    part.Bevol[:, 2] = B0 / 1.0
+    return part
+
+
+def setup_orstang(nx=64, nlayers=12):
+    """C3(ii): SETUP=orstang (setup_orstang.f90:88-125): thin slab, v=(-sin2piy, sin2pix, 0),
+    B=B0(-sin2piy, sin4pix, 0), B0=1/sqrt(4pi), beta0=10/3, M0=1, gamma=5/3."""
+    gamma = 5. / 3.
+    betazero, machzero = 10. / 3., 1.0
+    const = 4. * math.pi
+    bzero = 1.0 / math.sqrt(const)
+    przero = 0.5 * bzero ** 2 * betazero
+    rhozero = gamma * przero * machzero
+    deltax = 1.0 / nx
+    dz = 4. * math.sqrt(6.) / nx * (nlayers / 12.0)
+    p = default_params(mhd=1, gamma=gamma, ieos=2, xmin=-0.5, xmax=0.5, ymin=-0.5, ymax=0.5, zmin=-dz, zmax=dz)
+    xyzh = unifdis_closepacked(p.xmin, p.xmax, p.ymin, p.ymax, p.zmin, p.zmax, deltax, p.hfact, periodic=True)
+    n = len(xyzh)
+    totmass = rhozero * 1.0 * 1.0 * (2 * dz)
+    p.massoftype[IGAS] = totmass / n
+    part = Particles(p, xyzh)
+    x, y = xyzh[:, 0], xyzh[:, 1]
+    part.xyzh[:, 3] = p.hfact * (p.massoftype[IGAS] / rhozero) ** (1. / 3.)
+    part.vxyzu[:, 0] = -np.sin(2. * math.pi * (y - p.ymin))
+    part.vxyzu[:, 1] = np.sin(2. * math.pi * (x - p.xmin))
+    part.vxyzu[:, 3] = przero / ((gamma - 1.) * rhozero)
+    part.Bevol[:, 0] = -bzero * np.sin(2. * math.pi * (y - p.ymin)) / rhozero
+    part.Bevol[:, 1] = bzero * np.sin(4. * math.pi * (x - p.xmin)) / rhozero
+    return part
+
+
+def setup_random_sphere(n=1000, iseed=-43587, gravity=True, u=0.05):
+    """C5 / test_gravity.f90:300-330: uniform random sphere R=1, M=1."""
+    p = default_params(periodic=0, gravity=int(gravity), ieos=2, xmin=-1., xmax=1., ymin=-1., ymax=1., zmin=-1., zmax=1.)
+    psep = 2.0 / (n * 6.0 / math.pi) ** (1. / 3.)
+    xyzh = unifdis_random(-1., 1., -1., 1., -1., 1., psep, p.hfact, iseed=iseed, npnew=n, rmax=1.0)
+    p.massoftype[IGAS] = 1.0 / n
+    rho0 = 1.0 / (4. / 3. * math.pi)
+    xyzh[:, 3] = p.hfact * (p.massoftype[IGAS] / rho0) ** (1. / 3.)
+    part = Particles(p, xyzh)
+    part.vxyzu[:, 3] = u
+    return part
