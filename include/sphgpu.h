@@ -1,0 +1,185 @@
+/*
+ * sphgpu.h -- C ABI of the B200-native SPH derivative engine.
+ *
+ * The entry points are what a Fortran `bind(C)` shim binds in place of the
+ * reference's hot-path subroutines (danieljprice/phantom v2026.0.1):
+ *
+ *   sphgpu_build_tree              <-> build_tree            src/main/neigh_kdtree.f90:161-208
+ *   sphgpu_densityiterate          <-> densityiterate        src/main/dens.F90:117-152
+ *   sphgpu_cons2prim_everything    <-> cons2prim_everything  src/main/cons2prim.f90:274-291
+ *   sphgpu_force                   <-> force                 src/main/force.F90:193-263
+ *   sphgpu_derivs                  <-> derivs                src/main/deriv.f90:37-232  (the four above in sequence)
+ *   sphgpu_get_neighbour_stats     <-> get_neighbour_stats   src/main/dens.F90:1137-1155
+ *
+ * All array arguments are HOST pointers in the reference's Fortran
+ * column-major layout (xyzh(4,n) = n records of 4 doubles, ...), 1-based
+ * particle identity = position in the array.  "Literal" calls copy in,
+ * compute on the device and copy out, exactly like the Fortran argument
+ * lists; between sphgpu_upload and sphgpu_download the state is resident
+ * on the device and the *_resident calls touch no host memory.
+ * Everything the reference reads from module variables / cpp flags is passed
+ * explicitly in sphgpu_params.
+ *
+ * Return value: 0 on success, non-zero error code otherwise; the message is
+ * returned by sphgpu_last_error (the shim maps it to `call fatal('gpu',msg)`,
+ * src/main/io.F90:525-560).  One host thread per context; not re-entrant.
+ */
+#ifndef SPHGPU_H
+#define SPHGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHGPU_MAXTYPES 8
+
+/* error codes */
+enum {
+    SPHGPU_OK = 0,
+    SPHGPU_ERR_CUDA = 1,          /* CUDA runtime failure (also: no device) */
+    SPHGPU_ERR_ARG = 2,           /* bad argument */
+    SPHGPU_ERR_NAN = 3,           /* NaN in particle position           (kdtree.F90:391) */
+    SPHGPU_ERR_NOPART = 4,        /* no live particles                  (kdtree.F90:162-164) */
+    SPHGPU_ERR_NOCONVERGE = 5,    /* density iteration failed           (dens.F90:1443-1455) */
+    SPHGPU_ERR_NEGH = 6,          /* h < 0 in force                     (force.F90:2271) */
+    SPHGPU_ERR_OVERFLOW = 7,      /* internal neighbour scratch overflow */
+    SPHGPU_ERR_STATE = 8          /* call sequence violated (e.g. density before tree) */
+};
+
+/* cpp-flag tuple + module variables of the reference the path reads implicitly */
+typedef struct sphgpu_params {
+    int32_t kernel;          /* 0 cubic (kernel_cubic.f90) 1 quintic (kernel_quintic.f90); build/Makefile:283-290 */
+    int32_t periodic;        /* -DPERIODIC */
+    int32_t isothermal;      /* -DISOTHERMAL: vxyzu/fxyzu have 3 rows instead of 4 */
+    int32_t mhd;             /* -DMHD */
+    int32_t gravity;         /* -DGRAVITY */
+    int32_t dust;            /* -DDUST */
+    int32_t const_av;        /* -DCONST_AV */
+    int32_t ind_timesteps;   /* -DIND_TIMESTEPS */
+    int32_t disc_viscosity;  /* dim: disc_viscosity */
+    int32_t ieos;            /* eos.f90:183-256: 1, 2, 3 */
+    int32_t ipdv_heating, ishock_heating, iresistive_heating; /* eos.f90:1896-1898 */
+    int32_t set_boundaries_to_active;                          /* part.F90:439 */
+    int32_t idrag;
+    int32_t reserved_i[5];
+    double xmin, xmax, ymin, ymax, zmin, zmax;                 /* boundary.f90 */
+    double hfact, tolh;                                        /* part.F90 hfact, options.f90:92 tolh */
+    double massoftype[SPHGPU_MAXTYPES];                        /* part.F90 massoftype(itype), index 0 unused */
+    double alpha, alphamax, alphau, alphaB, beta;              /* shock_capturing.f90:47-64 */
+    double polyk, gamma, qfacdisc, cs_min;                     /* eos.f90 */
+    double C_cour, C_force, dtmax, psidecayfac, overcleanfac;  /* timestep.f90:52-62 */
+    double tree_accuracy;                                      /* kdtree.F90:46 */
+    double grainsize, graindens, K_code;
+    double reserved_d[8];
+} sphgpu_params;
+
+/* module-variable outputs: timestep:dtcourant,dtforce,rhomaxnow ; dens.F90:104-106 statistics */
+typedef struct sphgpu_scalars {
+    double dtcourant, dtforce, dtmini, dtmaxi, rhomax;
+    double trialmean, actualmean;
+    int64_t maxtrial, maxactual, nrhocalc, nactualtot, np, ncalls_neigh;
+    int64_t npairs_density, npairs_force;   /* real interacting pairs evaluated (roofline accounting) */
+    int64_t nbinmaxnew;
+    int64_t reserved[3];
+} sphgpu_scalars;
+
+/* host array bundle for upload/download (any pointer may be NULL = skip) */
+typedef struct sphgpu_host_arrays {
+    int64_t npart;
+    double *xyzh;        /* (4,n)          */
+    double *vxyzu;       /* (maxvxyzu,n)   */
+    double *fxyzu;       /* (maxvxyzu,n)   */
+    double *fext;        /* (3,n)          */
+    double *Bevol;       /* (4,n)          */
+    double *dBevol;      /* (4,n)          */
+    double *eos_vars;    /* (7,n)          */
+    float *divcurlv;     /* (1,n)          */
+    float *divcurlB;     /* (4,n)          */
+    float *alphaind;     /* (3,n)          */
+    float *gradh;        /* (ngradh,n)     */
+    float *dvdx;         /* (9,n)          */
+    float *poten;        /* (n)            */
+    float *divBsymm;     /* (n)            */
+    int8_t *iphase;      /* (n)            */
+    int8_t *ibin, *ibin_old, *ibin_wake;
+} sphgpu_host_arrays;
+
+/* field mask bits for upload/download */
+#define SPHGPU_F_XYZH      (1ull << 0)
+#define SPHGPU_F_VXYZU     (1ull << 1)
+#define SPHGPU_F_FXYZU     (1ull << 2)
+#define SPHGPU_F_FEXT      (1ull << 3)
+#define SPHGPU_F_BEVOL     (1ull << 4)
+#define SPHGPU_F_DBEVOL    (1ull << 5)
+#define SPHGPU_F_EOSVARS   (1ull << 6)
+#define SPHGPU_F_DIVCURLV  (1ull << 7)
+#define SPHGPU_F_DIVCURLB  (1ull << 8)
+#define SPHGPU_F_ALPHAIND  (1ull << 9)
+#define SPHGPU_F_GRADH     (1ull << 10)
+#define SPHGPU_F_DVDX      (1ull << 11)
+#define SPHGPU_F_POTEN     (1ull << 12)
+#define SPHGPU_F_DIVBSYMM  (1ull << 13)
+#define SPHGPU_F_IPHASE    (1ull << 14)
+#define SPHGPU_F_IBIN      (1ull << 15)
+#define SPHGPU_F_ALL       (~0ull)
+
+typedef struct sphgpu_ctx sphgpu_ctx;
+
+int  sphgpu_create(const sphgpu_params *params, int device, sphgpu_ctx **out);
+void sphgpu_destroy(sphgpu_ctx *ctx);
+int  sphgpu_set_params(sphgpu_ctx *ctx, const sphgpu_params *params);
+const char *sphgpu_last_error(sphgpu_ctx *ctx);
+/* tuning knobs: "max_cell" (particles per leaf cell, <=32), "list_margin" (x1e-4) ... ; returns 0 if known */
+int  sphgpu_set_option(sphgpu_ctx *ctx, const char *name, double value);
+/* per-phase device times of the last derivs (ms): tree, dens, cons2prim, force ; utils_timing.f90 labels */
+int  sphgpu_get_timings(sphgpu_ctx *ctx, double *ms4);
+/* number of kernel launches issued by this context since creation */
+int64_t sphgpu_launch_count(sphgpu_ctx *ctx);
+
+/* ---- resident mode ------------------------------------------------------------------- */
+int sphgpu_upload(sphgpu_ctx *ctx, const sphgpu_host_arrays *h, uint64_t mask);
+int sphgpu_download(sphgpu_ctx *ctx, sphgpu_host_arrays *h, uint64_t mask);
+int sphgpu_build_tree_resident(sphgpu_ctx *ctx);
+int sphgpu_densityiterate_resident(sphgpu_ctx *ctx, int icall, sphgpu_scalars *out);
+int sphgpu_cons2prim_resident(sphgpu_ctx *ctx);
+int sphgpu_force_resident(sphgpu_ctx *ctx, int icall, double dt, sphgpu_scalars *out);
+int sphgpu_derivs_resident(sphgpu_ctx *ctx, int icall, double dt, sphgpu_scalars *out);
+
+/* ---- literal mode: the reference's argument lists, host pointers ------------------------ */
+/* build_tree(npart,nactive,xyzh,vxyzu)  [+ hidden input iphase]; xyzh is inout (periodic wrap) */
+int sphgpu_build_tree(sphgpu_ctx *ctx, int64_t npart, int64_t nactive, double *xyzh, const double *vxyzu,
+                      const int8_t *iphase);
+/* densityiterate(icall,npart,nactive,xyzh,vxyzu,divcurlv,divcurlB,Bevol,stressmax,fxyzu,fext,alphaind,gradh,rad,radprop,dvdx,apr_level) */
+int sphgpu_densityiterate(sphgpu_ctx *ctx, int icall, int64_t npart, int64_t nactive, double *xyzh, const double *vxyzu,
+                          float *divcurlv, float *divcurlB, const double *Bevol, double *stressmax,
+                          const double *fxyzu, const double *fext, float *alphaind, float *gradh, float *dvdx,
+                          const int8_t *iphase, sphgpu_scalars *out);
+/* cons2prim_everything(npart,xyzh,vxyzu,dvdx,rad,eos_vars,radprop,Bevol,Bxyz,dustevol,dustfrac,alphaind) */
+int sphgpu_cons2prim_everything(sphgpu_ctx *ctx, int64_t npart, const double *xyzh, const double *vxyzu,
+                                const float *dvdx, double *eos_vars, const double *Bevol, double *Bxyz,
+                                float *alphaind, const int8_t *iphase);
+/* force(icall,npart,xyzh,vxyzu,fxyzu,divcurlv,divcurlB,Bevol,dBevol,...,fext,...,dt,stressmax,eos_vars,...) */
+int sphgpu_force(sphgpu_ctx *ctx, int icall, int64_t npart, const double *xyzh, const double *vxyzu, double *fxyzu,
+                 float *divcurlv, const float *divcurlB, const double *Bevol, double *dBevol, const double *fext,
+                 double dt, double stressmax, const double *eos_vars, const float *alphaind, const float *gradh,
+                 const float *dvdx, const int8_t *iphase, float *poten, float *divBsymm, sphgpu_scalars *out);
+/* derivs(icall,...): upload -> tree -> density -> cons2prim -> force -> download, all arrays of the bundle */
+int sphgpu_derivs(sphgpu_ctx *ctx, int icall, sphgpu_host_arrays *h, double dt, sphgpu_scalars *out);
+
+/* get_neighbour_stats(trialmean,actualmean,maxtrial,maxactual,nrhocalc,nactualtot) of the last density call */
+int sphgpu_get_neighbour_stats(sphgpu_ctx *ctx, sphgpu_scalars *out);
+/* exact neighbour sets of the last tree/density state in CSR form (1-based ids, sorted), for parity tests;
+ * symmetric=0: {j!=i : q2i < radkern2}; symmetric=1: {q2i < radkern2 or q2j < radkern2}.
+ * returns total count, or -(needed) when maxlist is too small */
+int64_t sphgpu_neighbour_sets(sphgpu_ctx *ctx, int symmetric, int64_t *offsets, int32_t *list, int64_t maxlist);
+
+/* register-resident DFMA microbenchmark: returns measured FP64 TFLOP/s of this device (roofline denominator) */
+double sphgpu_measure_fp64_peak(sphgpu_ctx *ctx);
+/* device copy bandwidth GB/s (read+write) */
+double sphgpu_measure_copy_bw(sphgpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,241 @@
+"""Host-side mirror of the reference's hot-path interface on top of the C ABI (include/sphgpu.h).
+
+`SphGpu` exposes the same call sequence `derivs` makes in the reference
+(src/main/deriv.f90:113-192):
+
+    build_tree(npart,nactive,xyzh,vxyzu)        neigh_kdtree.f90:161
+    densityiterate(icall,...)                   dens.F90:117
+    cons2prim_everything(...)                   cons2prim.f90:274
+    force(icall,...)                            force.F90:193
+
+with the same argument meaning (arrays in Fortran layout, updated in place)
+and the reference's error behaviour (`fatal` -> `SphGpuError`).  There is no
+CPU fallback: if the CUDA library is missing or no device is present the
+constructor raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from .params import SphParams, SphScalars
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsphgpu.so")
+
+F_XYZH, F_VXYZU, F_FXYZU, F_FEXT, F_BEVOL, F_DBEVOL, F_EOSVARS, F_DIVCURLV, F_DIVCURLB, F_ALPHAIND, F_GRADH, F_DVDX, \
+    F_POTEN, F_DIVBSYMM, F_IPHASE, F_IBIN = [1 << k for k in range(16)]
+F_ALL = (1 << 64) - 1
+
+ERRORS = {1: "CUDA", 2: "ARG", 3: "NAN", 4: "NOPART", 5: "NOCONVERGE", 6: "NEGH", 7: "OVERFLOW", 8: "STATE"}
+
+EXPORTS = [
+    "sphgpu_create", "sphgpu_destroy", "sphgpu_set_params", "sphgpu_last_error", "sphgpu_set_option", "sphgpu_get_timings",
+    "sphgpu_launch_count", "sphgpu_upload", "sphgpu_download", "sphgpu_build_tree_resident", "sphgpu_densityiterate_resident",
+    "sphgpu_cons2prim_resident", "sphgpu_force_resident", "sphgpu_derivs_resident", "sphgpu_build_tree", "sphgpu_densityiterate",
+    "sphgpu_cons2prim_everything", "sphgpu_force", "sphgpu_derivs", "sphgpu_get_neighbour_stats", "sphgpu_neighbour_sets",
+    "sphgpu_measure_fp64_peak", "sphgpu_measure_copy_bw",
+]
+
+
+class SphGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sphgpu error {code} ({ERRORS.get(code, '?')}): {msg}")
+        self.code = code
+
+
+class HostArrays(C.Structure):
+    _fields_ = [("npart", C.c_int64)] + [(k, C.c_void_p) for k in (
+        "xyzh", "vxyzu", "fxyzu", "fext", "Bevol", "dBevol", "eos_vars", "divcurlv", "divcurlB", "alphaind", "gradh", "dvdx",
+        "poten", "divBsymm", "iphase", "ibin", "ibin_old", "ibin_wake")]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; raises (never falls back) if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C phantom_b200/csrc); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+        L.sphgpu_create.argtypes = [C.POINTER(SphParams), i32, C.POINTER(vp)]
+        L.sphgpu_destroy.argtypes = [vp]
+        L.sphgpu_destroy.restype = None
+        L.sphgpu_set_params.argtypes = [vp, C.POINTER(SphParams)]
+        L.sphgpu_last_error.argtypes = [vp]
+        L.sphgpu_last_error.restype = C.c_char_p
+        L.sphgpu_set_option.argtypes = [vp, C.c_char_p, dbl]
+        L.sphgpu_get_timings.argtypes = [vp, C.POINTER(dbl)]
+        L.sphgpu_launch_count.argtypes = [vp]
+        L.sphgpu_launch_count.restype = i64
+        L.sphgpu_upload.argtypes = [vp, C.POINTER(HostArrays), C.c_uint64]
+        L.sphgpu_download.argtypes = [vp, C.POINTER(HostArrays), C.c_uint64]
+        L.sphgpu_build_tree_resident.argtypes = [vp]
+        L.sphgpu_densityiterate_resident.argtypes = [vp, i32, C.POINTER(SphScalars)]
+        L.sphgpu_cons2prim_resident.argtypes = [vp]
+        L.sphgpu_force_resident.argtypes = [vp, i32, dbl, C.POINTER(SphScalars)]
+        L.sphgpu_derivs_resident.argtypes = [vp, i32, dbl, C.POINTER(SphScalars)]
+        L.sphgpu_build_tree.argtypes = [vp, i64, i64, vp, vp, vp]
+        L.sphgpu_densityiterate.argtypes = [vp, i32, i64, i64, vp, vp, vp, vp, vp, C.POINTER(dbl), vp, vp, vp, vp, vp, vp, C.POINTER(SphScalars)]
+        L.sphgpu_cons2prim_everything.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.sphgpu_force.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp, vp, vp, vp, vp, C.POINTER(SphScalars)]
+        L.sphgpu_derivs.argtypes = [vp, i32, C.POINTER(HostArrays), dbl, C.POINTER(SphScalars)]
+        L.sphgpu_get_neighbour_stats.argtypes = [vp, C.POINTER(SphScalars)]
+        L.sphgpu_neighbour_sets.argtypes = [vp, i32, vp, vp, i64]
+        L.sphgpu_neighbour_sets.restype = i64
+        L.sphgpu_measure_fp64_peak.argtypes = [vp]
+        L.sphgpu_measure_fp64_peak.restype = dbl
+        L.sphgpu_measure_copy_bw.argtypes = [vp]
+        L.sphgpu_measure_copy_bw.restype = dbl
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def host_arrays(part):
+    h = HostArrays()
+    h.npart = part.npart
+    for name, _ in HostArrays._fields_[1:]:
+        arr = getattr(part, name, None)
+        setattr(h, name, None if arr is None else arr.ctypes.data)
+    return h
+
+
+class SphGpu:
+    """One context = one GPU (one process per GPU under torchrun)."""
+
+    def __init__(self, params, device=0):
+        self.L = load_library()
+        self.params = params
+        h = C.c_void_p()
+        rc = self.L.sphgpu_create(C.byref(params), device, C.byref(h))
+        if rc != 0:
+            raise SphGpuError(rc, "sphgpu_create failed (no CUDA device? there is no CPU fallback)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sphgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SphGpuError(rc, self.L.sphgpu_last_error(self.h).decode())
+
+    def set_params(self, params):
+        self.params = params
+        self._check(self.L.sphgpu_set_params(self.h, C.byref(params)))
+
+    def set_option(self, name, value):
+        self._check(self.L.sphgpu_set_option(self.h, name.encode(), float(value)))
+
+    # ---- literal mode: the reference's argument lists ------------------------------------------------
+    def build_tree(self, part):
+        self._check(self.L.sphgpu_build_tree(self.h, part.npart, part.npart, _p(part.xyzh), _p(part.vxyzu), _p(part.iphase)))
+
+    def densityiterate(self, part, icall=1):
+        sc = SphScalars()
+        stressmax = C.c_double(0.)
+        self._check(self.L.sphgpu_densityiterate(
+            self.h, icall, part.npart, part.npart, _p(part.xyzh), _p(part.vxyzu), _p(part.divcurlv), _p(part.divcurlB), _p(part.Bevol),
+            C.byref(stressmax), _p(part.fxyzu), _p(part.fext), _p(part.alphaind), _p(part.gradh), _p(part.dvdx), _p(part.iphase), C.byref(sc)))
+        return sc
+
+    def cons2prim_everything(self, part):
+        self._check(self.L.sphgpu_cons2prim_everything(
+            self.h, part.npart, _p(part.xyzh), _p(part.vxyzu), _p(part.dvdx), _p(part.eos_vars), _p(part.Bevol), _p(part.Bxyz),
+            _p(part.alphaind), _p(part.iphase)))
+
+    def force(self, part, icall=1, dt=0.0):
+        sc = SphScalars()
+        self._check(self.L.sphgpu_force(
+            self.h, icall, part.npart, _p(part.xyzh), _p(part.vxyzu), _p(part.fxyzu), _p(part.divcurlv), _p(part.divcurlB), _p(part.Bevol),
+            _p(part.dBevol), _p(part.fext), dt, 0.0, _p(part.eos_vars), _p(part.alphaind), _p(part.gradh), _p(part.dvdx), _p(part.iphase),
+            _p(part.poten), _p(part.divBsymm), C.byref(sc)))
+        return sc
+
+    def derivs(self, part, icall=1, dt=0.0):
+        """derivs(icall,...) with host arrays in and out (deriv.f90:37)."""
+        sc = SphScalars()
+        h = host_arrays(part)
+        self._check(self.L.sphgpu_derivs(self.h, icall, C.byref(h), dt, C.byref(sc)))
+        return sc
+
+    def derivs_by_phase(self, part):
+        """the four literal calls in the order of deriv.f90:113-192; returns (density scalars, force scalars)"""
+        self.build_tree(part)
+        sd = self.densityiterate(part, 1)
+        self.params.set_boundaries_to_active = 0
+        self.set_params(self.params)
+        self.cons2prim_everything(part)
+        sf = self.force(part, 1)
+        return sd, sf
+
+    # ---- resident mode ----------------------------------------------------------------------------------
+    def upload(self, part, mask=F_ALL):
+        h = host_arrays(part)
+        self._check(self.L.sphgpu_upload(self.h, C.byref(h), mask))
+
+    def download(self, part, mask=F_ALL):
+        h = host_arrays(part)
+        self._check(self.L.sphgpu_download(self.h, C.byref(h), mask))
+
+    def derivs_resident(self, icall=1, dt=0.0):
+        sc = SphScalars()
+        self._check(self.L.sphgpu_derivs_resident(self.h, icall, dt, C.byref(sc)))
+        return sc
+
+    def build_tree_resident(self):
+        self._check(self.L.sphgpu_build_tree_resident(self.h))
+
+    def densityiterate_resident(self, icall=1):
+        sc = SphScalars()
+        self._check(self.L.sphgpu_densityiterate_resident(self.h, icall, C.byref(sc)))
+        return sc
+
+    def cons2prim_resident(self):
+        self._check(self.L.sphgpu_cons2prim_resident(self.h))
+
+    def force_resident(self, icall=1, dt=0.0):
+        sc = SphScalars()
+        self._check(self.L.sphgpu_force_resident(self.h, icall, dt, C.byref(sc)))
+        return sc
+
+    def timings_ms(self):
+        t = (C.c_double * 4)()
+        self.L.sphgpu_get_timings(self.h, t)
+        return dict(tree=t[0], dens=t[1], cons2prim=t[2], force=t[3])
+
+    def launch_count(self):
+        return self.L.sphgpu_launch_count(self.h)
+
+    def neighbour_sets(self, npart, symmetric=False):
+        off = np.zeros(npart + 1, dtype=np.int64)
+        cap = 200 * npart
+        lst = np.zeros(cap, dtype=np.int32)
+        tot = self.L.sphgpu_neighbour_sets(self.h, int(symmetric), _p(off), _p(lst), cap)
+        if tot < -1:
+            cap = -tot
+            lst = np.zeros(cap, dtype=np.int32)
+            tot = self.L.sphgpu_neighbour_sets(self.h, int(symmetric), _p(off), _p(lst), cap)
+        if tot < 0:
+            raise SphGpuError(7, self.L.sphgpu_last_error(self.h).decode())
+        return off, lst[:tot]
+
+    def measure_fp64_peak(self):
+        return self.L.sphgpu_measure_fp64_peak(self.h)
+
+    def measure_copy_bw(self):
+        return self.L.sphgpu_measure_copy_bw(self.h)

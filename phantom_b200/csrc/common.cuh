@@ -1,0 +1,203 @@
+// common.cuh -- context, device buffers and small device helpers shared by the kernels of the
+// SPH hot path.  Hand-written for sm_100a; no fallback path exists.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/sphgpu.h"
+
+#define FULLMASK 0xffffffffu
+
+// particle types (src/main/part.F90:428-438)
+enum { IGAS = 1, IBOUNDARY = 3, IDUST = 7 };
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// kernel constants (kernel_cubic.f90:23-30, kernel_quintic.f90:23-30)
+struct KernConsts { double radkern, radkern2, cnormk, wab0, gradh0, dphidh0, cnormk_drag; };
+
+// parameters as seen by device code
+struct DevParams {
+    sphgpu_params p;
+    KernConsts kc;
+    double dxbound, dybound, dzbound;
+    int nvu, ngradh, nalpha;
+};
+
+// tree node of the cell hierarchy (binary radix tree over leaf cells).  Children boxes are stored in the parent
+// so that one 128-byte read tests both children.
+struct __align__(16) TreeNode {
+    double lo[2][3];   // child bbox min
+    double hi[2][3];   // child bbox max
+    double hmax[2];    // child max smoothing length
+    int child[2];      // >= 0: internal node id ; < 0: ~cell id
+    int parent;
+    int pad;
+};
+
+struct Cell {          // leaf cell = run of <= max_cell Morton-consecutive particles
+    double lo[3], hi[3];
+    double hmax;
+    int start, count;
+    int active;        // number of active particles
+    int parent;        // internal node owning this leaf
+};
+
+struct sphgpu_ctx {
+    int device = 0;
+    std::string err;
+    DevParams hp;              // host copy
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8];
+    int numSMs = 148;
+    int64_t launches = 0;
+    double ms_phase[4] = {0, 0, 0, 0};
+    // tuning
+    int max_cell = 16;
+    double list_margin = 1.02;
+    int scratch_per_warp = 8192;
+    // ---- canonical (original particle order) device arrays = device mirror of part.F90 ----
+    int64_t npart = 0;
+    DevBuf<double> xyzh, vxyzu, fxyzu, fext, Bevol, dBevol, eos_vars, Bxyz;
+    DevBuf<float> divcurlv, divcurlB, alphaind, gradh, dvdx, poten, divBsymm;
+    DevBuf<int8_t> iphase, ibin, ibin_old, ibin_wake;
+    // ---- sorted working set ----
+    int64_t nlive = 0;
+    bool tree_valid = false, dens_valid = false;
+    DevBuf<unsigned long long> keys, keys_alt;
+    DevBuf<int> perm, perm_alt;            // sorted slot -> original index
+    DevBuf<double4> pos4;                   // x,y,z,h   (sorted)
+    DevBuf<double4> vel4, acc4, bev4;       // density inputs (sorted)
+    DevBuf<int8_t> stype;                   // iphase (sorted)
+    DevBuf<double> hnew;                    // density output h (sorted)
+    DevBuf<double4> frecC, frecD, frecE;    // force j-side records (sorted)
+    DevBuf<float> s_gradh, s_divv, s_dvdx, s_alpha3, s_divcurlB;   // sorted density outputs
+    DevBuf<double4> s_fxyzu, s_dB;          // sorted force outputs
+    DevBuf<float> s_divvf, s_poten, s_divBsymm;
+    DevBuf<int> s_nneigh;
+    // tree
+    int64_t ncells = 0;
+    DevBuf<unsigned char> cpl;
+    DevBuf<int> cellflag, cellid_scan;
+    DevBuf<Cell> cells;
+    DevBuf<unsigned long long> cellkeys;
+    DevBuf<TreeNode> nodes;
+    DevBuf<int> nodeflag;
+    DevBuf<char> cubtemp;
+    DevBuf<int> scratch;                    // per-warp candidate lists
+    DevBuf<unsigned long long> counters;    // device scalars block
+    DevBuf<double> dscal;                   // device double scalars (bbox, dt minima, ...)
+    sphgpu_scalars last_dens{}, last_force{};
+};
+
+#define CUDA_TRY(ctx, call)                                                                           \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                         \
+            return SPHGPU_ERR_CUDA;                                                                   \
+        }                                                                                             \
+    } while (0)
+
+#define TRY(call)                       \
+    do {                                \
+        int r__ = (call);               \
+        if (r__ != SPHGPU_OK) return r__; \
+    } while (0)
+
+// ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// rho(h) = m (hfact/h)^3 (part.F90:779)
+__device__ __forceinline__ double rhoh_d(double hi, double pmassi, double hfact)
+{
+    double r = hfact / fabs(hi);
+    return pmassi * (r * r * r);
+}
+
+// decode iphase (part.F90:1026-1067), gas + boundary + one dust type
+__device__ __forceinline__ void get_partinfo_d(int8_t iphasei, int set_boundaries_to_active, int use_dust, bool &isactive, bool &isgas,
+                                               bool &isdust, int &itype)
+{
+    if (iphasei >= 0) { isactive = true; itype = iphasei; }
+    else { isactive = false; itype = -iphasei; }
+    isgas = (itype == IGAS || itype == IBOUNDARY);
+    isdust = use_dust ? (itype == IDUST) : false;
+    if (itype == IBOUNDARY) {
+        if (set_boundaries_to_active) { isactive = true; itype = IGAS; }
+        else isactive = false;
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(FULLMASK, v, s);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v = fmax(v, __shfl_xor_sync(FULLMASK, v, s));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v = fmin(v, __shfl_xor_sync(FULLMASK, v, s));
+    return v;
+}
+
+// butterfly "transpose" reduction of 32 per-lane partial sums: on return lane L holds sum over lanes of v[L].
+// 31 shuffles instead of 32*5.
+__device__ __forceinline__ double warp_transpose_reduce32(double (&v)[32])
+{
+    const int lane = lane_id();
+#pragma unroll
+    for (int s = 16, cnt = 32; s >= 1; s >>= 1, cnt >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int k = 0; k < cnt / 2; k++) {
+            const double send = upper ? v[k] : v[k + cnt / 2];
+            const double keep = upper ? v[k + cnt / 2] : v[k];
+            v[k] = keep + __shfl_xor_sync(FULLMASK, send, s);
+        }
+    }
+    return v[0];
+}
+
+// atomic min/max on non-negative doubles through their ordered bit patterns
+__device__ __forceinline__ void atomic_min_pos(double *addr, double v) { atomicMin((unsigned long long *)addr, (unsigned long long)__double_as_longlong(v)); }
+__device__ __forceinline__ void atomic_max_pos(double *addr, double v) { atomicMax((unsigned long long *)addr, (unsigned long long)__double_as_longlong(v)); }
+
+// indices into ctx->counters (unsigned long long)
+enum { CNT_WORK = 0, CNT_ERR, CNT_ERRID, CNT_NPAIRS, CNT_NTRIAL, CNT_NCALC, CNT_NACT, CNT_MAXACT, CNT_MAXTRIAL, CNT_NP, CNT_NWALK, CNT_NLIVE, CNT_NBINMAX, CNT_NCHECKBIN,
+       CNT_COUNT = 32 };
+// indices into ctx->dscal (double)
+enum { DS_XMIN = 0, DS_YMIN, DS_ZMIN, DS_XMAX, DS_YMAX, DS_ZMAX, DS_DTCOURANT, DS_DTFORCE, DS_DTMINI, DS_DTMAXI, DS_RHOMAX, DS_COUNT = 32 };
+
+// internal API between translation units
+int tree_build(sphgpu_ctx *c);
+int tree_refit_hmax(sphgpu_ctx *c);
+int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out);
+int cons2prim_run(sphgpu_ctx *c);
+int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out);
+int64_t neighbour_sets_run(sphgpu_ctx *c, int symmetric, int64_t *offsets, int32_t *list, int64_t maxlist);
+KernConsts make_kern_consts(int kernel);

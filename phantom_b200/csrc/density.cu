@@ -1,0 +1,441 @@
+// density.cu -- density pass with the h-rho Newton-Raphson iteration: replaces densityiterate
+// (src/main/dens.F90:117-568) with get_density_sums (:578-857), finish_cell/finish_rhosum (:1382-1507),
+// compute_hmax (:1275-1289) and store_results (:1511-1681).
+//
+// Mapping to the hardware: a persistent grid of warps pulls leaf cells from an atomic work counter; per cell the
+// warp walks the tree once (walk.cuh) and then iterates every active particle of the cell to convergence.  Lanes
+// run over *neighbour candidates*; accepted pairs are compacted so that the ~90-flop FP64 pair body runs with
+// full warps; the 28 (+10 MHD) per-particle sums live in registers as per-lane partials and are combined
+// with a 31-shuffle transpose reduction.  The kernel is FP64-pipe bound.
+//
+// Semantics kept from the reference: self term added analytically (dens.F90:1491-1492), neighbours of the same
+// (base) type only (:717-723), iteration per particle with clamp to +-20% and the tolh/omega test (:1425-1440),
+// final h = hrho(rho) (:1595), real*4 rounding of gradh before it is reused in `term` (:1601,:1610,:1631),
+// exact-linear gradients (:866-967), maxdensits = 100 (:101).
+// Deliberate difference: divcurlB uses h_j as it was at the START of the pass for every neighbour; the reference
+// reads xyzh(4,j) while other threads update it (fast_divcurlB race, config.F90:215-217), so its own result is
+// thread-order dependent.
+#include "walk.cuh"
+#include "sphkern.cuh"
+#include <float.h>
+
+namespace {
+
+struct DensArgs {
+    const TreeNode *nodes; const Cell *cells; int ncells;
+    const double4 *pos4, *vel4, *acc4, *bev4; const int8_t *stype; const int *perm;
+    double *hnew; float *s_gradh, *s_divv, *s_dvdx, *s_alpha3, *s_divcurlB; int *s_nneigh;
+    int *scratch; int scratch_per_warp; unsigned long long *cnt; double *dscal;
+    double margin; int icall;
+};
+
+enum {  // slots of the per-lane partial sums (order of dens.F90:51-95)
+    S_RHO = 0, S_GRADH, S_GRADSOFT, S_DIVV, S_DVXDX, S_DVXDY, S_DVXDZ, S_DVYDX, S_DVYDY, S_DVYDZ, S_DVZDX, S_DVZDY, S_DVZDZ,
+    S_DAXDX, S_DAXDY, S_DAXDZ, S_DAYDX, S_DAYDY, S_DAYDZ, S_DAZDX, S_DAZDY, S_DAZDZ, S_RXX, S_RXY, S_RXZ, S_RYY, S_RYZ, S_RZZ, S_RHODUST
+};
+#define MAXCELL 16     // leaf cells hold at most 16 particles (ctx->max_cell is clamped to this)
+#define FINROW 49      // odd row length: lane-per-target reads are bank-conflict free
+enum { F_H = 42, F_NN = 43, F_S = 44 };
+enum { B_DIVB = 0, B_DBXDX, B_DBXDY, B_DBXDZ, B_DBYDX, B_DBYDY, B_DBYDZ, B_DBZDX, B_DBZDY, B_DBZDZ };
+
+__global__ void k_gather_dens(int64_t nlive, const int *__restrict__ perm, const double *__restrict__ vxyzu, const double *__restrict__ fxyzu,
+                              const double *__restrict__ fext, const double *__restrict__ Bevol, int nvu, int mhd, const double4 *__restrict__ pos4,
+                              double4 *__restrict__ vel4, double4 *__restrict__ acc4, double4 *__restrict__ bev4, double *__restrict__ hnew,
+                              int *__restrict__ s_nneigh)
+{
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nlive) return;
+    const int i = perm[s];
+    const double *v = vxyzu + (size_t)nvu * i, *f = fxyzu + (size_t)nvu * i, *fe = fext + 3 * (size_t)i;
+    vel4[s] = make_double4(v[0], v[1], v[2], nvu >= 4 ? v[3] : 0.);
+    acc4[s] = make_double4(f[0] + fe[0], f[1] + fe[1], f[2] + fe[2], 0.);     // dens.F90:1353-1355
+    if (mhd) bev4[s] = reinterpret_cast<const double4 *>(Bevol)[i];
+    hnew[s] = pos4[s].w;
+    s_nneigh[s] = -1;
+}
+
+__global__ void k_scatter_dens(int64_t nlive, const int *__restrict__ perm, const int *__restrict__ s_nneigh, const double *__restrict__ hnew,
+                               double4 *__restrict__ pos4, double *__restrict__ xyzh, const float *__restrict__ s_gradh, const float *__restrict__ s_divv,
+                               const float *__restrict__ s_dvdx, const float *__restrict__ s_alpha3, const float *__restrict__ s_divcurlB,
+                               float *__restrict__ gradh, float *__restrict__ divcurlv, float *__restrict__ dvdx, float *__restrict__ alphaind,
+                               float *__restrict__ divcurlB, int ngradh, int nalpha, int mhd)
+{
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nlive) return;
+    if (s_nneigh[s] < 0) return;     // not an active target: keep stored values (test_derivs.f90:233-238)
+    const int i = perm[s];
+    const double h = hnew[s];
+    pos4[s].w = h;                                       // treecache(4,:) refresh (dens.F90:1596)
+    xyzh[4 * (size_t)i + 3] = h;
+    for (int k = 0; k < ngradh; k++) gradh[(size_t)ngradh * i + k] = s_gradh[(size_t)ngradh * s + k];
+    divcurlv[i] = s_divv[s];
+#pragma unroll
+    for (int k = 0; k < 9; k++) dvdx[9 * (size_t)i + k] = s_dvdx[9 * (size_t)s + k];
+    if (nalpha >= 3) alphaind[3 * (size_t)i + 2] = s_alpha3[s];
+    if (mhd) for (int k = 0; k < 4; k++) divcurlB[4 * (size_t)i + k] = s_divcurlB[4 * (size_t)s + k];
+}
+
+template <int K, bool MHD, bool GRAV>
+__device__ __forceinline__ void dens_pair(double (&v)[32], double (&w)[16], int &nneighi, int j, double dx, double dy, double dz, double r2,
+                                          double hi, double hi1, double hi21, int itypei, bool gasi, const double4 &vi, const double4 &ai,
+                                          const double4 &bi, const DensArgs &a, const DevParams &dp, bool use_da)
+{
+    typedef SphKern<K> KF;
+    const double q2i = r2 * hi21;
+    const double rij = sqrt(r2);
+    const double qi = rij * hi1;
+    double wabi, grkerni;
+    KF::get_kernel(q2i, qi, wabi, grkerni);
+    const int itypej = abs((int)a.stype[j]);
+    const int basej = (itypej == IBOUNDARY) ? IGAS : itypej;
+    const bool same_type = (itypei == itypej) || (basej == itypei);
+    const double pmassj = dp.p.massoftype[itypej];
+    if (same_type) {
+        const bool gas_gas = gasi;
+        const double dwdhi = (-qi * grkerni - 3. * wabi);
+        v[S_RHO] += wabi * pmassj;
+        v[S_GRADH] += dwdhi * pmassj;
+        if (GRAV) v[S_GRADSOFT] += KF::dphidh(q2i, qi) * pmassj;
+        nneighi++;
+        const double rij1 = 1. / (rij + DBL_EPSILON);
+        const double rij1grkern = rij1 * grkerni;
+        const double runix = dx * rij1grkern * pmassj, runiy = dy * rij1grkern * pmassj, runiz = dz * rij1grkern * pmassj;
+        const double4 vj = a.vel4[j];
+        const double dvx = vi.x - vj.x, dvy = vi.y - vj.y, dvz = vi.z - vj.z;
+        v[S_DIVV] += dvx * runix + dvy * runiy + dvz * runiz;
+        v[S_DVXDX] += dvx * runix; v[S_DVXDY] += dvx * runiy; v[S_DVXDZ] += dvx * runiz;
+        v[S_DVYDX] += dvy * runix; v[S_DVYDY] += dvy * runiy; v[S_DVYDZ] += dvy * runiz;
+        v[S_DVZDX] += dvz * runix; v[S_DVZDY] += dvz * runiy; v[S_DVZDZ] += dvz * runiz;
+        if (use_da && gas_gas) {
+            const double4 aj = a.acc4[j];
+            const double dax = ai.x - aj.x, day = ai.y - aj.y, daz = ai.z - aj.z;
+            v[S_DAXDX] += dax * runix; v[S_DAXDY] += dax * runiy; v[S_DAXDZ] += dax * runiz;
+            v[S_DAYDX] += day * runix; v[S_DAYDY] += day * runiy; v[S_DAYDZ] += day * runiz;
+            v[S_DAZDX] += daz * runix; v[S_DAZDY] += daz * runiy; v[S_DAZDZ] += daz * runiz;
+        }
+        v[S_RXX] -= dx * runix; v[S_RXY] -= dx * runiy; v[S_RXZ] -= dx * runiz;
+        v[S_RYY] -= dy * runiy; v[S_RYZ] -= dy * runiz; v[S_RZZ] -= dz * runiz;
+        if (MHD && gas_gas) {
+            const double pmassi = dp.p.massoftype[itypei];
+            const double rhoi = rhoh_d(hi, pmassi, dp.p.hfact);
+            const double rhoj = rhoh_d(a.pos4[j].w, pmassj, dp.p.hfact);
+            const double4 bj = a.bev4[j];
+            const double dBx = bi.x * rhoi - bj.x * rhoj, dBy = bi.y * rhoi - bj.y * rhoj, dBz = bi.z * rhoi - bj.z * rhoj;
+            w[B_DIVB] += dBx * runix + dBy * runiy + dBz * runiz;
+            w[B_DBXDX] += dBx * runix; w[B_DBXDY] += dBx * runiy; w[B_DBXDZ] += dBx * runiz;
+            w[B_DBYDX] += dBy * runix; w[B_DBYDY] += dBy * runiy; w[B_DBYDZ] += dBy * runiz;
+            w[B_DBZDX] += dBz * runix; w[B_DBZDY] += dBz * runiy; w[B_DBZDZ] += dBz * runiz;
+        }
+    } else if (dp.p.dust && gasi && itypej == IDUST) {
+        v[S_RHODUST] += wabi;
+    }
+}
+
+__device__ __forceinline__ void exactlinear_d(double &gx, double &gy, double &gz, double dAx, double dAy, double dAz, const double *rm, double ddenom)
+{
+    gx = (dAx * rm[0] + dAy * rm[1] + dAz * rm[2]) * ddenom;
+    gy = (dAx * rm[1] + dAy * rm[3] + dAz * rm[4]) * ddenom;
+    gz = (dAx * rm[2] + dAy * rm[4] + dAz * rm[5]) * ddenom;
+}
+
+template <int K, bool PERIODIC, bool MHD, bool GRAV>
+__global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_constant__ DevParams dp)
+{
+    typedef SphKern<K> KF;
+    __shared__ WarpShared wsh[4];
+    __shared__ double finbuf[4][MAXCELL][FINROW];    // per-target totals, finalised lane-parallel once the cell is done
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    WarpShared &ws = wsh[wib];
+    double (*fin)[FINROW] = finbuf[wib];
+    const int gwarp = blockIdx.x * 4 + wib;
+    int *list = a.scratch + (size_t)gwarp * a.scratch_per_warp;
+    const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
+    const double radkern = KF::radkern, radkern2 = KF::radkern2;
+    const bool use_da = dp.nalpha > 1;
+    const unsigned lt_mask = (1u << lane) - 1;
+    // per-warp statistics (dens.F90:104-106)
+    unsigned long long st_pairs = 0, st_trial = 0, st_ncalc = 0, st_nact = 0, st_np = 0, st_nwalk = 0;
+    int st_maxact = 0, st_maxtrial = 0;
+    double st_rhomax = 0.;
+
+    while (true) {
+        int cellid = 0;
+        if (lane == 0) cellid = (int)atomicAdd(&a.cnt[CNT_WORK], 1ull);
+        cellid = __shfl_sync(FULLMASK, cellid, 0);
+        if (cellid >= a.ncells) break;
+        const Cell cell = a.cells[cellid];
+        if (cell.active == 0) continue;                              // dens.F90:302
+        double hmax_list = cell.hmax * a.margin;
+        double rcut_list = radkern * hmax_list;
+        int nlist = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, cell.lo, cell.hi, rcut_list, radkern, Lx, Ly, Lz, list, a.scratch_per_warp, ws.stack);
+        st_nwalk++;
+        if (nlist < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+
+        int ntar = 0;
+        for (int t = 0; t < cell.count; t++) {
+            const int s = cell.start + t;
+            bool act, gasi, dusti; int itypei;
+            get_partinfo_d(a.stype[s], dp.p.set_boundaries_to_active, dp.p.dust, act, gasi, dusti, itypei);
+            if (!act) continue;                                      // dens.F90:1329
+            const double4 pi = a.pos4[s];
+            const double4 vi = a.vel4[s], ai = a.acc4[s];
+            double4 bi = make_double4(0., 0., 0., 0.);
+            if (MHD && gasi) bi = a.bev4[s];
+            const double pmassi = dp.p.massoftype[itypei];
+            double h = pi.w;
+            const double h_old = h;
+            int its = 0;
+            double v[32], w[16];
+            int nneighi = 0;
+            double rhoi = 0., gradh_sum = 0.;
+            bool failed = false;
+            while (true) {
+                its++;
+                if (radkern * h > rcut_list) {                       // compute_hmax / redo_neighbours (dens.F90:1275-1289, :343-347)
+                    hmax_list = h * a.margin * 1.01;
+                    rcut_list = radkern * hmax_list;
+                    nlist = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, cell.lo, cell.hi, rcut_list, radkern, Lx, Ly, Lz, list,
+                                                       a.scratch_per_warp, ws.stack);
+                    st_nwalk++;
+                    if (nlist < 0) { failed = true; if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+                }
+#pragma unroll
+                for (int k = 0; k < 32; k++) v[k] = 0.;
+#pragma unroll
+                for (int k = 0; k < 16; k++) w[k] = 0.;
+                nneighi = 0;
+                const double hi1 = 1. / h, hi21 = hi1 * hi1;
+                int qhead = 0, qcount = 0;
+                for (int c0 = 0; c0 < nlist; c0 += 32) {
+                    const int idx = c0 + lane;
+                    bool pass = false;
+                    int j = 0;
+                    double dx = 0., dy = 0., dz = 0., r2 = 0.;
+                    if (idx < nlist) {
+                        j = list[idx];
+                        const double4 pj = a.pos4[j];
+                        r2 = pair_r2<PERIODIC>(pi.x, pi.y, pi.z, pj, Lx, Ly, Lz, dx, dy, dz);
+                        const double q2i = __dmul_rn(r2, hi21);                       // dens.F90:675
+                        pass = (q2i < radkern2) && (j != s);                          // :679, :650
+                    }
+                    const unsigned m = __ballot_sync(FULLMASK, pass);
+                    if (pass) {
+                        const int pos = (qhead + qcount + __popc(m & lt_mask)) & (QRING - 1);
+                        ws.qj[pos] = j; ws.qdx[pos] = dx; ws.qdy[pos] = dy; ws.qdz[pos] = dz; ws.qr2[pos] = r2;
+                    }
+                    qcount += __popc(m);
+                    __syncwarp();
+                    if (qcount >= 32) {
+                        const int e = (qhead + lane) & (QRING - 1);
+                        dens_pair<K, MHD, GRAV>(v, w, nneighi, ws.qj[e], ws.qdx[e], ws.qdy[e], ws.qdz[e], ws.qr2[e], h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp,
+                                                use_da);
+                        qhead = (qhead + 32) & (QRING - 1);
+                        qcount -= 32;
+                        __syncwarp();
+                    }
+                }
+                if (lane < qcount) {
+                    const int e = (qhead + lane) & (QRING - 1);
+                    dens_pair<K, MHD, GRAV>(v, w, nneighi, ws.qj[e], ws.qdx[e], ws.qdy[e], ws.qdz[e], ws.qr2[e], h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp, use_da);
+                }
+                __syncwarp();
+                st_trial += (unsigned long long)nlist;
+                // finish_rhosum + finish_cell (dens.F90:1470-1507, :1401-1462)
+                const double rho_sum = warp_sum(v[S_RHO]);
+                gradh_sum = warp_sum(v[S_GRADH]);
+                const double hi31 = hi1 * hi21, hi41 = hi21 * hi21;
+                rhoi = KF::cnormk * (rho_sum + KF::wab0 * pmassi) * hi31;
+                const double gradhi = KF::cnormk * (gradh_sum + KF::gradh0 * pmassi) * hi41;
+                const double rhohi = rhoh_d(h, pmassi, dp.p.hfact);
+                const double dhdrhoi = -h / (3. * rhohi);
+                const double omegai = 1. - dhdrhoi * gradhi;
+                const double func = rhohi - rhoi;
+                double dfdh1;
+                if (omegai > DBL_MIN) dfdh1 = dhdrhoi / omegai;
+                else dfdh1 = dhdrhoi / fabs(omegai + DBL_EPSILON);
+                double hnew = h - func * dfdh1;
+                if (hnew > 1.2 * h) hnew = 1.2 * h;
+                else if (hnew < 0.8 * h) hnew = 0.8 * h;
+                bool converged = ((fabs(hnew - h) / h_old) < dp.p.tolh) && (omegai > 0.) && (h > 0.);
+                if (a.icall == 0) converged = true;
+                if (converged) break;
+                if (its >= 100) {                                   // maxdensits, dens.F90:1443-1456
+                    if (lane == 0) { atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_NOCONVERGE); atomicMax(&a.cnt[CNT_ERRID], (unsigned long long)(a.perm[s] + 1)); }
+                    failed = true;
+                    break;
+                }
+                h = hnew;
+            }
+            if (failed) continue;
+            // ---- totals of this particle -> shared memory; store_results runs lane-parallel after the target loop ----
+            int nn = nneighi;
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) nn += __shfl_xor_sync(FULLMASK, nn, sft);
+            st_pairs += (unsigned long long)nn * its;
+            nn += 1;   // self
+            const double tot = warp_transpose_reduce<32>(v);
+            fin[ntar][lane] = tot;
+            if (MHD) { const double tb = warp_transpose_reduce<16>(w); if ((lane & 1) == 0) fin[ntar][32 + (lane >> 1)] = tb; }
+            if (lane == 0) { fin[ntar][F_H] = h; fin[ntar][F_NN] = (double)nn; fin[ntar][F_S] = (double)s; }
+            ntar++;
+            __syncwarp();
+            st_ncalc += its; st_nact += nn; st_np += 1;
+            st_maxact = max(st_maxact, nn); st_maxtrial = max(st_maxtrial, nlist);
+        }
+        __syncwarp();
+        // ---- store_results (dens.F90:1511-1681), one lane per target ----
+        if (lane < ntar) {
+            const double *rs = fin[lane];
+            const double h = rs[F_H];
+            const int s = (int)rs[F_S];
+            bool act, gasi, dusti; int itypei;
+            get_partinfo_d(a.stype[s], dp.p.set_boundaries_to_active, dp.p.dust, act, gasi, dusti, itypei);
+            const double pmassi = dp.p.massoftype[itypei];
+            const double hi1 = 1. / h, hi21 = hi1 * hi1, hi31 = hi1 * hi21, hi41 = hi21 * hi21;
+            const double rho = KF::cnormk * (rs[S_RHO] + KF::wab0 * pmassi) * hi31;
+            double gradhi = KF::cnormk * (rs[S_GRADH] + KF::gradh0 * pmassi) * hi41;
+            const double rhohi = rhoh_d(h, pmassi, dp.p.hfact);
+            const double dhdrhoi = -h / (3. * rhohi);
+            const double omegai = 1. - dhdrhoi * gradhi;
+            gradhi = 1. / omegai;
+            a.hnew[s] = dp.p.hfact * pow(pmassi / fabs(rho), 1.0 / 3.0);            // hrho, part.F90:845
+            const float gradh4 = (float)gradhi;
+            a.s_gradh[(size_t)dp.ngradh * s] = gradh4;
+            if (GRAV) {
+                double gradsofti = (rs[S_GRADSOFT] + KF::dphidh0 * pmassi) * hi21;
+                gradsofti = gradsofti * dhdrhoi;
+                a.s_gradh[(size_t)dp.ngradh * s + 1] = (float)gradsofti;
+            }
+            gradhi = (double)gradh4;                                                  // dens.F90:1610
+            const double rho1i = 1. / rho;
+            const double term = KF::cnormk * gradhi * rho1i * hi41;
+            const double rxx = rs[S_RXX], rxy = rs[S_RXY], rxz = rs[S_RXZ], ryy = rs[S_RYY], ryz = rs[S_RYZ], rzz = rs[S_RZZ];
+            const double denom = rxx * ryy * rzz + 2. * rxy * rxz * ryz - rxx * ryz * ryz - ryy * rxz * rxz - rzz * rxy * rxy;
+            double rm[6];
+            rm[0] = ryy * rzz - ryz * ryz; rm[1] = rxz * ryz - rzz * rxy; rm[2] = rxy * ryz - rxz * ryy;
+            rm[3] = rzz * rxx - rxz * rxz; rm[4] = rxy * rxz - rxx * ryz; rm[5] = rxx * ryy - rxy * rxy;
+            const double divv = -rs[S_DIVV] * term;
+            double dv[9], divcurlv5 = 0.;
+            if (fabs(denom) > DBL_MIN) {
+                const double ddenom = 1. / denom;
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    double gx, gy, gz;
+                    exactlinear_d(gx, gy, gz, rs[S_DVXDX + 3 * r], rs[S_DVXDX + 3 * r + 1], rs[S_DVXDX + 3 * r + 2], rm, ddenom);
+                    dv[3 * r] = -gx; dv[3 * r + 1] = -gy; dv[3 * r + 2] = -gz;
+                }
+                if (use_da) {
+                    double ax, ay, az, bx, by, bz, cx, cy, cz;
+                    exactlinear_d(ax, ay, az, rs[S_DAXDX], rs[S_DAXDY], rs[S_DAXDZ], rm, ddenom);
+                    exactlinear_d(bx, by, bz, rs[S_DAYDX], rs[S_DAYDY], rs[S_DAYDZ], rm, ddenom);
+                    exactlinear_d(cx, cy, cz, rs[S_DAZDX], rs[S_DAZDY], rs[S_DAZDZ], rm, ddenom);
+                    const double div_a = -(ax + by + cz);
+                    divcurlv5 = div_a - (dv[0] * dv[0] + dv[4] * dv[4] + dv[8] * dv[8] + 2. * (dv[1] * dv[3] + dv[2] * dv[6] + dv[5] * dv[7]));
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 9; k++) dv[k] = -term * rs[S_DVXDX + k];
+                if (use_da) {
+                    const double div_a = -term * (rs[S_DAXDX] + rs[S_DAYDY] + rs[S_DAZDZ]);
+                    divcurlv5 = div_a - (dv[0] * dv[0] + dv[4] * dv[4] + dv[8] * dv[8] + 2. * (dv[1] * dv[3] + dv[2] * dv[6] + dv[5] * dv[7]));
+                }
+            }
+            a.s_divv[s] = (float)divv;
+            a.s_alpha3[s] = (float)divcurlv5;
+#pragma unroll
+            for (int k = 0; k < 9; k++) a.s_dvdx[9 * (size_t)s + k] = (float)dv[k];
+            if (MHD) {
+                const double *rb = rs + 32;
+                float *o = a.s_divcurlB + 4 * (size_t)s;
+                if (gasi) {
+                    o[0] = (float)(-rb[B_DIVB] * term);
+                    o[1] = (float)(-(rb[B_DBZDY] - rb[B_DBYDZ]) * term);
+                    o[2] = (float)(-(rb[B_DBXDZ] - rb[B_DBZDX]) * term);
+                    o[3] = (float)(-(rb[B_DBYDX] - rb[B_DBXDY]) * term);
+                } else { o[0] = o[1] = o[2] = o[3] = 0.f; }
+            }
+            a.s_nneigh[s] = (int)rs[F_NN];
+            st_rhomax = fmax(st_rhomax, rho);
+        }
+        __syncwarp();
+    }
+    st_rhomax = warp_max(st_rhomax);
+    if (lane == 0) {
+        atomicAdd(&a.cnt[CNT_NPAIRS], st_pairs); atomicAdd(&a.cnt[CNT_NTRIAL], st_trial); atomicAdd(&a.cnt[CNT_NCALC], st_ncalc);
+        atomicAdd(&a.cnt[CNT_NACT], st_nact); atomicAdd(&a.cnt[CNT_NP], st_np); atomicAdd(&a.cnt[CNT_NWALK], st_nwalk);
+        atomicMax(&a.cnt[CNT_MAXACT], (unsigned long long)st_maxact); atomicMax(&a.cnt[CNT_MAXTRIAL], (unsigned long long)st_maxtrial);
+        atomic_max_pos(&a.dscal[DS_RHOMAX], st_rhomax);
+    }
+}
+
+template <int K, bool PERIODIC, bool MHD, bool GRAV>
+void launch_density(sphgpu_ctx *c, const DensArgs &a, int grid)
+{
+    k_density<K, PERIODIC, MHD, GRAV><<<grid, 128, 0, c->stream>>>(a, c->hp);
+    c->launches++;
+}
+
+template <int K, bool PERIODIC>
+void dispatch_density2(sphgpu_ctx *c, const DensArgs &a, int grid)
+{
+    const bool mhd = c->hp.p.mhd, grav = c->hp.p.gravity;
+    if (mhd && grav) launch_density<K, PERIODIC, true, true>(c, a, grid);
+    else if (mhd) launch_density<K, PERIODIC, true, false>(c, a, grid);
+    else if (grav) launch_density<K, PERIODIC, false, true>(c, a, grid);
+    else launch_density<K, PERIODIC, false, false>(c, a, grid);
+}
+
+}  // namespace
+
+static inline int nblk(int64_t n, int b) { return (int)((n + b - 1) / b); }
+
+int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
+{
+    if (!c->tree_valid) { c->err = "densityiterate: build_tree has not been called"; return SPHGPU_ERR_STATE; }
+    const int64_t n = c->npart, nl = c->nlive;
+    const sphgpu_params &p = c->hp.p;
+    CUDA_TRY(c, c->vel4.ensure(n)); CUDA_TRY(c, c->acc4.ensure(n)); if (p.mhd) CUDA_TRY(c, c->bev4.ensure(n));
+    CUDA_TRY(c, c->hnew.ensure(n)); CUDA_TRY(c, c->s_gradh.ensure(n * c->hp.ngradh)); CUDA_TRY(c, c->s_divv.ensure(n));
+    CUDA_TRY(c, c->s_dvdx.ensure(9 * n)); CUDA_TRY(c, c->s_alpha3.ensure(n)); CUDA_TRY(c, c->s_divcurlB.ensure(4 * n)); CUDA_TRY(c, c->s_nneigh.ensure(n));
+    const int grid = c->numSMs * 3;          // persistent: 3 CTAs/SM fit (164-226 regs x 128 threads, 40 KB smem)
+    CUDA_TRY(c, c->scratch.ensure((size_t)grid * 4 * c->scratch_per_warp));
+    k_gather_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->vxyzu.p, c->fxyzu.p, c->fext.p, c->Bevol.p, c->hp.nvu, p.mhd, c->pos4.p, c->vel4.p,
+                                                        c->acc4.p, c->bev4.p, c->hnew.p, c->s_nneigh.p);
+    c->launches++;
+    CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->dscal.p + DS_RHOMAX, 0, sizeof(double), c->stream));
+    DensArgs a;
+    a.nodes = c->nodes.p; a.cells = c->cells.p; a.ncells = (int)c->ncells;
+    a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.acc4 = c->acc4.p; a.bev4 = c->bev4.p; a.stype = c->stype.p; a.perm = c->perm.p;
+    a.hnew = c->hnew.p; a.s_gradh = c->s_gradh.p; a.s_divv = c->s_divv.p; a.s_dvdx = c->s_dvdx.p; a.s_alpha3 = c->s_alpha3.p;
+    a.s_divcurlB = c->s_divcurlB.p; a.s_nneigh = c->s_nneigh.p;
+    a.scratch = c->scratch.p; a.scratch_per_warp = c->scratch_per_warp; a.cnt = c->counters.p; a.dscal = c->dscal.p;
+    a.margin = c->list_margin; a.icall = icall;
+    if (p.kernel == 0) { if (p.periodic) dispatch_density2<0, true>(c, a, grid); else dispatch_density2<0, false>(c, a, grid); }
+    else { if (p.periodic) dispatch_density2<1, true>(c, a, grid); else dispatch_density2<1, false>(c, a, grid); }
+    k_scatter_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->hnew.p, c->pos4.p, c->xyzh.p, c->s_gradh.p, c->s_divv.p, c->s_dvdx.p,
+                                                         c->s_alpha3.p, c->s_divcurlB.p, c->gradh.p, c->divcurlv.p, c->dvdx.p, c->alphaind.p, c->divcurlB.p,
+                                                         c->hp.ngradh, c->hp.nalpha, p.mhd);
+    c->launches++;
+    TRY(tree_refit_hmax(c));          // set_hmaxcell (neigh_kdtree.f90:115-131): the force walk needs the new hmax
+    unsigned long long hc[16]; double hrhomax;
+    CUDA_TRY(c, cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(&hrhomax, c->dscal.p + DS_RHOMAX, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    if (hc[CNT_ERR] == SPHGPU_ERR_NOCONVERGE) {
+        char buf[160]; snprintf(buf, sizeof buf, "densityiterate: could not converge in density on particle %llu", hc[CNT_ERRID]);
+        c->err = buf; return SPHGPU_ERR_NOCONVERGE;
+    }
+    if (hc[CNT_ERR]) { c->err = "densityiterate: neighbour scratch overflow (raise scratch_per_warp)"; return (int)hc[CNT_ERR]; }
+    sphgpu_scalars &sc = c->last_dens;
+    memset(&sc, 0, sizeof sc);
+    sc.rhomax = hrhomax; sc.np = (int64_t)hc[CNT_NP];
+    sc.trialmean = sc.np ? (double)hc[CNT_NTRIAL] / (double)hc[CNT_NCALC] : -1.;
+    sc.actualmean = sc.np ? (double)hc[CNT_NACT] / (double)sc.np : -1.;
+    sc.maxtrial = (int64_t)hc[CNT_MAXTRIAL]; sc.maxactual = (int64_t)hc[CNT_MAXACT]; sc.nrhocalc = (int64_t)hc[CNT_NCALC];
+    sc.nactualtot = (int64_t)hc[CNT_NACT]; sc.ncalls_neigh = (int64_t)hc[CNT_NWALK]; sc.npairs_density = (int64_t)hc[CNT_NPAIRS];
+    if (out) *out = sc;
+    c->dens_valid = true;
+    return SPHGPU_OK;
+}

@@ -1,0 +1,429 @@
+// force.cu -- force pass: replaces force (src/main/force.F90:193-905) with start_cell/get_stress (:2172-2514, :2068-2168),
+// compute_forces (:914-2060) and finish_cell_and_store_results (:2649-3330), for hydro + artificial viscosity
+// (Cullen-Dehnen alpha per particle or constant, optional disc viscosity) + artificial conductivity + ideal MHD with
+// artificial resistivity and hyperbolic/parabolic div-B cleaning.
+//
+// Same warp-per-leaf-cell skeleton as the density pass (walk.cuh) with the symmetric neighbour criterion
+// q2i < R^2 .or. q2j < R^2 (force.F90:1287).  What the reference recomputes per pair for particle j
+// (rho_j, get_stress -> P_j/rho_j^2, v_wave,j, the gradW prefactor h_j^-4 cnormk gradh_j: force.F90:1455-1504, :1327)
+// is computed once per particle by k_force_prep into 32-byte records so that a pair costs four sector gathers.
+#include "walk.cuh"
+#include "sphkern.cuh"
+#include <float.h>
+
+namespace {
+
+struct ForceArgs {
+    const TreeNode *nodes; const Cell *cells; int ncells;
+    const double4 *pos4, *vel4, *recC, *recD, *recE; const double2 *hinv; const int8_t *stype; const int *perm;
+    double4 *s_fxyzu, *s_dB; float *s_divvf, *s_divBsymm; int *s_done;
+    int *scratch; int scratch_per_warp; unsigned long long *cnt; double *dscal;
+    int icall;
+};
+
+enum { A_FX = 0, A_FY, A_FZ, A_DRHODT, A_DUDTDISS, A_DENDTDISS, A_DIVBSYM, A_DBX, A_DBY, A_DBZ, A_DIVBDIFF, A_POT };
+#define MAXCELL 16
+#define FROW 21
+enum { G_VSIG = 16, G_S = 17 };
+
+// one thread per sorted particle: the per-particle part of start_cell + get_stress
+__global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const double4 *__restrict__ pos4, const int8_t *__restrict__ stype,
+                             const double *__restrict__ vxyzu, const double *__restrict__ Bevol, const double *__restrict__ eos_vars,
+                             const float *__restrict__ alphaind, const float *__restrict__ gradh, double4 *__restrict__ vel4, double4 *__restrict__ recC,
+                             double4 *__restrict__ recD, double4 *__restrict__ recE, double2 *__restrict__ hinv, int *__restrict__ s_done,
+                             const __grid_constant__ DevParams dp, unsigned long long *cnt)
+{
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nlive) return;
+    const sphgpu_params &p = dp.p;
+    const int i = perm[s];
+    const double h = pos4[s].w;
+    bool act, gas, dust; int itype;
+    get_partinfo_d(stype[s], p.set_boundaries_to_active, p.dust, act, gas, dust, itype);
+    const int itypej = abs((int)stype[s]);                       // neighbours are looked up by raw type (force.F90:1363)
+    const double pmass = p.massoftype[itypej];
+    if (h < 0.) { atomicMax(&cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_NEGH); atomicMax(&cnt[CNT_ERRID], (unsigned long long)(i + 1)); }
+    const double h1 = 1. / fabs(h);                              // rhoanddhdrho (part.F90:805-817)
+    const double h21 = h1 * h1;
+    const double hf = p.hfact * h1;
+    const double rho = pmass * (hf * hf * hf);
+    const double rho1 = 1. / rho;
+    const double *v = vxyzu + (size_t)dp.nvu * i;
+    vel4[s] = make_double4(v[0], v[1], v[2], dp.nvu >= 4 ? v[3] : 0.);
+    hinv[s] = make_double2(h1, h21);
+    double pro2 = 0., vwave = 0., alpha = 0., pr = 0., cs = 0., gradhfac = 0.;
+    double4 E = make_double4(0., 0., 0., 0.);
+    const double gh = (double)gradh[(size_t)dp.ngradh * i];
+    gradhfac = h21 * h21 * dp.kc.cnormk * (gh > 0. ? gh : 1.);   // force.F90:2616-2621 resets a zero gradh to 1
+    if (gas) {
+        pr = eos_vars[7 * (size_t)i]; cs = eos_vars[7 * (size_t)i + 1];
+        alpha = p.const_av ? p.alpha : (double)alphaind[3 * (size_t)i];
+        if (p.mhd) {                                             // get_stress (force.F90:2132-2155)
+            const double4 B = reinterpret_cast<const double4 *>(Bevol)[i];
+            E = make_double4(B.x * rho, B.y * rho, B.z * rho, B.w);
+            const double bx = E.x * rho1, by = E.y * rho1, bz = E.z * rho1;
+            const double Bro2 = bx * bx + by * by + bz * bz;
+            vwave = sqrt(cs * cs + Bro2 * rho);
+            pro2 = pr * rho1 * rho1 + 0.5 * Bro2;
+        } else { pro2 = pr * rho1 * rho1; vwave = cs; }
+    }
+    recC[s] = make_double4(pro2, vwave, alpha, pr);
+    recD[s] = make_double4(rho1, gradhfac, pmass, cs);
+    if (p.mhd) recE[s] = E;
+    s_done[s] = 0;
+}
+
+template <int K, bool MHD>
+__device__ __forceinline__ void force_pair(double (&f)[16], double &vsigmax, int j, double dx, double dy, double dz, double r2, double hi, double hi1,
+                                           double hi21, bool gasi, const double4 &vi, const double4 &Ci, const double4 &Di, const double4 &Ei,
+                                           const ForceArgs &a, const DevParams &dp)
+{
+    typedef SphKern<K> KF;
+    const sphgpu_params &p = dp.p;
+    const double2 hj = a.hinv[j];
+    const double hj1 = hj.x, hj21 = hj.y;
+    const double q2i = r2 * hi21, q2j = r2 * hj21;
+    double rij1, rij;
+    if (r2 > DBL_MIN) { rij1 = 1. / sqrt(r2); rij = r2 * rij1; } else { rij1 = 0.; rij = 0.; }   // force.F90:1293-1299
+    const double qi = rij * hi1;
+    const double4 Cj = a.recC[j], Dj = a.recD[j];
+    const double4 vj = a.vel4[j];
+    const int itypej = abs((int)a.stype[j]);
+    const bool gasj = (itypej == IGAS || itypej == IBOUNDARY);
+    const double pmassj = Dj.z, pmassi = Di.z;
+    const double grkerni = (q2i < KF::radkern2) ? KF::grkern(q2i, qi) * Di.y : 0.;
+    double grkernj = 0.;
+    bool usej = false;
+    if (q2j < KF::radkern2) { const double qj = rij * hj1; grkernj = KF::grkern(q2j, qj) * Dj.y; usej = true; }
+    if (MHD) usej = true;
+    if (p.dust) usej = true;
+    if (dp.nvu >= 4 && !p.gravity) usej = true;                  // force.F90:1343-1345
+    const double runix = dx * rij1, runiy = dy * rij1, runiz = dz * rij1;
+    const double dvx = vi.x - vj.x, dvy = vi.y - vj.y, dvz = vi.z - vj.z;
+    const double projv = dvx * runix + dvy * runiy + dvz * runiz;
+    if (!(gasi && gasj)) {                                       // force.F90:1446-1452, :1852-1859 (no gravity, no drag here)
+        vsigmax = fmax(vsigmax, fmax(-projv, 0.));
+        return;
+    }
+    const double rho1i = Di.x, rho1j = usej ? Dj.x : 0.;
+    const double vwavei = Ci.y, alphai = Ci.z, pri = Ci.w, pro2i = Ci.x;
+    const double beta = p.beta;
+    const double vsigi = fmax(vwavei - beta * projv, 0.);
+    const double vsigavi = fmax(alphai * vwavei - beta * projv, 0.);
+    vsigmax = fmax(vsigmax, vsigi);
+    double vwavej = 0., vsigavj = 0., pro2j = 0., prj = 0., alphaj = alphai;
+    if (usej) {
+        vwavej = Cj.y; pro2j = Cj.x; prj = Cj.w;
+        if (!p.const_av) alphaj = Cj.z;
+        const double vsigj = fmax(vwavej - beta * projv, 0.);
+        vsigavj = fmax(alphaj * vwavej - beta * projv, 0.);
+        vsigmax = fmax(vsigmax, vsigj);
+    }
+    double qrho2i = 0., qrho2j = 0., dudtdissi;
+    if (p.disc_viscosity) {                                      // force.F90:1555-1579
+        const double hjv = 1. / hj1, csi = Di.w, csj = Dj.w;
+        if (projv < 0.) {
+            qrho2i = -0.5 * rho1i * (alphai * csi - beta * projv) * hi * rij1 * projv;
+            if (usej) qrho2j = -0.5 * rho1j * (alphaj * csj - beta * projv) * hjv * rij1 * projv;
+        } else {
+            qrho2i = -0.5 * rho1i * alphai * csi * hi * rij1 * projv;
+            if (usej) qrho2j = -0.5 * rho1j * alphaj * csj * hjv * rij1 * projv;
+        }
+        dudtdissi = -0.5 * pmassj * rho1i * alphai * csi * hi * rij1 * (projv * projv) * grkerni;
+    } else {
+        if (projv < 0.) {                                        // force.F90:1581-1592
+            qrho2i = -0.5 * rho1i * vsigavi * projv;
+            if (usej) qrho2j = -0.5 * rho1j * vsigavj * projv;
+        }
+        dudtdissi = pmassj * qrho2i * projv * grkerni;
+    }
+    const double gradpi = pmassj * (pro2i + qrho2i) * grkerni;
+    const double gradpj = usej ? pmassj * (pro2j + qrho2j) * grkernj : 0.;
+    double projsx = 0., projsy = 0., projsz = 0.;
+    double dudtresist = 0.;
+    if (dp.nvu >= 4) {                                           // artificial conductivity, force.F90:1606-1624
+        const double denij = vi.w - vj.w;
+        double vsigu;
+        if (p.gravity) vsigu = fabs(projv);
+        else { const double rhoi = 1. / rho1i, rhoj = 1. / Dj.x; vsigu = sqrt(fabs(pri - prj) * (2. / (rhoi + rhoj))); }
+        const double auterm = 0.5 * pmassi * rho1i * p.alphau, autermj = usej ? 0.5 * pmassj * rho1j * p.alphau : 0.;
+        f[A_DENDTDISS] += vsigu * denij * (auterm * grkerni + autermj * grkernj);
+    }
+    if (MHD) {                                                   // force.F90:1428-1444, :1626-1672, :2132-2150
+        const double4 Ej = a.recE[j];
+        const double Bxi = Ei.x, Byi = Ei.y, Bzi = Ei.z, psii = Ei.w;
+        const double Bxj = Ej.x, Byj = Ej.y, Bzj = Ej.z, psij = Ej.w;
+        const double dBx = Bxi - Bxj, dBy = Byi - Byj, dBz = Bzi - Bzj;
+        const double projBi = Bxi * runix + Byi * runiy + Bzi * runiz;
+        const double projBj = Bxj * runix + Byj * runiy + Bzj * runiz;
+        const double projdB = dBx * runix + dBy * runiy + dBz * runiz;
+        const double dB2 = dBx * dBx + dBy * dBy + dBz * dBz;
+        f[A_DIVBDIFF] += -pmassj * projdB * grkerni;
+        const double rho21i = rho1i * rho1i, rho21j = rho1j * rho1j;
+        const double avBterm = 0.5 * pmassi * rho1i * p.alphaB * rho1i, avBtermj = 0.5 * pmassj * rho1j * p.alphaB * rho1j;
+        const double tx = dvx - projv * runix, ty = dvy - projv * runiy, tz = dvz - projv * runiz;
+        const double vsigB = sqrt(tx * tx + ty * ty + tz * tz);
+        const double dBdissterm = (avBterm * grkerni + avBtermj * grkernj) * vsigB;
+        if (p.iresistive_heating > 0) dudtresist = -0.5 * dB2 * dBdissterm;
+        const double pmjrho21grkerni = pmassj * rho21i * grkerni, pmjrho21grkernj = pmassj * rho21j * grkernj;
+        const double termi = pmjrho21grkerni * projBi;
+        f[A_DIVBSYM] += termi + pmjrho21grkernj * projBj;
+        const double dBrhoterm = -termi;
+        const double dpsiterm = p.overcleanfac * (pmjrho21grkerni * psii * vwavei + pmjrho21grkernj * psij * vwavej);
+        f[A_DBX] += dBrhoterm * dvx + dBdissterm * dBx - dpsiterm * runix;
+        f[A_DBY] += dBrhoterm * dvy + dBdissterm * dBy - dpsiterm * runiy;
+        f[A_DBZ] += dBrhoterm * dvz + dBdissterm * dBz - dpsiterm * runiz;
+        // anisotropic Maxwell stress S_ab = -m B_a B_b / rho^2 projected on the pair direction (force.F90:1677-1684)
+        const double si = -pmassi * rho21i * projBi * grkerni, sj = -pmassj * rho21j * projBj * grkernj;
+        projsx = si * Bxi + sj * Bxj; projsy = si * Byi + sj * Byj; projsz = si * Bzi + sj * Bzj;
+    }
+    const double gradp = gradpi + gradpj;
+    f[A_FX] += -runix * gradp - projsx;
+    f[A_FY] += -runiy * gradp - projsy;
+    f[A_FZ] += -runiz * gradp - projsz;
+    f[A_DRHODT] += projv * grkerni;
+    if (dp.nvu >= 4) f[A_DUDTDISS] += dudtdissi + dudtresist;
+}
+
+template <int K, bool PERIODIC, bool MHD>
+__global__ void __launch_bounds__(128) k_force(const ForceArgs a, const __grid_constant__ DevParams dp)
+{
+    typedef SphKern<K> KF;
+    __shared__ WarpShared wsh[4];
+    __shared__ double finbuf[4][MAXCELL][FROW];
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    WarpShared &ws = wsh[wib];
+    double (*fin)[FROW] = finbuf[wib];
+    const int gwarp = blockIdx.x * 4 + wib;
+    int *list = a.scratch + (size_t)gwarp * a.scratch_per_warp;
+    const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
+    const unsigned lt_mask = (1u << lane) - 1;
+    const sphgpu_params &p = dp.p;
+    unsigned long long st_pairs = 0, st_trial = 0;
+    double st_dtc = 1.e29, st_dtf = 1.e29, st_dtmin = 1.e29, st_dtmax = 0.;
+
+    while (true) {
+        int cellid = 0;
+        if (lane == 0) cellid = (int)atomicAdd(&a.cnt[CNT_WORK], 1ull);
+        cellid = __shfl_sync(FULLMASK, cellid, 0);
+        if (cellid >= a.ncells) break;
+        const Cell cell = a.cells[cellid];
+        if (cell.active == 0) continue;                              // force.F90:509
+        const double rcut = KF::radkern * cell.hmax;
+        const int nlist = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, cell.lo, cell.hi, rcut, KF::radkern, Lx, Ly, Lz, list, a.scratch_per_warp, ws.stack);
+        if (nlist < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+        int ntar = 0;
+        for (int t = 0; t < cell.count; t++) {
+            const int s = cell.start + t;
+            bool act, gasi, dusti; int itypei;
+            get_partinfo_d(a.stype[s], p.set_boundaries_to_active, p.dust, act, gasi, dusti, itypei);
+            if (!act) continue;                                      // force.F90:2255
+            const double4 pi = a.pos4[s], vi = a.vel4[s], Ci = a.recC[s], Di = a.recD[s];
+            double4 Ei = make_double4(0., 0., 0., 0.);
+            if (MHD) Ei = a.recE[s];
+            const double h = pi.w;
+            const double2 hv = a.hinv[s];
+            const double hi1 = hv.x, hi21 = hv.y;
+            double f[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) f[k] = 0.;
+            double vsigmax = 0.;
+            int npair = 0;
+            int qhead = 0, qcount = 0;
+            for (int c0 = 0; c0 < nlist; c0 += 32) {
+                const int idx = c0 + lane;
+                bool pass = false;
+                int j = 0;
+                double dx = 0., dy = 0., dz = 0., r2 = 0.;
+                if (idx < nlist) {
+                    j = list[idx];
+                    const double4 pj = a.pos4[j];
+                    r2 = pair_r2<PERIODIC>(pi.x, pi.y, pi.z, pj, Lx, Ly, Lz, dx, dy, dz);
+                    const double q2i = __dmul_rn(r2, hi21), q2j = __dmul_rn(r2, a.hinv[j].y);      // force.F90:1272, :1285
+                    pass = (q2i < KF::radkern2 || q2j < KF::radkern2) && (j != s);                 // :1287, :1230
+                }
+                const unsigned m = __ballot_sync(FULLMASK, pass);
+                if (pass) {
+                    const int pos = (qhead + qcount + __popc(m & lt_mask)) & (QRING - 1);
+                    ws.qj[pos] = j; ws.qdx[pos] = dx; ws.qdy[pos] = dy; ws.qdz[pos] = dz; ws.qr2[pos] = r2;
+                }
+                qcount += __popc(m);
+                npair += __popc(m);
+                __syncwarp();
+                if (qcount >= 32) {
+                    const int e = (qhead + lane) & (QRING - 1);
+                    force_pair<K, MHD>(f, vsigmax, ws.qj[e], ws.qdx[e], ws.qdy[e], ws.qdz[e], ws.qr2[e], h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp);
+                    qhead = (qhead + 32) & (QRING - 1);
+                    qcount -= 32;
+                    __syncwarp();
+                }
+            }
+            if (lane < qcount) {
+                const int e = (qhead + lane) & (QRING - 1);
+                force_pair<K, MHD>(f, vsigmax, ws.qj[e], ws.qdx[e], ws.qdy[e], ws.qdz[e], ws.qr2[e], h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp);
+            }
+            __syncwarp();
+            st_pairs += npair; st_trial += nlist;
+            vsigmax = warp_max(vsigmax);
+            const double tot = warp_transpose_reduce<16>(f);         // lane L holds slot L>>1
+            if ((lane & 1) == 0) fin[ntar][lane >> 1] = tot;
+            if (lane == 0) { fin[ntar][G_VSIG] = vsigmax; fin[ntar][G_S] = (double)s; }
+            ntar++;
+            __syncwarp();
+        }
+        __syncwarp();
+        // ---- finish_cell_and_store_results (force.F90:2649-3330), one lane per target ----
+        if (lane < ntar) {
+            const double *fs = fin[lane];
+            const int s = (int)fs[G_S];
+            bool act, gasi, dusti; int itypei;
+            get_partinfo_d(a.stype[s], p.set_boundaries_to_active, p.dust, act, gasi, dusti, itypei);
+            const double4 pi = a.pos4[s], vi = a.vel4[s], Ci = a.recC[s], Di = a.recD[s];
+            const double hi = pi.w, hi1 = a.hinv[s].x, pmassi = Di.z;
+            double fx = fs[A_FX], fy = fs[A_FY], fz = fs[A_FZ];
+            const double vsigmax = fs[G_VSIG];
+            double dtc = p.dtmax, dtf = 1.e29, dtclean = 1.e29;
+            double fxyz4 = 0., divvi = 0.;
+            double4 dB = make_double4(0., 0., 0., 0.);
+            float divBsymm4 = 0.f;
+            if (gasi) {
+                const double rho1i = Di.x, rhoi = 1. / rho1i, pri = Ci.w, vwavei = Ci.y;
+                if (MHD) {                                           // force.F90:2939-2965
+                    const double4 Ei = a.recE[s];
+                    const double B2i = Ei.x * Ei.x + Ei.y * Ei.y + Ei.z * Ei.z;
+                    const double divBsymmi = fs[A_DIVBSYM];
+                    double frac_divB = 0.;
+                    if (B2i > 0.0) {
+                        const double betai = 2.0 * pri / B2i;
+                        if (betai < 2.0) frac_divB = 1.0;
+                        else if (betai < 10.0) frac_divB = (10.0 - betai) * 0.125;
+                    }
+                    fx -= Ei.x * divBsymmi * frac_divB; fy -= Ei.y * divBsymmi * frac_divB; fz -= Ei.z * divBsymmi * frac_divB;
+                    divBsymm4 = (float)(rhoi * divBsymmi);
+                }
+                const double drhodti = pmassi * fs[A_DRHODT];
+                divvi = -drhodti * rho1i;
+                if (dp.nvu >= 4) {                                   // force.F90:3024-3095 (ien_type = energy, fac = rho/rhogas = 1)
+                    const double pdv_work = pri * rho1i * rho1i * drhodti;
+                    if (p.ipdv_heating > 0) fxyz4 += pdv_work;
+                    if (p.ishock_heating > 0) fxyz4 += fs[A_DUDTDISS];
+                    fxyz4 += fs[A_DENDTDISS];
+                }
+                if (MHD) {                                           // force.F90:3103-3125
+                    dB.x = fs[A_DBX]; dB.y = fs[A_DBY]; dB.z = fs[A_DBZ];
+                    if (p.psidecayfac > 0.) {
+                        const double vcleani = p.overcleanfac * vwavei;
+                        const double dtau = p.psidecayfac * vcleani * hi1;
+                        const double psii = a.recE[s].w;
+                        dB.w = -vcleani * fs[A_DIVBDIFF] * rho1i - psii * dtau - 0.5 * psii * divvi;
+                        dtclean = p.C_cour * hi / (vcleani + DBL_MIN);
+                    }
+                }
+                const double vsigdtc = fmax(vsigmax, vwavei);
+                if (vsigdtc > DBL_MIN) dtc = p.C_cour * hi / (vsigdtc * fmax(p.alpha, 1.0));     // force.F90:3138-3141
+                if (dp.nvu >= 4) {
+                    const double eni = vi.w;
+                    if (eni + dtc * fxyz4 < DBL_EPSILON && eni > DBL_EPSILON) fxyz4 = fxyz4 / (1. - dtc * fxyz4 / eni);   // :3144-3148
+                }
+            } else {
+                if (vsigmax > DBL_MIN) dtc = p.C_cour * hi / vsigmax;
+            }
+            const double f2i = fx * fx + fy * fy + fz * fz;
+            if (fabs(f2i) > DBL_EPSILON) dtf = p.C_force * sqrt(hi / sqrt(f2i));                 // force.F90:3217-3219
+            a.s_fxyzu[s] = make_double4(fx, fy, fz, fxyz4);
+            a.s_divvf[s] = (float)divvi;
+            if (MHD) { a.s_dB[s] = dB; a.s_divBsymm[s] = divBsymm4; }
+            a.s_done[s] = gasi ? 2 : 1;
+            st_dtc = fmin(st_dtc, dtc);
+            st_dtf = fmin(st_dtf, fmin(dtf, dtclean));
+            st_dtmin = fmin(st_dtmin, dtc); st_dtmax = fmax(st_dtmax, dtc);
+        }
+        __syncwarp();
+    }
+    st_dtc = warp_min(st_dtc); st_dtf = warp_min(st_dtf); st_dtmin = warp_min(st_dtmin); st_dtmax = warp_max(st_dtmax);
+    if (lane == 0) {
+        atomicAdd(&a.cnt[CNT_NPAIRS], st_pairs); atomicAdd(&a.cnt[CNT_NTRIAL], st_trial);
+        atomic_min_pos(&a.dscal[DS_DTCOURANT], st_dtc); atomic_min_pos(&a.dscal[DS_DTFORCE], st_dtf);
+        atomic_min_pos(&a.dscal[DS_DTMINI], st_dtmin); atomic_max_pos(&a.dscal[DS_DTMAXI], st_dtmax);
+    }
+}
+
+__global__ void k_scatter_force(int64_t nlive, const int *__restrict__ perm, const int *__restrict__ s_done, const double4 *__restrict__ s_fxyzu,
+                                const double4 *__restrict__ s_dB, const float *__restrict__ s_divvf, const float *__restrict__ s_divBsymm,
+                                double *__restrict__ fxyzu, double *__restrict__ dBevol, float *__restrict__ divcurlv, float *__restrict__ divBsymm, int nvu,
+                                int mhd)
+{
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nlive) return;
+    const int d = s_done[s];
+    if (d == 0) return;
+    const int i = perm[s];
+    const double4 f = s_fxyzu[s];
+    double *fi = fxyzu + (size_t)nvu * i;
+    fi[0] = f.x; fi[1] = f.y; fi[2] = f.z;
+    if (d == 2) {
+        if (nvu >= 4) fi[3] = f.w;
+        divcurlv[i] = s_divvf[s];                                    // force.F90:2999
+        if (mhd) { reinterpret_cast<double4 *>(dBevol)[i] = s_dB[s]; divBsymm[i] = s_divBsymm[s]; }
+    }
+}
+
+template <int K, bool PERIODIC>
+void dispatch_force(sphgpu_ctx *c, const ForceArgs &a, int grid)
+{
+    if (c->hp.p.mhd) k_force<K, PERIODIC, true><<<grid, 128, 0, c->stream>>>(a, c->hp);
+    else k_force<K, PERIODIC, false><<<grid, 128, 0, c->stream>>>(a, c->hp);
+    c->launches++;
+}
+
+}  // namespace
+
+static inline int nblk(int64_t n, int b) { return (int)((n + b - 1) / b); }
+
+int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
+{
+    (void)dt;
+    if (!c->tree_valid) { c->err = "force: build_tree has not been called"; return SPHGPU_ERR_STATE; }
+    const int64_t n = c->npart, nl = c->nlive;
+    const sphgpu_params &p = c->hp.p;
+    if (p.gravity || p.dust || p.ind_timesteps) { c->err = "force: GRAVITY / DUST / IND_TIMESTEPS force terms are not built yet"; return SPHGPU_ERR_ARG; }
+    CUDA_TRY(c, c->vel4.ensure(n)); CUDA_TRY(c, c->frecC.ensure(n)); CUDA_TRY(c, c->frecD.ensure(n)); if (p.mhd) CUDA_TRY(c, c->frecE.ensure(n));
+    CUDA_TRY(c, c->hnew.ensure(2 * n));                                    // reused as double2 hinv
+    CUDA_TRY(c, c->s_fxyzu.ensure(n)); if (p.mhd) { CUDA_TRY(c, c->s_dB.ensure(n)); CUDA_TRY(c, c->s_divBsymm.ensure(n)); }
+    CUDA_TRY(c, c->s_divvf.ensure(n)); CUDA_TRY(c, c->s_nneigh.ensure(n));
+    const int grid = c->numSMs * 3;          // persistent grid, 3 CTAs/SM
+    CUDA_TRY(c, c->scratch.ensure((size_t)grid * 4 * c->scratch_per_warp));
+    CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
+    const double init[4] = {1.e29, 1.e29, 1.e29, 0.};
+    CUDA_TRY(c, cudaMemcpyAsync(c->dscal.p + DS_DTCOURANT, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    double2 *hinv = reinterpret_cast<double2 *>(c->hnew.p);
+    k_force_prep<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->pos4.p, c->stype.p, c->vxyzu.p, c->Bevol.p, c->eos_vars.p, c->alphaind.p, c->gradh.p,
+                                                       c->vel4.p, c->frecC.p, c->frecD.p, c->frecE.p, hinv, c->s_nneigh.p, c->hp, c->counters.p);
+    c->launches++;
+    ForceArgs a;
+    a.nodes = c->nodes.p; a.cells = c->cells.p; a.ncells = (int)c->ncells;
+    a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.recC = c->frecC.p; a.recD = c->frecD.p; a.recE = c->frecE.p; a.hinv = hinv; a.stype = c->stype.p; a.perm = c->perm.p;
+    a.s_fxyzu = c->s_fxyzu.p; a.s_dB = c->s_dB.p; a.s_divvf = c->s_divvf.p; a.s_divBsymm = c->s_divBsymm.p; a.s_done = c->s_nneigh.p;
+    a.scratch = c->scratch.p; a.scratch_per_warp = c->scratch_per_warp; a.cnt = c->counters.p; a.dscal = c->dscal.p; a.icall = icall;
+    if (p.kernel == 0) { if (p.periodic) dispatch_force<0, true>(c, a, grid); else dispatch_force<0, false>(c, a, grid); }
+    else { if (p.periodic) dispatch_force<1, true>(c, a, grid); else dispatch_force<1, false>(c, a, grid); }
+    k_scatter_force<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->s_fxyzu.p, c->s_dB.p, c->s_divvf.p, c->s_divBsymm.p, c->fxyzu.p,
+                                                          c->dBevol.p, c->divcurlv.p, c->divBsymm.p, c->hp.nvu, p.mhd);
+    c->launches++;
+    unsigned long long hc[16]; double hd[4];
+    CUDA_TRY(c, cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(hd, c->dscal.p + DS_DTCOURANT, sizeof(hd), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    if (hc[CNT_ERR] == SPHGPU_ERR_NEGH) {
+        char buf[128]; snprintf(buf, sizeof buf, "force: negative smoothing length on particle %llu", hc[CNT_ERRID]);
+        c->err = buf; return SPHGPU_ERR_NEGH;
+    }
+    if (hc[CNT_ERR]) { c->err = "force: neighbour scratch overflow (raise scratch_per_warp)"; return (int)hc[CNT_ERR]; }
+    sphgpu_scalars &sc = c->last_force;
+    memset(&sc, 0, sizeof sc);
+    sc.dtcourant = hd[0]; sc.dtforce = hd[1]; sc.dtmini = hd[2]; sc.dtmaxi = hd[3];
+    sc.npairs_force = (int64_t)hc[CNT_NPAIRS];
+    if (out) { sphgpu_scalars o = c->last_dens; o.dtcourant = sc.dtcourant; o.dtforce = sc.dtforce; o.dtmini = sc.dtmini; o.dtmaxi = sc.dtmaxi; o.npairs_force = sc.npairs_force; *out = o; }
+    return SPHGPU_OK;
+}

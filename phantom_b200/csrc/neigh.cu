@@ -1,0 +1,104 @@
+// neigh.cu -- exact neighbour sets of the current tree/h state in CSR form, for the bit-exact set parity tests
+// (the reference's own check is test_neigh.f90:264-367: tree neighbour counts == O(N^2) brute force).
+// Uses the same walk and the same non-contracted distance test as the density / force kernels.
+#include "walk.cuh"
+#include "sphkern.cuh"
+#include <cub/cub.cuh>
+#include <float.h>
+
+namespace {
+
+template <bool PERIODIC, bool SYM, bool FILL>
+__global__ void __launch_bounds__(128) k_neigh(const TreeNode *nodes, const Cell *cells, int ncells, const double4 *pos4, const int *perm, double radkern,
+                                               double Lx, double Ly, double Lz, int *scratch, int scratch_per_warp, unsigned long long *cnt,
+                                               int *counts, const long long *offsets, int *out)
+{
+    __shared__ WarpShared wsh[4];
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    WarpShared &ws = wsh[wib];
+    int *list = scratch + (size_t)(blockIdx.x * 4 + wib) * scratch_per_warp;
+    const double radkern2 = radkern * radkern;
+    const unsigned lt_mask = (1u << lane) - 1;
+    while (true) {
+        int cellid = 0;
+        if (lane == 0) cellid = (int)atomicAdd(&cnt[CNT_WORK], 1ull);
+        cellid = __shfl_sync(FULLMASK, cellid, 0);
+        if (cellid >= ncells) break;
+        const Cell cell = cells[cellid];
+        const int nlist = warp_walk<SYM, PERIODIC>(nodes, cells, ncells, cell.lo, cell.hi, radkern * cell.hmax, radkern, Lx, Ly, Lz, list, scratch_per_warp, ws.stack);
+        if (nlist < 0) { if (lane == 0) atomicMax(&cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+        for (int t = 0; t < cell.count; t++) {
+            const int s = cell.start + t;
+            const double4 pi = pos4[s];
+            const double hi1 = 1. / pi.w, hi21 = hi1 * hi1;
+            const int iorig = perm[s];
+            int n = 0;
+            for (int c0 = 0; c0 < nlist; c0 += 32) {
+                const int idx = c0 + lane;
+                bool pass = false; int j = 0;
+                if (idx < nlist) {
+                    j = list[idx];
+                    const double4 pj = pos4[j];
+                    double dx, dy, dz;
+                    const double r2 = pair_r2<PERIODIC>(pi.x, pi.y, pi.z, pj, Lx, Ly, Lz, dx, dy, dz);
+                    pass = __dmul_rn(r2, hi21) < radkern2;
+                    if (SYM) { const double hj1 = 1. / pj.w; pass = pass || (__dmul_rn(r2, hj1 * hj1) < radkern2); }
+                    pass = pass && (j != s);
+                }
+                const unsigned m = __ballot_sync(FULLMASK, pass);
+                if (FILL && pass) out[offsets[iorig] + n + __popc(m & lt_mask)] = perm[j] + 1;
+                n += __popc(m);
+            }
+            if (!FILL && lane == 0) counts[iorig] = n;
+        }
+    }
+}
+
+}  // namespace
+
+int64_t neighbour_sets_run(sphgpu_ctx *c, int symmetric, int64_t *offsets, int32_t *list, int64_t maxlist)
+{
+    if (!c->tree_valid) { c->err = "neighbour_sets: build_tree has not been called"; return -1; }
+    const int64_t n = c->npart;
+    const int grid = c->numSMs * 4;
+    if (c->scratch.ensure((size_t)grid * 4 * c->scratch_per_warp) != cudaSuccess) return -1;
+    DevBuf<int> counts; DevBuf<long long> offs; DevBuf<int> out; DevBuf<char> tmp;
+    if (counts.ensure(n + 1) != cudaSuccess || offs.ensure(n + 1) != cudaSuccess) return -1;
+    cudaMemsetAsync(counts.p, 0, sizeof(int) * (n + 1), c->stream);
+    cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream);
+    const double R = c->hp.kc.radkern, Lx = c->hp.dxbound, Ly = c->hp.dybound, Lz = c->hp.dzbound;
+    const bool per = c->hp.p.periodic;
+#define NEIGH_LAUNCH(FILLV)                                                                                                                       \
+    do {                                                                                                                                          \
+        if (per && symmetric) k_neigh<true, true, FILLV><<<grid, 128, 0, c->stream>>>(c->nodes.p, c->cells.p, (int)c->ncells, c->pos4.p, c->perm.p, R, Lx, Ly, Lz, c->scratch.p, c->scratch_per_warp, c->counters.p, counts.p, offs.p, out.p); \
+        else if (per) k_neigh<true, false, FILLV><<<grid, 128, 0, c->stream>>>(c->nodes.p, c->cells.p, (int)c->ncells, c->pos4.p, c->perm.p, R, Lx, Ly, Lz, c->scratch.p, c->scratch_per_warp, c->counters.p, counts.p, offs.p, out.p); \
+        else if (symmetric) k_neigh<false, true, FILLV><<<grid, 128, 0, c->stream>>>(c->nodes.p, c->cells.p, (int)c->ncells, c->pos4.p, c->perm.p, R, Lx, Ly, Lz, c->scratch.p, c->scratch_per_warp, c->counters.p, counts.p, offs.p, out.p); \
+        else k_neigh<false, false, FILLV><<<grid, 128, 0, c->stream>>>(c->nodes.p, c->cells.p, (int)c->ncells, c->pos4.p, c->perm.p, R, Lx, Ly, Lz, c->scratch.p, c->scratch_per_warp, c->counters.p, counts.p, offs.p, out.p); \
+        c->launches++;                                                                                                                            \
+    } while (0)
+    NEIGH_LAUNCH(false);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.p, offs.p, (int)(n + 1), c->stream);
+    tmp.ensure(tb);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, counts.p, offs.p, (int)(n + 1), c->stream);
+    long long total = 0;
+    cudaMemcpyAsync(&total, offs.p + n, sizeof(long long), cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    int64_t ret = total;
+    if (total > maxlist) ret = -total;
+    else {
+        out.ensure(total + 1);
+        cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream);
+        NEIGH_LAUNCH(true);
+        cudaMemcpyAsync(list, out.p, sizeof(int) * total, cudaMemcpyDeviceToHost, c->stream);
+        std::vector<long long> ho(n + 1);
+        cudaMemcpyAsync(ho.data(), offs.p, sizeof(long long) * (n + 1), cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+        for (int64_t i = 0; i <= n; i++) offsets[i] = ho[i];
+    }
+    unsigned long long err = 0;
+    cudaMemcpy(&err, c->counters.p + CNT_ERR, sizeof err, cudaMemcpyDeviceToHost);
+    counts.release(); offs.release(); out.release(); tmp.release();
+    if (cudaGetLastError() != cudaSuccess || err) { c->err = "neighbour_sets: kernel failure or scratch overflow"; return -1; }
+    return ret;
+}

@@ -1,0 +1,336 @@
+// tree.cu -- GPU spatial tree for neighbour finding: replaces maketree (src/main/kdtree.F90:117-314).
+//
+// B200-first design, not the reference's top-down COM-split kd-tree:
+//   1. 63-bit Morton keys (21 bits/axis, cubic normalisation) + cub radix sort      [HBM-bound, ~24 B/particle/pass]
+//   2. leaf cells = maximal octree nodes holding <= max_cell particles, found from the common-prefix
+//      lengths of adjacent sorted keys inside a +-max_cell window (no pointer structure needed)
+//   3. binary radix tree (Karras 2012) over the cell keys, one thread per internal node
+//   4. bottom-up refit of child boxes + hmax with one atomic flag per node
+// The tree shape differs from the reference's; what must agree (and is tested) are the neighbour *sets*.
+// Periodic wrap and the NaN check of construct_root_node (kdtree.F90:385-401) are done in k_wrap_count.
+#include "common.cuh"
+#include <cub/cub.cuh>
+#include <float.h>
+
+namespace {
+
+__device__ __forceinline__ unsigned long long enc_ordered(double v)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double dec_ordered(unsigned long long b)
+{
+    unsigned long long r = (b & 0x8000000000000000ull) ? (b & 0x7fffffffffffffffull) : ~b;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)r);
+#else
+    double d; memcpy(&d, &r, 8); return d;
+#endif
+}
+
+// periodic wrap (boundary.f90:123-157), NaN check (kdtree.F90:391), live count, bounding box
+__global__ void k_wrap_count(int64_t n, double *__restrict__ xyzh, DevParams dp, unsigned long long *cnt, unsigned long long *bbox_enc)
+{
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    int nlive = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double4 x = reinterpret_cast<double4 *>(xyzh)[i];
+        if (!(x.w < DBL_MIN)) {
+            if (dp.p.periodic) {
+                bool ch = false;
+                if (x.x < dp.p.xmin) { x.x += dp.dxbound; ch = true; } else if (x.x > dp.p.xmax) { x.x -= dp.dxbound; ch = true; }
+                if (x.y < dp.p.ymin) { x.y += dp.dybound; ch = true; } else if (x.y > dp.p.ymax) { x.y -= dp.dybound; ch = true; }
+                if (x.z < dp.p.zmin) { x.z += dp.dzbound; ch = true; } else if (x.z > dp.p.zmax) { x.z -= dp.dzbound; ch = true; }
+                if (ch) reinterpret_cast<double4 *>(xyzh)[i] = x;
+            }
+            if (isnan(x.x) || isnan(x.y) || isnan(x.z)) { atomicMax(&cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_NAN); atomicMax(&cnt[CNT_ERRID], (unsigned long long)(i + 1)); }
+            nlive++;
+            lo[0] = fmin(lo[0], x.x); lo[1] = fmin(lo[1], x.y); lo[2] = fmin(lo[2], x.z);
+            hi[0] = fmax(hi[0], x.x); hi[1] = fmax(hi[1], x.y); hi[2] = fmax(hi[2], x.z);
+        }
+    }
+    for (int k = 0; k < 3; k++) { lo[k] = warp_min(lo[k]); hi[k] = warp_max(hi[k]); }
+    int tot = nlive;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) tot += __shfl_xor_sync(FULLMASK, tot, s);
+    if (lane_id() == 0) {
+        if (tot) atomicAdd(&cnt[CNT_NLIVE], (unsigned long long)tot);
+        if (tot) for (int k = 0; k < 3; k++) { atomicMin(&bbox_enc[k], enc_ordered(lo[k])); atomicMax(&bbox_enc[3 + k], enc_ordered(hi[k])); }
+    }
+}
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long x)
+{
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_keys(int64_t n, const double *__restrict__ xyzh, double x0, double y0, double z0, double inv_scale,
+                       unsigned long long *__restrict__ keys, int *__restrict__ idx)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 x = reinterpret_cast<const double4 *>(xyzh)[i];
+    unsigned long long key;
+    if (x.w < DBL_MIN) key = ~0ull;   // dead/accreted particles sort to the end (part.F90:931)
+    else {
+        const double s = 2097152.0;   // 2^21
+        double ux = fmin(fmax((x.x - x0) * inv_scale, 0.0), 0.99999994) * s;
+        double uy = fmin(fmax((x.y - y0) * inv_scale, 0.0), 0.99999994) * s;
+        double uz = fmin(fmax((x.z - z0) * inv_scale, 0.0), 0.99999994) * s;
+        key = (spread21((unsigned long long)ux) << 2) | (spread21((unsigned long long)uy) << 1) | spread21((unsigned long long)uz);
+    }
+    keys[i] = key;
+    idx[i] = (int)i;
+}
+
+__global__ void k_gather_pos(int64_t nlive, const int *__restrict__ perm, const double *__restrict__ xyzh, const int8_t *__restrict__ iphase,
+                             double4 *__restrict__ pos4, int8_t *__restrict__ stype, const unsigned long long *__restrict__ keys,
+                             unsigned char *__restrict__ cpl)
+{
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nlive) return;
+    const int i = perm[s];
+    pos4[s] = reinterpret_cast<const double4 *>(xyzh)[i];
+    stype[s] = iphase[i];
+    // common leading octal digits with the previous key (0..21)
+    unsigned char c = 0;
+    if (s > 0) {
+        unsigned long long x = keys[s] ^ keys[s - 1];
+        c = x ? (unsigned char)((__clzll((long long)x) - 1) / 3) : (unsigned char)21;
+    }
+    cpl[s] = c;
+}
+
+// leaf-cell boundaries: particle s starts a cell iff its predecessor is not in the same maximal octree node of <= tmax particles
+__global__ void k_cell_flags(int64_t nlive, const unsigned char *__restrict__ cpl, int tmax, int *__restrict__ flag)
+{
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nlive) return;
+    int hist[23];
+#pragma unroll
+    for (int d = 0; d < 23; d++) hist[d] = 0;
+    int m = 22;
+    for (int k = 1; k <= tmax; k++) {           // to the left: m_k = min cpl over (s-k+1 .. s)
+        if (s - k < 0) break;
+        m = min(m, (int)cpl[s - k + 1]);
+        hist[m]++;
+    }
+    m = 22;
+    for (int k = 1; k <= tmax; k++) {           // to the right: min cpl over (s+1 .. s+k)
+        if (s + k >= nlive) break;
+        m = min(m, (int)cpl[s + k]);
+        hist[m]++;
+    }
+    int count = 1, depth = 22;
+    int cum[23];
+    for (int d = 22; d >= 0; d--) { count += hist[d]; cum[d] = count; }
+    for (int d = 0; d <= 21; d++) if (cum[d] <= tmax) { depth = d; break; }
+    int f;
+    if (s == 0) f = 1;
+    else if (depth == 22) f = (cpl[s] < 21) || (s % tmax == 0);
+    else f = (int)cpl[s] < depth;
+    flag[s] = f;
+}
+
+__global__ void k_cell_starts(int64_t nlive, const int *__restrict__ flag, const int *__restrict__ scan, Cell *__restrict__ cells)
+{
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nlive) return;
+    if (flag[s]) cells[scan[s]].start = (int)s;
+}
+
+__global__ void k_cell_props(int64_t ncells, int64_t nlive, Cell *__restrict__ cells, const double4 *__restrict__ pos4, const int8_t *__restrict__ stype,
+                             const unsigned long long *__restrict__ keys, unsigned long long *__restrict__ cellkeys, int sbta, int use_dust, int ind_ts)
+{
+    int64_t cidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (cidx >= ncells) return;
+    Cell c = cells[cidx];
+    const int end = (cidx + 1 < ncells) ? cells[cidx + 1].start : (int)nlive;
+    c.count = end - c.start;
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX}, hmax = 0.;
+    int nact = 0;
+    for (int s = c.start; s < end; s++) {
+        const double4 x = pos4[s];
+        lo[0] = fmin(lo[0], x.x); lo[1] = fmin(lo[1], x.y); lo[2] = fmin(lo[2], x.z);
+        hi[0] = fmax(hi[0], x.x); hi[1] = fmax(hi[1], x.y); hi[2] = fmax(hi[2], x.z);
+        hmax = fmax(hmax, x.w);
+        bool a, g, d; int t;
+        get_partinfo_d(stype[s], sbta, use_dust, a, g, d, t);
+        (void)ind_ts;
+        if (a) nact++;
+    }
+    for (int k = 0; k < 3; k++) { c.lo[k] = lo[k]; c.hi[k] = hi[k]; }
+    c.hmax = hmax; c.active = nact; c.parent = -1;
+    cells[cidx] = c;
+    cellkeys[cidx] = keys[c.start];
+}
+
+// ---- Karras binary radix tree over the M cell keys -------------------------------------------
+__device__ __forceinline__ int delta_k(const unsigned long long *keys, int M, int i, int j)
+{
+    if (j < 0 || j >= M) return -1;
+    const unsigned long long a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void k_radix_tree(int M, const unsigned long long *__restrict__ keys, TreeNode *__restrict__ nodes, Cell *__restrict__ cells)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M - 1) return;
+    const int d = (delta_k(keys, M, i, i + 1) - delta_k(keys, M, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta_k(keys, M, i, i - d);
+    int lmax = 2;
+    while (delta_k(keys, M, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta_k(keys, M, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta_k(keys, M, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta_k(keys, M, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    int cl, cr;
+    if (lo == gamma) { cl = ~gamma; cells[gamma].parent = i; } else { cl = gamma; nodes[gamma].parent = i; }
+    if (hi == gamma + 1) { cr = ~(gamma + 1); cells[gamma + 1].parent = i; } else { cr = gamma + 1; nodes[gamma + 1].parent = i; }
+    nodes[i].child[0] = cl; nodes[i].child[1] = cr;
+    if (i == 0) nodes[0].parent = -1;
+}
+
+// bottom-up refit: the second thread to arrive at a node merges its two child boxes into the grandparent slot
+__global__ void k_refit(int M, const Cell *__restrict__ cells, TreeNode *nodes, int *flags)
+{
+    int cidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cidx >= M) return;
+    const Cell c = cells[cidx];
+    double lo[3] = {c.lo[0], c.lo[1], c.lo[2]}, hi[3] = {c.hi[0], c.hi[1], c.hi[2]}, hmax = c.hmax;
+    int me = ~cidx, parent = c.parent;
+    while (parent >= 0) {
+        TreeNode *nd = &nodes[parent];
+        const int slot = (nd->child[0] == me) ? 0 : 1;
+        for (int k = 0; k < 3; k++) { nd->lo[slot][k] = lo[k]; nd->hi[slot][k] = hi[k]; }
+        nd->hmax[slot] = hmax;
+        __threadfence();
+        if (atomicAdd(&flags[parent], 1) == 0) return;     // first arrival: sibling not ready yet
+        __threadfence();
+        const int o = 1 - slot;
+        const volatile TreeNode *vn = nd;
+        for (int k = 0; k < 3; k++) { lo[k] = fmin(lo[k], vn->lo[o][k]); hi[k] = fmax(hi[k], vn->hi[o][k]); }
+        hmax = fmax(hmax, vn->hmax[o]);
+        me = parent;
+        parent = vn->parent;
+    }
+}
+
+__global__ void k_cell_hmax(int64_t ncells, Cell *__restrict__ cells, const double4 *__restrict__ pos4)
+{
+    int64_t cidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (cidx >= ncells) return;
+    const int start = cells[cidx].start, count = cells[cidx].count;
+    double hmax = 0.;
+    for (int s = start; s < start + count; s++) hmax = fmax(hmax, pos4[s].w);
+    cells[cidx].hmax = hmax;
+}
+
+}  // namespace
+
+#define LAUNCH(c, kern, grid, block, ...)                         \
+    do {                                                          \
+        kern<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__);   \
+        (c)->launches++;                                          \
+    } while (0)
+
+static inline int nblk(int64_t n, int b) { return (int)((n + b - 1) / b); }
+
+int tree_refit_hmax(sphgpu_ctx *c)
+{
+    const int M = (int)c->ncells;
+    LAUNCH(c, k_cell_hmax, nblk(M, 128), 128, M, c->cells.p, c->pos4.p);
+    if (M > 1) {
+        CUDA_TRY(c, cudaMemsetAsync(c->nodeflag.p, 0, sizeof(int) * (size_t)M, c->stream));
+        LAUNCH(c, k_refit, nblk(M, 128), 128, M, c->cells.p, c->nodes.p, c->nodeflag.p);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+int tree_build(sphgpu_ctx *c)
+{
+    const int64_t n = c->npart;
+    if (n <= 0) { c->err = "build_tree: no particles"; return SPHGPU_ERR_NOPART; }
+    c->tree_valid = false; c->dens_valid = false;
+    CUDA_TRY(c, c->keys.ensure(n)); CUDA_TRY(c, c->keys_alt.ensure(n));
+    CUDA_TRY(c, c->perm.ensure(n)); CUDA_TRY(c, c->perm_alt.ensure(n));
+    CUDA_TRY(c, c->counters.ensure(CNT_COUNT)); CUDA_TRY(c, c->dscal.ensure(DS_COUNT));
+    CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * CNT_COUNT, c->stream));
+    // bbox accumulators (ordered encoding): min slots start at all-ones, max slots at zero
+    unsigned long long *bbox_enc = c->counters.p + 16;
+    CUDA_TRY(c, cudaMemsetAsync(bbox_enc, 0xff, sizeof(unsigned long long) * 3, c->stream));
+    LAUNCH(c, k_wrap_count, c->numSMs * 8, 256, n, c->xyzh.p, c->hp, c->counters.p, bbox_enc);
+    unsigned long long hc[CNT_COUNT];
+    CUDA_TRY(c, cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (hc[CNT_ERR]) {
+        char buf[128]; snprintf(buf, sizeof buf, "maketree: NaN in particle position, likely caused by NaN in force (particle %llu)", hc[CNT_ERRID]);
+        c->err = buf; return (int)hc[CNT_ERR];
+    }
+    const int64_t nlive = (int64_t)hc[CNT_NLIVE];
+    if (nlive == 0) { c->err = "maketree: no particles or all particles dead/accreted"; return SPHGPU_ERR_NOPART; }
+    c->nlive = nlive;
+    double lo[3], hi[3];
+    for (int k = 0; k < 3; k++) { lo[k] = dec_ordered(hc[16 + k]); hi[k] = dec_ordered(hc[19 + k]); }
+    const sphgpu_params &p = c->hp.p;
+    if (p.periodic) {   // stable normalisation across steps: the periodic box itself
+        lo[0] = fmin(lo[0], p.xmin); lo[1] = fmin(lo[1], p.ymin); lo[2] = fmin(lo[2], p.zmin);
+        hi[0] = fmax(hi[0], p.xmax); hi[1] = fmax(hi[1], p.ymax); hi[2] = fmax(hi[2], p.zmax);
+    }
+    double scale = fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    if (!(scale > 0.)) scale = 1.0;
+    scale *= 1.0000001;
+    LAUNCH(c, k_keys, nblk(n, 256), 256, n, c->xyzh.p, lo[0], lo[1], lo[2], 1.0 / scale, c->keys_alt.p, c->perm_alt.p);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, c->keys_alt.p, c->keys.p, c->perm_alt.p, c->perm.p, (int)n, 0, 64, c->stream);
+    size_t tb2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb2, c->cellflag.p, c->cellid_scan.p, (int)n, c->stream);
+    tb = tb > tb2 ? tb : tb2;
+    CUDA_TRY(c, c->cubtemp.ensure(tb));
+    size_t tbb = c->cubtemp.cap;
+    CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(c->cubtemp.p, tbb, c->keys_alt.p, c->keys.p, c->perm_alt.p, c->perm.p, (int)n, 0, 64, c->stream));
+    c->launches += 8;
+    CUDA_TRY(c, c->pos4.ensure(n)); CUDA_TRY(c, c->stype.ensure(n)); CUDA_TRY(c, c->cpl.ensure(n));
+    CUDA_TRY(c, c->cellflag.ensure(n)); CUDA_TRY(c, c->cellid_scan.ensure(n));
+    LAUNCH(c, k_gather_pos, nblk(nlive, 256), 256, nlive, c->perm.p, c->xyzh.p, c->iphase.p, c->pos4.p, c->stype.p, c->keys.p, c->cpl.p);
+    LAUNCH(c, k_cell_flags, nblk(nlive, 128), 128, nlive, c->cpl.p, c->max_cell, c->cellflag.p);
+    tbb = c->cubtemp.cap;
+    CUDA_TRY(c, cub::DeviceScan::ExclusiveSum(c->cubtemp.p, tbb, c->cellflag.p, c->cellid_scan.p, (int)nlive, c->stream));
+    c->launches += 2;
+    int lastflag, lastscan;
+    CUDA_TRY(c, cudaMemcpyAsync(&lastflag, c->cellflag.p + (nlive - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(&lastscan, c->cellid_scan.p + (nlive - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    const int64_t M = (int64_t)lastscan + lastflag;
+    c->ncells = M;
+    CUDA_TRY(c, c->cells.ensure(M)); CUDA_TRY(c, c->cellkeys.ensure(M)); CUDA_TRY(c, c->nodes.ensure(M)); CUDA_TRY(c, c->nodeflag.ensure(M));
+    LAUNCH(c, k_cell_starts, nblk(nlive, 256), 256, nlive, c->cellflag.p, c->cellid_scan.p, c->cells.p);
+    LAUNCH(c, k_cell_props, nblk(M, 128), 128, M, nlive, c->cells.p, c->pos4.p, c->stype.p, c->keys.p, c->cellkeys.p,
+           p.set_boundaries_to_active, p.dust, p.ind_timesteps);
+    if (M > 1) {
+        LAUNCH(c, k_radix_tree, nblk(M - 1, 128), 128, (int)M, c->cellkeys.p, c->nodes.p, c->cells.p);
+        CUDA_TRY(c, cudaMemsetAsync(c->nodeflag.p, 0, sizeof(int) * (size_t)M, c->stream));
+        LAUNCH(c, k_refit, nblk(M, 128), 128, (int)M, c->cells.p, c->nodes.p, c->nodeflag.p);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    c->tree_valid = true;
+    return SPHGPU_OK;
+}
