@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of the SPH hot path (tree + density + cons2prim + force) on B200.
+
+One "step" = one derivs(icall=1) over the whole synthetic particle set (BASELINE.json metric).
+  value : device-resident throughput, timed on the device with CUDA events, max over ranks
+  e2e   : the same step through the reference-facing C-ABI call sphgpu_derivs with HOST (pinned) buffers,
+          host->device and device->host copies inside the timed region
+  roofline     : the dominant pair kernel against the FP64 pipe peak measured on this device (DFMA microbenchmark)
+  cpu_baseline : the CPU oracle ("port" of the reference algorithm; the reference is Fortran and cannot be built)
+`--impl reference` times that CPU implementation alone on the host cores with the same config/metric.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def flop_constants():
+    txt = open(os.path.join(ROOT, "phantom_b200", "csrc", "roofline_constants.h")).read()
+    return {k: int(v) for k, v in re.findall(r"#define\s+(\w+)\s+(\d+)", txt)}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons streamed DURING the timed region (B200_PROFILING.md recipe, -lms 100)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def start(self):
+        time.sleep(0.35)      # let the first samples land before the timed region starts
+
+    def stop(self):
+        self.samples = []
+        if self.proc is None:
+            return
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) >= 7:
+                self.samples.append(f)
+
+    def summary(self):
+        if not getattr(self, "samples", None):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons),
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples)}
+
+
+def pinned_like(part):
+    """re-home the particle arrays in pinned host memory so the e2e copies are the DMA path a resident host code would use"""
+    import torch
+    for k, v in list(part.__dict__.items()):
+        if isinstance(v, np.ndarray) and v.size > 0:
+            t = torch.empty(v.shape, dtype=torch.from_numpy(v).dtype, pin_memory=True)
+            a = t.numpy()
+            a[...] = v
+            setattr(part, k, a)
+            part.__dict__.setdefault("_pins", []).append(t)
+    return part
+
+
+def make_workload(args):
+    from phantom_b200 import setups
+    part = setups.setup_turb(nx=args.nx)
+    return part, f"turb: isothermal periodic box, {args.nx}^3 = {part.npart} particles, cubic kernel, hydro+AV (Cullen-Dehnen), all active"
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle (port of the reference algorithm) on all host threads; rank 0 only."""
+    if rank != 0:
+        return
+    from oraclelib import Oracle
+    part, wl = make_workload(args)
+    o = Oracle(part.params)
+    threads = o.max_threads()
+    # bounded sample: shrink the box until (steps+warmup) steps fit in ~150 s (cost is linear in N)
+    nx = args.nx
+    t_est = 9.0e-6 * part.npart * 8.0 / max(threads, 1)
+    while nx > 32 and t_est * (args.steps + args.warmup) > 150.0:
+        nx //= 2
+        t_est /= 8.0
+    if nx != args.nx:
+        args.nx = nx
+        part, _ = make_workload(args)
+        o = Oracle(part.params)
+    for _ in range(args.warmup):
+        o.derivs(part)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.derivs(part)
+    dt = time.perf_counter() - t0
+    val = part.npart * args.steps / dt
+    sample = f"{args.steps} full derivs on {nx}^3 = {part.npart} particles"
+    line = {
+        "impl": "reference", "metric": "particle-updates/s (tree+density+cons2prim+force)", "value": val, "unit": "particle-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl, "cpu_sample_nx": nx},
+        "cpu_baseline": {"value": val, "unit": "particle-updates/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--nx", type=int, default=128, help="lattice points per axis of the turb box (BASELINE configs[1]: 128)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-cell", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from phantom_b200.api import SphGpu, F_ALL
+    part, wl = make_workload(args)
+    n = part.npart
+    g = SphGpu(part.params.copy(), device=local)
+    if args.max_cell:
+        g.set_option("max_cell", args.max_cell)
+    fp64_peak = g.measure_fp64_peak()
+    copy_bw = g.measure_copy_bw()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm ----------------
+    g.upload(part)
+    for _ in range(args.warmup):
+        sc = g.derivs_resident(1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = g.launch_count()
+    barrier()
+    t_dev = 0.0
+    phases = dict(tree=0.0, dens=0.0, cons2prim=0.0, force=0.0)
+    kern = dict(density=0.0, force=0.0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sc = g.derivs_resident(1)
+        tm = g.timings_ms()
+        t_dev += sum(tm.values())
+        for k in phases:
+            phases[k] += tm[k]
+        kt = g.kernel_timings_ms()
+        for k in kern:
+            kern[k] += kt[k]
+    barrier()
+    t_wall = time.perf_counter() - t0
+    launches = g.launch_count() - l0
+    sampler.stop()
+    # max over ranks of the device time
+    tt = torch.tensor([t_dev, t_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev_max, t_wall_max = float(tt[0]) * 1e-3, float(tt[1])
+    value = n * world * args.steps / t_dev_max
+
+    # ---------------- end-to-end arm: the literal C-ABI call with host (pinned) buffers ----------------
+    part_e2e = pinned_like(part.copy())
+    g2 = SphGpu(part.params.copy(), device=local)
+    if args.max_cell:
+        g2.set_option("max_cell", args.max_cell)
+    nvu, ng = part.params.maxvxyzu, part.params.ngradh
+    h2d = n * (4 * 8 + nvu * 8 * 2 + 3 * 8 + 3 * 4 + 1 + ng * 4 + 4 + 9 * 4 + 7 * 8)
+    d2h = n * (4 * 8 + nvu * 8 + ng * 4 + 4 + 9 * 4 + 3 * 4 + 7 * 8)
+    for _ in range(2):
+        g2.derivs(part_e2e, 1)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        g2.derivs(part_e2e, 1)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = n * world * args.steps / float(te[0])
+
+    # ---------------- roofline of the dominant pair kernels ----------------
+    fc = flop_constants()
+    iso = bool(part.params.isothermal)
+    f_dens = fc["FLOP_DENS_PAIR_HYDRO"] * sc.npairs_density + fc["FLOP_DENS_EPILOGUE"] * sc.nrhocalc
+    f_force = (fc["FLOP_FORCE_PAIR_ISOTHERMAL"] if iso else fc["FLOP_FORCE_PAIR_ADIABATIC"]) * sc.npairs_force + fc["FLOP_FORCE_EPILOGUE"] * n
+    ms_d, ms_f = kern["density"] / args.steps, kern["force"] / args.steps
+    passes = {
+        "density": {"flops_per_launch": f_dens, "ms": ms_d, "achieved_tflops": f_dens / (ms_d * 1e-3) / 1e12, "pairs": sc.npairs_density,
+                    "its_mean": sc.nrhocalc / max(sc.np, 1)},
+        "force": {"flops_per_launch": f_force, "ms": ms_f, "achieved_tflops": f_force / (ms_f * 1e-3) / 1e12, "pairs": sc.npairs_force},
+    }
+    for v in passes.values():
+        v["frac_fp64"] = v["achieved_tflops"] / fp64_peak
+    dom = "density" if ms_d >= ms_f else "force"
+    bytes_step = n * (fc["BYTES_TREE_PER_PARTICLE"] + fc["BYTES_DENS_PER_PARTICLE"] + fc["BYTES_C2P_PER_PARTICLE"] + fc["BYTES_FORCE_PER_PARTICLE"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {
+        "bound": "fp64", "kernel": "k_density" if dom == "density" else "k_force",
+        "achieved": passes[dom]["achieved_tflops"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": passes[dom]["frac_fp64"],
+        "peak_source": "DFMA microbenchmark measured live on this device (MEASURED_PEAKS.json has no FP64 figure)",
+        "traffic": None,
+        "hbm_view": {"algorithmic_bytes_per_step": bytes_step, "achieved_gbs": bytes_step / (t_dev_max / args.steps) / 1e9, "peak_gbs": hbm_peak,
+                     "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback", "frac": bytes_step / (t_dev_max / args.steps) / 1e9 / hbm_peak,
+                     "copy_bw_live_gbs": copy_bw},
+        "passes": passes,
+    }
+
+    line = {
+        "metric": "particle-updates/s (tree+density+cons2prim+force)", "value": value, "unit": "particle-updates/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl, "per_gpu_particles": n, "parallelism": "single" if world == 1 else f"{world} independent periodic boxes (halo exchange not built yet)",
+                   "l2": "inputs_exceed_l2 (working set ~%.1f GB per step)" % (n * 600 / 1e9), "state": "device-resident, derivs(icall=1) repeated on the same state"},
+        "phases_ms": {k: v / args.steps for k, v in phases.items()},
+        "wall_ms_per_step": 1e3 * t_wall_max / args.steps,
+        "e2e": {"value": e2e_val, "unit": "particle-updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "call": "sphgpu_derivs (literal C-ABI, pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": roofline,
+        "neighbours": {"mean": sc.actualmean, "max": sc.maxactual, "trial_mean": sc.trialmean},
+    }
+
+    # ---------------- CPU baseline (oracle port) beside it: rank 0, N=1 ----------------
+    if world == 1 and not args.no_cpu_baseline and rank == 0:
+        from oraclelib import Oracle
+        pc = part.copy()
+        o = Oracle(pc.params)
+        threads = o.max_threads()
+        nxc = args.nx
+        if 9.0e-6 * pc.npart * 8.0 / max(threads, 1) > 40.0:     # keep to ~10-30 s of CPU work
+            nxc = args.nx // 2
+            import copy
+            a2 = copy.copy(args)
+            a2.nx = nxc
+            pc, _ = make_workload(a2)
+            o = Oracle(pc.params)
+        t0 = time.perf_counter()
+        o.derivs(pc)
+        tc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": pc.npart / tc, "unit": "particle-updates/s", "cores": threads, "kind": "port",
+                                "sample": f"1 full derivs on {nxc}^3 = {pc.npart} particles ({tc:.1f} s)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

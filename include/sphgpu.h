@@ -134,6 +134,8 @@ const char *sphgpu_last_error(sphgpu_ctx *ctx);
 int  sphgpu_set_option(sphgpu_ctx *ctx, const char *name, double value);
 /* per-phase device times of the last derivs (ms): tree, dens, cons2prim, force ; utils_timing.f90 labels */
 int  sphgpu_get_timings(sphgpu_ctx *ctx, double *ms4);
+/* device time (ms) of the two dominant kernels of the last call: [0] density pair kernel, [1] force pair kernel */
+int  sphgpu_get_kernel_timings(sphgpu_ctx *ctx, double *ms2);
 /* number of kernel launches issued by this context since creation */
 int64_t sphgpu_launch_count(sphgpu_ctx *ctx);
 

@@ -30,7 +30,7 @@ ERRORS = {1: "CUDA", 2: "ARG", 3: "NAN", 4: "NOPART", 5: "NOCONVERGE", 6: "NEGH"
 
 EXPORTS = [
     "sphgpu_create", "sphgpu_destroy", "sphgpu_set_params", "sphgpu_last_error", "sphgpu_set_option", "sphgpu_get_timings",
-    "sphgpu_launch_count", "sphgpu_upload", "sphgpu_download", "sphgpu_build_tree_resident", "sphgpu_densityiterate_resident",
+    "sphgpu_launch_count", "sphgpu_get_kernel_timings", "sphgpu_upload", "sphgpu_download", "sphgpu_build_tree_resident", "sphgpu_densityiterate_resident",
     "sphgpu_cons2prim_resident", "sphgpu_force_resident", "sphgpu_derivs_resident", "sphgpu_build_tree", "sphgpu_densityiterate",
     "sphgpu_cons2prim_everything", "sphgpu_force", "sphgpu_derivs", "sphgpu_get_neighbour_stats", "sphgpu_neighbour_sets",
     "sphgpu_measure_fp64_peak", "sphgpu_measure_copy_bw",
@@ -69,6 +69,7 @@ def load_library():
         L.sphgpu_last_error.restype = C.c_char_p
         L.sphgpu_set_option.argtypes = [vp, C.c_char_p, dbl]
         L.sphgpu_get_timings.argtypes = [vp, C.POINTER(dbl)]
+        L.sphgpu_get_kernel_timings.argtypes = [vp, C.POINTER(dbl)]
         L.sphgpu_launch_count.argtypes = [vp]
         L.sphgpu_launch_count.restype = i64
         L.sphgpu_upload.argtypes = [vp, C.POINTER(HostArrays), C.c_uint64]
@@ -217,6 +218,11 @@ class SphGpu:
         t = (C.c_double * 4)()
         self.L.sphgpu_get_timings(self.h, t)
         return dict(tree=t[0], dens=t[1], cons2prim=t[2], force=t[3])
+
+    def kernel_timings_ms(self):
+        t = (C.c_double * 2)()
+        self.L.sphgpu_get_kernel_timings(self.h, t)
+        return dict(density=t[0], force=t[1])
 
     def launch_count(self):
         return self.L.sphgpu_launch_count(self.h)

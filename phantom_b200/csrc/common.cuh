@@ -65,10 +65,11 @@ struct sphgpu_ctx {
     std::string err;
     DevParams hp;              // host copy
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[12];
     int numSMs = 148;
     int64_t launches = 0;
     double ms_phase[4] = {0, 0, 0, 0};
+    double ms_kernel[2] = {0, 0};   // k_density, k_force alone (CUDA events on the launching stream)
     // tuning
     int max_cell = 16;
     double list_margin = 1.02;

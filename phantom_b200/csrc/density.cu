@@ -397,7 +397,15 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     CUDA_TRY(c, c->vel4.ensure(n)); CUDA_TRY(c, c->acc4.ensure(n)); if (p.mhd) CUDA_TRY(c, c->bev4.ensure(n));
     CUDA_TRY(c, c->hnew.ensure(n)); CUDA_TRY(c, c->s_gradh.ensure(n * c->hp.ngradh)); CUDA_TRY(c, c->s_divv.ensure(n));
     CUDA_TRY(c, c->s_dvdx.ensure(9 * n)); CUDA_TRY(c, c->s_alpha3.ensure(n)); CUDA_TRY(c, c->s_divcurlB.ensure(4 * n)); CUDA_TRY(c, c->s_nneigh.ensure(n));
-    const int grid = c->numSMs * 3;          // persistent: 3 CTAs/SM fit (164-226 regs x 128 threads, 40 KB smem)
+    int bps = 3;     // persistent grid = resident CTAs/SM x SMs (register/smem limited; queried per instantiation below)
+    {
+        const bool mhd = p.mhd, grav = p.gravity;
+        if (p.kernel == 0 && p.periodic && !mhd && !grav) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_density<0, true, false, false>, 128, 0);
+        else if (p.kernel == 1 && p.periodic && !mhd && !grav) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_density<1, true, false, false>, 128, 0);
+        else if (p.kernel == 0 && p.periodic && mhd && !grav) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_density<0, true, true, false>, 128, 0);
+        if (bps < 1) bps = 1;
+    }
+    const int grid = c->numSMs * bps;
     CUDA_TRY(c, c->scratch.ensure((size_t)grid * 4 * c->scratch_per_warp));
     k_gather_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->vxyzu.p, c->fxyzu.p, c->fext.p, c->Bevol.p, c->hp.nvu, p.mhd, c->pos4.p, c->vel4.p,
                                                         c->acc4.p, c->bev4.p, c->hnew.p, c->s_nneigh.p);
@@ -411,8 +419,10 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     a.s_divcurlB = c->s_divcurlB.p; a.s_nneigh = c->s_nneigh.p;
     a.scratch = c->scratch.p; a.scratch_per_warp = c->scratch_per_warp; a.cnt = c->counters.p; a.dscal = c->dscal.p;
     a.margin = c->list_margin; a.icall = icall;
+    cudaEventRecord(c->ev[8], c->stream);
     if (p.kernel == 0) { if (p.periodic) dispatch_density2<0, true>(c, a, grid); else dispatch_density2<0, false>(c, a, grid); }
     else { if (p.periodic) dispatch_density2<1, true>(c, a, grid); else dispatch_density2<1, false>(c, a, grid); }
+    cudaEventRecord(c->ev[9], c->stream);
     k_scatter_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->hnew.p, c->pos4.p, c->xyzh.p, c->s_gradh.p, c->s_divv.p, c->s_dvdx.p,
                                                          c->s_alpha3.p, c->s_divcurlB.p, c->gradh.p, c->divcurlv.p, c->dvdx.p, c->alphaind.p, c->divcurlB.p,
                                                          c->hp.ngradh, c->hp.nalpha, p.mhd);
@@ -423,6 +433,7 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     CUDA_TRY(c, cudaMemcpyAsync(&hrhomax, c->dscal.p + DS_RHOMAX, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaGetLastError());
+    { float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); c->ms_kernel[0] = ms; }
     if (hc[CNT_ERR] == SPHGPU_ERR_NOCONVERGE) {
         char buf[160]; snprintf(buf, sizeof buf, "densityiterate: could not converge in density on particle %llu", hc[CNT_ERRID]);
         c->err = buf; return SPHGPU_ERR_NOCONVERGE;

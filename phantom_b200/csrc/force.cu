@@ -391,7 +391,12 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     CUDA_TRY(c, c->hnew.ensure(2 * n));                                    // reused as double2 hinv
     CUDA_TRY(c, c->s_fxyzu.ensure(n)); if (p.mhd) { CUDA_TRY(c, c->s_dB.ensure(n)); CUDA_TRY(c, c->s_divBsymm.ensure(n)); }
     CUDA_TRY(c, c->s_divvf.ensure(n)); CUDA_TRY(c, c->s_nneigh.ensure(n));
-    const int grid = c->numSMs * 3;          // persistent grid, 3 CTAs/SM
+    int bps = 3;     // persistent grid = resident CTAs/SM x SMs
+    if (p.kernel == 0 && p.periodic && !p.mhd) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force<0, true, false>, 128, 0);
+    else if (p.kernel == 1 && p.periodic && !p.mhd) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force<1, true, false>, 128, 0);
+    else if (p.kernel == 0 && p.periodic && p.mhd) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force<0, true, true>, 128, 0);
+    if (bps < 1) bps = 1;
+    const int grid = c->numSMs * bps;
     CUDA_TRY(c, c->scratch.ensure((size_t)grid * 4 * c->scratch_per_warp));
     CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
     const double init[4] = {1.e29, 1.e29, 1.e29, 0.};
@@ -405,8 +410,10 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.recC = c->frecC.p; a.recD = c->frecD.p; a.recE = c->frecE.p; a.hinv = hinv; a.stype = c->stype.p; a.perm = c->perm.p;
     a.s_fxyzu = c->s_fxyzu.p; a.s_dB = c->s_dB.p; a.s_divvf = c->s_divvf.p; a.s_divBsymm = c->s_divBsymm.p; a.s_done = c->s_nneigh.p;
     a.scratch = c->scratch.p; a.scratch_per_warp = c->scratch_per_warp; a.cnt = c->counters.p; a.dscal = c->dscal.p; a.icall = icall;
+    cudaEventRecord(c->ev[10], c->stream);
     if (p.kernel == 0) { if (p.periodic) dispatch_force<0, true>(c, a, grid); else dispatch_force<0, false>(c, a, grid); }
     else { if (p.periodic) dispatch_force<1, true>(c, a, grid); else dispatch_force<1, false>(c, a, grid); }
+    cudaEventRecord(c->ev[11], c->stream);
     k_scatter_force<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->s_fxyzu.p, c->s_dB.p, c->s_divvf.p, c->s_divBsymm.p, c->fxyzu.p,
                                                           c->dBevol.p, c->divcurlv.p, c->divBsymm.p, c->hp.nvu, p.mhd);
     c->launches++;
@@ -415,6 +422,7 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     CUDA_TRY(c, cudaMemcpyAsync(hd, c->dscal.p + DS_DTCOURANT, sizeof(hd), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaGetLastError());
+    { float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[10], c->ev[11]); c->ms_kernel[1] = ms; }
     if (hc[CNT_ERR] == SPHGPU_ERR_NEGH) {
         char buf[128]; snprintf(buf, sizeof buf, "force: negative smoothing length on particle %llu", hc[CNT_ERRID]);
         c->err = buf; return SPHGPU_ERR_NEGH;

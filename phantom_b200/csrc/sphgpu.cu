@@ -91,7 +91,7 @@ int sphgpu_create(const sphgpu_params *params, int device, sphgpu_ctx **out)
     cudaGetDeviceProperties(&prop, device);
     c->numSMs = prop.multiProcessorCount;
     cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    for (int k = 0; k < 8; k++) cudaEventCreate(&c->ev[k]);
+    for (int k = 0; k < 12; k++) cudaEventCreate(&c->ev[k]);
     set_params_internal(c, params);
     *out = c;
     return SPHGPU_OK;
@@ -111,7 +111,7 @@ void sphgpu_destroy(sphgpu_ctx *c)
     c->s_divvf.release(); c->s_poten.release(); c->s_divBsymm.release(); c->s_nneigh.release();
     c->cpl.release(); c->cellflag.release(); c->cellid_scan.release(); c->cells.release(); c->cellkeys.release(); c->nodes.release(); c->nodeflag.release();
     c->cubtemp.release(); c->scratch.release(); c->counters.release(); c->dscal.release();
-    for (int k = 0; k < 8; k++) cudaEventDestroy(c->ev[k]);
+    for (int k = 0; k < 12; k++) cudaEventDestroy(c->ev[k]);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -143,6 +143,12 @@ int sphgpu_get_timings(sphgpu_ctx *c, double *ms4)
     return SPHGPU_OK;
 }
 int64_t sphgpu_launch_count(sphgpu_ctx *c) { return c ? c->launches : 0; }
+int sphgpu_get_kernel_timings(sphgpu_ctx *c, double *ms2)
+{
+    if (!c || !ms2) return SPHGPU_ERR_ARG;
+    ms2[0] = c->ms_kernel[0]; ms2[1] = c->ms_kernel[1];
+    return SPHGPU_OK;
+}
 
 int sphgpu_upload(sphgpu_ctx *c, const sphgpu_host_arrays *h, uint64_t mask)
 {
