@@ -52,6 +52,14 @@ struct __align__(16) TreeNode {
     int pad;
 };
 
+// FP32 copy used by the walk: boxes rounded OUTWARD, hmax rounded up (conservative tests), 64 bytes = 2 sectors
+struct __align__(16) TreeNodeF {
+    float lo[2][3];
+    float hi[2][3];
+    float hmax[2];
+    int child[2];
+};
+
 struct Cell {          // leaf cell = run of <= max_cell Morton-consecutive particles
     double lo[3], hi[3];
     double hmax;
@@ -100,6 +108,10 @@ struct sphgpu_ctx {
     DevBuf<Cell> cells;
     DevBuf<unsigned long long> cellkeys;
     DevBuf<TreeNode> nodes;
+    DevBuf<TreeNodeF> nodesf;
+    bool multitype = false;                 // any particle that is not plain gas (boundary, dust, ...)
+    DevBuf<float4> stage_pos;               // per-warp staged candidates
+    DevBuf<int> stage_idx;
     DevBuf<int> nodeflag;
     DevBuf<char> cubtemp;
     DevBuf<int> scratch;                    // per-warp candidate lists
@@ -189,7 +201,7 @@ __device__ __forceinline__ void atomic_min_pos(double *addr, double v) { atomicM
 __device__ __forceinline__ void atomic_max_pos(double *addr, double v) { atomicMax((unsigned long long *)addr, (unsigned long long)__double_as_longlong(v)); }
 
 // indices into ctx->counters (unsigned long long)
-enum { CNT_WORK = 0, CNT_ERR, CNT_ERRID, CNT_NPAIRS, CNT_NTRIAL, CNT_NCALC, CNT_NACT, CNT_MAXACT, CNT_MAXTRIAL, CNT_NP, CNT_NWALK, CNT_NLIVE, CNT_NBINMAX, CNT_NCHECKBIN,
+enum { CNT_WORK = 0, CNT_ERR, CNT_ERRID, CNT_NPAIRS, CNT_NTRIAL, CNT_NCALC, CNT_NACT, CNT_MAXACT, CNT_MAXTRIAL, CNT_NP, CNT_NWALK, CNT_NLIVE, CNT_NBINMAX, CNT_NCHECKBIN, CNT_MULTITYPE, CNT_NSURV,
        CNT_COUNT = 32 };
 // indices into ctx->dscal (double)
 enum { DS_XMIN = 0, DS_YMIN, DS_ZMIN, DS_XMAX, DS_YMAX, DS_ZMAX, DS_DTCOURANT, DS_DTFORCE, DS_DTMINI, DS_DTMAXI, DS_RHOMAX, DS_COUNT = 32 };

@@ -22,10 +22,11 @@
 namespace {
 
 struct DensArgs {
-    const TreeNode *nodes; const Cell *cells; int ncells;
+    const TreeNodeF *nodes; const Cell *cells; int ncells;
     const double4 *pos4, *vel4, *acc4, *bev4; const int8_t *stype; const int *perm;
+    float4 *stage_pos; int *stage_idx; int multitype; double hmax_global;
     double *hnew; float *s_gradh, *s_divv, *s_dvdx, *s_alpha3, *s_divcurlB; int *s_nneigh;
-    int *scratch; int scratch_per_warp; unsigned long long *cnt; double *dscal;
+    int scratch_per_warp; unsigned long long *cnt; double *dscal;
     double margin; int icall;
 };
 
@@ -75,18 +76,26 @@ __global__ void k_scatter_dens(int64_t nlive, const int *__restrict__ perm, cons
     if (mhd) for (int k = 0; k < 4; k++) divcurlB[4 * (size_t)i + k] = s_divcurlB[4 * (size_t)s + k];
 }
 
-template <int K, bool MHD, bool GRAV>
-__device__ __forceinline__ void dens_pair(double (&v)[32], double (&w)[16], int &nneighi, int j, double dx, double dy, double dz, double r2,
-                                          double hi, double hi1, double hi21, int itypei, bool gasi, const double4 &vi, const double4 &ai,
-                                          const double4 &bi, const DensArgs &a, const DevParams &dp, bool use_da)
+// pair body: lane = one prefilter survivor j.  Re-evaluates the exact reference test, then the sums of get_density_sums.
+template <int K, bool PERIODIC, bool MHD, bool GRAV>
+__device__ __forceinline__ void dens_pair(double (&v)[32], double (&w)[16], int &nneighi, int j, int s, const double4 &pi, double hi, double hi1,
+                                          double hi21, int itypei, bool gasi, const double4 &vi, const double4 &ai, const double4 &bi,
+                                          const DensArgs &a, const DevParams &dp, bool use_da, double Lx, double Ly, double Lz)
 {
     typedef SphKern<K> KF;
-    const double q2i = r2 * hi21;
-    const double rij = sqrt(r2);
+    const double4 pj = a.pos4[j];
+    double dx, dy, dz;
+    const double r2 = pair_r2<PERIODIC>(pi.x, pi.y, pi.z, pj, Lx, Ly, Lz, dx, dy, dz);
+    const double q2i = __dmul_rn(r2, hi21);                                   // dens.F90:675
+    if (!(q2i < KF::radkern2) || j == s) return;                              // :679, :650 (exact membership)
+    // rij = sqrt(rij2), rij1 = 1/(rij + epsilon) (dens.F90:688,:746) from one reciprocal square root
+    const double rinv = (r2 > 0.) ? rsqrt(r2) : 0.;
+    const double rij = r2 * rinv;
     const double qi = rij * hi1;
     double wabi, grkerni;
     KF::get_kernel(q2i, qi, wabi, grkerni);
-    const int itypej = abs((int)a.stype[j]);
+    int itypej = IGAS;
+    if (a.multitype) itypej = abs((int)a.stype[j]);
     const int basej = (itypej == IBOUNDARY) ? IGAS : itypej;
     const bool same_type = (itypei == itypej) || (basej == itypei);
     const double pmassj = dp.p.massoftype[itypej];
@@ -97,7 +106,7 @@ __device__ __forceinline__ void dens_pair(double (&v)[32], double (&w)[16], int 
         v[S_GRADH] += dwdhi * pmassj;
         if (GRAV) v[S_GRADSOFT] += KF::dphidh(q2i, qi) * pmassj;
         nneighi++;
-        const double rij1 = 1. / (rij + DBL_EPSILON);
+        const double rij1 = rinv - DBL_EPSILON * rinv * rinv;
         const double rij1grkern = rij1 * grkerni;
         const double runix = dx * rij1grkern * pmassj, runiy = dy * rij1grkern * pmassj, runiz = dz * rij1grkern * pmassj;
         const double4 vj = a.vel4[j];
@@ -118,7 +127,7 @@ __device__ __forceinline__ void dens_pair(double (&v)[32], double (&w)[16], int 
         if (MHD && gas_gas) {
             const double pmassi = dp.p.massoftype[itypei];
             const double rhoi = rhoh_d(hi, pmassi, dp.p.hfact);
-            const double rhoj = rhoh_d(a.pos4[j].w, pmassj, dp.p.hfact);
+            const double rhoj = rhoh_d(pj.w, pmassj, dp.p.hfact);
             const double4 bj = a.bev4[j];
             const double dBx = bi.x * rhoi - bj.x * rhoj, dBy = bi.y * rhoi - bj.y * rhoj, dBz = bi.z * rhoi - bj.z * rhoj;
             w[B_DIVB] += dBx * runix + dBy * runiy + dBz * runiz;
@@ -148,13 +157,16 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
     WarpShared &ws = wsh[wib];
     double (*fin)[FINROW] = finbuf[wib];
     const int gwarp = blockIdx.x * 4 + wib;
-    int *list = a.scratch + (size_t)gwarp * a.scratch_per_warp;
+    Staged st;
+    st.pos = a.stage_pos + (size_t)gwarp * a.scratch_per_warp;
+    st.idx = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;
     const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
-    const double radkern = KF::radkern, radkern2 = KF::radkern2;
+    const double radkern = KF::radkern;
+    const double halfLmin = 0.5 * fmin(Lx, fmin(Ly, Lz));
     const bool use_da = dp.nalpha > 1;
     const unsigned lt_mask = (1u << lane) - 1;
     // per-warp statistics (dens.F90:104-106)
-    unsigned long long st_pairs = 0, st_trial = 0, st_ncalc = 0, st_nact = 0, st_np = 0, st_nwalk = 0;
+    unsigned long long st_pairs = 0, st_trial = 0, st_ncalc = 0, st_nact = 0, st_np = 0, st_nwalk = 0, st_surv = 0;
     int st_maxact = 0, st_maxtrial = 0;
     double st_rhomax = 0.;
 
@@ -165,11 +177,20 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
         if (cellid >= a.ncells) break;
         const Cell cell = a.cells[cellid];
         if (cell.active == 0) continue;                              // dens.F90:302
+        const double cx = 0.5 * (cell.lo[0] + cell.hi[0]), cy = 0.5 * (cell.lo[1] + cell.hi[1]), cz = 0.5 * (cell.lo[2] + cell.hi[2]);
+        const double halfext = 0.5 * fmax(cell.hi[0] - cell.lo[0], fmax(cell.hi[1] - cell.lo[1], cell.hi[2] - cell.lo[2]));
+        float tlo[3], thi[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { tlo[k] = __double2float_rd(cell.lo[k]); thi[k] = __double2float_ru(cell.hi[k]); }
         double hmax_list = cell.hmax * a.margin;
         double rcut_list = radkern * hmax_list;
-        int nlist = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, cell.lo, cell.hi, rcut_list, radkern, Lx, Ly, Lz, list, a.scratch_per_warp, ws.stack);
+        // the FP32 filter works on nearest images relative to the cell centre: only valid while the search sphere of every
+        // target stays inside half a box length; otherwise every candidate goes to the exact test
+        bool wide = PERIODIC && (halfext + rcut_list >= 0.999 * halfLmin);
+        bool ok = warp_walk_stage<false, PERIODIC>(a.nodes, a.cells, a.ncells, a.pos4, tlo, thi, __double2float_ru(rcut_list), (float)radkern, cx, cy, cz,
+                                                   Lx, Ly, Lz, ws, st, a.scratch_per_warp);
         st_nwalk++;
-        if (nlist < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+        if (!ok) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
 
         int ntar = 0;
         for (int t = 0; t < cell.count; t++) {
@@ -182,22 +203,23 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
             double4 bi = make_double4(0., 0., 0., 0.);
             if (MHD && gasi) bi = a.bev4[s];
             const double pmassi = dp.p.massoftype[itypei];
+            const float xif = (float)(pi.x - cx), yif = (float)(pi.y - cy), zif = (float)(pi.z - cz);
             double h = pi.w;
             const double h_old = h;
             int its = 0;
             double v[32], w[16];
             int nneighi = 0;
-            double rhoi = 0., gradh_sum = 0.;
             bool failed = false;
             while (true) {
                 its++;
                 if (radkern * h > rcut_list) {                       // compute_hmax / redo_neighbours (dens.F90:1275-1289, :343-347)
                     hmax_list = h * a.margin * 1.01;
                     rcut_list = radkern * hmax_list;
-                    nlist = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, cell.lo, cell.hi, rcut_list, radkern, Lx, Ly, Lz, list,
-                                                       a.scratch_per_warp, ws.stack);
+                    wide = PERIODIC && (halfext + rcut_list >= 0.999 * halfLmin);
+                    ok = warp_walk_stage<false, PERIODIC>(a.nodes, a.cells, a.ncells, a.pos4, tlo, thi, __double2float_ru(rcut_list), (float)radkern, cx, cy,
+                                                          cz, Lx, Ly, Lz, ws, st, a.scratch_per_warp);
                     st_nwalk++;
-                    if (nlist < 0) { failed = true; if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+                    if (!ok) { failed = true; if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
                 }
 #pragma unroll
                 for (int k = 0; k < 32; k++) v[k] = 0.;
@@ -205,46 +227,50 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
                 for (int k = 0; k < 16; k++) w[k] = 0.;
                 nneighi = 0;
                 const double hi1 = 1. / h, hi21 = hi1 * hi1;
+                const float lim = wide ? 3.0e38f : prefilter_limit(__double2float_ru(radkern * h), prefilter_slack(st.maxrel));
                 int qhead = 0, qcount = 0;
-                for (int c0 = 0; c0 < nlist; c0 += 32) {
-                    const int idx = c0 + lane;
-                    bool pass = false;
-                    int j = 0;
-                    double dx = 0., dy = 0., dz = 0., r2 = 0.;
-                    if (idx < nlist) {
-                        j = list[idx];
-                        const double4 pj = a.pos4[j];
-                        r2 = pair_r2<PERIODIC>(pi.x, pi.y, pi.z, pj, Lx, Ly, Lz, dx, dy, dz);
-                        const double q2i = __dmul_rn(r2, hi21);                       // dens.F90:675
-                        pass = (q2i < radkern2) && (j != s);                          // :679, :650
-                    }
-                    const unsigned m = __ballot_sync(FULLMASK, pass);
-                    if (pass) {
-                        const int pos = (qhead + qcount + __popc(m & lt_mask)) & (QRING - 1);
-                        ws.qj[pos] = j; ws.qdx[pos] = dx; ws.qdy[pos] = dy; ws.qdz[pos] = dz; ws.qr2[pos] = r2;
-                    }
-                    qcount += __popc(m);
+                const int nlist = st.n;
+                for (int c0 = 0; c0 < nlist; c0 += 64) {
+                    // two chunks per trip: both 16-byte records are in flight before either is used
+                    const int i0 = c0 + lane, i1 = c0 + 32 + lane;
+                    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+                    if (i0 < nlist) r0 = st.pos[i0];
+                    if (i1 < nlist) r1 = st.pos[i1];
+                    const float ax = xif - r0.x, ay = yif - r0.y, az = zif - r0.z;
+                    const float bx = xif - r1.x, by = yif - r1.y, bz = zif - r1.z;
+                    const bool p0 = (i0 < nlist) && (fmaf(az, az, fmaf(ay, ay, ax * ax)) < lim);
+                    const bool p1 = (i1 < nlist) && (fmaf(bz, bz, fmaf(by, by, bx * bx)) < lim);
+                    const unsigned m0 = __ballot_sync(FULLMASK, p0), m1 = __ballot_sync(FULLMASK, p1);
+                    if (p0) ws.qj[(qhead + qcount + __popc(m0 & lt_mask)) & (QRING - 1)] = st.idx[i0];
+                    qcount += __popc(m0);
                     __syncwarp();
                     if (qcount >= 32) {
-                        const int e = (qhead + lane) & (QRING - 1);
-                        dens_pair<K, MHD, GRAV>(v, w, nneighi, ws.qj[e], ws.qdx[e], ws.qdy[e], ws.qdz[e], ws.qr2[e], h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp,
-                                                use_da);
-                        qhead = (qhead + 32) & (QRING - 1);
-                        qcount -= 32;
+                        dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, ws.qj[(qhead + lane) & (QRING - 1)], s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a,
+                                                          dp, use_da, Lx, Ly, Lz);
+                        qhead = (qhead + 32) & (QRING - 1); qcount -= 32; st_surv += 32;
+                        __syncwarp();
+                    }
+                    if (p1) ws.qj[(qhead + qcount + __popc(m1 & lt_mask)) & (QRING - 1)] = st.idx[i1];
+                    qcount += __popc(m1);
+                    __syncwarp();
+                    if (qcount >= 32) {
+                        dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, ws.qj[(qhead + lane) & (QRING - 1)], s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a,
+                                                          dp, use_da, Lx, Ly, Lz);
+                        qhead = (qhead + 32) & (QRING - 1); qcount -= 32; st_surv += 32;
                         __syncwarp();
                     }
                 }
-                if (lane < qcount) {
-                    const int e = (qhead + lane) & (QRING - 1);
-                    dens_pair<K, MHD, GRAV>(v, w, nneighi, ws.qj[e], ws.qdx[e], ws.qdy[e], ws.qdz[e], ws.qr2[e], h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp, use_da);
-                }
+                if (lane < qcount)
+                    dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, ws.qj[(qhead + lane) & (QRING - 1)], s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp,
+                                                      use_da, Lx, Ly, Lz);
+                st_surv += qcount;
                 __syncwarp();
                 st_trial += (unsigned long long)nlist;
                 // finish_rhosum + finish_cell (dens.F90:1470-1507, :1401-1462)
                 const double rho_sum = warp_sum(v[S_RHO]);
-                gradh_sum = warp_sum(v[S_GRADH]);
+                const double gradh_sum = warp_sum(v[S_GRADH]);
                 const double hi31 = hi1 * hi21, hi41 = hi21 * hi21;
-                rhoi = KF::cnormk * (rho_sum + KF::wab0 * pmassi) * hi31;
+                const double rhoi = KF::cnormk * (rho_sum + KF::wab0 * pmassi) * hi31;
                 const double gradhi = KF::cnormk * (gradh_sum + KF::gradh0 * pmassi) * hi41;
                 const double rhohi = rhoh_d(h, pmassi, dp.p.hfact);
                 const double dhdrhoi = -h / (3. * rhohi);
@@ -267,6 +293,7 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
                 h = hnew;
             }
             if (failed) continue;
+            const int nlist = st.n;
             // ---- totals of this particle -> shared memory; store_results runs lane-parallel after the target loop ----
             int nn = nneighi;
 #pragma unroll
@@ -363,6 +390,7 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
     if (lane == 0) {
         atomicAdd(&a.cnt[CNT_NPAIRS], st_pairs); atomicAdd(&a.cnt[CNT_NTRIAL], st_trial); atomicAdd(&a.cnt[CNT_NCALC], st_ncalc);
         atomicAdd(&a.cnt[CNT_NACT], st_nact); atomicAdd(&a.cnt[CNT_NP], st_np); atomicAdd(&a.cnt[CNT_NWALK], st_nwalk);
+        atomicAdd(&a.cnt[CNT_NSURV], st_surv);
         atomicMax(&a.cnt[CNT_MAXACT], (unsigned long long)st_maxact); atomicMax(&a.cnt[CNT_MAXTRIAL], (unsigned long long)st_maxtrial);
         atomic_max_pos(&a.dscal[DS_RHOMAX], st_rhomax);
     }
@@ -406,18 +434,19 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
         if (bps < 1) bps = 1;
     }
     const int grid = c->numSMs * bps;
-    CUDA_TRY(c, c->scratch.ensure((size_t)grid * 4 * c->scratch_per_warp));
+    CUDA_TRY(c, c->stage_pos.ensure((size_t)grid * 4 * c->scratch_per_warp)); CUDA_TRY(c, c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp));
     k_gather_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->vxyzu.p, c->fxyzu.p, c->fext.p, c->Bevol.p, c->hp.nvu, p.mhd, c->pos4.p, c->vel4.p,
                                                         c->acc4.p, c->bev4.p, c->hnew.p, c->s_nneigh.p);
     c->launches++;
     CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->dscal.p + DS_RHOMAX, 0, sizeof(double), c->stream));
     DensArgs a;
-    a.nodes = c->nodes.p; a.cells = c->cells.p; a.ncells = (int)c->ncells;
+    a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.acc4 = c->acc4.p; a.bev4 = c->bev4.p; a.stype = c->stype.p; a.perm = c->perm.p;
     a.hnew = c->hnew.p; a.s_gradh = c->s_gradh.p; a.s_divv = c->s_divv.p; a.s_dvdx = c->s_dvdx.p; a.s_alpha3 = c->s_alpha3.p;
     a.s_divcurlB = c->s_divcurlB.p; a.s_nneigh = c->s_nneigh.p;
-    a.scratch = c->scratch.p; a.scratch_per_warp = c->scratch_per_warp; a.cnt = c->counters.p; a.dscal = c->dscal.p;
+    a.stage_pos = c->stage_pos.p; a.stage_idx = c->stage_idx.p; a.multitype = c->multitype ? 1 : 0; a.hmax_global = 0.;
+    a.scratch_per_warp = c->scratch_per_warp; a.cnt = c->counters.p; a.dscal = c->dscal.p;
     a.margin = c->list_margin; a.icall = icall;
     cudaEventRecord(c->ev[8], c->stream);
     if (p.kernel == 0) { if (p.periodic) dispatch_density2<0, true>(c, a, grid); else dispatch_density2<0, false>(c, a, grid); }

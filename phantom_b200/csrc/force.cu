@@ -14,10 +14,11 @@
 namespace {
 
 struct ForceArgs {
-    const TreeNode *nodes; const Cell *cells; int ncells;
+    const TreeNodeF *nodes; const Cell *cells; int ncells;
+    float4 *stage_pos; int *stage_idx; int multitype;
     const double4 *pos4, *vel4, *recC, *recD, *recE; const double2 *hinv; const int8_t *stype; const int *perm;
     double4 *s_fxyzu, *s_dB; float *s_divvf, *s_divBsymm; int *s_done;
-    int *scratch; int scratch_per_warp; unsigned long long *cnt; double *dscal;
+    int scratch_per_warp; unsigned long long *cnt; double *dscal;
     int icall;
 };
 
@@ -73,22 +74,29 @@ __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const 
     s_done[s] = 0;
 }
 
-template <int K, bool MHD>
-__device__ __forceinline__ void force_pair(double (&f)[16], double &vsigmax, int j, double dx, double dy, double dz, double r2, double hi, double hi1,
-                                           double hi21, bool gasi, const double4 &vi, const double4 &Ci, const double4 &Di, const double4 &Ei,
-                                           const ForceArgs &a, const DevParams &dp)
+// pair body: lane = one prefilter survivor j; exact membership test first (force.F90:1271-1287), then compute_forces
+template <int K, bool PERIODIC, bool MHD>
+__device__ __forceinline__ void force_pair(double (&f)[16], double &vsigmax, int &npair, int j, int s, const double4 &pi, double hi, double hi1, double hi21,
+                                           bool gasi, const double4 &vi, const double4 &Ci, const double4 &Di, const double4 &Ei, const ForceArgs &a,
+                                           const DevParams &dp, double Lx, double Ly, double Lz)
 {
     typedef SphKern<K> KF;
     const sphgpu_params &p = dp.p;
+    const double4 pj = a.pos4[j];
     const double2 hj = a.hinv[j];
+    double dx, dy, dz;
+    const double r2 = pair_r2<PERIODIC>(pi.x, pi.y, pi.z, pj, Lx, Ly, Lz, dx, dy, dz);
     const double hj1 = hj.x, hj21 = hj.y;
-    const double q2i = r2 * hi21, q2j = r2 * hj21;
+    const double q2i = __dmul_rn(r2, hi21), q2j = __dmul_rn(r2, hj21);        // force.F90:1272, :1285
+    if (!(q2i < KF::radkern2 || q2j < KF::radkern2) || j == s) return;        // :1287, :1230
+    npair++;
     double rij1, rij;
-    if (r2 > DBL_MIN) { rij1 = 1. / sqrt(r2); rij = r2 * rij1; } else { rij1 = 0.; rij = 0.; }   // force.F90:1293-1299
+    if (r2 > DBL_MIN) { rij1 = rsqrt(r2); rij = r2 * rij1; } else { rij1 = 0.; rij = 0.; }   // force.F90:1293-1299
     const double qi = rij * hi1;
     const double4 Cj = a.recC[j], Dj = a.recD[j];
     const double4 vj = a.vel4[j];
-    const int itypej = abs((int)a.stype[j]);
+    int itypej = IGAS;
+    if (a.multitype) itypej = abs((int)a.stype[j]);
     const bool gasj = (itypej == IGAS || itypej == IBOUNDARY);
     const double pmassj = Dj.z, pmassi = Di.z;
     const double grkerni = (q2i < KF::radkern2) ? KF::grkern(q2i, qi) * Di.y : 0.;
@@ -195,12 +203,16 @@ __global__ void __launch_bounds__(128) k_force(const ForceArgs a, const __grid_c
     WarpShared &ws = wsh[wib];
     double (*fin)[FROW] = finbuf[wib];
     const int gwarp = blockIdx.x * 4 + wib;
-    int *list = a.scratch + (size_t)gwarp * a.scratch_per_warp;
+    Staged st;
+    st.pos = a.stage_pos + (size_t)gwarp * a.scratch_per_warp;
+    st.idx = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;
     const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
+    const double halfLmin = 0.5 * fmin(Lx, fmin(Ly, Lz));
     const unsigned lt_mask = (1u << lane) - 1;
     const sphgpu_params &p = dp.p;
     unsigned long long st_pairs = 0, st_trial = 0;
     double st_dtc = 1.e29, st_dtf = 1.e29, st_dtmin = 1.e29, st_dtmax = 0.;
+    const float hmax_global = (a.ncells > 1) ? fmaxf(a.nodes[0].hmax[0], a.nodes[0].hmax[1]) : 0.f;
 
     while (true) {
         int cellid = 0;
@@ -209,9 +221,18 @@ __global__ void __launch_bounds__(128) k_force(const ForceArgs a, const __grid_c
         if (cellid >= a.ncells) break;
         const Cell cell = a.cells[cellid];
         if (cell.active == 0) continue;                              // force.F90:509
+        const double cx = 0.5 * (cell.lo[0] + cell.hi[0]), cy = 0.5 * (cell.lo[1] + cell.hi[1]), cz = 0.5 * (cell.lo[2] + cell.hi[2]);
+        const double halfext = 0.5 * fmax(cell.hi[0] - cell.lo[0], fmax(cell.hi[1] - cell.lo[1], cell.hi[2] - cell.lo[2]));
+        float tlo[3], thi[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { tlo[k] = __double2float_rd(cell.lo[k]); thi[k] = __double2float_ru(cell.hi[k]); }
         const double rcut = KF::radkern * cell.hmax;
-        const int nlist = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, cell.lo, cell.hi, rcut, KF::radkern, Lx, Ly, Lz, list, a.scratch_per_warp, ws.stack);
-        if (nlist < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+        const bool wide = PERIODIC && (halfext + KF::radkern * fmax(cell.hmax, (double)hmax_global) >= 0.999 * halfLmin);
+        const bool ok = warp_walk_stage<true, PERIODIC>(a.nodes, a.cells, a.ncells, a.pos4, tlo, thi, __double2float_ru(rcut), (float)KF::radkern, cx, cy, cz,
+                                                        Lx, Ly, Lz, ws, st, a.scratch_per_warp);
+        if (!ok) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+        const int nlist = st.n;
+        const float slack = prefilter_slack(st.maxrel);
         int ntar = 0;
         for (int t = 0; t < cell.count; t++) {
             const int s = cell.start + t;
@@ -224,45 +245,48 @@ __global__ void __launch_bounds__(128) k_force(const ForceArgs a, const __grid_c
             const double h = pi.w;
             const double2 hv = a.hinv[s];
             const double hi1 = hv.x, hi21 = hv.y;
+            const float xif = (float)(pi.x - cx), yif = (float)(pi.y - cy), zif = (float)(pi.z - cz);
+            const float lim = wide ? 3.0e38f : prefilter_limit(__double2float_ru(KF::radkern * h), slack);
             double f[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) f[k] = 0.;
             double vsigmax = 0.;
             int npair = 0;
             int qhead = 0, qcount = 0;
-            for (int c0 = 0; c0 < nlist; c0 += 32) {
-                const int idx = c0 + lane;
-                bool pass = false;
-                int j = 0;
-                double dx = 0., dy = 0., dz = 0., r2 = 0.;
-                if (idx < nlist) {
-                    j = list[idx];
-                    const double4 pj = a.pos4[j];
-                    r2 = pair_r2<PERIODIC>(pi.x, pi.y, pi.z, pj, Lx, Ly, Lz, dx, dy, dz);
-                    const double q2i = __dmul_rn(r2, hi21), q2j = __dmul_rn(r2, a.hinv[j].y);      // force.F90:1272, :1285
-                    pass = (q2i < KF::radkern2 || q2j < KF::radkern2) && (j != s);                 // :1287, :1230
-                }
-                const unsigned m = __ballot_sync(FULLMASK, pass);
-                if (pass) {
-                    const int pos = (qhead + qcount + __popc(m & lt_mask)) & (QRING - 1);
-                    ws.qj[pos] = j; ws.qdx[pos] = dx; ws.qdy[pos] = dy; ws.qdz[pos] = dz; ws.qr2[pos] = r2;
-                }
-                qcount += __popc(m);
-                npair += __popc(m);
+            for (int c0 = 0; c0 < nlist; c0 += 64) {
+                const int i0 = c0 + lane, i1 = c0 + 32 + lane;
+                float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+                if (i0 < nlist) r0 = st.pos[i0];
+                if (i1 < nlist) r1 = st.pos[i1];
+                const float ax = xif - r0.x, ay = yif - r0.y, az = zif - r0.z;
+                const float bx = xif - r1.x, by = yif - r1.y, bz = zif - r1.z;
+                // symmetric criterion: inside radkern*h_i OR inside radkern*h_j (staged .w), both with the FP32 error slack
+                const float l0 = fmaxf(lim, prefilter_limit(r0.w, slack)), l1 = fmaxf(lim, prefilter_limit(r1.w, slack));
+                const bool p0 = (i0 < nlist) && (fmaf(az, az, fmaf(ay, ay, ax * ax)) < l0);
+                const bool p1 = (i1 < nlist) && (fmaf(bz, bz, fmaf(by, by, bx * bx)) < l1);
+                const unsigned m0 = __ballot_sync(FULLMASK, p0), m1 = __ballot_sync(FULLMASK, p1);
+                if (p0) ws.qj[(qhead + qcount + __popc(m0 & lt_mask)) & (QRING - 1)] = st.idx[i0];
+                qcount += __popc(m0);
                 __syncwarp();
                 if (qcount >= 32) {
-                    const int e = (qhead + lane) & (QRING - 1);
-                    force_pair<K, MHD>(f, vsigmax, ws.qj[e], ws.qdx[e], ws.qdy[e], ws.qdz[e], ws.qr2[e], h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp);
-                    qhead = (qhead + 32) & (QRING - 1);
-                    qcount -= 32;
+                    force_pair<K, PERIODIC, MHD>(f, vsigmax, npair, ws.qj[(qhead + lane) & (QRING - 1)], s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz);
+                    qhead = (qhead + 32) & (QRING - 1); qcount -= 32;
+                    __syncwarp();
+                }
+                if (p1) ws.qj[(qhead + qcount + __popc(m1 & lt_mask)) & (QRING - 1)] = st.idx[i1];
+                qcount += __popc(m1);
+                __syncwarp();
+                if (qcount >= 32) {
+                    force_pair<K, PERIODIC, MHD>(f, vsigmax, npair, ws.qj[(qhead + lane) & (QRING - 1)], s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz);
+                    qhead = (qhead + 32) & (QRING - 1); qcount -= 32;
                     __syncwarp();
                 }
             }
-            if (lane < qcount) {
-                const int e = (qhead + lane) & (QRING - 1);
-                force_pair<K, MHD>(f, vsigmax, ws.qj[e], ws.qdx[e], ws.qdy[e], ws.qdz[e], ws.qr2[e], h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp);
-            }
+            if (lane < qcount)
+                force_pair<K, PERIODIC, MHD>(f, vsigmax, npair, ws.qj[(qhead + lane) & (QRING - 1)], s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz);
             __syncwarp();
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) npair += __shfl_xor_sync(FULLMASK, npair, sft);
             st_pairs += npair; st_trial += nlist;
             vsigmax = warp_max(vsigmax);
             const double tot = warp_transpose_reduce<16>(f);         // lane L holds slot L>>1
@@ -397,7 +421,7 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     else if (p.kernel == 0 && p.periodic && p.mhd) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force<0, true, true>, 128, 0);
     if (bps < 1) bps = 1;
     const int grid = c->numSMs * bps;
-    CUDA_TRY(c, c->scratch.ensure((size_t)grid * 4 * c->scratch_per_warp));
+    CUDA_TRY(c, c->stage_pos.ensure((size_t)grid * 4 * c->scratch_per_warp)); CUDA_TRY(c, c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp));
     CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
     const double init[4] = {1.e29, 1.e29, 1.e29, 0.};
     CUDA_TRY(c, cudaMemcpyAsync(c->dscal.p + DS_DTCOURANT, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
@@ -406,10 +430,11 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
                                                        c->vel4.p, c->frecC.p, c->frecD.p, c->frecE.p, hinv, c->s_nneigh.p, c->hp, c->counters.p);
     c->launches++;
     ForceArgs a;
-    a.nodes = c->nodes.p; a.cells = c->cells.p; a.ncells = (int)c->ncells;
+    a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.recC = c->frecC.p; a.recD = c->frecD.p; a.recE = c->frecE.p; a.hinv = hinv; a.stype = c->stype.p; a.perm = c->perm.p;
     a.s_fxyzu = c->s_fxyzu.p; a.s_dB = c->s_dB.p; a.s_divvf = c->s_divvf.p; a.s_divBsymm = c->s_divBsymm.p; a.s_done = c->s_nneigh.p;
-    a.scratch = c->scratch.p; a.scratch_per_warp = c->scratch_per_warp; a.cnt = c->counters.p; a.dscal = c->dscal.p; a.icall = icall;
+    a.stage_pos = c->stage_pos.p; a.stage_idx = c->stage_idx.p; a.multitype = c->multitype ? 1 : 0;
+    a.scratch_per_warp = c->scratch_per_warp; a.cnt = c->counters.p; a.dscal = c->dscal.p; a.icall = icall;
     cudaEventRecord(c->ev[10], c->stream);
     if (p.kernel == 0) { if (p.periodic) dispatch_force<0, true>(c, a, grid); else dispatch_force<0, false>(c, a, grid); }
     else { if (p.periodic) dispatch_force<1, true>(c, a, grid); else dispatch_force<1, false>(c, a, grid); }

@@ -92,13 +92,15 @@ __global__ void k_keys(int64_t n, const double *__restrict__ xyzh, double x0, do
 
 __global__ void k_gather_pos(int64_t nlive, const int *__restrict__ perm, const double *__restrict__ xyzh, const int8_t *__restrict__ iphase,
                              double4 *__restrict__ pos4, int8_t *__restrict__ stype, const unsigned long long *__restrict__ keys,
-                             unsigned char *__restrict__ cpl)
+                             unsigned char *__restrict__ cpl, unsigned long long *cnt)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nlive) return;
     const int i = perm[s];
     pos4[s] = reinterpret_cast<const double4 *>(xyzh)[i];
-    stype[s] = iphase[i];
+    const int8_t ph = iphase[i];
+    stype[s] = ph;
+    if (ph != IGAS && ph != -IGAS) cnt[CNT_MULTITYPE] = 1ull;
     // common leading octal digits with the previous key (0..21)
     unsigned char c = 0;
     if (s > 0) {
@@ -181,7 +183,7 @@ __device__ __forceinline__ int delta_k(const unsigned long long *keys, int M, in
     return __clzll((long long)(a ^ b));
 }
 
-__global__ void k_radix_tree(int M, const unsigned long long *__restrict__ keys, TreeNode *__restrict__ nodes, Cell *__restrict__ cells)
+__global__ void k_radix_tree(int M, const unsigned long long *__restrict__ keys, TreeNode *__restrict__ nodes, TreeNodeF *__restrict__ nodesf, Cell *__restrict__ cells)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M - 1) return;
@@ -205,11 +207,18 @@ __global__ void k_radix_tree(int M, const unsigned long long *__restrict__ keys,
     if (lo == gamma) { cl = ~gamma; cells[gamma].parent = i; } else { cl = gamma; nodes[gamma].parent = i; }
     if (hi == gamma + 1) { cr = ~(gamma + 1); cells[gamma + 1].parent = i; } else { cr = gamma + 1; nodes[gamma + 1].parent = i; }
     nodes[i].child[0] = cl; nodes[i].child[1] = cr;
+    nodesf[i].child[0] = cl; nodesf[i].child[1] = cr;
     if (i == 0) nodes[0].parent = -1;
 }
 
 // bottom-up refit: the second thread to arrive at a node merges its two child boxes into the grandparent slot
-__global__ void k_refit(int M, const Cell *__restrict__ cells, TreeNode *nodes, int *flags)
+__device__ __forceinline__ void write_nodef(TreeNodeF *nf, int slot, const double *lo, const double *hi, double hmax)
+{
+    for (int k = 0; k < 3; k++) { nf->lo[slot][k] = __double2float_rd(lo[k]); nf->hi[slot][k] = __double2float_ru(hi[k]); }
+    nf->hmax[slot] = __double2float_ru(hmax);
+}
+
+__global__ void k_refit(int M, const Cell *__restrict__ cells, TreeNode *nodes, TreeNodeF *nodesf, int *flags)
 {
     int cidx = blockIdx.x * blockDim.x + threadIdx.x;
     if (cidx >= M) return;
@@ -221,6 +230,7 @@ __global__ void k_refit(int M, const Cell *__restrict__ cells, TreeNode *nodes, 
         const int slot = (nd->child[0] == me) ? 0 : 1;
         for (int k = 0; k < 3; k++) { nd->lo[slot][k] = lo[k]; nd->hi[slot][k] = hi[k]; }
         nd->hmax[slot] = hmax;
+        write_nodef(&nodesf[parent], slot, lo, hi, hmax);
         __threadfence();
         if (atomicAdd(&flags[parent], 1) == 0) return;     // first arrival: sibling not ready yet
         __threadfence();
@@ -259,7 +269,7 @@ int tree_refit_hmax(sphgpu_ctx *c)
     LAUNCH(c, k_cell_hmax, nblk(M, 128), 128, M, c->cells.p, c->pos4.p);
     if (M > 1) {
         CUDA_TRY(c, cudaMemsetAsync(c->nodeflag.p, 0, sizeof(int) * (size_t)M, c->stream));
-        LAUNCH(c, k_refit, nblk(M, 128), 128, M, c->cells.p, c->nodes.p, c->nodeflag.p);
+        LAUNCH(c, k_refit, nblk(M, 128), 128, M, c->cells.p, c->nodes.p, c->nodesf.p, c->nodeflag.p);
     }
     CUDA_TRY(c, cudaGetLastError());
     return SPHGPU_OK;
@@ -310,7 +320,7 @@ int tree_build(sphgpu_ctx *c)
     c->launches += 8;
     CUDA_TRY(c, c->pos4.ensure(n)); CUDA_TRY(c, c->stype.ensure(n)); CUDA_TRY(c, c->cpl.ensure(n));
     CUDA_TRY(c, c->cellflag.ensure(n)); CUDA_TRY(c, c->cellid_scan.ensure(n));
-    LAUNCH(c, k_gather_pos, nblk(nlive, 256), 256, nlive, c->perm.p, c->xyzh.p, c->iphase.p, c->pos4.p, c->stype.p, c->keys.p, c->cpl.p);
+    LAUNCH(c, k_gather_pos, nblk(nlive, 256), 256, nlive, c->perm.p, c->xyzh.p, c->iphase.p, c->pos4.p, c->stype.p, c->keys.p, c->cpl.p, c->counters.p);
     LAUNCH(c, k_cell_flags, nblk(nlive, 128), 128, nlive, c->cpl.p, c->max_cell, c->cellflag.p);
     tbb = c->cubtemp.cap;
     CUDA_TRY(c, cub::DeviceScan::ExclusiveSum(c->cubtemp.p, tbb, c->cellflag.p, c->cellid_scan.p, (int)nlive, c->stream));
@@ -320,15 +330,16 @@ int tree_build(sphgpu_ctx *c)
     CUDA_TRY(c, cudaMemcpyAsync(&lastscan, c->cellid_scan.p + (nlive - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     const int64_t M = (int64_t)lastscan + lastflag;
+    { unsigned long long mt = 0; CUDA_TRY(c, cudaMemcpy(&mt, c->counters.p + CNT_MULTITYPE, sizeof mt, cudaMemcpyDeviceToHost)); c->multitype = mt != 0; }
     c->ncells = M;
-    CUDA_TRY(c, c->cells.ensure(M)); CUDA_TRY(c, c->cellkeys.ensure(M)); CUDA_TRY(c, c->nodes.ensure(M)); CUDA_TRY(c, c->nodeflag.ensure(M));
+    CUDA_TRY(c, c->cells.ensure(M)); CUDA_TRY(c, c->cellkeys.ensure(M)); CUDA_TRY(c, c->nodes.ensure(M)); CUDA_TRY(c, c->nodesf.ensure(M)); CUDA_TRY(c, c->nodeflag.ensure(M));
     LAUNCH(c, k_cell_starts, nblk(nlive, 256), 256, nlive, c->cellflag.p, c->cellid_scan.p, c->cells.p);
     LAUNCH(c, k_cell_props, nblk(M, 128), 128, M, nlive, c->cells.p, c->pos4.p, c->stype.p, c->keys.p, c->cellkeys.p,
            p.set_boundaries_to_active, p.dust, p.ind_timesteps);
     if (M > 1) {
-        LAUNCH(c, k_radix_tree, nblk(M - 1, 128), 128, (int)M, c->cellkeys.p, c->nodes.p, c->cells.p);
+        LAUNCH(c, k_radix_tree, nblk(M - 1, 128), 128, (int)M, c->cellkeys.p, c->nodes.p, c->nodesf.p, c->cells.p);
         CUDA_TRY(c, cudaMemsetAsync(c->nodeflag.p, 0, sizeof(int) * (size_t)M, c->stream));
-        LAUNCH(c, k_refit, nblk(M, 128), 128, (int)M, c->cells.p, c->nodes.p, c->nodeflag.p);
+        LAUNCH(c, k_refit, nblk(M, 128), 128, (int)M, c->cells.p, c->nodes.p, c->nodesf.p, c->nodeflag.p);
     }
     CUDA_TRY(c, cudaGetLastError());
     c->tree_valid = true;
