@@ -79,7 +79,7 @@ struct sphgpu_ctx {
     double ms_phase[4] = {0, 0, 0, 0};
     double ms_kernel[2] = {0, 0};   // k_density, k_force alone (CUDA events on the launching stream)
     // tuning
-    int max_cell = 16;
+    int max_cell = 32;
     double list_margin = 1.02;
     int scratch_per_warp = 8192;
     // ---- canonical (original particle order) device arrays = device mirror of part.F90 ----

@@ -2,11 +2,11 @@
 // (src/main/dens.F90:117-568) with get_density_sums (:578-857), finish_cell/finish_rhosum (:1382-1507),
 // compute_hmax (:1275-1289) and store_results (:1511-1681).
 //
-// Mapping to the hardware: a persistent grid of warps pulls leaf cells from an atomic work counter; per cell the
-// warp walks the tree once (walk.cuh) and then iterates every active particle of the cell to convergence.  Lanes
-// run over *neighbour candidates*; accepted pairs are compacted so that the ~90-flop FP64 pair body runs with
-// full warps; the 28 (+10 MHD) per-particle sums live in registers as per-lane partials and are combined
-// with a 31-shuffle transpose reduction.  The kernel is FP64-pipe bound.
+// Mapping to the hardware: a persistent grid of warps pulls leaf cells (<= 32 particles) from an atomic work counter;
+// per cell the warp walks the tree and stages the candidates once (walk.cuh), builds per-target FP32 hit masks
+// (lane = candidate), then switches to lane = TARGET: each lane walks its own hit masks and accumulates its own
+// 28 (+10 MHD) FP64 sums in registers -- no cross-lane reduction.  The h-rho Newton-Raphson step, the convergence
+// test and store_results are lane-parallel.  The kernel is FP64-pipe bound.
 //
 // Semantics kept from the reference: self term added analytically (dens.F90:1491-1492), neighbours of the same
 // (base) type only (:717-723), iteration per particle with clamp to +-20% and the tolh/omega test (:1425-1440),
@@ -34,9 +34,6 @@ enum {  // slots of the per-lane partial sums (order of dens.F90:51-95)
     S_RHO = 0, S_GRADH, S_GRADSOFT, S_DIVV, S_DVXDX, S_DVXDY, S_DVXDZ, S_DVYDX, S_DVYDY, S_DVYDZ, S_DVZDX, S_DVZDY, S_DVZDZ,
     S_DAXDX, S_DAXDY, S_DAXDZ, S_DAYDX, S_DAYDY, S_DAYDZ, S_DAZDX, S_DAZDY, S_DAZDZ, S_RXX, S_RXY, S_RXZ, S_RYY, S_RYZ, S_RZZ, S_RHODUST
 };
-#define MAXCELL 16     // leaf cells hold at most 16 particles (ctx->max_cell is clamped to this)
-#define FINROW 49      // odd row length: lane-per-target reads are bank-conflict free
-enum { F_H = 42, F_NN = 43, F_S = 44 };
 enum { B_DIVB = 0, B_DBXDX, B_DBXDY, B_DBXDZ, B_DBYDX, B_DBYDY, B_DBYDZ, B_DBZDX, B_DBZDY, B_DBZDZ };
 
 __global__ void k_gather_dens(int64_t nlive, const int *__restrict__ perm, const double *__restrict__ vxyzu, const double *__restrict__ fxyzu,
@@ -76,9 +73,9 @@ __global__ void k_scatter_dens(int64_t nlive, const int *__restrict__ perm, cons
     if (mhd) for (int k = 0; k < 4; k++) divcurlB[4 * (size_t)i + k] = s_divcurlB[4 * (size_t)s + k];
 }
 
-// pair body: lane = one prefilter survivor j.  Re-evaluates the exact reference test, then the sums of get_density_sums.
+// pair body: lane = target, j = this lane's next neighbour candidate.  Exact reference test first, then get_density_sums.
 template <int K, bool PERIODIC, bool MHD, bool GRAV>
-__device__ __forceinline__ void dens_pair(double (&v)[32], double (&w)[16], int &nneighi, int j, int s, const double4 &pi, double hi, double hi1,
+__device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[10], int &nneighi, int j, int s, const double4 &pi, double hi, double hi1,
                                           double hi21, int itypei, bool gasi, const double4 &vi, const double4 &ai, const double4 &bi,
                                           const DensArgs &a, const DevParams &dp, bool use_da, double Lx, double Ly, double Lz)
 {
@@ -152,10 +149,8 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
 {
     typedef SphKern<K> KF;
     __shared__ WarpShared wsh[4];
-    __shared__ double finbuf[4][MAXCELL][FINROW];    // per-target totals, finalised lane-parallel once the cell is done
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     WarpShared &ws = wsh[wib];
-    double (*fin)[FINROW] = finbuf[wib];
     const int gwarp = blockIdx.x * 4 + wib;
     Staged st;
     st.pos = a.stage_pos + (size_t)gwarp * a.scratch_per_warp;
@@ -164,8 +159,7 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
     const double radkern = KF::radkern;
     const double halfLmin = 0.5 * fmin(Lx, fmin(Ly, Lz));
     const bool use_da = dp.nalpha > 1;
-    const unsigned lt_mask = (1u << lane) - 1;
-    // per-warp statistics (dens.F90:104-106)
+    // per-lane statistics (dens.F90:104-106), reduced once at kernel exit
     unsigned long long st_pairs = 0, st_trial = 0, st_ncalc = 0, st_nact = 0, st_np = 0, st_nwalk = 0, st_surv = 0;
     int st_maxact = 0, st_maxtrial = 0;
     double st_rhomax = 0.;
@@ -182,6 +176,23 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
         float tlo[3], thi[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) { tlo[k] = __double2float_rd(cell.lo[k]); thi[k] = __double2float_ru(cell.hi[k]); }
+        // ---- lane = target: start_cell (dens.F90:1293-1378)
+        const int s = cell.start + min(lane, cell.count - 1);
+        bool act = false, gasi = true, dusti = false; int itypei = IGAS;
+        if (lane < cell.count) get_partinfo_d(a.stype[s], dp.p.set_boundaries_to_active, dp.p.dust, act, gasi, dusti, itypei);
+        const double4 pi = a.pos4[s];
+        const double4 vi = a.vel4[s], ai = a.acc4[s];
+        double4 bi = make_double4(0., 0., 0., 0.);
+        if (MHD && gasi) bi = a.bev4[s];
+        const double pmassi = dp.p.massoftype[itypei];
+        const float xif = (float)(pi.x - cx), yif = (float)(pi.y - cy), zif = (float)(pi.z - cz);
+        double h = pi.w;
+        const double h_old = h;
+        bool conv = !act;                                            // inactive / boundary lanes take no part (dens.F90:1329)
+        bool failed = false;
+        double v[29], w[10];
+        int nneighi = 0, its_lane = 0;
+
         double hmax_list = cell.hmax * a.margin;
         double rcut_list = radkern * hmax_list;
         // the FP32 filter works on nearest images relative to the cell centre: only valid while the search sphere of every
@@ -189,89 +200,58 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
         bool wide = PERIODIC && (halfext + rcut_list >= 0.999 * halfLmin);
         bool ok = warp_walk_stage<false, PERIODIC>(a.nodes, a.cells, a.ncells, a.pos4, tlo, thi, __double2float_ru(rcut_list), (float)radkern, cx, cy, cz,
                                                    Lx, Ly, Lz, ws, st, a.scratch_per_warp);
-        st_nwalk++;
+        st_nwalk += (lane == 0);
         if (!ok) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
 
-        int ntar = 0;
-        for (int t = 0; t < cell.count; t++) {
-            const int s = cell.start + t;
-            bool act, gasi, dusti; int itypei;
-            get_partinfo_d(a.stype[s], dp.p.set_boundaries_to_active, dp.p.dust, act, gasi, dusti, itypei);
-            if (!act) continue;                                      // dens.F90:1329
-            const double4 pi = a.pos4[s];
-            const double4 vi = a.vel4[s], ai = a.acc4[s];
-            double4 bi = make_double4(0., 0., 0., 0.);
-            if (MHD && gasi) bi = a.bev4[s];
-            const double pmassi = dp.p.massoftype[itypei];
-            const float xif = (float)(pi.x - cx), yif = (float)(pi.y - cy), zif = (float)(pi.z - cz);
-            double h = pi.w;
-            const double h_old = h;
-            int its = 0;
-            double v[32], w[16];
-            int nneighi = 0;
-            bool failed = false;
-            while (true) {
-                its++;
-                if (radkern * h > rcut_list) {                       // compute_hmax / redo_neighbours (dens.F90:1275-1289, :343-347)
-                    hmax_list = h * a.margin * 1.01;
-                    rcut_list = radkern * hmax_list;
-                    wide = PERIODIC && (halfext + rcut_list >= 0.999 * halfLmin);
-                    ok = warp_walk_stage<false, PERIODIC>(a.nodes, a.cells, a.ncells, a.pos4, tlo, thi, __double2float_ru(rcut_list), (float)radkern, cx, cy,
-                                                          cz, Lx, Ly, Lz, ws, st, a.scratch_per_warp);
-                    st_nwalk++;
-                    if (!ok) { failed = true; if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
-                }
+        for (int its = 1;; its++) {                                  // local_its (dens.F90:338-373): the cell iterates until every particle converged
+            // compute_hmax / redo_neighbours (dens.F90:1275-1289, :343-347)
+            const double hneed = warp_max(conv ? 0. : h);
+            if (radkern * hneed > rcut_list) {
+                hmax_list = hneed * a.margin * 1.01;
+                rcut_list = radkern * hmax_list;
+                wide = PERIODIC && (halfext + rcut_list >= 0.999 * halfLmin);
+                ok = warp_walk_stage<false, PERIODIC>(a.nodes, a.cells, a.ncells, a.pos4, tlo, thi, __double2float_ru(rcut_list), (float)radkern, cx, cy, cz,
+                                                      Lx, Ly, Lz, ws, st, a.scratch_per_warp);
+                st_nwalk += (lane == 0);
+                if (!ok) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); failed = true; }
+            }
+            if (__any_sync(FULLMASK, failed)) break;
+            const float slack = prefilter_slack(st.maxrel);
+            float lim = 0.f;                                         // converged / inactive targets get an empty mask
+            if (!conv) lim = wide ? 3.0e38f : prefilter_limit(__double2float_ru(radkern * h), slack);
+            ws.tgt[lane] = make_float4(xif, yif, zif, lim);
+            __syncwarp();
+            if (!conv) {
 #pragma unroll
-                for (int k = 0; k < 32; k++) v[k] = 0.;
+                for (int k = 0; k < 29; k++) v[k] = 0.;
 #pragma unroll
-                for (int k = 0; k < 16; k++) w[k] = 0.;
+                for (int k = 0; k < 10; k++) w[k] = 0.;
                 nneighi = 0;
-                const double hi1 = 1. / h, hi21 = hi1 * hi1;
-                const float lim = wide ? 3.0e38f : prefilter_limit(__double2float_ru(radkern * h), prefilter_slack(st.maxrel));
-                int qhead = 0, qcount = 0;
-                const int nlist = st.n;
-                for (int c0 = 0; c0 < nlist; c0 += 64) {
-                    // two chunks per trip: both 16-byte records are in flight before either is used
-                    const int i0 = c0 + lane, i1 = c0 + 32 + lane;
-                    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-                    if (i0 < nlist) r0 = st.pos[i0];
-                    if (i1 < nlist) r1 = st.pos[i1];
-                    const float ax = xif - r0.x, ay = yif - r0.y, az = zif - r0.z;
-                    const float bx = xif - r1.x, by = yif - r1.y, bz = zif - r1.z;
-                    const bool p0 = (i0 < nlist) && (fmaf(az, az, fmaf(ay, ay, ax * ax)) < lim);
-                    const bool p1 = (i1 < nlist) && (fmaf(bz, bz, fmaf(by, by, bx * bx)) < lim);
-                    const unsigned m0 = __ballot_sync(FULLMASK, p0), m1 = __ballot_sync(FULLMASK, p1);
-                    if (p0) ws.qj[(qhead + qcount + __popc(m0 & lt_mask)) & (QRING - 1)] = st.idx[i0];
-                    qcount += __popc(m0);
-                    __syncwarp();
-                    if (qcount >= 32) {
-                        dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, ws.qj[(qhead + lane) & (QRING - 1)], s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a,
-                                                          dp, use_da, Lx, Ly, Lz);
-                        qhead = (qhead + 32) & (QRING - 1); qcount -= 32; st_surv += 32;
-                        __syncwarp();
-                    }
-                    if (p1) ws.qj[(qhead + qcount + __popc(m1 & lt_mask)) & (QRING - 1)] = st.idx[i1];
-                    qcount += __popc(m1);
-                    __syncwarp();
-                    if (qcount >= 32) {
-                        dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, ws.qj[(qhead + lane) & (QRING - 1)], s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a,
-                                                          dp, use_da, Lx, Ly, Lz);
-                        qhead = (qhead + 32) & (QRING - 1); qcount -= 32; st_surv += 32;
-                        __syncwarp();
+                its_lane = its;
+            }
+            const double hi1 = 1. / h, hi21 = hi1 * hi1;
+            const int nlist = st.n;
+            for (int base = 0; base < nlist; base += MAXCHUNK * 32) {
+                const int nchunk = min(MAXCHUNK, (nlist - base + 31) >> 5);
+                build_masks<false>(ws, st, base, nchunk, cell.count, slack);
+                int c = -1; unsigned m = 0u;
+                while (true) {
+                    const int slot = conv ? -1 : next_hit(ws, lane, nchunk, c, m);
+                    if (!__any_sync(FULLMASK, slot >= 0)) break;
+                    if (slot >= 0) {
+                        st_surv++;
+                        dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, st.idx[base + slot], s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp, use_da, Lx,
+                                                          Ly, Lz);
                     }
                 }
-                if (lane < qcount)
-                    dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, ws.qj[(qhead + lane) & (QRING - 1)], s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp,
-                                                      use_da, Lx, Ly, Lz);
-                st_surv += qcount;
                 __syncwarp();
+            }
+            if (!conv) {
                 st_trial += (unsigned long long)nlist;
                 // finish_rhosum + finish_cell (dens.F90:1470-1507, :1401-1462)
-                const double rho_sum = warp_sum(v[S_RHO]);
-                const double gradh_sum = warp_sum(v[S_GRADH]);
                 const double hi31 = hi1 * hi21, hi41 = hi21 * hi21;
-                const double rhoi = KF::cnormk * (rho_sum + KF::wab0 * pmassi) * hi31;
-                const double gradhi = KF::cnormk * (gradh_sum + KF::gradh0 * pmassi) * hi41;
+                const double rhoi = KF::cnormk * (v[S_RHO] + KF::wab0 * pmassi) * hi31;
+                const double gradhi = KF::cnormk * (v[S_GRADH] + KF::gradh0 * pmassi) * hi41;
                 const double rhohi = rhoh_d(h, pmassi, dp.p.hfact);
                 const double dhdrhoi = -h / (3. * rhohi);
                 const double omegai = 1. - dhdrhoi * gradhi;
@@ -282,45 +262,23 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
                 double hnew = h - func * dfdh1;
                 if (hnew > 1.2 * h) hnew = 1.2 * h;
                 else if (hnew < 0.8 * h) hnew = 0.8 * h;
-                bool converged = ((fabs(hnew - h) / h_old) < dp.p.tolh) && (omegai > 0.) && (h > 0.);
-                if (a.icall == 0) converged = true;
-                if (converged) break;
-                if (its >= 100) {                                   // maxdensits, dens.F90:1443-1456
-                    if (lane == 0) { atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_NOCONVERGE); atomicMax(&a.cnt[CNT_ERRID], (unsigned long long)(a.perm[s] + 1)); }
-                    failed = true;
-                    break;
+                conv = ((fabs(hnew - h) / h_old) < dp.p.tolh) && (omegai > 0.) && (h > 0.);
+                if (a.icall == 0) conv = true;
+                if (!conv) {
+                    if (its >= 100) {                               // maxdensits, dens.F90:1443-1456
+                        atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_NOCONVERGE);
+                        atomicMax(&a.cnt[CNT_ERRID], (unsigned long long)(a.perm[s] + 1));
+                        failed = true; conv = true;
+                    } else h = hnew;
                 }
-                h = hnew;
             }
-            if (failed) continue;
-            const int nlist = st.n;
-            // ---- totals of this particle -> shared memory; store_results runs lane-parallel after the target loop ----
-            int nn = nneighi;
-#pragma unroll
-            for (int sft = 16; sft >= 1; sft >>= 1) nn += __shfl_xor_sync(FULLMASK, nn, sft);
-            st_pairs += (unsigned long long)nn * its;
-            nn += 1;   // self
-            const double tot = warp_transpose_reduce<32>(v);
-            fin[ntar][lane] = tot;
-            if (MHD) { const double tb = warp_transpose_reduce<16>(w); if ((lane & 1) == 0) fin[ntar][32 + (lane >> 1)] = tb; }
-            if (lane == 0) { fin[ntar][F_H] = h; fin[ntar][F_NN] = (double)nn; fin[ntar][F_S] = (double)s; }
-            ntar++;
-            __syncwarp();
-            st_ncalc += its; st_nact += nn; st_np += 1;
-            st_maxact = max(st_maxact, nn); st_maxtrial = max(st_maxtrial, nlist);
+            if (__all_sync(FULLMASK, conv)) break;
         }
-        __syncwarp();
-        // ---- store_results (dens.F90:1511-1681), one lane per target ----
-        if (lane < ntar) {
-            const double *rs = fin[lane];
-            const double h = rs[F_H];
-            const int s = (int)rs[F_S];
-            bool act, gasi, dusti; int itypei;
-            get_partinfo_d(a.stype[s], dp.p.set_boundaries_to_active, dp.p.dust, act, gasi, dusti, itypei);
-            const double pmassi = dp.p.massoftype[itypei];
+        // ---- store_results (dens.F90:1511-1681), lane = target ----
+        if (act && !failed) {
             const double hi1 = 1. / h, hi21 = hi1 * hi1, hi31 = hi1 * hi21, hi41 = hi21 * hi21;
-            const double rho = KF::cnormk * (rs[S_RHO] + KF::wab0 * pmassi) * hi31;
-            double gradhi = KF::cnormk * (rs[S_GRADH] + KF::gradh0 * pmassi) * hi41;
+            const double rho = KF::cnormk * (v[S_RHO] + KF::wab0 * pmassi) * hi31;
+            double gradhi = KF::cnormk * (v[S_GRADH] + KF::gradh0 * pmassi) * hi41;
             const double rhohi = rhoh_d(h, pmassi, dp.p.hfact);
             const double dhdrhoi = -h / (3. * rhohi);
             const double omegai = 1. - dhdrhoi * gradhi;
@@ -329,41 +287,41 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
             const float gradh4 = (float)gradhi;
             a.s_gradh[(size_t)dp.ngradh * s] = gradh4;
             if (GRAV) {
-                double gradsofti = (rs[S_GRADSOFT] + KF::dphidh0 * pmassi) * hi21;
+                double gradsofti = (v[S_GRADSOFT] + KF::dphidh0 * pmassi) * hi21;
                 gradsofti = gradsofti * dhdrhoi;
                 a.s_gradh[(size_t)dp.ngradh * s + 1] = (float)gradsofti;
             }
             gradhi = (double)gradh4;                                                  // dens.F90:1610
             const double rho1i = 1. / rho;
             const double term = KF::cnormk * gradhi * rho1i * hi41;
-            const double rxx = rs[S_RXX], rxy = rs[S_RXY], rxz = rs[S_RXZ], ryy = rs[S_RYY], ryz = rs[S_RYZ], rzz = rs[S_RZZ];
+            const double rxx = v[S_RXX], rxy = v[S_RXY], rxz = v[S_RXZ], ryy = v[S_RYY], ryz = v[S_RYZ], rzz = v[S_RZZ];
             const double denom = rxx * ryy * rzz + 2. * rxy * rxz * ryz - rxx * ryz * ryz - ryy * rxz * rxz - rzz * rxy * rxy;
             double rm[6];
             rm[0] = ryy * rzz - ryz * ryz; rm[1] = rxz * ryz - rzz * rxy; rm[2] = rxy * ryz - rxz * ryy;
             rm[3] = rzz * rxx - rxz * rxz; rm[4] = rxy * rxz - rxx * ryz; rm[5] = rxx * ryy - rxy * rxy;
-            const double divv = -rs[S_DIVV] * term;
+            const double divv = -v[S_DIVV] * term;
             double dv[9], divcurlv5 = 0.;
             if (fabs(denom) > DBL_MIN) {
                 const double ddenom = 1. / denom;
+                exactlinear_d(dv[0], dv[1], dv[2], v[S_DVXDX], v[S_DVXDY], v[S_DVXDZ], rm, ddenom);
+                exactlinear_d(dv[3], dv[4], dv[5], v[S_DVYDX], v[S_DVYDY], v[S_DVYDZ], rm, ddenom);
+                exactlinear_d(dv[6], dv[7], dv[8], v[S_DVZDX], v[S_DVZDY], v[S_DVZDZ], rm, ddenom);
 #pragma unroll
-                for (int r = 0; r < 3; r++) {
-                    double gx, gy, gz;
-                    exactlinear_d(gx, gy, gz, rs[S_DVXDX + 3 * r], rs[S_DVXDX + 3 * r + 1], rs[S_DVXDX + 3 * r + 2], rm, ddenom);
-                    dv[3 * r] = -gx; dv[3 * r + 1] = -gy; dv[3 * r + 2] = -gz;
-                }
+                for (int k = 0; k < 9; k++) dv[k] = -dv[k];
                 if (use_da) {
-                    double ax, ay, az, bx, by, bz, cx, cy, cz;
-                    exactlinear_d(ax, ay, az, rs[S_DAXDX], rs[S_DAXDY], rs[S_DAXDZ], rm, ddenom);
-                    exactlinear_d(bx, by, bz, rs[S_DAYDX], rs[S_DAYDY], rs[S_DAYDZ], rm, ddenom);
-                    exactlinear_d(cx, cy, cz, rs[S_DAZDX], rs[S_DAZDY], rs[S_DAZDZ], rm, ddenom);
-                    const double div_a = -(ax + by + cz);
+                    double ax, ay, az, bx, by, bz, cxx, cyy, czz;
+                    exactlinear_d(ax, ay, az, v[S_DAXDX], v[S_DAXDY], v[S_DAXDZ], rm, ddenom);
+                    exactlinear_d(bx, by, bz, v[S_DAYDX], v[S_DAYDY], v[S_DAYDZ], rm, ddenom);
+                    exactlinear_d(cxx, cyy, czz, v[S_DAZDX], v[S_DAZDY], v[S_DAZDZ], rm, ddenom);
+                    const double div_a = -(ax + by + czz);
                     divcurlv5 = div_a - (dv[0] * dv[0] + dv[4] * dv[4] + dv[8] * dv[8] + 2. * (dv[1] * dv[3] + dv[2] * dv[6] + dv[5] * dv[7]));
                 }
             } else {
-#pragma unroll
-                for (int k = 0; k < 9; k++) dv[k] = -term * rs[S_DVXDX + k];
+                dv[0] = -term * v[S_DVXDX]; dv[1] = -term * v[S_DVXDY]; dv[2] = -term * v[S_DVXDZ];
+                dv[3] = -term * v[S_DVYDX]; dv[4] = -term * v[S_DVYDY]; dv[5] = -term * v[S_DVYDZ];
+                dv[6] = -term * v[S_DVZDX]; dv[7] = -term * v[S_DVZDY]; dv[8] = -term * v[S_DVZDZ];
                 if (use_da) {
-                    const double div_a = -term * (rs[S_DAXDX] + rs[S_DAYDY] + rs[S_DAZDZ]);
+                    const double div_a = -term * (v[S_DAXDX] + v[S_DAYDY] + v[S_DAZDZ]);
                     divcurlv5 = div_a - (dv[0] * dv[0] + dv[4] * dv[4] + dv[8] * dv[8] + 2. * (dv[1] * dv[3] + dv[2] * dv[6] + dv[5] * dv[7]));
                 }
             }
@@ -372,21 +330,33 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
 #pragma unroll
             for (int k = 0; k < 9; k++) a.s_dvdx[9 * (size_t)s + k] = (float)dv[k];
             if (MHD) {
-                const double *rb = rs + 32;
                 float *o = a.s_divcurlB + 4 * (size_t)s;
                 if (gasi) {
-                    o[0] = (float)(-rb[B_DIVB] * term);
-                    o[1] = (float)(-(rb[B_DBZDY] - rb[B_DBYDZ]) * term);
-                    o[2] = (float)(-(rb[B_DBXDZ] - rb[B_DBZDX]) * term);
-                    o[3] = (float)(-(rb[B_DBYDX] - rb[B_DBXDY]) * term);
+                    o[0] = (float)(-w[B_DIVB] * term);
+                    o[1] = (float)(-(w[B_DBZDY] - w[B_DBYDZ]) * term);
+                    o[2] = (float)(-(w[B_DBXDZ] - w[B_DBZDX]) * term);
+                    o[3] = (float)(-(w[B_DBYDX] - w[B_DBXDY]) * term);
                 } else { o[0] = o[1] = o[2] = o[3] = 0.f; }
             }
-            a.s_nneigh[s] = (int)rs[F_NN];
+            const int nn = nneighi + 1;   // + self
+            a.s_nneigh[s] = nn;
             st_rhomax = fmax(st_rhomax, rho);
+            st_pairs += (unsigned long long)nneighi * its_lane;
+            st_ncalc += its_lane; st_nact += nn; st_np += 1;
+            st_maxact = max(st_maxact, nn); st_maxtrial = max(st_maxtrial, st.n);
         }
         __syncwarp();
     }
+    // ---- statistics: one atomic per warp
     st_rhomax = warp_max(st_rhomax);
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) {
+        st_pairs += __shfl_xor_sync(FULLMASK, st_pairs, sft); st_trial += __shfl_xor_sync(FULLMASK, st_trial, sft);
+        st_ncalc += __shfl_xor_sync(FULLMASK, st_ncalc, sft); st_nact += __shfl_xor_sync(FULLMASK, st_nact, sft);
+        st_np += __shfl_xor_sync(FULLMASK, st_np, sft); st_nwalk += __shfl_xor_sync(FULLMASK, st_nwalk, sft);
+        st_surv += __shfl_xor_sync(FULLMASK, st_surv, sft);
+        st_maxact = max(st_maxact, __shfl_xor_sync(FULLMASK, st_maxact, sft)); st_maxtrial = max(st_maxtrial, __shfl_xor_sync(FULLMASK, st_maxtrial, sft));
+    }
     if (lane == 0) {
         atomicAdd(&a.cnt[CNT_NPAIRS], st_pairs); atomicAdd(&a.cnt[CNT_NTRIAL], st_trial); atomicAdd(&a.cnt[CNT_NCALC], st_ncalc);
         atomicAdd(&a.cnt[CNT_NACT], st_nact); atomicAdd(&a.cnt[CNT_NP], st_np); atomicAdd(&a.cnt[CNT_NWALK], st_nwalk);

@@ -23,9 +23,6 @@ struct ForceArgs {
 };
 
 enum { A_FX = 0, A_FY, A_FZ, A_DRHODT, A_DUDTDISS, A_DENDTDISS, A_DIVBSYM, A_DBX, A_DBY, A_DBZ, A_DIVBDIFF, A_POT };
-#define MAXCELL 16
-#define FROW 21
-enum { G_VSIG = 16, G_S = 17 };
 
 // one thread per sorted particle: the per-particle part of start_cell + get_stress
 __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const double4 *__restrict__ pos4, const int8_t *__restrict__ stype,
@@ -76,7 +73,7 @@ __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const 
 
 // pair body: lane = one prefilter survivor j; exact membership test first (force.F90:1271-1287), then compute_forces
 template <int K, bool PERIODIC, bool MHD>
-__device__ __forceinline__ void force_pair(double (&f)[16], double &vsigmax, int &npair, int j, int s, const double4 &pi, double hi, double hi1, double hi21,
+__device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int &npair, int j, int s, const double4 &pi, double hi, double hi1, double hi21,
                                            bool gasi, const double4 &vi, const double4 &Ci, const double4 &Di, const double4 &Ei, const ForceArgs &a,
                                            const DevParams &dp, double Lx, double Ly, double Lz)
 {
@@ -198,17 +195,14 @@ __global__ void __launch_bounds__(128) k_force(const ForceArgs a, const __grid_c
 {
     typedef SphKern<K> KF;
     __shared__ WarpShared wsh[4];
-    __shared__ double finbuf[4][MAXCELL][FROW];
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     WarpShared &ws = wsh[wib];
-    double (*fin)[FROW] = finbuf[wib];
     const int gwarp = blockIdx.x * 4 + wib;
     Staged st;
     st.pos = a.stage_pos + (size_t)gwarp * a.scratch_per_warp;
     st.idx = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;
     const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
     const double halfLmin = 0.5 * fmin(Lx, fmin(Ly, Lz));
-    const unsigned lt_mask = (1u << lane) - 1;
     const sphgpu_params &p = dp.p;
     unsigned long long st_pairs = 0, st_trial = 0;
     double st_dtc = 1.e29, st_dtf = 1.e29, st_dtmin = 1.e29, st_dtmax = 0.;
@@ -233,79 +227,43 @@ __global__ void __launch_bounds__(128) k_force(const ForceArgs a, const __grid_c
         if (!ok) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
         const int nlist = st.n;
         const float slack = prefilter_slack(st.maxrel);
-        int ntar = 0;
-        for (int t = 0; t < cell.count; t++) {
-            const int s = cell.start + t;
-            bool act, gasi, dusti; int itypei;
-            get_partinfo_d(a.stype[s], p.set_boundaries_to_active, p.dust, act, gasi, dusti, itypei);
-            if (!act) continue;                                      // force.F90:2255
-            const double4 pi = a.pos4[s], vi = a.vel4[s], Ci = a.recC[s], Di = a.recD[s];
-            double4 Ei = make_double4(0., 0., 0., 0.);
-            if (MHD) Ei = a.recE[s];
-            const double h = pi.w;
-            const double2 hv = a.hinv[s];
-            const double hi1 = hv.x, hi21 = hv.y;
-            const float xif = (float)(pi.x - cx), yif = (float)(pi.y - cy), zif = (float)(pi.z - cz);
-            const float lim = wide ? 3.0e38f : prefilter_limit(__double2float_ru(KF::radkern * h), slack);
-            double f[16];
+        // ---- lane = target: start_cell (force.F90:2172-2514); the per-particle part was done by k_force_prep
+        const int s = cell.start + min(lane, cell.count - 1);
+        bool act = false, gasi = true, dusti = false; int itypei = IGAS;
+        if (lane < cell.count) get_partinfo_d(a.stype[s], p.set_boundaries_to_active, p.dust, act, gasi, dusti, itypei);
+        const double4 pi = a.pos4[s], vi = a.vel4[s], Ci = a.recC[s], Di = a.recD[s];
+        double4 Ei = make_double4(0., 0., 0., 0.);
+        if (MHD) Ei = a.recE[s];
+        const double h = pi.w;
+        const double2 hv = a.hinv[s];
+        const double hi1 = hv.x, hi21 = hv.y;
+        float lim = 0.f;
+        if (act) lim = wide ? 3.0e38f : prefilter_limit(__double2float_ru(KF::radkern * h), slack);    // force.F90:2255: inactive targets skipped
+        ws.tgt[lane] = make_float4((float)(pi.x - cx), (float)(pi.y - cy), (float)(pi.z - cz), lim);
+        __syncwarp();
+        double f[12];
 #pragma unroll
-            for (int k = 0; k < 16; k++) f[k] = 0.;
-            double vsigmax = 0.;
-            int npair = 0;
-            int qhead = 0, qcount = 0;
-            for (int c0 = 0; c0 < nlist; c0 += 64) {
-                const int i0 = c0 + lane, i1 = c0 + 32 + lane;
-                float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-                if (i0 < nlist) r0 = st.pos[i0];
-                if (i1 < nlist) r1 = st.pos[i1];
-                const float ax = xif - r0.x, ay = yif - r0.y, az = zif - r0.z;
-                const float bx = xif - r1.x, by = yif - r1.y, bz = zif - r1.z;
-                // symmetric criterion: inside radkern*h_i OR inside radkern*h_j (staged .w), both with the FP32 error slack
-                const float l0 = fmaxf(lim, prefilter_limit(r0.w, slack)), l1 = fmaxf(lim, prefilter_limit(r1.w, slack));
-                const bool p0 = (i0 < nlist) && (fmaf(az, az, fmaf(ay, ay, ax * ax)) < l0);
-                const bool p1 = (i1 < nlist) && (fmaf(bz, bz, fmaf(by, by, bx * bx)) < l1);
-                const unsigned m0 = __ballot_sync(FULLMASK, p0), m1 = __ballot_sync(FULLMASK, p1);
-                if (p0) ws.qj[(qhead + qcount + __popc(m0 & lt_mask)) & (QRING - 1)] = st.idx[i0];
-                qcount += __popc(m0);
-                __syncwarp();
-                if (qcount >= 32) {
-                    force_pair<K, PERIODIC, MHD>(f, vsigmax, npair, ws.qj[(qhead + lane) & (QRING - 1)], s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz);
-                    qhead = (qhead + 32) & (QRING - 1); qcount -= 32;
-                    __syncwarp();
-                }
-                if (p1) ws.qj[(qhead + qcount + __popc(m1 & lt_mask)) & (QRING - 1)] = st.idx[i1];
-                qcount += __popc(m1);
-                __syncwarp();
-                if (qcount >= 32) {
-                    force_pair<K, PERIODIC, MHD>(f, vsigmax, npair, ws.qj[(qhead + lane) & (QRING - 1)], s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz);
-                    qhead = (qhead + 32) & (QRING - 1); qcount -= 32;
-                    __syncwarp();
-                }
+        for (int k = 0; k < 12; k++) f[k] = 0.;
+        double vsigmax = 0.;
+        int npair = 0;
+        for (int base = 0; base < nlist; base += MAXCHUNK * 32) {
+            const int nchunk = min(MAXCHUNK, (nlist - base + 31) >> 5);
+            if (wide) build_masks<false>(ws, st, base, nchunk, cell.count, slack);
+            else build_masks<true>(ws, st, base, nchunk, cell.count, slack);
+            int c = -1; unsigned m = 0u;
+            while (true) {
+                const int slot = act ? next_hit(ws, lane, nchunk, c, m) : -1;
+                if (!__any_sync(FULLMASK, slot >= 0)) break;
+                if (slot >= 0)
+                    force_pair<K, PERIODIC, MHD>(f, vsigmax, npair, st.idx[base + slot], s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz);
             }
-            if (lane < qcount)
-                force_pair<K, PERIODIC, MHD>(f, vsigmax, npair, ws.qj[(qhead + lane) & (QRING - 1)], s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz);
-            __syncwarp();
-#pragma unroll
-            for (int sft = 16; sft >= 1; sft >>= 1) npair += __shfl_xor_sync(FULLMASK, npair, sft);
-            st_pairs += npair; st_trial += nlist;
-            vsigmax = warp_max(vsigmax);
-            const double tot = warp_transpose_reduce<16>(f);         // lane L holds slot L>>1
-            if ((lane & 1) == 0) fin[ntar][lane >> 1] = tot;
-            if (lane == 0) { fin[ntar][G_VSIG] = vsigmax; fin[ntar][G_S] = (double)s; }
-            ntar++;
             __syncwarp();
         }
-        __syncwarp();
-        // ---- finish_cell_and_store_results (force.F90:2649-3330), one lane per target ----
-        if (lane < ntar) {
-            const double *fs = fin[lane];
-            const int s = (int)fs[G_S];
-            bool act, gasi, dusti; int itypei;
-            get_partinfo_d(a.stype[s], p.set_boundaries_to_active, p.dust, act, gasi, dusti, itypei);
-            const double4 pi = a.pos4[s], vi = a.vel4[s], Ci = a.recC[s], Di = a.recD[s];
-            const double hi = pi.w, hi1 = a.hinv[s].x, pmassi = Di.z;
-            double fx = fs[A_FX], fy = fs[A_FY], fz = fs[A_FZ];
-            const double vsigmax = fs[G_VSIG];
+        // ---- finish_cell_and_store_results (force.F90:2649-3330), lane = target ----
+        if (act) {
+            st_pairs += npair; st_trial += nlist;
+            const double pmassi = Di.z;
+            double fx = f[A_FX], fy = f[A_FY], fz = f[A_FZ];
             double dtc = p.dtmax, dtf = 1.e29, dtclean = 1.e29;
             double fxyz4 = 0., divvi = 0.;
             double4 dB = make_double4(0., 0., 0., 0.);
@@ -313,9 +271,8 @@ __global__ void __launch_bounds__(128) k_force(const ForceArgs a, const __grid_c
             if (gasi) {
                 const double rho1i = Di.x, rhoi = 1. / rho1i, pri = Ci.w, vwavei = Ci.y;
                 if (MHD) {                                           // force.F90:2939-2965
-                    const double4 Ei = a.recE[s];
                     const double B2i = Ei.x * Ei.x + Ei.y * Ei.y + Ei.z * Ei.z;
-                    const double divBsymmi = fs[A_DIVBSYM];
+                    const double divBsymmi = f[A_DIVBSYM];
                     double frac_divB = 0.;
                     if (B2i > 0.0) {
                         const double betai = 2.0 * pri / B2i;
@@ -325,35 +282,35 @@ __global__ void __launch_bounds__(128) k_force(const ForceArgs a, const __grid_c
                     fx -= Ei.x * divBsymmi * frac_divB; fy -= Ei.y * divBsymmi * frac_divB; fz -= Ei.z * divBsymmi * frac_divB;
                     divBsymm4 = (float)(rhoi * divBsymmi);
                 }
-                const double drhodti = pmassi * fs[A_DRHODT];
+                const double drhodti = pmassi * f[A_DRHODT];
                 divvi = -drhodti * rho1i;
                 if (dp.nvu >= 4) {                                   // force.F90:3024-3095 (ien_type = energy, fac = rho/rhogas = 1)
                     const double pdv_work = pri * rho1i * rho1i * drhodti;
                     if (p.ipdv_heating > 0) fxyz4 += pdv_work;
-                    if (p.ishock_heating > 0) fxyz4 += fs[A_DUDTDISS];
-                    fxyz4 += fs[A_DENDTDISS];
+                    if (p.ishock_heating > 0) fxyz4 += f[A_DUDTDISS];
+                    fxyz4 += f[A_DENDTDISS];
                 }
                 if (MHD) {                                           // force.F90:3103-3125
-                    dB.x = fs[A_DBX]; dB.y = fs[A_DBY]; dB.z = fs[A_DBZ];
+                    dB.x = f[A_DBX]; dB.y = f[A_DBY]; dB.z = f[A_DBZ];
                     if (p.psidecayfac > 0.) {
                         const double vcleani = p.overcleanfac * vwavei;
                         const double dtau = p.psidecayfac * vcleani * hi1;
-                        const double psii = a.recE[s].w;
-                        dB.w = -vcleani * fs[A_DIVBDIFF] * rho1i - psii * dtau - 0.5 * psii * divvi;
-                        dtclean = p.C_cour * hi / (vcleani + DBL_MIN);
+                        const double psii = Ei.w;
+                        dB.w = -vcleani * f[A_DIVBDIFF] * rho1i - psii * dtau - 0.5 * psii * divvi;
+                        dtclean = p.C_cour * h / (vcleani + DBL_MIN);
                     }
                 }
                 const double vsigdtc = fmax(vsigmax, vwavei);
-                if (vsigdtc > DBL_MIN) dtc = p.C_cour * hi / (vsigdtc * fmax(p.alpha, 1.0));     // force.F90:3138-3141
+                if (vsigdtc > DBL_MIN) dtc = p.C_cour * h / (vsigdtc * fmax(p.alpha, 1.0));      // force.F90:3138-3141
                 if (dp.nvu >= 4) {
                     const double eni = vi.w;
                     if (eni + dtc * fxyz4 < DBL_EPSILON && eni > DBL_EPSILON) fxyz4 = fxyz4 / (1. - dtc * fxyz4 / eni);   // :3144-3148
                 }
             } else {
-                if (vsigmax > DBL_MIN) dtc = p.C_cour * hi / vsigmax;
+                if (vsigmax > DBL_MIN) dtc = p.C_cour * h / vsigmax;
             }
             const double f2i = fx * fx + fy * fy + fz * fz;
-            if (fabs(f2i) > DBL_EPSILON) dtf = p.C_force * sqrt(hi / sqrt(f2i));                 // force.F90:3217-3219
+            if (fabs(f2i) > DBL_EPSILON) dtf = p.C_force * sqrt(h / sqrt(f2i));                  // force.F90:3217-3219
             a.s_fxyzu[s] = make_double4(fx, fy, fz, fxyz4);
             a.s_divvf[s] = (float)divvi;
             if (MHD) { a.s_dB[s] = dB; a.s_divBsymm[s] = divBsymm4; }
@@ -365,6 +322,8 @@ __global__ void __launch_bounds__(128) k_force(const ForceArgs a, const __grid_c
         __syncwarp();
     }
     st_dtc = warp_min(st_dtc); st_dtf = warp_min(st_dtf); st_dtmin = warp_min(st_dtmin); st_dtmax = warp_max(st_dtmax);
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) { st_pairs += __shfl_xor_sync(FULLMASK, st_pairs, sft); st_trial += __shfl_xor_sync(FULLMASK, st_trial, sft); }
     if (lane == 0) {
         atomicAdd(&a.cnt[CNT_NPAIRS], st_pairs); atomicAdd(&a.cnt[CNT_NTRIAL], st_trial);
         atomic_min_pos(&a.dscal[DS_DTCOURANT], st_dtc); atomic_min_pos(&a.dscal[DS_DTFORCE], st_dtf);

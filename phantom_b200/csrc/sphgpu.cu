@@ -130,7 +130,7 @@ const char *sphgpu_last_error(sphgpu_ctx *c) { return c ? c->err.c_str() : "null
 int sphgpu_set_option(sphgpu_ctx *c, const char *name, double value)
 {
     if (!c || !name) return SPHGPU_ERR_ARG;
-    if (!strcmp(name, "max_cell")) { int v = (int)value; c->max_cell = v < 1 ? 1 : (v > 16 ? 16 : v); c->tree_valid = false; return 0; }
+    if (!strcmp(name, "max_cell")) { int v = (int)value; c->max_cell = v < 1 ? 1 : (v > 32 ? 32 : v); c->tree_valid = false; return 0; }
     if (!strcmp(name, "list_margin")) { c->list_margin = value < 1. ? 1. : value; return 0; }
     if (!strcmp(name, "scratch_per_warp")) { c->scratch_per_warp = (int)value; c->stage_pos.release(); c->stage_idx.release(); return 0; }
     return SPHGPU_ERR_ARG;

@@ -101,42 +101,42 @@ __global__ void k_gather_pos(int64_t nlive, const int *__restrict__ perm, const 
     const int8_t ph = iphase[i];
     stype[s] = ph;
     if (ph != IGAS && ph != -IGAS) cnt[CNT_MULTITYPE] = 1ull;
-    // common leading octal digits with the previous key (0..21)
+    // common leading bits (of the 63 key bits) with the previous key: 0..63
     unsigned char c = 0;
     if (s > 0) {
         unsigned long long x = keys[s] ^ keys[s - 1];
-        c = x ? (unsigned char)((__clzll((long long)x) - 1) / 3) : (unsigned char)21;
+        c = x ? (unsigned char)(__clzll((long long)x) - 1) : (unsigned char)63;
     }
     cpl[s] = c;
 }
 
-// leaf-cell boundaries: particle s starts a cell iff its predecessor is not in the same maximal octree node of <= tmax particles
+// leaf-cell boundaries: particle s starts a cell iff its predecessor is not in the same maximal binary-radix node
+// (key prefix) holding <= tmax particles.  Prefix nodes of a Morton key are boxes (each bit halves one axis).
 __global__ void k_cell_flags(int64_t nlive, const unsigned char *__restrict__ cpl, int tmax, int *__restrict__ flag)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nlive) return;
-    int hist[23];
-#pragma unroll
-    for (int d = 0; d < 23; d++) hist[d] = 0;
-    int m = 22;
+    unsigned char hist[66];
+    for (int d = 0; d < 66; d++) hist[d] = 0;
+    int m = 65;
     for (int k = 1; k <= tmax; k++) {           // to the left: m_k = min cpl over (s-k+1 .. s)
         if (s - k < 0) break;
         m = min(m, (int)cpl[s - k + 1]);
         hist[m]++;
     }
-    m = 22;
+    m = 65;
     for (int k = 1; k <= tmax; k++) {           // to the right: min cpl over (s+1 .. s+k)
         if (s + k >= nlive) break;
         m = min(m, (int)cpl[s + k]);
         hist[m]++;
     }
-    int count = 1, depth = 22;
-    int cum[23];
-    for (int d = 22; d >= 0; d--) { count += hist[d]; cum[d] = count; }
-    for (int d = 0; d <= 21; d++) if (cum[d] <= tmax) { depth = d; break; }
+    // count(d) = particles sharing the first d bits with s (inside the window) ; depth = shallowest d with count <= tmax
+    int count = 1, depth = 64;
+    for (int d = 65; d >= 0; d--) { count += hist[d]; if (count <= tmax) depth = d; }
+    if (depth > 64) depth = 64;
     int f;
     if (s == 0) f = 1;
-    else if (depth == 22) f = (cpl[s] < 21) || (s % tmax == 0);
+    else if (depth == 64) f = (cpl[s] < 63) || (s % tmax == 0);   // > tmax identical keys: split the run arbitrarily
     else f = (int)cpl[s] < depth;
     flag[s] = f;
 }

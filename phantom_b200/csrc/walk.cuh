@@ -8,21 +8,25 @@
 //   stage  : the particles of the hit cells are copied ONCE per cell into the warp's scratch slice as
 //            float4 {x,y,z relative to the target-cell centre (nearest periodic image), radkern*h_j} + int index, so the
 //            per-target scan reads contiguous 16-byte records (like the reference's xyzcache, but FP32 and only a filter).
-//   scan   : per target particle the lanes stride over the staged records with a conservative FP32 distance test
-//            (error bound derived from the staged extent); survivors are compacted through a shared-memory ring and
-//            the pair body re-evaluates the EXACT reference test in FP64 (non-contracted mul/add in the reference's
-//            association order, dens.F90:671-679 / force.F90:1271-1287), so set membership is bit-identical.
+//   masks  : lane = staged candidate, loop over the cell's <= 32 targets (broadcast from shared memory): a conservative
+//            FP32 distance test (error bound derived from the staged extent) + one ballot per target gives, per chunk of
+//            32 candidates, a 32-bit hit mask per target; ~10 instructions per (chunk, target), none on the FP64 pipe.
+//   pairs  : lane = TARGET.  Every lane walks its own hit masks and evaluates its own neighbours; the pair body
+//            re-evaluates the EXACT reference test in FP64 (non-contracted mul/add in the reference's association
+//            order, dens.F90:671-679 / force.F90:1271-1287) so set membership is bit-identical.  The per-particle
+//            sums stay in the lane's registers: no cross-lane reduction, no queue, no synchronisation in the pair loop.
 #pragma once
 #include "common.cuh"
 
 #define WALK_STACK 256
-#define QRING 64
 #define CELLLIST 128
+#define MAXCHUNK 64            // hit masks cover 64 chunks x 32 = 2048 staged candidates per round
 
 struct WarpShared {
     int stack[WALK_STACK];
-    int qj[QRING];
-    int celllist[CELLLIST];     // packed (start << 5) | (count - 1)
+    int celllist[CELLLIST];             // packed (start << 5) | (count - 1)
+    unsigned hm[MAXCHUNK][32];          // hm[chunk][t] = candidates of the chunk inside target t's (FP32, conservative) radius
+    float4 tgt[32];                     // per target: cell-relative position + FP32 limit on r^2
 };
 
 struct Staged {
@@ -163,6 +167,47 @@ __device__ bool warp_walk_stage(const TreeNodeF *__restrict__ nodes, const Cell 
     st.maxrel = fmaxf(st.maxrel, __shfl_xor_sync(FULLMASK, st.maxrel, 1));
     __syncwarp();
     return true;
+}
+
+__device__ __forceinline__ float prefilter_slack(float maxrel);
+__device__ __forceinline__ float prefilter_limit(float rc, float slack);
+
+// hit masks for one round of staged candidates [base, base + nchunk*32): lane = candidate, loop over targets
+template <bool SYM>
+__device__ __forceinline__ void build_masks(WarpShared &ws, const Staged &st, int base, int nchunk, int ntargets, float slack)
+{
+    const int lane = lane_id();
+    for (int c = 0; c < nchunk; c++) {
+        const int i = base + c * 32 + lane;
+        const bool valid = i < st.n;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) r = st.pos[i];
+        float limj = 0.f;
+        if (SYM) limj = prefilter_limit(r.w, slack);
+        unsigned mine = 0u;
+        for (int t = 0; t < ntargets; t++) {
+            const float4 tg = ws.tgt[t];
+            const float ax = tg.x - r.x, ay = tg.y - r.y, az = tg.z - r.z;
+            const float r2 = fmaf(az, az, fmaf(ay, ay, ax * ax));
+            const float lim = SYM ? ((tg.w > 0.f) ? fmaxf(tg.w, limj) : 0.f) : tg.w;
+            const unsigned m = __ballot_sync(FULLMASK, valid && (r2 < lim));
+            if (lane == t) mine = m;
+        }
+        ws.hm[c][lane] = mine;
+    }
+    __syncwarp();
+}
+
+// advance this lane to its next hit; returns the staged slot or -1 when the lane has consumed all its hits of the round
+__device__ __forceinline__ int next_hit(const WarpShared &ws, int lane, int nchunk, int &c, unsigned &m)
+{
+    while (m == 0u) {
+        if (++c >= nchunk) return -1;
+        m = ws.hm[c][lane];
+    }
+    const int bit = __ffs(m) - 1;
+    m &= m - 1;
+    return c * 32 + bit;
 }
 
 // exact reference separation: dx = xi - xj, minimum image (dens.F90:666-670), rij2 = dx*dx + dy*dy + dz*dz evaluated
