@@ -50,6 +50,9 @@ struct __align__(16) TreeNode {
     int child[2];      // >= 0: internal node id ; < 0: ~cell id
     int parent;
     int pad;
+    int cnt[2];        // particles below each child
+    int start[2];      // first sorted slot of each child's range
+    int act[2];        // active particles below each child
 };
 
 // FP32 copy used by the walk: boxes rounded OUTWARD, hmax rounded up (conservative tests), 64 bytes = 2 sectors
@@ -79,7 +82,8 @@ struct sphgpu_ctx {
     double ms_phase[4] = {0, 0, 0, 0};
     double ms_kernel[2] = {0, 0};   // k_density, k_force alone (CUDA events on the launching stream)
     // tuning
-    int max_cell = 32;
+    int max_cell = 32;       // target group: <= 32 particles (one lane per target)
+    int max_leaf = 8;        // tree leaf (source granularity of the walk)
     double list_margin = 1.02;
     int scratch_per_warp = 8192;
     // ---- canonical (original particle order) device arrays = device mirror of part.F90 ----
@@ -106,6 +110,8 @@ struct sphgpu_ctx {
     DevBuf<unsigned char> cpl;
     DevBuf<int> cellflag, cellid_scan;
     DevBuf<Cell> cells;
+    DevBuf<Cell> groups;                    // target groups = maximal subtrees with <= max_cell particles
+    int64_t ngroups = 0;
     DevBuf<unsigned long long> cellkeys;
     DevBuf<TreeNode> nodes;
     DevBuf<TreeNodeF> nodesf;

@@ -22,7 +22,7 @@
 namespace {
 
 struct DensArgs {
-    const TreeNodeF *nodes; const Cell *cells; int ncells;
+    const TreeNodeF *nodes; const Cell *cells; int ncells; const Cell *groups; int ngroups;
     const double4 *pos4, *vel4, *acc4, *bev4; const int8_t *stype; const int *perm;
     float4 *stage_pos; int *stage_idx; int multitype; double hmax_global;
     double *hnew; float *s_gradh, *s_divv, *s_dvdx, *s_alpha3, *s_divcurlB; int *s_nneigh;
@@ -73,68 +73,72 @@ __global__ void k_scatter_dens(int64_t nlive, const int *__restrict__ perm, cons
     if (mhd) for (int k = 0; k < 4; k++) divcurlB[4 * (size_t)i + k] = s_divcurlB[4 * (size_t)s + k];
 }
 
-// pair body: lane = target, j = this lane's next neighbour candidate.  Exact reference test first, then get_density_sums.
+// pair body: lane = target, j = this lane's next neighbour candidate (slot < 0: none).  Branch-free so that two
+// neighbours per trip give the scheduler two independent FP64 dependency chains: the exact reference membership test
+// (dens.F90:675-679, :650) becomes a 0/1 weight on m_j, through which every same-type sum of get_density_sums scales.
 template <int K, bool PERIODIC, bool MHD, bool GRAV>
-__device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[10], int &nneighi, int j, int s, const double4 &pi, double hi, double hi1,
-                                          double hi21, int itypei, bool gasi, const double4 &vi, const double4 &ai, const double4 &bi,
-                                          const DensArgs &a, const DevParams &dp, bool use_da, double Lx, double Ly, double Lz)
+__device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[10], int &nneighi, int slot, const int *__restrict__ idxlist, int s,
+                                          const double4 &pi, double hi, double hi1, double hi21, int itypei, bool gasi, const double4 &vi,
+                                          const double4 &ai, const double4 &bi, const DensArgs &a, const DevParams &dp, bool use_da, double Lx, double Ly,
+                                          double Lz)
 {
     typedef SphKern<K> KF;
+    const int j = (slot >= 0) ? idxlist[slot] : s;
     const double4 pj = a.pos4[j];
+    const double4 vj = a.vel4[j];
+    const double4 aj = a.acc4[j];
     double dx, dy, dz;
     const double r2 = pair_r2<PERIODIC>(pi.x, pi.y, pi.z, pj, Lx, Ly, Lz, dx, dy, dz);
     const double q2i = __dmul_rn(r2, hi21);                                   // dens.F90:675
-    if (!(q2i < KF::radkern2) || j == s) return;                              // :679, :650 (exact membership)
+    const bool isn = (q2i < KF::radkern2) && (j != s);                        // :679, :650 (exact membership)
     // rij = sqrt(rij2), rij1 = 1/(rij + epsilon) (dens.F90:688,:746) from one reciprocal square root
-    const double rinv = (r2 > 0.) ? rsqrt(r2) : 0.;
-    const double rij = r2 * rinv;
+    const double r2s = isn ? r2 : 1.0;
+    const double rinv = (r2s > 0.) ? rsqrt(r2s) : 0.;
+    const double rij = r2s * rinv;
     const double qi = rij * hi1;
     double wabi, grkerni;
-    KF::get_kernel(q2i, qi, wabi, grkerni);
+    KF::get_kernel(isn ? q2i : 1.0, qi, wabi, grkerni);
     int itypej = IGAS;
     if (a.multitype) itypej = abs((int)a.stype[j]);
     const int basej = (itypej == IBOUNDARY) ? IGAS : itypej;
     const bool same_type = (itypei == itypej) || (basej == itypei);
-    const double pmassj = dp.p.massoftype[itypej];
-    if (same_type) {
-        const bool gas_gas = gasi;
-        const double dwdhi = (-qi * grkerni - 3. * wabi);
-        v[S_RHO] += wabi * pmassj;
-        v[S_GRADH] += dwdhi * pmassj;
-        if (GRAV) v[S_GRADSOFT] += KF::dphidh(q2i, qi) * pmassj;
-        nneighi++;
-        const double rij1 = rinv - DBL_EPSILON * rinv * rinv;
-        const double rij1grkern = rij1 * grkerni;
-        const double runix = dx * rij1grkern * pmassj, runiy = dy * rij1grkern * pmassj, runiz = dz * rij1grkern * pmassj;
-        const double4 vj = a.vel4[j];
-        const double dvx = vi.x - vj.x, dvy = vi.y - vj.y, dvz = vi.z - vj.z;
-        v[S_DIVV] += dvx * runix + dvy * runiy + dvz * runiz;
-        v[S_DVXDX] += dvx * runix; v[S_DVXDY] += dvx * runiy; v[S_DVXDZ] += dvx * runiz;
-        v[S_DVYDX] += dvy * runix; v[S_DVYDY] += dvy * runiy; v[S_DVYDZ] += dvy * runiz;
-        v[S_DVZDX] += dvz * runix; v[S_DVZDY] += dvz * runiy; v[S_DVZDZ] += dvz * runiz;
-        if (use_da && gas_gas) {
-            const double4 aj = a.acc4[j];
-            const double dax = ai.x - aj.x, day = ai.y - aj.y, daz = ai.z - aj.z;
-            v[S_DAXDX] += dax * runix; v[S_DAXDY] += dax * runiy; v[S_DAXDZ] += dax * runiz;
-            v[S_DAYDX] += day * runix; v[S_DAYDY] += day * runiy; v[S_DAYDZ] += day * runiz;
-            v[S_DAZDX] += daz * runix; v[S_DAZDY] += daz * runiy; v[S_DAZDZ] += daz * runiz;
-        }
-        v[S_RXX] -= dx * runix; v[S_RXY] -= dx * runiy; v[S_RXZ] -= dx * runiz;
-        v[S_RYY] -= dy * runiy; v[S_RYZ] -= dy * runiz; v[S_RZZ] -= dz * runiz;
-        if (MHD && gas_gas) {
-            const double pmassi = dp.p.massoftype[itypei];
-            const double rhoi = rhoh_d(hi, pmassi, dp.p.hfact);
-            const double rhoj = rhoh_d(pj.w, pmassj, dp.p.hfact);
-            const double4 bj = a.bev4[j];
-            const double dBx = bi.x * rhoi - bj.x * rhoj, dBy = bi.y * rhoi - bj.y * rhoj, dBz = bi.z * rhoi - bj.z * rhoj;
-            w[B_DIVB] += dBx * runix + dBy * runiy + dBz * runiz;
-            w[B_DBXDX] += dBx * runix; w[B_DBXDY] += dBx * runiy; w[B_DBXDZ] += dBx * runiz;
-            w[B_DBYDX] += dBy * runix; w[B_DBYDY] += dBy * runiy; w[B_DBYDZ] += dBy * runiz;
-            w[B_DBZDX] += dBz * runix; w[B_DBZDY] += dBz * runiy; w[B_DBZDZ] += dBz * runiz;
-        }
-    } else if (dp.p.dust && gasi && itypej == IDUST) {
-        v[S_RHODUST] += wabi;
+    const double pmj = dp.p.massoftype[itypej];
+    const double pmassj = (isn && same_type) ? pmj : 0.;
+    nneighi += (isn && same_type) ? 1 : 0;
+    const double dwdhi = (-qi * grkerni - 3. * wabi);
+    v[S_RHO] += wabi * pmassj;
+    v[S_GRADH] += dwdhi * pmassj;
+    if (GRAV) v[S_GRADSOFT] += KF::dphidh(isn ? q2i : 1.0, qi) * pmassj;
+    const double rij1 = rinv - DBL_EPSILON * rinv * rinv;
+    const double rij1grkern = rij1 * grkerni;
+    const double runix = dx * rij1grkern * pmassj, runiy = dy * rij1grkern * pmassj, runiz = dz * rij1grkern * pmassj;
+    const double dvx = vi.x - vj.x, dvy = vi.y - vj.y, dvz = vi.z - vj.z;
+    v[S_DIVV] += dvx * runix + dvy * runiy + dvz * runiz;
+    v[S_DVXDX] += dvx * runix; v[S_DVXDY] += dvx * runiy; v[S_DVXDZ] += dvx * runiz;
+    v[S_DVYDX] += dvy * runix; v[S_DVYDY] += dvy * runiy; v[S_DVYDZ] += dvy * runiz;
+    v[S_DVZDX] += dvz * runix; v[S_DVZDY] += dvz * runiy; v[S_DVZDZ] += dvz * runiz;
+    if (use_da) {
+        const double g = gasi ? 1. : 0.;                                      // gas_gas (dens.F90:722, :777)
+        const double dax = (ai.x - aj.x) * g, day = (ai.y - aj.y) * g, daz = (ai.z - aj.z) * g;
+        v[S_DAXDX] += dax * runix; v[S_DAXDY] += dax * runiy; v[S_DAXDZ] += dax * runiz;
+        v[S_DAYDX] += day * runix; v[S_DAYDY] += day * runiy; v[S_DAYDZ] += day * runiz;
+        v[S_DAZDX] += daz * runix; v[S_DAZDY] += daz * runiy; v[S_DAZDZ] += daz * runiz;
     }
+    v[S_RXX] -= dx * runix; v[S_RXY] -= dx * runiy; v[S_RXZ] -= dx * runiz;
+    v[S_RYY] -= dy * runiy; v[S_RYZ] -= dy * runiz; v[S_RZZ] -= dz * runiz;
+    if (MHD) {
+        const double g = gasi ? 1. : 0.;
+        const double pmassi = dp.p.massoftype[itypei];
+        const double rhoi = rhoh_d(hi, pmassi, dp.p.hfact);
+        const double rhoj = rhoh_d(pj.w, pmj, dp.p.hfact);
+        const double4 bj = a.bev4[j];
+        const double dBx = (bi.x * rhoi - bj.x * rhoj) * g, dBy = (bi.y * rhoi - bj.y * rhoj) * g, dBz = (bi.z * rhoi - bj.z * rhoj) * g;
+        w[B_DIVB] += dBx * runix + dBy * runiy + dBz * runiz;
+        w[B_DBXDX] += dBx * runix; w[B_DBXDY] += dBx * runiy; w[B_DBXDZ] += dBx * runiz;
+        w[B_DBYDX] += dBy * runix; w[B_DBYDY] += dBy * runiy; w[B_DBYDZ] += dBy * runiz;
+        w[B_DBZDX] += dBz * runix; w[B_DBZDY] += dBz * runiy; w[B_DBZDZ] += dBz * runiz;
+    }
+    if (dp.p.dust) v[S_RHODUST] += (isn && !same_type && gasi && itypej == IDUST) ? wabi : 0.;
 }
 
 __device__ __forceinline__ void exactlinear_d(double &gx, double &gy, double &gz, double dAx, double dAy, double dAz, const double *rm, double ddenom)
@@ -168,8 +172,8 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
         int cellid = 0;
         if (lane == 0) cellid = (int)atomicAdd(&a.cnt[CNT_WORK], 1ull);
         cellid = __shfl_sync(FULLMASK, cellid, 0);
-        if (cellid >= a.ncells) break;
-        const Cell cell = a.cells[cellid];
+        if (cellid >= a.ngroups) break;
+        const Cell cell = a.groups[cellid];
         if (cell.active == 0) continue;                              // dens.F90:302
         const double cx = 0.5 * (cell.lo[0] + cell.hi[0]), cy = 0.5 * (cell.lo[1] + cell.hi[1]), cz = 0.5 * (cell.lo[2] + cell.hi[2]);
         const double halfext = 0.5 * fmax(cell.hi[0] - cell.lo[0], fmax(cell.hi[1] - cell.lo[1], cell.hi[2] - cell.lo[2]));
@@ -235,13 +239,14 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
                 const int nchunk = min(MAXCHUNK, (nlist - base + 31) >> 5);
                 build_masks<false>(ws, st, base, nchunk, cell.count, slack);
                 int c = -1; unsigned m = 0u;
-                while (true) {
-                    const int slot = conv ? -1 : next_hit(ws, lane, nchunk, c, m);
-                    if (!__any_sync(FULLMASK, slot >= 0)) break;
-                    if (slot >= 0) {
-                        st_surv++;
-                        dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, st.idx[base + slot], s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp, use_da, Lx,
-                                                          Ly, Lz);
+                while (true) {      // two neighbours per trip: independent dependency chains, loads of both in flight
+                    const int slot0 = conv ? -1 : next_hit(ws, lane, nchunk, c, m);
+                    const int slot1 = (slot0 < 0) ? -1 : next_hit(ws, lane, nchunk, c, m);
+                    if (!__any_sync(FULLMASK, slot0 >= 0)) break;
+                    if (slot0 >= 0) {
+                        st_surv += 1 + (slot1 >= 0);
+                        dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, slot0, st.idx + base, s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp, use_da, Lx, Ly, Lz);
+                        dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, slot1, st.idx + base, s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp, use_da, Lx, Ly, Lz);
                     }
                 }
                 __syncwarp();
@@ -411,7 +416,7 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->dscal.p + DS_RHOMAX, 0, sizeof(double), c->stream));
     DensArgs a;
-    a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells;
+    a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.acc4 = c->acc4.p; a.bev4 = c->bev4.p; a.stype = c->stype.p; a.perm = c->perm.p;
     a.hnew = c->hnew.p; a.s_gradh = c->s_gradh.p; a.s_divv = c->s_divv.p; a.s_dvdx = c->s_dvdx.p; a.s_alpha3 = c->s_alpha3.p;
     a.s_divcurlB = c->s_divcurlB.p; a.s_nneigh = c->s_nneigh.p;

@@ -14,7 +14,7 @@
 namespace {
 
 struct ForceArgs {
-    const TreeNodeF *nodes; const Cell *cells; int ncells;
+    const TreeNodeF *nodes; const Cell *cells; int ncells; const Cell *groups; int ngroups;
     float4 *stage_pos; int *stage_idx; int multitype;
     const double4 *pos4, *vel4, *recC, *recD, *recE; const double2 *hinv; const int8_t *stype; const int *perm;
     double4 *s_fxyzu, *s_dB; float *s_divvf, *s_divBsymm; int *s_done;
@@ -71,90 +71,83 @@ __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const 
     s_done[s] = 0;
 }
 
-// pair body: lane = one prefilter survivor j; exact membership test first (force.F90:1271-1287), then compute_forces
+// pair body: lane = target, j = this lane's next neighbour candidate (slot < 0: none).  Branch-free: the exact membership
+// test (force.F90:1271-1287, :1230) and the gas-gas condition (:1539) become zero weights on grad W_i, grad W_j, through
+// which every sum of compute_forces scales; two calls per trip give two independent FP64 dependency chains.
 template <int K, bool PERIODIC, bool MHD>
-__device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int &npair, int j, int s, const double4 &pi, double hi, double hi1, double hi21,
-                                           bool gasi, const double4 &vi, const double4 &Ci, const double4 &Di, const double4 &Ei, const ForceArgs &a,
-                                           const DevParams &dp, double Lx, double Ly, double Lz)
+__device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int &npair, int slot, const int *__restrict__ idxlist, int s,
+                                           const double4 &pi, double hi, double hi1, double hi21, bool gasi, const double4 &vi, const double4 &Ci,
+                                           const double4 &Di, const double4 &Ei, const ForceArgs &a, const DevParams &dp, double Lx, double Ly, double Lz)
 {
     typedef SphKern<K> KF;
     const sphgpu_params &p = dp.p;
+    const int j = (slot >= 0) ? idxlist[slot] : s;
     const double4 pj = a.pos4[j];
     const double2 hj = a.hinv[j];
+    const double4 Cj = a.recC[j], Dj = a.recD[j];
+    const double4 vj = a.vel4[j];
     double dx, dy, dz;
     const double r2 = pair_r2<PERIODIC>(pi.x, pi.y, pi.z, pj, Lx, Ly, Lz, dx, dy, dz);
     const double hj1 = hj.x, hj21 = hj.y;
     const double q2i = __dmul_rn(r2, hi21), q2j = __dmul_rn(r2, hj21);        // force.F90:1272, :1285
-    if (!(q2i < KF::radkern2 || q2j < KF::radkern2) || j == s) return;        // :1287, :1230
-    npair++;
-    double rij1, rij;
-    if (r2 > DBL_MIN) { rij1 = rsqrt(r2); rij = r2 * rij1; } else { rij1 = 0.; rij = 0.; }   // force.F90:1293-1299
-    const double qi = rij * hi1;
-    const double4 Cj = a.recC[j], Dj = a.recD[j];
-    const double4 vj = a.vel4[j];
+    const bool isn = (q2i < KF::radkern2 || q2j < KF::radkern2) && (j != s);  // :1287, :1230
+    npair += isn ? 1 : 0;
     int itypej = IGAS;
     if (a.multitype) itypej = abs((int)a.stype[j]);
     const bool gasj = (itypej == IGAS || itypej == IBOUNDARY);
+    const bool gg = isn && gasi && gasj;
+    const double r2s = isn ? r2 : 1.0;
+    const double rij1 = (r2s > DBL_MIN) ? rsqrt(r2s) : 0.;                    // force.F90:1293-1299
+    const double rij = r2s * rij1;
+    const double qi = rij * hi1, qj = rij * hj1;
     const double pmassj = Dj.z, pmassi = Di.z;
-    const double grkerni = (q2i < KF::radkern2) ? KF::grkern(q2i, qi) * Di.y : 0.;
-    double grkernj = 0.;
-    bool usej = false;
-    if (q2j < KF::radkern2) { const double qj = rij * hj1; grkernj = KF::grkern(q2j, qj) * Dj.y; usej = true; }
+    const bool ini = gg && (q2i < KF::radkern2), inj = gg && (q2j < KF::radkern2);
+    const double grkerni = ini ? KF::grkern(q2i, qi) * Di.y : 0.;             // :1301-1302
+    const double grkernj = inj ? KF::grkern(q2j, qj) * Dj.y : 0.;             // :1325-1327
+    bool usej = (q2j < KF::radkern2);
     if (MHD) usej = true;
     if (p.dust) usej = true;
-    if (dp.nvu >= 4 && !p.gravity) usej = true;                  // force.F90:1343-1345
+    if (dp.nvu >= 4 && !p.gravity) usej = true;                               // :1343-1345
     const double runix = dx * rij1, runiy = dy * rij1, runiz = dz * rij1;
     const double dvx = vi.x - vj.x, dvy = vi.y - vj.y, dvz = vi.z - vj.z;
     const double projv = dvx * runix + dvy * runiy + dvz * runiz;
-    if (!(gasi && gasj)) {                                       // force.F90:1446-1452, :1852-1859 (no gravity, no drag here)
-        vsigmax = fmax(vsigmax, fmax(-projv, 0.));
-        return;
-    }
     const double rho1i = Di.x, rho1j = usej ? Dj.x : 0.;
     const double vwavei = Ci.y, alphai = Ci.z, pri = Ci.w, pro2i = Ci.x;
     const double beta = p.beta;
-    const double vsigi = fmax(vwavei - beta * projv, 0.);
+    const double vsigi = fmax(vwavei - beta * projv, 0.);                     // :1423-1426
     const double vsigavi = fmax(alphai * vwavei - beta * projv, 0.);
-    vsigmax = fmax(vsigmax, vsigi);
-    double vwavej = 0., vsigavj = 0., pro2j = 0., prj = 0., alphaj = alphai;
-    if (usej) {
-        vwavej = Cj.y; pro2j = Cj.x; prj = Cj.w;
-        if (!p.const_av) alphaj = Cj.z;
-        const double vsigj = fmax(vwavej - beta * projv, 0.);
-        vsigavj = fmax(alphaj * vwavej - beta * projv, 0.);
-        vsigmax = fmax(vsigmax, vsigj);
-    }
+    const double vwavej = usej ? Cj.y : 0., pro2j = usej ? Cj.x : 0., prj = usej ? Cj.w : 0.;
+    const double alphaj = (usej && !p.const_av) ? Cj.z : alphai;
+    const double vsigj = usej ? fmax(vwavej - beta * projv, 0.) : 0.;         // :1501-1504
+    const double vsigavj = usej ? fmax(alphaj * vwavej - beta * projv, 0.) : 0.;
+    const double vs_gg = fmax(vsigi, vsigj), vs_other = fmax(-projv, 0.);     // :1446-1448 for non gas-gas pairs
+    vsigmax = fmax(vsigmax, isn ? ((gasi && gasj) ? vs_gg : vs_other) : 0.);
     double qrho2i = 0., qrho2j = 0., dudtdissi;
-    if (p.disc_viscosity) {                                      // force.F90:1555-1579
+    if (p.disc_viscosity) {                                                   // force.F90:1555-1579
         const double hjv = 1. / hj1, csi = Di.w, csj = Dj.w;
-        if (projv < 0.) {
-            qrho2i = -0.5 * rho1i * (alphai * csi - beta * projv) * hi * rij1 * projv;
-            if (usej) qrho2j = -0.5 * rho1j * (alphaj * csj - beta * projv) * hjv * rij1 * projv;
-        } else {
-            qrho2i = -0.5 * rho1i * alphai * csi * hi * rij1 * projv;
-            if (usej) qrho2j = -0.5 * rho1j * alphaj * csj * hjv * rij1 * projv;
-        }
+        const double bi_ = (projv < 0.) ? (alphai * csi - beta * projv) : alphai * csi;
+        const double bj_ = (projv < 0.) ? (alphaj * csj - beta * projv) : alphaj * csj;
+        qrho2i = -0.5 * rho1i * bi_ * hi * rij1 * projv;
+        qrho2j = usej ? -0.5 * rho1j * bj_ * hjv * rij1 * projv : 0.;
         dudtdissi = -0.5 * pmassj * rho1i * alphai * csi * hi * rij1 * (projv * projv) * grkerni;
     } else {
-        if (projv < 0.) {                                        // force.F90:1581-1592
-            qrho2i = -0.5 * rho1i * vsigavi * projv;
-            if (usej) qrho2j = -0.5 * rho1j * vsigavj * projv;
-        }
+        const double ap = (projv < 0.) ? projv : 0.;                          // force.F90:1581-1592: approaching pairs only
+        qrho2i = -0.5 * rho1i * vsigavi * ap;
+        qrho2j = -0.5 * rho1j * vsigavj * ap;
         dudtdissi = pmassj * qrho2i * projv * grkerni;
     }
-    const double gradpi = pmassj * (pro2i + qrho2i) * grkerni;
-    const double gradpj = usej ? pmassj * (pro2j + qrho2j) * grkernj : 0.;
+    const double gradp = pmassj * ((pro2i + qrho2i) * grkerni + (pro2j + qrho2j) * grkernj);
     double projsx = 0., projsy = 0., projsz = 0.;
     double dudtresist = 0.;
-    if (dp.nvu >= 4) {                                           // artificial conductivity, force.F90:1606-1624
+    if (dp.nvu >= 4) {                                                        // artificial conductivity, force.F90:1606-1624
         const double denij = vi.w - vj.w;
         double vsigu;
         if (p.gravity) vsigu = fabs(projv);
-        else { const double rhoi = 1. / rho1i, rhoj = 1. / Dj.x; vsigu = sqrt(fabs(pri - prj) * (2. / (rhoi + rhoj))); }
-        const double auterm = 0.5 * pmassi * rho1i * p.alphau, autermj = usej ? 0.5 * pmassj * rho1j * p.alphau : 0.;
+        else vsigu = sqrt(fabs(pri - prj) * (2. * rho1i * Dj.x / (rho1i + Dj.x)));      // 2/(rho_i + rho_j)
+        const double auterm = 0.5 * pmassi * rho1i * p.alphau, autermj = 0.5 * pmassj * rho1j * p.alphau;
         f[A_DENDTDISS] += vsigu * denij * (auterm * grkerni + autermj * grkernj);
     }
-    if (MHD) {                                                   // force.F90:1428-1444, :1626-1672, :2132-2150
+    if (MHD) {                                                                // force.F90:1428-1444, :1626-1672, :2132-2150
         const double4 Ej = a.recE[j];
         const double Bxi = Ei.x, Byi = Ei.y, Bzi = Ei.z, psii = Ei.w;
         const double Bxj = Ej.x, Byj = Ej.y, Bzj = Ej.z, psij = Ej.w;
@@ -182,7 +175,6 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
         const double si = -pmassi * rho21i * projBi * grkerni, sj = -pmassj * rho21j * projBj * grkernj;
         projsx = si * Bxi + sj * Bxj; projsy = si * Byi + sj * Byj; projsz = si * Bzi + sj * Bzj;
     }
-    const double gradp = gradpi + gradpj;
     f[A_FX] += -runix * gradp - projsx;
     f[A_FY] += -runiy * gradp - projsy;
     f[A_FZ] += -runiz * gradp - projsz;
@@ -191,7 +183,7 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
 }
 
 template <int K, bool PERIODIC, bool MHD>
-__global__ void __launch_bounds__(128) k_force(const ForceArgs a, const __grid_constant__ DevParams dp)
+__global__ void __launch_bounds__(128, 4) k_force(const ForceArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
     __shared__ WarpShared wsh[4];
@@ -212,8 +204,8 @@ __global__ void __launch_bounds__(128) k_force(const ForceArgs a, const __grid_c
         int cellid = 0;
         if (lane == 0) cellid = (int)atomicAdd(&a.cnt[CNT_WORK], 1ull);
         cellid = __shfl_sync(FULLMASK, cellid, 0);
-        if (cellid >= a.ncells) break;
-        const Cell cell = a.cells[cellid];
+        if (cellid >= a.ngroups) break;
+        const Cell cell = a.groups[cellid];
         if (cell.active == 0) continue;                              // force.F90:509
         const double cx = 0.5 * (cell.lo[0] + cell.hi[0]), cy = 0.5 * (cell.lo[1] + cell.hi[1]), cz = 0.5 * (cell.lo[2] + cell.hi[2]);
         const double halfext = 0.5 * fmax(cell.hi[0] - cell.lo[0], fmax(cell.hi[1] - cell.lo[1], cell.hi[2] - cell.lo[2]));
@@ -251,11 +243,14 @@ __global__ void __launch_bounds__(128) k_force(const ForceArgs a, const __grid_c
             if (wide) build_masks<false>(ws, st, base, nchunk, cell.count, slack);
             else build_masks<true>(ws, st, base, nchunk, cell.count, slack);
             int c = -1; unsigned m = 0u;
-            while (true) {
-                const int slot = act ? next_hit(ws, lane, nchunk, c, m) : -1;
-                if (!__any_sync(FULLMASK, slot >= 0)) break;
-                if (slot >= 0)
-                    force_pair<K, PERIODIC, MHD>(f, vsigmax, npair, st.idx[base + slot], s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz);
+            while (true) {      // two neighbours per trip
+                const int slot0 = act ? next_hit(ws, lane, nchunk, c, m) : -1;
+                const int slot1 = (slot0 < 0) ? -1 : next_hit(ws, lane, nchunk, c, m);
+                if (!__any_sync(FULLMASK, slot0 >= 0)) break;
+                if (slot0 >= 0) {
+                    force_pair<K, PERIODIC, MHD>(f, vsigmax, npair, slot0, st.idx + base, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz);
+                    force_pair<K, PERIODIC, MHD>(f, vsigmax, npair, slot1, st.idx + base, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz);
+                }
             }
             __syncwarp();
         }
@@ -389,7 +384,7 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
                                                        c->vel4.p, c->frecC.p, c->frecD.p, c->frecE.p, hinv, c->s_nneigh.p, c->hp, c->counters.p);
     c->launches++;
     ForceArgs a;
-    a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells;
+    a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.recC = c->frecC.p; a.recD = c->frecD.p; a.recE = c->frecE.p; a.hinv = hinv; a.stype = c->stype.p; a.perm = c->perm.p;
     a.s_fxyzu = c->s_fxyzu.p; a.s_dB = c->s_dB.p; a.s_divvf = c->s_divvf.p; a.s_divBsymm = c->s_divBsymm.p; a.s_done = c->s_nneigh.p;
     a.stage_pos = c->stage_pos.p; a.stage_idx = c->stage_idx.p; a.multitype = c->multitype ? 1 : 0;

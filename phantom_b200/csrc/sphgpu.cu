@@ -109,7 +109,7 @@ void sphgpu_destroy(sphgpu_ctx *c)
     c->stype.release(); c->hnew.release(); c->frecC.release(); c->frecD.release(); c->frecE.release();
     c->s_gradh.release(); c->s_divv.release(); c->s_dvdx.release(); c->s_alpha3.release(); c->s_divcurlB.release(); c->s_fxyzu.release(); c->s_dB.release();
     c->s_divvf.release(); c->s_poten.release(); c->s_divBsymm.release(); c->s_nneigh.release();
-    c->cpl.release(); c->cellflag.release(); c->cellid_scan.release(); c->cells.release(); c->cellkeys.release(); c->nodes.release(); c->nodeflag.release();
+    c->cpl.release(); c->cellflag.release(); c->cellid_scan.release(); c->cells.release(); c->groups.release(); c->cellkeys.release(); c->nodes.release(); c->nodeflag.release();
     c->cubtemp.release(); c->scratch.release(); c->nodesf.release(); c->stage_pos.release(); c->stage_idx.release(); c->counters.release(); c->dscal.release();
     for (int k = 0; k < 12; k++) cudaEventDestroy(c->ev[k]);
     cudaStreamDestroy(c->stream);
@@ -131,6 +131,7 @@ int sphgpu_set_option(sphgpu_ctx *c, const char *name, double value)
 {
     if (!c || !name) return SPHGPU_ERR_ARG;
     if (!strcmp(name, "max_cell")) { int v = (int)value; c->max_cell = v < 1 ? 1 : (v > 32 ? 32 : v); c->tree_valid = false; return 0; }
+    if (!strcmp(name, "max_leaf")) { int v = (int)value; c->max_leaf = v < 1 ? 1 : (v > 32 ? 32 : v); c->tree_valid = false; return 0; }
     if (!strcmp(name, "list_margin")) { c->list_margin = value < 1. ? 1. : value; return 0; }
     if (!strcmp(name, "scratch_per_warp")) { c->scratch_per_warp = (int)value; c->stage_pos.release(); c->stage_idx.release(); return 0; }
     return SPHGPU_ERR_ARG;

@@ -224,12 +224,14 @@ __global__ void k_refit(int M, const Cell *__restrict__ cells, TreeNode *nodes, 
     if (cidx >= M) return;
     const Cell c = cells[cidx];
     double lo[3] = {c.lo[0], c.lo[1], c.lo[2]}, hi[3] = {c.hi[0], c.hi[1], c.hi[2]}, hmax = c.hmax;
+    int cnt = c.count, start = c.start, act = c.active;
     int me = ~cidx, parent = c.parent;
     while (parent >= 0) {
         TreeNode *nd = &nodes[parent];
         const int slot = (nd->child[0] == me) ? 0 : 1;
         for (int k = 0; k < 3; k++) { nd->lo[slot][k] = lo[k]; nd->hi[slot][k] = hi[k]; }
         nd->hmax[slot] = hmax;
+        nd->cnt[slot] = cnt; nd->start[slot] = start; nd->act[slot] = act;
         write_nodef(&nodesf[parent], slot, lo, hi, hmax);
         __threadfence();
         if (atomicAdd(&flags[parent], 1) == 0) return;     // first arrival: sibling not ready yet
@@ -238,9 +240,38 @@ __global__ void k_refit(int M, const Cell *__restrict__ cells, TreeNode *nodes, 
         const volatile TreeNode *vn = nd;
         for (int k = 0; k < 3; k++) { lo[k] = fmin(lo[k], vn->lo[o][k]); hi[k] = fmax(hi[k], vn->hi[o][k]); }
         hmax = fmax(hmax, vn->hmax[o]);
+        cnt += vn->cnt[o]; start = min(start, vn->start[o]); act += vn->act[o];
         me = parent;
         parent = vn->parent;
     }
+}
+
+// target groups: maximal subtrees holding <= gmax particles (one lane per target in the pair kernels)
+__global__ void k_groups(int M, int gmax, const Cell *__restrict__ cells, const TreeNode *__restrict__ nodes, Cell *__restrict__ groups,
+                         unsigned long long *ngroups)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * M - 1) return;
+    int me, parent, total;
+    if (t < M) { me = ~t; parent = cells[t].parent; total = cells[t].count; }
+    else { const int i = t - M; me = i; parent = nodes[i].parent; total = nodes[i].cnt[0] + nodes[i].cnt[1]; }
+    if (total > gmax) return;
+    Cell g;
+    if (parent >= 0) {
+        const TreeNode &pn = nodes[parent];
+        if (pn.cnt[0] + pn.cnt[1] <= gmax) return;          // the parent is (inside) a group already
+        const int slot = (pn.child[0] == me) ? 0 : 1;
+        for (int k = 0; k < 3; k++) { g.lo[k] = pn.lo[slot][k]; g.hi[k] = pn.hi[slot][k]; }
+        g.hmax = pn.hmax[slot]; g.start = pn.start[slot]; g.count = pn.cnt[slot]; g.active = pn.act[slot]; g.parent = parent;
+    } else if (t < M) {
+        g = cells[t];                                         // a single cell is the whole tree
+    } else {
+        const TreeNode &nd = nodes[me];                       // the root itself fits in one group
+        for (int k = 0; k < 3; k++) { g.lo[k] = fmin(nd.lo[0][k], nd.lo[1][k]); g.hi[k] = fmax(nd.hi[0][k], nd.hi[1][k]); }
+        g.hmax = fmax(nd.hmax[0], nd.hmax[1]); g.start = min(nd.start[0], nd.start[1]); g.count = total; g.active = nd.act[0] + nd.act[1]; g.parent = -1;
+    }
+    const unsigned long long slotg = atomicAdd(ngroups, 1ull);
+    groups[slotg] = g;
 }
 
 __global__ void k_cell_hmax(int64_t ncells, Cell *__restrict__ cells, const double4 *__restrict__ pos4)
@@ -263,6 +294,20 @@ __global__ void k_cell_hmax(int64_t ncells, Cell *__restrict__ cells, const doub
 
 static inline int nblk(int64_t n, int b) { return (int)((n + b - 1) / b); }
 
+static int build_groups(sphgpu_ctx *c)
+{
+    const int M = (int)c->ncells;
+    CUDA_TRY(c, c->groups.ensure(M));
+    unsigned long long *ng = c->counters.p + CNT_COUNT - 1;
+    CUDA_TRY(c, cudaMemsetAsync(ng, 0, sizeof(unsigned long long), c->stream));
+    LAUNCH(c, k_groups, nblk(2 * M - 1, 128), 128, M, c->max_cell, c->cells.p, c->nodes.p, c->groups.p, ng);
+    unsigned long long h = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&h, ng, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->ngroups = (int64_t)h;
+    return SPHGPU_OK;
+}
+
 int tree_refit_hmax(sphgpu_ctx *c)
 {
     const int M = (int)c->ncells;
@@ -271,6 +316,7 @@ int tree_refit_hmax(sphgpu_ctx *c)
         CUDA_TRY(c, cudaMemsetAsync(c->nodeflag.p, 0, sizeof(int) * (size_t)M, c->stream));
         LAUNCH(c, k_refit, nblk(M, 128), 128, M, c->cells.p, c->nodes.p, c->nodesf.p, c->nodeflag.p);
     }
+    TRY(build_groups(c));
     CUDA_TRY(c, cudaGetLastError());
     return SPHGPU_OK;
 }
@@ -321,7 +367,7 @@ int tree_build(sphgpu_ctx *c)
     CUDA_TRY(c, c->pos4.ensure(n)); CUDA_TRY(c, c->stype.ensure(n)); CUDA_TRY(c, c->cpl.ensure(n));
     CUDA_TRY(c, c->cellflag.ensure(n)); CUDA_TRY(c, c->cellid_scan.ensure(n));
     LAUNCH(c, k_gather_pos, nblk(nlive, 256), 256, nlive, c->perm.p, c->xyzh.p, c->iphase.p, c->pos4.p, c->stype.p, c->keys.p, c->cpl.p, c->counters.p);
-    LAUNCH(c, k_cell_flags, nblk(nlive, 128), 128, nlive, c->cpl.p, c->max_cell, c->cellflag.p);
+    LAUNCH(c, k_cell_flags, nblk(nlive, 128), 128, nlive, c->cpl.p, c->max_leaf, c->cellflag.p);
     tbb = c->cubtemp.cap;
     CUDA_TRY(c, cub::DeviceScan::ExclusiveSum(c->cubtemp.p, tbb, c->cellflag.p, c->cellid_scan.p, (int)nlive, c->stream));
     c->launches += 2;
@@ -341,6 +387,7 @@ int tree_build(sphgpu_ctx *c)
         CUDA_TRY(c, cudaMemsetAsync(c->nodeflag.p, 0, sizeof(int) * (size_t)M, c->stream));
         LAUNCH(c, k_refit, nblk(M, 128), 128, (int)M, c->cells.p, c->nodes.p, c->nodesf.p, c->nodeflag.p);
     }
+    TRY(build_groups(c));
     CUDA_TRY(c, cudaGetLastError());
     c->tree_valid = true;
     return SPHGPU_OK;

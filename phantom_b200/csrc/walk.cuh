@@ -185,6 +185,7 @@ __device__ __forceinline__ void build_masks(WarpShared &ws, const Staged &st, in
         float limj = 0.f;
         if (SYM) limj = prefilter_limit(r.w, slack);
         unsigned mine = 0u;
+#pragma unroll 4
         for (int t = 0; t < ntargets; t++) {
             const float4 tg = ws.tgt[t];
             const float ax = tg.x - r.x, ay = tg.y - r.y, az = tg.z - r.z;
