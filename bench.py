@@ -88,10 +88,15 @@ def pinned_like(part):
     return part
 
 
-def make_workload(args):
+def make_workload(args, rank=0, world=1):
     from phantom_b200 import setups
-    part = setups.setup_turb(nx=args.nx)
-    return part, f"turb: isothermal periodic box, {args.nx}^3 = {part.npart} particles, cubic kernel, hydro+AV (Cullen-Dehnen), all active"
+    if world == 1:
+        part = setups.setup_turb(nx=args.nx)
+        return part, None, f"turb: isothermal periodic box, {args.nx}^3 = {part.npart} particles, cubic kernel, hydro+AV (Cullen-Dehnen), all active"
+    part, boxes = setups.setup_turb_block(args.nx, world, rank)
+    bd = setups.block_dims(world)
+    return part, boxes, (f"turb (weak scaling): periodic box of {bd[0]}x{bd[1]}x{bd[2]} blocks, {args.nx}^3 = {part.npart} particles per GPU, "
+                         f"{part.npart * world} in total, cubic kernel, hydro+AV (Cullen-Dehnen), all active")
 
 
 def run_reference(args, rank, world):
@@ -99,7 +104,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oraclelib import Oracle
-    part, wl = make_workload(args)
+    part, _, wl = make_workload(args)
     o = Oracle(part.params)
     threads = o.max_threads()
     # bounded sample: shrink the box until (steps+warmup) steps fit in ~150 s (cost is linear in N)
@@ -110,7 +115,7 @@ def run_reference(args, rank, world):
         t_est /= 8.0
     if nx != args.nx:
         args.nx = nx
-        part, _ = make_workload(args)
+        part, _, _ = make_workload(args)
         o = Oracle(part.params)
     for _ in range(args.warmup):
         o.derivs(part)
@@ -140,6 +145,7 @@ def main():
     ap.add_argument("--nx", type=int, default=128, help="lattice points per axis of the turb box (BASELINE configs[1]: 128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-cell", type=int, default=0)
+    ap.add_argument("--max-leaf", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -160,11 +166,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from phantom_b200.api import SphGpu, F_ALL
-    part, wl = make_workload(args)
+    from phantom_b200.halo import DistributedSph
+    part, boxes, wl = make_workload(args, rank, world)
     n = part.npart
     g = SphGpu(part.params.copy(), device=local)
     if args.max_cell:
         g.set_option("max_cell", args.max_cell)
+    if args.max_leaf:
+        g.set_option("max_leaf", args.max_leaf)
     fp64_peak = g.measure_fp64_peak()
     copy_bw = g.measure_copy_bw()
 
@@ -176,8 +185,13 @@ def main():
 
     # ---------------- device-resident arm ----------------
     g.upload(part)
+    dsph = DistributedSph(g, boxes, rank, world) if world > 1 else None
+
+    def step():
+        return dsph.derivs(1) if dsph else g.derivs_resident(1)
+
     for _ in range(args.warmup):
-        sc = g.derivs_resident(1)
+        sc = step()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = g.launch_count()
@@ -187,16 +201,19 @@ def main():
     kern = dict(density=0.0, force=0.0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        sc = g.derivs_resident(1)
-        tm = g.timings_ms()
-        t_dev += sum(tm.values())
-        for k in phases:
-            phases[k] += tm[k]
+        sc = step()
+        if world == 1:
+            tm = g.timings_ms()
+            t_dev += sum(tm.values())
+            for k in phases:
+                phases[k] += tm[k]
         kt = g.kernel_timings_ms()
         for k in kern:
             kern[k] += kt[k]
     barrier()
     t_wall = time.perf_counter() - t0
+    if world > 1:
+        t_dev = 1e3 * t_wall        # N > 1: wall clock between device-synchronised barriers (covers kernels + NCCL halo exchange)
     launches = g.launch_count() - l0
     sampler.stop()
     # max over ranks of the device time
@@ -205,21 +222,39 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev_max, t_wall_max = float(tt[0]) * 1e-3, float(tt[1])
     value = n * world * args.steps / t_dev_max
+    halo_info = None
+    if dsph:
+        hb = torch.tensor([float(dsph.nghost), float(dsph.halo_bytes)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(hb, op=dist.ReduceOp.MAX)
+        halo_info = {"ghosts_per_gpu_max": int(hb[0]), "halo_bytes_per_step_per_gpu_max": int(hb[1]), "exchanges_per_step": 2,
+                     "collective": "NCCL all_to_all_single on device buffers (NVLink)"}
 
     # ---------------- end-to-end arm: the literal C-ABI call with host (pinned) buffers ----------------
     part_e2e = pinned_like(part.copy())
     g2 = SphGpu(part.params.copy(), device=local)
     if args.max_cell:
         g2.set_option("max_cell", args.max_cell)
+    if args.max_leaf:
+        g2.set_option("max_leaf", args.max_leaf)
     nvu, ng = part.params.maxvxyzu, part.params.ngradh
     h2d = n * (4 * 8 + nvu * 8 * 2 + 3 * 8 + 3 * 4 + 1 + ng * 4 + 4 + 9 * 4 + 7 * 8)
     d2h = n * (4 * 8 + nvu * 8 + ng * 4 + 4 + 9 * 4 + 3 * 4 + 7 * 8)
+    dsph2 = DistributedSph(g2, boxes, rank, world) if world > 1 else None
+
+    def step_e2e():
+        if dsph2:
+            g2.upload(part_e2e)
+            dsph2.derivs(1)
+            g2.download(part_e2e)
+        else:
+            g2.derivs(part_e2e, 1)
+
     for _ in range(2):
-        g2.derivs(part_e2e, 1)
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        g2.derivs(part_e2e, 1)
+        step_e2e()
     barrier()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -262,7 +297,8 @@ def main():
         "metric": "particle-updates/s (tree+density+cons2prim+force)", "value": value, "unit": "particle-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev_max / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl, "per_gpu_particles": n, "parallelism": "single" if world == 1 else f"{world} independent periodic boxes (halo exchange not built yet)",
+        "config": {"workload": wl, "per_gpu_particles": n, "parallelism": "single" if world == 1 else f"spatial domain decomposition over {world} GPUs, ghost-particle halo (NCCL all-to-all-v), 1 process per GPU",
+                   "timing": "CUDA events on the library stream" if world == 1 else "wall clock between device-synchronised barriers, max over ranks",
                    "l2": "inputs_exceed_l2 (working set ~%.1f GB per step)" % (n * 600 / 1e9), "state": "device-resident, derivs(icall=1) repeated on the same state"},
         "phases_ms": {k: v / args.steps for k, v in phases.items()},
         "wall_ms_per_step": 1e3 * t_wall_max / args.steps,
@@ -272,6 +308,7 @@ def main():
         "clocks": sampler.summary(),
         "roofline": roofline,
         "neighbours": {"mean": sc.actualmean, "max": sc.maxactual, "trial_mean": sc.trialmean},
+        "halo": halo_info,
     }
 
     # ---------------- CPU baseline (oracle port) beside it: rank 0, N=1 ----------------
@@ -286,7 +323,7 @@ def main():
             import copy
             a2 = copy.copy(args)
             a2.nx = nxc
-            pc, _ = make_workload(a2)
+            pc, _, _ = make_workload(a2)
             o = Oracle(pc.params)
         t0 = time.perf_counter()
         o.derivs(pc)

@@ -176,6 +176,18 @@ int sphgpu_get_neighbour_stats(sphgpu_ctx *ctx, sphgpu_scalars *out);
  * returns total count, or -(needed) when maxlist is too small */
 int64_t sphgpu_neighbour_sets(sphgpu_ctx *ctx, int symmetric, int64_t *offsets, int32_t *list, int64_t maxlist);
 
+/* ---- multi-GPU halo (one context per rank / GPU): replaces the MPI cell export of mpi_dens.F90 / mpi_force.F90 /
+ * mpi_derivs.F90:197-522.  Ghost particles are appended after the owned ones as inactive (neighbour-only) particles.
+ * The host side moves the packed buffers with NCCL (all-to-all-v) directly between the returned DEVICE pointers. */
+int sphgpu_local_hmax(sphgpu_ctx *ctx, double *hmax);
+/* boxes = 6 doubles per rank {lo xyz, hi xyz}; counts[r] = owned particles within dhalo of rank r's box (minimum image) */
+int sphgpu_halo_select(sphgpu_ctx *ctx, int nranks, int myrank, const double *boxes, double dhalo, int64_t *counts);
+/* stage 1 (before build_tree): 16 doubles/ghost; stage 2 (after densityiterate): 4 doubles/ghost {h, gradh, alpha, gradsoft} */
+int sphgpu_halo_pack(sphgpu_ctx *ctx, int stage, void **sendptr_device, int *record_doubles);
+int sphgpu_halo_recvbuf(sphgpu_ctx *ctx, int64_t nrecords, int record_doubles, void **recvptr_device);
+int sphgpu_halo_unpack(sphgpu_ctx *ctx, int stage, int64_t nghost);
+int64_t sphgpu_nghost(sphgpu_ctx *ctx);
+
 /* register-resident DFMA microbenchmark: returns measured FP64 TFLOP/s of this device (roofline denominator) */
 double sphgpu_measure_fp64_peak(sphgpu_ctx *ctx);
 /* device copy bandwidth GB/s (read+write) */

@@ -33,7 +33,8 @@ EXPORTS = [
     "sphgpu_launch_count", "sphgpu_get_kernel_timings", "sphgpu_upload", "sphgpu_download", "sphgpu_build_tree_resident", "sphgpu_densityiterate_resident",
     "sphgpu_cons2prim_resident", "sphgpu_force_resident", "sphgpu_derivs_resident", "sphgpu_build_tree", "sphgpu_densityiterate",
     "sphgpu_cons2prim_everything", "sphgpu_force", "sphgpu_derivs", "sphgpu_get_neighbour_stats", "sphgpu_neighbour_sets",
-    "sphgpu_measure_fp64_peak", "sphgpu_measure_copy_bw",
+    "sphgpu_measure_fp64_peak", "sphgpu_measure_copy_bw", "sphgpu_local_hmax", "sphgpu_halo_select", "sphgpu_halo_pack",
+    "sphgpu_halo_recvbuf", "sphgpu_halo_unpack", "sphgpu_nghost",
 ]
 
 
@@ -91,6 +92,13 @@ def load_library():
         L.sphgpu_measure_fp64_peak.restype = dbl
         L.sphgpu_measure_copy_bw.argtypes = [vp]
         L.sphgpu_measure_copy_bw.restype = dbl
+        L.sphgpu_local_hmax.argtypes = [vp, C.POINTER(dbl)]
+        L.sphgpu_halo_select.argtypes = [vp, i32, i32, vp, dbl, vp]
+        L.sphgpu_halo_pack.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i32)]
+        L.sphgpu_halo_recvbuf.argtypes = [vp, i64, i32, C.POINTER(vp)]
+        L.sphgpu_halo_unpack.argtypes = [vp, i32, i64]
+        L.sphgpu_nghost.argtypes = [vp]
+        L.sphgpu_nghost.restype = i64
         _lib = L
     return _lib
 
@@ -239,6 +247,34 @@ class SphGpu:
         if tot < 0:
             raise SphGpuError(7, self.L.sphgpu_last_error(self.h).decode())
         return off, lst[:tot]
+
+    # ---- multi-GPU halo (see halo.py for the orchestration) ---------------------------------------------
+    def local_hmax(self):
+        v = C.c_double()
+        self._check(self.L.sphgpu_local_hmax(self.h, C.byref(v)))
+        return v.value
+
+    def halo_select(self, nranks, myrank, boxes, dhalo):
+        boxes = np.ascontiguousarray(boxes, dtype=np.float64)
+        counts = np.zeros(nranks, dtype=np.int64)
+        self._check(self.L.sphgpu_halo_select(self.h, nranks, myrank, _p(boxes), float(dhalo), _p(counts)))
+        return counts
+
+    def halo_pack(self, stage):
+        ptr, rd = C.c_void_p(), C.c_int32()
+        self._check(self.L.sphgpu_halo_pack(self.h, stage, C.byref(ptr), C.byref(rd)))
+        return ptr.value, rd.value
+
+    def halo_recvbuf(self, nrecords, record_doubles):
+        ptr = C.c_void_p()
+        self._check(self.L.sphgpu_halo_recvbuf(self.h, int(nrecords), int(record_doubles), C.byref(ptr)))
+        return ptr.value
+
+    def halo_unpack(self, stage, nghost):
+        self._check(self.L.sphgpu_halo_unpack(self.h, stage, int(nghost)))
+
+    def nghost(self):
+        return self.L.sphgpu_nghost(self.h)
 
     def measure_fp64_peak(self):
         return self.L.sphgpu_measure_fp64_peak(self.h)

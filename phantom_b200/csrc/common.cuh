@@ -27,6 +27,21 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    // grow while preserving the first `keep` elements (used when ghost particles are appended to the local set)
+    cudaError_t ensure_keep(size_t n, size_t keep, cudaStream_t st)
+    {
+        if (n <= cap) return cudaSuccess;
+        T *q = nullptr;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc((void **)&q, want * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (p && keep) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return e; }
+        if (want > keep) cudaMemsetAsync(q + keep, 0, (want - keep) * sizeof(T), st);
+        cudaStreamSynchronize(st);
+        if (p) cudaFree(p);
+        p = q; cap = want;
+        return cudaSuccess;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
@@ -124,6 +139,13 @@ struct sphgpu_ctx {
     DevBuf<unsigned long long> counters;    // device scalars block
     DevBuf<double> dscal;                   // device double scalars (bbox, dt minima, ...)
     sphgpu_scalars last_dens{}, last_force{};
+    // ---- multi-GPU halo state (halo.cu): ghosts are appended after the nlocal owned particles as inactive particles ----
+    int64_t nlocal = 0, nghost = 0;
+    int halo_nranks = 1, halo_rank = 0;
+    std::vector<long long> halo_sendcnt, halo_sendoff;
+    DevBuf<int> halo_sendidx;
+    DevBuf<unsigned long long> halo_cnt;
+    DevBuf<double> halo_boxes, halo_sendbuf, halo_recvbuf;
 };
 
 #define CUDA_TRY(ctx, call)                                                                           \
@@ -220,3 +242,4 @@ int cons2prim_run(sphgpu_ctx *c);
 int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out);
 int64_t neighbour_sets_run(sphgpu_ctx *c, int symmetric, int64_t *offsets, int32_t *list, int64_t maxlist);
 KernConsts make_kern_consts(int kernel);
+int ensure_all_keep(sphgpu_ctx *c, int64_t n, int64_t keep);

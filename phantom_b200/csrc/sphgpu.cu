@@ -58,6 +58,19 @@ static int ensure_all(sphgpu_ctx *c, int64_t n)
     return SPHGPU_OK;
 }
 
+// grow every canonical array to n particles keeping the first `keep` (ghost append)
+int ensure_all_keep(sphgpu_ctx *c, int64_t n, int64_t keep)
+{
+    const int nvu = c->hp.nvu, ng = c->hp.ngradh;
+    cudaStream_t st = c->stream;
+#define GROW(buf, w) CUDA_TRY(c, (buf).ensure_keep((size_t)(w) * n, (size_t)(w) * keep, st))
+    GROW(c->xyzh, 4); GROW(c->vxyzu, nvu); GROW(c->fxyzu, nvu); GROW(c->fext, 3); GROW(c->Bevol, 4); GROW(c->dBevol, 4); GROW(c->eos_vars, 7);
+    GROW(c->divcurlv, 1); GROW(c->divcurlB, 4); GROW(c->alphaind, 3); GROW(c->gradh, ng); GROW(c->dvdx, 9); GROW(c->poten, 1); GROW(c->divBsymm, 1);
+    GROW(c->iphase, 1);
+#undef GROW
+    return SPHGPU_OK;
+}
+
 // ---- microbenchmarks for the roofline denominators ----------------------------------------------
 __global__ void k_dfma_peak(double *out, int iters)
 {
@@ -110,6 +123,7 @@ void sphgpu_destroy(sphgpu_ctx *c)
     c->s_gradh.release(); c->s_divv.release(); c->s_dvdx.release(); c->s_alpha3.release(); c->s_divcurlB.release(); c->s_fxyzu.release(); c->s_dB.release();
     c->s_divvf.release(); c->s_poten.release(); c->s_divBsymm.release(); c->s_nneigh.release();
     c->cpl.release(); c->cellflag.release(); c->cellid_scan.release(); c->cells.release(); c->groups.release(); c->cellkeys.release(); c->nodes.release(); c->nodeflag.release();
+    c->halo_sendidx.release(); c->halo_cnt.release(); c->halo_boxes.release(); c->halo_sendbuf.release(); c->halo_recvbuf.release();
     c->cubtemp.release(); c->scratch.release(); c->nodesf.release(); c->stage_pos.release(); c->stage_idx.release(); c->counters.release(); c->dscal.release();
     for (int k = 0; k < 12; k++) cudaEventDestroy(c->ev[k]);
     cudaStreamDestroy(c->stream);
@@ -157,7 +171,7 @@ int sphgpu_upload(sphgpu_ctx *c, const sphgpu_host_arrays *h, uint64_t mask)
     CUDA_TRY(c, cudaSetDevice(c->device));
     const int64_t n = h->npart;
     if (n != c->npart) { c->tree_valid = false; c->dens_valid = false; }
-    c->npart = n;
+    c->npart = n; c->nlocal = n; c->nghost = 0;
     TRY(ensure_all(c, n));
     const int nvu = c->hp.nvu, ng = c->hp.ngradh;
     if (mask & SPHGPU_F_XYZH) { TRY(upload_arr(c, c->xyzh, h->xyzh, 4 * n)); if (h->xyzh) c->tree_valid = false; }
@@ -183,7 +197,7 @@ int sphgpu_download(sphgpu_ctx *c, sphgpu_host_arrays *h, uint64_t mask)
 {
     if (!c || !h) return SPHGPU_ERR_ARG;
     CUDA_TRY(c, cudaSetDevice(c->device));
-    const int64_t n = c->npart;
+    const int64_t n = (h->npart > 0 && h->npart < c->npart) ? h->npart : c->npart;    // ghosts (beyond nlocal) are never returned
     const int nvu = c->hp.nvu, ng = c->hp.ngradh;
     if (mask & SPHGPU_F_XYZH) TRY(download_arr(c, c->xyzh, h->xyzh, 4 * n));
     if (mask & SPHGPU_F_VXYZU) TRY(download_arr(c, c->vxyzu, h->vxyzu, (size_t)nvu * n));

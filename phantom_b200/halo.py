@@ -1,0 +1,145 @@
+"""Multi-GPU orchestration of the hot path: spatial domain decomposition + ghost-particle halo over NCCL.
+
+Replaces, for one node with N GPUs (one process per GPU, torch.distributed/NCCL over NVLink), the reference's MPI stack
+for this path:
+
+  maketreeglobal / balancedomains   src/main/kdtree.F90:2044-2300, src/main/mpi_balance.F90:82
+      -> `orb_boxes`: the same rule the reference applies globally -- split at the centre of mass along the longest
+         axis, log2(N) levels -- giving one box per rank;
+  send_cell / recv_cells / combine_cells  src/main/mpi_derivs.F90:197-522 (cell export, one round trip per pass)
+      -> ghost particles: every rank receives the remote particles within radkern*hmax*margin of its box (stage 1,
+         before the tree) and their post-density h, gradh, alpha (stage 2); ghosts enter as inactive particles, the
+         owner alone accumulates its particles' sums, nothing is sent back;
+  reduceall_mpi('min'|'max')  src/main/force.F90:848-852, src/main/dens.F90:546-549
+      -> one packed all_reduce for dtcourant / dtforce / rhomax.
+
+The selection, packing and unpacking run on the device (phantom_b200/csrc/halo.cu); the exchange is an all-to-all-v
+(`all_to_all_single`) issued directly on the library's device buffers.  With the gloo backend (CPU tests) the same
+host logic runs against numpy restatements of the device kernels.
+"""
+import math
+import numpy as np
+
+RADKERN = {0: 2.0, 1: 3.0}
+
+
+def orb_boxes(xyz, mass, nranks, box_lo, box_hi):
+    """Recursive bisection of `box` at the centre of mass along the longest axis (kdtree.F90:2098-2160).
+    xyz may be a sample of the particle set; returns (nranks, 6) boxes {lo, hi} tiling the input box."""
+    boxes = [(np.array(box_lo, dtype=float), np.array(box_hi, dtype=float), np.arange(len(xyz)))]
+    assert nranks & (nranks - 1) == 0, "number of ranks must be a power of two (log2 N bisection levels)"
+    while len(boxes) < nranks:
+        new = []
+        for lo, hi, idx in boxes:
+            axis = int(np.argmax(hi - lo))
+            x = xyz[idx, axis]
+            w = mass[idx] if np.ndim(mass) else np.full(len(idx), mass)
+            pivot = float(np.sum(w * x) / np.sum(w)) if len(idx) else 0.5 * (lo[axis] + hi[axis])
+            left = idx[x <= pivot]
+            right = idx[x > pivot]
+            hl, lr = hi.copy(), lo.copy()
+            hl[axis] = pivot
+            lr[axis] = pivot
+            new.append((lo, hl, left))
+            new.append((lr, hi, right))
+        boxes = new
+    return np.array([np.concatenate([lo, hi]) for lo, hi, _ in boxes])
+
+
+def owner_of(xyz, boxes):
+    """rank owning each position (half-open boxes: lo <= x < hi, the last box closed)"""
+    owner = np.full(len(xyz), -1, dtype=np.int64)
+    for r, b in enumerate(boxes):
+        m = np.all((xyz >= b[:3]) & (xyz < b[3:]), axis=1) & (owner < 0)
+        owner[m] = r
+    # positions exactly on the global upper faces
+    if np.any(owner < 0):
+        for r, b in enumerate(boxes):
+            m = np.all((xyz >= b[:3]) & (xyz <= b[3:]), axis=1) & (owner < 0)
+            owner[m] = r
+    return owner
+
+
+def box_gap2(xyz, box, L, periodic):
+    """squared minimum-image distance from points to a box (numpy restatement of k_halo_select)"""
+    g2 = np.zeros(len(xyz))
+    for k in range(3):
+        x = xyz[:, k]
+        g = np.maximum(0., np.maximum(box[k] - x, x - box[3 + k]))
+        if periodic:
+            for s in (-L[k], L[k]):
+                g = np.minimum(g, np.maximum(0., np.maximum(box[k] - (x + s), (x + s) - box[3 + k])))
+        g2 += g * g
+    return g2
+
+
+def select_ghosts_numpy(xyz, boxes, myrank, dhalo, L, periodic):
+    """indices of owned particles each other rank needs"""
+    return [np.nonzero(box_gap2(xyz, boxes[r], L, periodic) < dhalo * dhalo)[0] if r != myrank else np.zeros(0, dtype=np.int64)
+            for r in range(len(boxes))]
+
+
+class _DevArray:
+    """zero-copy view of a library-owned device buffer for torch (CUDA array interface)"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class DistributedSph:
+    """derivs on a domain-decomposed particle set: one instance per rank, SphGpu context underneath."""
+
+    def __init__(self, gpu, boxes, rank, world, margin=1.15):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.g = gpu
+        self.boxes = np.ascontiguousarray(boxes, dtype=np.float64)
+        self.rank, self.world = rank, world
+        self.margin = margin
+        self.radkern = RADKERN[gpu.params.kernel]
+        self.halo_bytes = 0
+        self.nghost = 0
+
+    def _alltoall(self, sendptr, rd, sendcounts, recvcounts, stage):
+        torch, dist = self.torch, self.dist
+        ntot_s, ntot_r = int(sendcounts.sum()), int(recvcounts.sum())
+        recvptr = self.g.halo_recvbuf(ntot_r, rd)
+        send = torch.as_tensor(_DevArray(sendptr, max(ntot_s, 1) * rd), device="cuda")[: ntot_s * rd]
+        recv = torch.as_tensor(_DevArray(recvptr, max(ntot_r, 1) * rd), device="cuda")[: ntot_r * rd]
+        dist.all_to_all_single(recv, send, [int(c) * rd for c in recvcounts], [int(c) * rd for c in sendcounts])
+        torch.cuda.synchronize()
+        self.halo_bytes += 8 * rd * (ntot_s + ntot_r)
+        return ntot_r
+
+    def derivs(self, icall=1, dt=0.0):
+        """tree + density + cons2prim + force with the two ghost exchanges; returns the reduced scalars"""
+        torch, dist = self.torch, self.dist
+        g = self.g
+        self.halo_bytes = 0
+        # halo width from the global hmax (one tiny all_reduce)
+        hm = torch.tensor([g.local_hmax()], dtype=torch.float64, device="cuda")
+        dist.all_reduce(hm, op=dist.ReduceOp.MAX)
+        dhalo = self.radkern * float(hm[0]) * self.margin
+        sendcounts = g.halo_select(self.world, self.rank, self.boxes, dhalo)
+        sc = torch.from_numpy(sendcounts).cuda()
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc)
+        recvcounts = rc.cpu().numpy()
+        ptr, rd = g.halo_pack(1)
+        self.nghost = self._alltoall(ptr, rd, sendcounts, recvcounts, 1)
+        g.halo_unpack(1, self.nghost)
+        g.build_tree_resident()
+        sd = g.densityiterate_resident(1)
+        g.params.set_boundaries_to_active = 0
+        ptr, rd = g.halo_pack(2)
+        self._alltoall(ptr, rd, sendcounts, recvcounts, 2)
+        g.halo_unpack(2, self.nghost)
+        g.cons2prim_resident()
+        sf = g.force_resident(icall, dt)
+        red = torch.tensor([sf.dtcourant, sf.dtforce, -sd.rhomax], dtype=torch.float64, device="cuda")
+        dist.all_reduce(red, op=dist.ReduceOp.MIN)
+        sf.dtcourant, sf.dtforce, sf.rhomax = float(red[0]), float(red[1]), -float(red[2])
+        sf.np, sf.nrhocalc, sf.npairs_density = sd.np, sd.nrhocalc, sd.npairs_density
+        sf.actualmean, sf.maxactual, sf.trialmean, sf.nactualtot = sd.actualmean, sd.maxactual, sd.trialmean, sd.nactualtot
+        return sf

@@ -303,6 +303,36 @@ def setup_turb(nx=128, mach=5.0, seed=1234, ind_timesteps=False):
     return part
 
 
+def block_dims(world):
+    """(bx,by,bz) blocks of the weak-scaling box: 1 -> (1,1,1), 2 -> (2,1,1), 4 -> (2,2,1), 8 -> (2,2,2)"""
+    dims = [1, 1, 1]
+    k = 0
+    n = world
+    while n > 1:
+        dims[k % 3] *= 2
+        n //= 2
+        k += 1
+    return tuple(dims)
+
+
+def setup_turb_block(nx, world, rank, mach=5.0, seed=1234):
+    """Weak-scaling version of C2 for `world` GPUs: a periodic box of bx x by x bz unit blocks, each block an nx^3 lattice
+    (same particle spacing, mass and h as setup_turb); returns the particles of block `rank` and all block boxes."""
+    bx, by, bz = block_dims(world)
+    p = default_params(isothermal=1, ieos=1, polyk=1.0, gamma=1.0, xmin=0., xmax=float(bx), ymin=0., ymax=float(by), zmin=0., zmax=float(bz))
+    ix, iy, iz = rank % bx, (rank // bx) % by, rank // (bx * by)
+    xyzh = unifdis_cubic(float(ix), ix + 1., float(iy), iy + 1., float(iz), iz + 1., 1.0 / nx, p.hfact)
+    p.massoftype[IGAS] = 1.0 / (nx ** 3)
+    part = Particles(p, xyzh)
+    scaled = xyzh.copy()
+    scaled[:, 0] /= bx
+    scaled[:, 1] /= by
+    scaled[:, 2] /= bz
+    part.vxyzu[:, :3] = _solenoidal_field(scaled, (0.0, 1.0), seed, mach, 1.0)
+    boxes = np.array([[r % bx, (r // bx) % by, r // (bx * by), r % bx + 1., (r // bx) % by + 1., r // (bx * by) + 1.] for r in range(world)], dtype=float)
+    return part, boxes
+
+
 def setup_shock(nx=256, gamma=5. / 3.):
     """C1: SETUP=shock -- 3D Sod tube, quintic kernel, adiabatic, closepacked, periodic in y,z
     (setup_shock.f90:497-499 states; set_shock.f90:35-140; adjust_shock_boundaries :180-209)."""
