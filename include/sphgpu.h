@@ -70,8 +70,9 @@ typedef struct sphgpu_params {
     double polyk, gamma, qfacdisc, cs_min;                     /* eos.f90 */
     double C_cour, C_force, dtmax, psidecayfac, overcleanfac;  /* timestep.f90:52-62 */
     double tree_accuracy;                                      /* kdtree.F90:46 */
-    double grainsize, graindens, K_code;
-    double reserved_d[8];
+    double grainsize, graindens, K_code;                       /* dust.f90: grain size / intrinsic density (code units), K_code(1) */
+    double seff;                                               /* dust.f90:96-99 init_drag: effective surface density for the mean free path (code units) */
+    double reserved_d[7];
 } sphgpu_params;
 
 /* module-variable outputs: timestep:dtcourant,dtforce,rhomaxnow ; dens.F90:104-106 statistics */
@@ -81,7 +82,8 @@ typedef struct sphgpu_scalars {
     int64_t maxtrial, maxactual, nrhocalc, nactualtot, np, ncalls_neigh;
     int64_t npairs_density, npairs_force;   /* real interacting pairs evaluated (roofline accounting) */
     int64_t nbinmaxnew;
-    int64_t reserved[3];
+    int64_t npairs_gravity, nm2l;           /* Newtonian P2P pairs outside both kernels; accepted node-node M2L evaluations */
+    int64_t reserved[1];
 } sphgpu_scalars;
 
 /* host array bundle for upload/download (any pointer may be NULL = skip) */
@@ -102,7 +104,9 @@ typedef struct sphgpu_host_arrays {
     float *poten;        /* (n)            */
     float *divBsymm;     /* (n)            */
     int8_t *iphase;      /* (n)            */
-    int8_t *ibin, *ibin_old, *ibin_wake;
+    int8_t *ibin, *ibin_old, *ibin_wake;   /* (n) timestep_ind / part.F90 */
+    double *dustfrac;    /* (n)  two-fluid dust-to-gas ratio seen by gas particles (dens.F90:1612-1624) */
+    double *tstop;       /* (n)  stopping time (force.F90:3240) */
 } sphgpu_host_arrays;
 
 /* field mask bits for upload/download */
@@ -122,6 +126,8 @@ typedef struct sphgpu_host_arrays {
 #define SPHGPU_F_DIVBSYMM  (1ull << 13)
 #define SPHGPU_F_IPHASE    (1ull << 14)
 #define SPHGPU_F_IBIN      (1ull << 15)
+#define SPHGPU_F_DUSTFRAC  (1ull << 16)
+#define SPHGPU_F_TSTOP     (1ull << 17)
 #define SPHGPU_F_ALL       (~0ull)
 
 typedef struct sphgpu_ctx sphgpu_ctx;
@@ -136,6 +142,12 @@ int  sphgpu_set_option(sphgpu_ctx *ctx, const char *name, double value);
 int  sphgpu_get_timings(sphgpu_ctx *ctx, double *ms4);
 /* device time (ms) of the two dominant kernels of the last call: [0] density pair kernel, [1] force pair kernel */
 int  sphgpu_get_kernel_timings(sphgpu_ctx *ctx, double *ms2);
+/* device time (ms) of the last self-gravity pass: [0] whole pass (tree + FMM walk + P2P), [1] the P2P kernel alone */
+int  sphgpu_get_gravity_timings(sphgpu_ctx *ctx, double *ms2);
+/* node records of the self-gravity tree (maketree with -DGRAVITY, kdtree.F90:531-929; kdnode, dtype_kdtree.F90:53-68) after the last force call:
+ * rec12 = {xcen[3], size, hmax, mass, quads[6]}, irec6 = {leftchild, rightchild, parent, first slot, count, level} (0-based, -1 = none),
+ * ids = inodeparts (1-based particle ids by slot).  rec12 == NULL: returns only the number of nodes; -1 when no tree exists */
+int64_t sphgpu_gravity_tree(sphgpu_ctx *ctx, int64_t maxnodes, double *rec12, int32_t *irec6, int32_t *ids);
 /* number of kernel launches issued by this context since creation */
 int64_t sphgpu_launch_count(sphgpu_ctx *ctx);
 
@@ -175,6 +187,11 @@ int sphgpu_get_neighbour_stats(sphgpu_ctx *ctx, sphgpu_scalars *out);
  * symmetric=0: {j!=i : q2i < radkern2}; symmetric=1: {q2i < radkern2 or q2j < radkern2}.
  * returns total count, or -(needed) when maxlist is too small */
 int64_t sphgpu_neighbour_sets(sphgpu_ctx *ctx, int symmetric, int64_t *offsets, int32_t *list, int64_t maxlist);
+
+/* individual timesteps (-DIND_TIMESTEPS): module timestep_ind inputs nbinmax, ibinnow, istepfrac (utils_indtimesteps.f90);
+ * the force pass then updates ibin (get_newbin + Saitoh-Makino limiter, force.F90:3272-3310), flags ibin_wake of every
+ * neighbour of an active particle (force.F90:1346-1358) and returns nbinmaxnew in sphgpu_scalars */
+int sphgpu_set_timestep_bins(sphgpu_ctx *ctx, int nbinmax, int ibinnow, int istepfrac);
 
 /* ---- multi-GPU halo (one context per rank / GPU): replaces the MPI cell export of mpi_dens.F90 / mpi_force.F90 /
  * mpi_derivs.F90:197-522.  Ghost particles are appended after the owned ones as inactive (neighbour-only) particles.

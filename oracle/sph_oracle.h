@@ -62,7 +62,8 @@ typedef struct oracle_params {
     double tree_accuracy;
     /* dust.f90 (two-fluid): grain size/density in code units, K_code */
     double grainsize, graindens, K_code;
-    double reserved_d[8];
+    double seff;             /* dust.f90:96-99 (init_drag): effective surface density, code units */
+    double reserved_d[7];
 } oracle_params;
 
 /* scalars the reference returns through module variables
@@ -73,7 +74,8 @@ typedef struct oracle_scalars {
     int64_t maxtrial, maxactual, nrhocalc, nactualtot, np, ncalls_neigh;
     int64_t npairs_density, npairs_force;  /* real interacting pairs (for roofline accounting) */
     int64_t nbinmaxnew;
-    int64_t reserved[3];
+    int64_t npairs_gravity, nm2l;
+    int64_t reserved[1];
 } oracle_scalars;
 
 typedef struct oracle_ctx oracle_ctx;

@@ -23,7 +23,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsphgpu.so")
 
 F_XYZH, F_VXYZU, F_FXYZU, F_FEXT, F_BEVOL, F_DBEVOL, F_EOSVARS, F_DIVCURLV, F_DIVCURLB, F_ALPHAIND, F_GRADH, F_DVDX, \
-    F_POTEN, F_DIVBSYMM, F_IPHASE, F_IBIN = [1 << k for k in range(16)]
+    F_POTEN, F_DIVBSYMM, F_IPHASE, F_IBIN, F_DUSTFRAC, F_TSTOP = [1 << k for k in range(18)]
 F_ALL = (1 << 64) - 1
 
 ERRORS = {1: "CUDA", 2: "ARG", 3: "NAN", 4: "NOPART", 5: "NOCONVERGE", 6: "NEGH", 7: "OVERFLOW", 8: "STATE"}
@@ -34,7 +34,7 @@ EXPORTS = [
     "sphgpu_cons2prim_resident", "sphgpu_force_resident", "sphgpu_derivs_resident", "sphgpu_build_tree", "sphgpu_densityiterate",
     "sphgpu_cons2prim_everything", "sphgpu_force", "sphgpu_derivs", "sphgpu_get_neighbour_stats", "sphgpu_neighbour_sets",
     "sphgpu_measure_fp64_peak", "sphgpu_measure_copy_bw", "sphgpu_local_hmax", "sphgpu_halo_select", "sphgpu_halo_pack",
-    "sphgpu_halo_recvbuf", "sphgpu_halo_unpack", "sphgpu_nghost",
+    "sphgpu_halo_recvbuf", "sphgpu_halo_unpack", "sphgpu_nghost", "sphgpu_set_timestep_bins", "sphgpu_get_gravity_timings", "sphgpu_gravity_tree",
 ]
 
 
@@ -47,7 +47,7 @@ class SphGpuError(RuntimeError):
 class HostArrays(C.Structure):
     _fields_ = [("npart", C.c_int64)] + [(k, C.c_void_p) for k in (
         "xyzh", "vxyzu", "fxyzu", "fext", "Bevol", "dBevol", "eos_vars", "divcurlv", "divcurlB", "alphaind", "gradh", "dvdx",
-        "poten", "divBsymm", "iphase", "ibin", "ibin_old", "ibin_wake")]
+        "poten", "divBsymm", "iphase", "ibin", "ibin_old", "ibin_wake", "dustfrac", "tstop")]
 
 
 _lib = None
@@ -99,6 +99,10 @@ def load_library():
         L.sphgpu_halo_unpack.argtypes = [vp, i32, i64]
         L.sphgpu_nghost.argtypes = [vp]
         L.sphgpu_nghost.restype = i64
+        L.sphgpu_set_timestep_bins.argtypes = [vp, i32, i32, i32]
+        L.sphgpu_get_gravity_timings.argtypes = [vp, C.POINTER(dbl)]
+        L.sphgpu_gravity_tree.argtypes = [vp, i64, vp, vp, vp]
+        L.sphgpu_gravity_tree.restype = i64
         _lib = L
     return _lib
 
@@ -160,6 +164,8 @@ class SphGpu:
         self._check(self.L.sphgpu_densityiterate(
             self.h, icall, part.npart, part.npart, _p(part.xyzh), _p(part.vxyzu), _p(part.divcurlv), _p(part.divcurlB), _p(part.Bevol),
             C.byref(stressmax), _p(part.fxyzu), _p(part.fext), _p(part.alphaind), _p(part.gradh), _p(part.dvdx), _p(part.iphase), C.byref(sc)))
+        if self.params.dust:               # hidden module output dustfrac (dens.F90:1612-1624)
+            self.download(part, F_DUSTFRAC)
         return sc
 
     def cons2prim_everything(self, part):
@@ -167,13 +173,25 @@ class SphGpu:
             self.h, part.npart, _p(part.xyzh), _p(part.vxyzu), _p(part.dvdx), _p(part.eos_vars), _p(part.Bevol), _p(part.Bxyz),
             _p(part.alphaind), _p(part.iphase)))
 
+    def set_timestep_bins(self, nbinmax, ibinnow, istepfrac):
+        """timestep_ind module inputs of the force pass (utils_indtimesteps.f90)"""
+        self._check(self.L.sphgpu_set_timestep_bins(self.h, int(nbinmax), int(ibinnow), int(istepfrac)))
+
     def force(self, part, icall=1, dt=0.0):
         sc = SphScalars()
+        if self.params.ind_timesteps:      # hidden module inputs ibin, ibin_old, ibin_wake (part.F90)
+            self.upload(part, F_IBIN)
+        self._force_literal(part, icall, dt, sc)
+        extra = (F_IBIN if self.params.ind_timesteps else 0) | (F_TSTOP if self.params.dust else 0)
+        if extra:                          # hidden module outputs ibin, ibin_wake, tstop
+            self.download(part, extra)
+        return sc
+
+    def _force_literal(self, part, icall, dt, sc):
         self._check(self.L.sphgpu_force(
             self.h, icall, part.npart, _p(part.xyzh), _p(part.vxyzu), _p(part.fxyzu), _p(part.divcurlv), _p(part.divcurlB), _p(part.Bevol),
             _p(part.dBevol), _p(part.fext), dt, 0.0, _p(part.eos_vars), _p(part.alphaind), _p(part.gradh), _p(part.dvdx), _p(part.iphase),
             _p(part.poten), _p(part.divBsymm), C.byref(sc)))
-        return sc
 
     def derivs(self, part, icall=1, dt=0.0):
         """derivs(icall,...) with host arrays in and out (deriv.f90:37)."""
@@ -231,6 +249,22 @@ class SphGpu:
         t = (C.c_double * 2)()
         self.L.sphgpu_get_kernel_timings(self.h, t)
         return dict(density=t[0], force=t[1])
+
+    def gravity_timings_ms(self):
+        t = (C.c_double * 2)()
+        self.L.sphgpu_get_gravity_timings(self.h, t)
+        return dict(total=t[0], p2p=t[1])
+
+    def gravity_tree(self, npart):
+        """kdnode records of the self-gravity tree after the last force call (see include/sphgpu.h)"""
+        nn = self.L.sphgpu_gravity_tree(self.h, 0, None, None, None)
+        if nn < 0:
+            raise SphGpuError(8, "no gravity tree: call force with gravity first")
+        rec = np.zeros((nn, 12))
+        irec = np.zeros((nn, 6), dtype=np.int32)
+        ids = np.zeros(npart, dtype=np.int32)
+        self.L.sphgpu_gravity_tree(self.h, nn, _p(rec), _p(irec), _p(ids))
+        return rec, irec, ids
 
     def launch_count(self):
         return self.L.sphgpu_launch_count(self.h)

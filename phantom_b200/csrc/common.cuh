@@ -91,11 +91,18 @@ struct sphgpu_ctx {
     std::string err;
     DevParams hp;              // host copy
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[12];
+    cudaEvent_t ev[16];
     int numSMs = 148;
     int64_t launches = 0;
     double ms_phase[4] = {0, 0, 0, 0};
     double ms_kernel[2] = {0, 0};   // k_density, k_force alone (CUDA events on the launching stream)
+    double ms_gravity[2] = {0, 0};  // whole gravity pass, k_g_p2p alone
+    int64_t npairs_gravity = 0, nm2l = 0;
+    int grav_p2p_per_particle = 48; // capacity of the leaf P2P lists (source leaves per particle)
+    struct GravState *grav = nullptr;
+    bool grav_tree_valid = false;
+    DevBuf<double> h_build, h_hist; // h at build_tree and after each h-rho iteration (replayed by k_g_hmax_leaf)
+    DevBuf<int> h_its;
     // tuning
     int max_cell = 32;       // target group: <= 32 particles (one lane per target)
     int max_leaf = 8;        // tree leaf (source granularity of the walk)
@@ -106,6 +113,8 @@ struct sphgpu_ctx {
     DevBuf<double> xyzh, vxyzu, fxyzu, fext, Bevol, dBevol, eos_vars, Bxyz;
     DevBuf<float> divcurlv, divcurlB, alphaind, gradh, dvdx, poten, divBsymm;
     DevBuf<int8_t> iphase, ibin, ibin_old, ibin_wake;
+    DevBuf<double> dustfrac, tstop;
+    DevBuf<double4> gacc;                   // far-field gravity {fx,fy,fz,pot} per particle (gravity.cu -> force epilogue)
     // ---- sorted working set ----
     int64_t nlive = 0;
     bool tree_valid = false, dens_valid = false;
@@ -139,6 +148,10 @@ struct sphgpu_ctx {
     DevBuf<unsigned long long> counters;    // device scalars block
     DevBuf<double> dscal;                   // device double scalars (bbox, dt minima, ...)
     sphgpu_scalars last_dens{}, last_force{};
+    int nbinmax = 0, ibinnow = 0, istepfrac = 0;   // timestep_ind module state
+    DevBuf<int8_t> s_ibin, s_ibinold, s_ibinnew;   // sorted copies for the force pass
+    DevBuf<int> s_wake;
+    DevBuf<double> s_gsoft, s_tstop, s_dustfrac;
     // ---- multi-GPU halo state (halo.cu): ghosts are appended after the nlocal owned particles as inactive particles ----
     int64_t nlocal = 0, nghost = 0;
     int halo_nranks = 1, halo_rank = 0;
@@ -230,7 +243,7 @@ __device__ __forceinline__ void atomic_max_pos(double *addr, double v) { atomicM
 
 // indices into ctx->counters (unsigned long long)
 enum { CNT_WORK = 0, CNT_ERR, CNT_ERRID, CNT_NPAIRS, CNT_NTRIAL, CNT_NCALC, CNT_NACT, CNT_MAXACT, CNT_MAXTRIAL, CNT_NP, CNT_NWALK, CNT_NLIVE, CNT_NBINMAX, CNT_NCHECKBIN, CNT_MULTITYPE, CNT_NSURV,
-       CNT_COUNT = 32 };
+       CNT_NGRAVPAIRS = 24, CNT_NM2L = 25, CNT_COUNT = 32 };
 // indices into ctx->dscal (double)
 enum { DS_XMIN = 0, DS_YMIN, DS_ZMIN, DS_XMAX, DS_YMAX, DS_ZMAX, DS_DTCOURANT, DS_DTFORCE, DS_DTMINI, DS_DTMAXI, DS_RHOMAX, DS_COUNT = 32 };
 
@@ -240,6 +253,10 @@ int tree_refit_hmax(sphgpu_ctx *c);
 int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out);
 int cons2prim_run(sphgpu_ctx *c);
 int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out);
+int gravity_run(sphgpu_ctx *c);
+void gravity_release(sphgpu_ctx *c);
+int64_t gravity_tree_dump(sphgpu_ctx *c, int64_t maxnodes, double *rec12, int32_t *irec6, int32_t *ids);
+#define SPHGPU_HHIST 6   // h-rho iterations logged per particle for the node-hmax replay
 int64_t neighbour_sets_run(sphgpu_ctx *c, int symmetric, int64_t *offsets, int32_t *list, int64_t maxlist);
 KernConsts make_kern_consts(int kernel);
 int ensure_all_keep(sphgpu_ctx *c, int64_t n, int64_t keep);

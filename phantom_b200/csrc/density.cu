@@ -25,7 +25,8 @@ struct DensArgs {
     const TreeNodeF *nodes; const Cell *cells; int ncells; const Cell *groups; int ngroups;
     const double4 *pos4, *vel4, *acc4, *bev4; const int8_t *stype; const int *perm;
     float4 *stage_pos; int *stage_idx; int multitype; double hmax_global;
-    double *hnew; float *s_gradh, *s_divv, *s_dvdx, *s_alpha3, *s_divcurlB; int *s_nneigh;
+    double *hnew; float *s_gradh, *s_divv, *s_dvdx, *s_alpha3, *s_divcurlB; int *s_nneigh; double *s_dustfrac;
+    double *h_hist; int *h_its; int64_t npart;     // GRAV: per-particle h after every iteration, for the node-hmax replay of gravity.cu
     int scratch_per_warp; unsigned long long *cnt; double *dscal;
     double margin; int icall;
 };
@@ -56,7 +57,8 @@ __global__ void k_scatter_dens(int64_t nlive, const int *__restrict__ perm, cons
                                double4 *__restrict__ pos4, double *__restrict__ xyzh, const float *__restrict__ s_gradh, const float *__restrict__ s_divv,
                                const float *__restrict__ s_dvdx, const float *__restrict__ s_alpha3, const float *__restrict__ s_divcurlB,
                                float *__restrict__ gradh, float *__restrict__ divcurlv, float *__restrict__ dvdx, float *__restrict__ alphaind,
-                               float *__restrict__ divcurlB, int ngradh, int nalpha, int mhd)
+                               float *__restrict__ divcurlB, int ngradh, int nalpha, int mhd, const double *__restrict__ s_dustfrac,
+                               double *__restrict__ dustfrac)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nlive) return;
@@ -71,6 +73,7 @@ __global__ void k_scatter_dens(int64_t nlive, const int *__restrict__ perm, cons
     for (int k = 0; k < 9; k++) dvdx[9 * (size_t)i + k] = s_dvdx[9 * (size_t)s + k];
     if (nalpha >= 3) alphaind[3 * (size_t)i + 2] = s_alpha3[s];
     if (mhd) for (int k = 0; k < 4; k++) divcurlB[4 * (size_t)i + k] = s_divcurlB[4 * (size_t)s + k];
+    if (s_dustfrac) dustfrac[i] = s_dustfrac[s];
 }
 
 // pair body: lane = target, j = this lane's next neighbour candidate (slot < 0: none).  Branch-free so that two
@@ -274,7 +277,10 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
                         atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_NOCONVERGE);
                         atomicMax(&a.cnt[CNT_ERRID], (unsigned long long)(a.perm[s] + 1));
                         failed = true; conv = true;
-                    } else h = hnew;
+                    } else {
+                        h = hnew;
+                        if (GRAV && its <= SPHGPU_HHIST) a.h_hist[(size_t)(its - 1) * a.npart + a.perm[s]] = hnew;
+                    }
                 }
             }
             if (__all_sync(FULLMASK, conv)) break;
@@ -298,6 +304,7 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
             }
             gradhi = (double)gradh4;                                                  // dens.F90:1610
             const double rho1i = 1. / rho;
+            if (dp.p.dust) a.s_dustfrac[s] = gasi ? (KF::cnormk * dp.p.massoftype[IDUST] * v[S_RHODUST] * hi31) * rho1i : 0.;   // dens.F90:1612-1624
             const double term = KF::cnormk * gradhi * rho1i * hi41;
             const double rxx = v[S_RXX], rxy = v[S_RXY], rxz = v[S_RXZ], ryy = v[S_RYY], ryz = v[S_RYZ], rzz = v[S_RZZ];
             const double denom = rxx * ryy * rzz + 2. * rxy * rxz * ryz - rxx * ryz * ryz - ryy * rxz * rxz - rzz * rxy * rxy;
@@ -345,6 +352,7 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
             }
             const int nn = nneighi + 1;   // + self
             a.s_nneigh[s] = nn;
+            if (GRAV) a.h_its[a.perm[s]] = its_lane;
             st_rhomax = fmax(st_rhomax, rho);
             st_pairs += (unsigned long long)nneighi * its_lane;
             st_ncalc += its_lane; st_nact += nn; st_np += 1;
@@ -400,6 +408,7 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     CUDA_TRY(c, c->vel4.ensure(n)); CUDA_TRY(c, c->acc4.ensure(n)); if (p.mhd) CUDA_TRY(c, c->bev4.ensure(n));
     CUDA_TRY(c, c->hnew.ensure(n)); CUDA_TRY(c, c->s_gradh.ensure(n * c->hp.ngradh)); CUDA_TRY(c, c->s_divv.ensure(n));
     CUDA_TRY(c, c->s_dvdx.ensure(9 * n)); CUDA_TRY(c, c->s_alpha3.ensure(n)); CUDA_TRY(c, c->s_divcurlB.ensure(4 * n)); CUDA_TRY(c, c->s_nneigh.ensure(n));
+    if (p.dust) CUDA_TRY(c, c->s_dustfrac.ensure(n));
     int bps = 3;     // persistent grid = resident CTAs/SM x SMs (register/smem limited; queried per instantiation below)
     {
         const bool mhd = p.mhd, grav = p.gravity;
@@ -419,17 +428,19 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.acc4 = c->acc4.p; a.bev4 = c->bev4.p; a.stype = c->stype.p; a.perm = c->perm.p;
     a.hnew = c->hnew.p; a.s_gradh = c->s_gradh.p; a.s_divv = c->s_divv.p; a.s_dvdx = c->s_dvdx.p; a.s_alpha3 = c->s_alpha3.p;
-    a.s_divcurlB = c->s_divcurlB.p; a.s_nneigh = c->s_nneigh.p;
+    a.s_divcurlB = c->s_divcurlB.p; a.s_nneigh = c->s_nneigh.p; a.s_dustfrac = c->s_dustfrac.p;
     a.stage_pos = c->stage_pos.p; a.stage_idx = c->stage_idx.p; a.multitype = c->multitype ? 1 : 0; a.hmax_global = 0.;
     a.scratch_per_warp = c->scratch_per_warp; a.cnt = c->counters.p; a.dscal = c->dscal.p;
     a.margin = c->list_margin; a.icall = icall;
+    a.h_hist = c->h_hist.p; a.h_its = c->h_its.p; a.npart = n;
+    c->grav_tree_valid = false;            // h changes below: the gravity tree caches h
     cudaEventRecord(c->ev[8], c->stream);
     if (p.kernel == 0) { if (p.periodic) dispatch_density2<0, true>(c, a, grid); else dispatch_density2<0, false>(c, a, grid); }
     else { if (p.periodic) dispatch_density2<1, true>(c, a, grid); else dispatch_density2<1, false>(c, a, grid); }
     cudaEventRecord(c->ev[9], c->stream);
     k_scatter_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->hnew.p, c->pos4.p, c->xyzh.p, c->s_gradh.p, c->s_divv.p, c->s_dvdx.p,
                                                          c->s_alpha3.p, c->s_divcurlB.p, c->gradh.p, c->divcurlv.p, c->dvdx.p, c->alphaind.p, c->divcurlB.p,
-                                                         c->hp.ngradh, c->hp.nalpha, p.mhd);
+                                                         c->hp.ngradh, c->hp.nalpha, p.mhd, p.dust ? c->s_dustfrac.p : nullptr, c->dustfrac.p);
     c->launches++;
     TRY(tree_refit_hmax(c));          // set_hmaxcell (neigh_kdtree.f90:115-131): the force walk needs the new hmax
     unsigned long long hc[16]; double hrhomax;

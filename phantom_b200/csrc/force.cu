@@ -1,7 +1,9 @@
 // force.cu -- force pass: replaces force (src/main/force.F90:193-905) with start_cell/get_stress (:2172-2514, :2068-2168),
 // compute_forces (:914-2060) and finish_cell_and_store_results (:2649-3330), for hydro + artificial viscosity
 // (Cullen-Dehnen alpha per particle or constant, optional disc viscosity) + artificial conductivity + ideal MHD with
-// artificial resistivity and hyperbolic/parabolic div-B cleaning.
+// artificial resistivity and hyperbolic/parabolic div-B cleaning; and, in the XTRA instantiation, the softened
+// self-gravity of SPH-neighbour pairs (:1303-1339; the far field comes from gravity.cu), two-fluid gas-dust drag
+// (:1852-1989, get_ts of dust.f90:161-276, reconstruct_dv :3338-3372) and individual timestep bins (:1346-1358, :3272-3310).
 //
 // Same warp-per-leaf-cell skeleton as the density pass (walk.cuh) with the symmetric neighbour criterion
 // q2i < R^2 .or. q2j < R^2 (force.F90:1287).  What the reference recomputes per pair for particle j
@@ -10,6 +12,7 @@
 #include "walk.cuh"
 #include "sphkern.cuh"
 #include <float.h>
+#include <string.h>
 
 namespace {
 
@@ -20,7 +23,13 @@ struct ForceArgs {
     double4 *s_fxyzu, *s_dB; float *s_divvf, *s_divBsymm; int *s_done;
     int scratch_per_warp; unsigned long long *cnt; double *dscal;
     int icall;
+    // XTRA (gravity / dust / individual timesteps) only
+    const double *gsoft; const float *dvdx9; const double4 *gacc; float *s_poten; double *s_tstop;
+    const int8_t *s_ibinold, *s_ibin; int *s_wake; int8_t *s_ibinnew;
+    int nbinmax, ibinnow_m1, istepfrac;
 };
+
+struct XtraSums { double fdx, fdy, fdz, tsmin; int ibin_neigh; };
 
 enum { A_FX = 0, A_FY, A_FZ, A_DRHODT, A_DUDTDISS, A_DENDTDISS, A_DIVBSYM, A_DBX, A_DBY, A_DBZ, A_DIVBDIFF, A_POT };
 
@@ -29,7 +38,9 @@ __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const 
                              const double *__restrict__ vxyzu, const double *__restrict__ Bevol, const double *__restrict__ eos_vars,
                              const float *__restrict__ alphaind, const float *__restrict__ gradh, double4 *__restrict__ vel4, double4 *__restrict__ recC,
                              double4 *__restrict__ recD, double4 *__restrict__ recE, double2 *__restrict__ hinv, int *__restrict__ s_done,
-                             const __grid_constant__ DevParams dp, unsigned long long *cnt)
+                             const __grid_constant__ DevParams dp, unsigned long long *cnt, double *__restrict__ gsoft, const float *__restrict__ dvdx,
+                             float *__restrict__ dvdx9, const int8_t *__restrict__ ibin, const int8_t *__restrict__ ibin_old,
+                             const int8_t *__restrict__ ibin_wake, int8_t *__restrict__ s_ibin, int8_t *__restrict__ s_ibinold, int *__restrict__ s_wake)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nlive) return;
@@ -69,15 +80,59 @@ __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const 
     recD[s] = make_double4(rho1, gradhfac, pmass, cs);
     if (p.mhd) recE[s] = E;
     s_done[s] = 0;
+    if (p.gravity) gsoft[s] = (double)gradh[(size_t)dp.ngradh * i + 1];
+    if (p.dust) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) dvdx9[9 * (size_t)s + k] = dvdx[9 * (size_t)i + k];
+    }
+    if (p.ind_timesteps) { s_ibin[s] = ibin[i]; s_ibinold[s] = ibin_old[i]; s_wake[s] = (int)ibin_wake[i]; }
+}
+
+// get_ts (dust.f90:161-276): stopping time of a gas-dust pair
+__device__ __forceinline__ double get_ts_d(const sphgpu_params &p, double rhogas, double rhodust, double spsoundgas, double dv2)
+{
+    const double pi = 3.14159265358979323846264338327950288;
+    const double rhosum = rhogas + rhodust;
+    const double sgrain = p.grainsize, densgrain = p.graindens;
+    if (p.idrag == 1) {
+        const double cste_mu = sqrt(2. / (pi * p.gamma)), coeff_gei_1 = sqrt(8. / (pi * p.gamma));
+        double dragcoeff, f;
+        const double lambda = p.seff / rhogas;
+        const double kn_eff = (sgrain > 0.) ? 9. * lambda / (4. * sgrain) : DBL_MAX;
+        if (kn_eff >= 1.) {                               // Epstein, with the Kwok (1975) supersonic correction
+            dragcoeff = (densgrain > DBL_MIN) ? coeff_gei_1 * spsoundgas / (densgrain * sgrain) : DBL_MAX;
+            f = (spsoundgas > 0. && dv2 > 0.) ? sqrt(1. + 9. * pi / 128. * dv2 / (spsoundgas * spsoundgas)) : 1.;
+        } else {                                          // Stokes, three Reynolds-number regimes
+            const double viscmol_nu = cste_mu * lambda * spsoundgas;
+            const double abs_dv = sqrt(dv2);
+            const double Re_dust = 2. * sgrain * abs_dv / viscmol_nu;
+            if (Re_dust <= 1.) { dragcoeff = 4.5 * viscmol_nu / (densgrain * sgrain * sgrain); f = 1.; }
+            else if (Re_dust <= 800.) { dragcoeff = 9. / (densgrain * sgrain * pow(Re_dust, 0.6)); f = abs_dv; }
+            else { dragcoeff = 0.163075 / (densgrain * sgrain); f = abs_dv; }
+        }
+        const double ts1 = (dragcoeff == DBL_MAX) ? DBL_MAX : dragcoeff * f * rhosum;
+        return (ts1 > 0.) ? 1. / ts1 : DBL_MAX;
+    }
+    if (p.idrag == 2) return (p.K_code > 0.) ? rhogas * rhodust / (p.K_code * rhosum) : DBL_MAX;
+    if (p.idrag == 3) return p.K_code;
+    return 0.;
+}
+
+// slope of the velocity along the pair direction (reconstruct_dv, force.F90:3348-3354)
+__device__ __forceinline__ double recon_slope(const float *__restrict__ d, double dx, double dy, double dz, double rx, double ry, double rz)
+{
+    return dx * (rx * (double)d[0] + ry * (double)d[3] + rz * (double)d[6]) + dy * (rx * (double)d[1] + ry * (double)d[4] + rz * (double)d[7]) +
+           dz * (rx * (double)d[2] + ry * (double)d[5] + rz * (double)d[8]);
 }
 
 // pair body: lane = target, j = this lane's next neighbour candidate (slot < 0: none).  Branch-free: the exact membership
 // test (force.F90:1271-1287, :1230) and the gas-gas condition (:1539) become zero weights on grad W_i, grad W_j, through
 // which every sum of compute_forces scales; two calls per trip give two independent FP64 dependency chains.
-template <int K, bool PERIODIC, bool MHD>
+template <int K, bool PERIODIC, bool MHD, bool XTRA>
 __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int &npair, int slot, const int *__restrict__ idxlist, int s,
                                            const double4 &pi, double hi, double hi1, double hi21, bool gasi, const double4 &vi, const double4 &Ci,
-                                           const double4 &Di, const double4 &Ei, const ForceArgs &a, const DevParams &dp, double Lx, double Ly, double Lz)
+                                           const double4 &Di, const double4 &Ei, const ForceArgs &a, const DevParams &dp, double Lx, double Ly, double Lz,
+                                           XtraSums &xs, int itypei)
 {
     typedef SphKern<K> KF;
     const sphgpu_params &p = dp.p;
@@ -101,9 +156,52 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
     const double rij = r2s * rij1;
     const double qi = rij * hi1, qj = rij * hj1;
     const double pmassj = Dj.z, pmassi = Di.z;
-    const bool ini = gg && (q2i < KF::radkern2), inj = gg && (q2j < KF::radkern2);
-    const double grkerni = ini ? KF::grkern(q2i, qi) * Di.y : 0.;             // :1301-1302
-    const double grkernj = inj ? KF::grkern(q2j, qj) * Dj.y : 0.;             // :1325-1327
+    double grkerni, grkernj;
+    if (XTRA) {
+        // kernel gradients for every pair type (gravity and drag use them), masked to gas-gas for the hydro sums below
+        const bool ki = isn && (q2i < KF::radkern2), kj = isn && (q2j < KF::radkern2);
+        const double gri = ki ? KF::grkern(q2i, qi) * Di.y : 0., grj = kj ? KF::grkern(q2j, qj) * Dj.y : 0.;
+        if (p.ind_timesteps && isn && itypej != IBOUNDARY) {                  // force.F90:1346-1358
+            if (a.s_wake[j] < a.ibinnow_m1) atomicMax(&a.s_wake[j], a.ibinnow_m1);
+            xs.ibin_neigh = max(xs.ibin_neigh, (int)a.s_ibinold[j]);
+        }
+        if (p.gravity && isn) {                                               // force.F90:1303-1339, :1522
+            double phii, fgravi, fgravj;
+            if (ki) { double fmi; KF::softening(q2i, qi, phii, fmi); phii *= hi1; fgravi = fmi * hi21 + a.gsoft[s] * gri; }
+            else { phii = -rij1; fgravi = rij1 * rij1; }
+            if (kj) { double phij, fmj; KF::softening(q2j, qj, phij, fmj); fgravj = fmj * hj21 + a.gsoft[j] * grj; }
+            else fgravj = rij1 * rij1;
+            const double fgrav = 0.5 * (Dj.z * fgravi + Di.z * fgravj);
+            f[A_FX] -= dx * rij1 * fgrav; f[A_FY] -= dy * rij1 * fgrav; f[A_FZ] -= dz * rij1 * fgrav;
+            f[A_POT] += Dj.z * phii;
+        }
+        if (p.dust && p.idrag > 0 && isn) {                                   // force.F90:1864-1970 (explicit drag, large grains)
+            const bool dusti = (itypei == IDUST), dustj = (itypej == IDUST);
+            const bool gas_dust = gasi && dustj, dust_gas = dusti && gasj;
+            if (gas_dust || dust_gas) {
+                const double rx = dx * rij1, ry = dy * rij1, rz = dz * rij1;
+                const double pv = (vi.x - vj.x) * rx + (vi.y - vj.y) * ry + (vi.z - vj.z) * rz;
+                const double sl = recon_slope(a.dvdx9 + 9 * (size_t)s, dx, dy, dz, rx, ry, rz);
+                const double sr = recon_slope(a.dvdx9 + 9 * (size_t)j, dx, dy, dz, rx, ry, rz);
+                double slope = 0.;                                            // Van Leer MC limiter (force.F90:3419-3438), irecon = 1
+                if (sl * sr > 0.) slope = copysign(1.0, sl) * fmin(fmin(fabs(0.5 * (sl + sr)), 2. * fabs(sl)), 2. * fabs(sr));
+                const double projvstar = pv - slope;
+                const double dv2 = projvstar * projvstar;
+                const double wdrag = (q2i < q2j) ? KF::wdrag(q2i, qi) * hi21 * hi1 * KF::cnormk_drag : KF::wdrag(q2j, qj) * hj21 * hj1 * KF::cnormk_drag;
+                const double rhoi = 1. / Di.x, rhoj = 1. / Dj.x;
+                const double ts = gas_dust ? get_ts_d(p, rhoi, rhoj, Di.w, dv2) : get_ts_d(p, rhoj, rhoi, Dj.w, dv2);
+                const double dragterm = 3. * Dj.z / ((rhoi + rhoj) * ts) * projvstar * wdrag;
+                xs.tsmin = fmin(xs.tsmin, ts);
+                xs.fdx -= dragterm * rx; xs.fdy -= dragterm * ry; xs.fdz -= dragterm * rz;
+                if (gas_dust && dp.nvu >= 4) f[A_DUDTDISS] += dragterm * pv;
+            }
+        }
+        grkerni = gg ? gri : 0.; grkernj = gg ? grj : 0.;
+    } else {
+        const bool ini = gg && (q2i < KF::radkern2), inj = gg && (q2j < KF::radkern2);
+        grkerni = ini ? KF::grkern(q2i, qi) * Di.y : 0.;                      // :1301-1302
+        grkernj = inj ? KF::grkern(q2j, qj) * Dj.y : 0.;                      // :1325-1327
+    }
     bool usej = (q2j < KF::radkern2);
     if (MHD) usej = true;
     if (p.dust) usej = true;
@@ -182,8 +280,8 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
     if (dp.nvu >= 4) f[A_DUDTDISS] += dudtdissi + dudtresist;
 }
 
-template <int K, bool PERIODIC, bool MHD>
-__global__ void __launch_bounds__(128, 4) k_force(const ForceArgs a, const __grid_constant__ DevParams dp)
+template <int K, bool PERIODIC, bool MHD, bool XTRA>
+__global__ void __launch_bounds__(128, XTRA ? 2 : 4) k_force(const ForceArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
     __shared__ WarpShared wsh[4];
@@ -198,6 +296,7 @@ __global__ void __launch_bounds__(128, 4) k_force(const ForceArgs a, const __gri
     const sphgpu_params &p = dp.p;
     unsigned long long st_pairs = 0, st_trial = 0;
     double st_dtc = 1.e29, st_dtf = 1.e29, st_dtmin = 1.e29, st_dtmax = 0.;
+    int st_nbinmax = 0, st_ncheckbin = 0;
     const float hmax_global = (a.ncells > 1) ? fmaxf(a.nodes[0].hmax[0], a.nodes[0].hmax[1]) : 0.f;
 
     while (true) {
@@ -238,6 +337,7 @@ __global__ void __launch_bounds__(128, 4) k_force(const ForceArgs a, const __gri
         for (int k = 0; k < 12; k++) f[k] = 0.;
         double vsigmax = 0.;
         int npair = 0;
+        XtraSums xs; xs.fdx = xs.fdy = xs.fdz = 0.; xs.tsmin = 1.e29; xs.ibin_neigh = 0;
         for (int base = 0; base < nlist; base += MAXCHUNK * 32) {
             const int nchunk = min(MAXCHUNK, (nlist - base + 31) >> 5);
             if (wide) build_masks<false>(ws, st, base, nchunk, cell.count, slack);
@@ -248,8 +348,8 @@ __global__ void __launch_bounds__(128, 4) k_force(const ForceArgs a, const __gri
                 const int slot1 = (slot0 < 0) ? -1 : next_hit(ws, lane, nchunk, c, m);
                 if (!__any_sync(FULLMASK, slot0 >= 0)) break;
                 if (slot0 >= 0) {
-                    force_pair<K, PERIODIC, MHD>(f, vsigmax, npair, slot0, st.idx + base, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz);
-                    force_pair<K, PERIODIC, MHD>(f, vsigmax, npair, slot1, st.idx + base, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz);
+                    force_pair<K, PERIODIC, MHD, XTRA>(f, vsigmax, npair, slot0, st.idx + base, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei);
+                    force_pair<K, PERIODIC, MHD, XTRA>(f, vsigmax, npair, slot1, st.idx + base, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei);
                 }
             }
             __syncwarp();
@@ -259,8 +359,15 @@ __global__ void __launch_bounds__(128, 4) k_force(const ForceArgs a, const __gri
             st_pairs += npair; st_trial += nlist;
             const double pmassi = Di.z;
             double fx = f[A_FX], fy = f[A_FY], fz = f[A_FZ];
-            double dtc = p.dtmax, dtf = 1.e29, dtclean = 1.e29;
+            double dtc = p.dtmax, dtf = 1.e29, dtclean = 1.e29, dtdrag = 1.e29;
             double fxyz4 = 0., divvi = 0.;
+            if (XTRA && p.gravity) {                                 // force.F90:2909-2927: far field (L2P + distant P2P) from gravity.cu
+                const double4 g = a.gacc[a.perm[s]];
+                double potensoft0, dum;
+                KF::softening(0., 0., potensoft0, dum);
+                fx += g.x; fy += g.y; fz += g.z;
+                a.s_poten[s] = (float)(0.5 * pmassi * (f[A_POT] + pmassi * potensoft0 * hi1) + 0.5 * pmassi * g.w);
+            }
             double4 dB = make_double4(0., 0., 0., 0.);
             float divBsymm4 = 0.f;
             if (gasi) {
@@ -306,19 +413,48 @@ __global__ void __launch_bounds__(128, 4) k_force(const ForceArgs a, const __gri
             }
             const double f2i = fx * fx + fy * fy + fz * fz;
             if (fabs(f2i) > DBL_EPSILON) dtf = p.C_force * sqrt(h / sqrt(f2i));                  // force.F90:3217-3219
+            if (XTRA && p.dust) {                                    // force.F90:2978-2988, :3239-3246
+                fx += xs.fdx; fy += xs.fdy; fz += xs.fdz;
+                a.s_tstop[s] = xs.tsmin;
+                dtdrag = 0.9 * xs.tsmin;
+            }
             a.s_fxyzu[s] = make_double4(fx, fy, fz, fxyz4);
             a.s_divvf[s] = (float)divvi;
             if (MHD) { a.s_dB[s] = dB; a.s_divBsymm[s] = divBsymm4; }
             a.s_done[s] = gasi ? 2 : 1;
-            st_dtc = fmin(st_dtc, dtc);
-            st_dtf = fmin(st_dtf, fmin(dtf, dtclean));
-            st_dtmin = fmin(st_dtmin, dtc); st_dtmax = fmax(st_dtmax, dtc);
+            if (XTRA && p.ind_timesteps) {                           // force.F90:3272-3310 + get_newbin (utils_indtimesteps.f90:230-287)
+                double dti = dtc;
+                const double dtitmp = fmin(fmin(dtf, dtclean), dtdrag);
+                if (dtitmp < dti + DBL_MIN && dtitmp < p.dtmax) dti = dtitmp;
+                const int ibin_oldi = (int)a.s_ibin[s];
+                int ibin_newi;
+                if (dti > p.dtmax) ibin_newi = 0;
+                else if (dti < DBL_MIN) ibin_newi = 30;
+                else ibin_newi = max((int)(log(2. * p.dtmax / dti) * 1.4426950408889634 - DBL_EPSILON), 0);
+                int ibini = ibin_oldi;
+                if (ibin_newi > ibin_oldi) ibini = ibin_newi;
+                else if (ibin_newi < ibin_oldi && ibin_oldi <= a.nbinmax && a.icall < 2) {
+                    if (a.istepfrac % (1 << (a.nbinmax - (ibin_oldi - 1))) == 0) ibini = ibini - 1;
+                }
+                ibini = max(ibini, xs.ibin_neigh - 1);               // Saitoh-Makino limiter
+                a.s_ibinnew[s] = (int8_t)ibini;
+                st_nbinmax = max(st_nbinmax, ibini); st_ncheckbin += 1;
+            } else {
+                st_dtc = fmin(st_dtc, dtc);
+                st_dtf = fmin(st_dtf, fmin(fmin(dtf, dtdrag), dtclean));
+                st_dtmin = fmin(st_dtmin, dtc); st_dtmax = fmax(st_dtmax, dtc);
+            }
         }
         __syncwarp();
     }
     st_dtc = warp_min(st_dtc); st_dtf = warp_min(st_dtf); st_dtmin = warp_min(st_dtmin); st_dtmax = warp_max(st_dtmax);
 #pragma unroll
     for (int sft = 16; sft >= 1; sft >>= 1) { st_pairs += __shfl_xor_sync(FULLMASK, st_pairs, sft); st_trial += __shfl_xor_sync(FULLMASK, st_trial, sft); }
+    if (XTRA) {
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) { st_nbinmax = max(st_nbinmax, __shfl_xor_sync(FULLMASK, st_nbinmax, sft)); st_ncheckbin += __shfl_xor_sync(FULLMASK, st_ncheckbin, sft); }
+        if (lane == 0 && st_ncheckbin) { atomicMax(&a.cnt[CNT_NBINMAX], (unsigned long long)st_nbinmax); atomicAdd(&a.cnt[CNT_NCHECKBIN], (unsigned long long)st_ncheckbin); }
+    }
     if (lane == 0) {
         atomicAdd(&a.cnt[CNT_NPAIRS], st_pairs); atomicAdd(&a.cnt[CNT_NTRIAL], st_trial);
         atomic_min_pos(&a.dscal[DS_DTCOURANT], st_dtc); atomic_min_pos(&a.dscal[DS_DTFORCE], st_dtf);
@@ -329,13 +465,19 @@ __global__ void __launch_bounds__(128, 4) k_force(const ForceArgs a, const __gri
 __global__ void k_scatter_force(int64_t nlive, const int *__restrict__ perm, const int *__restrict__ s_done, const double4 *__restrict__ s_fxyzu,
                                 const double4 *__restrict__ s_dB, const float *__restrict__ s_divvf, const float *__restrict__ s_divBsymm,
                                 double *__restrict__ fxyzu, double *__restrict__ dBevol, float *__restrict__ divcurlv, float *__restrict__ divBsymm, int nvu,
-                                int mhd)
+                                int mhd, int gravity, int dust, int ind_ts, const float *__restrict__ s_poten, float *__restrict__ poten,
+                                const double *__restrict__ s_tstop, double *__restrict__ tstop, const int8_t *__restrict__ s_ibinnew,
+                                int8_t *__restrict__ ibin, const int *__restrict__ s_wake, int8_t *__restrict__ ibin_wake)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nlive) return;
     const int d = s_done[s];
-    if (d == 0) return;
     const int i = perm[s];
+    if (ind_ts) ibin_wake[i] = (int8_t)s_wake[s];                    // neighbours of active particles, active or not
+    if (d == 0) return;
+    if (gravity) poten[i] = s_poten[s];
+    if (dust) tstop[i] = s_tstop[s];
+    if (ind_ts) ibin[i] = s_ibinnew[s];
     const double4 f = s_fxyzu[s];
     double *fi = fxyzu + (size_t)nvu * i;
     fi[0] = f.x; fi[1] = f.y; fi[2] = f.z;
@@ -346,12 +488,34 @@ __global__ void k_scatter_force(int64_t nlive, const int *__restrict__ perm, con
     }
 }
 
-template <int K, bool PERIODIC>
-void dispatch_force(sphgpu_ctx *c, const ForceArgs &a, int grid)
+// grid < 0: only query the resident CTAs/SM of the instantiation; otherwise launch on `grid` CTAs
+template <int K, bool PERIODIC, bool MHD, bool XTRA>
+int launch_force(sphgpu_ctx *c, const ForceArgs &a, int grid)
 {
-    if (c->hp.p.mhd) k_force<K, PERIODIC, true><<<grid, 128, 0, c->stream>>>(a, c->hp);
-    else k_force<K, PERIODIC, false><<<grid, 128, 0, c->stream>>>(a, c->hp);
+    if (grid < 0) {
+        int bps = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force<K, PERIODIC, MHD, XTRA>, 128, 0);
+        return bps < 1 ? 1 : bps;
+    }
+    k_force<K, PERIODIC, MHD, XTRA><<<grid, 128, 0, c->stream>>>(a, c->hp);
     c->launches++;
+    return 0;
+}
+
+template <int K, bool PERIODIC>
+int dispatch_force2(sphgpu_ctx *c, const ForceArgs &a, int grid)
+{
+    const sphgpu_params &p = c->hp.p;
+    const bool xtra = p.gravity || p.dust || p.ind_timesteps;
+    if (p.mhd) return xtra ? launch_force<K, PERIODIC, true, true>(c, a, grid) : launch_force<K, PERIODIC, true, false>(c, a, grid);
+    return xtra ? launch_force<K, PERIODIC, false, true>(c, a, grid) : launch_force<K, PERIODIC, false, false>(c, a, grid);
+}
+
+int dispatch_force(sphgpu_ctx *c, const ForceArgs &a, int grid)
+{
+    const sphgpu_params &p = c->hp.p;
+    if (p.kernel == 0) return p.periodic ? dispatch_force2<0, true>(c, a, grid) : dispatch_force2<0, false>(c, a, grid);
+    return p.periodic ? dispatch_force2<1, true>(c, a, grid) : dispatch_force2<1, false>(c, a, grid);
 }
 
 }  // namespace
@@ -364,37 +528,42 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     if (!c->tree_valid) { c->err = "force: build_tree has not been called"; return SPHGPU_ERR_STATE; }
     const int64_t n = c->npart, nl = c->nlive;
     const sphgpu_params &p = c->hp.p;
-    if (p.gravity || p.dust || p.ind_timesteps) { c->err = "force: GRAVITY / DUST / IND_TIMESTEPS force terms are not built yet"; return SPHGPU_ERR_ARG; }
+    if (p.gravity) TRY(gravity_run(c));                                    // far field -> c->gacc (canonical order)
     CUDA_TRY(c, c->vel4.ensure(n)); CUDA_TRY(c, c->frecC.ensure(n)); CUDA_TRY(c, c->frecD.ensure(n)); if (p.mhd) CUDA_TRY(c, c->frecE.ensure(n));
     CUDA_TRY(c, c->hnew.ensure(2 * n));                                    // reused as double2 hinv
     CUDA_TRY(c, c->s_fxyzu.ensure(n)); if (p.mhd) { CUDA_TRY(c, c->s_dB.ensure(n)); CUDA_TRY(c, c->s_divBsymm.ensure(n)); }
     CUDA_TRY(c, c->s_divvf.ensure(n)); CUDA_TRY(c, c->s_nneigh.ensure(n));
-    int bps = 3;     // persistent grid = resident CTAs/SM x SMs
-    if (p.kernel == 0 && p.periodic && !p.mhd) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force<0, true, false>, 128, 0);
-    else if (p.kernel == 1 && p.periodic && !p.mhd) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force<1, true, false>, 128, 0);
-    else if (p.kernel == 0 && p.periodic && p.mhd) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force<0, true, true>, 128, 0);
-    if (bps < 1) bps = 1;
-    const int grid = c->numSMs * bps;
+    if (p.gravity) { CUDA_TRY(c, c->s_gsoft.ensure(n)); CUDA_TRY(c, c->s_poten.ensure(n)); }
+    if (p.dust) { CUDA_TRY(c, c->s_dvdx.ensure(9 * n)); CUDA_TRY(c, c->s_tstop.ensure(n)); }
+    if (p.ind_timesteps) { CUDA_TRY(c, c->s_ibin.ensure(n)); CUDA_TRY(c, c->s_ibinold.ensure(n)); CUDA_TRY(c, c->s_ibinnew.ensure(n)); CUDA_TRY(c, c->s_wake.ensure(n)); }
+    ForceArgs a;
+    memset(&a, 0, sizeof a);
+    const int grid = c->numSMs * dispatch_force(c, a, -1);
     CUDA_TRY(c, c->stage_pos.ensure((size_t)grid * 4 * c->scratch_per_warp)); CUDA_TRY(c, c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp));
     CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
     const double init[4] = {1.e29, 1.e29, 1.e29, 0.};
     CUDA_TRY(c, cudaMemcpyAsync(c->dscal.p + DS_DTCOURANT, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     double2 *hinv = reinterpret_cast<double2 *>(c->hnew.p);
     k_force_prep<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->pos4.p, c->stype.p, c->vxyzu.p, c->Bevol.p, c->eos_vars.p, c->alphaind.p, c->gradh.p,
-                                                       c->vel4.p, c->frecC.p, c->frecD.p, c->frecE.p, hinv, c->s_nneigh.p, c->hp, c->counters.p);
+                                                       c->vel4.p, c->frecC.p, c->frecD.p, c->frecE.p, hinv, c->s_nneigh.p, c->hp, c->counters.p,
+                                                       c->s_gsoft.p, c->dvdx.p, c->s_dvdx.p, c->ibin.p, c->ibin_old.p, c->ibin_wake.p, c->s_ibin.p,
+                                                       c->s_ibinold.p, c->s_wake.p);
     c->launches++;
-    ForceArgs a;
     a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.recC = c->frecC.p; a.recD = c->frecD.p; a.recE = c->frecE.p; a.hinv = hinv; a.stype = c->stype.p; a.perm = c->perm.p;
     a.s_fxyzu = c->s_fxyzu.p; a.s_dB = c->s_dB.p; a.s_divvf = c->s_divvf.p; a.s_divBsymm = c->s_divBsymm.p; a.s_done = c->s_nneigh.p;
     a.stage_pos = c->stage_pos.p; a.stage_idx = c->stage_idx.p; a.multitype = c->multitype ? 1 : 0;
     a.scratch_per_warp = c->scratch_per_warp; a.cnt = c->counters.p; a.dscal = c->dscal.p; a.icall = icall;
+    a.gsoft = c->s_gsoft.p; a.dvdx9 = c->s_dvdx.p; a.gacc = c->gacc.p; a.s_poten = c->s_poten.p; a.s_tstop = c->s_tstop.p;
+    a.s_ibinold = c->s_ibinold.p; a.s_ibin = c->s_ibin.p; a.s_wake = c->s_wake.p; a.s_ibinnew = c->s_ibinnew.p;
+    a.nbinmax = c->nbinmax; a.ibinnow_m1 = c->ibinnow - 1; a.istepfrac = c->istepfrac;
     cudaEventRecord(c->ev[10], c->stream);
-    if (p.kernel == 0) { if (p.periodic) dispatch_force<0, true>(c, a, grid); else dispatch_force<0, false>(c, a, grid); }
-    else { if (p.periodic) dispatch_force<1, true>(c, a, grid); else dispatch_force<1, false>(c, a, grid); }
+    dispatch_force(c, a, grid);
     cudaEventRecord(c->ev[11], c->stream);
     k_scatter_force<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->s_fxyzu.p, c->s_dB.p, c->s_divvf.p, c->s_divBsymm.p, c->fxyzu.p,
-                                                          c->dBevol.p, c->divcurlv.p, c->divBsymm.p, c->hp.nvu, p.mhd);
+                                                          c->dBevol.p, c->divcurlv.p, c->divBsymm.p, c->hp.nvu, p.mhd, p.gravity, p.dust, p.ind_timesteps,
+                                                          c->s_poten.p, c->poten.p, c->s_tstop.p, c->tstop.p, c->s_ibinnew.p, c->ibin.p, c->s_wake.p,
+                                                          c->ibin_wake.p);
     c->launches++;
     unsigned long long hc[16]; double hd[4];
     CUDA_TRY(c, cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
@@ -411,6 +580,12 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     memset(&sc, 0, sizeof sc);
     sc.dtcourant = hd[0]; sc.dtforce = hd[1]; sc.dtmini = hd[2]; sc.dtmaxi = hd[3];
     sc.npairs_force = (int64_t)hc[CNT_NPAIRS];
-    if (out) { sphgpu_scalars o = c->last_dens; o.dtcourant = sc.dtcourant; o.dtforce = sc.dtforce; o.dtmini = sc.dtmini; o.dtmaxi = sc.dtmaxi; o.npairs_force = sc.npairs_force; *out = o; }
+    sc.nbinmaxnew = p.ind_timesteps ? (hc[CNT_NCHECKBIN] ? (int64_t)hc[CNT_NBINMAX] : (int64_t)c->nbinmax) : 0;   // force.F90:856-861
+    if (out) {
+        sphgpu_scalars o = c->last_dens;
+        o.dtcourant = sc.dtcourant; o.dtforce = sc.dtforce; o.dtmini = sc.dtmini; o.dtmaxi = sc.dtmaxi; o.npairs_force = sc.npairs_force;
+        o.nbinmaxnew = sc.nbinmaxnew; o.npairs_gravity = c->npairs_gravity; o.nm2l = c->nm2l;
+        *out = o;
+    }
     return SPHGPU_OK;
 }

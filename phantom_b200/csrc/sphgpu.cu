@@ -54,6 +54,8 @@ static int ensure_all(sphgpu_ctx *c, int64_t n)
     TRY(ensure_zero(c, c->eos_vars, 7 * n)); TRY(ensure_zero(c, c->divcurlv, n)); TRY(ensure_zero(c, c->divcurlB, 4 * n));
     TRY(ensure_zero(c, c->alphaind, 3 * n)); TRY(ensure_zero(c, c->gradh, (size_t)ng * n)); TRY(ensure_zero(c, c->dvdx, 9 * n));
     TRY(ensure_zero(c, c->poten, n)); TRY(ensure_zero(c, c->divBsymm, n)); TRY(ensure_zero(c, c->iphase, n));
+    TRY(ensure_zero(c, c->ibin, n)); TRY(ensure_zero(c, c->ibin_old, n)); TRY(ensure_zero(c, c->ibin_wake, n));
+    TRY(ensure_zero(c, c->dustfrac, n)); TRY(ensure_zero(c, c->tstop, n));
     TRY(ensure_zero(c, c->counters, CNT_COUNT)); TRY(ensure_zero(c, c->dscal, DS_COUNT));
     return SPHGPU_OK;
 }
@@ -66,7 +68,7 @@ int ensure_all_keep(sphgpu_ctx *c, int64_t n, int64_t keep)
 #define GROW(buf, w) CUDA_TRY(c, (buf).ensure_keep((size_t)(w) * n, (size_t)(w) * keep, st))
     GROW(c->xyzh, 4); GROW(c->vxyzu, nvu); GROW(c->fxyzu, nvu); GROW(c->fext, 3); GROW(c->Bevol, 4); GROW(c->dBevol, 4); GROW(c->eos_vars, 7);
     GROW(c->divcurlv, 1); GROW(c->divcurlB, 4); GROW(c->alphaind, 3); GROW(c->gradh, ng); GROW(c->dvdx, 9); GROW(c->poten, 1); GROW(c->divBsymm, 1);
-    GROW(c->iphase, 1);
+    GROW(c->iphase, 1); GROW(c->ibin, 1); GROW(c->ibin_old, 1); GROW(c->ibin_wake, 1); GROW(c->dustfrac, 1); GROW(c->tstop, 1);
 #undef GROW
     return SPHGPU_OK;
 }
@@ -104,7 +106,7 @@ int sphgpu_create(const sphgpu_params *params, int device, sphgpu_ctx **out)
     cudaGetDeviceProperties(&prop, device);
     c->numSMs = prop.multiProcessorCount;
     cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    for (int k = 0; k < 12; k++) cudaEventCreate(&c->ev[k]);
+    for (int k = 0; k < 16; k++) cudaEventCreate(&c->ev[k]);
     set_params_internal(c, params);
     *out = c;
     return SPHGPU_OK;
@@ -121,11 +123,12 @@ void sphgpu_destroy(sphgpu_ctx *c)
     c->keys.release(); c->keys_alt.release(); c->perm.release(); c->perm_alt.release(); c->pos4.release(); c->vel4.release(); c->acc4.release(); c->bev4.release();
     c->stype.release(); c->hnew.release(); c->frecC.release(); c->frecD.release(); c->frecE.release();
     c->s_gradh.release(); c->s_divv.release(); c->s_dvdx.release(); c->s_alpha3.release(); c->s_divcurlB.release(); c->s_fxyzu.release(); c->s_dB.release();
-    c->s_divvf.release(); c->s_poten.release(); c->s_divBsymm.release(); c->s_nneigh.release();
+    c->s_ibin.release(); c->s_ibinold.release(); c->s_wake.release(); c->s_ibinnew.release(); c->s_gsoft.release(); c->s_tstop.release(); c->s_dustfrac.release(); c->dustfrac.release(); c->tstop.release(); c->gacc.release(); c->s_divvf.release(); c->s_poten.release(); c->s_divBsymm.release(); c->s_nneigh.release();
     c->cpl.release(); c->cellflag.release(); c->cellid_scan.release(); c->cells.release(); c->groups.release(); c->cellkeys.release(); c->nodes.release(); c->nodeflag.release();
     c->halo_sendidx.release(); c->halo_cnt.release(); c->halo_boxes.release(); c->halo_sendbuf.release(); c->halo_recvbuf.release();
     c->cubtemp.release(); c->scratch.release(); c->nodesf.release(); c->stage_pos.release(); c->stage_idx.release(); c->counters.release(); c->dscal.release();
-    for (int k = 0; k < 12; k++) cudaEventDestroy(c->ev[k]);
+    for (int k = 0; k < 16; k++) cudaEventDestroy(c->ev[k]);
+    gravity_release(c); c->h_build.release(); c->h_hist.release(); c->h_its.release();
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -147,8 +150,16 @@ int sphgpu_set_option(sphgpu_ctx *c, const char *name, double value)
     if (!strcmp(name, "max_cell")) { int v = (int)value; c->max_cell = v < 1 ? 1 : (v > 32 ? 32 : v); c->tree_valid = false; return 0; }
     if (!strcmp(name, "max_leaf")) { int v = (int)value; c->max_leaf = v < 1 ? 1 : (v > 32 ? 32 : v); c->tree_valid = false; return 0; }
     if (!strcmp(name, "list_margin")) { c->list_margin = value < 1. ? 1. : value; return 0; }
+    if (!strcmp(name, "grav_p2p_per_particle")) { c->grav_p2p_per_particle = (int)value < 8 ? 8 : (int)value; return 0; }
     if (!strcmp(name, "scratch_per_warp")) { c->scratch_per_warp = (int)value; c->stage_pos.release(); c->stage_idx.release(); return 0; }
     return SPHGPU_ERR_ARG;
+}
+
+int sphgpu_set_timestep_bins(sphgpu_ctx *c, int nbinmax, int ibinnow, int istepfrac)
+{
+    if (!c) return SPHGPU_ERR_ARG;
+    c->nbinmax = nbinmax; c->ibinnow = ibinnow; c->istepfrac = istepfrac;
+    return SPHGPU_OK;
 }
 
 int sphgpu_get_timings(sphgpu_ctx *c, double *ms4)
@@ -158,6 +169,18 @@ int sphgpu_get_timings(sphgpu_ctx *c, double *ms4)
     return SPHGPU_OK;
 }
 int64_t sphgpu_launch_count(sphgpu_ctx *c) { return c ? c->launches : 0; }
+int sphgpu_get_gravity_timings(sphgpu_ctx *c, double *ms2)
+{
+    if (!c || !ms2) return SPHGPU_ERR_ARG;
+    ms2[0] = c->ms_gravity[0]; ms2[1] = c->ms_gravity[1];
+    return SPHGPU_OK;
+}
+int64_t sphgpu_gravity_tree(sphgpu_ctx *c, int64_t maxnodes, double *rec12, int32_t *irec6, int32_t *ids)
+{
+    if (!c) return -1;
+    cudaSetDevice(c->device);
+    return gravity_tree_dump(c, maxnodes, rec12, irec6, ids);
+}
 int sphgpu_get_kernel_timings(sphgpu_ctx *c, double *ms2)
 {
     if (!c || !ms2) return SPHGPU_ERR_ARG;
@@ -189,6 +212,7 @@ int sphgpu_upload(sphgpu_ctx *c, const sphgpu_host_arrays *h, uint64_t mask)
     if (mask & SPHGPU_F_POTEN) TRY(upload_arr(c, c->poten, h->poten, n));
     if (mask & SPHGPU_F_DIVBSYMM) TRY(upload_arr(c, c->divBsymm, h->divBsymm, n));
     if (mask & SPHGPU_F_IPHASE) { TRY(upload_arr(c, c->iphase, h->iphase, n)); if (h->iphase) c->tree_valid = false; }
+    if (mask & SPHGPU_F_IBIN) { TRY(upload_arr(c, c->ibin, h->ibin, n)); TRY(upload_arr(c, c->ibin_old, h->ibin_old, n)); TRY(upload_arr(c, c->ibin_wake, h->ibin_wake, n)); }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return SPHGPU_OK;
 }
@@ -214,6 +238,9 @@ int sphgpu_download(sphgpu_ctx *c, sphgpu_host_arrays *h, uint64_t mask)
     if (mask & SPHGPU_F_POTEN) TRY(download_arr(c, c->poten, h->poten, n));
     if (mask & SPHGPU_F_DIVBSYMM) TRY(download_arr(c, c->divBsymm, h->divBsymm, n));
     if (mask & SPHGPU_F_IPHASE) TRY(download_arr(c, c->iphase, h->iphase, n));
+    if (mask & SPHGPU_F_IBIN) { TRY(download_arr(c, c->ibin, h->ibin, n)); TRY(download_arr(c, c->ibin_wake, h->ibin_wake, n)); }
+    if (mask & SPHGPU_F_DUSTFRAC) TRY(download_arr(c, c->dustfrac, h->dustfrac, n));
+    if (mask & SPHGPU_F_TSTOP) TRY(download_arr(c, c->tstop, h->tstop, n));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return SPHGPU_OK;
 }
@@ -346,9 +373,12 @@ int sphgpu_derivs(sphgpu_ctx *c, int icall, sphgpu_host_arrays *h, double dt, sp
     uint64_t in = SPHGPU_F_XYZH | SPHGPU_F_VXYZU | SPHGPU_F_FXYZU | SPHGPU_F_FEXT | SPHGPU_F_ALPHAIND | SPHGPU_F_IPHASE | SPHGPU_F_GRADH | SPHGPU_F_DIVCURLV |
                   SPHGPU_F_DVDX | SPHGPU_F_EOSVARS;
     if (c->hp.p.mhd) in |= SPHGPU_F_BEVOL | SPHGPU_F_DIVCURLB;
+    if (c->hp.p.ind_timesteps) in |= SPHGPU_F_IBIN;
     TRY(sphgpu_upload(c, h, in));
     TRY(sphgpu_derivs_resident(c, icall, dt, out));
     uint64_t outm = SPHGPU_F_XYZH | SPHGPU_F_FXYZU | SPHGPU_F_GRADH | SPHGPU_F_DIVCURLV | SPHGPU_F_DVDX | SPHGPU_F_ALPHAIND | SPHGPU_F_EOSVARS;
+    if (c->hp.p.ind_timesteps) outm |= SPHGPU_F_IBIN;
+    if (c->hp.p.dust) outm |= SPHGPU_F_DUSTFRAC | SPHGPU_F_TSTOP;
     if (c->hp.p.mhd) outm |= SPHGPU_F_DBEVOL | SPHGPU_F_DIVCURLB | SPHGPU_F_DIVBSYMM;
     if (c->hp.p.gravity) outm |= SPHGPU_F_POTEN;
     return sphgpu_download(c, h, outm);

@@ -274,6 +274,14 @@ __global__ void k_groups(int M, int gmax, const Cell *__restrict__ cells, const 
     groups[slotg] = g;
 }
 
+// gravity: the reference's node hmax starts from the h the tree was built with (kdtree.F90:654-666)
+__global__ void k_hbuild(int64_t n, const double *__restrict__ xyzh, double *__restrict__ h_build, int *__restrict__ h_its)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    h_build[i] = xyzh[4 * i + 3]; h_its[i] = 0;
+}
+
 __global__ void k_cell_hmax(int64_t ncells, Cell *__restrict__ cells, const double4 *__restrict__ pos4)
 {
     int64_t cidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -388,6 +396,11 @@ int tree_build(sphgpu_ctx *c)
         LAUNCH(c, k_refit, nblk(M, 128), 128, (int)M, c->cells.p, c->nodes.p, c->nodesf.p, c->nodeflag.p);
     }
     TRY(build_groups(c));
+    if (p.gravity) {
+        CUDA_TRY(c, c->h_build.ensure(n)); CUDA_TRY(c, c->h_its.ensure(n)); CUDA_TRY(c, c->h_hist.ensure((size_t)SPHGPU_HHIST * n));
+        LAUNCH(c, k_hbuild, nblk(n, 256), 256, n, c->xyzh.p, c->h_build.p, c->h_its.p);
+    }
+    c->grav_tree_valid = false;
     CUDA_TRY(c, cudaGetLastError());
     c->tree_valid = true;
     return SPHGPU_OK;

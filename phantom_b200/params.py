@@ -32,7 +32,8 @@ class SphParams(C.Structure):
         ("psidecayfac", C.c_double), ("overcleanfac", C.c_double),
         ("tree_accuracy", C.c_double),
         ("grainsize", C.c_double), ("graindens", C.c_double), ("K_code", C.c_double),
-        ("reserved_d", C.c_double * 8),
+        ("seff", C.c_double),
+        ("reserved_d", C.c_double * 7),
     ]
 
     @property
@@ -56,7 +57,7 @@ class SphScalars(C.Structure):
         ("maxtrial", C.c_int64), ("maxactual", C.c_int64), ("nrhocalc", C.c_int64), ("nactualtot", C.c_int64),
         ("np", C.c_int64), ("ncalls_neigh", C.c_int64),
         ("npairs_density", C.c_int64), ("npairs_force", C.c_int64), ("nbinmaxnew", C.c_int64),
-        ("reserved", C.c_int64 * 3),
+        ("npairs_gravity", C.c_int64), ("nm2l", C.c_int64), ("reserved", C.c_int64 * 1),
     ]
 
 
