@@ -107,7 +107,7 @@ struct sphgpu_ctx {
     int max_cell = 32;       // target group: <= 32 particles (one lane per target)
     int max_leaf = 8;        // tree leaf (source granularity of the walk)
     double list_margin = 1.02;
-    int scratch_per_warp = 8192;
+    int scratch_per_warp = 4096;    // capacity (cells) of a warp's cell list
     // ---- canonical (original particle order) device arrays = device mirror of part.F90 ----
     int64_t npart = 0;
     DevBuf<double> xyzh, vxyzu, fxyzu, fext, Bevol, dBevol, eos_vars, Bxyz;
@@ -125,6 +125,9 @@ struct sphgpu_ctx {
     DevBuf<int8_t> stype;                   // iphase (sorted)
     DevBuf<double> hnew;                    // density output h (sorted)
     DevBuf<double4> frecC, frecD, frecE;    // force j-side records (sorted)
+    DevBuf<double4> drec;                   // packed records of the single-type fast density path (4 x 32 B per particle)
+    DevBuf<double4> frec;                   // packed records of the all-gas fast path (5 x 32 B per particle)
+    bool force_general = false;             // option: route everything through the general force kernel (A/B testing)
     DevBuf<float> s_gradh, s_divv, s_dvdx, s_alpha3, s_divcurlB;   // sorted density outputs
     DevBuf<double4> s_fxyzu, s_dB;          // sorted force outputs
     DevBuf<float> s_divvf, s_poten, s_divBsymm;
@@ -140,8 +143,7 @@ struct sphgpu_ctx {
     DevBuf<TreeNode> nodes;
     DevBuf<TreeNodeF> nodesf;
     bool multitype = false;                 // any particle that is not plain gas (boundary, dust, ...)
-    DevBuf<float4> stage_pos;               // per-warp staged candidates
-    DevBuf<int> stage_idx;
+    DevBuf<int> stage_idx;                  // per-warp cell lists of the pair kernels (candidates themselves are staged in shared memory)
     DevBuf<int> nodeflag;
     DevBuf<char> cubtemp;
     DevBuf<int> scratch;                    // per-warp candidate lists
@@ -199,6 +201,10 @@ __device__ __forceinline__ void get_partinfo_d(int8_t iphasei, int set_boundarie
         else isactive = false;
     }
 }
+
+// max/min without the NaN canonicalisation of fmax/fmin (3 instructions instead of ~7); operands here are never NaN
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 
 __device__ __forceinline__ double warp_sum(double v)
 {

@@ -18,13 +18,15 @@
 #include "walk.cuh"
 #include "sphkern.cuh"
 #include <float.h>
+#include <string.h>
 
 namespace {
 
 struct DensArgs {
     const TreeNodeF *nodes; const Cell *cells; int ncells; const Cell *groups; int ngroups;
     const double4 *pos4, *vel4, *acc4, *bev4; const int8_t *stype; const int *perm;
-    float4 *stage_pos; int *stage_idx; int multitype; double hmax_global;
+    const double4 *drec;     // fast path: 4 x 32 B per particle {x,y,z,h} {v,u} {f+fext} {B/rho,psi}
+    int *stage_idx; int multitype; int max_leaf; double hmax_global;
     double *hnew; float *s_gradh, *s_divv, *s_dvdx, *s_alpha3, *s_divcurlB; int *s_nneigh; double *s_dustfrac;
     double *h_hist; int *h_its; int64_t npart;     // GRAV: per-particle h after every iteration, for the node-hmax replay of gravity.cu
     int scratch_per_warp; unsigned long long *cnt; double *dscal;
@@ -40,7 +42,7 @@ enum { B_DIVB = 0, B_DBXDX, B_DBXDY, B_DBXDZ, B_DBYDX, B_DBYDY, B_DBYDZ, B_DBZDX
 __global__ void k_gather_dens(int64_t nlive, const int *__restrict__ perm, const double *__restrict__ vxyzu, const double *__restrict__ fxyzu,
                               const double *__restrict__ fext, const double *__restrict__ Bevol, int nvu, int mhd, const double4 *__restrict__ pos4,
                               double4 *__restrict__ vel4, double4 *__restrict__ acc4, double4 *__restrict__ bev4, double *__restrict__ hnew,
-                              int *__restrict__ s_nneigh)
+                              int *__restrict__ s_nneigh, double4 *__restrict__ drec)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nlive) return;
@@ -51,6 +53,11 @@ __global__ void k_gather_dens(int64_t nlive, const int *__restrict__ perm, const
     if (mhd) bev4[s] = reinterpret_cast<const double4 *>(Bevol)[i];
     hnew[s] = pos4[s].w;
     s_nneigh[s] = -1;
+    if (drec) {
+        double4 *r = drec + (mhd ? 4 : 3) * (size_t)s;
+        r[0] = pos4[s]; r[1] = vel4[s]; r[2] = acc4[s];
+        if (mhd) r[3] = bev4[s];
+    }
 }
 
 __global__ void k_scatter_dens(int64_t nlive, const int *__restrict__ perm, const int *__restrict__ s_nneigh, const double *__restrict__ hnew,
@@ -144,6 +151,64 @@ __device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[10], int 
     if (dp.p.dust) v[S_RHODUST] += (isn && !same_type && gasi && itypej == IDUST) ? wabi : 0.;
 }
 
+
+// fast path (every particle has the same type and mass, no dust): same sums as dens_pair, but the exact membership test is a
+// real branch, the neighbour comes as one packed record, and the minimum-image wrap is skipped for interior target groups
+template <int K, bool PERIODIC, bool MHD, bool GRAV>
+__device__ __forceinline__ void dens_pair_fast(double (&v)[29], double (&w)[10], int &nneighi, int j, int s, double xi, double yi, double zi, double hi,
+                                               double hi1, double hi21, const double4 &vi, const double4 &ai, const double4 &bi, const double4 *__restrict__ drec,
+                                               double pmass0, double hfact, bool use_da, bool interior, double Lx, double Ly, double Lz)
+{
+    typedef SphKern<K> KF;
+    const double4 *rj = drec + (MHD ? 4 : 3) * (size_t)j;
+    const double4 pj = rj[0];
+    const double4 vj = rj[1];
+    double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
+    if (PERIODIC && !interior) {                                              // dens.F90:666-670
+        if (fabs(dx) > 0.5 * Lx) dx = dx - copysign(Lx, dx);
+        if (fabs(dy) > 0.5 * Ly) dy = dy - copysign(Ly, dy);
+        if (fabs(dz) > 0.5 * Lz) dz = dz - copysign(Lz, dz);
+    }
+    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    const double q2i = __dmul_rn(r2, hi21);                                   // dens.F90:675
+    const bool isn = (q2i < KF::radkern2) && (j != s);                        // :679, :650 (exact membership) -> 0/1 weight on m_j
+    const double pmass = isn ? pmass0 : 0.;
+    const double r2s = isn ? r2 : 1.0;
+    const double rinv = (r2s > 0.) ? rsqrt(r2s) : 0.;
+    const double qi = (r2s * rinv) * hi1;
+    double wabi, grkerni;
+    KF::get_kernel(isn ? q2i : 1.0, qi, wabi, grkerni);
+    nneighi += isn ? 1 : 0;
+    v[S_RHO] += wabi * pmass;
+    v[S_GRADH] += (-qi * grkerni - 3. * wabi) * pmass;
+    if (GRAV) v[S_GRADSOFT] += KF::dphidh(isn ? q2i : 1.0, qi) * pmass;
+    const double g = (rinv - DBL_EPSILON * rinv * rinv) * grkerni * pmass;     // rij1 = 1/(rij + epsilon) (dens.F90:746), times grkern m_j
+    const double runix = dx * g, runiy = dy * g, runiz = dz * g;
+    const double dvx = vi.x - vj.x, dvy = vi.y - vj.y, dvz = vi.z - vj.z;
+    v[S_DIVV] += dvx * runix + dvy * runiy + dvz * runiz;
+    v[S_DVXDX] += dvx * runix; v[S_DVXDY] += dvx * runiy; v[S_DVXDZ] += dvx * runiz;
+    v[S_DVYDX] += dvy * runix; v[S_DVYDY] += dvy * runiy; v[S_DVYDZ] += dvy * runiz;
+    v[S_DVZDX] += dvz * runix; v[S_DVZDY] += dvz * runiy; v[S_DVZDZ] += dvz * runiz;
+    if (use_da) {
+        const double4 aj = rj[2];
+        const double dax = ai.x - aj.x, day = ai.y - aj.y, daz = ai.z - aj.z;
+        v[S_DAXDX] += dax * runix; v[S_DAXDY] += dax * runiy; v[S_DAXDZ] += dax * runiz;
+        v[S_DAYDX] += day * runix; v[S_DAYDY] += day * runiy; v[S_DAYDZ] += day * runiz;
+        v[S_DAZDX] += daz * runix; v[S_DAZDY] += daz * runiy; v[S_DAZDZ] += daz * runiz;
+    }
+    v[S_RXX] -= dx * runix; v[S_RXY] -= dx * runiy; v[S_RXZ] -= dx * runiz;
+    v[S_RYY] -= dy * runiy; v[S_RYZ] -= dy * runiz; v[S_RZZ] -= dz * runiz;
+    if (MHD) {
+        const double rhoi = rhoh_d(hi, pmass, hfact), rhoj = rhoh_d(pj.w, pmass, hfact);
+        const double4 bj = rj[3];
+        const double dBx = bi.x * rhoi - bj.x * rhoj, dBy = bi.y * rhoi - bj.y * rhoj, dBz = bi.z * rhoi - bj.z * rhoj;
+        w[B_DIVB] += dBx * runix + dBy * runiy + dBz * runiz;
+        w[B_DBXDX] += dBx * runix; w[B_DBXDY] += dBx * runiy; w[B_DBXDZ] += dBx * runiz;
+        w[B_DBYDX] += dBy * runix; w[B_DBYDY] += dBy * runiy; w[B_DBYDZ] += dBy * runiz;
+        w[B_DBZDX] += dBz * runix; w[B_DBZDY] += dBz * runiy; w[B_DBZDZ] += dBz * runiz;
+    }
+}
+
 __device__ __forceinline__ void exactlinear_d(double &gx, double &gy, double &gz, double dAx, double dAy, double dAz, const double *rm, double ddenom)
 {
     gx = (dAx * rm[0] + dAy * rm[1] + dAz * rm[2]) * ddenom;
@@ -151,18 +216,20 @@ __device__ __forceinline__ void exactlinear_d(double &gx, double &gy, double &gz
     gz = (dAx * rm[2] + dAy * rm[4] + dAz * rm[5]) * ddenom;
 }
 
-template <int K, bool PERIODIC, bool MHD, bool GRAV>
-__global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_constant__ DevParams dp)
+template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST>
+__global__ void __launch_bounds__(128, 3) k_density(const DensArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
     __shared__ WarpShared wsh[4];
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     WarpShared &ws = wsh[wib];
     const int gwarp = blockIdx.x * 4 + wib;
-    Staged st;
-    st.pos = a.stage_pos + (size_t)gwarp * a.scratch_per_warp;
-    st.idx = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;
+    int *clist = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;      // cell list of the current group (the only global scratch)
+    constexpr int DSTRIDE = MHD ? 4 : 3;                                 // double4 per packed record of the fast path
+    const double4 *posrec = FAST ? a.drec : a.pos4;
+    const int pstride = FAST ? DSTRIDE : 1;
     const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
+    const float fLx = (float)Lx, fLy = (float)Ly, fLz = (float)Lz;
     const double radkern = KF::radkern;
     const double halfLmin = 0.5 * fmin(Lx, fmin(Ly, Lz));
     const bool use_da = dp.nalpha > 1;
@@ -198,17 +265,24 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
         bool conv = !act;                                            // inactive / boundary lanes take no part (dens.F90:1329)
         bool failed = false;
         double v[29], w[10];
-        int nneighi = 0, its_lane = 0;
+        int nneighi = 0, its_lane = 0, nlist_last = 0;
 
         double hmax_list = cell.hmax * a.margin;
         double rcut_list = radkern * hmax_list;
+        bool interior = false;   // no candidate of this group lies across the periodic boundary: the minimum-image branch can be skipped
         // the FP32 filter works on nearest images relative to the cell centre: only valid while the search sphere of every
         // target stays inside half a box length; otherwise every candidate goes to the exact test
         bool wide = PERIODIC && (halfext + rcut_list >= 0.999 * halfLmin);
-        bool ok = warp_walk_stage<false, PERIODIC>(a.nodes, a.cells, a.ncells, a.pos4, tlo, thi, __double2float_ru(rcut_list), (float)radkern, cx, cy, cz,
-                                                   Lx, Ly, Lz, ws, st, a.scratch_per_warp);
+        float reach = 0.f;
+        int ncl = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut_list), (float)radkern, fLx, fLy, fLz, ws, clist,
+                                             a.scratch_per_warp, reach);
         st_nwalk += (lane == 0);
-        if (!ok) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+        if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+        if (FAST && PERIODIC) {
+            const double rr = rcut_list * 1.0001;
+            interior = cell.lo[0] - rr > dp.p.xmin && cell.hi[0] + rr < dp.p.xmax && cell.lo[1] - rr > dp.p.ymin && cell.hi[1] + rr < dp.p.ymax &&
+                       cell.lo[2] - rr > dp.p.zmin && cell.hi[2] + rr < dp.p.zmax;
+        }
 
         for (int its = 1;; its++) {                                  // local_its (dens.F90:338-373): the cell iterates until every particle converged
             // compute_hmax / redo_neighbours (dens.F90:1275-1289, :343-347)
@@ -217,13 +291,18 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
                 hmax_list = hneed * a.margin * 1.01;
                 rcut_list = radkern * hmax_list;
                 wide = PERIODIC && (halfext + rcut_list >= 0.999 * halfLmin);
-                ok = warp_walk_stage<false, PERIODIC>(a.nodes, a.cells, a.ncells, a.pos4, tlo, thi, __double2float_ru(rcut_list), (float)radkern, cx, cy, cz,
-                                                      Lx, Ly, Lz, ws, st, a.scratch_per_warp);
+                ncl = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut_list), (float)radkern, fLx, fLy, fLz, ws, clist,
+                                                 a.scratch_per_warp, reach);
                 st_nwalk += (lane == 0);
-                if (!ok) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); failed = true; }
+                if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); failed = true; }
+                if (FAST && PERIODIC) {
+                    const double rr = rcut_list * 1.0001;
+                    interior = cell.lo[0] - rr > dp.p.xmin && cell.hi[0] + rr < dp.p.xmax && cell.lo[1] - rr > dp.p.ymin && cell.hi[1] + rr < dp.p.ymax &&
+                               cell.lo[2] - rr > dp.p.zmin && cell.hi[2] + rr < dp.p.zmax;
+                }
             }
             if (__any_sync(FULLMASK, failed)) break;
-            const float slack = prefilter_slack(st.maxrel);
+            const float slack = prefilter_slack((float)halfext * 1.0001f + reach);
             float lim = 0.f;                                         // converged / inactive targets get an empty mask
             if (!conv) lim = wide ? 3.0e38f : prefilter_limit(__double2float_ru(radkern * h), slack);
             ws.tgt[lane] = make_float4(xif, yif, zif, lim);
@@ -237,23 +316,40 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
                 its_lane = its;
             }
             const double hi1 = 1. / h, hi21 = hi1 * hi1;
-            const int nlist = st.n;
-            for (int base = 0; base < nlist; base += MAXCHUNK * 32) {
-                const int nchunk = min(MAXCHUNK, (nlist - base + 31) >> 5);
-                build_masks<false>(ws, st, base, nchunk, cell.count, slack);
+            int nlist = 0;
+            for (int cellpos = 0; cellpos < ncl;) {                  // rounds of <= ROUND candidates staged in shared memory
+                const int nr = stage_round<PERIODIC, false>(ws, clist, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf);
+                nlist += nr;
+                const int nchunk = (nr + 31) >> 5;
+                build_masks<false>(ws, nr, cell.count, slack);
                 int c = -1; unsigned m = 0u;
+                if (FAST) {
+                    const int *idxlist = ws.sidx;
+                    while (true) {      // two neighbours per trip: independent dependency chains, both records in flight
+                        const int slot0 = conv ? -1 : next_hit(ws, lane, nchunk, c, m);
+                        if (slot0 < 0) break;
+                        const int slot1 = next_hit(ws, lane, nchunk, c, m);
+                        const int j0 = idxlist[slot0], j1 = (slot1 >= 0) ? idxlist[slot1] : s;
+                        st_surv += 1 + (slot1 >= 0);
+                        dens_pair_fast<K, PERIODIC, MHD, GRAV>(v, w, nneighi, j0, s, pi.x, pi.y, pi.z, h, hi1, hi21, vi, ai, bi, a.drec, pmassi,
+                                                               dp.p.hfact, use_da, interior, Lx, Ly, Lz);
+                        dens_pair_fast<K, PERIODIC, MHD, GRAV>(v, w, nneighi, j1, s, pi.x, pi.y, pi.z, h, hi1, hi21, vi, ai, bi, a.drec, pmassi,
+                                                               dp.p.hfact, use_da, interior, Lx, Ly, Lz);
+                    }
+                } else
                 while (true) {      // two neighbours per trip: independent dependency chains, loads of both in flight
                     const int slot0 = conv ? -1 : next_hit(ws, lane, nchunk, c, m);
                     const int slot1 = (slot0 < 0) ? -1 : next_hit(ws, lane, nchunk, c, m);
                     if (!__any_sync(FULLMASK, slot0 >= 0)) break;
                     if (slot0 >= 0) {
                         st_surv += 1 + (slot1 >= 0);
-                        dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, slot0, st.idx + base, s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp, use_da, Lx, Ly, Lz);
-                        dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, slot1, st.idx + base, s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp, use_da, Lx, Ly, Lz);
+                        dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, slot0, ws.sidx, s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp, use_da, Lx, Ly, Lz);
+                        dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, slot1, ws.sidx, s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp, use_da, Lx, Ly, Lz);
                     }
                 }
                 __syncwarp();
             }
+            nlist_last = nlist;
             if (!conv) {
                 st_trial += (unsigned long long)nlist;
                 // finish_rhosum + finish_cell (dens.F90:1470-1507, :1401-1462)
@@ -356,7 +452,7 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
             st_rhomax = fmax(st_rhomax, rho);
             st_pairs += (unsigned long long)nneighi * its_lane;
             st_ncalc += its_lane; st_nact += nn; st_np += 1;
-            st_maxact = max(st_maxact, nn); st_maxtrial = max(st_maxtrial, st.n);
+            st_maxact = max(st_maxact, nn); st_maxtrial = max(st_maxtrial, nlist_last);
         }
         __syncwarp();
     }
@@ -379,21 +475,43 @@ __global__ void __launch_bounds__(128) k_density(const DensArgs a, const __grid_
     }
 }
 
-template <int K, bool PERIODIC, bool MHD, bool GRAV>
-void launch_density(sphgpu_ctx *c, const DensArgs &a, int grid)
+// grid < 0: only query the resident CTAs/SM of the instantiation; otherwise launch on `grid` CTAs
+template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST>
+int launch_density(sphgpu_ctx *c, const DensArgs &a, int grid)
 {
-    k_density<K, PERIODIC, MHD, GRAV><<<grid, 128, 0, c->stream>>>(a, c->hp);
+    if (grid < 0) {
+        int bps = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_density<K, PERIODIC, MHD, GRAV, FAST>, 128, 0);
+        return bps < 1 ? 1 : bps;
+    }
+    k_density<K, PERIODIC, MHD, GRAV, FAST><<<grid, 128, 0, c->stream>>>(a, c->hp);
     c->launches++;
+    return 0;
 }
 
-template <int K, bool PERIODIC>
-void dispatch_density2(sphgpu_ctx *c, const DensArgs &a, int grid)
+template <int K, bool PERIODIC, bool FAST>
+int dispatch_density3(sphgpu_ctx *c, const DensArgs &a, int grid)
 {
     const bool mhd = c->hp.p.mhd, grav = c->hp.p.gravity;
-    if (mhd && grav) launch_density<K, PERIODIC, true, true>(c, a, grid);
-    else if (mhd) launch_density<K, PERIODIC, true, false>(c, a, grid);
-    else if (grav) launch_density<K, PERIODIC, false, true>(c, a, grid);
-    else launch_density<K, PERIODIC, false, false>(c, a, grid);
+    if (mhd && grav) return launch_density<K, PERIODIC, true, true, FAST>(c, a, grid);
+    if (mhd) return launch_density<K, PERIODIC, true, false, FAST>(c, a, grid);
+    if (grav) return launch_density<K, PERIODIC, false, true, FAST>(c, a, grid);
+    return launch_density<K, PERIODIC, false, false, FAST>(c, a, grid);
+}
+
+// general path: several particle types (boundary, dust) in the set
+bool density_is_general(const sphgpu_ctx *c) { return c->multitype || c->hp.p.dust || c->force_general; }
+
+int dispatch_density(sphgpu_ctx *c, const DensArgs &a, int grid)
+{
+    const sphgpu_params &p = c->hp.p;
+    const bool fast = !density_is_general(c);
+    if (p.kernel == 0) {
+        if (p.periodic) return fast ? dispatch_density3<0, true, true>(c, a, grid) : dispatch_density3<0, true, false>(c, a, grid);
+        return fast ? dispatch_density3<0, false, true>(c, a, grid) : dispatch_density3<0, false, false>(c, a, grid);
+    }
+    if (p.periodic) return fast ? dispatch_density3<1, true, true>(c, a, grid) : dispatch_density3<1, true, false>(c, a, grid);
+    return fast ? dispatch_density3<1, false, true>(c, a, grid) : dispatch_density3<1, false, false>(c, a, grid);
 }
 
 }  // namespace
@@ -409,34 +527,29 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     CUDA_TRY(c, c->hnew.ensure(n)); CUDA_TRY(c, c->s_gradh.ensure(n * c->hp.ngradh)); CUDA_TRY(c, c->s_divv.ensure(n));
     CUDA_TRY(c, c->s_dvdx.ensure(9 * n)); CUDA_TRY(c, c->s_alpha3.ensure(n)); CUDA_TRY(c, c->s_divcurlB.ensure(4 * n)); CUDA_TRY(c, c->s_nneigh.ensure(n));
     if (p.dust) CUDA_TRY(c, c->s_dustfrac.ensure(n));
-    int bps = 3;     // persistent grid = resident CTAs/SM x SMs (register/smem limited; queried per instantiation below)
-    {
-        const bool mhd = p.mhd, grav = p.gravity;
-        if (p.kernel == 0 && p.periodic && !mhd && !grav) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_density<0, true, false, false>, 128, 0);
-        else if (p.kernel == 1 && p.periodic && !mhd && !grav) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_density<1, true, false, false>, 128, 0);
-        else if (p.kernel == 0 && p.periodic && mhd && !grav) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_density<0, true, true, false>, 128, 0);
-        if (bps < 1) bps = 1;
-    }
-    const int grid = c->numSMs * bps;
-    CUDA_TRY(c, c->stage_pos.ensure((size_t)grid * 4 * c->scratch_per_warp)); CUDA_TRY(c, c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp));
+    DensArgs a;
+    memset(&a, 0, sizeof a);
+    const int grid = c->numSMs * dispatch_density(c, a, -1);     // persistent grid = resident CTAs/SM x SMs
+    const bool fast = !density_is_general(c);
+    if (fast) CUDA_TRY(c, c->drec.ensure(4 * (size_t)n));
+    CUDA_TRY(c, c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp));
     k_gather_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->vxyzu.p, c->fxyzu.p, c->fext.p, c->Bevol.p, c->hp.nvu, p.mhd, c->pos4.p, c->vel4.p,
-                                                        c->acc4.p, c->bev4.p, c->hnew.p, c->s_nneigh.p);
+                                                        c->acc4.p, c->bev4.p, c->hnew.p, c->s_nneigh.p, fast ? c->drec.p : nullptr);
     c->launches++;
     CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->dscal.p + DS_RHOMAX, 0, sizeof(double), c->stream));
-    DensArgs a;
+    a.drec = c->drec.p;
     a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.acc4 = c->acc4.p; a.bev4 = c->bev4.p; a.stype = c->stype.p; a.perm = c->perm.p;
     a.hnew = c->hnew.p; a.s_gradh = c->s_gradh.p; a.s_divv = c->s_divv.p; a.s_dvdx = c->s_dvdx.p; a.s_alpha3 = c->s_alpha3.p;
     a.s_divcurlB = c->s_divcurlB.p; a.s_nneigh = c->s_nneigh.p; a.s_dustfrac = c->s_dustfrac.p;
-    a.stage_pos = c->stage_pos.p; a.stage_idx = c->stage_idx.p; a.multitype = c->multitype ? 1 : 0; a.hmax_global = 0.;
+    a.stage_idx = c->stage_idx.p; a.multitype = c->multitype ? 1 : 0; a.max_leaf = c->max_leaf; a.hmax_global = 0.;
     a.scratch_per_warp = c->scratch_per_warp; a.cnt = c->counters.p; a.dscal = c->dscal.p;
     a.margin = c->list_margin; a.icall = icall;
     a.h_hist = c->h_hist.p; a.h_its = c->h_its.p; a.npart = n;
     c->grav_tree_valid = false;            // h changes below: the gravity tree caches h
     cudaEventRecord(c->ev[8], c->stream);
-    if (p.kernel == 0) { if (p.periodic) dispatch_density2<0, true>(c, a, grid); else dispatch_density2<0, false>(c, a, grid); }
-    else { if (p.periodic) dispatch_density2<1, true>(c, a, grid); else dispatch_density2<1, false>(c, a, grid); }
+    dispatch_density(c, a, grid);
     cudaEventRecord(c->ev[9], c->stream);
     k_scatter_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->hnew.p, c->pos4.p, c->xyzh.p, c->s_gradh.p, c->s_divv.p, c->s_dvdx.p,
                                                          c->s_alpha3.p, c->s_divcurlB.p, c->gradh.p, c->divcurlv.p, c->dvdx.p, c->alphaind.p, c->divcurlB.p,

@@ -18,12 +18,13 @@ namespace {
 
 struct ForceArgs {
     const TreeNodeF *nodes; const Cell *cells; int ncells; const Cell *groups; int ngroups;
-    float4 *stage_pos; int *stage_idx; int multitype;
+    int *stage_idx; int multitype; int max_leaf;
     const double4 *pos4, *vel4, *recC, *recD, *recE; const double2 *hinv; const int8_t *stype; const int *perm;
     double4 *s_fxyzu, *s_dB; float *s_divvf, *s_divBsymm; int *s_done;
     int scratch_per_warp; unsigned long long *cnt; double *dscal;
     int icall;
     // XTRA (gravity / dust / individual timesteps) only
+    const double4 *frec;     // fast path: 5 x 32 B per particle {x,y,z,1/h} {v,gradW factor} {P/rho^2.., v_wave, alpha v_wave, 1/rho} {P,u,cs,alpha} {B,psi}
     const double *gsoft; const float *dvdx9; const double4 *gacc; float *s_poten; double *s_tstop;
     const int8_t *s_ibinold, *s_ibin; int *s_wake; int8_t *s_ibinnew;
     int nbinmax, ibinnow_m1, istepfrac;
@@ -40,7 +41,8 @@ __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const 
                              double4 *__restrict__ recD, double4 *__restrict__ recE, double2 *__restrict__ hinv, int *__restrict__ s_done,
                              const __grid_constant__ DevParams dp, unsigned long long *cnt, double *__restrict__ gsoft, const float *__restrict__ dvdx,
                              float *__restrict__ dvdx9, const int8_t *__restrict__ ibin, const int8_t *__restrict__ ibin_old,
-                             const int8_t *__restrict__ ibin_wake, int8_t *__restrict__ s_ibin, int8_t *__restrict__ s_ibinold, int *__restrict__ s_wake)
+                             const int8_t *__restrict__ ibin_wake, int8_t *__restrict__ s_ibin, int8_t *__restrict__ s_ibinold, int *__restrict__ s_wake,
+                             double4 *__restrict__ frec)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nlive) return;
@@ -80,6 +82,16 @@ __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const 
     recD[s] = make_double4(rho1, gradhfac, pmass, cs);
     if (p.mhd) recE[s] = E;
     s_done[s] = 0;
+    if (frec) {                                                  // packed j-records of the all-gas fast path
+        const double4 x = pos4[s];
+        const int fstride = p.mhd ? 5 : (dp.nvu >= 4 ? 4 : 3);
+        double4 *r = frec + fstride * (size_t)s;
+        r[0] = make_double4(x.x, x.y, x.z, h1);
+        r[1] = make_double4(v[0], v[1], v[2], gradhfac);
+        r[2] = make_double4(pro2, vwave, alpha * vwave, rho1);
+        if (fstride >= 4) r[3] = make_double4(pr, dp.nvu >= 4 ? v[3] : 0., cs, alpha);
+        if (fstride >= 5) r[4] = E;
+    }
     if (p.gravity) gsoft[s] = (double)gradh[(size_t)dp.ngradh * i + 1];
     if (p.dust) {
 #pragma unroll
@@ -280,6 +292,234 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
     if (dp.nvu >= 4) f[A_DUDTDISS] += dudtdissi + dudtresist;
 }
 
+
+// ---- fast path: every particle is gas, no gravity / dust / individual timesteps / disc viscosity ---------------------------------
+// Same sums as force_pair above, restructured for instruction count: the exact membership test is a real branch (the FP32 prefilter
+// passes ~1% false candidates, so the warp stays converged), one packed 96/128/160-byte record per neighbour instead of five
+// gathers, the minimum-image wrap is skipped for target groups whose search region lies inside the box, and the j-side terms that
+// vanish with grad W_j (q2j >= R^2) are not masked separately.
+template <int K, bool PERIODIC, bool MHD, bool ADIA>
+__global__ void __launch_bounds__(128, MHD ? 3 : 4) k_force_fast(const ForceArgs a, const __grid_constant__ DevParams dp)
+{
+    typedef SphKern<K> KF;
+    __shared__ WarpShared wsh[4];
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    WarpShared &ws = wsh[wib];
+    const int gwarp = blockIdx.x * 4 + wib;
+    int *clist = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;      // cell list of the current group (the only global scratch)
+    const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
+    const float fLx = (float)Lx, fLy = (float)Ly, fLz = (float)Lz;
+    const double halfLmin = 0.5 * fmin(Lx, fmin(Ly, Lz));
+    const sphgpu_params &p = dp.p;
+    unsigned long long st_pairs = 0, st_trial = 0;
+    double st_dtc = 1.e29, st_dtf = 1.e29, st_dtmax = 0.;
+    const float hmax_global = (a.ncells > 1) ? fmaxf(a.nodes[0].hmax[0], a.nodes[0].hmax[1]) : 0.f;
+    const double pmass = p.massoftype[IGAS];
+    const double beta = p.beta;
+    constexpr bool USEJ = MHD || ADIA;                               // force.F90:1343-1345 without gravity and dust
+    constexpr int FSTRIDE = MHD ? 5 : (ADIA ? 4 : 3);               // double4 per packed record
+
+    while (true) {
+        int cellid = 0;
+        if (lane == 0) cellid = (int)atomicAdd(&a.cnt[CNT_WORK], 1ull);
+        cellid = __shfl_sync(FULLMASK, cellid, 0);
+        if (cellid >= a.ngroups) break;
+        const Cell cell = a.groups[cellid];
+        if (cell.active == 0) continue;                              // force.F90:509
+        const double cx = 0.5 * (cell.lo[0] + cell.hi[0]), cy = 0.5 * (cell.lo[1] + cell.hi[1]), cz = 0.5 * (cell.lo[2] + cell.hi[2]);
+        const double halfext = 0.5 * fmax(cell.hi[0] - cell.lo[0], fmax(cell.hi[1] - cell.lo[1], cell.hi[2] - cell.lo[2]));
+        float tlo[3], thi[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { tlo[k] = __double2float_rd(cell.lo[k]); thi[k] = __double2float_ru(cell.hi[k]); }
+        const double rreach = KF::radkern * fmax(cell.hmax, (double)hmax_global) * 1.0001;
+        const double rcut = KF::radkern * cell.hmax;
+        const bool wide = PERIODIC && (halfext + rreach >= 0.999 * halfLmin);
+        // no pair of this group can straddle the periodic boundary: |xi - xj| <= L/2 for every candidate that survives the prefilter
+        const bool interior = !PERIODIC || (cell.lo[0] - rreach > p.xmin && cell.hi[0] + rreach < p.xmax && cell.lo[1] - rreach > p.ymin &&
+                                            cell.hi[1] + rreach < p.ymax && cell.lo[2] - rreach > p.zmin && cell.hi[2] + rreach < p.zmax);
+        float reach = 0.f;
+        const int ncl = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut), (float)KF::radkern, fLx, fLy, fLz, ws, clist,
+                                                  a.scratch_per_warp, reach);
+        if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+        int nlist = 0;
+        const float slack = prefilter_slack((float)halfext * 1.0001f + reach);
+        // ---- lane = target (start_cell, force.F90:2172-2514; per-particle part done by k_force_prep)
+        const int s = cell.start + min(lane, cell.count - 1);
+        const bool act = (lane < cell.count) && (a.stype[s] > 0);
+        const double4 *ri = a.frec + FSTRIDE * (size_t)s;
+        const double4 T0 = ri[0], T1 = ri[1], T2 = ri[2];
+        double4 T3 = make_double4(0., 0., 0., 0.), T4 = T3;
+        if (ADIA || MHD) T3 = ri[3];
+        if (MHD) T4 = ri[4];
+        const double xi = T0.x, yi = T0.y, zi = T0.z, hi1 = T0.w, hi21 = hi1 * hi1;
+        const double h = a.pos4[s].w;
+        const double gi = T1.w, pro2i = T2.x, vwavei = T2.y, avwi = T2.z, rho1i = T2.w, pri = T3.x, alphai = T3.w;
+        const double hrho1i = -0.5 * rho1i;
+        float lim = 0.f;
+        if (act) lim = wide ? 3.0e38f : prefilter_limit(__double2float_ru(KF::radkern * h), slack);    // force.F90:2255: inactive targets skipped
+        ws.tgt[lane] = make_float4((float)(xi - cx), (float)(yi - cy), (float)(zi - cz), lim);
+        __syncwarp();
+        double fx = 0., fy = 0., fz = 0., drhodt = 0., dudtdiss = 0., dendtdiss = 0., divBsym = 0., dBx = 0., dBy = 0., dBz = 0., divBdiff = 0.;
+        double vsigmax = 0.;
+        int npair = 0;
+        for (int cellpos = 0; cellpos < ncl;) {                     // rounds of <= ROUND candidates staged in shared memory
+            const int nr = stage_round<PERIODIC, true>(ws, clist, ncl, cellpos, a.frec, FSTRIDE, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf);
+            nlist += nr;
+            const int nchunk = (nr + 31) >> 5;
+            if (wide) build_masks<false>(ws, nr, cell.count, slack);
+            else build_masks<true>(ws, nr, cell.count, slack);
+            const int *idxlist = ws.sidx;
+            int c = -1; unsigned m = 0u;
+            // two neighbours per trip, branch-free (weights through ini/inj): two independent FP64 dependency chains and both
+            // records in flight; a lane that has run out of hits evaluates itself (j == s), which every weight zeroes
+            auto pair = [&](int slot) {
+                const int j = (slot >= 0) ? idxlist[slot] : s;
+                const double4 *rj = a.frec + FSTRIDE * (size_t)j;
+                const double4 R0 = rj[0], R1 = rj[1], R2 = rj[2];
+                double dx = xi - R0.x, dy = yi - R0.y, dz = zi - R0.z;
+                if (PERIODIC && !interior) {                            // force.F90:1266-1270
+                    if (fabs(dx) > 0.5 * Lx) dx = dx - copysign(Lx, dx);
+                    if (fabs(dy) > 0.5 * Ly) dy = dy - copysign(Ly, dy);
+                    if (fabs(dz) > 0.5 * Lz) dz = dz - copysign(Lz, dz);
+                }
+                const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                const double hj1 = R0.w;
+                const double q2i = __dmul_rn(r2, hi21), q2j = __dmul_rn(r2, __dmul_rn(hj1, hj1));         // force.F90:1272, :1285
+                const bool notself = (j != s);
+                const bool ini = (q2i < KF::radkern2) && notself, inj = (q2j < KF::radkern2) && notself;   // :1287, :1230 (exact membership)
+                const bool isn = ini || inj;
+                npair += isn ? 1 : 0;
+                const double r2s = isn ? r2 : 1.0;
+                const double rij1 = (r2s > DBL_MIN) ? rsqrt(r2s) : 0.;  // force.F90:1293-1299
+                const double rij = r2s * rij1;
+                const double grkerni = ini ? KF::grkern(q2i, rij * hi1) * gi : 0.;      // :1301-1302
+                const double grkernj = inj ? KF::grkern(q2j, rij * hj1) * R1.w : 0.;    // :1325-1327
+                const double runix = dx * rij1, runiy = dy * rij1, runiz = dz * rij1;
+                const double dvx = T1.x - R1.x, dvy = T1.y - R1.y, dvz = T1.z - R1.z;
+                const double projv = dvx * runix + dvy * runiy + dvz * runiz;
+                const double bp = beta * projv;
+                const double vwavej = R2.y;
+                // :1423-1426, :1501-1504: vsigmax >= 0 makes the clip at 0 implicit; j-side only when its terms are used (:1343-1345)
+                double vs = vwavei - bp;
+                if (USEJ || inj) vs = dmax(vs, vwavej - bp);
+                vsigmax = dmax(vsigmax, isn ? vs : 0.);
+                const double ap = (projv < 0.) ? projv : 0.;          // force.F90:1581-1592: approaching pairs only
+                const double qrho2i = hrho1i * dmax(avwi - bp, 0.) * ap;
+                const double rho1j = R2.w;
+                const double qrho2j = (-0.5 * rho1j) * dmax(R2.z - bp, 0.) * ap;
+                const double gradp = pmass * ((pro2i + qrho2i) * grkerni + (R2.x + qrho2j) * grkernj);
+                double projsx = 0., projsy = 0., projsz = 0.;
+                if (ADIA) {                                            // artificial conductivity, force.F90:1606-1624
+                    const double4 R3 = rj[3];
+                    const double denij = T3.y - R3.y;
+                    const double vsigu = sqrt(fabs(pri - R3.x) * (2. * rho1i * rho1j / (rho1i + rho1j)));
+                    const double auterm = 0.5 * pmass * rho1i * p.alphau, autermj = 0.5 * pmass * rho1j * p.alphau;
+                    dendtdiss += vsigu * denij * (auterm * grkerni + autermj * grkernj);
+                    dudtdiss += pmass * qrho2i * projv * grkerni;
+                }
+                if (MHD) {                                             // force.F90:1428-1444, :1626-1684, :2132-2150
+                    const double4 E = rj[4];
+                    const double Bxi = T4.x, Byi = T4.y, Bzi = T4.z, psii = T4.w;
+                    const double dBxx = Bxi - E.x, dByy = Byi - E.y, dBzz = Bzi - E.z;
+                    const double projBi = Bxi * runix + Byi * runiy + Bzi * runiz;
+                    const double projBj = E.x * runix + E.y * runiy + E.z * runiz;
+                    const double projdB = dBxx * runix + dByy * runiy + dBzz * runiz;
+                    divBdiff += -pmass * projdB * grkerni;
+                    const double rho21i = rho1i * rho1i, rho21j = rho1j * rho1j;
+                    const double avBterm = 0.5 * pmass * rho1i * p.alphaB * rho1i, avBtermj = 0.5 * pmass * rho1j * p.alphaB * rho1j;
+                    const double tx = dvx - projv * runix, ty = dvy - projv * runiy, tz = dvz - projv * runiz;
+                    const double vsigB = sqrt(tx * tx + ty * ty + tz * tz);
+                    const double dBdissterm = (avBterm * grkerni + avBtermj * grkernj) * vsigB;
+                    if (ADIA && p.iresistive_heating > 0) dudtdiss += -0.5 * (dBxx * dBxx + dByy * dByy + dBzz * dBzz) * dBdissterm;
+                    const double pmjrho21grkerni = pmass * rho21i * grkerni, pmjrho21grkernj = pmass * rho21j * grkernj;
+                    const double termi = pmjrho21grkerni * projBi;
+                    divBsym += termi + pmjrho21grkernj * projBj;
+                    const double dpsiterm = p.overcleanfac * (pmjrho21grkerni * psii * vwavei + pmjrho21grkernj * E.w * vwavej);
+                    dBx += -termi * dvx + dBdissterm * dBxx - dpsiterm * runix;
+                    dBy += -termi * dvy + dBdissterm * dByy - dpsiterm * runiy;
+                    dBz += -termi * dvz + dBdissterm * dBzz - dpsiterm * runiz;
+                    const double si = -pmass * rho21i * projBi * grkerni, sj = -pmass * rho21j * projBj * grkernj;   // Maxwell stress, :1677-1684
+                    projsx = si * Bxi + sj * E.x; projsy = si * Byi + sj * E.y; projsz = si * Bzi + sj * E.z;
+                }
+                fx += -runix * gradp - projsx;
+                fy += -runiy * gradp - projsy;
+                fz += -runiz * gradp - projsz;
+                drhodt += projv * grkerni;
+            };
+            while (true) {
+                const int slot0 = act ? next_hit(ws, lane, nchunk, c, m) : -1;
+                if (slot0 < 0) break;
+                const int slot1 = next_hit(ws, lane, nchunk, c, m);
+                pair(slot0);
+                pair(slot1);
+            }
+            __syncwarp();
+        }
+        // ---- finish_cell_and_store_results (force.F90:2649-3330), lane = target, gas only ----
+        if (act) {
+            st_pairs += npair; st_trial += nlist;
+            double dtc = p.dtmax, dtf = 1.e29, dtclean = 1.e29;
+            double fxyz4 = 0.;
+            double4 dB = make_double4(0., 0., 0., 0.);
+            float divBsymm4 = 0.f;
+            const double rhoi = 1. / rho1i;
+            if (MHD) {                                               // force.F90:2939-2965
+                const double B2i = T4.x * T4.x + T4.y * T4.y + T4.z * T4.z;
+                double frac_divB = 0.;
+                if (B2i > 0.0) {
+                    const double betai = 2.0 * pri / B2i;
+                    if (betai < 2.0) frac_divB = 1.0;
+                    else if (betai < 10.0) frac_divB = (10.0 - betai) * 0.125;
+                }
+                fx -= T4.x * divBsym * frac_divB; fy -= T4.y * divBsym * frac_divB; fz -= T4.z * divBsym * frac_divB;
+                divBsymm4 = (float)(rhoi * divBsym);
+            }
+            const double drhodti = pmass * drhodt;
+            const double divvi = -drhodti * rho1i;
+            if (ADIA) {                                              // force.F90:3024-3095 (ien_type = energy, fac = 1)
+                const double pdv_work = pri * rho1i * rho1i * drhodti;
+                if (p.ipdv_heating > 0) fxyz4 += pdv_work;
+                if (p.ishock_heating > 0) fxyz4 += dudtdiss;
+                fxyz4 += dendtdiss;
+            }
+            if (MHD) {                                               // force.F90:3103-3125
+                dB.x = dBx; dB.y = dBy; dB.z = dBz;
+                if (p.psidecayfac > 0.) {
+                    const double vcleani = p.overcleanfac * vwavei;
+                    const double dtau = p.psidecayfac * vcleani * hi1;
+                    dB.w = -vcleani * divBdiff * rho1i - T4.w * dtau - 0.5 * T4.w * divvi;
+                    dtclean = p.C_cour * h / (vcleani + DBL_MIN);
+                }
+            }
+            const double vsigdtc = fmax(vsigmax, vwavei);
+            if (vsigdtc > DBL_MIN) dtc = p.C_cour * h / (vsigdtc * fmax(p.alpha, 1.0));          // force.F90:3138-3141
+            if (ADIA) {
+                const double eni = T3.y;
+                if (eni + dtc * fxyz4 < DBL_EPSILON && eni > DBL_EPSILON) fxyz4 = fxyz4 / (1. - dtc * fxyz4 / eni);       // :3144-3148
+            }
+            const double f2i = fx * fx + fy * fy + fz * fz;
+            if (fabs(f2i) > DBL_EPSILON) dtf = p.C_force * sqrt(h / sqrt(f2i));                  // force.F90:3217-3219
+            a.s_fxyzu[s] = make_double4(fx, fy, fz, fxyz4);
+            a.s_divvf[s] = (float)divvi;
+            if (MHD) { a.s_dB[s] = dB; a.s_divBsymm[s] = divBsymm4; }
+            a.s_done[s] = 2;
+            st_dtc = fmin(st_dtc, dtc);
+            st_dtf = fmin(st_dtf, fmin(dtf, dtclean));
+            st_dtmax = fmax(st_dtmax, dtc);
+            (void)alphai;
+        }
+        __syncwarp();
+    }
+    st_dtc = warp_min(st_dtc); st_dtf = warp_min(st_dtf); st_dtmax = warp_max(st_dtmax);
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) { st_pairs += __shfl_xor_sync(FULLMASK, st_pairs, sft); st_trial += __shfl_xor_sync(FULLMASK, st_trial, sft); }
+    if (lane == 0) {
+        atomicAdd(&a.cnt[CNT_NPAIRS], st_pairs); atomicAdd(&a.cnt[CNT_NTRIAL], st_trial);
+        atomic_min_pos(&a.dscal[DS_DTCOURANT], st_dtc); atomic_min_pos(&a.dscal[DS_DTFORCE], st_dtf);
+        atomic_min_pos(&a.dscal[DS_DTMINI], st_dtc); atomic_max_pos(&a.dscal[DS_DTMAXI], st_dtmax);
+    }
+}
+
 template <int K, bool PERIODIC, bool MHD, bool XTRA>
 __global__ void __launch_bounds__(128, XTRA ? 2 : 4) k_force(const ForceArgs a, const __grid_constant__ DevParams dp)
 {
@@ -288,10 +528,9 @@ __global__ void __launch_bounds__(128, XTRA ? 2 : 4) k_force(const ForceArgs a, 
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     WarpShared &ws = wsh[wib];
     const int gwarp = blockIdx.x * 4 + wib;
-    Staged st;
-    st.pos = a.stage_pos + (size_t)gwarp * a.scratch_per_warp;
-    st.idx = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;
+    int *clist = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;      // cell list of the current group (the only global scratch)
     const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
+    const float fLx = (float)Lx, fLy = (float)Ly, fLz = (float)Lz;
     const double halfLmin = 0.5 * fmin(Lx, fmin(Ly, Lz));
     const sphgpu_params &p = dp.p;
     unsigned long long st_pairs = 0, st_trial = 0;
@@ -313,11 +552,12 @@ __global__ void __launch_bounds__(128, XTRA ? 2 : 4) k_force(const ForceArgs a, 
         for (int k = 0; k < 3; k++) { tlo[k] = __double2float_rd(cell.lo[k]); thi[k] = __double2float_ru(cell.hi[k]); }
         const double rcut = KF::radkern * cell.hmax;
         const bool wide = PERIODIC && (halfext + KF::radkern * fmax(cell.hmax, (double)hmax_global) >= 0.999 * halfLmin);
-        const bool ok = warp_walk_stage<true, PERIODIC>(a.nodes, a.cells, a.ncells, a.pos4, tlo, thi, __double2float_ru(rcut), (float)KF::radkern, cx, cy, cz,
-                                                        Lx, Ly, Lz, ws, st, a.scratch_per_warp);
-        if (!ok) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
-        const int nlist = st.n;
-        const float slack = prefilter_slack(st.maxrel);
+        float reach = 0.f;
+        const int ncl = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut), (float)KF::radkern, fLx, fLy, fLz, ws, clist,
+                                                  a.scratch_per_warp, reach);
+        if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+        int nlist = 0;
+        const float slack = prefilter_slack((float)halfext * 1.0001f + reach);
         // ---- lane = target: start_cell (force.F90:2172-2514); the per-particle part was done by k_force_prep
         const int s = cell.start + min(lane, cell.count - 1);
         bool act = false, gasi = true, dusti = false; int itypei = IGAS;
@@ -338,18 +578,20 @@ __global__ void __launch_bounds__(128, XTRA ? 2 : 4) k_force(const ForceArgs a, 
         double vsigmax = 0.;
         int npair = 0;
         XtraSums xs; xs.fdx = xs.fdy = xs.fdz = 0.; xs.tsmin = 1.e29; xs.ibin_neigh = 0;
-        for (int base = 0; base < nlist; base += MAXCHUNK * 32) {
-            const int nchunk = min(MAXCHUNK, (nlist - base + 31) >> 5);
-            if (wide) build_masks<false>(ws, st, base, nchunk, cell.count, slack);
-            else build_masks<true>(ws, st, base, nchunk, cell.count, slack);
+        for (int cellpos = 0; cellpos < ncl;) {                     // rounds of <= ROUND candidates staged in shared memory
+            const int nr = stage_round<PERIODIC, false>(ws, clist, ncl, cellpos, a.pos4, 1, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf);
+            nlist += nr;
+            const int nchunk = (nr + 31) >> 5;
+            if (wide) build_masks<false>(ws, nr, cell.count, slack);
+            else build_masks<true>(ws, nr, cell.count, slack);
             int c = -1; unsigned m = 0u;
             while (true) {      // two neighbours per trip
                 const int slot0 = act ? next_hit(ws, lane, nchunk, c, m) : -1;
                 const int slot1 = (slot0 < 0) ? -1 : next_hit(ws, lane, nchunk, c, m);
                 if (!__any_sync(FULLMASK, slot0 >= 0)) break;
                 if (slot0 >= 0) {
-                    force_pair<K, PERIODIC, MHD, XTRA>(f, vsigmax, npair, slot0, st.idx + base, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei);
-                    force_pair<K, PERIODIC, MHD, XTRA>(f, vsigmax, npair, slot1, st.idx + base, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei);
+                    force_pair<K, PERIODIC, MHD, XTRA>(f, vsigmax, npair, slot0, ws.sidx, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei);
+                    force_pair<K, PERIODIC, MHD, XTRA>(f, vsigmax, npair, slot1, ws.sidx, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei);
                 }
             }
             __syncwarp();
@@ -489,26 +731,46 @@ __global__ void k_scatter_force(int64_t nlive, const int *__restrict__ perm, con
 }
 
 // grid < 0: only query the resident CTAs/SM of the instantiation; otherwise launch on `grid` CTAs
-template <int K, bool PERIODIC, bool MHD, bool XTRA>
-int launch_force(sphgpu_ctx *c, const ForceArgs &a, int grid)
+template <int K, bool PERIODIC, bool MHD>
+int launch_force_general(sphgpu_ctx *c, const ForceArgs &a, int grid)
 {
     if (grid < 0) {
         int bps = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force<K, PERIODIC, MHD, XTRA>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force<K, PERIODIC, MHD, true>, 128, 0);
         return bps < 1 ? 1 : bps;
     }
-    k_force<K, PERIODIC, MHD, XTRA><<<grid, 128, 0, c->stream>>>(a, c->hp);
+    k_force<K, PERIODIC, MHD, true><<<grid, 128, 0, c->stream>>>(a, c->hp);
     c->launches++;
     return 0;
+}
+template <int K, bool PERIODIC, bool MHD, bool ADIA>
+int launch_force_fast(sphgpu_ctx *c, const ForceArgs &a, int grid)
+{
+    if (grid < 0) {
+        int bps = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force_fast<K, PERIODIC, MHD, ADIA>, 128, 0);
+        return bps < 1 ? 1 : bps;
+    }
+    k_force_fast<K, PERIODIC, MHD, ADIA><<<grid, 128, 0, c->stream>>>(a, c->hp);
+    c->launches++;
+    return 0;
+}
+
+// general path: anything beyond all-gas hydro / MHD (boundary or dust particles, gravity, individual timesteps, disc viscosity)
+bool force_is_general(const sphgpu_ctx *c)
+{
+    const sphgpu_params &p = c->hp.p;
+    return p.gravity || p.dust || p.ind_timesteps || p.disc_viscosity || c->multitype || c->force_general;
 }
 
 template <int K, bool PERIODIC>
 int dispatch_force2(sphgpu_ctx *c, const ForceArgs &a, int grid)
 {
     const sphgpu_params &p = c->hp.p;
-    const bool xtra = p.gravity || p.dust || p.ind_timesteps;
-    if (p.mhd) return xtra ? launch_force<K, PERIODIC, true, true>(c, a, grid) : launch_force<K, PERIODIC, true, false>(c, a, grid);
-    return xtra ? launch_force<K, PERIODIC, false, true>(c, a, grid) : launch_force<K, PERIODIC, false, false>(c, a, grid);
+    if (force_is_general(c)) return p.mhd ? launch_force_general<K, PERIODIC, true>(c, a, grid) : launch_force_general<K, PERIODIC, false>(c, a, grid);
+    const bool adia = c->hp.nvu >= 4;
+    if (p.mhd) return adia ? launch_force_fast<K, PERIODIC, true, true>(c, a, grid) : launch_force_fast<K, PERIODIC, true, false>(c, a, grid);
+    return adia ? launch_force_fast<K, PERIODIC, false, true>(c, a, grid) : launch_force_fast<K, PERIODIC, false, false>(c, a, grid);
 }
 
 int dispatch_force(sphgpu_ctx *c, const ForceArgs &a, int grid)
@@ -536,10 +798,12 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     if (p.gravity) { CUDA_TRY(c, c->s_gsoft.ensure(n)); CUDA_TRY(c, c->s_poten.ensure(n)); }
     if (p.dust) { CUDA_TRY(c, c->s_dvdx.ensure(9 * n)); CUDA_TRY(c, c->s_tstop.ensure(n)); }
     if (p.ind_timesteps) { CUDA_TRY(c, c->s_ibin.ensure(n)); CUDA_TRY(c, c->s_ibinold.ensure(n)); CUDA_TRY(c, c->s_ibinnew.ensure(n)); CUDA_TRY(c, c->s_wake.ensure(n)); }
+    const bool fast = !force_is_general(c);
+    if (fast) CUDA_TRY(c, c->frec.ensure(5 * (size_t)n));
     ForceArgs a;
     memset(&a, 0, sizeof a);
     const int grid = c->numSMs * dispatch_force(c, a, -1);
-    CUDA_TRY(c, c->stage_pos.ensure((size_t)grid * 4 * c->scratch_per_warp)); CUDA_TRY(c, c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp));
+    CUDA_TRY(c, c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp));
     CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
     const double init[4] = {1.e29, 1.e29, 1.e29, 0.};
     CUDA_TRY(c, cudaMemcpyAsync(c->dscal.p + DS_DTCOURANT, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
@@ -547,13 +811,14 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     k_force_prep<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->pos4.p, c->stype.p, c->vxyzu.p, c->Bevol.p, c->eos_vars.p, c->alphaind.p, c->gradh.p,
                                                        c->vel4.p, c->frecC.p, c->frecD.p, c->frecE.p, hinv, c->s_nneigh.p, c->hp, c->counters.p,
                                                        c->s_gsoft.p, c->dvdx.p, c->s_dvdx.p, c->ibin.p, c->ibin_old.p, c->ibin_wake.p, c->s_ibin.p,
-                                                       c->s_ibinold.p, c->s_wake.p);
+                                                       c->s_ibinold.p, c->s_wake.p, fast ? c->frec.p : nullptr);
     c->launches++;
     a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.recC = c->frecC.p; a.recD = c->frecD.p; a.recE = c->frecE.p; a.hinv = hinv; a.stype = c->stype.p; a.perm = c->perm.p;
     a.s_fxyzu = c->s_fxyzu.p; a.s_dB = c->s_dB.p; a.s_divvf = c->s_divvf.p; a.s_divBsymm = c->s_divBsymm.p; a.s_done = c->s_nneigh.p;
-    a.stage_pos = c->stage_pos.p; a.stage_idx = c->stage_idx.p; a.multitype = c->multitype ? 1 : 0;
+    a.stage_idx = c->stage_idx.p; a.multitype = c->multitype ? 1 : 0; a.max_leaf = c->max_leaf;
     a.scratch_per_warp = c->scratch_per_warp; a.cnt = c->counters.p; a.dscal = c->dscal.p; a.icall = icall;
+    a.frec = c->frec.p;
     a.gsoft = c->s_gsoft.p; a.dvdx9 = c->s_dvdx.p; a.gacc = c->gacc.p; a.s_poten = c->s_poten.p; a.s_tstop = c->s_tstop.p;
     a.s_ibinold = c->s_ibinold.p; a.s_ibin = c->s_ibin.p; a.s_wake = c->s_wake.p; a.s_ibinnew = c->s_ibinnew.p;
     a.nbinmax = c->nbinmax; a.ibinnow_m1 = c->ibinnow - 1; a.istepfrac = c->istepfrac;

@@ -10,15 +10,13 @@ namespace {
 
 template <bool PERIODIC, bool SYM, bool FILL>
 __global__ void __launch_bounds__(128) k_neigh(const TreeNodeF *nodes, const Cell *cells, int ncells, const double4 *pos4, const int *perm, double radkern,
-                                               double Lx, double Ly, double Lz, float4 *stage_pos, int *stage_idx, int scratch_per_warp, unsigned long long *cnt,
+                                               double Lx, double Ly, double Lz, int *stage_idx, int scratch_per_warp, int max_leaf, unsigned long long *cnt,
                                                int *counts, const long long *offsets, int *out)
 {
     __shared__ WarpShared wsh[4];
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     WarpShared &ws = wsh[wib];
-    Staged st;
-    st.pos = stage_pos + (size_t)(blockIdx.x * 4 + wib) * scratch_per_warp;
-    st.idx = stage_idx + (size_t)(blockIdx.x * 4 + wib) * scratch_per_warp;
+    int *clist = stage_idx + (size_t)(blockIdx.x * 4 + wib) * scratch_per_warp;
     const double radkern2 = radkern * radkern;
     const unsigned lt_mask = (1u << lane) - 1;
     while (true) {
@@ -30,17 +28,21 @@ __global__ void __launch_bounds__(128) k_neigh(const TreeNodeF *nodes, const Cel
         float tlo[3], thi[3];
         for (int k = 0; k < 3; k++) { tlo[k] = __double2float_rd(cell.lo[k]); thi[k] = __double2float_ru(cell.hi[k]); }
         const double cx = 0.5 * (cell.lo[0] + cell.hi[0]), cy = 0.5 * (cell.lo[1] + cell.hi[1]), cz = 0.5 * (cell.lo[2] + cell.hi[2]);
-        const bool ok = warp_walk_stage<SYM, PERIODIC>(nodes, cells, ncells, pos4, tlo, thi, __double2float_ru(radkern * cell.hmax), (float)radkern, cx, cy, cz,
-                                                       Lx, Ly, Lz, ws, st, scratch_per_warp);
-        if (!ok) { if (lane == 0) atomicMax(&cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
-        const int nlist = st.n;
-        const int *list = st.idx;
-        for (int t = 0; t < cell.count; t++) {
+        float reach = 0.f;
+        const int ncl = warp_walk<SYM, PERIODIC>(nodes, cells, ncells, tlo, thi, __double2float_ru(radkern * cell.hmax), (float)radkern, (float)Lx, (float)Ly,
+                                                 (float)Lz, ws, clist, scratch_per_warp, reach);
+        if (ncl < 0) { if (lane == 0) atomicMax(&cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+        int nfound[32];                                      // per target of the cell (max_leaf <= 32), kept across rounds
+        for (int t = 0; t < 32; t++) nfound[t] = 0;
+        for (int cellpos = 0; cellpos < ncl;) {
+          const int nlist = stage_round<PERIODIC, false>(ws, clist, ncl, cellpos, pos4, 1, cx, cy, cz, Lx, Ly, Lz, (float)radkern, max_leaf);
+          const int *list = ws.sidx;
+          for (int t = 0; t < cell.count; t++) {
             const int s = cell.start + t;
             const double4 pi = pos4[s];
             const double hi1 = 1. / pi.w, hi21 = hi1 * hi1;
             const int iorig = perm[s];
-            int n = 0;
+            int n = nfound[t];
             for (int c0 = 0; c0 < nlist; c0 += 32) {
                 const int idx = c0 + lane;
                 bool pass = false; int j = 0;
@@ -57,7 +59,10 @@ __global__ void __launch_bounds__(128) k_neigh(const TreeNodeF *nodes, const Cel
                 if (FILL && pass) out[offsets[iorig] + n + __popc(m & lt_mask)] = perm[j] + 1;
                 n += __popc(m);
             }
+            nfound[t] = n;
             if (!FILL && lane == 0) counts[iorig] = n;
+          }
+          __syncwarp();
         }
     }
 }
@@ -69,7 +74,7 @@ int64_t neighbour_sets_run(sphgpu_ctx *c, int symmetric, int64_t *offsets, int32
     if (!c->tree_valid) { c->err = "neighbour_sets: build_tree has not been called"; return -1; }
     const int64_t n = c->npart;
     const int grid = c->numSMs * 4;
-    if (c->stage_pos.ensure((size_t)grid * 4 * c->scratch_per_warp) != cudaSuccess || c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp) != cudaSuccess) return -1;
+    if (c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp) != cudaSuccess) return -1;
     DevBuf<int> counts; DevBuf<long long> offs; DevBuf<int> out; DevBuf<char> tmp;
     if (counts.ensure(n + 1) != cudaSuccess || offs.ensure(n + 1) != cudaSuccess) return -1;
     cudaMemsetAsync(counts.p, 0, sizeof(int) * (n + 1), c->stream);
@@ -78,10 +83,10 @@ int64_t neighbour_sets_run(sphgpu_ctx *c, int symmetric, int64_t *offsets, int32
     const bool per = c->hp.p.periodic;
 #define NEIGH_LAUNCH(FILLV)                                                                                                                       \
     do {                                                                                                                                          \
-        if (per && symmetric) k_neigh<true, true, FILLV><<<grid, 128, 0, c->stream>>>(c->nodesf.p, c->cells.p, (int)c->ncells, c->pos4.p, c->perm.p, R, Lx, Ly, Lz, c->stage_pos.p, c->stage_idx.p, c->scratch_per_warp, c->counters.p, counts.p, offs.p, out.p); \
-        else if (per) k_neigh<true, false, FILLV><<<grid, 128, 0, c->stream>>>(c->nodesf.p, c->cells.p, (int)c->ncells, c->pos4.p, c->perm.p, R, Lx, Ly, Lz, c->stage_pos.p, c->stage_idx.p, c->scratch_per_warp, c->counters.p, counts.p, offs.p, out.p); \
-        else if (symmetric) k_neigh<false, true, FILLV><<<grid, 128, 0, c->stream>>>(c->nodesf.p, c->cells.p, (int)c->ncells, c->pos4.p, c->perm.p, R, Lx, Ly, Lz, c->stage_pos.p, c->stage_idx.p, c->scratch_per_warp, c->counters.p, counts.p, offs.p, out.p); \
-        else k_neigh<false, false, FILLV><<<grid, 128, 0, c->stream>>>(c->nodesf.p, c->cells.p, (int)c->ncells, c->pos4.p, c->perm.p, R, Lx, Ly, Lz, c->stage_pos.p, c->stage_idx.p, c->scratch_per_warp, c->counters.p, counts.p, offs.p, out.p); \
+        if (per && symmetric) k_neigh<true, true, FILLV><<<grid, 128, 0, c->stream>>>(c->nodesf.p, c->cells.p, (int)c->ncells, c->pos4.p, c->perm.p, R, Lx, Ly, Lz, c->stage_idx.p, c->scratch_per_warp, c->max_leaf, c->counters.p, counts.p, offs.p, out.p); \
+        else if (per) k_neigh<true, false, FILLV><<<grid, 128, 0, c->stream>>>(c->nodesf.p, c->cells.p, (int)c->ncells, c->pos4.p, c->perm.p, R, Lx, Ly, Lz, c->stage_idx.p, c->scratch_per_warp, c->max_leaf, c->counters.p, counts.p, offs.p, out.p); \
+        else if (symmetric) k_neigh<false, true, FILLV><<<grid, 128, 0, c->stream>>>(c->nodesf.p, c->cells.p, (int)c->ncells, c->pos4.p, c->perm.p, R, Lx, Ly, Lz, c->stage_idx.p, c->scratch_per_warp, c->max_leaf, c->counters.p, counts.p, offs.p, out.p); \
+        else k_neigh<false, false, FILLV><<<grid, 128, 0, c->stream>>>(c->nodesf.p, c->cells.p, (int)c->ncells, c->pos4.p, c->perm.p, R, Lx, Ly, Lz, c->stage_idx.p, c->scratch_per_warp, c->max_leaf, c->counters.p, counts.p, offs.p, out.p); \
         c->launches++;                                                                                                                            \
     } while (0)
     NEIGH_LAUNCH(false);

@@ -121,12 +121,12 @@ void sphgpu_destroy(sphgpu_ctx *c)
     c->divcurlv.release(); c->divcurlB.release(); c->alphaind.release(); c->gradh.release(); c->dvdx.release(); c->poten.release(); c->divBsymm.release();
     c->iphase.release(); c->ibin.release(); c->ibin_old.release(); c->ibin_wake.release();
     c->keys.release(); c->keys_alt.release(); c->perm.release(); c->perm_alt.release(); c->pos4.release(); c->vel4.release(); c->acc4.release(); c->bev4.release();
-    c->stype.release(); c->hnew.release(); c->frecC.release(); c->frecD.release(); c->frecE.release();
+    c->stype.release(); c->hnew.release(); c->frecC.release(); c->frecD.release(); c->frecE.release(); c->frec.release(); c->drec.release();
     c->s_gradh.release(); c->s_divv.release(); c->s_dvdx.release(); c->s_alpha3.release(); c->s_divcurlB.release(); c->s_fxyzu.release(); c->s_dB.release();
     c->s_ibin.release(); c->s_ibinold.release(); c->s_wake.release(); c->s_ibinnew.release(); c->s_gsoft.release(); c->s_tstop.release(); c->s_dustfrac.release(); c->dustfrac.release(); c->tstop.release(); c->gacc.release(); c->s_divvf.release(); c->s_poten.release(); c->s_divBsymm.release(); c->s_nneigh.release();
     c->cpl.release(); c->cellflag.release(); c->cellid_scan.release(); c->cells.release(); c->groups.release(); c->cellkeys.release(); c->nodes.release(); c->nodeflag.release();
     c->halo_sendidx.release(); c->halo_cnt.release(); c->halo_boxes.release(); c->halo_sendbuf.release(); c->halo_recvbuf.release();
-    c->cubtemp.release(); c->scratch.release(); c->nodesf.release(); c->stage_pos.release(); c->stage_idx.release(); c->counters.release(); c->dscal.release();
+    c->cubtemp.release(); c->scratch.release(); c->nodesf.release(); c->stage_idx.release(); c->counters.release(); c->dscal.release();
     for (int k = 0; k < 16; k++) cudaEventDestroy(c->ev[k]);
     gravity_release(c); c->h_build.release(); c->h_hist.release(); c->h_its.release();
     cudaStreamDestroy(c->stream);
@@ -150,8 +150,9 @@ int sphgpu_set_option(sphgpu_ctx *c, const char *name, double value)
     if (!strcmp(name, "max_cell")) { int v = (int)value; c->max_cell = v < 1 ? 1 : (v > 32 ? 32 : v); c->tree_valid = false; return 0; }
     if (!strcmp(name, "max_leaf")) { int v = (int)value; c->max_leaf = v < 1 ? 1 : (v > 32 ? 32 : v); c->tree_valid = false; return 0; }
     if (!strcmp(name, "list_margin")) { c->list_margin = value < 1. ? 1. : value; return 0; }
+    if (!strcmp(name, "force_general")) { c->force_general = value != 0.; return 0; }
     if (!strcmp(name, "grav_p2p_per_particle")) { c->grav_p2p_per_particle = (int)value < 8 ? 8 : (int)value; return 0; }
-    if (!strcmp(name, "scratch_per_warp")) { c->scratch_per_warp = (int)value; c->stage_pos.release(); c->stage_idx.release(); return 0; }
+    if (!strcmp(name, "scratch_per_warp")) { c->scratch_per_warp = (int)value; c->stage_idx.release(); return 0; }
     return SPHGPU_ERR_ARG;
 }
 

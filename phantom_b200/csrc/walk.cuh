@@ -1,14 +1,15 @@
-// walk.cuh -- warp-cooperative tree walk, candidate staging and prefiltered pair scan shared by the density and
+// walk.cuh -- warp-cooperative tree walk, shared-memory candidate staging and prefiltered pair scan shared by the density and
 // force passes.  Replaces getneigh + cache_neighbours (src/main/kdtree.F90:1221-1347, :1175-1213).
 //
-// One WARP owns one leaf cell:
+// One WARP owns one target group (<= 32 particles, lane = target in the pair loop):
 //   walk   : pops up to 16 tree nodes per step; lane L tests child (L&1) of node (L>>1) with FP32 boxes that were
 //            rounded OUTWARD (conservative), periodic minimum-image gaps; internal hits go to a shared-memory stack,
-//            leaf hits to a small shared-memory cell list.
-//   stage  : the particles of the hit cells are copied ONCE per cell into the warp's scratch slice as
-//            float4 {x,y,z relative to the target-cell centre (nearest periodic image), radkern*h_j} + int index, so the
-//            per-target scan reads contiguous 16-byte records (like the reference's xyzcache, but FP32 and only a filter).
-//   masks  : lane = staged candidate, loop over the cell's <= 32 targets (broadcast from shared memory): a conservative
+//            leaf hits are appended to the group's CELL LIST (one packed int per 8-particle leaf; a few hundred bytes per
+//            group in a per-warp global slice -- the only global scratch the pair kernels touch).
+//   rounds : the candidates are consumed in rounds of <= ROUND particles.  Each round copies the particles of the next
+//            cells ONCE into SHARED memory as float4 {x,y,z relative to the target-group centre (nearest periodic image),
+//            radkern*h_j} + slot index -- the reference's xyzcache (kdtree.F90:1175), but FP32, on chip and only a filter.
+//   masks  : lane = staged candidate, loop over the group's targets (broadcast from shared memory): a conservative
 //            FP32 distance test (error bound derived from the staged extent) + one ballot per target gives, per chunk of
 //            32 candidates, a 32-bit hit mask per target; ~10 instructions per (chunk, target), none on the FP64 pipe.
 //   pairs  : lane = TARGET.  Every lane walks its own hit masks and evaluates its own neighbours; the pair body
@@ -19,21 +20,15 @@
 #include "common.cuh"
 
 #define WALK_STACK 256
-#define CELLLIST 128
-#define MAXCHUNK 64            // hit masks cover 64 chunks x 32 = 2048 staged candidates per round
+#define ROUND 384              // staged candidates per round
+#define NCHUNK (ROUND / 32)    // hit-mask chunks per round
 
 struct WarpShared {
     int stack[WALK_STACK];
-    int celllist[CELLLIST];             // packed (start << 5) | (count - 1)
-    unsigned hm[MAXCHUNK][32];          // hm[chunk][t] = candidates of the chunk inside target t's (FP32, conservative) radius
-    float4 tgt[32];                     // per target: cell-relative position + FP32 limit on r^2
-};
-
-struct Staged {
-    float4 *pos;     // relative position + radkern*h_j (rounded up)
-    int *idx;        // sorted particle slot
-    int n;           // number of staged candidates
-    float maxrel;    // max |relative coordinate| staged (for the FP32 error bound)
+    float4 spos[ROUND];                 // staged candidates: relative position + radkern*h_j (rounded up)
+    int sidx[ROUND];                    // their sorted particle slots
+    unsigned hm[NCHUNK][32];            // hm[chunk][t] = candidates of the chunk inside target t's (FP32, conservative) radius
+    float4 tgt[32];                     // per target: group-relative position + FP32 limit on r^2
 };
 
 // squared minimum-image gap between two boxes, FP32 (inputs already rounded outward)
@@ -63,55 +58,22 @@ __device__ __forceinline__ float box_gap2f(const float *tlo, const float *thi, f
     return g2;
 }
 
-// copy the particles of the cells in ws.celllist[0..ncl) into the staging slice; 4 cells per step, 8 lanes per cell
-template <bool PERIODIC>
-__device__ __forceinline__ bool stage_cells(const WarpShared &ws, int ncl, const double4 *__restrict__ pos4, double cx, double cy, double cz, double Lx,
-                                            double Ly, double Lz, float radkern, Staged &st, int cap)
-{
-    const int lane = lane_id();
-    const int sub = lane >> 3, l8 = lane & 7;
-    for (int c0 = 0; c0 < ncl; c0 += 4) {
-        int start = 0, cnt = 0;
-        if (c0 + sub < ncl) { const int pk = ws.celllist[c0 + sub]; start = pk >> 5; cnt = (pk & 31) + 1; }
-        // exclusive offsets of the (up to) 4 cells of this step
-        const int c1 = __shfl_sync(FULLMASK, cnt, 0), c2 = __shfl_sync(FULLMASK, cnt, 8), c3 = __shfl_sync(FULLMASK, cnt, 16), c4 = __shfl_sync(FULLMASK, cnt, 24);
-        const int off = (sub > 0 ? c1 : 0) + (sub > 1 ? c2 : 0) + (sub > 2 ? c3 : 0);
-        const int total = c1 + c2 + c3 + c4;
-        if (st.n + total > cap) return false;
-        for (int k = l8; k < cnt; k += 8) {
-            const int j = start + k;
-            const double4 p = pos4[j];
-            double rx = p.x - cx, ry = p.y - cy, rz = p.z - cz;
-            if (PERIODIC) {
-                if (rx > 0.5 * Lx) rx -= Lx; else if (rx < -0.5 * Lx) rx += Lx;
-                if (ry > 0.5 * Ly) ry -= Ly; else if (ry < -0.5 * Ly) ry += Ly;
-                if (rz > 0.5 * Lz) rz -= Lz; else if (rz < -0.5 * Lz) rz += Lz;
-            }
-            const float fx = (float)rx, fy = (float)ry, fz = (float)rz;
-            st.pos[st.n + off + k] = make_float4(fx, fy, fz, __double2float_ru((double)radkern * p.w));
-            st.idx[st.n + off + k] = j;
-            st.maxrel = fmaxf(st.maxrel, fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))));
-        }
-        st.n += total;
-    }
-    return true;
-}
-
-// Walk + stage.  tlo/thi: target-cell box (FP32, outward rounded); rcut_t: search radius of the target cell (incl. margin);
+// Walk.  tlo/thi: target-group box (FP32, outward rounded); rcut_t: search radius of the group (incl. margin);
 // SYM: also open nodes whose own radkern*hmax reaches the target box (force pass, get_hj of kdtree.F90:1288-1291).
-// Returns false when the scratch slice (cap) or the stack overflows.
+// Fills clist[0..ncl) with the packed hit cells ((start << 5) | (count - 1)) and returns ncl, or -1 when the list (cap) or the
+// stack overflows.  reach = max over hit cells of (search radius used + cell extent): every staged coordinate relative to the
+// group centre is bounded by halfext + reach (input of the FP32 error bound).
 template <bool SYM, bool PERIODIC>
-__device__ bool warp_walk_stage(const TreeNodeF *__restrict__ nodes, const Cell *__restrict__ cells, int ncells, const double4 *__restrict__ pos4,
-                                const float *tlo, const float *thi, float rcut_t, float radkern, double cx, double cy, double cz, double Lx, double Ly,
-                                double Lz, WarpShared &ws, Staged &st, int cap)
+__device__ int warp_walk(const TreeNodeF *__restrict__ nodes, const Cell *__restrict__ cells, int ncells, const float *tlo, const float *thi, float rcut_t,
+                         float radkern, float fLx, float fLy, float fLz, WarpShared &ws, int *__restrict__ clist, int cap, float &reach)
 {
     const int lane = lane_id();
-    st.n = 0; st.maxrel = 0.f;
-    const float fLx = (float)Lx, fLy = (float)Ly, fLz = (float)Lz;
     int ncl = 0;
+    float rmax = 0.f;
     if (ncells == 1) {
-        if (lane == 0) ws.celllist[0] = (cells[0].start << 5) | (cells[0].count - 1);
-        __syncwarp();
+        const Cell c0 = cells[0];
+        if (lane == 0) clist[0] = (c0.start << 5) | (c0.count - 1);
+        rmax = fmaxf(rcut_t, SYM ? radkern * (float)c0.hmax * 1.0001f : 0.f) + (float)fmax(c0.hi[0] - c0.lo[0], fmax(c0.hi[1] - c0.lo[1], c0.hi[2] - c0.lo[2])) * 1.0001f;
         ncl = 1;
     } else {
         int sp = 1;
@@ -127,61 +89,95 @@ __device__ bool warp_walk_stage(const TreeNodeF *__restrict__ nodes, const Cell 
             __syncwarp();
             bool hit = false;
             int child = 0;
+            float ext = 0.f;
             if (node >= 0) {
                 const TreeNodeF *nd = &nodes[node];
                 child = nd->child[slot];
                 float rc = rcut_t;
                 if (SYM) rc = fmaxf(rc, radkern * nd->hmax[slot]);
                 rc *= 1.00001f;
-                const float g2 = box_gap2f<PERIODIC>(tlo, thi, nd->lo[slot][0], nd->lo[slot][1], nd->lo[slot][2], nd->hi[slot][0], nd->hi[slot][1],
-                                                     nd->hi[slot][2], fLx, fLy, fLz);
+                const float l0 = nd->lo[slot][0], l1 = nd->lo[slot][1], l2 = nd->lo[slot][2], h0 = nd->hi[slot][0], h1 = nd->hi[slot][1], h2 = nd->hi[slot][2];
+                const float g2 = box_gap2f<PERIODIC>(tlo, thi, l0, l1, l2, h0, h1, h2, fLx, fLy, fLz);
                 hit = g2 <= rc * rc;
+                ext = rc + fmaxf(h0 - l0, fmaxf(h1 - l1, h2 - l2)) * 1.0001f;
             }
+            const bool leafhit = hit && child < 0;
             const unsigned mint = __ballot_sync(FULLMASK, hit && child >= 0);
-            const unsigned mleaf = __ballot_sync(FULLMASK, hit && child < 0);
-            if (sp + __popc(mint) > WALK_STACK) return false;
+            const unsigned mleaf = __ballot_sync(FULLMASK, leafhit);
+            if (sp + __popc(mint) > WALK_STACK) return -1;
             if (hit && child >= 0) ws.stack[sp + __popc(mint & ((1u << lane) - 1))] = child;
             sp += __popc(mint);
             if (mleaf) {
                 const int nl = __popc(mleaf);
-                if (ncl + nl > CELLLIST) {           // flush the cell list into the staging slice
-                    __syncwarp();
-                    if (!stage_cells<PERIODIC>(ws, ncl, pos4, cx, cy, cz, Lx, Ly, Lz, radkern, st, cap)) return false;
-                    ncl = 0;
-                    __syncwarp();
-                }
-                if (hit && child < 0) {
+                if (ncl + nl > cap) return -1;
+                if (leafhit) {
                     const Cell *cl = &cells[~child];
-                    ws.celllist[ncl + __popc(mleaf & ((1u << lane) - 1))] = (cl->start << 5) | (cl->count - 1);
+                    clist[ncl + __popc(mleaf & ((1u << lane) - 1))] = (cl->start << 5) | (cl->count - 1);
+                    rmax = fmaxf(rmax, ext);
                 }
                 ncl += nl;
             }
             __syncwarp();
         }
     }
-    if (ncl > 0 && !stage_cells<PERIODIC>(ws, ncl, pos4, cx, cy, cz, Lx, Ly, Lz, radkern, st, cap)) return false;
-    st.maxrel = fmaxf(st.maxrel, __shfl_xor_sync(FULLMASK, st.maxrel, 16));
-    st.maxrel = fmaxf(st.maxrel, __shfl_xor_sync(FULLMASK, st.maxrel, 8));
-    st.maxrel = fmaxf(st.maxrel, __shfl_xor_sync(FULLMASK, st.maxrel, 4));
-    st.maxrel = fmaxf(st.maxrel, __shfl_xor_sync(FULLMASK, st.maxrel, 2));
-    st.maxrel = fmaxf(st.maxrel, __shfl_xor_sync(FULLMASK, st.maxrel, 1));
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(FULLMASK, rmax, s));
+    reach = rmax;
     __syncwarp();
-    return true;
+    return ncl;
+}
+
+// Copy the particles of the next cells of the list into the shared-memory round buffer: 4 cells per step, 8 lanes per cell.
+// posrec[j * stride] = {x, y, z, w} with w = h (WINV = false) or 1/h (WINV = true).  Returns the number staged; cellpos advances.
+template <bool PERIODIC, bool WINV>
+__device__ __forceinline__ int stage_round(WarpShared &ws, const int *__restrict__ clist, int ncl, int &cellpos, const double4 *__restrict__ posrec, int stride,
+                                           double cx, double cy, double cz, double Lx, double Ly, double Lz, float radkern, int maxleaf)
+{
+    const int lane = lane_id();
+    const int sub = lane >> 3, l8 = lane & 7;
+    int n = 0;
+    while (cellpos < ncl && n + 4 * maxleaf <= ROUND) {  // the next 4 cells (<= maxleaf particles each) always fit
+        int start = 0, cnt = 0;
+        if (cellpos + sub < ncl) { const int pk = clist[cellpos + sub]; start = pk >> 5; cnt = (pk & 31) + 1; }
+        // exclusive offsets of the (up to) 4 cells of this step
+        const int c1 = __shfl_sync(FULLMASK, cnt, 0), c2 = __shfl_sync(FULLMASK, cnt, 8), c3 = __shfl_sync(FULLMASK, cnt, 16), c4 = __shfl_sync(FULLMASK, cnt, 24);
+        const int off = n + (sub > 0 ? c1 : 0) + (sub > 1 ? c2 : 0) + (sub > 2 ? c3 : 0);
+        for (int k = l8; k < cnt; k += 8) {
+            const int j = start + k;
+            const double4 p = posrec[(size_t)j * stride];
+            double rx = p.x - cx, ry = p.y - cy, rz = p.z - cz;
+            if (PERIODIC) {
+                if (rx > 0.5 * Lx) rx -= Lx; else if (rx < -0.5 * Lx) rx += Lx;
+                if (ry > 0.5 * Ly) ry -= Ly; else if (ry < -0.5 * Ly) ry += Ly;
+                if (rz > 0.5 * Lz) rz -= Lz; else if (rz < -0.5 * Lz) rz += Lz;
+            }
+            float rkh;
+            if (WINV) rkh = __fmul_ru(radkern, __frcp_ru(__double2float_rd(p.w)));   // >= radkern * h_j
+            else rkh = __double2float_ru((double)radkern * p.w);
+            ws.spos[off + k] = make_float4((float)rx, (float)ry, (float)rz, rkh);
+            ws.sidx[off + k] = j;
+        }
+        n += c1 + c2 + c3 + c4;
+        cellpos += 4;
+    }
+    __syncwarp();
+    return n;
 }
 
 __device__ __forceinline__ float prefilter_slack(float maxrel);
 __device__ __forceinline__ float prefilter_limit(float rc, float slack);
 
-// hit masks for one round of staged candidates [base, base + nchunk*32): lane = candidate, loop over targets
+// hit masks for the n staged candidates of the round: lane = candidate, loop over targets
 template <bool SYM>
-__device__ __forceinline__ void build_masks(WarpShared &ws, const Staged &st, int base, int nchunk, int ntargets, float slack)
+__device__ __forceinline__ void build_masks(WarpShared &ws, int n, int ntargets, float slack)
 {
     const int lane = lane_id();
+    const int nchunk = (n + 31) >> 5;
     for (int c = 0; c < nchunk; c++) {
-        const int i = base + c * 32 + lane;
-        const bool valid = i < st.n;
+        const int i = c * 32 + lane;
+        const bool valid = i < n;
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) r = st.pos[i];
+        if (valid) r = ws.spos[i];
         float limj = 0.f;
         if (SYM) limj = prefilter_limit(r.w, slack);
         unsigned mine = 0u;
@@ -233,25 +229,4 @@ __device__ __forceinline__ float prefilter_limit(float rc, float slack)
 {
     const float r = rc + slack;
     return r * r * 1.000002f;
-}
-
-// generic transpose reduction for N = 8,16,32 partial sums per lane; lane L ends with the total of v[L >> (5 - log2 N)]
-template <int N>
-__device__ __forceinline__ double warp_transpose_reduce(double (&v)[N])
-{
-    const int lane = lane_id();
-    int s = 16;
-#pragma unroll
-    for (int cnt = N; cnt > 1; cnt >>= 1, s >>= 1) {
-        const bool upper = (lane & s) != 0;
-#pragma unroll
-        for (int k = 0; k < cnt / 2; k++) {
-            const double send = upper ? v[k] : v[k + cnt / 2];
-            const double keep = upper ? v[k + cnt / 2] : v[k];
-            v[k] = keep + __shfl_xor_sync(FULLMASK, send, s);
-        }
-    }
-    double r = v[0];
-    for (; s >= 1; s >>= 1) r += __shfl_xor_sync(FULLMASK, r, s);
-    return r;
 }
