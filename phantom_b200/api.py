@@ -20,7 +20,7 @@ import numpy as np
 from .params import SphParams, SphScalars
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsphgpu.so")
+LIB_PATH = os.environ.get("SPHGPU_LIB", os.path.join(_HERE, "libsphgpu.so"))   # SPHGPU_LIB: A/B builds of the same library (tools/variants.sh)
 
 F_XYZH, F_VXYZU, F_FXYZU, F_FEXT, F_BEVOL, F_DBEVOL, F_EOSVARS, F_DIVCURLV, F_DIVCURLB, F_ALPHAIND, F_GRADH, F_DVDX, \
     F_POTEN, F_DIVBSYMM, F_IPHASE, F_IBIN, F_DUSTFRAC, F_TSTOP = [1 << k for k in range(18)]

@@ -217,7 +217,13 @@ __device__ __forceinline__ void exactlinear_d(double &gx, double &gy, double &gz
 }
 
 template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST>
-__global__ void __launch_bounds__(128, 3) k_density(const DensArgs a, const __grid_constant__ DevParams dp)
+#ifndef DENS_MINB
+#define DENS_MINB 4
+#endif
+#ifndef DENS_NPAIR
+#define DENS_NPAIR 2
+#endif
+__global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density(const DensArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
     __shared__ WarpShared wsh[4];
@@ -331,6 +337,13 @@ __global__ void __launch_bounds__(128, 3) k_density(const DensArgs a, const __gr
                         const int slot1 = next_hit(ws, lane, nchunk, c, m);
                         const int j0 = idxlist[slot0], j1 = (slot1 >= 0) ? idxlist[slot1] : s;
                         st_surv += 1 + (slot1 >= 0);
+#if DENS_NPAIR >= 3
+                        const int slot2 = (slot1 >= 0) ? next_hit(ws, lane, nchunk, c, m) : -1;
+                        const int j2 = (slot2 >= 0) ? idxlist[slot2] : s;
+                        st_surv += (slot2 >= 0);
+                        dens_pair_fast<K, PERIODIC, MHD, GRAV>(v, w, nneighi, j2, s, pi.x, pi.y, pi.z, h, hi1, hi21, vi, ai, bi, a.drec, pmassi,
+                                                               dp.p.hfact, use_da, interior, Lx, Ly, Lz);
+#endif
                         dens_pair_fast<K, PERIODIC, MHD, GRAV>(v, w, nneighi, j0, s, pi.x, pi.y, pi.z, h, hi1, hi21, vi, ai, bi, a.drec, pmassi,
                                                                dp.p.hfact, use_da, interior, Lx, Ly, Lz);
                         dens_pair_fast<K, PERIODIC, MHD, GRAV>(v, w, nneighi, j1, s, pi.x, pi.y, pi.z, h, hi1, hi21, vi, ai, bi, a.drec, pmassi,

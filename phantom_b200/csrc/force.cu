@@ -299,7 +299,13 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
 // gathers, the minimum-image wrap is skipped for target groups whose search region lies inside the box, and the j-side terms that
 // vanish with grad W_j (q2j >= R^2) are not masked separately.
 template <int K, bool PERIODIC, bool MHD, bool ADIA>
-__global__ void __launch_bounds__(128, MHD ? 3 : 4) k_force_fast(const ForceArgs a, const __grid_constant__ DevParams dp)
+#ifndef FORCE_MINB
+#define FORCE_MINB 5
+#endif
+#ifndef FORCE_NPAIR
+#define FORCE_NPAIR 2
+#endif
+__global__ void __launch_bounds__(128, MHD ? 3 : FORCE_MINB) k_force_fast(const ForceArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
     __shared__ WarpShared wsh[4];
@@ -450,8 +456,20 @@ __global__ void __launch_bounds__(128, MHD ? 3 : 4) k_force_fast(const ForceArgs
                 const int slot0 = act ? next_hit(ws, lane, nchunk, c, m) : -1;
                 if (slot0 < 0) break;
                 const int slot1 = next_hit(ws, lane, nchunk, c, m);
+#if FORCE_NPAIR >= 3
+                const int slot2 = (slot1 >= 0) ? next_hit(ws, lane, nchunk, c, m) : -1;
+#endif
+#if FORCE_NPAIR >= 4
+                const int slot3 = (slot2 >= 0) ? next_hit(ws, lane, nchunk, c, m) : -1;
+#endif
                 pair(slot0);
                 pair(slot1);
+#if FORCE_NPAIR >= 3
+                pair(slot2);
+#endif
+#if FORCE_NPAIR >= 4
+                pair(slot3);
+#endif
             }
             __syncwarp();
         }

@@ -20,7 +20,9 @@
 #include "common.cuh"
 
 #define WALK_STACK 256
+#ifndef ROUND
 #define ROUND 384              // staged candidates per round
+#endif
 #define NCHUNK (ROUND / 32)    // hit-mask chunks per round
 
 struct WarpShared {
