@@ -16,7 +16,7 @@ interfaces take: xyzh(4,N) is a C-contiguous (N,4) array, etc.
 import math
 import numpy as np
 
-from .params import default_params, IGAS, IBOUNDARY, KERNEL_CUBIC, KERNEL_QUINTIC
+from .params import default_params, IGAS, IBOUNDARY, IDUST, KERNEL_CUBIC, KERNEL_QUINTIC
 
 _M1, _M2 = 2147483563, 2147483399
 _A1, _A2 = 40014, 40692
@@ -424,4 +424,71 @@ def setup_random_sphere(n=1000, iseed=-43587, gravity=True, u=0.05):
     xyzh[:, 3] = p.hfact * (p.massoftype[IGAS] / rho0) ** (1. / 3.)
     part = Particles(p, xyzh)
     part.vxyzu[:, 3] = u
+    return part
+
+
+def setup_dustydisc(ngas=8000, ndust=2000, iseed=-43587, r_in=1.0, r_out=150.0, pindex=1.0, qindex=0.25, hor_in=0.05,
+                    alpha_ss=0.005, disc_mass=0.05, dust_to_gas=0.01, ind_timesteps=True):
+    """C4: SETUP=dustydisc -- gas + dust (two-fluid, dust as particles) accretion disc around a central star that is handled
+    outside the hot path (its force enters through fext).  Reference defaults: R_in=1, R_out=150, Sigma ~ R^-pindex,
+    c_s ~ R^-qindex, H/R = 0.05 at R_in, alphaSS = 0.005 (setup_disc.f90:427-443); locally isothermal ieos = 3 (:709);
+    disc_viscosity because alphaSS > 0 (set_disc.f90:488-489) with alpha_AV from alphaSS (setup_disc.f90:1166);
+    dust_method = 2, dust-to-gas 0.01, 1 cm grains of 3 g/cm^3, Epstein/Stokes drag idrag = 1 (set_dust_options.f90:96-103);
+    quintic kernel (DUST default, build/Makefile:213-218); IND_TIMESTEPS (Makefile_setups:541-549).
+    Positions are Monte-Carlo sampled with ran2 (seed -43587): R from Sigma(R) R dR, z Gaussian with H(R), uniform azimuth.
+    Code units: au, solar mass, G = 1."""
+    udist, umass = 1.496e13, 1.989e33
+    unit_density = umass / udist ** 3
+    p = default_params(kernel=KERNEL_QUINTIC, hfact=1.0, periodic=0, isothermal=1, ieos=3, dust=1, idrag=1, disc_viscosity=1,
+                       ind_timesteps=int(ind_timesteps), qfacdisc=qindex, gamma=1.0,
+                       xmin=-r_out, xmax=r_out, ymin=-r_out, ymax=r_out, zmin=-r_out, zmax=r_out)
+    cs_in = hor_in * math.sqrt(1.0 / r_in)                 # H = c_s / Omega with M_star = 1
+    p.polyk = cs_in ** 2 * r_in ** (2. * qindex)           # c_s^2 = polyk R^-2q (eos.f90:226-234)
+    # alpha_AV from alphaSS: alpha_SS ~ alpha_AV/10 <h>/H (setup_disc.f90:1166, Lodato & Price 2010); <h>/H ~ 0.5 at this resolution
+    p.alpha = min(max(10. * alpha_ss / 0.5, 0.01), 1.0)
+    p.const_av = 0
+    p.grainsize = 1.0 / udist
+    p.graindens = 3.0 / unit_density
+    mass_mol_gas = 2. * 1.67262158e-24 / umass             # dust.f90:96-99 (init_drag)
+    cross_section_gas = 2.367e-15 / udist ** 2
+    p.seff = math.pi / math.sqrt(2.) * 5. / 64. * mass_mol_gas / cross_section_gas
+    p.massoftype[IGAS] = disc_mass / ngas
+    p.massoftype[IDUST] = disc_mass * dust_to_gas / ndust
+    rng = Ran2(iseed)
+
+    def sample(n, hfac):
+        u = rng.draw(3 * n).reshape(n, 3)
+        if abs(pindex - 2.) < 1e-12:
+            R = r_in * (r_out / r_in) ** u[:, 0]
+        else:                                              # P(R) ~ R^(1-pindex)
+            e = 2. - pindex
+            R = (r_in ** e + u[:, 0] * (r_out ** e - r_in ** e)) ** (1. / e)
+        phi = 2. * math.pi * u[:, 1]
+        H = hfac * hor_in * r_in * (R / r_in) ** (1.5 - qindex)
+        g = rng.draw(2 * n).reshape(n, 2)
+        z = H * np.sqrt(-2. * np.log(np.maximum(g[:, 0], 1e-300))) * np.cos(2. * math.pi * g[:, 1])
+        return R, phi, z, H
+
+    Rg, phig, zg, Hg = sample(ngas, 1.0)
+    Rd, phid, zd, Hd = sample(ndust, 0.5)                  # settled dust layer
+    R = np.concatenate([Rg, Rd]); phi = np.concatenate([phig, phid]); z = np.concatenate([zg, zd]); H = np.concatenate([Hg, Hd])
+    n = ngas + ndust
+    iphase = np.full(n, IGAS, dtype=np.int8)
+    iphase[ngas:] = IDUST
+    pm = np.where(iphase == IGAS, p.massoftype[IGAS], p.massoftype[IDUST])
+    ntype = np.where(iphase == IGAS, ngas, ndust)
+    sig0 = (2. - pindex) / (2. * math.pi * (r_out ** (2. - pindex) - r_in ** (2. - pindex))) if abs(pindex - 2.) > 1e-12 else 1.
+    rho_mid = pm * ntype * sig0 * R ** (-pindex) / (math.sqrt(2. * math.pi) * H)
+    rho = np.maximum(rho_mid * np.exp(-0.5 * (z / H) ** 2), 1e-3 * rho_mid)
+    xyzh = np.zeros((n, 4))
+    xyzh[:, 0], xyzh[:, 1], xyzh[:, 2] = R * np.cos(phi), R * np.sin(phi), z
+    xyzh[:, 3] = p.hfact * (pm / rho) ** (1. / 3.)
+    part = Particles(p, xyzh, iphase)
+    vk = np.sqrt(1.0 / R)                                   # Keplerian; gas slightly sub-Keplerian through the pressure gradient
+    cs2 = p.polyk * R ** (-2. * qindex)
+    vphi = np.where(iphase == IGAS, vk * np.sqrt(np.maximum(1. - (pindex + qindex + 1.5) * cs2 / vk ** 2, 0.)), vk)
+    part.vxyzu[:, 0], part.vxyzu[:, 1] = -vphi * np.sin(phi), vphi * np.cos(phi)
+    r3 = (R * R + z * z) ** 1.5
+    part.fext[:, 0], part.fext[:, 1], part.fext[:, 2] = -xyzh[:, 0] / r3, -xyzh[:, 1] / r3, -z / r3      # central star, M = 1
+    part.alphaind[:, 0] = p.alpha
     return part
