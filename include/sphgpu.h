@@ -205,6 +205,26 @@ int sphgpu_halo_recvbuf(sphgpu_ctx *ctx, int64_t nrecords, int record_doubles, v
 int sphgpu_halo_unpack(sphgpu_ctx *ctx, int stage, int64_t nghost);
 int64_t sphgpu_nghost(sphgpu_ctx *ctx);
 
+/* ---- the callers either side of the path, resident on the device -------------------------------- */
+/* step (src/main/step_leapfrog.f90:95-760) with global timesteps and substep_sph (substepping.F90:241-264):
+ * predictor, drift, predict_sph (h prediction, alpha decay), derivs(1), corrector iterated with derivs(2) until the velocity
+ * error is below tolv (timestep.f90 tolv = 1e-2).  dterr as check_velocity_error returns it (:769-843). */
+typedef struct sphgpu_step_out {
+    double dtcourant, dtforce, dterr, errmax;
+    int64_t its;
+    sphgpu_scalars scalars;     /* of the last derivs call of the step */
+} sphgpu_step_out;
+int sphgpu_step_resident(sphgpu_ctx *ctx, double dtsph, double tolv, sphgpu_step_out *out);
+
+/* compute_energies (src/main/energies.f90:64-760): the conserved-quantity sums of the resident state */
+typedef struct sphgpu_energies {
+    double ekin, etherm, emag, epot, etot;
+    double totmom, xmom, ymom, zmom, angtot, angx, angy, angz;
+    double mtot, xcom, ycom, zcom, rhomax;
+    int64_t np;
+} sphgpu_energies;
+int sphgpu_energies_resident(sphgpu_ctx *ctx, sphgpu_energies *out);
+
 /* register-resident DFMA microbenchmark: returns measured FP64 TFLOP/s of this device (roofline denominator) */
 double sphgpu_measure_fp64_peak(sphgpu_ctx *ctx);
 /* device copy bandwidth GB/s (read+write) */

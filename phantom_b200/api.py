@@ -17,7 +17,7 @@ import ctypes as C
 import os
 import numpy as np
 
-from .params import SphParams, SphScalars
+from .params import SphParams, SphScalars, SphStepOut, SphEnergies
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SPHGPU_LIB", os.path.join(_HERE, "libsphgpu.so"))   # SPHGPU_LIB: A/B builds of the same library (tools/variants.sh)
@@ -34,7 +34,7 @@ EXPORTS = [
     "sphgpu_cons2prim_resident", "sphgpu_force_resident", "sphgpu_derivs_resident", "sphgpu_build_tree", "sphgpu_densityiterate",
     "sphgpu_cons2prim_everything", "sphgpu_force", "sphgpu_derivs", "sphgpu_get_neighbour_stats", "sphgpu_neighbour_sets",
     "sphgpu_measure_fp64_peak", "sphgpu_measure_copy_bw", "sphgpu_local_hmax", "sphgpu_halo_select", "sphgpu_halo_pack",
-    "sphgpu_halo_recvbuf", "sphgpu_halo_unpack", "sphgpu_nghost", "sphgpu_set_timestep_bins", "sphgpu_get_gravity_timings", "sphgpu_gravity_tree",
+    "sphgpu_halo_recvbuf", "sphgpu_halo_unpack", "sphgpu_nghost", "sphgpu_set_timestep_bins", "sphgpu_get_gravity_timings", "sphgpu_gravity_tree", "sphgpu_step_resident", "sphgpu_energies_resident",
 ]
 
 
@@ -103,6 +103,8 @@ def load_library():
         L.sphgpu_get_gravity_timings.argtypes = [vp, C.POINTER(dbl)]
         L.sphgpu_gravity_tree.argtypes = [vp, i64, vp, vp, vp]
         L.sphgpu_gravity_tree.restype = i64
+        L.sphgpu_step_resident.argtypes = [vp, dbl, dbl, C.POINTER(SphStepOut)]
+        L.sphgpu_energies_resident.argtypes = [vp, C.POINTER(SphEnergies)]
         _lib = L
     return _lib
 
@@ -239,6 +241,18 @@ class SphGpu:
         sc = SphScalars()
         self._check(self.L.sphgpu_force_resident(self.h, icall, dt, C.byref(sc)))
         return sc
+
+    def step_resident(self, dtsph, tolv=1.e-2):
+        """one leapfrog step of the resident state (step_leapfrog.f90:95, global timesteps)"""
+        out = SphStepOut()
+        self._check(self.L.sphgpu_step_resident(self.h, float(dtsph), float(tolv), C.byref(out)))
+        return out
+
+    def energies_resident(self):
+        """compute_energies (energies.f90:64) on the resident state"""
+        out = SphEnergies()
+        self._check(self.L.sphgpu_energies_resident(self.h, C.byref(out)))
+        return out
 
     def timings_ms(self):
         t = (C.c_double * 4)()

@@ -114,6 +114,7 @@ struct sphgpu_ctx {
     DevBuf<float> divcurlv, divcurlB, alphaind, gradh, dvdx, poten, divBsymm;
     DevBuf<int8_t> iphase, ibin, ibin_old, ibin_wake;
     DevBuf<double> dustfrac, tstop;
+    DevBuf<double> v_true, B_true;          // step.cu: the evolved v, B/rho while vxyzu/Bevol hold the predicted values
     DevBuf<double4> gacc;                   // far-field gravity {fx,fy,fz,pot} per particle (gravity.cu -> force epilogue)
     // ---- sorted working set ----
     int64_t nlive = 0;

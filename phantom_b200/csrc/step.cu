@@ -1,0 +1,280 @@
+// step.cu -- the callers either side of the hot path, kept on the device so that a run never moves particle data over PCIe
+// between steps:
+//   * leapfrog step with global timesteps: step (src/main/step_leapfrog.f90:95-760) -- velocity predictor (:183-235), drift of
+//     substep_sph (substepping.F90:241-264), predict_sph with the h prediction and the Cullen-Dehnen alpha decay (:307-400),
+//     derivs, corrector with the velocity-error iteration (:482-623, check_velocity_error :769-843);
+//   * conserved-quantity diagnostics: compute_energies (src/main/energies.f90:64-760; ekin, etherm, emag, epot, linear and
+//     angular momentum, centre of mass).
+// All of it is O(N) streaming over the caller-ordered arrays (HBM-bound, ~250 B per particle and step against the ~20 kflop of
+// the derivative evaluation); the kernels are plain grid-stride AXPYs, the reductions one block sum + one atomic per block.
+// External forces and sink particles (substep with fext, step_leapfrog.f90:280-284) and individual timesteps are outside this
+// routine: the host integrates those and calls sphgpu_derivs.
+#include "common.cuh"
+#include <float.h>
+#include <string.h>
+
+namespace {
+
+struct StepArgs {
+    int64_t n; int nvu, mhd, nalpha, multitype;
+    double *xyzh, *v, *vpred, *f, *B, *Bpred, *dB, *eos_vars; float *divcurlv, *alphaind; const int8_t *iphase;
+    double hfact, dt, hdt; double massoftype[SPHGPU_MAXTYPES];
+    double *red;       // [0] errmax (as ordered bits), [1] v2mean sum, [2] np
+};
+
+__device__ __forceinline__ bool dead(double h) { return h < DBL_MIN; }     // isdead_or_accreted (part.F90:931)
+
+// velocity predictor (step_leapfrog.f90:183-235): v, u, B/rho, psi to the half step with the "slow" forces
+__global__ void k_predict(const StepArgs a)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (dead(a.xyzh[4 * i + 3])) continue;
+        const int itype = abs((int)a.iphase[i]);
+        if (itype == IBOUNDARY) continue;
+        for (int k = 0; k < a.nvu; k++) a.v[a.nvu * i + k] += a.hdt * a.f[a.nvu * i + k];
+        if (a.mhd && itype == IGAS) for (int k = 0; k < 4; k++) a.B[4 * i + k] += a.hdt * a.dB[4 * i + k];
+    }
+}
+
+// substep_sph (substepping.F90:241-264): main position update
+__global__ void k_drift(const StepArgs a)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (dead(a.xyzh[4 * i + 3])) continue;
+        for (int k = 0; k < 3; k++) a.xyzh[4 * i + k] += a.dt * a.v[a.nvu * i + k];
+    }
+}
+
+// predict_sph (step_leapfrog.f90:307-400): h prediction, v/u/B to the full step for the force evaluation, alpha decay
+__global__ void k_predict_sph(const StepArgs a)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double h = a.xyzh[4 * i + 3];
+        if (dead(h)) continue;
+        const int itype = abs((int)a.iphase[i]);
+        if (itype == IBOUNDARY) {
+            for (int k = 0; k < a.nvu; k++) a.vpred[a.nvu * i + k] = a.v[a.nvu * i + k];
+            if (a.mhd) for (int k = 0; k < 4; k++) a.Bpred[4 * i + k] = a.B[4 * i + k];
+            continue;
+        }
+        const double pmassi = a.massoftype[a.multitype ? itype : IGAS];
+        const double rhoi = rhoh_d(h, pmassi, a.hfact);
+        const double dhdrhoi = -h / (3. * rhoi);                                        // part.F90:791
+        const double hnew = h - a.dt * dhdrhoi * rhoi * (double)a.divcurlv[i];           // :332
+        a.xyzh[4 * i + 3] = hnew;
+        for (int k = 0; k < a.nvu; k++) a.vpred[a.nvu * i + k] = a.v[a.nvu * i + k] + a.hdt * a.f[a.nvu * i + k];
+        if (a.mhd) {
+            if (itype == IGAS) for (int k = 0; k < 4; k++) a.Bpred[4 * i + k] = a.B[4 * i + k] + a.hdt * a.dB[4 * i + k];
+            else for (int k = 0; k < 4; k++) a.Bpred[4 * i + k] = a.B[4 * i + k];
+        }
+        if (a.nalpha >= 2) {                                                             // Cullen & Dehnen (2010) switch, :378-389
+            const double spsoundi = a.eos_vars[7 * i + 1];
+            const double tdecay1 = 0.1 * spsoundi / hnew;                                // avdecayconst (shock_capturing.f90:32)
+            const double ddenom = 1. / (1. + a.dt * tdecay1);
+            const double alphaloci = (double)a.alphaind[3 * i + 1];
+            const float a1 = a.alphaind[3 * i];
+            if ((double)a1 < alphaloci) a.alphaind[3 * i] = (float)alphaloci;
+            else a.alphaind[3 * i] = (float)(((double)a1 + a.dt * alphaloci * tdecay1) * ddenom);
+        }
+    }
+}
+
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.;
+    if (threadIdx.x < 32) { r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.; r = warp_sum(r); }
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ double block_max(double v, double *sh)
+{
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.;
+    if (threadIdx.x < 32) { r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.; r = warp_max(r); }
+    __syncthreads();
+    return r;
+}
+
+// corrector (step_leapfrog.f90:482-623, global timesteps): v to the full step, error against the predicted v
+__global__ void k_correct(const StepArgs a)
+{
+    __shared__ double sh[32];
+    double errmax = 0., v2sum = 0., np = 0.;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (dead(a.xyzh[4 * i + 3])) continue;
+        const int itype = abs((int)a.iphase[i]);
+        if (itype == IBOUNDARY) continue;
+        const double vx = a.v[a.nvu * i] + a.hdt * a.f[a.nvu * i], vy = a.v[a.nvu * i + 1] + a.hdt * a.f[a.nvu * i + 1],
+                     vz = a.v[a.nvu * i + 2] + a.hdt * a.f[a.nvu * i + 2];
+        const double ex = vx - a.vpred[a.nvu * i], ey = vy - a.vpred[a.nvu * i + 1], ez = vz - a.vpred[a.nvu * i + 2];
+        errmax = fmax(errmax, ex * ex + ey * ey + ez * ez);
+        v2sum += vx * vx + vy * vy + vz * vz; np += 1.;
+        a.v[a.nvu * i] = vx; a.v[a.nvu * i + 1] = vy; a.v[a.nvu * i + 2] = vz;
+        if (a.nvu >= 4) a.v[a.nvu * i + 3] += a.hdt * a.f[a.nvu * i + 3];
+        if (a.mhd && itype == IGAS) for (int k = 0; k < 4; k++) a.B[4 * i + k] += a.hdt * a.dB[4 * i + k];
+    }
+    errmax = block_max(errmax, sh); v2sum = block_sum(v2sum, sh); np = block_sum(np, sh);
+    if (threadIdx.x == 0) { atomic_max_pos(&a.red[0], errmax); atomicAdd(&a.red[1], v2sum); atomicAdd(&a.red[2], np); }
+}
+
+// not converged (step_leapfrog.f90:651-701): the new v becomes the prediction, v goes back to the half step
+__global__ void k_unconverged(const StepArgs a)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int itype = abs((int)a.iphase[i]);
+        if (itype == IBOUNDARY) continue;
+        for (int k = 0; k < a.nvu; k++) { const double v = a.v[a.nvu * i + k]; a.vpred[a.nvu * i + k] = v; a.v[a.nvu * i + k] = v - a.hdt * a.f[a.nvu * i + k]; }
+        if (a.mhd) for (int k = 0; k < 4; k++) {
+            const double b = a.B[4 * i + k]; a.Bpred[4 * i + k] = b;
+            if (itype == IGAS) a.B[4 * i + k] = b - a.hdt * a.dB[4 * i + k];
+        }
+    }
+}
+
+// compute_energies (energies.f90:205-706), the sums this path defines
+struct EnArgs {
+    int64_t n; int nvu, mhd, gravity, ieos, multitype;
+    const double *xyzh, *v, *B, *eos_vars; const float *poten; const int8_t *iphase;
+    double hfact, gamma; double massoftype[SPHGPU_MAXTYPES];
+    double *out;       // 16 sums
+};
+enum { E_KIN = 0, E_THERM, E_MAG, E_POT, E_XMOM, E_YMOM, E_ZMOM, E_ANGX, E_ANGY, E_ANGZ, E_MTOT, E_XCOM, E_YCOM, E_ZCOM, E_NP, E_RHOMAX, E_COUNT };
+
+__global__ void k_energies(const EnArgs a)
+{
+    __shared__ double sh[32];
+    double s[E_COUNT];
+    for (int k = 0; k < E_COUNT; k++) s[k] = 0.;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double4 x = reinterpret_cast<const double4 *>(a.xyzh)[i];
+        if (dead(x.w)) continue;                                   // accreted particles are outside this path
+        const int itype = abs((int)a.iphase[i]);
+        const double pm = a.massoftype[a.multitype ? itype : IGAS];
+        const double rho = rhoh_d(x.w, pm, a.hfact);
+        const double vx = a.v[a.nvu * i], vy = a.v[a.nvu * i + 1], vz = a.v[a.nvu * i + 2];
+        s[E_XCOM] += pm * x.x; s[E_YCOM] += pm * x.y; s[E_ZCOM] += pm * x.z;
+        s[E_MTOT] += pm; s[E_NP] += 1.; s[E_RHOMAX] = fmax(s[E_RHOMAX], rho);
+        s[E_XMOM] += pm * vx; s[E_YMOM] += pm * vy; s[E_ZMOM] += pm * vz;
+        s[E_ANGX] += pm * (x.y * vz - x.z * vy); s[E_ANGY] += pm * (x.z * vx - x.x * vz); s[E_ANGZ] += pm * (x.x * vy - x.y * vx);
+        s[E_KIN] += pm * (vx * vx + vy * vy + vz * vz);
+        if (a.gravity) s[E_POT] += (double)a.poten[i];
+        if (itype == IGAS) {
+            if (a.nvu >= 4) s[E_THERM] += pm * a.v[a.nvu * i + 3];
+            else if (a.ieos == 2 && a.gamma > 1.001) s[E_THERM] += pm * (a.eos_vars[7 * i] / rho) / (a.gamma - 1.);     // :413-416
+            if (a.mhd) {
+                const double bx = a.B[4 * i] * rho, by = a.B[4 * i + 1] * rho, bz = a.B[4 * i + 2] * rho;
+                s[E_MAG] += pm * (bx * bx + by * by + bz * bz) * (1. / rho);
+            }
+        }
+    }
+    for (int k = 0; k < E_COUNT; k++) {
+        const double r = (k == E_RHOMAX) ? block_max(s[k], sh) : block_sum(s[k], sh);
+        if (threadIdx.x == 0) { if (k == E_RHOMAX) atomic_max_pos(&a.out[k], r); else atomicAdd(&a.out[k], r); }
+    }
+}
+
+}  // namespace
+
+#define SL(c, kern, ...) do { kern<<<(c)->numSMs * 8, 256, 0, (c)->stream>>>(__VA_ARGS__); (c)->launches++; } while (0)
+
+extern "C" {
+
+int sphgpu_step_resident(sphgpu_ctx *c, double dtsph, double tolv, sphgpu_step_out *out)
+{
+    if (!c || !(dtsph > 0.)) return SPHGPU_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const sphgpu_params &p = c->hp.p;
+    if (p.ind_timesteps) { c->err = "step: individual timesteps are integrated by the host (sphgpu_derivs); this routine is the global-timestep leapfrog"; return SPHGPU_ERR_ARG; }
+    const int64_t n = c->npart;
+    const int nvu = c->hp.nvu;
+    if (n <= 0) return SPHGPU_ERR_STATE;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, c->v_true.ensure((size_t)nvu * n)); if (p.mhd) CUDA_TRY(c, c->B_true.ensure(4 * (size_t)n));
+    CUDA_TRY(c, c->dscal.ensure(DS_COUNT));
+    // the evolved v, B live in v_true/B_true during the step; c->vxyzu / c->Bevol hold the predicted values derivs reads
+    CUDA_TRY(c, cudaMemcpyAsync(c->v_true.p, c->vxyzu.p, sizeof(double) * nvu * n, cudaMemcpyDeviceToDevice, st));
+    if (p.mhd) CUDA_TRY(c, cudaMemcpyAsync(c->B_true.p, c->Bevol.p, sizeof(double) * 4 * n, cudaMemcpyDeviceToDevice, st));
+    StepArgs a; memset(&a, 0, sizeof a);
+    a.n = n; a.nvu = nvu; a.mhd = p.mhd; a.nalpha = c->hp.nalpha; a.multitype = 1;
+    a.xyzh = c->xyzh.p; a.v = c->v_true.p; a.vpred = c->vxyzu.p; a.f = c->fxyzu.p; a.B = c->B_true.p; a.Bpred = c->Bevol.p; a.dB = c->dBevol.p;
+    a.eos_vars = c->eos_vars.p; a.divcurlv = c->divcurlv.p; a.alphaind = c->alphaind.p; a.iphase = c->iphase.p;
+    a.hfact = p.hfact; a.dt = dtsph; a.hdt = 0.5 * dtsph; a.red = c->dscal.p + 16;
+    for (int k = 0; k < SPHGPU_MAXTYPES; k++) a.massoftype[k] = p.massoftype[k];
+    SL(c, k_predict, a);
+    SL(c, k_drift, a);
+    SL(c, k_predict_sph, a);
+    c->tree_valid = false;
+    sphgpu_scalars sc;
+    TRY(sphgpu_derivs_resident(c, 1, dtsph, &sc));
+    int its = 0; bool converged = false;
+    double errmax = 0., dterr = 1.e29;
+    while (its < 30 && !converged) {                                  // step_leapfrog.f90:441-759
+        its++;
+        CUDA_TRY(c, cudaMemsetAsync(a.red, 0, 3 * sizeof(double), st));
+        SL(c, k_correct, a);
+        double red[3];
+        CUDA_TRY(c, cudaMemcpyAsync(red, a.red, sizeof red, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        // check_velocity_error (step_leapfrog.f90:769-843)
+        const double v2mean = red[2] > 0. ? red[1] / red[2] : 0.;
+        errmax = v2mean > DBL_MIN ? red[0] / sqrt(v2mean) : 0.;
+        double errtol = tolv;
+        if (tolv < 1.e2) {
+            const double dtf = fmin(sc.dtcourant, sc.dtforce);
+            if (dtf > dtsph && dtf < 1.e29) errtol = errtol * (dtsph / dtf) * (dtsph / dtf);
+            if (its == 1 && errtol > DBL_MIN && errmax > DBL_EPSILON) dterr = dtsph * sqrt(errtol / errmax);
+            converged = errmax < tolv;
+        } else converged = true;
+        if (!converged) {
+            SL(c, k_unconverged, a);
+            TRY(sphgpu_derivs_resident(c, 2, dtsph, &sc));
+        }
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->vxyzu.p, c->v_true.p, sizeof(double) * nvu * n, cudaMemcpyDeviceToDevice, st));
+    if (p.mhd) CUDA_TRY(c, cudaMemcpyAsync(c->Bevol.p, c->B_true.p, sizeof(double) * 4 * n, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    CUDA_TRY(c, cudaGetLastError());
+    if (out) { memset(out, 0, sizeof *out); out->dtcourant = sc.dtcourant; out->dtforce = sc.dtforce; out->dterr = dterr; out->errmax = errmax; out->its = its; out->scalars = sc; }
+    return SPHGPU_OK;
+}
+
+int sphgpu_energies_resident(sphgpu_ctx *c, sphgpu_energies *out)
+{
+    if (!c || !out) return SPHGPU_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const sphgpu_params &p = c->hp.p;
+    const int64_t n = c->nlocal > 0 ? c->nlocal : c->npart;          // ghosts are not summed
+    if (n <= 0) return SPHGPU_ERR_STATE;
+    CUDA_TRY(c, c->dscal.ensure(DS_COUNT));
+    double *dout = c->dscal.p + 16;
+    CUDA_TRY(c, cudaMemsetAsync(dout, 0, E_COUNT * sizeof(double), c->stream));
+    EnArgs a; memset(&a, 0, sizeof a);
+    a.n = n; a.nvu = c->hp.nvu; a.mhd = p.mhd; a.gravity = p.gravity; a.ieos = p.ieos; a.multitype = 1;
+    a.xyzh = c->xyzh.p; a.v = c->vxyzu.p; a.B = c->Bevol.p; a.eos_vars = c->eos_vars.p; a.poten = c->poten.p; a.iphase = c->iphase.p;
+    a.hfact = p.hfact; a.gamma = p.gamma; a.out = dout;
+    for (int k = 0; k < SPHGPU_MAXTYPES; k++) a.massoftype[k] = p.massoftype[k];
+    SL(c, k_energies, a);
+    double h[E_COUNT];
+    CUDA_TRY(c, cudaMemcpyAsync(h, dout, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    memset(out, 0, sizeof *out);
+    out->ekin = 0.5 * h[E_KIN]; out->etherm = h[E_THERM]; out->emag = 0.5 * h[E_MAG]; out->epot = h[E_POT];        // energies.f90:676-691
+    out->etot = out->ekin + out->etherm + out->emag + out->epot;
+    out->xmom = h[E_XMOM]; out->ymom = h[E_YMOM]; out->zmom = h[E_ZMOM];
+    out->totmom = sqrt(h[E_XMOM] * h[E_XMOM] + h[E_YMOM] * h[E_YMOM] + h[E_ZMOM] * h[E_ZMOM]);
+    out->angx = h[E_ANGX]; out->angy = h[E_ANGY]; out->angz = h[E_ANGZ];
+    out->angtot = sqrt(h[E_ANGX] * h[E_ANGX] + h[E_ANGY] * h[E_ANGY] + h[E_ANGZ] * h[E_ANGZ]);
+    out->mtot = h[E_MTOT];
+    const double dm = h[E_MTOT] > 0. ? 1. / h[E_MTOT] : 0.;
+    out->xcom = h[E_XCOM] * dm; out->ycom = h[E_YCOM] * dm; out->zcom = h[E_ZCOM] * dm;
+    out->np = (int64_t)h[E_NP]; out->rhomax = h[E_RHOMAX];
+    return SPHGPU_OK;
+}
+
+}  // extern "C"

@@ -88,3 +88,15 @@ def default_params(**kw):
         else:
             setattr(p, k, v)
     return p
+
+
+class SphStepOut(C.Structure):
+    """sphgpu_step_out (include/sphgpu.h)"""
+    _fields_ = [("dtcourant", C.c_double), ("dtforce", C.c_double), ("dterr", C.c_double), ("errmax", C.c_double),
+                ("its", C.c_int64), ("scalars", SphScalars)]
+
+
+class SphEnergies(C.Structure):
+    """sphgpu_energies (include/sphgpu.h): energies.f90 module variables ekin, etherm, emag, epot, etot, totmom, angtot, mtot, xyzcom"""
+    _fields_ = [(k, C.c_double) for k in ("ekin", "etherm", "emag", "epot", "etot", "totmom", "xmom", "ymom", "zmom", "angtot",
+                                          "angx", "angy", "angz", "mtot", "xcom", "ycom", "zcom", "rhomax")] + [("np", C.c_int64)]
