@@ -84,12 +84,12 @@ __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const 
     s_done[s] = 0;
     if (frec) {                                                  // packed j-records of the all-gas fast path
         const double4 x = pos4[s];
-        const int fstride = p.mhd ? 5 : (dp.nvu >= 4 ? 4 : 3);
+        const int fstride = p.mhd ? 5 : ((dp.nvu >= 4 || p.gravity) ? 4 : 3);
         double4 *r = frec + fstride * (size_t)s;
         r[0] = make_double4(x.x, x.y, x.z, h1);
         r[1] = make_double4(v[0], v[1], v[2], gradhfac);
         r[2] = make_double4(pro2, vwave, alpha * vwave, rho1);
-        if (fstride >= 4) r[3] = make_double4(pr, dp.nvu >= 4 ? v[3] : 0., cs, alpha);
+        if (fstride >= 4) r[3] = make_double4(pr, dp.nvu >= 4 ? v[3] : 0., p.gravity ? (double)gradh[(size_t)dp.ngradh * i + 1] : cs, alpha);
         if (fstride >= 5) r[4] = E;
     }
     if (p.gravity) gsoft[s] = (double)gradh[(size_t)dp.ngradh * i + 1];
@@ -298,14 +298,14 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
 // passes ~1% false candidates, so the warp stays converged), one packed 96/128/160-byte record per neighbour instead of five
 // gathers, the minimum-image wrap is skipped for target groups whose search region lies inside the box, and the j-side terms that
 // vanish with grad W_j (q2j >= R^2) are not masked separately.
-template <int K, bool PERIODIC, bool MHD, bool ADIA>
+template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV>
 #ifndef FORCE_MINB
 #define FORCE_MINB 5
 #endif
 #ifndef FORCE_NPAIR
 #define FORCE_NPAIR 2
 #endif
-__global__ void __launch_bounds__(128, MHD ? 3 : FORCE_MINB) k_force_fast(const ForceArgs a, const __grid_constant__ DevParams dp)
+__global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : FORCE_MINB) k_force_fast(const ForceArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
     __shared__ WarpShared wsh[4];
@@ -322,8 +322,8 @@ __global__ void __launch_bounds__(128, MHD ? 3 : FORCE_MINB) k_force_fast(const 
     const float hmax_global = (a.ncells > 1) ? fmaxf(a.nodes[0].hmax[0], a.nodes[0].hmax[1]) : 0.f;
     const double pmass = p.massoftype[IGAS];
     const double beta = p.beta;
-    constexpr bool USEJ = MHD || ADIA;                               // force.F90:1343-1345 without gravity and dust
-    constexpr int FSTRIDE = MHD ? 5 : (ADIA ? 4 : 3);               // double4 per packed record
+    constexpr bool USEJ = MHD || (ADIA && !GRAV);                    // force.F90:1343-1345 without dust
+    constexpr int FSTRIDE = MHD ? 5 : ((ADIA || GRAV) ? 4 : 3);     // double4 per packed record
 
     while (true) {
         int cellid = 0;
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(128, MHD ? 3 : FORCE_MINB) k_force_fast(const 
         const double4 *ri = a.frec + FSTRIDE * (size_t)s;
         const double4 T0 = ri[0], T1 = ri[1], T2 = ri[2];
         double4 T3 = make_double4(0., 0., 0., 0.), T4 = T3;
-        if (ADIA || MHD) T3 = ri[3];
+        if (ADIA || MHD || GRAV) T3 = ri[3];
         if (MHD) T4 = ri[4];
         const double xi = T0.x, yi = T0.y, zi = T0.z, hi1 = T0.w, hi21 = hi1 * hi1;
         const double h = a.pos4[s].w;
@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(128, MHD ? 3 : FORCE_MINB) k_force_fast(const 
         if (act) lim = wide ? 3.0e38f : prefilter_limit(__double2float_ru(KF::radkern * h), slack);    // force.F90:2255: inactive targets skipped
         ws.tgt[lane] = make_float4((float)(xi - cx), (float)(yi - cy), (float)(zi - cz), lim);
         __syncwarp();
+        double fpot = 0.;
         double fx = 0., fy = 0., fz = 0., drhodt = 0., dudtdiss = 0., dendtdiss = 0., divBsym = 0., dBx = 0., dBy = 0., dBz = 0., divBdiff = 0.;
         double vsigmax = 0.;
         int npair = 0;
@@ -401,6 +402,15 @@ __global__ void __launch_bounds__(128, MHD ? 3 : FORCE_MINB) k_force_fast(const 
                 const double grkerni = ini ? KF::grkern(q2i, rij * hi1) * gi : 0.;      // :1301-1302
                 const double grkernj = inj ? KF::grkern(q2j, rij * hj1) * R1.w : 0.;    // :1325-1327
                 const double runix = dx * rij1, runiy = dy * rij1, runiz = dz * rij1;
+                double fgrav = 0.;
+                if (GRAV) {                                            // softened gravity of SPH-neighbour pairs, force.F90:1303-1339, :1522
+                    const double4 G3 = rj[3];
+                    double phii = -rij1, fgravi = rij1 * rij1, fgravj = fgravi;
+                    if (ini) { double fmi; KF::softening(q2i, rij * hi1, phii, fmi); phii *= hi1; fgravi = fmi * hi21 + T3.z * grkerni; }
+                    if (inj) { double phij, fmj; KF::softening(q2j, rij * hj1, phij, fmj); fgravj = fmj * (hj1 * hj1) + G3.z * grkernj; }
+                    fgrav = isn ? 0.5 * pmass * (fgravi + fgravj) : 0.;
+                    fpot += isn ? pmass * phii : 0.;
+                }
                 const double dvx = T1.x - R1.x, dvy = T1.y - R1.y, dvz = T1.z - R1.z;
                 const double projv = dvx * runix + dvy * runiy + dvz * runiz;
                 const double bp = beta * projv;
@@ -418,7 +428,7 @@ __global__ void __launch_bounds__(128, MHD ? 3 : FORCE_MINB) k_force_fast(const 
                 if (ADIA) {                                            // artificial conductivity, force.F90:1606-1624
                     const double4 R3 = rj[3];
                     const double denij = T3.y - R3.y;
-                    const double vsigu = sqrt(fabs(pri - R3.x) * (2. * rho1i * rho1j / (rho1i + rho1j)));
+                    const double vsigu = GRAV ? fabs(projv) : sqrt(fabs(pri - R3.x) * (2. * rho1i * rho1j / (rho1i + rho1j)));
                     const double auterm = 0.5 * pmass * rho1i * p.alphau, autermj = 0.5 * pmass * rho1j * p.alphau;
                     dendtdiss += vsigu * denij * (auterm * grkerni + autermj * grkernj);
                     dudtdiss += pmass * qrho2i * projv * grkerni;
@@ -447,9 +457,9 @@ __global__ void __launch_bounds__(128, MHD ? 3 : FORCE_MINB) k_force_fast(const 
                     const double si = -pmass * rho21i * projBi * grkerni, sj = -pmass * rho21j * projBj * grkernj;   // Maxwell stress, :1677-1684
                     projsx = si * Bxi + sj * E.x; projsy = si * Byi + sj * E.y; projsz = si * Bzi + sj * E.z;
                 }
-                fx += -runix * gradp - projsx;
-                fy += -runiy * gradp - projsy;
-                fz += -runiz * gradp - projsz;
+                fx += -runix * (gradp + fgrav) - projsx;
+                fy += -runiy * (gradp + fgrav) - projsy;
+                fz += -runiz * (gradp + fgrav) - projsz;
                 drhodt += projv * grkerni;
             };
             while (true) {
@@ -481,6 +491,13 @@ __global__ void __launch_bounds__(128, MHD ? 3 : FORCE_MINB) k_force_fast(const 
             double4 dB = make_double4(0., 0., 0., 0.);
             float divBsymm4 = 0.f;
             const double rhoi = 1. / rho1i;
+            if (GRAV) {                                              // force.F90:2909-2927: far field (L2P + distant P2P) from gravity.cu
+                const double4 g = a.gacc[a.perm[s]];
+                double potensoft0, dum;
+                KF::softening(0., 0., potensoft0, dum);
+                fx += g.x; fy += g.y; fz += g.z;
+                a.s_poten[s] = (float)(0.5 * pmass * (fpot + pmass * potensoft0 * hi1) + 0.5 * pmass * g.w);
+            }
             if (MHD) {                                               // force.F90:2939-2965
                 const double B2i = T4.x * T4.x + T4.y * T4.y + T4.z * T4.z;
                 double frac_divB = 0.;
@@ -761,15 +778,15 @@ int launch_force_general(sphgpu_ctx *c, const ForceArgs &a, int grid)
     c->launches++;
     return 0;
 }
-template <int K, bool PERIODIC, bool MHD, bool ADIA>
+template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV>
 int launch_force_fast(sphgpu_ctx *c, const ForceArgs &a, int grid)
 {
     if (grid < 0) {
         int bps = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force_fast<K, PERIODIC, MHD, ADIA>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force_fast<K, PERIODIC, MHD, ADIA, GRAV>, 128, 0);
         return bps < 1 ? 1 : bps;
     }
-    k_force_fast<K, PERIODIC, MHD, ADIA><<<grid, 128, 0, c->stream>>>(a, c->hp);
+    k_force_fast<K, PERIODIC, MHD, ADIA, GRAV><<<grid, 128, 0, c->stream>>>(a, c->hp);
     c->launches++;
     return 0;
 }
@@ -778,7 +795,7 @@ int launch_force_fast(sphgpu_ctx *c, const ForceArgs &a, int grid)
 bool force_is_general(const sphgpu_ctx *c)
 {
     const sphgpu_params &p = c->hp.p;
-    return p.gravity || p.dust || p.ind_timesteps || p.disc_viscosity || c->multitype || c->force_general;
+    return p.dust || p.ind_timesteps || p.disc_viscosity || c->multitype || c->force_general;
 }
 
 template <int K, bool PERIODIC>
@@ -787,8 +804,13 @@ int dispatch_force2(sphgpu_ctx *c, const ForceArgs &a, int grid)
     const sphgpu_params &p = c->hp.p;
     if (force_is_general(c)) return p.mhd ? launch_force_general<K, PERIODIC, true>(c, a, grid) : launch_force_general<K, PERIODIC, false>(c, a, grid);
     const bool adia = c->hp.nvu >= 4;
-    if (p.mhd) return adia ? launch_force_fast<K, PERIODIC, true, true>(c, a, grid) : launch_force_fast<K, PERIODIC, true, false>(c, a, grid);
-    return adia ? launch_force_fast<K, PERIODIC, false, true>(c, a, grid) : launch_force_fast<K, PERIODIC, false, false>(c, a, grid);
+    if (p.gravity) {       // self-gravity is not periodic (gravity_run rejects it): PERIODIC instantiations are not needed
+        if (PERIODIC) return launch_force_general<K, PERIODIC, false>(c, a, grid);
+        if (p.mhd) return adia ? launch_force_fast<K, false, true, true, true>(c, a, grid) : launch_force_fast<K, false, true, false, true>(c, a, grid);
+        return adia ? launch_force_fast<K, false, false, true, true>(c, a, grid) : launch_force_fast<K, false, false, false, true>(c, a, grid);
+    }
+    if (p.mhd) return adia ? launch_force_fast<K, PERIODIC, true, true, false>(c, a, grid) : launch_force_fast<K, PERIODIC, true, false, false>(c, a, grid);
+    return adia ? launch_force_fast<K, PERIODIC, false, true, false>(c, a, grid) : launch_force_fast<K, PERIODIC, false, false, false>(c, a, grid);
 }
 
 int dispatch_force(sphgpu_ctx *c, const ForceArgs &a, int grid)

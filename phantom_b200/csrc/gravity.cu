@@ -112,24 +112,52 @@ __global__ void k_g_node_reset(int n0, int n1, GBuild *__restrict__ gb)
     gb[d] = b;
 }
 
+// block-level combine for the upper levels, where a whole 256-thread block lies inside one node: one atomic per block and value
+// instead of one per warp (the root alone would otherwise serialise N/32 atomics on a single address)
+template <int NV>
+__device__ __forceinline__ bool block_uniform_sum(int key, bool head, double (&v)[NV], double (*sh)[NV], int *shkey)
+{
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    const bool wuni = __all_sync(FULLMASK, key == __shfl_sync(FULLMASK, key, 0)) && key >= 0;
+    if (lane == 0) shkey[w] = wuni ? key : -2 - w;
+    __syncthreads();
+    bool buni = true;
+    for (int k = 1; k < (int)(blockDim.x >> 5); k++) buni = buni && (shkey[k] == shkey[0]);
+    buni = buni && shkey[0] >= 0;
+    if (buni) {
+        if (head) for (int k = 0; k < NV; k++) sh[w][k] = v[k];
+        __syncthreads();
+        if (threadIdx.x == 0) for (int k = 0; k < NV; k++) { double t = sh[0][k]; for (int q = 1; q < (int)(blockDim.x >> 5); q++) t += sh[q][k]; v[k] = t; }
+    }
+    return buni;
+}
+
 // pass 1: mass, mass-weighted position, bounding box per node of the current level (kdtree.F90:654-666, :867-900)
-__global__ void k_g_sums(int nlive, const int *__restrict__ pnode, const double4 *__restrict__ pos, const double *__restrict__ mass, double dfac,
+__global__ void __launch_bounds__(256) k_g_sums(int nlive, const int *__restrict__ pnode, const double4 *__restrict__ pos, const double *__restrict__ mass, double dfac,
                          GBuild *__restrict__ gb)
 {
+    __shared__ double sh[8][4]; __shared__ double shm[8][6]; __shared__ int shkey[8];
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     int key = -1; double4 x = make_double4(0., 0., 0., 0.); double m = 0.;
     if (s < nlive) { key = pnode[s]; if (key >= 0) { x = pos[s]; m = mass[s]; } }
-    if (__all_sync(FULLMASK, key < 0)) return;
     int last; const bool head = seg_bounds(key, last);
     const double fac = m * dfac;
-    const double sm = seg_sum(m, last), sx = seg_sum(fac * x.x, last), sy = seg_sum(fac * x.y, last), sz = seg_sum(fac * x.z, last);
-    const double lx = seg_min(x.x, last), ly = seg_min(x.y, last), lz = seg_min(x.z, last);
-    const double hx = seg_max(x.x, last), hy = seg_max(x.y, last), hz = seg_max(x.z, last);
-    if (head && key >= 0) {
+    double v[4] = {seg_sum(m, last), seg_sum(fac * x.x, last), seg_sum(fac * x.y, last), seg_sum(fac * x.z, last)};
+    double lo[3] = {seg_min(x.x, last), seg_min(x.y, last), seg_min(x.z, last)}, hi[3] = {seg_max(x.x, last), seg_max(x.y, last), seg_max(x.z, last)};
+    const bool buni = block_uniform_sum<4>(key, head, v, sh, shkey);
+    if (buni) {                                   // min/max of the block through the same shared staging
+        const int w = threadIdx.x >> 5;
+        if (head) for (int k = 0; k < 3; k++) { shm[w][k] = lo[k]; shm[w][3 + k] = hi[k]; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int q = 1; q < 8; q++) for (int k = 0; k < 3; k++) { lo[k] = fmin(lo[k], shm[q][k]); hi[k] = fmax(hi[k], shm[q][3 + k]); }
+        }
+    }
+    if ((buni && threadIdx.x == 0) || (!buni && head && key >= 0)) {
         GBuild *b = &gb[key];
-        atomicAdd(&b->sm, sm); atomicAdd(&b->sx, sx); atomicAdd(&b->sy, sy); atomicAdd(&b->sz, sz);
-        atomicMin(&b->lo[0], enc_ord(lx)); atomicMin(&b->lo[1], enc_ord(ly)); atomicMin(&b->lo[2], enc_ord(lz));
-        atomicMax(&b->hi[0], enc_ord(hx)); atomicMax(&b->hi[1], enc_ord(hy)); atomicMax(&b->hi[2], enc_ord(hz));
+        atomicAdd(&b->sm, v[0]); atomicAdd(&b->sx, v[1]); atomicAdd(&b->sy, v[2]); atomicAdd(&b->sz, v[3]);
+        atomicMin(&b->lo[0], enc_ord(lo[0])); atomicMin(&b->lo[1], enc_ord(lo[1])); atomicMin(&b->lo[2], enc_ord(lo[2]));
+        atomicMax(&b->hi[0], enc_ord(hi[0])); atomicMax(&b->hi[1], enc_ord(hi[1])); atomicMax(&b->hi[2], enc_ord(hi[2]));
     }
 }
 
@@ -152,13 +180,13 @@ __global__ void k_g_nodes_a(int n0, int n1, GNode *__restrict__ nodes, GBuild *_
 }
 
 // pass 2: size^2 = max |x - xcen|^2, quadrupole moments (kdtree.F90:734-752) and the left/right flag of sort_particles_in_cell (:937-1001)
-__global__ void k_g_moments(int nlive, const int *__restrict__ pnode, const double4 *__restrict__ pos, const double *__restrict__ mass,
+__global__ void __launch_bounds__(256) k_g_moments(int nlive, const int *__restrict__ pnode, const double4 *__restrict__ pos, const double *__restrict__ mass,
                             const GNode *__restrict__ nodes, GBuild *__restrict__ gb, int *__restrict__ flag)
 {
+    __shared__ double sh[8][7]; __shared__ int shkey[8];
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     int key = -1; double4 x = make_double4(0., 0., 0., 0.); double m = 0.;
     if (s < nlive) { key = pnode[s]; if (key >= 0) { x = pos[s]; m = mass[s]; } }
-    if (__all_sync(FULLMASK, key < 0)) { if (s < nlive) flag[s] = 0; return; }
     double dx = 0., dy = 0., dz = 0.; int fl = 0;
     if (key >= 0) {
         const GNode &nd = nodes[key];
@@ -169,14 +197,22 @@ __global__ void k_g_moments(int nlive, const int *__restrict__ pnode, const doub
     if (s < nlive) flag[s] = fl;
     int last; const bool head = seg_bounds(key, last);
     const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    const double r2m = seg_max(r2, last);
-    const double qxx = seg_sum(m * (dx * dx), last), qxy = seg_sum(m * (dx * dy), last), qxz = seg_sum(m * (dx * dz), last);
-    const double qyy = seg_sum(m * (dy * dy), last), qyz = seg_sum(m * (dy * dz), last), qzz = seg_sum(m * (dz * dz), last);
-    if (head && key >= 0) {
+    double r2m = seg_max(r2, last);
+    double v[7] = {seg_sum(m * (dx * dx), last), seg_sum(m * (dx * dy), last), seg_sum(m * (dx * dz), last), seg_sum(m * (dy * dy), last),
+                   seg_sum(m * (dy * dz), last), seg_sum(m * (dz * dz), last), 0.};
+    const bool buni = block_uniform_sum<7>(key, head, v, sh, shkey);
+    if (buni) {                                   // block maximum of r2 through slot 6
+        const int w = threadIdx.x >> 5;
+        __syncthreads();
+        if (head) sh[w][6] = r2m;
+        __syncthreads();
+        if (threadIdx.x == 0) for (int q = 1; q < 8; q++) r2m = fmax(r2m, sh[q][6]);
+    }
+    if ((buni && threadIdx.x == 0) || (!buni && head && key >= 0)) {
         GBuild *b = &gb[key];
         atomicMax(&b->r2max, (unsigned long long)__double_as_longlong(r2m));
-        atomicAdd(&b->q[0], qxx); atomicAdd(&b->q[1], qxy); atomicAdd(&b->q[2], qxz);
-        atomicAdd(&b->q[3], qyy); atomicAdd(&b->q[4], qyz); atomicAdd(&b->q[5], qzz);
+        atomicAdd(&b->q[0], v[0]); atomicAdd(&b->q[1], v[1]); atomicAdd(&b->q[2], v[2]);
+        atomicAdd(&b->q[3], v[3]); atomicAdd(&b->q[4], v[4]); atomicAdd(&b->q[5], v[5]);
     }
 }
 
@@ -468,63 +504,90 @@ struct P2PArgs {
     double4 *gacc; unsigned long long *cnt;
 };
 
+#define P2P_BATCH 32                       // source leaves staged per batch
+#define P2P_SLOTS (P2P_BATCH * MINPART)    // source particles per batch (upper bound)
+
+// One warp per leaf.  The source leaves of the P2P list are staged batch by batch into shared memory as a dense particle array
+// (lane = source leaf copies its <= 10 particles), then lane = source PARTICLE: full lanes regardless of the leaves' fill.
+// The <= 10 targets of the leaf live in registers and are broadcast across the lanes; per-target sums are reduced once at the end.
 template <int K>
-__global__ void __launch_bounds__(128) k_g_p2p(const P2PArgs a)
+__global__ void __launch_bounds__(128, 4) k_g_p2p(const P2PArgs a)
 {
     typedef SphKern<K> KF;
-    const int lane = lane_id();
+    extern __shared__ double4 p2p_smem[];
+    __shared__ double4 tgt_smem[4][MINPART];                                             // targets {x, y, z, 1/h^2}: broadcast reads
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    double4 *spos = p2p_smem + (size_t)wib * P2P_SLOTS;                                  // {x, y, z, 1/h^2}
+    double *smass = reinterpret_cast<double *>(p2p_smem + 4 * P2P_SLOTS) + (size_t)wib * P2P_SLOTS;
+    double4 *tg = tgt_smem[wib];
     const int d = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
     if (d >= a.nn) return;
     const GNode nd = a.nodes[d];
     if (nd.left >= 0 || !(nd.flags & 1)) return;             // leaves with an active particle only (force.F90:509)
-    const int nt = nd.count;                                  // <= MINPART targets, broadcast through registers
-    double tx[MINPART], ty[MINPART], tz[MINPART], th21[MINPART];
+    const int nt = nd.count;                                  // <= MINPART targets
     double fx[MINPART], fy[MINPART], fz[MINPART], ph[MINPART];
 #pragma unroll
-    for (int t = 0; t < MINPART; t++) {
-        const double4 p = a.pos[nd.start + min(t, nt - 1)];
-        tx[t] = p.x; ty[t] = p.y; tz[t] = p.z;
+    for (int t = 0; t < MINPART; t++) fx[t] = fy[t] = fz[t] = ph[t] = 0.;
+    if (lane < MINPART) {
+        const double4 p = a.pos[nd.start + min(lane, nt - 1)];
         const double h1 = 1. / fabs(p.w);
-        th21[t] = h1 * h1;                                    // same expression as k_force_prep: the SPH-pair test below must be the one k_force uses
-        fx[t] = fy[t] = fz[t] = ph[t] = 0.;
+        tg[lane] = make_double4(p.x, p.y, p.z, h1 * h1);       // same expression as k_force_prep: the SPH-pair test below must be the one k_force uses
     }
+    __syncwarp();
     const int *lst = a.p2p + a.p2poff[d];
     const int nl = a.p2pcnt[d];
     unsigned long long npairs = 0;
-    for (int base = 0; base < nl; base += 32) {               // lane = source leaf
+    for (int base = 0; base < nl; base += P2P_BATCH) {
+        // ---- stage: lane = source leaf
         int sstart = 0, scount = 0;
         if (base + lane < nl) { const GNode &ns = a.nodes[lst[base + lane]]; sstart = ns.start; scount = ns.count; }
-        const int kmax = __reduce_max_sync(FULLMASK, scount);
-        for (int k = 0; k < kmax; k++) {
-            if (k < scount) {
-                const int js = sstart + k;
-                const double4 pj = a.pos[js];
-                const double mj = a.mass[js];
-                const double hj1 = 1. / fabs(pj.w);
-                const double hj21 = hj1 * hj1;
+        int off = scount;                                     // inclusive warp scan of the counts
 #pragma unroll
-                for (int t = 0; t < MINPART; t++) {
-                    const double dx = tx[t] - pj.x, dy = ty[t] - pj.y, dz = tz[t] - pj.z;
+        for (int sft = 1; sft < 32; sft <<= 1) { const int o = __shfl_up_sync(FULLMASK, off, sft); if (lane >= sft) off += o; }
+        const int total = __shfl_sync(FULLMASK, off, 31);
+        off -= scount;
+        for (int k = 0; k < scount; k++) {
+            const double4 pj = a.pos[sstart + k];
+            const double hj1 = 1. / fabs(pj.w);
+            spos[off + k] = make_double4(pj.x, pj.y, pj.z, hj1 * hj1);
+            smass[off + k] = a.mass[sstart + k];
+        }
+        // where (if anywhere) this leaf's own particles sit in the batch: source slot selfoff + t is target t itself
+        const bool selfleaf = (sstart == nd.start) && scount > 0;
+        const unsigned selfmask = __ballot_sync(FULLMASK, selfleaf);
+        const int selfoff = selfmask ? __shfl_sync(FULLMASK, off, __ffs(selfmask) - 1) : -(1 << 20);
+        __syncwarp();
+        // ---- pairs: lane = source particle
+        for (int j = lane; j < total; j += 32) {
+            const double4 pj = spos[j];
+            const double mj = smass[j];
+            const int tself = j - selfoff;                    // index of the target this source is (out of range if none)
+#pragma unroll
+            for (int t = 0; t < MINPART; t++) {
+                if (t < nt) {
+                    const double4 ti = tg[t];
+                    const double dx = ti.x - pj.x, dy = ti.y - pj.y, dz = ti.z - pj.z;
                     const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                    const double q2i = __dmul_rn(r2, th21[t]), q2j = __dmul_rn(r2, hj21);
-                    const bool sph = (q2i < KF::radkern2) || (q2j < KF::radkern2);     // force.F90:1287: handled by k_force
-                    const bool self = (js == nd.start + t);
-                    const bool use = !sph && !self && (t < nt);
+                    const double q2i = __dmul_rn(r2, ti.w), q2j = __dmul_rn(r2, pj.w);
+                    const bool sph = (q2i < KF::radkern2) || (q2j < KF::radkern2);       // force.F90:1287: handled by k_force
+                    const bool use = !sph && (t != tself);
                     const double rinv = use ? rsqrt(r2) : 0.;
-                    const double mr3 = mj * rinv * rinv * rinv;                          // force.F90:2020-2043
+                    const double mr3 = mj * rinv * rinv * rinv;                            // force.F90:2020-2043
                     fx[t] -= dx * mr3; fy[t] -= dy * mr3; fz[t] -= dz * mr3;
                     ph[t] -= mj * rinv;
                     npairs += use ? 1 : 0;
                 }
             }
         }
+        __syncwarp();
     }
 #pragma unroll
     for (int t = 0; t < MINPART; t++) { fx[t] = warp_sum(fx[t]); fy[t] = warp_sum(fy[t]); fz[t] = warp_sum(fz[t]); ph[t] = warp_sum(ph[t]); }
     // L2P at every particle of the leaf (force.F90:2909-2927), lane = target
     double ox = 0., oy = 0., oz = 0., op = 0., px = 0., py = 0., pz = 0.;
 #pragma unroll
-    for (int t = 0; t < MINPART; t++) if (lane == t) { ox = fx[t]; oy = fy[t]; oz = fz[t]; op = ph[t]; px = tx[t]; py = ty[t]; pz = tz[t]; }
+    for (int t = 0; t < MINPART; t++) if (lane == t) { ox = fx[t]; oy = fy[t]; oz = fz[t]; op = ph[t]; }
+    if (lane < nt) { const double4 ti = tg[lane]; px = ti.x; py = ti.y; pz = ti.z; }
     if (lane < nt) {
         double gx, gy, gz, gp;
         l2p(a.fnode + (size_t)LENF * d, px - nd.xcen[0], py - nd.xcen[1], pz - nd.xcen[2], gx, gy, gz, gp);
@@ -678,8 +741,15 @@ int gravity_run(sphgpu_ctx *c)
     a.nodes = g.nodes.p; a.nn = nn; a.p2p = g.p2p.p; a.p2poff = g.p2poff.p; a.p2pcnt = g.p2pcnt.p; a.pos = g.pos[cur].p; a.mass = g.mass[cur].p;
     a.gid = g.gid[cur].p; a.fnode = g.fnode.p; a.gacc = c->gacc.p; a.cnt = c->counters.p;
     cudaEventRecord(c->ev[13], st);
-    if (p.kernel == 0) GL(c, k_g_p2p<0>, nblk((int64_t)nn * 32, 128), 128, a);
-    else GL(c, k_g_p2p<1>, nblk((int64_t)nn * 32, 128), 128, a);
+    const size_t p2psmem = (size_t)4 * P2P_SLOTS * (sizeof(double4) + sizeof(double));
+    if (p.kernel == 0) {
+        CUDA_TRY(c, cudaFuncSetAttribute(k_g_p2p<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2psmem));
+        k_g_p2p<0><<<nblk((int64_t)nn * 32, 128), 128, p2psmem, st>>>(a);
+    } else {
+        CUDA_TRY(c, cudaFuncSetAttribute(k_g_p2p<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2psmem));
+        k_g_p2p<1><<<nblk((int64_t)nn * 32, 128), 128, p2psmem, st>>>(a);
+    }
+    c->launches++;
     cudaEventRecord(c->ev[14], st);
     unsigned long long hg[2];
     CUDA_TRY(c, cudaMemcpyAsync(hg, c->counters.p + CNT_NGRAVPAIRS, sizeof hg, cudaMemcpyDeviceToHost, st));
