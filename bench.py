@@ -282,11 +282,20 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
+    # (profiles/ncu_traffic.json, written by tools/make_profile_summaries.py); null when no capture covers this workload
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if tr.get("workload_particles") == n:
+            traffic = tr["kernels"].get("k_density" if dom == "density" else "k_force")
+    except Exception:
+        pass
     roofline = {
         "bound": "fp64", "kernel": "k_density" if dom == "density" else "k_force",
         "achieved": passes[dom]["achieved_tflops"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": passes[dom]["frac_fp64"],
         "peak_source": "DFMA microbenchmark measured live on this device (MEASURED_PEAKS.json has no FP64 figure)",
-        "traffic": None,
+        "traffic": traffic,
         "hbm_view": {"algorithmic_bytes_per_step": bytes_step, "achieved_gbs": bytes_step / (t_dev_max / args.steps) / 1e9, "peak_gbs": hbm_peak,
                      "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback", "frac": bytes_step / (t_dev_max / args.steps) / 1e9 / hbm_peak,
                      "copy_bw_live_gbs": copy_bw},

@@ -168,3 +168,82 @@ def test_ran2_matches_vectorised_generator():
     b = setups.Ran2(-43587).draw(1000)
     assert np.array_equal(a, b)
     assert 0.0 < a.min() and a.max() < 1.0
+
+
+# ---------------------------------------------------------------------------------------------
+#  self-gravity: the reference's own known answers (src/tests/test_gravity.f90)
+# ---------------------------------------------------------------------------------------------
+def _m2l_l2p(dx, dr, totmass, quads, xeval):
+    import ctypes as C
+    from oraclelib import lib
+    L = lib()
+    fnode = np.zeros(20)
+    q = np.ascontiguousarray(quads, dtype=np.float64)
+    L.oracle_compute_M2L(C.c_double(dx[0]), C.c_double(dx[1]), C.c_double(dx[2]), C.c_double(dr), C.c_double(totmass),
+                         q.ctypes.data_as(C.c_void_p), fnode.ctypes.data_as(C.c_void_p))
+    out = np.zeros(4)
+    L.oracle_expand_fgrav(fnode.ctypes.data_as(C.c_void_p), C.c_double(xeval[0]), C.c_double(xeval[1]), C.c_double(xeval[2]),
+                          out.ctypes.data_as(C.c_void_p))
+    return out[:3], out[3]
+
+
+def _checkval(x, ref, tol):
+    # testutils.f90 checkvalconst: relative error when the reference is non-zero
+    err = abs(x - ref)
+    if abs(ref) > 1e-300:
+        err /= abs(ref)
+    assert err <= tol, (x, ref, err, tol)
+
+
+def test_gravity_taylor_series_hand_cases():
+    """test_taylorseries (test_gravity.f90:97-220): compute_M2L + expand_fgrav_in_taylor_series against exact point-mass sums,
+    with the reference's own tolerances"""
+    totmass = 5.
+    xposi, xposj, x0 = np.array([0.05, -0.04, -0.05]), np.array([1., 1., 1.]), np.zeros(3)
+    dx = xposi - xposj; dr = 1. / np.linalg.norm(dx)
+    fexact, phiexact = -totmass * dr ** 3 * dx, -totmass * dr
+    dx = x0 - xposj; dr = 1. / np.linalg.norm(dx)
+    f0, phi = _m2l_l2p(dx, dr, totmass, np.zeros(6), xposi - x0)
+    for k, tol in enumerate((3.e-4, 1.1e-4, 9.e-5)):
+        _checkval(f0[k], fexact[k], tol)
+    _checkval(phi, phiexact, 8.e-4)
+    # expansion about a distant node of three particles, with quadrupole moments
+    xd = np.array([[1.03, 0.98, 1.01], [0.95, 1.01, 1.03], [0.99, 0.95, 0.95]])
+    pm = totmass / 3.
+    xj = np.sum(pm * xd, axis=0) / totmass
+    d = xd - xj
+    quads = np.array([np.sum(pm * d[:, 0] * d[:, 0]), np.sum(pm * d[:, 0] * d[:, 1]), np.sum(pm * d[:, 0] * d[:, 2]),
+                      np.sum(pm * d[:, 1] * d[:, 1]), np.sum(pm * d[:, 1] * d[:, 2]), np.sum(pm * d[:, 2] * d[:, 2])])
+
+    def exact(xe):
+        dd = xe - xd
+        r1 = 1. / np.linalg.norm(dd, axis=1)
+        return -pm * np.sum(r1[:, None] ** 3 * dd, axis=0), -pm * np.sum(r1)
+
+    for xe, tols in ((np.zeros(3), (8.7e-5, 1.5e-6, 1.6e-5, 5.9e-6)), (np.array([0.05, 0.05, -0.05]), (1.3e-4, 1.4e-4, 3.2e-4, 9.7e-4))):
+        fexact, phiexact = exact(xe)
+        dx = x0 - xj; dr = 1. / np.linalg.norm(dx)
+        f0, phi = _m2l_l2p(dx, dr, totmass, quads, xe - x0)
+        for k in range(3):
+            _checkval(f0[k], fexact[k], tols[k])
+        _checkval(phi, phiexact, tols[3])
+
+
+def test_gravity_tree_force_against_direct_sum():
+    """test_directsum (test_gravity.f90:300-400): tree (FMM) force on the uniform random sphere against the direct sum; the direct sum
+    is the same code with tree_accuracy = 0, which accepts no node pair.  Force tolerances are the reference's; potential = -3/5 GMM/R."""
+    part = setups.setup_random_sphere(n=4000)
+    part.params.alpha = 0.
+    pt, pd = part.copy(), part.copy()
+    pd.params.tree_accuracy = 0.0
+    Oracle(pt.params).derivs(pt)
+    Oracle(pd.params).derivs(pd)
+    scale = np.max(np.abs(pd.fxyzu[:, :3]))
+    for k, tol in enumerate((7.2e-3, 6.e-3, 9.4e-3)):
+        assert np.max(np.abs(pt.fxyzu[:, k] - pd.fxyzu[:, k])) / scale < tol
+    m = part.params.massoftype[1]
+    fsum = m * np.sum(pd.fxyzu[:, :3], axis=0)
+    assert np.max(np.abs(fsum)) < 1e-15                                   # direct sum conserves momentum to round-off (:390-392)
+    epot, phitot = float(np.sum(pt.poten.astype(np.float64))), float(np.sum(pd.poten.astype(np.float64)))
+    assert abs(epot - phitot) / abs(phitot) < 1.e-3
+    assert abs(epot + 0.6) / 0.6 < 3.6e-2
