@@ -197,6 +197,10 @@ int sphgpu_set_timestep_bins(sphgpu_ctx *ctx, int nbinmax, int ibinnow, int iste
  * mpi_derivs.F90:197-522.  Ghost particles are appended after the owned ones as inactive (neighbour-only) particles.
  * The host side moves the packed buffers with NCCL (all-to-all-v) directly between the returned DEVICE pointers. */
 int sphgpu_local_hmax(sphgpu_ctx *ctx, double *hmax);
+/* halo sufficiency (the reference re-exports cells when h grows, mpi_dens.F90 / dens.F90:343-365): largest trial h of the last
+ * density pass; when radkern * (global max of it) exceeds the halo width used, restore the pre-density h and repeat with a wider halo */
+int sphgpu_density_hmax_used(sphgpu_ctx *ctx, double *hmax);
+int sphgpu_halo_restore_h(sphgpu_ctx *ctx);
 /* boxes = 6 doubles per rank {lo xyz, hi xyz}; counts[r] = owned particles within dhalo of rank r's box (minimum image) */
 int sphgpu_halo_select(sphgpu_ctx *ctx, int nranks, int myrank, const double *boxes, double dhalo, int64_t *counts);
 /* stage 1 (before build_tree): 16 doubles/ghost; stage 2 (after densityiterate): 4 doubles/ghost {h, gradh, alpha, gradsoft} */
@@ -204,6 +208,14 @@ int sphgpu_halo_pack(sphgpu_ctx *ctx, int stage, void **sendptr_device, int *rec
 int sphgpu_halo_recvbuf(sphgpu_ctx *ctx, int64_t nrecords, int record_doubles, void **recvptr_device);
 int sphgpu_halo_unpack(sphgpu_ctx *ctx, int stage, int64_t nghost);
 int64_t sphgpu_nghost(sphgpu_ctx *ctx);
+/* self-gravity across GPUs (replaces maketreeglobal + the remote cell export for the gravity terms, kdtree.F90:2044-2300, mpi_force.F90):
+ * after the density pass every rank packs 13 doubles per OWNED particle {x,y,z,h, iphase, h at build_tree, iterations, h history(6)},
+ * the ranks all-gather them (NCCL, padded to `stride` records per rank) into the buffer returned by _recvbuf, and _unpack makes the
+ * gathered set the input of the gravity pass of the next force call: every rank builds the same tree of the whole set and evaluates
+ * walk / M2L / P2P only for nodes holding its own particles, so the result equals the single-GPU result to round-off. */
+int sphgpu_gravity_gather_pack(sphgpu_ctx *ctx, void **sendptr_device, int *record_doubles);
+int sphgpu_gravity_gather_recvbuf(sphgpu_ctx *ctx, int nranks, int64_t stride, void **recvptr_device);
+int sphgpu_gravity_gather_unpack(sphgpu_ctx *ctx, int nranks, int myrank, int64_t stride, const int64_t *counts);
 
 /* ---- the callers either side of the path, resident on the device -------------------------------- */
 /* step (src/main/step_leapfrog.f90:95-760) with global timesteps and substep_sph (substepping.F90:241-264):

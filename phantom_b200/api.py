@@ -34,7 +34,8 @@ EXPORTS = [
     "sphgpu_cons2prim_resident", "sphgpu_force_resident", "sphgpu_derivs_resident", "sphgpu_build_tree", "sphgpu_densityiterate",
     "sphgpu_cons2prim_everything", "sphgpu_force", "sphgpu_derivs", "sphgpu_get_neighbour_stats", "sphgpu_neighbour_sets",
     "sphgpu_measure_fp64_peak", "sphgpu_measure_copy_bw", "sphgpu_local_hmax", "sphgpu_halo_select", "sphgpu_halo_pack",
-    "sphgpu_halo_recvbuf", "sphgpu_halo_unpack", "sphgpu_nghost", "sphgpu_set_timestep_bins", "sphgpu_get_gravity_timings", "sphgpu_gravity_tree", "sphgpu_step_resident", "sphgpu_energies_resident",
+    "sphgpu_halo_recvbuf", "sphgpu_halo_unpack", "sphgpu_nghost", "sphgpu_set_timestep_bins", "sphgpu_get_gravity_timings", "sphgpu_gravity_tree", "sphgpu_step_resident", "sphgpu_energies_resident", "sphgpu_gravity_gather_pack", "sphgpu_gravity_gather_recvbuf",
+    "sphgpu_gravity_gather_unpack", "sphgpu_density_hmax_used", "sphgpu_halo_restore_h",
 ]
 
 
@@ -105,6 +106,11 @@ def load_library():
         L.sphgpu_gravity_tree.restype = i64
         L.sphgpu_step_resident.argtypes = [vp, dbl, dbl, C.POINTER(SphStepOut)]
         L.sphgpu_energies_resident.argtypes = [vp, C.POINTER(SphEnergies)]
+        L.sphgpu_density_hmax_used.argtypes = [vp, C.POINTER(dbl)]
+        L.sphgpu_halo_restore_h.argtypes = [vp]
+        L.sphgpu_gravity_gather_pack.argtypes = [vp, C.POINTER(vp), C.POINTER(i32)]
+        L.sphgpu_gravity_gather_recvbuf.argtypes = [vp, i32, i64, C.POINTER(vp)]
+        L.sphgpu_gravity_gather_unpack.argtypes = [vp, i32, i32, i64, vp]
         _lib = L
     return _lib
 
@@ -214,6 +220,7 @@ class SphGpu:
 
     # ---- resident mode ----------------------------------------------------------------------------------
     def upload(self, part, mask=F_ALL):
+        self.npart_uploaded = part.npart        # owned particles of this context (ghosts are appended by the halo exchange)
         h = host_arrays(part)
         self._check(self.L.sphgpu_upload(self.h, C.byref(h), mask))
 
@@ -302,6 +309,14 @@ class SphGpu:
         self._check(self.L.sphgpu_local_hmax(self.h, C.byref(v)))
         return v.value
 
+    def density_hmax_used(self):
+        v = C.c_double()
+        self._check(self.L.sphgpu_density_hmax_used(self.h, C.byref(v)))
+        return v.value
+
+    def halo_restore_h(self):
+        self._check(self.L.sphgpu_halo_restore_h(self.h))
+
     def halo_select(self, nranks, myrank, boxes, dhalo):
         boxes = np.ascontiguousarray(boxes, dtype=np.float64)
         counts = np.zeros(nranks, dtype=np.int64)
@@ -320,6 +335,20 @@ class SphGpu:
 
     def halo_unpack(self, stage, nghost):
         self._check(self.L.sphgpu_halo_unpack(self.h, stage, int(nghost)))
+
+    def gravity_gather_pack(self):
+        ptr, rd = C.c_void_p(), C.c_int32()
+        self._check(self.L.sphgpu_gravity_gather_pack(self.h, C.byref(ptr), C.byref(rd)))
+        return ptr.value, rd.value
+
+    def gravity_gather_recvbuf(self, nranks, stride):
+        ptr = C.c_void_p()
+        self._check(self.L.sphgpu_gravity_gather_recvbuf(self.h, int(nranks), int(stride), C.byref(ptr)))
+        return ptr.value
+
+    def gravity_gather_unpack(self, nranks, myrank, stride, counts):
+        counts = np.ascontiguousarray(counts, dtype=np.int64)
+        self._check(self.L.sphgpu_gravity_gather_unpack(self.h, int(nranks), int(myrank), int(stride), _p(counts)))
 
     def nghost(self):
         return self.L.sphgpu_nghost(self.h)

@@ -101,6 +101,7 @@ struct sphgpu_ctx {
     int grav_p2p_per_particle = 48; // capacity of the leaf P2P lists (source leaves per particle)
     struct GravState *grav = nullptr;
     bool grav_tree_valid = false;
+    double dens_hmax_used = 0.;     // largest trial h any active particle took during the last density pass (halo sufficiency check)
     DevBuf<double> h_build, h_hist; // h at build_tree and after each h-rho iteration (replayed by k_g_hmax_leaf)
     DevBuf<int> h_its;
     // tuning
@@ -252,7 +253,7 @@ __device__ __forceinline__ void atomic_max_pos(double *addr, double v) { atomicM
 enum { CNT_WORK = 0, CNT_ERR, CNT_ERRID, CNT_NPAIRS, CNT_NTRIAL, CNT_NCALC, CNT_NACT, CNT_MAXACT, CNT_MAXTRIAL, CNT_NP, CNT_NWALK, CNT_NLIVE, CNT_NBINMAX, CNT_NCHECKBIN, CNT_MULTITYPE, CNT_NSURV,
        CNT_NGRAVPAIRS = 24, CNT_NM2L = 25, CNT_COUNT = 32 };
 // indices into ctx->dscal (double)
-enum { DS_XMIN = 0, DS_YMIN, DS_ZMIN, DS_XMAX, DS_YMAX, DS_ZMAX, DS_DTCOURANT, DS_DTFORCE, DS_DTMINI, DS_DTMAXI, DS_RHOMAX, DS_COUNT = 32 };
+enum { DS_XMIN = 0, DS_YMIN, DS_ZMIN, DS_XMAX, DS_YMAX, DS_ZMAX, DS_DTCOURANT, DS_DTFORCE, DS_DTMINI, DS_DTMAXI, DS_RHOMAX, DS_HUSED, DS_COUNT = 32 };
 
 // internal API between translation units
 int tree_build(sphgpu_ctx *c);
@@ -262,6 +263,9 @@ int cons2prim_run(sphgpu_ctx *c);
 int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out);
 int gravity_run(sphgpu_ctx *c);
 void gravity_release(sphgpu_ctx *c);
+int gravity_gather_pack(sphgpu_ctx *c, void **sendptr, int *record_doubles);
+int gravity_gather_recvbuf(sphgpu_ctx *c, int nranks, int64_t stride, void **recvptr);
+int gravity_gather_unpack(sphgpu_ctx *c, int nranks, int myrank, int64_t stride, const int64_t *counts);
 int64_t gravity_tree_dump(sphgpu_ctx *c, int64_t maxnodes, double *rec12, int32_t *irec6, int32_t *ids);
 #define SPHGPU_HHIST 6   // h-rho iterations logged per particle for the node-hmax replay
 int64_t neighbour_sets_run(sphgpu_ctx *c, int symmetric, int64_t *offsets, int32_t *list, int64_t maxlist);

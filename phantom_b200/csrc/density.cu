@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density
     // per-lane statistics (dens.F90:104-106), reduced once at kernel exit
     unsigned long long st_pairs = 0, st_trial = 0, st_ncalc = 0, st_nact = 0, st_np = 0, st_nwalk = 0, st_surv = 0;
     int st_maxact = 0, st_maxtrial = 0;
-    double st_rhomax = 0.;
+    double st_rhomax = 0., st_hused = 0.;
 
     while (true) {
         int cellid = 0;
@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density
         for (int its = 1;; its++) {                                  // local_its (dens.F90:338-373): the cell iterates until every particle converged
             // compute_hmax / redo_neighbours (dens.F90:1275-1289, :343-347)
             const double hneed = warp_max(conv ? 0. : h);
+            st_hused = fmax(st_hused, hneed);
             if (radkern * hneed > rcut_list) {
                 hmax_list = hneed * a.margin * 1.01;
                 rcut_list = radkern * hmax_list;
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density
         atomicAdd(&a.cnt[CNT_NACT], st_nact); atomicAdd(&a.cnt[CNT_NP], st_np); atomicAdd(&a.cnt[CNT_NWALK], st_nwalk);
         atomicAdd(&a.cnt[CNT_NSURV], st_surv);
         atomicMax(&a.cnt[CNT_MAXACT], (unsigned long long)st_maxact); atomicMax(&a.cnt[CNT_MAXTRIAL], (unsigned long long)st_maxtrial);
-        atomic_max_pos(&a.dscal[DS_RHOMAX], st_rhomax);
+        atomic_max_pos(&a.dscal[DS_RHOMAX], st_rhomax); atomic_max_pos(&a.dscal[DS_HUSED], st_hused);
     }
 }
 
@@ -550,7 +551,7 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
                                                         c->acc4.p, c->bev4.p, c->hnew.p, c->s_nneigh.p, fast ? c->drec.p : nullptr);
     c->launches++;
     CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
-    CUDA_TRY(c, cudaMemsetAsync(c->dscal.p + DS_RHOMAX, 0, sizeof(double), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->dscal.p + DS_RHOMAX, 0, 2 * sizeof(double), c->stream));
     a.drec = c->drec.p;
     a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.acc4 = c->acc4.p; a.bev4 = c->bev4.p; a.stype = c->stype.p; a.perm = c->perm.p;
@@ -569,9 +570,10 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
                                                          c->hp.ngradh, c->hp.nalpha, p.mhd, p.dust ? c->s_dustfrac.p : nullptr, c->dustfrac.p);
     c->launches++;
     TRY(tree_refit_hmax(c));          // set_hmaxcell (neigh_kdtree.f90:115-131): the force walk needs the new hmax
-    unsigned long long hc[16]; double hrhomax;
+    unsigned long long hc[16]; double hrhomax, hused;
     CUDA_TRY(c, cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(&hrhomax, c->dscal.p + DS_RHOMAX, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(&hused, c->dscal.p + DS_HUSED, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaGetLastError());
     { float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); c->ms_kernel[0] = ms; }
@@ -583,6 +585,7 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     sphgpu_scalars &sc = c->last_dens;
     memset(&sc, 0, sizeof sc);
     sc.rhomax = hrhomax; sc.np = (int64_t)hc[CNT_NP];
+    c->dens_hmax_used = hused;
     sc.trialmean = sc.np ? (double)hc[CNT_NTRIAL] / (double)hc[CNT_NCALC] : -1.;
     sc.actualmean = sc.np ? (double)hc[CNT_NACT] / (double)sc.np : -1.;
     sc.maxtrial = (int64_t)hc[CNT_MAXTRIAL]; sc.maxactual = (int64_t)hc[CNT_MAXACT]; sc.nrhocalc = (int64_t)hc[CNT_NCALC];

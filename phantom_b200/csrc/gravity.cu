@@ -269,7 +269,7 @@ __global__ void k_g_scatter(int nlive, const int *__restrict__ pnode, const doub
 // ---- node hmax: replay of set_hmaxcell during the density iterations (see header) -------------------------------------------
 __global__ void k_g_hmax_leaf(int nn, GNode *__restrict__ nodes, GBuild *__restrict__ gb, const int *__restrict__ gid, const double *__restrict__ hbuild,
                               const int *__restrict__ hits, const double *__restrict__ hhist, int64_t npart, int hk, const int8_t *__restrict__ iphase,
-                              int ind_ts)
+                              int ind_ts, int64_t own_lo, int64_t own_hi)
 {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= nn) return;
@@ -280,7 +280,9 @@ __global__ void k_g_hmax_leaf(int nn, GNode *__restrict__ nodes, GBuild *__restr
         const int i = gid[s];
         hb = fmax(hb, hbuild[i]);
         nits = max(nits, hits[i]);
-        if (!ind_ts || iphase[i] > 0) act = 1;
+        const bool own = (i >= own_lo && i < own_hi);                            // multi-GPU: this rank evaluates only leaves holding its own particles
+        if (own) act |= 2;
+        if (own && (!ind_ts || iphase[i] > 0)) act |= 1;
     }
     double cellh = hb, hset = hb, hmaxset = hb;
     for (int k = 1; k <= nits - 1; k++) {                                       // iterations after which the cell was not yet converged
@@ -307,6 +309,7 @@ __global__ void k_g_hmax_up(int n0, int n1, GNode *__restrict__ nodes, GBuild *_
     if (nd.left < 0) return;
     const double h = fmax(gb[nd.left].hmaxP, gb[nd.right].hmaxP);
     nd.hmax = h; gb[d].hmaxP = h;
+    nd.flags = (nodes[nd.left].flags | nodes[nd.right].flags) & 2;               // some owned particle below
 }
 
 // ---- FMM pieces ------------------------------------------------------------------------------------------------------------
@@ -399,6 +402,7 @@ __global__ void __launch_bounds__(128) k_g_walk(const WalkArgs a)
     const int d = a.n0 + (blockIdx.x * blockDim.x + threadIdx.x) / 32;
     if (d >= a.n1) return;
     const GNode nd = a.nodes[d];
+    if (!(nd.flags & 2)) { if (lane == 0) { a.outoff[d] = 0; a.outcnt[d] = 0; } return; }     // no particle of this rank below: nobody needs F(d)
     const bool dleaf = nd.left < 0;
     const int *pend; int npend; int rootlist = 0;
     if (nd.parent < 0) { pend = &rootlist; npend = 1; }
@@ -492,7 +496,7 @@ __global__ void k_g_need(int n0, int n1, const GNode *__restrict__ nodes, const 
 {
     const int d = n0 + blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long v = 0;
-    if (d < n1) { const GNode &nd = nodes[d]; v = 2ull * (unsigned long long)outcnt[nd.parent] + (nd.left < 0 ? 256ull : 0ull); }
+    if (d < n1) { const GNode &nd = nodes[d]; if (nd.flags & 2) v = 2ull * (unsigned long long)outcnt[nd.parent] + (nd.left < 0 ? 256ull : 0ull); }
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(FULLMASK, v, s);
     if (lane_id() == 0 && v) atomicAdd(need, v);
@@ -501,7 +505,7 @@ __global__ void k_g_need(int n0, int n1, const GNode *__restrict__ nodes, const 
 // ---- P2P + L2P: one warp per leaf ---------------------------------------------------------------------------------------------
 struct P2PArgs {
     const GNode *nodes; int nn; const int *p2p; const long long *p2poff; const int *p2pcnt; const double4 *pos; const double *mass; const int *gid; const double *fnode;
-    double4 *gacc; unsigned long long *cnt;
+    double4 *gacc; unsigned long long *cnt; int64_t own_lo, own_hi;
 };
 
 #define P2P_BATCH 32                       // source leaves staged per batch
@@ -591,7 +595,8 @@ __global__ void __launch_bounds__(128, 4) k_g_p2p(const P2PArgs a)
     if (lane < nt) {
         double gx, gy, gz, gp;
         l2p(a.fnode + (size_t)LENF * d, px - nd.xcen[0], py - nd.xcen[1], pz - nd.xcen[2], gx, gy, gz, gp);
-        a.gacc[a.gid[nd.start + lane]] = make_double4(ox + gx, oy + gy, oz + gz, op + gp);
+        const int64_t gi = a.gid[nd.start + lane];
+        if (gi >= a.own_lo && gi < a.own_hi) a.gacc[gi - a.own_lo] = make_double4(ox + gx, oy + gy, oz + gz, op + gp);
     }
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) npairs += __shfl_xor_sync(FULLMASK, npairs, s);
@@ -613,11 +618,14 @@ struct GravState {
     DevBuf<char> cubtmp;
     std::vector<int> level_start;              // nodes of level L are [level_start[L], level_start[L+1])
     int nn = 0, cur = 0, nlive = 0;
+    // multi-GPU: the gathered particle set of all ranks (positions, h history) in rank order; this rank owns [own_lo, own_hi)
+    int64_t nglobal = 0, own_lo = 0;
+    DevBuf<double> gsend, grecv, g_xyzh, g_hbuild, g_hhist; DevBuf<int> g_hits; DevBuf<int8_t> g_iphase; DevBuf<long long> g_counts;
     void release()
     {
         nodes.release(); gb.release(); for (int k = 0; k < 2; k++) { pos[k].release(); mass[k].release(); gid[k].release(); pnode[k].release(); lst[k].release(); }
         flag.release(); scan.release(); outoff.release(); outcnt.release(); p2p.release(); p2poff.release(); p2pcnt.release(); fnode.release(); ptrs.release();
-        cubtmp.release();
+        cubtmp.release(); gsend.release(); grecv.release(); g_xyzh.release(); g_hbuild.release(); g_hhist.release(); g_hits.release(); g_iphase.release(); g_counts.release();
     }
 };
 
@@ -627,9 +635,19 @@ void gravity_release(sphgpu_ctx *c)
 }
 
 // level-synchronous construction of the reference-topology tree (positions and masses only: valid until the next build_tree)
-static int grav_build(sphgpu_ctx *c, GravState &g)
+struct GravInput { int64_t n; const double *xyzh; const int8_t *iphase; const double *hbuild; const int *hits; const double *hhist; int64_t own_lo, own_hi; };
+
+static GravInput grav_input(sphgpu_ctx *c, GravState &g)
 {
-    const int64_t n = c->npart;
+    GravInput in;
+    if (g.nglobal > 0) { in.n = g.nglobal; in.xyzh = g.g_xyzh.p; in.iphase = g.g_iphase.p; in.hbuild = g.g_hbuild.p; in.hits = g.g_hits.p; in.hhist = g.g_hhist.p; in.own_lo = g.own_lo; in.own_hi = g.own_lo + c->nlocal; }
+    else { in.n = c->npart; in.xyzh = c->xyzh.p; in.iphase = c->iphase.p; in.hbuild = c->h_build.p; in.hits = c->h_its.p; in.hhist = c->h_hist.p; in.own_lo = 0; in.own_hi = c->npart; }
+    return in;
+}
+
+static int grav_build(sphgpu_ctx *c, GravState &g, const GravInput &in)
+{
+    const int64_t n = in.n;
     const sphgpu_params &p = c->hp.p;
     cudaStream_t st = c->stream;
     CUDA_TRY(c, g.flag.ensure(n)); CUDA_TRY(c, g.scan.ensure(n)); CUDA_TRY(c, g.ptrs.ensure(8));
@@ -637,14 +655,19 @@ static int grav_build(sphgpu_ctx *c, GravState &g)
     cub::DeviceScan::ExclusiveSum(nullptr, tb, g.flag.p, g.scan.p, (int)n, st);
     CUDA_TRY(c, g.cubtmp.ensure(tb + 256));
     // live particles keep the caller's order (construct_root_node)
-    GL(c, k_g_liveflag, nblk(n, 256), 256, n, c->xyzh.p, g.flag.p);
+    GL(c, k_g_liveflag, nblk(n, 256), 256, n, in.xyzh, g.flag.p);
     size_t tbb = g.cubtmp.cap;
     CUDA_TRY(c, cub::DeviceScan::ExclusiveSum(g.cubtmp.p, tbb, g.flag.p, g.scan.p, (int)n, st));
     c->launches++;
-    const int nlive = (int)c->nlive;
+    int lastf = 0, lasts = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&lastf, g.flag.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(&lasts, g.scan.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    const int nlive = lastf + lasts;
+    if (nlive <= 0) { c->err = "gravity tree: no live particles"; return SPHGPU_ERR_NOPART; }
     g.nlive = nlive;
     for (int k = 0; k < 2; k++) { CUDA_TRY(c, g.pos[k].ensure(nlive)); CUDA_TRY(c, g.mass[k].ensure(nlive)); CUDA_TRY(c, g.gid[k].ensure(nlive)); CUDA_TRY(c, g.pnode[k].ensure(nlive)); }
-    GL(c, k_g_init, nblk(n, 256), 256, n, c->xyzh.p, c->iphase.p, c->hp, g.pos[0].p, g.mass[0].p, g.gid[0].p, g.pnode[0].p, g.scan.p);
+    GL(c, k_g_init, nblk(n, 256), 256, n, in.xyzh, in.iphase, c->hp, g.pos[0].p, g.mass[0].p, g.gid[0].p, g.pnode[0].p, g.scan.p);
     const int maxnodes = nlive + 1024;          // leaves hold > 1 particle except in degenerate splits; overflow is reported
     CUDA_TRY(c, g.nodes.ensure(maxnodes)); CUDA_TRY(c, g.gb.ensure(maxnodes));
     // dfac = 1/massoftype(igas), or the first massive type when there is no gas (kdtree.F90:612-624)
@@ -691,16 +714,17 @@ int gravity_run(sphgpu_ctx *c)
     if (!c->grav) c->grav = new GravState();
     GravState &g = *c->grav;
     cudaStream_t st = c->stream;
-    const int64_t n = c->npart;
+    const GravInput in = grav_input(c, g);
+    const int64_t n = in.n;
     cudaEventRecord(c->ev[12], st);
     CUDA_TRY(c, cudaMemsetAsync(c->counters.p + CNT_ERR, 0, 2 * sizeof(unsigned long long), st));
     CUDA_TRY(c, cudaMemsetAsync(c->counters.p + CNT_NGRAVPAIRS, 0, 2 * sizeof(unsigned long long), st));
-    if (!c->grav_tree_valid) { TRY(grav_build(c, g)); c->grav_tree_valid = true; }
+    if (!c->grav_tree_valid) { TRY(grav_build(c, g, in)); c->grav_tree_valid = true; }
     const int nn = g.nn, cur = g.cur, nlive = g.nlive;
     const int nlev = (int)g.level_start.size() - 1;
     // node hmax as the reference's tree holds it at force time
-    GL(c, k_g_hmax_leaf, nblk(nn, 128), 128, nn, g.nodes.p, g.gb.p, g.gid[cur].p, c->h_build.p, c->h_its.p, c->h_hist.p, n, SPHGPU_HHIST, c->iphase.p,
-       p.ind_timesteps);
+    GL(c, k_g_hmax_leaf, nblk(nn, 128), 128, nn, g.nodes.p, g.gb.p, g.gid[cur].p, in.hbuild, in.hits, in.hhist, n, SPHGPU_HHIST, in.iphase,
+       p.ind_timesteps, in.own_lo, in.own_hi);
     for (int L = nlev - 1; L >= 0; L--) {
         const int a0 = g.level_start[L], a1 = g.level_start[L + 1];
         GL(c, k_g_hmax_up, nblk(a1 - a0, 128), 128, a0, a1, g.nodes.p, g.gb.p);
@@ -736,10 +760,10 @@ int gravity_run(sphgpu_ctx *c)
         if (err) { c->err = "gravity: interaction list pool overflow (raise option grav_p2p_per_particle)"; return SPHGPU_ERR_OVERFLOW; }
         need = hp[2] + 512;
     }
-    CUDA_TRY(c, c->gacc.ensure(n));
+    CUDA_TRY(c, c->gacc.ensure(c->npart));
     P2PArgs a;
     a.nodes = g.nodes.p; a.nn = nn; a.p2p = g.p2p.p; a.p2poff = g.p2poff.p; a.p2pcnt = g.p2pcnt.p; a.pos = g.pos[cur].p; a.mass = g.mass[cur].p;
-    a.gid = g.gid[cur].p; a.fnode = g.fnode.p; a.gacc = c->gacc.p; a.cnt = c->counters.p;
+    a.gid = g.gid[cur].p; a.fnode = g.fnode.p; a.gacc = c->gacc.p; a.cnt = c->counters.p; a.own_lo = in.own_lo; a.own_hi = in.own_hi;
     cudaEventRecord(c->ev[13], st);
     const size_t p2psmem = (size_t)4 * P2P_SLOTS * (sizeof(double4) + sizeof(double));
     if (p.kernel == 0) {
@@ -757,6 +781,82 @@ int gravity_run(sphgpu_ctx *c)
     CUDA_TRY(c, cudaGetLastError());
     c->npairs_gravity = (int64_t)hg[0]; c->nm2l = (int64_t)hg[1];
     { float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[12], c->ev[14]); c->ms_gravity[0] = ms; cudaEventElapsedTime(&ms, c->ev[13], c->ev[14]); c->ms_gravity[1] = ms; }
+    return SPHGPU_OK;
+}
+
+// ---- multi-GPU: every rank evaluates the FMM for its own particles on the tree of the WHOLE particle set ---------------------------
+// (replaces the global tree + remote cell export of maketreeglobal / mpi_force for the gravity terms, kdtree.F90:2044-2300).
+// The ranks all-gather 13 doubles per owned particle {x,y,z,h, iphase, h at build_tree, iterations, h history(6)}; each rank then
+// builds the same tree, so the result is the single-GPU result to round-off.  Walk, M2L and P2P are restricted to nodes that hold
+// particles of this rank; only the tree construction is replicated.
+#define GREC (7 + SPHGPU_HHIST)
+
+__global__ void k_gg_pack(int64_t nlocal, int64_t npart, const double *__restrict__ xyzh, const int8_t *__restrict__ iphase, const double *__restrict__ hbuild,
+                          const int *__restrict__ hits, const double *__restrict__ hhist, double *__restrict__ out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    double *o = out + (size_t)GREC * i;
+    for (int k = 0; k < 4; k++) o[k] = xyzh[4 * i + k];
+    o[4] = (double)iphase[i]; o[5] = hbuild[i]; o[6] = (double)hits[i];
+    for (int k = 0; k < SPHGPU_HHIST; k++) o[7 + k] = hhist[(size_t)k * npart + i];
+}
+
+// recv = nranks blocks of `stride` records (padded); counts/offs per rank
+__global__ void k_gg_unpack(int nranks, int64_t stride, int64_t nglobal, const long long *__restrict__ counts, const long long *__restrict__ offs,
+                            const double *__restrict__ in, double *__restrict__ xyzh, int8_t *__restrict__ iphase, double *__restrict__ hbuild,
+                            int *__restrict__ hits, double *__restrict__ hhist)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)nranks * stride) return;
+    const int r = (int)(t / stride); const int64_t k = t - (int64_t)r * stride;
+    if (k >= counts[r]) return;
+    const int64_t gi = offs[r] + k;
+    const double *o = in + (size_t)GREC * t;
+    for (int q = 0; q < 4; q++) xyzh[4 * gi + q] = o[q];
+    iphase[gi] = (int8_t)o[4]; hbuild[gi] = o[5]; hits[gi] = (int)o[6];
+    for (int q = 0; q < SPHGPU_HHIST; q++) hhist[(size_t)q * nglobal + gi] = o[7 + q];
+}
+
+int gravity_gather_pack(sphgpu_ctx *c, void **sendptr, int *record_doubles)
+{
+    if (!c->grav) c->grav = new GravState();
+    GravState &g = *c->grav;
+    const int64_t nl = c->nlocal;
+    CUDA_TRY(c, g.gsend.ensure((size_t)GREC * nl));
+    GL(c, k_gg_pack, nblk(nl, 256), 256, nl, c->npart, c->xyzh.p, c->iphase.p, c->h_build.p, c->h_its.p, c->h_hist.p, g.gsend.p);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *sendptr = g.gsend.p; *record_doubles = GREC;
+    return SPHGPU_OK;
+}
+
+int gravity_gather_recvbuf(sphgpu_ctx *c, int nranks, int64_t stride, void **recvptr)
+{
+    if (!c->grav) c->grav = new GravState();
+    GravState &g = *c->grav;
+    CUDA_TRY(c, g.grecv.ensure((size_t)GREC * nranks * stride));
+    *recvptr = g.grecv.p;
+    return SPHGPU_OK;
+}
+
+int gravity_gather_unpack(sphgpu_ctx *c, int nranks, int myrank, int64_t stride, const int64_t *counts)
+{
+    if (!c->grav) return SPHGPU_ERR_STATE;
+    GravState &g = *c->grav;
+    std::vector<long long> hc(nranks), ho(nranks);
+    long long tot = 0;
+    for (int r = 0; r < nranks; r++) { hc[r] = counts[r]; ho[r] = tot; tot += counts[r]; }
+    if (counts[myrank] != c->nlocal) { c->err = "gravity gather: counts[myrank] differs from the number of owned particles"; return SPHGPU_ERR_ARG; }
+    CUDA_TRY(c, g.g_counts.ensure(2 * nranks));
+    CUDA_TRY(c, cudaMemcpyAsync(g.g_counts.p, hc.data(), sizeof(long long) * nranks, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(g.g_counts.p + nranks, ho.data(), sizeof(long long) * nranks, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, g.g_xyzh.ensure(4 * (size_t)tot)); CUDA_TRY(c, g.g_iphase.ensure(tot)); CUDA_TRY(c, g.g_hbuild.ensure(tot)); CUDA_TRY(c, g.g_hits.ensure(tot));
+    CUDA_TRY(c, g.g_hhist.ensure((size_t)SPHGPU_HHIST * tot));
+    GL(c, k_gg_unpack, nblk((int64_t)nranks * stride, 256), 256, nranks, stride, (int64_t)tot, g.g_counts.p, g.g_counts.p + nranks, g.grecv.p, g.g_xyzh.p,
+       g.g_iphase.p, g.g_hbuild.p, g.g_hits.p, g.g_hhist.p);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    g.nglobal = tot; g.own_lo = ho[myrank];
+    c->grav_tree_valid = false;
     return SPHGPU_OK;
 }
 

@@ -144,6 +144,34 @@ int sphgpu_local_hmax(sphgpu_ctx *c, double *hmax)
     return SPHGPU_OK;
 }
 
+// largest trial smoothing length of the last density pass: if radkern * this exceeds the halo width the ghosts were selected with,
+// some particle iterated without all its neighbours -> the caller restores h and repeats with a wider halo
+int sphgpu_density_hmax_used(sphgpu_ctx *c, double *hmax)
+{
+    if (!c || !hmax) return SPHGPU_ERR_ARG;
+    *hmax = c->dens_hmax_used;
+    return SPHGPU_OK;
+}
+
+__global__ void k_restore_h(int64_t n, double *__restrict__ xyzh, const double *__restrict__ h_build)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) xyzh[4 * i + 3] = h_build[i];
+}
+
+// put back the smoothing lengths the last build_tree saw (owned particles), for a halo-widening retry of the density pass
+int sphgpu_halo_restore_h(sphgpu_ctx *c)
+{
+    if (!c) return SPHGPU_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->h_build.cap < (size_t)c->nlocal) { c->err = "halo_restore_h: no build_tree has run"; return SPHGPU_ERR_STATE; }
+    k_restore_h<<<(unsigned)((c->nlocal + 255) / 256), 256, 0, c->stream>>>(c->nlocal, c->xyzh.p, c->h_build.p);
+    c->launches++;
+    c->tree_valid = false;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SPHGPU_OK;
+}
+
 // boxes: 6 doubles per rank {xlo,ylo,zlo,xhi,yhi,zhi}; counts[nranks] receives the number of owned particles each rank needs
 int sphgpu_halo_select(sphgpu_ctx *c, int nranks, int myrank, const double *boxes, double dhalo, int64_t *counts)
 {

@@ -176,6 +176,24 @@ int sphgpu_get_gravity_timings(sphgpu_ctx *c, double *ms2)
     ms2[0] = c->ms_gravity[0]; ms2[1] = c->ms_gravity[1];
     return SPHGPU_OK;
 }
+int sphgpu_gravity_gather_pack(sphgpu_ctx *c, void **sendptr_device, int *record_doubles)
+{
+    if (!c || !sendptr_device || !record_doubles) return SPHGPU_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return gravity_gather_pack(c, sendptr_device, record_doubles);
+}
+int sphgpu_gravity_gather_recvbuf(sphgpu_ctx *c, int nranks, int64_t stride, void **recvptr_device)
+{
+    if (!c || !recvptr_device) return SPHGPU_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return gravity_gather_recvbuf(c, nranks, stride, recvptr_device);
+}
+int sphgpu_gravity_gather_unpack(sphgpu_ctx *c, int nranks, int myrank, int64_t stride, const int64_t *counts)
+{
+    if (!c || !counts) return SPHGPU_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return gravity_gather_unpack(c, nranks, myrank, stride, counts);
+}
 int64_t sphgpu_gravity_tree(sphgpu_ctx *c, int64_t maxnodes, double *rec12, int32_t *irec6, int32_t *ids)
 {
     if (!c) return -1;

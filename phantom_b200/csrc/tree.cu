@@ -396,8 +396,8 @@ int tree_build(sphgpu_ctx *c)
         LAUNCH(c, k_refit, nblk(M, 128), 128, (int)M, c->cells.p, c->nodes.p, c->nodesf.p, c->nodeflag.p);
     }
     TRY(build_groups(c));
-    if (p.gravity) {
-        CUDA_TRY(c, c->h_build.ensure(n)); CUDA_TRY(c, c->h_its.ensure(n)); CUDA_TRY(c, c->h_hist.ensure((size_t)SPHGPU_HHIST * n));
+    {   // h as the tree was built with: start of the node-hmax history (gravity) and restore point of a halo-widening retry
+        CUDA_TRY(c, c->h_build.ensure(n)); CUDA_TRY(c, c->h_its.ensure(n)); if (p.gravity) CUDA_TRY(c, c->h_hist.ensure((size_t)SPHGPU_HHIST * n));
         LAUNCH(c, k_hbuild, nblk(n, 256), 256, n, c->xyzh.p, c->h_build.p, c->h_its.p);
     }
     c->grav_tree_valid = false;

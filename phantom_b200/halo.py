@@ -79,6 +79,24 @@ def select_ghosts_numpy(xyz, boxes, myrank, dhalo, L, periodic):
             for r in range(len(boxes))]
 
 
+def gather_padded(dist, torch, records):
+    """all-gather of a different number of records per rank through padding to the largest count (numpy restatement of the
+    device path k_gg_pack -> all_gather_into_tensor -> k_gg_unpack); returns (records of all ranks in rank order, counts, own offset)"""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n, w = records.shape
+    cnt = torch.tensor([n], dtype=torch.int64)
+    allc = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allc, cnt)
+    counts = np.array([int(c[0]) for c in allc])
+    stride = int(counts.max())
+    padded = torch.zeros(stride * w, dtype=torch.float64)
+    padded[: n * w] = torch.from_numpy(np.ascontiguousarray(records, dtype=np.float64).reshape(-1))
+    recv = [torch.zeros(stride * w, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(recv, padded)
+    glob = np.concatenate([recv[r].numpy().reshape(stride, w)[: counts[r]] for r in range(world)])
+    return glob, counts, int(counts[:rank].sum())
+
+
 class _DevArray:
     """zero-copy view of a library-owned device buffer for torch (CUDA array interface)"""
 
@@ -100,6 +118,7 @@ class DistributedSph:
         self.radkern = RADKERN[gpu.params.kernel]
         self.halo_bytes = 0
         self.nghost = 0
+        self.nlocal = 0
 
     def _alltoall(self, sendptr, rd, sendcounts, recvcounts, stage):
         torch, dist = self.torch, self.dist
@@ -112,30 +131,64 @@ class DistributedSph:
         self.halo_bytes += 8 * rd * (ntot_s + ntot_r)
         return ntot_r
 
+    def _gather_gravity_set(self):
+        """all-gather of the owned particles' positions and h history: the input of the self-gravity pass (see include/sphgpu.h)"""
+        torch, dist = self.torch, self.dist
+        g = self.g
+        nloc = torch.tensor([self.nlocal], dtype=torch.int64, device="cuda")
+        allc = torch.empty(self.world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(allc, nloc)
+        counts = allc.cpu().numpy()
+        stride = int(counts.max())
+        sendptr, rd = g.gravity_gather_pack()
+        recvptr = g.gravity_gather_recvbuf(self.world, stride)
+        send = torch.as_tensor(_DevArray(sendptr, max(self.nlocal, 1) * rd), device="cuda")[: self.nlocal * rd]
+        recv = torch.as_tensor(_DevArray(recvptr, self.world * stride * rd), device="cuda")
+        padded = torch.zeros(stride * rd, dtype=torch.float64, device="cuda")
+        padded[: self.nlocal * rd] = send
+        dist.all_gather_into_tensor(recv, padded)
+        torch.cuda.synchronize()
+        self.halo_bytes += 8 * rd * stride * self.world
+        g.gravity_gather_unpack(self.world, self.rank, stride, counts)
+
     def derivs(self, icall=1, dt=0.0):
         """tree + density + cons2prim + force with the two ghost exchanges; returns the reduced scalars"""
         torch, dist = self.torch, self.dist
         g = self.g
         self.halo_bytes = 0
+        self.nlocal = int(g.npart_uploaded)
         # halo width from the global hmax (one tiny all_reduce)
         hm = torch.tensor([g.local_hmax()], dtype=torch.float64, device="cuda")
         dist.all_reduce(hm, op=dist.ReduceOp.MAX)
         dhalo = self.radkern * float(hm[0]) * self.margin
-        sendcounts = g.halo_select(self.world, self.rank, self.boxes, dhalo)
-        sc = torch.from_numpy(sendcounts).cuda()
-        rc = torch.empty_like(sc)
-        dist.all_to_all_single(rc, sc)
-        recvcounts = rc.cpu().numpy()
-        ptr, rd = g.halo_pack(1)
-        self.nghost = self._alltoall(ptr, rd, sendcounts, recvcounts, 1)
-        g.halo_unpack(1, self.nghost)
-        g.build_tree_resident()
-        sd = g.densityiterate_resident(1)
+        self.halo_rounds = 0
+        while True:
+            self.halo_rounds += 1
+            sendcounts = g.halo_select(self.world, self.rank, self.boxes, dhalo)
+            sc = torch.from_numpy(sendcounts).cuda()
+            rc = torch.empty_like(sc)
+            dist.all_to_all_single(rc, sc)
+            recvcounts = rc.cpu().numpy()
+            ptr, rd = g.halo_pack(1)
+            self.nghost = self._alltoall(ptr, rd, sendcounts, recvcounts, 1)
+            g.halo_unpack(1, self.nghost)
+            g.build_tree_resident()
+            sd = g.densityiterate_resident(1)
+            # widening round (the reference re-exports a cell whenever its h outgrows the search radius, dens.F90:343-365): if any
+            # particle anywhere iterated with 2h beyond the halo the ghosts were selected with, restore h and repeat with a wider halo
+            hu = torch.tensor([g.density_hmax_used()], dtype=torch.float64, device="cuda")
+            dist.all_reduce(hu, op=dist.ReduceOp.MAX)
+            if self.radkern * float(hu[0]) <= dhalo or self.halo_rounds >= 8:
+                break
+            dhalo = self.radkern * float(hu[0]) * self.margin
+            g.halo_restore_h()
         g.params.set_boundaries_to_active = 0
         ptr, rd = g.halo_pack(2)
         self._alltoall(ptr, rd, sendcounts, recvcounts, 2)
         g.halo_unpack(2, self.nghost)
         g.cons2prim_resident()
+        if g.params.gravity:
+            self._gather_gravity_set()
         sf = g.force_resident(icall, dt)
         red = torch.tensor([sf.dtcourant, sf.dtforce, -sd.rhomax], dtype=torch.float64, device="cuda")
         dist.all_reduce(red, op=dist.ReduceOp.MIN)

@@ -17,6 +17,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def global_problem(nx, mhd=False):
     from phantom_b200 import setups
+    if nx >= 1000:          # self-gravitating sphere of nx particles (C5): exercises the gathered gravity set
+        part = setups.setup_random_sphere(n=nx)
+        rng = setups.Ran2(-97531)
+        part.vxyzu[:, :3] = 0.1 * (rng.draw(3 * part.npart).reshape(-1, 3) - 0.5)
+        part.alphaind[:, 0] = 0.5
+        return part
     part, _ = setups.setup_test_derivs(nx=nx, lattice="random", mhd=mhd)
     rng = setups.Ran2(-24358)
     part.xyzh[:, 3] *= (0.9 + 0.2 * rng.draw(part.npart))
@@ -57,12 +63,19 @@ def main():
         sc = d.derivs(1)
         g.download(loc)
         np.savez(os.path.join(outdir, f"rank{rank}.npz"), idx=mine, xyzh=loc.xyzh, fxyzu=loc.fxyzu, gradh=loc.gradh, divcurlv=loc.divcurlv,
-                 dtcourant=sc.dtcourant, dtforce=sc.dtforce, nghost=d.nghost)
+                 dtcourant=sc.dtcourant, dtforce=sc.dtforce, nghost=d.nghost, poten=loc.poten)
         dist.destroy_process_group()
         return
 
     # ---------------- gloo: host logic with the oracle as the compute stand-in ----------------
     dist.init_process_group("gloo")
+    if p.gravity:
+        # bookkeeping of the gathered gravity set (halo.gather_padded = numpy restatement of k_gg_pack / k_gg_unpack + all-gather)
+        rec = np.concatenate([loc.xyzh, mine[:, None].astype(np.float64)], axis=1)
+        glob, counts, own_lo = halo.gather_padded(dist, torch, rec)
+        np.savez(os.path.join(outdir, f"rank{rank}.npz"), idx=mine, glob=glob, counts=counts, own_lo=own_lo)
+        dist.destroy_process_group()
+        return
     from oraclelib import Oracle
     radkern = halo.RADKERN[p.kernel]
     hm = torch.tensor([loc.xyzh[:, 3].max()], dtype=torch.float64)

@@ -14,3 +14,31 @@ def test_two_gpu_halo_exchange_matches_undivided():
     with tempfile.TemporaryDirectory() as d:
         launch("nccl", 2, 20, d, 29611)
         check_against_undivided(d, 2, 20)
+
+
+def test_two_gpu_selfgravity_matches_undivided():
+    """self-gravity over 2 GPUs (gathered particle set, same tree on every rank) against the oracle on the undivided sphere"""
+    import os
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    from test_halo_gloo import launch
+    from halo_worker import global_problem
+    from oraclelib import Oracle
+    n = 4000
+    with tempfile.TemporaryDirectory() as d:
+        launch("nccl", 2, n, d, 29613)
+        ref = global_problem(n)
+        sd, sf = Oracle(ref.params).derivs(ref)
+        fs = np.sqrt(np.mean(ref.fxyzu[:, :3] ** 2))
+        seen = np.zeros(n, dtype=int)
+        for r in range(2):
+            o = np.load(os.path.join(d, f"rank{r}.npz"))
+            idx = o["idx"]
+            seen[idx] += 1
+            assert np.max(np.abs(o["xyzh"][:, 3] - ref.xyzh[idx, 3]) / ref.xyzh[idx, 3]) < 1e-10
+            assert np.max(np.abs(o["fxyzu"][:, :3] - ref.fxyzu[idx, :3])) < 1e-8 * fs
+            assert np.max(np.abs(o["poten"] - ref.poten[idx])) <= 3e-7 * np.max(np.abs(ref.poten))
+            assert abs(o["dtforce"] - sf.dtforce) < 1e-8 * sf.dtforce
+        assert np.all(seen == 1)

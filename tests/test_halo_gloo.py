@@ -48,6 +48,24 @@ def test_domain_decomposition_host_logic_gloo(world):
         check_against_undivided(d, world, 14)
 
 
+def test_gravity_set_gather_bookkeeping_gloo():
+    # multi-GPU self-gravity: every rank must end up with the owned particles of all ranks in rank order and know its own offset
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from halo_worker import global_problem
+    world, n = 2, 1500
+    with tempfile.TemporaryDirectory() as d:
+        launch("gloo", world, n, d, 29520)
+        ref = global_problem(n)
+        outs = [np.load(os.path.join(d, f"rank{r}.npz")) for r in range(world)]
+        assert np.array_equal(outs[0]["glob"], outs[1]["glob"]) and len(outs[0]["glob"]) == n
+        assert sum(len(o["idx"]) for o in outs) == n
+        for r, o in enumerate(outs):
+            lo = int(o["own_lo"])
+            assert lo == int(np.sum(o["counts"][:r]))
+            own = o["glob"][lo:lo + len(o["idx"])]
+            assert np.array_equal(own[:, 4].astype(np.int64), o["idx"]) and np.array_equal(own[:, :4], ref.xyzh[o["idx"]])
+
+
 def test_orb_boxes_tile_the_box():
     sys.path.insert(0, ROOT)
     from phantom_b200 import halo
