@@ -62,7 +62,8 @@ typedef struct sphgpu_params {
     int32_t ipdv_heating, ishock_heating, iresistive_heating; /* eos.f90:1896-1898 */
     int32_t set_boundaries_to_active;                          /* part.F90:439 */
     int32_t idrag;
-    int32_t reserved_i[5];
+    int32_t driving;         /* -DDRIVING: turbulent stirring (forcing.f90); force() then ADDS to fxyzu (force.F90:2969-2973) */
+    int32_t reserved_i[4];
     double xmin, xmax, ymin, ymax, zmin, zmax;                 /* boundary.f90 */
     double hfact, tolh;                                        /* part.F90 hfact, options.f90:92 tolh */
     double massoftype[SPHGPU_MAXTYPES];                        /* part.F90 massoftype(itype), index 0 unused */
@@ -236,6 +237,16 @@ typedef struct sphgpu_energies {
     int64_t np;
 } sphgpu_energies;
 int sphgpu_energies_resident(sphgpu_ctx *ctx, sphgpu_energies *out);
+
+/* turbulent driving: st_calcAccel (src/main/forcing.f90:728-830), called by derivs before force when
+ * -DDRIVING (deriv.f90:178-182).  The host keeps the Ornstein-Uhlenbeck phases (st_ounoiseupdate / st_calcPhases use the Fortran
+ * random_number stream) and hands the current mode set over whenever it changes: mode(3,n) wave vectors, ampl(n), aka(3,n), akb(3,n),
+ * st_amplfac, st_solweightnorm, correct_mean_force.  With params.driving = 1 every derivs call evaluates
+ * f_i = 2 amplfac solweightnorm sum_m ampl_m (aka_m cos(k_m.x_i) - akb_m sin(k_m.x_i)) into fxyzu before the force pass adds to it. */
+int sphgpu_set_forcing_modes(sphgpu_ctx *ctx, int nmodes, const double *mode, const double *ampl, const double *aka, const double *akb,
+                             double amplfac, double solweightnorm, int correct_mean_force);
+/* st_calcAccel alone on the resident state (fxyzu(1:3,:) of the active particles is overwritten) */
+int sphgpu_forcing_resident(sphgpu_ctx *ctx);
 
 /* register-resident DFMA microbenchmark: returns measured FP64 TFLOP/s of this device (roofline denominator) */
 double sphgpu_measure_fp64_peak(sphgpu_ctx *ctx);

@@ -1290,6 +1290,40 @@ void oracle_expand_fgrav(const double *fnode20, double dx, double dy, double dz,
 void oracle_propagate_fnode(double *dst, const double *src, double dx, double dy, double dz) { propagate_fnode_to_node(dst, src, dx, dy, dz); }
 
 // ran2 / get_random (random.f90:38-114); the second state is module-level and reset when the seed is negative
+// st_calcAccel (forcing.f90:728-830)
+void oracle_forcing(oracle_ctx *cp, int64_t npart, const double *xyzh, const int8_t *iphase, double *fxyzu, int nmodes, const double *mode,
+                    const double *ampl, const double *aka, const double *akb, double amplfac, double solweightnorm, int correct_mean_force)
+{
+    const oracle_ctx &c = *cp;
+    const int nvu = c.nvu();
+    double fm0 = 0., fm1 = 0., fm2 = 0.;
+#pragma omp parallel for schedule(static) reduction(+ : fm0, fm1, fm2)
+    for (int64_t i = 0; i < npart; i++) {
+        const bool active = c.p.ind_timesteps ? (iphase[i] > 0) : true;
+        if (!(active || correct_mean_force)) continue;
+        const double *x = xyzh + 4 * i;
+        double fxi = 0., fyi = 0., fzi = 0.;
+        for (int m = 0; m < nmodes; m++) {
+            const double kdotx = mode[3 * m] * x[0] + mode[3 * m + 1] * x[1] + mode[3 * m + 2] * x[2];
+            const double re = std::cos(kdotx), im = std::sin(kdotx);
+            fxi += ampl[m] * (aka[3 * m] * re - akb[3 * m] * im);
+            fyi += ampl[m] * (aka[3 * m + 1] * re - akb[3 * m + 1] * im);
+            fzi += ampl[m] * (aka[3 * m + 2] * re - akb[3 * m + 2] * im);
+        }
+        fxi = 2. * amplfac * solweightnorm * fxi; fyi = 2. * amplfac * solweightnorm * fyi; fzi = 2. * amplfac * solweightnorm * fzi;
+        if (active) { fxyzu[nvu * i] = fxi; fxyzu[nvu * i + 1] = fyi; fxyzu[nvu * i + 2] = fzi; }
+        if (correct_mean_force) { fm0 += fxi; fm1 += fyi; fm2 += fzi; }
+    }
+    if (correct_mean_force) {
+        fm0 /= (double)npart; fm1 /= (double)npart; fm2 /= (double)npart;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < npart; i++) {
+            const bool active = c.p.ind_timesteps ? (iphase[i] > 0) : true;
+            if (active) { fxyzu[nvu * i] -= fm0; fxyzu[nvu * i + 1] -= fm1; fxyzu[nvu * i + 2] -= fm2; }
+        }
+    }
+}
+
 double oracle_ran2(int32_t *s1p)
 {
     static int32_t s2 = 123456789;

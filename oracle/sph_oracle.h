@@ -46,7 +46,8 @@ typedef struct oracle_params {
     int32_t ipdv_heating, ishock_heating, iresistive_heating; /* eos.f90:1896-1898 */
     int32_t set_boundaries_to_active; /* part.F90:439 */
     int32_t idrag;           /* dust.f90: 1 Epstein/Stokes, 2 const K, 3 const ts */
-    int32_t reserved_i[5];
+    int32_t driving;         /* -DDRIVING: turbulent stirring (forcing.f90); force() then ADDS to fxyzu (force.F90:2969-2973) */
+    int32_t reserved_i[4];
     /* boundary.f90 */
     double xmin, xmax, ymin, ymax, zmin, zmax;
     /* part / options */
@@ -140,6 +141,10 @@ void oracle_kernel_constants(int kernel, double *radkern, double *cnormk, double
 void oracle_compute_M2L(double dx, double dy, double dz, double dr, double totmass, const double *quads, double *fnode20);
 void oracle_expand_fgrav(const double *fnode20, double dx, double dy, double dz, double *fxyzpot4);
 void oracle_propagate_fnode(double *fnode_dst20, const double *fnode_src20, double dx, double dy, double dz);
+
+/* st_calcAccel (forcing.f90:728-830): turbulent stirring acceleration into fxyzu(1:3,:) */
+void oracle_forcing(oracle_ctx *c, int64_t npart, const double *xyzh, const int8_t *iphase, double *fxyzu, int nmodes, const double *mode,
+                    const double *ampl, const double *aka, const double *akb, double amplfac, double solweightnorm, int correct_mean_force);
 
 /* L'Ecuyer ran2 (random.f90) */
 double oracle_ran2(int32_t *iseed);

@@ -35,7 +35,7 @@ EXPORTS = [
     "sphgpu_cons2prim_everything", "sphgpu_force", "sphgpu_derivs", "sphgpu_get_neighbour_stats", "sphgpu_neighbour_sets",
     "sphgpu_measure_fp64_peak", "sphgpu_measure_copy_bw", "sphgpu_local_hmax", "sphgpu_halo_select", "sphgpu_halo_pack",
     "sphgpu_halo_recvbuf", "sphgpu_halo_unpack", "sphgpu_nghost", "sphgpu_set_timestep_bins", "sphgpu_get_gravity_timings", "sphgpu_gravity_tree", "sphgpu_step_resident", "sphgpu_energies_resident", "sphgpu_gravity_gather_pack", "sphgpu_gravity_gather_recvbuf",
-    "sphgpu_gravity_gather_unpack", "sphgpu_density_hmax_used", "sphgpu_halo_restore_h",
+    "sphgpu_gravity_gather_unpack", "sphgpu_density_hmax_used", "sphgpu_halo_restore_h", "sphgpu_set_forcing_modes", "sphgpu_forcing_resident",
 ]
 
 
@@ -106,6 +106,8 @@ def load_library():
         L.sphgpu_gravity_tree.restype = i64
         L.sphgpu_step_resident.argtypes = [vp, dbl, dbl, C.POINTER(SphStepOut)]
         L.sphgpu_energies_resident.argtypes = [vp, C.POINTER(SphEnergies)]
+        L.sphgpu_set_forcing_modes.argtypes = [vp, i32, vp, vp, vp, vp, dbl, dbl, i32]
+        L.sphgpu_forcing_resident.argtypes = [vp]
         L.sphgpu_density_hmax_used.argtypes = [vp, C.POINTER(dbl)]
         L.sphgpu_halo_restore_h.argtypes = [vp]
         L.sphgpu_gravity_gather_pack.argtypes = [vp, C.POINTER(vp), C.POINTER(i32)]
@@ -248,6 +250,15 @@ class SphGpu:
         sc = SphScalars()
         self._check(self.L.sphgpu_force_resident(self.h, icall, dt, C.byref(sc)))
         return sc
+
+    def set_forcing_modes(self, mode, ampl, aka, akb, amplfac=1.0, solweightnorm=1.0, correct_mean_force=False):
+        """current stirring mode set of forcing.f90 (st_mode, st_ampl, st_aka, st_akb, st_amplfac, st_solweightnorm)"""
+        mode, ampl, aka, akb = [np.ascontiguousarray(a, dtype=np.float64) for a in (mode, ampl, aka, akb)]
+        self._check(self.L.sphgpu_set_forcing_modes(self.h, len(ampl), _p(mode), _p(ampl), _p(aka), _p(akb), float(amplfac), float(solweightnorm),
+                                                    int(correct_mean_force)))
+
+    def forcing_resident(self):
+        self._check(self.L.sphgpu_forcing_resident(self.h))
 
     def step_resident(self, dtsph, tolv=1.e-2):
         """one leapfrog step of the resident state (step_leapfrog.f90:95, global timesteps)"""

@@ -115,6 +115,7 @@ struct sphgpu_ctx {
     DevBuf<float> divcurlv, divcurlB, alphaind, gradh, dvdx, poten, divBsymm;
     DevBuf<int8_t> iphase, ibin, ibin_old, ibin_wake;
     DevBuf<double> dustfrac, tstop;
+    DevBuf<double> forc_tab; int forc_nmodes = 0, forc_correct_mean = 0; double forc_fac = 0.;   // turbulent driving mode table (forcing.f90)
     DevBuf<double> v_true, B_true;          // step.cu: the evolved v, B/rho while vxyzu/Bevol hold the predicted values
     DevBuf<double4> gacc;                   // far-field gravity {fx,fy,fz,pot} per particle (gravity.cu -> force epilogue)
     // ---- sorted working set ----

@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(128, XTRA ? 2 : 4) k_force(const ForceArgs a, 
 __global__ void k_scatter_force(int64_t nlive, const int *__restrict__ perm, const int *__restrict__ s_done, const double4 *__restrict__ s_fxyzu,
                                 const double4 *__restrict__ s_dB, const float *__restrict__ s_divvf, const float *__restrict__ s_divBsymm,
                                 double *__restrict__ fxyzu, double *__restrict__ dBevol, float *__restrict__ divcurlv, float *__restrict__ divBsymm, int nvu,
-                                int mhd, int gravity, int dust, int ind_ts, const float *__restrict__ s_poten, float *__restrict__ poten,
+                                int mhd, int gravity, int dust, int ind_ts, int driving, const float *__restrict__ s_poten, float *__restrict__ poten,
                                 const double *__restrict__ s_tstop, double *__restrict__ tstop, const int8_t *__restrict__ s_ibinnew,
                                 int8_t *__restrict__ ibin, const int *__restrict__ s_wake, int8_t *__restrict__ ibin_wake)
 {
@@ -757,7 +757,8 @@ __global__ void k_scatter_force(int64_t nlive, const int *__restrict__ perm, con
     if (ind_ts) ibin[i] = s_ibinnew[s];
     const double4 f = s_fxyzu[s];
     double *fi = fxyzu + (size_t)nvu * i;
-    fi[0] = f.x; fi[1] = f.y; fi[2] = f.z;
+    if (driving) { fi[0] += f.x; fi[1] += f.y; fi[2] += f.z; }      // the driving routine initialised the force (force.F90:2969-2973)
+    else { fi[0] = f.x; fi[1] = f.y; fi[2] = f.z; }
     if (d == 2) {
         if (nvu >= 4) fi[3] = f.w;
         divcurlv[i] = s_divvf[s];                                    // force.F90:2999
@@ -866,7 +867,7 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     dispatch_force(c, a, grid);
     cudaEventRecord(c->ev[11], c->stream);
     k_scatter_force<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->s_fxyzu.p, c->s_dB.p, c->s_divvf.p, c->s_divBsymm.p, c->fxyzu.p,
-                                                          c->dBevol.p, c->divcurlv.p, c->divBsymm.p, c->hp.nvu, p.mhd, p.gravity, p.dust, p.ind_timesteps,
+                                                          c->dBevol.p, c->divcurlv.p, c->divBsymm.p, c->hp.nvu, p.mhd, p.gravity, p.dust, p.ind_timesteps, p.driving,
                                                           c->s_poten.p, c->poten.p, c->s_tstop.p, c->tstop.p, c->s_ibinnew.p, c->ibin.p, c->s_wake.p,
                                                           c->ibin_wake.p);
     c->launches++;

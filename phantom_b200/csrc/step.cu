@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include <float.h>
 #include <string.h>
+#include <vector>
 
 namespace {
 
@@ -178,6 +179,65 @@ __global__ void k_energies(const EnArgs a)
     }
 }
 
+// st_calcAccel (forcing.f90:728-830): thread = particle, the mode table streams through shared memory in tiles
+struct ForcingArgs {
+    int64_t n; int nvu, nmodes, ind_ts, correct_mean;
+    const double *xyzh; const int8_t *iphase; double *f; const double *tab;     // tab: 10 doubles per mode {k(3), ampl, aka(3), akb(3)}
+    double fac; double *fmean;                                                     // fac = 2 amplfac solweightnorm
+};
+#define FORC_TILE 64
+
+__global__ void __launch_bounds__(256) k_forcing(const ForcingArgs a)
+{
+    __shared__ double tile[FORC_TILE * 10];
+    __shared__ double sh[32];
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool live = false, active = false;
+    double x = 0., y = 0., z = 0.;
+    if (i < a.n) {
+        const double4 p = reinterpret_cast<const double4 *>(a.xyzh)[i];
+        live = true;                                        // the reference loops over 1..npart without a dead-particle test
+        active = a.ind_ts ? (a.iphase[i] > 0) : true;
+        x = p.x; y = p.y; z = p.z;
+    }
+    const bool work = live && (active || a.correct_mean);
+    double fx = 0., fy = 0., fz = 0.;
+    for (int m0 = 0; m0 < a.nmodes; m0 += FORC_TILE) {
+        const int nt = min(FORC_TILE, a.nmodes - m0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < nt * 10; k += blockDim.x) tile[k] = a.tab[(size_t)m0 * 10 + k];
+        __syncthreads();
+        if (work) {
+            for (int m = 0; m < nt; m++) {
+                const double *t = tile + 10 * m;
+                const double kdotx = t[0] * x + t[1] * y + t[2] * z;
+                double im, re;
+                sincos(kdotx, &im, &re);
+                fx += t[3] * (t[4] * re - t[7] * im);
+                fy += t[3] * (t[5] * re - t[8] * im);
+                fz += t[3] * (t[6] * re - t[9] * im);
+            }
+        }
+    }
+    fx *= a.fac; fy *= a.fac; fz *= a.fac;
+    if (live && active) { a.f[a.nvu * i] = fx; a.f[a.nvu * i + 1] = fy; a.f[a.nvu * i + 2] = fz; }
+    if (a.correct_mean) {
+        if (!work) { fx = fy = fz = 0.; }
+        const double sx = block_sum(fx, sh), sy = block_sum(fy, sh), sz = block_sum(fz, sh);
+        if (threadIdx.x == 0) { atomicAdd(&a.fmean[0], sx); atomicAdd(&a.fmean[1], sy); atomicAdd(&a.fmean[2], sz); }
+    }
+}
+
+__global__ void k_forcing_mean(const ForcingArgs a)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const bool active = a.ind_ts ? (a.iphase[i] > 0) : true;
+    if (!active) return;
+    const double inv = 1. / (double)a.n;
+    a.f[a.nvu * i] -= a.fmean[0] * inv; a.f[a.nvu * i + 1] -= a.fmean[1] * inv; a.f[a.nvu * i + 2] -= a.fmean[2] * inv;
+}
+
 }  // namespace
 
 #define SL(c, kern, ...) do { kern<<<(c)->numSMs * 8, 256, 0, (c)->stream>>>(__VA_ARGS__); (c)->launches++; } while (0)
@@ -240,6 +300,43 @@ int sphgpu_step_resident(sphgpu_ctx *c, double dtsph, double tolv, sphgpu_step_o
     CUDA_TRY(c, cudaStreamSynchronize(st));
     CUDA_TRY(c, cudaGetLastError());
     if (out) { memset(out, 0, sizeof *out); out->dtcourant = sc.dtcourant; out->dtforce = sc.dtforce; out->dterr = dterr; out->errmax = errmax; out->its = its; out->scalars = sc; }
+    return SPHGPU_OK;
+}
+
+int sphgpu_set_forcing_modes(sphgpu_ctx *c, int nmodes, const double *mode, const double *ampl, const double *aka, const double *akb, double amplfac,
+                             double solweightnorm, int correct_mean_force)
+{
+    if (!c || nmodes < 0 || (nmodes > 0 && (!mode || !ampl || !aka || !akb))) return SPHGPU_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    std::vector<double> tab((size_t)10 * (nmodes > 0 ? nmodes : 1));
+    for (int m = 0; m < nmodes; m++) {
+        double *t = tab.data() + 10 * (size_t)m;
+        t[0] = mode[3 * m]; t[1] = mode[3 * m + 1]; t[2] = mode[3 * m + 2]; t[3] = ampl[m];
+        for (int k = 0; k < 3; k++) { t[4 + k] = aka[3 * m + k]; t[7 + k] = akb[3 * m + k]; }
+    }
+    CUDA_TRY(c, c->forc_tab.ensure(tab.size()));
+    CUDA_TRY(c, cudaMemcpyAsync(c->forc_tab.p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->forc_nmodes = nmodes; c->forc_fac = 2. * amplfac * solweightnorm; c->forc_correct_mean = correct_mean_force;
+    return SPHGPU_OK;
+}
+
+int sphgpu_forcing_resident(sphgpu_ctx *c)
+{
+    if (!c) return SPHGPU_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int64_t n = c->nlocal > 0 ? c->nlocal : c->npart;
+    if (n <= 0) return SPHGPU_ERR_STATE;
+    CUDA_TRY(c, c->dscal.ensure(DS_COUNT));
+    CUDA_TRY(c, c->forc_tab.ensure(10));
+    ForcingArgs a; memset(&a, 0, sizeof a);
+    a.n = n; a.nvu = c->hp.nvu; a.nmodes = c->forc_nmodes; a.ind_ts = c->hp.p.ind_timesteps; a.correct_mean = c->forc_correct_mean;
+    a.xyzh = c->xyzh.p; a.iphase = c->iphase.p; a.f = c->fxyzu.p; a.tab = c->forc_tab.p; a.fac = c->forc_fac; a.fmean = c->dscal.p + 16;
+    CUDA_TRY(c, cudaMemsetAsync(a.fmean, 0, 3 * sizeof(double), c->stream));
+    k_forcing<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(a);
+    c->launches++;
+    if (a.correct_mean) { k_forcing_mean<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(a); c->launches++; }
+    CUDA_TRY(c, cudaGetLastError());
     return SPHGPU_OK;
 }
 

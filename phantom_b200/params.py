@@ -20,7 +20,7 @@ class SphParams(C.Structure):
         ("gravity", C.c_int32), ("dust", C.c_int32), ("const_av", C.c_int32), ("ind_timesteps", C.c_int32),
         ("disc_viscosity", C.c_int32), ("ieos", C.c_int32),
         ("ipdv_heating", C.c_int32), ("ishock_heating", C.c_int32), ("iresistive_heating", C.c_int32),
-        ("set_boundaries_to_active", C.c_int32), ("idrag", C.c_int32), ("reserved_i", C.c_int32 * 5),
+        ("set_boundaries_to_active", C.c_int32), ("idrag", C.c_int32), ("driving", C.c_int32), ("reserved_i", C.c_int32 * 4),
         ("xmin", C.c_double), ("xmax", C.c_double), ("ymin", C.c_double), ("ymax", C.c_double),
         ("zmin", C.c_double), ("zmax", C.c_double),
         ("hfact", C.c_double), ("tolh", C.c_double),

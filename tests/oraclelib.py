@@ -118,6 +118,11 @@ class Oracle:
             C.c_int(nbinmax), C.c_int(ibinnow), C.c_int(istepfrac), C.byref(sc)))
         return sc
 
+    def forcing(self, part, mode, ampl, aka, akb, amplfac=1.0, solweightnorm=1.0, correct_mean_force=False):
+        mode, ampl, aka, akb = [np.ascontiguousarray(a, dtype=np.float64) for a in (mode, ampl, aka, akb)]
+        self.L.oracle_forcing(self.h, C.c_int64(part.npart), _p(part.xyzh), _p(part.iphase), _p(part.fxyzu), C.c_int(len(ampl)), _p(mode), _p(ampl),
+                              _p(aka), _p(akb), C.c_double(amplfac), C.c_double(solweightnorm), C.c_int(int(correct_mean_force)))
+
     def derivs(self, part, icall=1, dt=0.0):
         """derivs(icall=1): tree -> density -> cons2prim -> force (deriv.f90:113-192)."""
         self.build_tree(part)

@@ -201,3 +201,60 @@ def test_selfgravity_against_direct_sum():
     epot, phitot = float(np.sum(pg.poten.astype(np.float64))), float(np.sum(pd.poten.astype(np.float64)))
     assert abs(epot - phitot) / abs(phitot) < 1.e-3      # 5.2e-4 in the reference at its own (larger) particle number
     assert abs(epot - (-3. / 5.)) / (3. / 5.) < 3.6e-2
+
+
+# ------------------------------------------------------------------------------------------------
+#  turbulent driving
+# ------------------------------------------------------------------------------------------------
+def stirring_modes(seed=7, kmax=3):
+    """a mode set shaped like init_stir's (forcing.f90:160-200): wave vectors 2 pi (i,j,k), paraboloid amplitudes, random aka/akb"""
+    rng = np.random.RandomState(seed)
+    modes = []
+    for i in range(0, kmax + 1):
+        for j in range(0, kmax + 1):
+            for k in range(0, kmax + 1):
+                k2 = i * i + j * j + k * k
+                if 1 <= k2 <= kmax * kmax:
+                    for sj in ((1, -1) if j else (1,)):
+                        for sk in ((1, -1) if k else (1,)):
+                            modes.append((i, sj * j, sk * k))
+    mode = 2. * np.pi * np.array(modes, dtype=np.float64)
+    kk = np.linalg.norm(mode, axis=1) / (2. * np.pi)
+    ampl = 4. * (0. - 1.) / ((kmax - 1.) ** 2) * (kk - 0.5 * (1. + kmax)) ** 2 + 1.
+    aka, akb = rng.normal(size=mode.shape), rng.normal(size=mode.shape)
+    return mode, ampl, aka, akb
+
+
+@pytest.mark.parametrize("correct_mean,ind_ts", [(False, False), (True, False), (True, True)])
+def test_turbulent_driving(correct_mean, ind_ts):
+    part = setups.setup_turb(nx=16, ind_timesteps=ind_ts)
+    part.params.driving = 1
+    part.alphaind[:, 0] = 1.0
+    if ind_ts:
+        part.iphase[::3] = -IGAS
+        part.gradh[:, 0] = 1.0
+        part.fxyzu[:, :3] = 0.123
+    mode, ampl, aka, akb = stirring_modes()
+    assert len(ampl) > 64                      # more than one shared-memory tile of modes
+    args = dict(amplfac=0.7, solweightnorm=1.3, correct_mean_force=correct_mean)
+    po, pg = part.copy(), part.copy()
+    o = Oracle(po.params)
+    o.build_tree(po); o.densityiterate(po); po.params.set_boundaries_to_active = 0; o.set_params(po.params); o.cons2prim(po)
+    o.forcing(po, mode, ampl, aka, akb, **args)
+    fdrive = po.fxyzu[:, :3].copy()
+    so = o.force(po, 1, 0.0)
+    g = gpu(pg.params)
+    g.set_forcing_modes(mode, ampl, aka, akb, **args)
+    sg = g.derivs(pg)
+    active = part.iphase > 0
+    assert np.sqrt(np.mean(fdrive[active] ** 2)) > 0.1 * np.sqrt(np.mean((po.fxyzu[active, :3] - fdrive[active]) ** 2))   # driving is a visible part of the force
+    assert relmax(pg.fxyzu[active, :3], po.fxyzu[active, :3]) < TOL_F
+    if ind_ts:
+        assert np.array_equal(pg.fxyzu[~active], part.fxyzu[~active])
+    # the driving acceleration alone (st_calcAccel)
+    g2 = gpu(part.params)
+    p2 = part.copy()
+    g2.set_forcing_modes(mode, ampl, aka, akb, **args)
+    g2.upload(p2); g2.forcing_resident(); g2.download(p2)
+    scale = np.sqrt(np.mean(fdrive[active] ** 2))
+    assert np.max(np.abs(p2.fxyzu[active, :3] - fdrive[active])) < 1e-12 * scale
