@@ -101,6 +101,7 @@ struct sphgpu_ctx {
     int grav_p2p_per_particle = 48; // capacity of the leaf P2P lists (source leaves per particle)
     struct GravState *grav = nullptr;
     bool grav_tree_valid = false;
+    double hscale = 1.;             // largest growth factor of any h since the tree's hmax were refitted (force walk inflates hmax by it)
     double dens_hmax_used = 0.;     // largest trial h any active particle took during the last density pass (halo sufficiency check)
     DevBuf<double> h_build, h_hist; // h at build_tree and after each h-rho iteration (replayed by k_g_hmax_leaf)
     DevBuf<int> h_its;
@@ -130,6 +131,7 @@ struct sphgpu_ctx {
     DevBuf<double4> frecC, frecD, frecE;    // force j-side records (sorted)
     DevBuf<double4> drec;                   // packed records of the single-type fast density path (4 x 32 B per particle)
     DevBuf<double4> frec;                   // packed records of the all-gas fast path (5 x 32 B per particle)
+    bool always_refit = false;              // option: refit the tree's hmax after every density pass (A/B testing)
     bool force_general = false;             // option: route everything through the general force kernel (A/B testing)
     DevBuf<float> s_gradh, s_divv, s_dvdx, s_alpha3, s_divcurlB;   // sorted density outputs
     DevBuf<double4> s_fxyzu, s_dB;          // sorted force outputs
@@ -254,7 +256,7 @@ __device__ __forceinline__ void atomic_max_pos(double *addr, double v) { atomicM
 enum { CNT_WORK = 0, CNT_ERR, CNT_ERRID, CNT_NPAIRS, CNT_NTRIAL, CNT_NCALC, CNT_NACT, CNT_MAXACT, CNT_MAXTRIAL, CNT_NP, CNT_NWALK, CNT_NLIVE, CNT_NBINMAX, CNT_NCHECKBIN, CNT_MULTITYPE, CNT_NSURV,
        CNT_NGRAVPAIRS = 24, CNT_NM2L = 25, CNT_COUNT = 32 };
 // indices into ctx->dscal (double)
-enum { DS_XMIN = 0, DS_YMIN, DS_ZMIN, DS_XMAX, DS_YMAX, DS_ZMAX, DS_DTCOURANT, DS_DTFORCE, DS_DTMINI, DS_DTMAXI, DS_RHOMAX, DS_HUSED, DS_COUNT = 32 };
+enum { DS_XMIN = 0, DS_YMIN, DS_ZMIN, DS_XMAX, DS_YMAX, DS_ZMAX, DS_DTCOURANT, DS_DTFORCE, DS_DTMINI, DS_DTMAXI, DS_RHOMAX, DS_HUSED, DS_HGROW, DS_COUNT = 32 };
 
 // internal API between translation units
 int tree_build(sphgpu_ctx *c);

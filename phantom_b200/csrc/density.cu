@@ -48,16 +48,18 @@ __global__ void k_gather_dens(int64_t nlive, const int *__restrict__ perm, const
     if (s >= nlive) return;
     const int i = perm[s];
     const double *v = vxyzu + (size_t)nvu * i, *f = fxyzu + (size_t)nvu * i, *fe = fext + 3 * (size_t)i;
-    vel4[s] = make_double4(v[0], v[1], v[2], nvu >= 4 ? v[3] : 0.);
-    acc4[s] = make_double4(f[0] + fe[0], f[1] + fe[1], f[2] + fe[2], 0.);     // dens.F90:1353-1355
-    if (mhd) bev4[s] = reinterpret_cast<const double4 *>(Bevol)[i];
+    const double4 vv = make_double4(v[0], v[1], v[2], nvu >= 4 ? v[3] : 0.);
+    const double4 aa = make_double4(f[0] + fe[0], f[1] + fe[1], f[2] + fe[2], 0.);     // dens.F90:1353-1355
+    if (drec) {                                                  // packed record of the single-type fast path
+        double4 *r = drec + (mhd ? 4 : 3) * (size_t)s;
+        r[0] = pos4[s]; r[1] = vv; r[2] = aa;
+        if (mhd) r[3] = reinterpret_cast<const double4 *>(Bevol)[i];
+    } else {
+        vel4[s] = vv; acc4[s] = aa;
+        if (mhd) bev4[s] = reinterpret_cast<const double4 *>(Bevol)[i];
+    }
     hnew[s] = pos4[s].w;
     s_nneigh[s] = -1;
-    if (drec) {
-        double4 *r = drec + (mhd ? 4 : 3) * (size_t)s;
-        r[0] = pos4[s]; r[1] = vel4[s]; r[2] = acc4[s];
-        if (mhd) r[3] = bev4[s];
-    }
 }
 
 __global__ void k_scatter_dens(int64_t nlive, const int *__restrict__ perm, const int *__restrict__ s_nneigh, const double *__restrict__ hnew,
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density
     // per-lane statistics (dens.F90:104-106), reduced once at kernel exit
     unsigned long long st_pairs = 0, st_trial = 0, st_ncalc = 0, st_nact = 0, st_np = 0, st_nwalk = 0, st_surv = 0;
     int st_maxact = 0, st_maxtrial = 0;
-    double st_rhomax = 0., st_hused = 0.;
+    double st_rhomax = 0., st_hused = 0., st_hgrow = 0.;
 
     while (true) {
         int cellid = 0;
@@ -261,9 +263,9 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density
         bool act = false, gasi = true, dusti = false; int itypei = IGAS;
         if (lane < cell.count) get_partinfo_d(a.stype[s], dp.p.set_boundaries_to_active, dp.p.dust, act, gasi, dusti, itypei);
         const double4 pi = a.pos4[s];
-        const double4 vi = a.vel4[s], ai = a.acc4[s];
-        double4 bi = make_double4(0., 0., 0., 0.);
-        if (MHD && gasi) bi = a.bev4[s];
+        double4 vi, ai, bi = make_double4(0., 0., 0., 0.);
+        if (FAST) { const double4 *r = a.drec + DSTRIDE * (size_t)s; vi = r[1]; ai = r[2]; if (MHD && gasi) bi = r[3]; }
+        else { vi = a.vel4[s]; ai = a.acc4[s]; if (MHD && gasi) bi = a.bev4[s]; }
         const double pmassi = dp.p.massoftype[itypei];
         const float xif = (float)(pi.x - cx), yif = (float)(pi.y - cy), zif = (float)(pi.z - cz);
         double h = pi.w;
@@ -404,7 +406,9 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density
             const double dhdrhoi = -h / (3. * rhohi);
             const double omegai = 1. - dhdrhoi * gradhi;
             gradhi = 1. / omegai;
-            a.hnew[s] = dp.p.hfact * pow(pmassi / fabs(rho), 1.0 / 3.0);            // hrho, part.F90:845
+            const double hfin = dp.p.hfact * pow(pmassi / fabs(rho), 1.0 / 3.0);    // hrho, part.F90:845
+            a.hnew[s] = hfin;
+            st_hgrow = fmax(st_hgrow, hfin / h_old);
             const float gradh4 = (float)gradhi;
             a.s_gradh[(size_t)dp.ngradh * s] = gradh4;
             if (GRAV) {
@@ -471,7 +475,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density
         __syncwarp();
     }
     // ---- statistics: one atomic per warp
-    st_rhomax = warp_max(st_rhomax);
+    st_rhomax = warp_max(st_rhomax); st_hused = warp_max(st_hused); st_hgrow = warp_max(st_hgrow);
 #pragma unroll
     for (int sft = 16; sft >= 1; sft >>= 1) {
         st_pairs += __shfl_xor_sync(FULLMASK, st_pairs, sft); st_trial += __shfl_xor_sync(FULLMASK, st_trial, sft);
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density
         atomicAdd(&a.cnt[CNT_NACT], st_nact); atomicAdd(&a.cnt[CNT_NP], st_np); atomicAdd(&a.cnt[CNT_NWALK], st_nwalk);
         atomicAdd(&a.cnt[CNT_NSURV], st_surv);
         atomicMax(&a.cnt[CNT_MAXACT], (unsigned long long)st_maxact); atomicMax(&a.cnt[CNT_MAXTRIAL], (unsigned long long)st_maxtrial);
-        atomic_max_pos(&a.dscal[DS_RHOMAX], st_rhomax); atomic_max_pos(&a.dscal[DS_HUSED], st_hused);
+        atomic_max_pos(&a.dscal[DS_RHOMAX], st_rhomax); atomic_max_pos(&a.dscal[DS_HUSED], st_hused); atomic_max_pos(&a.dscal[DS_HGROW], st_hgrow);
     }
 }
 
@@ -551,7 +555,7 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
                                                         c->acc4.p, c->bev4.p, c->hnew.p, c->s_nneigh.p, fast ? c->drec.p : nullptr);
     c->launches++;
     CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
-    CUDA_TRY(c, cudaMemsetAsync(c->dscal.p + DS_RHOMAX, 0, 2 * sizeof(double), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->dscal.p + DS_RHOMAX, 0, 3 * sizeof(double), c->stream));
     a.drec = c->drec.p;
     a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.acc4 = c->acc4.p; a.bev4 = c->bev4.p; a.stype = c->stype.p; a.perm = c->perm.p;
@@ -569,11 +573,11 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
                                                          c->s_alpha3.p, c->s_divcurlB.p, c->gradh.p, c->divcurlv.p, c->dvdx.p, c->alphaind.p, c->divcurlB.p,
                                                          c->hp.ngradh, c->hp.nalpha, p.mhd, p.dust ? c->s_dustfrac.p : nullptr, c->dustfrac.p);
     c->launches++;
-    TRY(tree_refit_hmax(c));          // set_hmaxcell (neigh_kdtree.f90:115-131): the force walk needs the new hmax
-    unsigned long long hc[16]; double hrhomax, hused;
+    unsigned long long hc[16]; double hrhomax, hused, hgrow = 0.;
     CUDA_TRY(c, cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(&hrhomax, c->dscal.p + DS_RHOMAX, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(&hused, c->dscal.p + DS_HUSED, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(&hgrow, c->dscal.p + DS_HGROW, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaGetLastError());
     { float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); c->ms_kernel[0] = ms; }
@@ -586,6 +590,10 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     memset(&sc, 0, sizeof sc);
     sc.rhomax = hrhomax; sc.np = (int64_t)hc[CNT_NP];
     c->dens_hmax_used = hused;
+    // set_hmaxcell (neigh_kdtree.f90:115-131): the force walk needs hmax >= the new h.  When no h grew by more than 2 % the tree's
+    // hmax are inflated by that factor instead of refitted (saves the bottom-up pass); otherwise refit.
+    if (hgrow <= 1.02 && !c->always_refit) c->hscale = fmax(c->hscale, 1.) * fmax(hgrow, 1.) * (1. + 1e-12);
+    else TRY(tree_refit_hmax(c));
     sc.trialmean = sc.np ? (double)hc[CNT_NTRIAL] / (double)hc[CNT_NCALC] : -1.;
     sc.actualmean = sc.np ? (double)hc[CNT_NACT] / (double)sc.np : -1.;
     sc.maxtrial = (int64_t)hc[CNT_MAXTRIAL]; sc.maxactual = (int64_t)hc[CNT_MAXACT]; sc.nrhocalc = (int64_t)hc[CNT_NCALC];

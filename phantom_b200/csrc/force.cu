@@ -23,6 +23,7 @@ struct ForceArgs {
     double4 *s_fxyzu, *s_dB; float *s_divvf, *s_divBsymm; int *s_done;
     int scratch_per_warp; unsigned long long *cnt; double *dscal;
     int icall;
+    double hscale;           // >= largest growth of any h since the tree's hmax were last refitted (1 after a refit): the walk inflates hmax by it
     // XTRA (gravity / dust / individual timesteps) only
     const double4 *frec;     // fast path: 5 x 32 B per particle {x,y,z,1/h} {v,gradW factor} {P/rho^2.., v_wave, alpha v_wave, 1/rho} {P,u,cs,alpha} {B,psi}
     const double *gsoft; const float *dvdx9; const double4 *gacc; float *s_poten; double *s_tstop;
@@ -60,8 +61,10 @@ __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const 
     const double rho = pmass * (hf * hf * hf);
     const double rho1 = 1. / rho;
     const double *v = vxyzu + (size_t)dp.nvu * i;
-    vel4[s] = make_double4(v[0], v[1], v[2], dp.nvu >= 4 ? v[3] : 0.);
-    hinv[s] = make_double2(h1, h21);
+    if (!frec) {                                                 // separate records: general kernel only
+        vel4[s] = make_double4(v[0], v[1], v[2], dp.nvu >= 4 ? v[3] : 0.);
+        hinv[s] = make_double2(h1, h21);
+    }
     double pro2 = 0., vwave = 0., alpha = 0., pr = 0., cs = 0., gradhfac = 0.;
     double4 E = make_double4(0., 0., 0., 0.);
     const double gh = (double)gradh[(size_t)dp.ngradh * i];
@@ -78,9 +81,11 @@ __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const 
             pro2 = pr * rho1 * rho1 + 0.5 * Bro2;
         } else { pro2 = pr * rho1 * rho1; vwave = cs; }
     }
-    recC[s] = make_double4(pro2, vwave, alpha, pr);
-    recD[s] = make_double4(rho1, gradhfac, pmass, cs);
-    if (p.mhd) recE[s] = E;
+    if (!frec) {
+        recC[s] = make_double4(pro2, vwave, alpha, pr);
+        recD[s] = make_double4(rho1, gradhfac, pmass, cs);
+        if (p.mhd) recE[s] = E;
+    }
     s_done[s] = 0;
     if (frec) {                                                  // packed j-records of the all-gas fast path
         const double4 x = pos4[s];
@@ -337,15 +342,15 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : FORCE_MINB) k_force_f
         float tlo[3], thi[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) { tlo[k] = __double2float_rd(cell.lo[k]); thi[k] = __double2float_ru(cell.hi[k]); }
-        const double rreach = KF::radkern * fmax(cell.hmax, (double)hmax_global) * 1.0001;
-        const double rcut = KF::radkern * cell.hmax;
+        const double rreach = KF::radkern * fmax(cell.hmax, (double)hmax_global) * a.hscale * 1.0001;
+        const double rcut = KF::radkern * cell.hmax * a.hscale;
         const bool wide = PERIODIC && (halfext + rreach >= 0.999 * halfLmin);
         // no pair of this group can straddle the periodic boundary: |xi - xj| <= L/2 for every candidate that survives the prefilter
         const bool interior = !PERIODIC || (cell.lo[0] - rreach > p.xmin && cell.hi[0] + rreach < p.xmax && cell.lo[1] - rreach > p.ymin &&
                                             cell.hi[1] + rreach < p.ymax && cell.lo[2] - rreach > p.zmin && cell.hi[2] + rreach < p.zmax);
         float reach = 0.f;
-        const int ncl = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut), (float)KF::radkern, fLx, fLy, fLz, ws, clist,
-                                                  a.scratch_per_warp, reach);
+        const int ncl = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut), __double2float_ru(KF::radkern * a.hscale),
+                                                  fLx, fLy, fLz, ws, clist, a.scratch_per_warp, reach);
         if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
         int nlist = 0;
         const float slack = prefilter_slack((float)halfext * 1.0001f + reach);
@@ -585,11 +590,11 @@ __global__ void __launch_bounds__(128, XTRA ? 2 : 4) k_force(const ForceArgs a, 
         float tlo[3], thi[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) { tlo[k] = __double2float_rd(cell.lo[k]); thi[k] = __double2float_ru(cell.hi[k]); }
-        const double rcut = KF::radkern * cell.hmax;
-        const bool wide = PERIODIC && (halfext + KF::radkern * fmax(cell.hmax, (double)hmax_global) >= 0.999 * halfLmin);
+        const double rcut = KF::radkern * cell.hmax * a.hscale;
+        const bool wide = PERIODIC && (halfext + KF::radkern * fmax(cell.hmax, (double)hmax_global) * a.hscale >= 0.999 * halfLmin);
         float reach = 0.f;
-        const int ncl = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut), (float)KF::radkern, fLx, fLy, fLz, ws, clist,
-                                                  a.scratch_per_warp, reach);
+        const int ncl = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut), __double2float_ru(KF::radkern * a.hscale),
+                                                  fLx, fLy, fLz, ws, clist, a.scratch_per_warp, reach);
         if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
         int nlist = 0;
         const float slack = prefilter_slack((float)halfext * 1.0001f + reach);
@@ -862,6 +867,7 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     a.frec = c->frec.p;
     a.gsoft = c->s_gsoft.p; a.dvdx9 = c->s_dvdx.p; a.gacc = c->gacc.p; a.s_poten = c->s_poten.p; a.s_tstop = c->s_tstop.p;
     a.s_ibinold = c->s_ibinold.p; a.s_ibin = c->s_ibin.p; a.s_wake = c->s_wake.p; a.s_ibinnew = c->s_ibinnew.p;
+    a.hscale = c->hscale;
     a.nbinmax = c->nbinmax; a.ibinnow_m1 = c->ibinnow - 1; a.istepfrac = c->istepfrac;
     cudaEventRecord(c->ev[10], c->stream);
     dispatch_force(c, a, grid);

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(128) k_neigh(const TreeNodeF *nodes, const Cel
 int64_t neighbour_sets_run(sphgpu_ctx *c, int symmetric, int64_t *offsets, int32_t *list, int64_t maxlist)
 {
     if (!c->tree_valid) { c->err = "neighbour_sets: build_tree has not been called"; return -1; }
+    if (c->hscale != 1.) { if (tree_refit_hmax(c) != SPHGPU_OK) return -1; }      // the cells' hmax must hold the current h
     const int64_t n = c->npart;
     const int grid = c->numSMs * 4;
     if (c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp) != cudaSuccess) return -1;

@@ -319,6 +319,7 @@ static int build_groups(sphgpu_ctx *c)
 int tree_refit_hmax(sphgpu_ctx *c)
 {
     const int M = (int)c->ncells;
+    c->hscale = 1.;
     LAUNCH(c, k_cell_hmax, nblk(M, 128), 128, M, c->cells.p, c->pos4.p);
     if (M > 1) {
         CUDA_TRY(c, cudaMemsetAsync(c->nodeflag.p, 0, sizeof(int) * (size_t)M, c->stream));
@@ -400,7 +401,7 @@ int tree_build(sphgpu_ctx *c)
         CUDA_TRY(c, c->h_build.ensure(n)); CUDA_TRY(c, c->h_its.ensure(n)); if (p.gravity) CUDA_TRY(c, c->h_hist.ensure((size_t)SPHGPU_HHIST * n));
         LAUNCH(c, k_hbuild, nblk(n, 256), 256, n, c->xyzh.p, c->h_build.p, c->h_its.p);
     }
-    c->grav_tree_valid = false;
+    c->grav_tree_valid = false; c->hscale = 1.;
     CUDA_TRY(c, cudaGetLastError());
     c->tree_valid = true;
     return SPHGPU_OK;
