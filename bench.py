@@ -260,6 +260,8 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = n * world * args.steps / float(te[0])
+    if not dsph2:
+        h2d, d2h = g2.copy_bytes()       # what the last sphgpu_derivs call moved over PCIe, counted by the library from the arrays it copies
 
     # ---------------- roofline of the dominant pair kernels ----------------
     fc = flop_constants()

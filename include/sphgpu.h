@@ -182,6 +182,8 @@ int sphgpu_force(sphgpu_ctx *ctx, int icall, int64_t npart, const double *xyzh, 
 /* derivs(icall,...): upload -> tree -> density -> cons2prim -> force -> download, all arrays of the bundle */
 int sphgpu_derivs(sphgpu_ctx *ctx, int icall, sphgpu_host_arrays *h, double dt, sphgpu_scalars *out);
 
+/* bytes the last sphgpu_derivs copied host->device and device->host (arrays every particle overwrites are not uploaded when all are active) */
+int sphgpu_get_copy_bytes(sphgpu_ctx *ctx, int64_t *h2d, int64_t *d2h);
 /* get_neighbour_stats(trialmean,actualmean,maxtrial,maxactual,nrhocalc,nactualtot) of the last density call */
 int sphgpu_get_neighbour_stats(sphgpu_ctx *ctx, sphgpu_scalars *out);
 /* exact neighbour sets of the last tree/density state in CSR form (1-based ids, sorted), for parity tests;

@@ -35,7 +35,7 @@ EXPORTS = [
     "sphgpu_cons2prim_everything", "sphgpu_force", "sphgpu_derivs", "sphgpu_get_neighbour_stats", "sphgpu_neighbour_sets",
     "sphgpu_measure_fp64_peak", "sphgpu_measure_copy_bw", "sphgpu_local_hmax", "sphgpu_halo_select", "sphgpu_halo_pack",
     "sphgpu_halo_recvbuf", "sphgpu_halo_unpack", "sphgpu_nghost", "sphgpu_set_timestep_bins", "sphgpu_get_gravity_timings", "sphgpu_gravity_tree", "sphgpu_step_resident", "sphgpu_energies_resident", "sphgpu_gravity_gather_pack", "sphgpu_gravity_gather_recvbuf",
-    "sphgpu_gravity_gather_unpack", "sphgpu_density_hmax_used", "sphgpu_halo_restore_h", "sphgpu_set_forcing_modes", "sphgpu_forcing_resident",
+    "sphgpu_gravity_gather_unpack", "sphgpu_density_hmax_used", "sphgpu_halo_restore_h", "sphgpu_set_forcing_modes", "sphgpu_forcing_resident", "sphgpu_get_copy_bytes",
 ]
 
 
@@ -108,6 +108,7 @@ def load_library():
         L.sphgpu_energies_resident.argtypes = [vp, C.POINTER(SphEnergies)]
         L.sphgpu_set_forcing_modes.argtypes = [vp, i32, vp, vp, vp, vp, dbl, dbl, i32]
         L.sphgpu_forcing_resident.argtypes = [vp]
+        L.sphgpu_get_copy_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
         L.sphgpu_density_hmax_used.argtypes = [vp, C.POINTER(dbl)]
         L.sphgpu_halo_restore_h.argtypes = [vp]
         L.sphgpu_gravity_gather_pack.argtypes = [vp, C.POINTER(vp), C.POINTER(i32)]
@@ -297,6 +298,12 @@ class SphGpu:
         ids = np.zeros(npart, dtype=np.int32)
         self.L.sphgpu_gravity_tree(self.h, nn, _p(rec), _p(irec), _p(ids))
         return rec, irec, ids
+
+    def copy_bytes(self):
+        """(host->device, device->host) bytes of the last derivs() call"""
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.L.sphgpu_get_copy_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def launch_count(self):
         return self.L.sphgpu_launch_count(self.h)

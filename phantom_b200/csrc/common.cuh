@@ -92,6 +92,9 @@ struct sphgpu_ctx {
     DevParams hp;              // host copy
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[16];
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // sphgpu_derivs: host<->device copies pipelined against the passes
+    cudaEvent_t cev[6];
+    int64_t bytes_h2d = 0, bytes_d2h = 0;   // bytes the last sphgpu_derivs moved over PCIe
     int numSMs = 148;
     int64_t launches = 0;
     double ms_phase[4] = {0, 0, 0, 0};

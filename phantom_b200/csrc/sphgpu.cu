@@ -128,6 +128,7 @@ void sphgpu_destroy(sphgpu_ctx *c)
     c->halo_sendidx.release(); c->halo_cnt.release(); c->halo_boxes.release(); c->halo_sendbuf.release(); c->halo_recvbuf.release();
     c->cubtemp.release(); c->scratch.release(); c->nodesf.release(); c->stage_idx.release(); c->counters.release(); c->dscal.release();
     for (int k = 0; k < 16; k++) cudaEventDestroy(c->ev[k]);
+    if (c->copy_in) { cudaStreamDestroy(c->copy_in); cudaStreamDestroy(c->copy_out); for (int k = 0; k < 6; k++) cudaEventDestroy(c->cev[k]); }
     gravity_release(c); c->h_build.release(); c->h_hist.release(); c->h_its.release();
     cudaStreamDestroy(c->stream);
     delete c;
@@ -388,21 +389,86 @@ int sphgpu_force(sphgpu_ctx *c, int icall, int64_t npart, const double *xyzh, co
     return sphgpu_download(c, &h, outm);
 }
 
+// derivs with host arrays in and out.  The copies are PIPELINED against the passes on two copy streams (pinned host buffers make
+// them truly asynchronous): positions go first and the tree builds while v, f, fext, alpha follow; the density outputs go back
+// while cons2prim and the force pass run, eos_vars/alpha during the force pass, and only fxyzu, divv (+ dB/dt, poten, bins)
+// after it.  Arrays that the passes overwrite for EVERY particle (gradh, divcurlv, dvdx, eos_vars) are uploaded only when some
+// particle is inactive or a boundary particle and therefore keeps its stored values (test_derivs.f90:233-238).
 int sphgpu_derivs(sphgpu_ctx *c, int icall, sphgpu_host_arrays *h, double dt, sphgpu_scalars *out)
 {
-    if (!c || !h) return SPHGPU_ERR_ARG;
-    uint64_t in = SPHGPU_F_XYZH | SPHGPU_F_VXYZU | SPHGPU_F_FXYZU | SPHGPU_F_FEXT | SPHGPU_F_ALPHAIND | SPHGPU_F_IPHASE | SPHGPU_F_GRADH | SPHGPU_F_DIVCURLV |
-                  SPHGPU_F_DVDX | SPHGPU_F_EOSVARS;
-    if (c->hp.p.mhd) in |= SPHGPU_F_BEVOL | SPHGPU_F_DIVCURLB;
-    if (c->hp.p.ind_timesteps) in |= SPHGPU_F_IBIN;
-    TRY(sphgpu_upload(c, h, in));
-    TRY(sphgpu_derivs_resident(c, icall, dt, out));
-    uint64_t outm = SPHGPU_F_XYZH | SPHGPU_F_FXYZU | SPHGPU_F_GRADH | SPHGPU_F_DIVCURLV | SPHGPU_F_DVDX | SPHGPU_F_ALPHAIND | SPHGPU_F_EOSVARS;
-    if (c->hp.p.ind_timesteps) outm |= SPHGPU_F_IBIN;
-    if (c->hp.p.dust) outm |= SPHGPU_F_DUSTFRAC | SPHGPU_F_TSTOP;
-    if (c->hp.p.mhd) outm |= SPHGPU_F_DBEVOL | SPHGPU_F_DIVCURLB | SPHGPU_F_DIVBSYMM;
-    if (c->hp.p.gravity) outm |= SPHGPU_F_POTEN;
-    return sphgpu_download(c, h, outm);
+    if (!c || !h || h->npart <= 0 || icall < 0 || icall > 2) return SPHGPU_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const sphgpu_params &p = c->hp.p;
+    const int64_t n = h->npart;
+    const int nvu = c->hp.nvu, ng = c->hp.ngradh;
+    if (!c->copy_in) { CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking)); CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+                       for (int k = 0; k < 6; k++) CUDA_TRY(c, cudaEventCreateWithFlags(&c->cev[k], cudaEventDisableTiming)); }
+    if (n != c->npart) { c->tree_valid = false; c->dens_valid = false; }
+    c->npart = n; c->nlocal = n; c->nghost = 0;
+    TRY(ensure_all(c, n));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));           // ensure_all may have zero-filled new buffers on the compute stream
+    bool all_active = (h->iphase != nullptr) && !p.set_boundaries_to_active && icall == 1;
+    if (all_active) { const int8_t *ip = h->iphase; for (int64_t i = 0; i < n; i++) if (ip[i] != IGAS) { all_active = false; break; } }
+    cudaStream_t si = c->copy_in, so = c->copy_out;
+    c->bytes_h2d = c->bytes_d2h = 0;
+#define H2D(buf, ptr, count) do { if (ptr) { CUDA_TRY(c, cudaMemcpyAsync((buf).p, ptr, sizeof(*(buf).p) * (size_t)(count), cudaMemcpyHostToDevice, si)); c->bytes_h2d += (int64_t)(sizeof(*(buf).p) * (size_t)(count)); } } while (0)
+#define D2H(buf, ptr, count) do { if ((ptr) && (buf).p) { CUDA_TRY(c, cudaMemcpyAsync(ptr, (buf).p, sizeof(*(buf).p) * (size_t)(count), cudaMemcpyDeviceToHost, so)); c->bytes_d2h += (int64_t)(sizeof(*(buf).p) * (size_t)(count)); } } while (0)
+    // ---- wave 1: what the tree needs
+    if (icall != 2) { H2D(c->xyzh, h->xyzh, 4 * n); H2D(c->iphase, h->iphase, n); c->tree_valid = false; }
+    CUDA_TRY(c, cudaEventRecord(c->cev[0], si));
+    // ---- wave 2: what density / cons2prim / force read
+    H2D(c->vxyzu, h->vxyzu, (size_t)nvu * n); H2D(c->fxyzu, h->fxyzu, (size_t)nvu * n); H2D(c->fext, h->fext, 3 * n); H2D(c->alphaind, h->alphaind, 3 * n);
+    if (p.mhd) { H2D(c->Bevol, h->Bevol, 4 * n); }
+    if (p.ind_timesteps) { H2D(c->ibin, h->ibin, n); H2D(c->ibin_old, h->ibin_old, n); H2D(c->ibin_wake, h->ibin_wake, n); }
+    if (!all_active) {
+        H2D(c->gradh, h->gradh, (size_t)ng * n); H2D(c->divcurlv, h->divcurlv, n); H2D(c->dvdx, h->dvdx, 9 * n); H2D(c->eos_vars, h->eos_vars, 7 * n);
+        if (p.mhd) H2D(c->divcurlB, h->divcurlB, 4 * n);
+    }
+    CUDA_TRY(c, cudaEventRecord(c->cev[1], si));
+    // ---- passes
+    cudaEventRecord(c->ev[0], c->stream);
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->cev[0], 0));
+    if (icall == 1 || icall == 0) TRY(tree_build(c));
+    cudaEventRecord(c->ev[1], c->stream);
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->cev[1], 0));
+    if (icall == 1) {
+        TRY(density_run(c, 1, nullptr));
+        c->hp.p.set_boundaries_to_active = 0;                     // deriv.f90:146
+    }
+    cudaEventRecord(c->ev[2], c->stream);
+    CUDA_TRY(c, cudaEventRecord(c->cev[2], c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(so, c->cev[2], 0));          // density outputs go home while cons2prim and force run
+    D2H(c->xyzh, h->xyzh, 4 * n); D2H(c->gradh, h->gradh, (size_t)ng * n); D2H(c->dvdx, h->dvdx, 9 * n);
+    if (p.mhd) D2H(c->divcurlB, h->divcurlB, 4 * n);
+    if (p.dust) D2H(c->dustfrac, h->dustfrac, n);
+    TRY(cons2prim_run(c));
+    cudaEventRecord(c->ev[3], c->stream);
+    CUDA_TRY(c, cudaEventRecord(c->cev[3], c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(so, c->cev[3], 0));
+    D2H(c->eos_vars, h->eos_vars, 7 * n); D2H(c->alphaind, h->alphaind, 3 * n);
+    if (p.driving) TRY(sphgpu_forcing_resident(c));              // forceit (deriv.f90:178-182)
+    TRY(force_run(c, icall, dt, out));
+    cudaEventRecord(c->ev[4], c->stream);
+    CUDA_TRY(c, cudaEventRecord(c->cev[4], c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(so, c->cev[4], 0));
+    D2H(c->fxyzu, h->fxyzu, (size_t)nvu * n); D2H(c->divcurlv, h->divcurlv, n);
+    if (p.mhd) { D2H(c->dBevol, h->dBevol, 4 * n); D2H(c->divBsymm, h->divBsymm, n); }
+    if (p.gravity) D2H(c->poten, h->poten, n);
+    if (p.dust) D2H(c->tstop, h->tstop, n);
+    if (p.ind_timesteps) { D2H(c->ibin, h->ibin, n); D2H(c->ibin_wake, h->ibin_wake, n); }
+#undef H2D
+#undef D2H
+    CUDA_TRY(c, cudaStreamSynchronize(so));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 4; k++) { float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1]); c->ms_phase[k] = ms; }
+    return SPHGPU_OK;
+}
+
+int sphgpu_get_copy_bytes(sphgpu_ctx *c, int64_t *h2d, int64_t *d2h)
+{
+    if (!c || !h2d || !d2h) return SPHGPU_ERR_ARG;
+    *h2d = c->bytes_h2d; *d2h = c->bytes_d2h;
+    return SPHGPU_OK;
 }
 
 int sphgpu_get_neighbour_stats(sphgpu_ctx *c, sphgpu_scalars *out)
