@@ -204,6 +204,8 @@ int sphgpu_local_hmax(sphgpu_ctx *ctx, double *hmax);
  * density pass; when radkern * (global max of it) exceeds the halo width used, restore the pre-density h and repeat with a wider halo */
 int sphgpu_density_hmax_used(sphgpu_ctx *ctx, double *hmax);
 int sphgpu_halo_restore_h(sphgpu_ctx *ctx);
+/* largest h_new/h_old of the last density pass on this rank (reduced over ranks by the driver, handed back as option "halo_hgrow") */
+int sphgpu_density_hgrow(sphgpu_ctx *ctx, double *hgrow);
 /* boxes = 6 doubles per rank {lo xyz, hi xyz}; counts[r] = owned particles within dhalo of rank r's box (minimum image) */
 int sphgpu_halo_select(sphgpu_ctx *ctx, int nranks, int myrank, const double *boxes, double dhalo, int64_t *counts);
 /* stage 1 (before build_tree): 16 doubles/ghost; stage 2 (after densityiterate): 4 doubles/ghost {h, gradh, alpha, gradsoft} */

@@ -35,7 +35,7 @@ EXPORTS = [
     "sphgpu_cons2prim_everything", "sphgpu_force", "sphgpu_derivs", "sphgpu_get_neighbour_stats", "sphgpu_neighbour_sets",
     "sphgpu_measure_fp64_peak", "sphgpu_measure_copy_bw", "sphgpu_local_hmax", "sphgpu_halo_select", "sphgpu_halo_pack",
     "sphgpu_halo_recvbuf", "sphgpu_halo_unpack", "sphgpu_nghost", "sphgpu_set_timestep_bins", "sphgpu_get_gravity_timings", "sphgpu_gravity_tree", "sphgpu_step_resident", "sphgpu_energies_resident", "sphgpu_gravity_gather_pack", "sphgpu_gravity_gather_recvbuf",
-    "sphgpu_gravity_gather_unpack", "sphgpu_density_hmax_used", "sphgpu_halo_restore_h", "sphgpu_set_forcing_modes", "sphgpu_forcing_resident", "sphgpu_get_copy_bytes",
+    "sphgpu_gravity_gather_unpack", "sphgpu_density_hmax_used", "sphgpu_halo_restore_h", "sphgpu_set_forcing_modes", "sphgpu_forcing_resident", "sphgpu_get_copy_bytes", "sphgpu_density_hgrow",
 ]
 
 
@@ -109,6 +109,7 @@ def load_library():
         L.sphgpu_set_forcing_modes.argtypes = [vp, i32, vp, vp, vp, vp, dbl, dbl, i32]
         L.sphgpu_forcing_resident.argtypes = [vp]
         L.sphgpu_get_copy_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+        L.sphgpu_density_hgrow.argtypes = [vp, C.POINTER(dbl)]
         L.sphgpu_density_hmax_used.argtypes = [vp, C.POINTER(dbl)]
         L.sphgpu_halo_restore_h.argtypes = [vp]
         L.sphgpu_gravity_gather_pack.argtypes = [vp, C.POINTER(vp), C.POINTER(i32)]
@@ -330,6 +331,11 @@ class SphGpu:
     def density_hmax_used(self):
         v = C.c_double()
         self._check(self.L.sphgpu_density_hmax_used(self.h, C.byref(v)))
+        return v.value
+
+    def density_hgrow(self):
+        v = C.c_double()
+        self._check(self.L.sphgpu_density_hgrow(self.h, C.byref(v)))
         return v.value
 
     def halo_restore_h(self):

@@ -105,6 +105,7 @@ struct sphgpu_ctx {
     struct GravState *grav = nullptr;
     bool grav_tree_valid = false;
     double hscale = 1.;             // largest growth factor of any h since the tree's hmax were refitted (force walk inflates hmax by it)
+    double dens_hgrow = 0., halo_hgrow = 0.;   // largest h_new/h_old of the last density pass (local) ; global value handed in by the halo driver
     double dens_hmax_used = 0.;     // largest trial h any active particle took during the last density pass (halo sufficiency check)
     DevBuf<double> h_build, h_hist; // h at build_tree and after each h-rho iteration (replayed by k_g_hmax_leaf)
     DevBuf<int> h_its;

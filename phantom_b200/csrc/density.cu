@@ -589,7 +589,7 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     sphgpu_scalars &sc = c->last_dens;
     memset(&sc, 0, sizeof sc);
     sc.rhomax = hrhomax; sc.np = (int64_t)hc[CNT_NP];
-    c->dens_hmax_used = hused;
+    c->dens_hmax_used = hused; c->dens_hgrow = hgrow;
     // set_hmaxcell (neigh_kdtree.f90:115-131): the force walk needs hmax >= the new h.  When no h grew by more than 2 % the tree's
     // hmax are inflated by that factor instead of refitted (saves the bottom-up pass); otherwise refit.
     if (hgrow <= 1.02 && !c->always_refit) c->hscale = fmax(c->hscale, 1.) * fmax(hgrow, 1.) * (1. + 1e-12);

@@ -153,6 +153,15 @@ int sphgpu_density_hmax_used(sphgpu_ctx *c, double *hmax)
     return SPHGPU_OK;
 }
 
+// largest h_new / h_old of the last density pass on this rank; the driver reduces it over the ranks and hands the global value back
+// (sphgpu_set_option "halo_hgrow") so that stage 2 can inflate the tree's hmax instead of refitting it
+int sphgpu_density_hgrow(sphgpu_ctx *c, double *hgrow)
+{
+    if (!c || !hgrow) return SPHGPU_ERR_ARG;
+    *hgrow = c->dens_hgrow;
+    return SPHGPU_OK;
+}
+
 __global__ void k_restore_h(int64_t n, double *__restrict__ xyzh, const double *__restrict__ h_build)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -256,7 +265,10 @@ int sphgpu_halo_unpack(sphgpu_ctx *c, int stage, int64_t nghost)
             if (c->tree_valid) {
                 k_refresh_h<<<nblk(c->nlive, 256), 256, 0, c->stream>>>(c->nlive, c->perm.p, c->xyzh.p, c->pos4.p);
                 c->launches++;
-                TRY(tree_refit_hmax(c));
+                // the ghosts' h grew by at most the global growth factor: inflate the tree's hmax by it when it is small, else refit
+                if (c->halo_hgrow > 0. && c->halo_hgrow <= 1.02 && !c->always_refit) c->hscale = fmax(c->hscale, fmax(c->halo_hgrow, 1.) * (1. + 1e-12));
+                else TRY(tree_refit_hmax(c));
+                c->halo_hgrow = 0.;
             }
         }
     }

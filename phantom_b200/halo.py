@@ -119,6 +119,7 @@ class DistributedSph:
         self.halo_bytes = 0
         self.nghost = 0
         self.nlocal = 0
+        self._hu_prev = None
 
     def _alltoall(self, sendptr, rd, sendcounts, recvcounts, stage):
         torch, dist = self.torch, self.dist
@@ -157,10 +158,22 @@ class DistributedSph:
         g = self.g
         self.halo_bytes = 0
         self.nlocal = int(g.npart_uploaded)
-        # halo width from the global hmax (one tiny all_reduce)
-        hm = torch.tensor([g.local_hmax()], dtype=torch.float64, device="cuda")
-        dist.all_reduce(hm, op=dist.ReduceOp.MAX)
-        dhalo = self.radkern * float(hm[0]) * self.margin
+        import os, time
+        timing = os.environ.get("SPHGPU_HALO_TIMING") and self.rank == 0
+        marks = []
+
+        def mark(name):
+            if timing:
+                torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+        mark("start")
+        # halo width from the global hmax: one tiny all_reduce on the first call; afterwards the largest trial h of the previous
+        # density pass (already reduced) -- the widening check below keeps this safe when h grows between steps
+        if self._hu_prev is None:
+            hm = torch.tensor([g.local_hmax()], dtype=torch.float64, device="cuda")
+            dist.all_reduce(hm, op=dist.ReduceOp.MAX)
+            self._hu_prev = float(hm[0])
+        dhalo = self.radkern * self._hu_prev * self.margin
         self.halo_rounds = 0
         while True:
             self.halo_rounds += 1
@@ -172,27 +185,39 @@ class DistributedSph:
             ptr, rd = g.halo_pack(1)
             self.nghost = self._alltoall(ptr, rd, sendcounts, recvcounts, 1)
             g.halo_unpack(1, self.nghost)
+            mark("halo1")
             g.build_tree_resident()
+            mark("tree")
             sd = g.densityiterate_resident(1)
+            mark("density")
             # widening round (the reference re-exports a cell whenever its h outgrows the search radius, dens.F90:343-365): if any
             # particle anywhere iterated with 2h beyond the halo the ghosts were selected with, restore h and repeat with a wider halo
-            hu = torch.tensor([g.density_hmax_used()], dtype=torch.float64, device="cuda")
+            hu = torch.tensor([g.density_hmax_used(), g.density_hgrow()], dtype=torch.float64, device="cuda")
             dist.all_reduce(hu, op=dist.ReduceOp.MAX)
+            hu = hu.cpu().numpy()
+            self._hu_prev = float(hu[0])
             if self.radkern * float(hu[0]) <= dhalo or self.halo_rounds >= 8:
                 break
             dhalo = self.radkern * float(hu[0]) * self.margin
             g.halo_restore_h()
+        g.set_option("halo_hgrow", float(hu[1]))
         g.params.set_boundaries_to_active = 0
         ptr, rd = g.halo_pack(2)
         self._alltoall(ptr, rd, sendcounts, recvcounts, 2)
         g.halo_unpack(2, self.nghost)
+        mark("halo2")
         g.cons2prim_resident()
         if g.params.gravity:
             self._gather_gravity_set()
         sf = g.force_resident(icall, dt)
+        mark("c2p+force")
         red = torch.tensor([sf.dtcourant, sf.dtforce, -sd.rhomax], dtype=torch.float64, device="cuda")
         dist.all_reduce(red, op=dist.ReduceOp.MIN)
         sf.dtcourant, sf.dtforce, sf.rhomax = float(red[0]), float(red[1]), -float(red[2])
         sf.np, sf.nrhocalc, sf.npairs_density = sd.np, sd.nrhocalc, sd.npairs_density
         sf.actualmean, sf.maxactual, sf.trialmean, sf.nactualtot = sd.actualmean, sd.maxactual, sd.trialmean, sd.nactualtot
+        mark("reduce")
+        if timing:
+            print("halo timing (ms): " + " ".join(f"{n}={1e3 * (t - marks[k][1]):.3f}" for k, (n, t) in enumerate(marks[1:])) +
+                  f" total={1e3 * (marks[-1][1] - marks[0][1]):.3f} nghost={self.nghost}", flush=True)
         return sf
