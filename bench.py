@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-cell", type=int, default=0)
     ap.add_argument("--max-leaf", type=int, default=0)
+    ap.add_argument("--hilbert", action="store_true", help="A/B: Hilbert instead of Morton particle order")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -174,6 +175,8 @@ def main():
         g.set_option("max_cell", args.max_cell)
     if args.max_leaf:
         g.set_option("max_leaf", args.max_leaf)
+    if args.hilbert:
+        g.set_option("hilbert", 1)
     fp64_peak = g.measure_fp64_peak()
     copy_bw = g.measure_copy_bw()
 

@@ -135,6 +135,7 @@ struct sphgpu_ctx {
     DevBuf<double4> frecC, frecD, frecE;    // force j-side records (sorted)
     DevBuf<double4> drec;                   // packed records of the single-type fast density path (4 x 32 B per particle)
     DevBuf<double4> frec;                   // packed records of the all-gas fast path (5 x 32 B per particle)
+    bool hilbert = false;                   // space-filling curve of the particle order: Morton (default) or Hilbert (option "hilbert" 1; measured equal on B200)
     bool always_refit = false;              // option: refit the tree's hmax after every density pass (A/B testing)
     bool force_general = false;             // option: route everything through the general force kernel (A/B testing)
     DevBuf<float> s_gradh, s_divv, s_dvdx, s_alpha3, s_divcurlB;   // sorted density outputs

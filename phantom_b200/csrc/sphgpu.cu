@@ -151,6 +151,7 @@ int sphgpu_set_option(sphgpu_ctx *c, const char *name, double value)
     if (!strcmp(name, "max_cell")) { int v = (int)value; c->max_cell = v < 1 ? 1 : (v > 32 ? 32 : v); c->tree_valid = false; return 0; }
     if (!strcmp(name, "max_leaf")) { int v = (int)value; c->max_leaf = v < 1 ? 1 : (v > 32 ? 32 : v); c->tree_valid = false; return 0; }
     if (!strcmp(name, "list_margin")) { c->list_margin = value < 1. ? 1. : value; return 0; }
+    if (!strcmp(name, "hilbert")) { c->hilbert = value != 0.; c->tree_valid = false; return 0; }
     if (!strcmp(name, "halo_hgrow")) { c->halo_hgrow = value; return 0; }
     if (!strcmp(name, "always_refit")) { c->always_refit = value != 0.; return 0; }
     if (!strcmp(name, "force_general")) { c->force_general = value != 0.; return 0; }

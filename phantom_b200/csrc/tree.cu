@@ -71,8 +71,27 @@ __device__ __forceinline__ unsigned long long spread21(unsigned long long x)
     return x;
 }
 
+// 3-D Hilbert index of 21-bit coordinates (Skilling 2004, "Programming the Hilbert curve": axes -> transposed index).  Like Morton
+// keys, every key prefix is an octree (binary-radix) node, so the cell and tree construction below is unchanged; unlike Morton order,
+// consecutive keys are always spatial neighbours, which keeps the candidate sets of consecutively processed target groups overlapping
+// (L1/L2 reuse of the neighbour records).
+__device__ __forceinline__ void hilbert_transpose(unsigned &x0, unsigned &x1, unsigned &x2)
+{
+    const unsigned M = 1u << 20;
+    for (unsigned Q = M; Q > 1; Q >>= 1) {
+        const unsigned P = Q - 1;
+        if (x0 & Q) x0 ^= P;                                   // i = 0: invert
+        if (x1 & Q) x0 ^= P; else { const unsigned t = (x0 ^ x1) & P; x0 ^= t; x1 ^= t; }
+        if (x2 & Q) x0 ^= P; else { const unsigned t = (x0 ^ x2) & P; x0 ^= t; x2 ^= t; }
+    }
+    x1 ^= x0; x2 ^= x1;                                        // Gray encode
+    unsigned t = 0;
+    for (unsigned Q = M; Q > 1; Q >>= 1) if (x2 & Q) t ^= Q - 1;
+    x0 ^= t; x1 ^= t; x2 ^= t;
+}
+
 __global__ void k_keys(int64_t n, const double *__restrict__ xyzh, double x0, double y0, double z0, double inv_scale,
-                       unsigned long long *__restrict__ keys, int *__restrict__ idx)
+                       unsigned long long *__restrict__ keys, int *__restrict__ idx, int hilbert)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -84,7 +103,9 @@ __global__ void k_keys(int64_t n, const double *__restrict__ xyzh, double x0, do
         double ux = fmin(fmax((x.x - x0) * inv_scale, 0.0), 0.99999994) * s;
         double uy = fmin(fmax((x.y - y0) * inv_scale, 0.0), 0.99999994) * s;
         double uz = fmin(fmax((x.z - z0) * inv_scale, 0.0), 0.99999994) * s;
-        key = (spread21((unsigned long long)ux) << 2) | (spread21((unsigned long long)uy) << 1) | spread21((unsigned long long)uz);
+        unsigned ix = (unsigned)ux, iy = (unsigned)uy, iz = (unsigned)uz;
+        if (hilbert) hilbert_transpose(ix, iy, iz);
+        key = (spread21((unsigned long long)ix) << 2) | (spread21((unsigned long long)iy) << 1) | spread21((unsigned long long)iz);
     }
     keys[i] = key;
     idx[i] = (int)i;
@@ -363,7 +384,7 @@ int tree_build(sphgpu_ctx *c)
     double scale = fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
     if (!(scale > 0.)) scale = 1.0;
     scale *= 1.0000001;
-    LAUNCH(c, k_keys, nblk(n, 256), 256, n, c->xyzh.p, lo[0], lo[1], lo[2], 1.0 / scale, c->keys_alt.p, c->perm_alt.p);
+    LAUNCH(c, k_keys, nblk(n, 256), 256, n, c->xyzh.p, lo[0], lo[1], lo[2], 1.0 / scale, c->keys_alt.p, c->perm_alt.p, c->hilbert ? 1 : 0);
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, c->keys_alt.p, c->keys.p, c->perm_alt.p, c->perm.p, (int)n, 0, 64, c->stream);
     size_t tb2 = 0;
