@@ -554,38 +554,49 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     k_gather_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->vxyzu.p, c->fxyzu.p, c->fext.p, c->Bevol.p, c->hp.nvu, p.mhd, c->pos4.p, c->vel4.p,
                                                         c->acc4.p, c->bev4.p, c->hnew.p, c->s_nneigh.p, fast ? c->drec.p : nullptr);
     c->launches++;
-    CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
-    CUDA_TRY(c, cudaMemsetAsync(c->dscal.p + DS_RHOMAX, 0, 3 * sizeof(double), c->stream));
     a.drec = c->drec.p;
     a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.acc4 = c->acc4.p; a.bev4 = c->bev4.p; a.stype = c->stype.p; a.perm = c->perm.p;
     a.hnew = c->hnew.p; a.s_gradh = c->s_gradh.p; a.s_divv = c->s_divv.p; a.s_dvdx = c->s_dvdx.p; a.s_alpha3 = c->s_alpha3.p;
     a.s_divcurlB = c->s_divcurlB.p; a.s_nneigh = c->s_nneigh.p; a.s_dustfrac = c->s_dustfrac.p;
-    a.stage_idx = c->stage_idx.p; a.multitype = c->multitype ? 1 : 0; a.max_leaf = c->max_leaf; a.hmax_global = 0.;
-    a.scratch_per_warp = c->scratch_per_warp; a.cnt = c->counters.p; a.dscal = c->dscal.p;
+    a.multitype = c->multitype ? 1 : 0; a.max_leaf = c->max_leaf; a.hmax_global = 0.;
+    a.cnt = c->counters.p; a.dscal = c->dscal.p;
     a.margin = c->list_margin; a.icall = icall;
     a.h_hist = c->h_hist.p; a.h_its = c->h_its.p; a.npart = n;
     c->grav_tree_valid = false;            // h changes below: the gravity tree caches h
-    cudaEventRecord(c->ev[8], c->stream);
-    dispatch_density(c, a, grid);
-    cudaEventRecord(c->ev[9], c->stream);
-    k_scatter_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->hnew.p, c->pos4.p, c->xyzh.p, c->s_gradh.p, c->s_divv.p, c->s_dvdx.p,
-                                                         c->s_alpha3.p, c->s_divcurlB.p, c->gradh.p, c->divcurlv.p, c->dvdx.p, c->alphaind.p, c->divcurlB.p,
-                                                         c->hp.ngradh, c->hp.nalpha, p.mhd, p.dust ? c->s_dustfrac.p : nullptr, c->dustfrac.p);
-    c->launches++;
     unsigned long long hc[16]; double hrhomax, hused, hgrow = 0.;
-    CUDA_TRY(c, cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(&hrhomax, c->dscal.p + DS_RHOMAX, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(&hused, c->dscal.p + DS_HUSED, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(&hgrow, c->dscal.p + DS_HGROW, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    CUDA_TRY(c, cudaGetLastError());
+    for (int attempt = 0;; attempt++) {
+        CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(c->dscal.p + DS_RHOMAX, 0, 3 * sizeof(double), c->stream));
+        a.stage_idx = c->stage_idx.p; a.scratch_per_warp = c->scratch_per_warp;
+        cudaEventRecord(c->ev[8], c->stream);
+        dispatch_density(c, a, grid);
+        cudaEventRecord(c->ev[9], c->stream);
+        CUDA_TRY(c, cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(&hrhomax, c->dscal.p + DS_RHOMAX, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(&hused, c->dscal.p + DS_HUSED, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(&hgrow, c->dscal.p + DS_HGROW, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        CUDA_TRY(c, cudaGetLastError());
+        // a group whose search sphere covers more leaf cells than a warp's cell list holds (strongly non-uniform h): grow the lists and
+        // repeat the pass -- nothing has been scattered to the caller's arrays yet
+        if (hc[CNT_ERR] == SPHGPU_ERR_OVERFLOW && attempt < 3 && c->scratch_per_warp < (1 << 20)) {
+            c->scratch_per_warp *= 8;
+            CUDA_TRY(c, c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp));
+            continue;
+        }
+        break;
+    }
     { float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); c->ms_kernel[0] = ms; }
     if (hc[CNT_ERR] == SPHGPU_ERR_NOCONVERGE) {
         char buf[160]; snprintf(buf, sizeof buf, "densityiterate: could not converge in density on particle %llu", hc[CNT_ERRID]);
         c->err = buf; return SPHGPU_ERR_NOCONVERGE;
     }
     if (hc[CNT_ERR]) { c->err = "densityiterate: neighbour scratch overflow (raise scratch_per_warp)"; return (int)hc[CNT_ERR]; }
+    k_scatter_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->hnew.p, c->pos4.p, c->xyzh.p, c->s_gradh.p, c->s_divv.p, c->s_dvdx.p,
+                                                         c->s_alpha3.p, c->s_divcurlB.p, c->gradh.p, c->divcurlv.p, c->dvdx.p, c->alphaind.p, c->divcurlB.p,
+                                                         c->hp.ngradh, c->hp.nalpha, p.mhd, p.dust ? c->s_dustfrac.p : nullptr, c->dustfrac.p);
+    c->launches++;
     sphgpu_scalars &sc = c->last_dens;
     memset(&sc, 0, sizeof sc);
     sc.rhomax = hrhomax; sc.np = (int64_t)hc[CNT_NP];

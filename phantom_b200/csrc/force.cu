@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : FORCE_MINB) k_force_f
         const float slack = prefilter_slack((float)halfext * 1.0001f + reach);
         // ---- lane = target (start_cell, force.F90:2172-2514; per-particle part done by k_force_prep)
         const int s = cell.start + min(lane, cell.count - 1);
-        const bool act = (lane < cell.count) && (a.stype[s] > 0);
+        bool act = false;
+        { bool g_, d_; int t_; if (lane < cell.count) get_partinfo_d(a.stype[s], p.set_boundaries_to_active, 0, act, g_, d_, t_); }
         const double4 *ri = a.frec + FSTRIDE * (size_t)s;
         const double4 T0 = ri[0], T1 = ri[1], T2 = ri[2];
         double4 T3 = make_double4(0., 0., 0., 0.), T4 = T3;
@@ -850,44 +851,54 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     memset(&a, 0, sizeof a);
     const int grid = c->numSMs * dispatch_force(c, a, -1);
     CUDA_TRY(c, c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp));
-    CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
-    const double init[4] = {1.e29, 1.e29, 1.e29, 0.};
-    CUDA_TRY(c, cudaMemcpyAsync(c->dscal.p + DS_DTCOURANT, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     double2 *hinv = reinterpret_cast<double2 *>(c->hnew.p);
-    k_force_prep<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->pos4.p, c->stype.p, c->vxyzu.p, c->Bevol.p, c->eos_vars.p, c->alphaind.p, c->gradh.p,
-                                                       c->vel4.p, c->frecC.p, c->frecD.p, c->frecE.p, hinv, c->s_nneigh.p, c->hp, c->counters.p,
-                                                       c->s_gsoft.p, c->dvdx.p, c->s_dvdx.p, c->ibin.p, c->ibin_old.p, c->ibin_wake.p, c->s_ibin.p,
-                                                       c->s_ibinold.p, c->s_wake.p, fast ? c->frec.p : nullptr);
-    c->launches++;
     a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.recC = c->frecC.p; a.recD = c->frecD.p; a.recE = c->frecE.p; a.hinv = hinv; a.stype = c->stype.p; a.perm = c->perm.p;
     a.s_fxyzu = c->s_fxyzu.p; a.s_dB = c->s_dB.p; a.s_divvf = c->s_divvf.p; a.s_divBsymm = c->s_divBsymm.p; a.s_done = c->s_nneigh.p;
-    a.stage_idx = c->stage_idx.p; a.multitype = c->multitype ? 1 : 0; a.max_leaf = c->max_leaf;
-    a.scratch_per_warp = c->scratch_per_warp; a.cnt = c->counters.p; a.dscal = c->dscal.p; a.icall = icall;
+    a.multitype = c->multitype ? 1 : 0; a.max_leaf = c->max_leaf;
+    a.cnt = c->counters.p; a.dscal = c->dscal.p; a.icall = icall;
     a.frec = c->frec.p;
     a.gsoft = c->s_gsoft.p; a.dvdx9 = c->s_dvdx.p; a.gacc = c->gacc.p; a.s_poten = c->s_poten.p; a.s_tstop = c->s_tstop.p;
     a.s_ibinold = c->s_ibinold.p; a.s_ibin = c->s_ibin.p; a.s_wake = c->s_wake.p; a.s_ibinnew = c->s_ibinnew.p;
     a.hscale = c->hscale;
     a.nbinmax = c->nbinmax; a.ibinnow_m1 = c->ibinnow - 1; a.istepfrac = c->istepfrac;
-    cudaEventRecord(c->ev[10], c->stream);
-    dispatch_force(c, a, grid);
-    cudaEventRecord(c->ev[11], c->stream);
-    k_scatter_force<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->s_fxyzu.p, c->s_dB.p, c->s_divvf.p, c->s_divBsymm.p, c->fxyzu.p,
-                                                          c->dBevol.p, c->divcurlv.p, c->divBsymm.p, c->hp.nvu, p.mhd, p.gravity, p.dust, p.ind_timesteps, p.driving,
-                                                          c->s_poten.p, c->poten.p, c->s_tstop.p, c->tstop.p, c->s_ibinnew.p, c->ibin.p, c->s_wake.p,
-                                                          c->ibin_wake.p);
-    c->launches++;
     unsigned long long hc[16]; double hd[4];
-    CUDA_TRY(c, cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(hd, c->dscal.p + DS_DTCOURANT, sizeof(hd), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    CUDA_TRY(c, cudaGetLastError());
+    for (int attempt = 0;; attempt++) {
+        CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
+        const double init[4] = {1.e29, 1.e29, 1.e29, 0.};
+        CUDA_TRY(c, cudaMemcpyAsync(c->dscal.p + DS_DTCOURANT, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+        k_force_prep<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->pos4.p, c->stype.p, c->vxyzu.p, c->Bevol.p, c->eos_vars.p, c->alphaind.p, c->gradh.p,
+                                                           c->vel4.p, c->frecC.p, c->frecD.p, c->frecE.p, hinv, c->s_nneigh.p, c->hp, c->counters.p,
+                                                           c->s_gsoft.p, c->dvdx.p, c->s_dvdx.p, c->ibin.p, c->ibin_old.p, c->ibin_wake.p, c->s_ibin.p,
+                                                           c->s_ibinold.p, c->s_wake.p, fast ? c->frec.p : nullptr);
+        c->launches++;
+        a.stage_idx = c->stage_idx.p; a.scratch_per_warp = c->scratch_per_warp;
+        cudaEventRecord(c->ev[10], c->stream);
+        dispatch_force(c, a, grid);
+        cudaEventRecord(c->ev[11], c->stream);
+        CUDA_TRY(c, cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(hd, c->dscal.p + DS_DTCOURANT, sizeof(hd), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        CUDA_TRY(c, cudaGetLastError());
+        // cell lists too short for some group (strongly non-uniform h): grow them and repeat -- nothing has been scattered yet
+        if (hc[CNT_ERR] == SPHGPU_ERR_OVERFLOW && attempt < 3 && c->scratch_per_warp < (1 << 20)) {
+            c->scratch_per_warp *= 8;
+            CUDA_TRY(c, c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp));
+            continue;
+        }
+        break;
+    }
     { float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[10], c->ev[11]); c->ms_kernel[1] = ms; }
     if (hc[CNT_ERR] == SPHGPU_ERR_NEGH) {
         char buf[128]; snprintf(buf, sizeof buf, "force: negative smoothing length on particle %llu", hc[CNT_ERRID]);
         c->err = buf; return SPHGPU_ERR_NEGH;
     }
     if (hc[CNT_ERR]) { c->err = "force: neighbour scratch overflow (raise scratch_per_warp)"; return (int)hc[CNT_ERR]; }
+    k_scatter_force<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->s_fxyzu.p, c->s_dB.p, c->s_divvf.p, c->s_divBsymm.p, c->fxyzu.p,
+                                                          c->dBevol.p, c->divcurlv.p, c->divBsymm.p, c->hp.nvu, p.mhd, p.gravity, p.dust, p.ind_timesteps, p.driving,
+                                                          c->s_poten.p, c->poten.p, c->s_tstop.p, c->tstop.p, c->s_ibinnew.p, c->ibin.p, c->s_wake.p,
+                                                          c->ibin_wake.p);
+    c->launches++;
     sphgpu_scalars &sc = c->last_force;
     memset(&sc, 0, sizeof sc);
     sc.dtcourant = hd[0]; sc.dtforce = hd[1]; sc.dtmini = hd[2]; sc.dtmaxi = hd[3];

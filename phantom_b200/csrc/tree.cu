@@ -113,7 +113,7 @@ __global__ void k_keys(int64_t n, const double *__restrict__ xyzh, double x0, do
 
 __global__ void k_gather_pos(int64_t nlive, const int *__restrict__ perm, const double *__restrict__ xyzh, const int8_t *__restrict__ iphase,
                              double4 *__restrict__ pos4, int8_t *__restrict__ stype, const unsigned long long *__restrict__ keys,
-                             unsigned char *__restrict__ cpl, unsigned long long *cnt)
+                             unsigned char *__restrict__ cpl, unsigned long long *cnt, int boundary_is_gas)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nlive) return;
@@ -121,7 +121,10 @@ __global__ void k_gather_pos(int64_t nlive, const int *__restrict__ perm, const 
     pos4[s] = reinterpret_cast<const double4 *>(xyzh)[i];
     const int8_t ph = iphase[i];
     stype[s] = ph;
-    if (ph != IGAS && ph != -IGAS) cnt[CNT_MULTITYPE] = 1ull;
+    // anything but gas makes the set "multitype" (general kernels); boundary particles of the gas mass behave as gas in every sum
+    // (dens.F90:717-723, force.F90:1539) and differ only in being inactive, which the fast kernels honour through get_partinfo
+    const int ta = ph < 0 ? -ph : ph;
+    if (!(ta == IGAS || (boundary_is_gas && ta == IBOUNDARY))) cnt[CNT_MULTITYPE] = 1ull;
     // common leading bits (of the 63 key bits) with the previous key: 0..63
     unsigned char c = 0;
     if (s > 0) {
@@ -396,7 +399,8 @@ int tree_build(sphgpu_ctx *c)
     c->launches += 8;
     CUDA_TRY(c, c->pos4.ensure(n)); CUDA_TRY(c, c->stype.ensure(n)); CUDA_TRY(c, c->cpl.ensure(n));
     CUDA_TRY(c, c->cellflag.ensure(n)); CUDA_TRY(c, c->cellid_scan.ensure(n));
-    LAUNCH(c, k_gather_pos, nblk(nlive, 256), 256, nlive, c->perm.p, c->xyzh.p, c->iphase.p, c->pos4.p, c->stype.p, c->keys.p, c->cpl.p, c->counters.p);
+    LAUNCH(c, k_gather_pos, nblk(nlive, 256), 256, nlive, c->perm.p, c->xyzh.p, c->iphase.p, c->pos4.p, c->stype.p, c->keys.p, c->cpl.p, c->counters.p,
+           (p.massoftype[IBOUNDARY] == p.massoftype[IGAS]) ? 1 : 0);
     LAUNCH(c, k_cell_flags, nblk(nlive, 128), 128, nlive, c->cpl.p, c->max_leaf, c->cellflag.p);
     tbb = c->cubtemp.cap;
     CUDA_TRY(c, cub::DeviceScan::ExclusiveSum(c->cubtemp.p, tbb, c->cellflag.p, c->cellid_scan.p, (int)nlive, c->stream));

@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Full-size runs of the BASELINE.json configurations on one GPU: device-resident derivs, per-phase times, pair counts.
+usage: tools/run_config.py {shock|turb|mhdblast|orstang|dustydisc|sphere} SIZE [reps]"""
+import json, os, sys, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np
+from phantom_b200 import setups
+from phantom_b200.api import SphGpu
+
+name, size = sys.argv[1], int(float(sys.argv[2]))
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+t0 = time.time()
+if name == "shock":
+    part = setups.setup_shock(nx=size)
+elif name == "turb":
+    part = setups.setup_turb(nx=size)
+elif name == "mhdblast":
+    part = setups.setup_mhdblast(nx=size)
+elif name == "orstang":
+    part = setups.setup_orstang(nx=size)
+elif name == "dustydisc":
+    part = setups.setup_dustydisc(ngas=size, ndust=size // 4)
+    part.params.dtmax = 1.0
+elif name == "sphere":
+    rng = np.random.RandomState(1234)
+    u = rng.uniform(-1, 1, size=(int(size * 2.2), 3)); u = u[np.sum(u * u, axis=1) < 1.0][:size]
+    p = setups.setup_random_sphere(n=1000).params
+    p.massoftype[1] = 1.0 / size
+    xyzh = np.zeros((size, 4)); xyzh[:, :3] = u
+    xyzh[:, 3] = p.hfact * (p.massoftype[1] / (1.0 / (4. / 3. * np.pi))) ** (1. / 3.)
+    part = setups.Particles(p, xyzh); part.vxyzu[:, 3] = 0.05
+else:
+    raise SystemExit(__doc__)
+part.alphaind[:, 0] = 1.0
+tsetup = time.time() - t0
+g = SphGpu(part.params.copy())
+if part.params.ind_timesteps:
+    g.set_timestep_bins(0, 0, 0)
+g.upload(part)
+for r in range(reps):
+    t = time.time(); sc = g.derivs_resident(1); wall = (time.time() - t) * 1e3
+    nact = int(np.sum(part.iphase > 0))
+    print(json.dumps(dict(config=name, npart=part.npart, setup_s=round(tsetup, 1), wall_ms=round(wall, 2), updates_per_s=round(nact / (wall * 1e-3)),
+                          phases=g.timings_ms(), kernels=g.kernel_timings_ms(), gravity=g.gravity_timings_ms() if part.params.gravity else None,
+                          neigh_mean=sc.actualmean, neigh_max=sc.maxactual, its_mean=sc.nrhocalc / max(sc.np, 1), npairs_force=sc.npairs_force,
+                          npairs_gravity=sc.npairs_gravity, nm2l=sc.nm2l, dtcourant=sc.dtcourant, dtforce=sc.dtforce)), flush=True)
