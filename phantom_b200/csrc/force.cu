@@ -561,8 +561,11 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : FORCE_MINB) k_force_f
     }
 }
 
+#ifndef XTRA_MINB
+#define XTRA_MINB 3
+#endif
 template <int K, bool PERIODIC, bool MHD, bool XTRA>
-__global__ void __launch_bounds__(128, XTRA ? 2 : 4) k_force(const ForceArgs a, const __grid_constant__ DevParams dp)
+__global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const ForceArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
     __shared__ WarpShared wsh[4];

@@ -492,3 +492,25 @@ def setup_dustydisc(ngas=8000, ndust=2000, iseed=-43587, r_in=1.0, r_out=150.0, 
     part.fext[:, 0], part.fext[:, 1], part.fext[:, 2] = -xyzh[:, 0] / r3, -xyzh[:, 1] / r3, -z / r3      # central star, M = 1
     part.alphaind[:, 0] = p.alpha
     return part
+
+
+def setup_dustybox(nx=16, idrag=2, isothermal=False, seed=-2468, lattice="random"):
+    """two-fluid dusty box (test_dust.f90-like): 30 % of the particles are dust (type idust) drifting through the gas"""
+    part, _ = setup_test_derivs(nx=nx, lattice=lattice, isothermal=isothermal, dust=1, idrag=idrag)
+    n = part.npart
+    rng = Ran2(seed)
+    isdust = rng.draw(n) < 0.3
+    part.iphase[isdust] = IDUST
+    p = part.params
+    p.massoftype[IDUST] = 0.05 * p.massoftype[IGAS]
+    part.xyzh[isdust, 3] *= (1.0 / 0.3) ** (1. / 3.)        # each phase gets its own smoothing length from its own number density
+    part.xyzh[~isdust, 3] *= (1.0 / 0.7) ** (1. / 3.)
+    part.vxyzu[isdust, :3] *= 0.5                             # relative drift between the phases
+    if idrag == 2:
+        p.K_code = 3.0
+    elif idrag == 3:
+        p.K_code = 0.04
+    else:                                                     # Epstein/Stokes: put the box across the kn = 1 transition
+        p.grainsize, p.graindens, p.seff = 0.02, 30.0, 0.01 * 5.0 * 4. / 9.
+    part.alphaind[:, 0] = 0.2
+    return part, isdust

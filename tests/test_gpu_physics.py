@@ -78,25 +78,7 @@ def test_individual_timestep_bins(istepfrac, icall):
 #  two-fluid dust
 # ------------------------------------------------------------------------------------------------
 def dusty_box(nx=16, idrag=2, isothermal=False, seed=-2468):
-    part, _ = setups.setup_test_derivs(nx=nx, lattice="random", isothermal=isothermal, dust=1, idrag=idrag)
-    n = part.npart
-    rng = setups.Ran2(seed)
-    isdust = rng.draw(n) < 0.3
-    part.iphase[isdust] = IDUST
-    p = part.params
-    p.massoftype[IDUST] = 0.05 * p.massoftype[IGAS]
-    # dust particles need their own smoothing length guess (fewer of them)
-    part.xyzh[isdust, 3] *= (1.0 / 0.3) ** (1. / 3.)
-    part.xyzh[~isdust, 3] *= (1.0 / 0.7) ** (1. / 3.)
-    part.vxyzu[isdust, :3] *= 0.5            # relative drift between the phases
-    if idrag == 2:
-        p.K_code = 3.0
-    elif idrag == 3:
-        p.K_code = 0.04
-    else:                                     # Epstein/Stokes: put the box across the kn = 1 transition
-        p.grainsize, p.graindens, p.seff = 0.02, 30.0, 0.01 * 5.0 * 4. / 9.
-    part.alphaind[:, 0] = 0.2
-    return part, isdust
+    return setups.setup_dustybox(nx=nx, idrag=idrag, isothermal=isothermal, seed=seed)
 
 
 @pytest.mark.parametrize("idrag,isothermal", [(2, False), (3, True), (1, False)])

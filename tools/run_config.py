@@ -21,6 +21,8 @@ elif name == "orstang":
 elif name == "dustydisc":
     part = setups.setup_dustydisc(ngas=size, ndust=size // 4)
     part.params.dtmax = 1.0
+elif name == "dustybox":
+    part, _ = setups.setup_dustybox(nx=size, idrag=2, lattice="cubic")
 elif name == "sphere":
     rng = np.random.RandomState(1234)
     u = rng.uniform(-1, 1, size=(int(size * 2.2), 3)); u = u[np.sum(u * u, axis=1) < 1.0][:size]

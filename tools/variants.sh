@@ -2,18 +2,22 @@
 # A/B builds of the pair kernels with different launch bounds / pairs per trip: builds libsphgpu_<tag>.so variants (CPU side)
 # usage: tools/variants.sh build   |   tools/variants.sh run   (run = on the GPU box: times each variant with bench.py)
 cd "$(dirname "$0")/.."
-VARIANTS=("f5p2d4p3:-DFORCE_MINB=5 -DFORCE_NPAIR=2 -DDENS_MINB=4 -DDENS_NPAIR=3" "r256f6p2d5p2:-DROUND=256 -DFORCE_MINB=6 -DFORCE_NPAIR=2 -DDENS_MINB=5 -DDENS_NPAIR=2" "r256f5p2d4p2:-DROUND=256 -DFORCE_MINB=5 -DFORCE_NPAIR=2 -DDENS_MINB=4 -DDENS_NPAIR=2" "r512f4p2d4p2:-DROUND=512 -DFORCE_MINB=4 -DFORCE_NPAIR=2 -DDENS_MINB=4 -DDENS_NPAIR=2")
+VARIANTS=("x2:-DXTRA_MINB=2" "x3:-DXTRA_MINB=3" "x4:-DXTRA_MINB=4")
 if [ "$1" == "build" ]; then
   mkdir -p build/variants
   for v in "${VARIANTS[@]}"; do
     tag=${v%%:*}; flags=${v#*:}
     ( cd phantom_b200/csrc && for f in force density neigh; do /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -ccbin /usr/bin/g++ -Xcompiler -fPIC,-O2 --expt-relaxed-constexpr $flags -c $f.cu -o ../../build/variants/${f}_$tag.o & done; wait
-      /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -shared -o ../../build/variants/libsphgpu_$tag.so sphgpu.o tree.o ../../build/variants/density_$tag.o ../../build/variants/force_$tag.o cons2prim.o ../../build/variants/neigh_$tag.o halo.o gravity.o )
+      /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -shared -o ../../build/variants/libsphgpu_$tag.so sphgpu.o tree.o ../../build/variants/density_$tag.o ../../build/variants/force_$tag.o cons2prim.o ../../build/variants/neigh_$tag.o halo.o gravity.o step.o )
     echo built $tag
   done
 else
   for v in "${VARIANTS[@]}"; do
     tag=${v%%:*}
+    if [ -n "$VARIANT_CMD" ]; then
+      echo -n "$tag "; SPHGPU_LIB=$PWD/build/variants/libsphgpu_$tag.so $VARIANT_CMD 2>&1 | tail -1 | cut -c1-400
+    else
     SPHGPU_LIB=$PWD/build/variants/libsphgpu_$tag.so python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); p=d['roofline']['passes']; print('$tag', round(d['ms_per_step'],3), 'dens', round(p['density']['ms'],3), 'force', round(p['force']['ms'],3))"
+    fi
   done
 fi
