@@ -303,14 +303,14 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
 // passes ~1% false candidates, so the warp stays converged), one packed 96/128/160-byte record per neighbour instead of five
 // gathers, the minimum-image wrap is skipped for target groups whose search region lies inside the box, and the j-side terms that
 // vanish with grad W_j (q2j >= R^2) are not masked separately.
-template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV>
+template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS>
 #ifndef FORCE_MINB
 #define FORCE_MINB 5
 #endif
 #ifndef FORCE_NPAIR
 #define FORCE_NPAIR 2
 #endif
-__global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : FORCE_MINB) k_force_fast(const ForceArgs a, const __grid_constant__ DevParams dp)
+__global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : (INDTS ? 4 : FORCE_MINB)) k_force_fast(const ForceArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
     __shared__ WarpShared wsh[4];
@@ -324,6 +324,8 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : FORCE_MINB) k_force_f
     const sphgpu_params &p = dp.p;
     unsigned long long st_pairs = 0, st_trial = 0;
     double st_dtc = 1.e29, st_dtf = 1.e29, st_dtmax = 0.;
+    int st_nbinmax = 0, st_ncheckbin = 0;
+    constexpr bool indts = INDTS;                                    // individual timestep bins (force.F90:1346-1358, :3272-3310)
     const float hmax_global = (a.ncells > 1) ? fmaxf(a.nodes[0].hmax[0], a.nodes[0].hmax[1]) : 0.f;
     const double pmass = p.massoftype[IGAS];
     const double beta = p.beta;
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : FORCE_MINB) k_force_f
         double fpot = 0.;
         double fx = 0., fy = 0., fz = 0., drhodt = 0., dudtdiss = 0., dendtdiss = 0., divBsym = 0., dBx = 0., dBy = 0., dBz = 0., divBdiff = 0.;
         double vsigmax = 0.;
-        int npair = 0;
+        int npair = 0, ibin_neigh = 0;
         for (int cellpos = 0; cellpos < ncl;) {                     // rounds of <= ROUND candidates staged in shared memory
             const int nr = stage_round<PERIODIC, true>(ws, clist, ncl, cellpos, a.frec, FSTRIDE, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf);
             nlist += nr;
@@ -402,6 +404,10 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : FORCE_MINB) k_force_f
                 const bool ini = (q2i < KF::radkern2) && notself, inj = (q2j < KF::radkern2) && notself;   // :1287, :1230 (exact membership)
                 const bool isn = ini || inj;
                 npair += isn ? 1 : 0;
+                if (indts && isn && abs((int)a.stype[j]) != IBOUNDARY) {        // j neighbours an active particle: wake flag, Saitoh-Makino input
+                    if (a.s_wake[j] < a.ibinnow_m1) atomicMax(&a.s_wake[j], a.ibinnow_m1);
+                    ibin_neigh = max(ibin_neigh, (int)a.s_ibinold[j]);
+                }
                 const double r2s = isn ? r2 : 1.0;
                 const double rij1 = (r2s > DBL_MIN) ? rsqrt(r2s) : 0.;  // force.F90:1293-1299
                 const double rij = r2s * rij1;
@@ -544,9 +550,28 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : FORCE_MINB) k_force_f
             a.s_divvf[s] = (float)divvi;
             if (MHD) { a.s_dB[s] = dB; a.s_divBsymm[s] = divBsymm4; }
             a.s_done[s] = 2;
-            st_dtc = fmin(st_dtc, dtc);
-            st_dtf = fmin(st_dtf, fmin(dtf, dtclean));
-            st_dtmax = fmax(st_dtmax, dtc);
+            if (indts) {                                             // force.F90:3272-3310 + get_newbin (utils_indtimesteps.f90:230-287)
+                double dti = dtc;
+                const double dtitmp = fmin(dtf, dtclean);
+                if (dtitmp < dti + DBL_MIN && dtitmp < p.dtmax) dti = dtitmp;
+                const int ibin_oldi = (int)a.s_ibin[s];
+                int ibin_newi;
+                if (dti > p.dtmax) ibin_newi = 0;
+                else if (dti < DBL_MIN) ibin_newi = 30;
+                else ibin_newi = max((int)(log(2. * p.dtmax / dti) * 1.4426950408889634 - DBL_EPSILON), 0);
+                int ibini = ibin_oldi;
+                if (ibin_newi > ibin_oldi) ibini = ibin_newi;
+                else if (ibin_newi < ibin_oldi && ibin_oldi <= a.nbinmax && a.icall < 2) {
+                    if (a.istepfrac % (1 << (a.nbinmax - (ibin_oldi - 1))) == 0) ibini = ibini - 1;
+                }
+                ibini = max(ibini, ibin_neigh - 1);                  // Saitoh-Makino limiter
+                a.s_ibinnew[s] = (int8_t)ibini;
+                st_nbinmax = max(st_nbinmax, ibini); st_ncheckbin += 1;
+            } else {
+                st_dtc = fmin(st_dtc, dtc);
+                st_dtf = fmin(st_dtf, fmin(dtf, dtclean));
+                st_dtmax = fmax(st_dtmax, dtc);
+            }
             (void)alphai;
         }
         __syncwarp();
@@ -554,6 +579,11 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : FORCE_MINB) k_force_f
     st_dtc = warp_min(st_dtc); st_dtf = warp_min(st_dtf); st_dtmax = warp_max(st_dtmax);
 #pragma unroll
     for (int sft = 16; sft >= 1; sft >>= 1) { st_pairs += __shfl_xor_sync(FULLMASK, st_pairs, sft); st_trial += __shfl_xor_sync(FULLMASK, st_trial, sft); }
+    if (indts) {
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) { st_nbinmax = max(st_nbinmax, __shfl_xor_sync(FULLMASK, st_nbinmax, sft)); st_ncheckbin += __shfl_xor_sync(FULLMASK, st_ncheckbin, sft); }
+        if (lane == 0 && st_ncheckbin) { atomicMax(&a.cnt[CNT_NBINMAX], (unsigned long long)st_nbinmax); atomicAdd(&a.cnt[CNT_NCHECKBIN], (unsigned long long)st_ncheckbin); }
+    }
     if (lane == 0) {
         atomicAdd(&a.cnt[CNT_NPAIRS], st_pairs); atomicAdd(&a.cnt[CNT_NTRIAL], st_trial);
         atomic_min_pos(&a.dscal[DS_DTCOURANT], st_dtc); atomic_min_pos(&a.dscal[DS_DTFORCE], st_dtf);
@@ -788,24 +818,30 @@ int launch_force_general(sphgpu_ctx *c, const ForceArgs &a, int grid)
     c->launches++;
     return 0;
 }
-template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV>
-int launch_force_fast(sphgpu_ctx *c, const ForceArgs &a, int grid)
+template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS>
+int launch_force_fast2(sphgpu_ctx *c, const ForceArgs &a, int grid)
 {
     if (grid < 0) {
         int bps = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force_fast<K, PERIODIC, MHD, ADIA, GRAV>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS>, 128, 0);
         return bps < 1 ? 1 : bps;
     }
-    k_force_fast<K, PERIODIC, MHD, ADIA, GRAV><<<grid, 128, 0, c->stream>>>(a, c->hp);
+    k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS><<<grid, 128, 0, c->stream>>>(a, c->hp);
     c->launches++;
     return 0;
+}
+template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV>
+int launch_force_fast(sphgpu_ctx *c, const ForceArgs &a, int grid)
+{
+    if (c->hp.p.ind_timesteps) return launch_force_fast2<K, PERIODIC, MHD, ADIA, GRAV, true>(c, a, grid);
+    return launch_force_fast2<K, PERIODIC, MHD, ADIA, GRAV, false>(c, a, grid);
 }
 
 // general path: anything beyond all-gas hydro / MHD (boundary or dust particles, gravity, individual timesteps, disc viscosity)
 bool force_is_general(const sphgpu_ctx *c)
 {
     const sphgpu_params &p = c->hp.p;
-    return p.dust || p.ind_timesteps || p.disc_viscosity || c->multitype || c->force_general;
+    return p.dust || p.disc_viscosity || c->multitype || c->force_general;
 }
 
 template <int K, bool PERIODIC>
