@@ -39,11 +39,18 @@ def launches(csvfile, title, out):
             f.write(f"{k:72s} {cnt[k]:8d} {v / 1e3:12.1f} {100 * v / s:6.1f}%\n")
 
 
+def _raw_rows(rep):
+    """raw-metric table of a capture: from the .raw.csv exported on the GPU box (tools/profile.sh) or from the report itself"""
+    if rep.endswith(".csv"):
+        return list(csv.reader(open(rep)))
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    return list(csv.reader(txt.splitlines()))
+
+
 def traffic_json(rep, out, nparticles):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the pair kernels -> profiles/ncu_traffic.json (read by bench.py)"""
     import json
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(txt.splitlines()))
+    rows = _raw_rows(rep)
     hdr, units = rows[0], rows[1]
     def tobytes(v, u):
         v = float(v)
@@ -61,8 +68,7 @@ def traffic_json(rep, out, nparticles):
 
 
 def raw(rep, title, out, mintime_ms=0.2):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(txt.splitlines()))
+    rows = _raw_rows(rep)
     hdr, units = rows[0], rows[1]
     seen = set()
     with open(out, "w") as f:
@@ -89,8 +95,10 @@ if __name__ == "__main__":
         launches(os.path.join(OUT, "launches.csv"), "ncu launch list: bench.py --steps 2 --warmup 3 (turb 128^3, 1 B200); tools/profile.sh", P("launches_turb128.txt"))
     if os.path.exists(os.path.join(OUT, "launches_grav.csv")):
         launches(os.path.join(OUT, "launches_grav.csv"), "ncu launch list: tools/bench_gravity.py 1e6 2 (self-gravitating sphere, 1M particles, 2 derivs calls)", P("launches_gravity1M.txt"))
-    if os.path.exists(os.path.join(OUT, "prof_pair.ncu-rep")):
-        raw(os.path.join(OUT, "prof_pair.ncu-rep"), "ncu --set full --clock-control none: density / force pair kernels, turb 128^3 (2,097,152 particles, 57 neighbours)", P("pair_kernels_ncu.txt"))
-        traffic_json(os.path.join(OUT, "prof_pair.ncu-rep"), os.path.join(ROOT, "profiles", "ncu_traffic.json"), 128 ** 3)
-    if os.path.exists(os.path.join(OUT, "prof_grav.ncu-rep")):
-        raw(os.path.join(OUT, "prof_grav.ncu-rep"), "ncu --set full --clock-control none: self-gravity kernels, random sphere 1M particles, tree_accuracy 0.5", P("gravity_kernels_ncu.txt"))
+    pair = os.path.join(OUT, "prof_pair.raw.csv") if os.path.exists(os.path.join(OUT, "prof_pair.raw.csv")) else os.path.join(OUT, "prof_pair.ncu-rep")
+    grav = os.path.join(OUT, "prof_grav.raw.csv") if os.path.exists(os.path.join(OUT, "prof_grav.raw.csv")) else os.path.join(OUT, "prof_grav.ncu-rep")
+    if os.path.exists(pair):
+        raw(pair, "ncu --set full --clock-control none: density / force pair kernels, turb 128^3 (2,097,152 particles, 57 neighbours)", P("pair_kernels_ncu.txt"))
+        traffic_json(pair, os.path.join(ROOT, "profiles", "ncu_traffic.json"), 128 ** 3)
+    if os.path.exists(grav):
+        raw(grav, "ncu --set full --clock-control none: self-gravity kernels, random sphere 1M particles, tree_accuracy 0.5", P("gravity_kernels_ncu.txt"))

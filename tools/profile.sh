@@ -11,7 +11,11 @@ ncu --set full --clock-control none --import-source on -k regex:'k_density|k_for
 if [ "$1" == "gravity" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_grav.csv \
     python tools/bench_gravity.py 1e6 2 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'k_g_p2p|k_g_walk|k_force_fast|k_density' -s 30 -c 24 -o gpurun_out/prof_grav -f \
+ncu --set full --clock-control none -k regex:'k_g_p2p|k_g_walk|k_force_fast|k_density' -s 30 -c 24 -o gpurun_out/prof_grav -f \
     python tools/bench_gravity.py 1e6 2 > /dev/null 2>&1
 fi
+# gpurun_out/ is capped at 64 MiB: keep the raw-metric CSVs (read by tools/make_profile_summaries.py), drop the big reports
+for r in prof_pair prof_grav; do [ -f gpurun_out/$r.ncu-rep ] && ncu -i gpurun_out/$r.ncu-rep --page raw --csv > gpurun_out/$r.raw.csv 2>/dev/null; done
+rm -f gpurun_out/prof_grav.ncu-rep
+[ "$KEEP_REP" == "1" ] || rm -f gpurun_out/prof_pair.ncu-rep
 ls -la gpurun_out
