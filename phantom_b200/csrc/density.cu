@@ -37,12 +37,13 @@ enum {  // slots of the per-lane partial sums (order of dens.F90:51-95)
     S_RHO = 0, S_GRADH, S_GRADSOFT, S_DIVV, S_DVXDX, S_DVXDY, S_DVXDZ, S_DVYDX, S_DVYDY, S_DVYDZ, S_DVZDX, S_DVZDY, S_DVZDZ,
     S_DAXDX, S_DAXDY, S_DAXDZ, S_DAYDX, S_DAYDY, S_DAYDZ, S_DAZDX, S_DAZDY, S_DAZDZ, S_RXX, S_RXY, S_RXZ, S_RYY, S_RYZ, S_RZZ, S_RHODUST
 };
-enum { B_DIVB = 0, B_DBXDX, B_DBXDY, B_DBXDZ, B_DBYDX, B_DBYDY, B_DBYDZ, B_DBZDX, B_DBZDY, B_DBZDZ };
+// MHD sums: div B and the three curl B components (the nine dB_a/dx_b sums of dens.F90:806-829 are only ever combined into the curl, :975-989)
+enum { B_DIVB = 0, B_CURLX, B_CURLY, B_CURLZ, B_COUNT };
 
 __global__ void k_gather_dens(int64_t nlive, const int *__restrict__ perm, const double *__restrict__ vxyzu, const double *__restrict__ fxyzu,
                               const double *__restrict__ fext, const double *__restrict__ Bevol, int nvu, int mhd, const double4 *__restrict__ pos4,
                               double4 *__restrict__ vel4, double4 *__restrict__ acc4, double4 *__restrict__ bev4, double *__restrict__ hnew,
-                              int *__restrict__ s_nneigh, double4 *__restrict__ drec)
+                              int *__restrict__ s_nneigh, double4 *__restrict__ drec, double pmass, double hfact)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nlive) return;
@@ -53,7 +54,12 @@ __global__ void k_gather_dens(int64_t nlive, const int *__restrict__ perm, const
     if (drec) {                                                  // packed record of the single-type fast path
         double4 *r = drec + (mhd ? 4 : 3) * (size_t)s;
         r[0] = pos4[s]; r[1] = vv; r[2] = aa;
-        if (mhd) r[3] = reinterpret_cast<const double4 *>(Bevol)[i];
+        if (mhd) {
+            const double4 be = reinterpret_cast<const double4 *>(Bevol)[i];
+            const double rho = rhoh_d(pos4[s].w, pmass, hfact);             // rho_j of dens.F90:810, the same for every pair j enters
+            r[3] = make_double4(be.x * rho, be.y * rho, be.z * rho, be.w);
+            bev4[s] = be;
+        }
     } else {
         vel4[s] = vv; acc4[s] = aa;
         if (mhd) bev4[s] = reinterpret_cast<const double4 *>(Bevol)[i];
@@ -89,7 +95,7 @@ __global__ void k_scatter_dens(int64_t nlive, const int *__restrict__ perm, cons
 // neighbours per trip give the scheduler two independent FP64 dependency chains: the exact reference membership test
 // (dens.F90:675-679, :650) becomes a 0/1 weight on m_j, through which every same-type sum of get_density_sums scales.
 template <int K, bool PERIODIC, bool MHD, bool GRAV>
-__device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[10], int &nneighi, int slot, const int *__restrict__ idxlist, int s,
+__device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[B_COUNT], int &nneighi, int slot, const int *__restrict__ idxlist, int s,
                                           const double4 &pi, double hi, double hi1, double hi21, int itypei, bool gasi, const double4 &vi,
                                           const double4 &ai, const double4 &bi, const DensArgs &a, const DevParams &dp, bool use_da, double Lx, double Ly,
                                           double Lz)
@@ -146,9 +152,9 @@ __device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[10], int 
         const double4 bj = a.bev4[j];
         const double dBx = (bi.x * rhoi - bj.x * rhoj) * g, dBy = (bi.y * rhoi - bj.y * rhoj) * g, dBz = (bi.z * rhoi - bj.z * rhoj) * g;
         w[B_DIVB] += dBx * runix + dBy * runiy + dBz * runiz;
-        w[B_DBXDX] += dBx * runix; w[B_DBXDY] += dBx * runiy; w[B_DBXDZ] += dBx * runiz;
-        w[B_DBYDX] += dBy * runix; w[B_DBYDY] += dBy * runiy; w[B_DBYDZ] += dBy * runiz;
-        w[B_DBZDX] += dBz * runix; w[B_DBZDY] += dBz * runiy; w[B_DBZDZ] += dBz * runiz;
+        w[B_CURLX] += dBz * runiy - dBy * runiz;          // dBz/dy - dBy/dz
+        w[B_CURLY] += dBx * runiz - dBz * runix;          // dBx/dz - dBz/dx
+        w[B_CURLZ] += dBy * runix - dBx * runiy;          // dBy/dx - dBx/dy
     }
     if (dp.p.dust) v[S_RHODUST] += (isn && !same_type && gasi && itypej == IDUST) ? wabi : 0.;
 }
@@ -157,9 +163,9 @@ __device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[10], int 
 // fast path (every particle has the same type and mass, no dust): same sums as dens_pair, but the exact membership test is a
 // real branch, the neighbour comes as one packed record, and the minimum-image wrap is skipped for interior target groups
 template <int K, bool PERIODIC, bool MHD, bool GRAV>
-__device__ __forceinline__ void dens_pair_fast(double (&v)[29], double (&w)[10], int &nneighi, int j, int s, double xi, double yi, double zi, double hi,
+__device__ __forceinline__ void dens_pair_fast(double (&v)[29], double (&w)[B_COUNT], int &nneighi, int j, int s, double xi, double yi, double zi, double hi,
                                                double hi1, double hi21, const double4 &vi, const double4 &ai, const double4 &bi, const double4 *__restrict__ drec,
-                                               double pmass0, double hfact, bool use_da, bool interior, double Lx, double Ly, double Lz)
+                                               double pmass0, bool use_da, bool interior, double Lx, double Ly, double Lz)
 {
     typedef SphKern<K> KF;
     const double4 *rj = drec + (MHD ? 4 : 3) * (size_t)j;
@@ -201,13 +207,12 @@ __device__ __forceinline__ void dens_pair_fast(double (&v)[29], double (&w)[10],
     v[S_RXX] -= dx * runix; v[S_RXY] -= dx * runiy; v[S_RXZ] -= dx * runiz;
     v[S_RYY] -= dy * runiy; v[S_RYZ] -= dy * runiz; v[S_RZZ] -= dz * runiz;
     if (MHD) {
-        const double rhoi = rhoh_d(hi, pmass, hfact), rhoj = rhoh_d(pj.w, pmass, hfact);
-        const double4 bj = rj[3];
-        const double dBx = bi.x * rhoi - bj.x * rhoj, dBy = bi.y * rhoi - bj.y * rhoj, dBz = bi.z * rhoi - bj.z * rhoj;
+        const double4 bj = rj[3];                                             // B_j = (B/rho)_j rho(h_j), formed once per particle by k_gather_dens
+        const double dBx = bi.x - bj.x, dBy = bi.y - bj.y, dBz = bi.z - bj.z;   // bi = (B/rho)_i rho(h_i) of this iteration (dens.F90:806-812)
         w[B_DIVB] += dBx * runix + dBy * runiy + dBz * runiz;
-        w[B_DBXDX] += dBx * runix; w[B_DBXDY] += dBx * runiy; w[B_DBXDZ] += dBx * runiz;
-        w[B_DBYDX] += dBy * runix; w[B_DBYDY] += dBy * runiy; w[B_DBYDZ] += dBy * runiz;
-        w[B_DBZDX] += dBz * runix; w[B_DBZDY] += dBz * runiy; w[B_DBZDZ] += dBz * runiz;
+        w[B_CURLX] += dBz * runiy - dBy * runiz;          // dBz/dy - dBy/dz
+        w[B_CURLY] += dBx * runiz - dBz * runix;          // dBx/dz - dBz/dx
+        w[B_CURLZ] += dBy * runix - dBx * runiy;          // dBy/dx - dBx/dy
     }
 }
 
@@ -222,10 +227,13 @@ template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST>
 #ifndef DENS_MINB
 #define DENS_MINB 4
 #endif
+#ifndef DENS_MHD_MINB
+#define DENS_MHD_MINB 3
+#endif
 #ifndef DENS_NPAIR
 #define DENS_NPAIR 2
 #endif
-__global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density(const DensArgs a, const __grid_constant__ DevParams dp)
+__global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MHD) ? DENS_MHD_MINB : 3)) k_density(const DensArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
     __shared__ WarpShared wsh[4];
@@ -264,7 +272,8 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density
         if (lane < cell.count) get_partinfo_d(a.stype[s], dp.p.set_boundaries_to_active, dp.p.dust, act, gasi, dusti, itypei);
         const double4 pi = a.pos4[s];
         double4 vi, ai, bi = make_double4(0., 0., 0., 0.);
-        if (FAST) { const double4 *r = a.drec + DSTRIDE * (size_t)s; vi = r[1]; ai = r[2]; if (MHD && gasi) bi = r[3]; }
+        double4 bevi = make_double4(0., 0., 0., 0.);            // (B/rho, psi) of the target; the fast pair body takes B = (B/rho) rho(h) of the current iterate
+        if (FAST) { const double4 *r = a.drec + DSTRIDE * (size_t)s; vi = r[1]; ai = r[2]; if (MHD && gasi) bevi = a.bev4[s]; }
         else { vi = a.vel4[s]; ai = a.acc4[s]; if (MHD && gasi) bi = a.bev4[s]; }
         const double pmassi = dp.p.massoftype[itypei];
         const float xif = (float)(pi.x - cx), yif = (float)(pi.y - cy), zif = (float)(pi.z - cz);
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density
         const double h_old = h;
         bool conv = !act;                                            // inactive / boundary lanes take no part (dens.F90:1329)
         bool failed = false;
-        double v[29], w[10];
+        double v[29], w[B_COUNT];
         int nneighi = 0, its_lane = 0, nlist_last = 0;
 
         double hmax_list = cell.hmax * a.margin;
@@ -320,11 +329,12 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density
 #pragma unroll
                 for (int k = 0; k < 29; k++) v[k] = 0.;
 #pragma unroll
-                for (int k = 0; k < 10; k++) w[k] = 0.;
+                for (int k = 0; k < B_COUNT; k++) w[k] = 0.;
                 nneighi = 0;
                 its_lane = its;
             }
             const double hi1 = 1. / h, hi21 = hi1 * hi1;
+            if (FAST && MHD) { const double rhoi = rhoh_d(h, pmassi, dp.p.hfact); bi = make_double4(bevi.x * rhoi, bevi.y * rhoi, bevi.z * rhoi, bevi.w); }
             int nlist = 0;
             for (int cellpos = 0; cellpos < ncl;) {                  // rounds of <= ROUND candidates staged in shared memory
                 const int nr = stage_round<PERIODIC, false>(ws, clist, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf);
@@ -345,12 +355,12 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density
                         const int j2 = (slot2 >= 0) ? idxlist[slot2] : s;
                         st_surv += (slot2 >= 0);
                         dens_pair_fast<K, PERIODIC, MHD, GRAV>(v, w, nneighi, j2, s, pi.x, pi.y, pi.z, h, hi1, hi21, vi, ai, bi, a.drec, pmassi,
-                                                               dp.p.hfact, use_da, interior, Lx, Ly, Lz);
+                                                               use_da, interior, Lx, Ly, Lz);
 #endif
                         dens_pair_fast<K, PERIODIC, MHD, GRAV>(v, w, nneighi, j0, s, pi.x, pi.y, pi.z, h, hi1, hi21, vi, ai, bi, a.drec, pmassi,
-                                                               dp.p.hfact, use_da, interior, Lx, Ly, Lz);
+                                                               use_da, interior, Lx, Ly, Lz);
                         dens_pair_fast<K, PERIODIC, MHD, GRAV>(v, w, nneighi, j1, s, pi.x, pi.y, pi.z, h, hi1, hi21, vi, ai, bi, a.drec, pmassi,
-                                                               dp.p.hfact, use_da, interior, Lx, Ly, Lz);
+                                                               use_da, interior, Lx, Ly, Lz);
                     }
                 } else
                 while (true) {      // two neighbours per trip: independent dependency chains, loads of both in flight
@@ -459,9 +469,9 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : 3) k_density
                 float *o = a.s_divcurlB + 4 * (size_t)s;
                 if (gasi) {
                     o[0] = (float)(-w[B_DIVB] * term);
-                    o[1] = (float)(-(w[B_DBZDY] - w[B_DBYDZ]) * term);
-                    o[2] = (float)(-(w[B_DBXDZ] - w[B_DBZDX]) * term);
-                    o[3] = (float)(-(w[B_DBYDX] - w[B_DBXDY]) * term);
+                    o[1] = (float)(-w[B_CURLX] * term);
+                    o[2] = (float)(-w[B_CURLY] * term);
+                    o[3] = (float)(-w[B_CURLZ] * term);
                 } else { o[0] = o[1] = o[2] = o[3] = 0.f; }
             }
             const int nn = nneighi + 1;   // + self
@@ -552,7 +562,7 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     if (fast) CUDA_TRY(c, c->drec.ensure(4 * (size_t)n));
     CUDA_TRY(c, c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp));
     k_gather_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->vxyzu.p, c->fxyzu.p, c->fext.p, c->Bevol.p, c->hp.nvu, p.mhd, c->pos4.p, c->vel4.p,
-                                                        c->acc4.p, c->bev4.p, c->hnew.p, c->s_nneigh.p, fast ? c->drec.p : nullptr);
+                                                        c->acc4.p, c->bev4.p, c->hnew.p, c->s_nneigh.p, fast ? c->drec.p : nullptr, p.massoftype[IGAS], p.hfact);
     c->launches++;
     a.drec = c->drec.p;
     a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
