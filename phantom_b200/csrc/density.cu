@@ -320,11 +320,9 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                 }
             }
             if (__any_sync(FULLMASK, failed)) break;
-            const float slack = prefilter_slack((float)halfext * 1.0001f + reach);
-            float lim = 0.f;                                         // converged / inactive targets get an empty mask
-            if (!conv) lim = wide ? 3.0e38f : prefilter_limit(__double2float_ru(radkern * h), slack);
-            ws.tgt[lane] = make_float4(xif, yif, zif, lim);
-            __syncwarp();
+            const FilterScale fs = filter_scale((float)halfext, reach);
+            // converged / inactive targets get an empty mask; a wide periodic search switches the filter off
+            const FilterTarget ft = filter_target(fs, xif, yif, zif, conv ? 0.f : (wide ? -1.f : __double2float_ru(radkern * h)));
             if (!conv) {
 #pragma unroll
                 for (int k = 0; k < 29; k++) v[k] = 0.;
@@ -337,10 +335,10 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
             if (FAST && MHD) { const double rhoi = rhoh_d(h, pmassi, dp.p.hfact); bi = make_double4(bevi.x * rhoi, bevi.y * rhoi, bevi.z * rhoi, bevi.w); }
             int nlist = 0;
             for (int cellpos = 0; cellpos < ncl;) {                  // rounds of <= ROUND candidates staged in shared memory
-                const int nr = stage_round<PERIODIC, false>(ws, clist, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf);
+                const int nr = stage_round<PERIODIC, false>(ws, clist, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf, fs);
                 nlist += nr;
                 const int nchunk = (nr + 31) >> 5;
-                build_masks<false>(ws, nr, cell.count, slack);
+                build_masks<false>(ws, nr, ft);
                 int c = -1; unsigned m = 0u;
                 if (FAST) {
                     const int *idxlist = ws.sidx;

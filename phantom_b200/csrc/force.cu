@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : (INDTS ? 4 : FORCE_MI
                                                   fLx, fLy, fLz, ws, clist, a.scratch_per_warp, reach);
         if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
         int nlist = 0;
-        const float slack = prefilter_slack((float)halfext * 1.0001f + reach);
+        const FilterScale fs = filter_scale((float)halfext, reach);
         // ---- lane = target (start_cell, force.F90:2172-2514; per-particle part done by k_force_prep)
         const int s = cell.start + min(lane, cell.count - 1);
         bool act = false;
@@ -369,20 +369,19 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : (INDTS ? 4 : FORCE_MI
         const double h = a.pos4[s].w;
         const double gi = T1.w, pro2i = T2.x, vwavei = T2.y, avwi = T2.z, rho1i = T2.w, pri = T3.x, alphai = T3.w;
         const double hrho1i = -0.5 * rho1i;
-        float lim = 0.f;
-        if (act) lim = wide ? 3.0e38f : prefilter_limit(__double2float_ru(KF::radkern * h), slack);    // force.F90:2255: inactive targets skipped
-        ws.tgt[lane] = make_float4((float)(xi - cx), (float)(yi - cy), (float)(zi - cz), lim);
-        __syncwarp();
+        // force.F90:2255: inactive targets skipped (empty masks); a wide periodic search switches the filter off
+        const FilterTarget ft = filter_target(fs, (float)(xi - cx), (float)(yi - cy), (float)(zi - cz),
+                                              act ? (wide ? -1.f : __double2float_ru(KF::radkern * h)) : 0.f);
         double fpot = 0.;
         double fx = 0., fy = 0., fz = 0., drhodt = 0., dudtdiss = 0., dendtdiss = 0., divBsym = 0., dBx = 0., dBy = 0., dBz = 0., divBdiff = 0.;
         double vsigmax = 0.;
         int npair = 0, ibin_neigh = 0;
         for (int cellpos = 0; cellpos < ncl;) {                     // rounds of <= ROUND candidates staged in shared memory
-            const int nr = stage_round<PERIODIC, true>(ws, clist, ncl, cellpos, a.frec, FSTRIDE, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf);
+            const int nr = stage_round<PERIODIC, true>(ws, clist, ncl, cellpos, a.frec, FSTRIDE, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs);
             nlist += nr;
             const int nchunk = (nr + 31) >> 5;
-            if (wide) build_masks<false>(ws, nr, cell.count, slack);
-            else build_masks<true>(ws, nr, cell.count, slack);
+            if (wide) build_masks<false>(ws, nr, ft);
+            else build_masks<true>(ws, nr, ft);
             const int *idxlist = ws.sidx;
             int c = -1; unsigned m = 0u;
             // two neighbours per trip, branch-free (weights through ini/inj): two independent FP64 dependency chains and both
@@ -631,7 +630,7 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
                                                   fLx, fLy, fLz, ws, clist, a.scratch_per_warp, reach);
         if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
         int nlist = 0;
-        const float slack = prefilter_slack((float)halfext * 1.0001f + reach);
+        const FilterScale fs = filter_scale((float)halfext, reach);
         // ---- lane = target: start_cell (force.F90:2172-2514); the per-particle part was done by k_force_prep
         const int s = cell.start + min(lane, cell.count - 1);
         bool act = false, gasi = true, dusti = false; int itypei = IGAS;
@@ -642,10 +641,9 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
         const double h = pi.w;
         const double2 hv = a.hinv[s];
         const double hi1 = hv.x, hi21 = hv.y;
-        float lim = 0.f;
-        if (act) lim = wide ? 3.0e38f : prefilter_limit(__double2float_ru(KF::radkern * h), slack);    // force.F90:2255: inactive targets skipped
-        ws.tgt[lane] = make_float4((float)(pi.x - cx), (float)(pi.y - cy), (float)(pi.z - cz), lim);
-        __syncwarp();
+        // force.F90:2255: inactive targets skipped (empty masks); a wide periodic search switches the filter off
+        const FilterTarget ft = filter_target(fs, (float)(pi.x - cx), (float)(pi.y - cy), (float)(pi.z - cz),
+                                              act ? (wide ? -1.f : __double2float_ru(KF::radkern * h)) : 0.f);
         double f[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) f[k] = 0.;
@@ -653,11 +651,11 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
         int npair = 0;
         XtraSums xs; xs.fdx = xs.fdy = xs.fdz = 0.; xs.tsmin = 1.e29; xs.ibin_neigh = 0;
         for (int cellpos = 0; cellpos < ncl;) {                     // rounds of <= ROUND candidates staged in shared memory
-            const int nr = stage_round<PERIODIC, false>(ws, clist, ncl, cellpos, a.pos4, 1, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf);
+            const int nr = stage_round<PERIODIC, false>(ws, clist, ncl, cellpos, a.pos4, 1, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs);
             nlist += nr;
             const int nchunk = (nr + 31) >> 5;
-            if (wide) build_masks<false>(ws, nr, cell.count, slack);
-            else build_masks<true>(ws, nr, cell.count, slack);
+            if (wide) build_masks<false>(ws, nr, ft);
+            else build_masks<true>(ws, nr, ft);
             int c = -1; unsigned m = 0u;
             while (true) {      // two neighbours per trip
                 const int slot0 = act ? next_hit(ws, lane, nchunk, c, m) : -1;

@@ -32,10 +32,11 @@ __global__ void __launch_bounds__(128) k_neigh(const TreeNodeF *nodes, const Cel
         const int ncl = warp_walk<SYM, PERIODIC>(nodes, cells, ncells, tlo, thi, __double2float_ru(radkern * cell.hmax), (float)radkern, (float)Lx, (float)Ly,
                                                  (float)Lz, ws, clist, scratch_per_warp, reach);
         if (ncl < 0) { if (lane == 0) atomicMax(&cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+        const FilterScale fs = filter_scale(0.f, reach);     // the FP16 filter words are staged but not used here: every candidate gets the exact test
         int nfound[32];                                      // per target of the cell (max_leaf <= 32), kept across rounds
         for (int t = 0; t < 32; t++) nfound[t] = 0;
         for (int cellpos = 0; cellpos < ncl;) {
-          const int nlist = stage_round<PERIODIC, false>(ws, clist, ncl, cellpos, pos4, 1, cx, cy, cz, Lx, Ly, Lz, (float)radkern, max_leaf);
+          const int nlist = stage_round<PERIODIC, false>(ws, clist, ncl, cellpos, pos4, 1, cx, cy, cz, Lx, Ly, Lz, (float)radkern, max_leaf, fs);
           const int *list = ws.sidx;
           for (int t = 0; t < cell.count; t++) {
             const int s = cell.start + t;

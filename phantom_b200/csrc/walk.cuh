@@ -7,17 +7,19 @@
 //            leaf hits are appended to the group's CELL LIST (one packed int per 8-particle leaf; a few hundred bytes per
 //            group in a per-warp global slice -- the only global scratch the pair kernels touch).
 //   rounds : the candidates are consumed in rounds of <= ROUND particles.  Each round copies the particles of the next
-//            cells ONCE into SHARED memory as float4 {x,y,z relative to the target-group centre (nearest periodic image),
-//            radkern*h_j} + slot index -- the reference's xyzcache (kdtree.F90:1175), but FP32, on chip and only a filter.
-//   masks  : lane = staged candidate, loop over the group's targets (broadcast from shared memory): a conservative
-//            FP32 distance test (error bound derived from the staged extent) + one ballot per target gives, per chunk of
-//            32 candidates, a 32-bit hit mask per target; ~10 instructions per (chunk, target), none on the FP64 pipe.
+//            cells ONCE into SHARED memory as packed FP16 {x,y,z relative to the target-group centre (nearest periodic image)
+//            in units of the staged extent, limit on r^2} + slot index -- the reference's xyzcache (kdtree.F90:1175), but on
+//            chip, two candidates per 16-byte word, and only a filter.
+//   masks  : lane = TARGET (its own scaled position in registers), loop over candidate PAIRS broadcast from shared memory:
+//            a conservative half2 distance test (error bound below) decides two candidates in 9 instructions and ORs the
+//            two result bits into the lane's 32-bit hit mask of the chunk; nothing on the FP64 pipe, no ballots.
 //   pairs  : lane = TARGET.  Every lane walks its own hit masks and evaluates its own neighbours; the pair body
 //            re-evaluates the EXACT reference test in FP64 (non-contracted mul/add in the reference's association
 //            order, dens.F90:671-679 / force.F90:1271-1287) so set membership is bit-identical.  The per-particle
 //            sums stay in the lane's registers: no cross-lane reduction, no queue, no synchronisation in the pair loop.
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 #define WALK_STACK 256
 #ifndef ROUND
@@ -27,11 +29,15 @@
 
 struct WarpShared {
     int stack[WALK_STACK];
-    float4 spos[ROUND];                 // staged candidates: relative position + radkern*h_j (rounded up)
+    uint4 hp[NCHUNK][16];               // staged candidates, two per word: half2 {x, y, z, limit}; slot c*32+b sits in word b&15, half b>>4
     int sidx[ROUND];                    // their sorted particle slots
-    unsigned hm[NCHUNK][32];            // hm[chunk][t] = candidates of the chunk inside target t's (FP32, conservative) radius
-    float4 tgt[32];                     // per target: group-relative position + FP32 limit on r^2
+    unsigned hm[NCHUNK][32];            // hm[chunk][t] = candidates of the chunk inside target t's (FP16, conservative) radius
 };
+
+// Scale of the FP16 filter of one target group: coordinates relative to the group centre times `scale` lie in [-1, 1].
+struct FilterScale { float scale, slack; };
+// The lane's own target: scaled position and limit on the scaled r^2, each duplicated in both halves
+struct FilterTarget { __half2 x, y, z, lim; };
 
 // squared minimum-image gap between two boxes, FP32 (inputs already rounded outward)
 template <bool PERIODIC>
@@ -129,11 +135,43 @@ __device__ int warp_walk(const TreeNodeF *__restrict__ nodes, const Cell *__rest
     return ncl;
 }
 
+// ---- FP16 prefilter -------------------------------------------------------------------------------------------------------
+// Every staged coordinate u = scale*(x - centre) has |u| <= 1 (scale = 1/(halfext + reach), see warp_walk).  Rounding u to FP16 errs
+// by <= 2^-11 |u|, so a coordinate DIFFERENCE of a target (|u_t| <= tau = scale*halfext) and a candidate, rounded once more,
+// errs by <= 2^-11 (|u_t| + |u_c| + |a|) <= 2^-11 (2 tau + 2 rho) whenever the true |a| <= rho, the scaled kernel radius of the
+// pair (rho <= 1).  Over three axes: |r_f - r| <= sqrt(3) 2^-10 (tau + 1) =: slack.  The three half2 roundings of the sum of squares
+// add <= 1.5e-3 relatively.  Hence a true pair (r < rho) always satisfies r_f^2 < (rho + slack)^2 * 1.002, with the limit rounded
+// UP to FP16; flushed subnormals only lower r_f^2.  The filter may pass non-neighbours (about 2 % here); the FP64 test decides.
+__device__ __forceinline__ FilterScale filter_scale(float halfext, float reach)
+{
+    FilterScale fs;
+    const float ext = halfext * 1.0001f + reach + 1e-30f;
+    fs.scale = __frcp_rd(ext);
+    fs.slack = 1.7321f * 9.77e-4f * (halfext * 1.0001f * __frcp_rd(ext) * 1.0001f + 1.f) + 1e-6f;
+    return fs;
+}
+// limit on the scaled, FP16-evaluated r^2 for a kernel radius rc (>= the exact one); rc < 0: pass everything
+__device__ __forceinline__ __half filter_limit(const FilterScale &fs, float rc)
+{
+    if (rc < 0.f) return __ushort_as_half((unsigned short)0x7c00);           // +inf
+    const float r = __fmul_ru(rc, fs.scale * 1.000001f) + fs.slack;
+    return __float2half_ru(r * r * 1.0021f + 1e-7f);
+}
+// rc: kernel radius of the target (rounded up), 0 for a target that takes no part, < 0 to switch the filter off (wide periodic search)
+__device__ __forceinline__ FilterTarget filter_target(const FilterScale &fs, float rx, float ry, float rz, float rc)
+{
+    FilterTarget t;
+    t.x = __float2half2_rn(rx * fs.scale); t.y = __float2half2_rn(ry * fs.scale); t.z = __float2half2_rn(rz * fs.scale);
+    t.lim = __half2half2(rc == 0.f ? __ushort_as_half((unsigned short)0) : filter_limit(fs, rc));
+    return t;
+}
+
 // Copy the particles of the next cells of the list into the shared-memory round buffer: 4 cells per step, 8 lanes per cell.
 // posrec[j * stride] = {x, y, z, w} with w = h (WINV = false) or 1/h (WINV = true).  Returns the number staged; cellpos advances.
 template <bool PERIODIC, bool WINV>
 __device__ __forceinline__ int stage_round(WarpShared &ws, const int *__restrict__ clist, int ncl, int &cellpos, const double4 *__restrict__ posrec, int stride,
-                                           double cx, double cy, double cz, double Lx, double Ly, double Lz, float radkern, int maxleaf)
+                                           double cx, double cy, double cz, double Lx, double Ly, double Lz, float radkern, int maxleaf,
+                                           const FilterScale &fs)
 {
     const int lane = lane_id();
     const int sub = lane >> 3, l8 = lane & 7;
@@ -156,8 +194,13 @@ __device__ __forceinline__ int stage_round(WarpShared &ws, const int *__restrict
             float rkh;
             if (WINV) rkh = __fmul_ru(radkern, __frcp_ru(__double2float_rd(p.w)));   // >= radkern * h_j
             else rkh = __double2float_ru((double)radkern * p.w);
-            ws.spos[off + k] = make_float4((float)rx, (float)ry, (float)rz, rkh);
-            ws.sidx[off + k] = j;
+            // |u| <= 1 by construction; the clamp only keeps a stray value finite (it could not be a neighbour: limits are <= ~1)
+            const float ux = fminf(fmaxf((float)rx * fs.scale, -8.f), 8.f), uy = fminf(fmaxf((float)ry * fs.scale, -8.f), 8.f),
+                        uz = fminf(fmaxf((float)rz * fs.scale, -8.f), 8.f);
+            const int slot = off + k;
+            __half *w = reinterpret_cast<__half *>(&ws.hp[slot >> 5][slot & 15]) + ((slot >> 4) & 1);
+            w[0] = __float2half_rn(ux); w[2] = __float2half_rn(uy); w[4] = __float2half_rn(uz); w[6] = filter_limit(fs, rkh);
+            ws.sidx[slot] = j;
         }
         n += c1 + c2 + c3 + c4;
         cellpos += 4;
@@ -166,33 +209,28 @@ __device__ __forceinline__ int stage_round(WarpShared &ws, const int *__restrict
     return n;
 }
 
-__device__ __forceinline__ float prefilter_slack(float maxrel);
-__device__ __forceinline__ float prefilter_limit(float rc, float slack);
-
-// hit masks for the n staged candidates of the round: lane = candidate, loop over targets
+// hit masks for the n staged candidates of the round: lane = target, loop over candidate pairs.  SYM: a pair passes when it is
+// inside the target's OR the candidate's radius (force pass); targets with limit 0 (inactive, converged) get empty masks.
 template <bool SYM>
-__device__ __forceinline__ void build_masks(WarpShared &ws, int n, int ntargets, float slack)
+__device__ __forceinline__ void build_masks(WarpShared &ws, int n, const FilterTarget &t)
 {
     const int lane = lane_id();
     const int nchunk = (n + 31) >> 5;
+    const bool takes_part = __low2float(t.lim) > 0.f;
     for (int c = 0; c < nchunk; c++) {
-        const int i = c * 32 + lane;
-        const bool valid = i < n;
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) r = ws.spos[i];
-        float limj = 0.f;
-        if (SYM) limj = prefilter_limit(r.w, slack);
         unsigned mine = 0u;
-#pragma unroll 4
-        for (int t = 0; t < ntargets; t++) {
-            const float4 tg = ws.tgt[t];
-            const float ax = tg.x - r.x, ay = tg.y - r.y, az = tg.z - r.z;
-            const float r2 = fmaf(az, az, fmaf(ay, ay, ax * ax));
-            const float lim = SYM ? ((tg.w > 0.f) ? fmaxf(tg.w, limj) : 0.f) : tg.w;
-            const unsigned m = __ballot_sync(FULLMASK, valid && (r2 < lim));
-            if (lane == t) mine = m;
+#pragma unroll
+        for (int p = 0; p < 16; p++) {
+            const uint4 q = ws.hp[c][p];
+            const __half2 ax = __hsub2(t.x, *reinterpret_cast<const __half2 *>(&q.x)), ay = __hsub2(t.y, *reinterpret_cast<const __half2 *>(&q.y)),
+                          az = __hsub2(t.z, *reinterpret_cast<const __half2 *>(&q.z));
+            const __half2 r2 = __hfma2(az, az, __hfma2(ay, ay, __hmul2(ax, ax)));
+            const __half2 lim = SYM ? __hmax2(t.lim, *reinterpret_cast<const __half2 *>(&q.w)) : t.lim;
+            mine |= __hlt2_mask(r2, lim) & (0x00010001u << p);
         }
-        ws.hm[c][lane] = mine;
+        const int left = n - c * 32;                          // slots beyond n hold stale data
+        if (left < 32) mine &= (1u << left) - 1u;
+        ws.hm[c][lane] = takes_part ? mine : 0u;
     }
     __syncwarp();
 }
@@ -224,11 +262,3 @@ __device__ __forceinline__ double pair_r2(double xi, double yi, double zi, const
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-// FP32 prefilter limits.  A staged coordinate differs from the exact relative coordinate by at most 2^-24*maxrel; so does the
-// target's.  |r_f - r| <= sqrt(3)*2*2^-24*maxrel =: e.  For a true pair r < rc  =>  r_f^2 < (rc + e)^2 (1 + 4 ulp).
-__device__ __forceinline__ float prefilter_slack(float maxrel) { return 2.1e-7f * maxrel + 1e-30f; }
-__device__ __forceinline__ float prefilter_limit(float rc, float slack)
-{
-    const float r = rc + slack;
-    return r * r * 1.000002f;
-}
