@@ -160,59 +160,79 @@ __device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[B_COUNT],
 }
 
 
-// fast path (every particle has the same type and mass, no dust): same sums as dens_pair, but the exact membership test is a
-// real branch, the neighbour comes as one packed record, and the minimum-image wrap is skipped for interior target groups
+// fast path (every particle has the same type and mass, no dust): same sums as dens_pair for TWO neighbours of the lane at once,
+// written phase by phase over both so that two independent FP64 dependency chains are in flight.  No branches: the kernel is
+// evaluated as truncated powers, a non-member (exact test fails, j == s, or the padding of an odd hit count) enters with weight 0
+// on m_j, through which every sum scales, and r = 0 gives 1/r := 0 (rsqrt_pos).  The neighbour comes as one packed record; the
+// minimum-image wrap is skipped for interior target groups.
 template <int K, bool PERIODIC, bool MHD, bool GRAV>
-__device__ __forceinline__ void dens_pair_fast(double (&v)[29], double (&w)[B_COUNT], int &nneighi, int j, int s, double xi, double yi, double zi, double hi,
-                                               double hi1, double hi21, const double4 &vi, const double4 &ai, const double4 &bi, const double4 *__restrict__ drec,
-                                               double pmass0, bool use_da, bool interior, double Lx, double Ly, double Lz)
+__device__ __forceinline__ void dens_pair2_fast(double (&v)[29], double (&w)[B_COUNT], int &nneighi, int j0, int j1, int s, double xi, double yi, double zi,
+                                                double hi1, double hi21, const double4 &vi, const double4 &ai, const double4 &bi,
+                                                const double4 *__restrict__ drec, double pmass0, bool use_da, bool interior, double Lx, double Ly, double Lz)
 {
     typedef SphKern<K> KF;
-    const double4 *rj = drec + (MHD ? 4 : 3) * (size_t)j;
-    const double4 pj = rj[0];
-    const double4 vj = rj[1];
-    double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
+    const int jj[2] = {j0, j1};
+    double4 pj[2], vj[2], aj[2], bj[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const double4 *rj = drec + (MHD ? 4 : 3) * (size_t)jj[k];
+        pj[k] = rj[0]; vj[k] = rj[1]; aj[k] = rj[2];
+        if (MHD) bj[k] = rj[3];                                              // B_j = (B/rho)_j rho(h_j), formed once per particle by k_gather_dens
+    }
+    double dx[2], dy[2], dz[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) { dx[k] = xi - pj[k].x; dy[k] = yi - pj[k].y; dz[k] = zi - pj[k].z; }
     if (PERIODIC && !interior) {                                              // dens.F90:666-670
-        if (fabs(dx) > 0.5 * Lx) dx = dx - copysign(Lx, dx);
-        if (fabs(dy) > 0.5 * Ly) dy = dy - copysign(Ly, dy);
-        if (fabs(dz) > 0.5 * Lz) dz = dz - copysign(Lz, dz);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (fabs(dx[k]) > 0.5 * Lx) dx[k] = dx[k] - copysign(Lx, dx[k]);
+            if (fabs(dy[k]) > 0.5 * Ly) dy[k] = dy[k] - copysign(Ly, dy[k]);
+            if (fabs(dz[k]) > 0.5 * Lz) dz[k] = dz[k] - copysign(Lz, dz[k]);
+        }
     }
-    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    const double q2i = __dmul_rn(r2, hi21);                                   // dens.F90:675
-    const bool isn = (q2i < KF::radkern2) && (j != s);                        // :679, :650 (exact membership) -> 0/1 weight on m_j
-    const double pmass = isn ? pmass0 : 0.;
-    const double r2s = isn ? r2 : 1.0;
-    const double rinv = (r2s > 0.) ? rsqrt(r2s) : 0.;
-    const double qi = (r2s * rinv) * hi1;
-    double wabi, grkerni;
-    KF::get_kernel(isn ? q2i : 1.0, qi, wabi, grkerni);
-    nneighi += isn ? 1 : 0;
-    v[S_RHO] += wabi * pmass;
-    v[S_GRADH] += (-qi * grkerni - 3. * wabi) * pmass;
-    if (GRAV) v[S_GRADSOFT] += KF::dphidh(isn ? q2i : 1.0, qi) * pmass;
-    const double g = (rinv - DBL_EPSILON * rinv * rinv) * grkerni * pmass;     // rij1 = 1/(rij + epsilon) (dens.F90:746), times grkern m_j
-    const double runix = dx * g, runiy = dy * g, runiz = dz * g;
-    const double dvx = vi.x - vj.x, dvy = vi.y - vj.y, dvz = vi.z - vj.z;
-    v[S_DIVV] += dvx * runix + dvy * runiy + dvz * runiz;
-    v[S_DVXDX] += dvx * runix; v[S_DVXDY] += dvx * runiy; v[S_DVXDZ] += dvx * runiz;
-    v[S_DVYDX] += dvy * runix; v[S_DVYDY] += dvy * runiy; v[S_DVYDZ] += dvy * runiz;
-    v[S_DVZDX] += dvz * runix; v[S_DVZDY] += dvz * runiy; v[S_DVZDZ] += dvz * runiz;
-    if (use_da) {
-        const double4 aj = rj[2];
-        const double dax = ai.x - aj.x, day = ai.y - aj.y, daz = ai.z - aj.z;
-        v[S_DAXDX] += dax * runix; v[S_DAXDY] += dax * runiy; v[S_DAXDZ] += dax * runiz;
-        v[S_DAYDX] += day * runix; v[S_DAYDY] += day * runiy; v[S_DAYDZ] += day * runiz;
-        v[S_DAZDX] += daz * runix; v[S_DAZDY] += daz * runiy; v[S_DAZDZ] += daz * runiz;
+    double r2[2], q2i[2], pmass[2], rinv[2], qi[2], wabi[2], grkerni[2], g[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        r2[k] = __dadd_rn(__dadd_rn(__dmul_rn(dx[k], dx[k]), __dmul_rn(dy[k], dy[k])), __dmul_rn(dz[k], dz[k]));
+        q2i[k] = __dmul_rn(r2[k], hi21);                                      // dens.F90:675
+        const bool isn = (q2i[k] < KF::radkern2) && (jj[k] != s);             // :679, :650 (exact membership) -> 0/1 weight on m_j
+        pmass[k] = isn ? pmass0 : 0.;
+        nneighi += isn ? 1 : 0;
     }
-    v[S_RXX] -= dx * runix; v[S_RXY] -= dx * runiy; v[S_RXZ] -= dx * runiz;
-    v[S_RYY] -= dy * runiy; v[S_RYZ] -= dy * runiz; v[S_RZZ] -= dz * runiz;
-    if (MHD) {
-        const double4 bj = rj[3];                                             // B_j = (B/rho)_j rho(h_j), formed once per particle by k_gather_dens
-        const double dBx = bi.x - bj.x, dBy = bi.y - bj.y, dBz = bi.z - bj.z;   // bi = (B/rho)_i rho(h_i) of this iteration (dens.F90:806-812)
-        w[B_DIVB] += dBx * runix + dBy * runiy + dBz * runiz;
-        w[B_CURLX] += dBz * runiy - dBy * runiz;          // dBz/dy - dBy/dz
-        w[B_CURLY] += dBx * runiz - dBz * runix;          // dBx/dz - dBz/dx
-        w[B_CURLZ] += dBy * runix - dBx * runiy;          // dBy/dx - dBx/dy
+#pragma unroll
+    for (int k = 0; k < 2; k++) rinv[k] = rsqrt_pos(r2[k]);
+#pragma unroll
+    for (int k = 0; k < 2; k++) { qi[k] = (r2[k] * rinv[k]) * hi1; KF::get_kernel_bf(qi[k], wabi[k], grkerni[k]); }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        v[S_RHO] += wabi[k] * pmass[k];
+        v[S_GRADH] += (-qi[k] * grkerni[k] - 3. * wabi[k]) * pmass[k];
+        if (GRAV) v[S_GRADSOFT] += KF::dphidh(fmin(q2i[k], KF::radkern2), fmin(qi[k], KF::radkern)) * pmass[k];
+        g[k] = fma(-DBL_EPSILON * rinv[k], rinv[k], rinv[k]) * (grkerni[k] * pmass[k]);   // rij1 = 1/(rij + epsilon) (dens.F90:746), times grkern m_j
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const double runix = dx[k] * g[k], runiy = dy[k] * g[k], runiz = dz[k] * g[k];
+        const double dvx = vi.x - vj[k].x, dvy = vi.y - vj[k].y, dvz = vi.z - vj[k].z;
+        v[S_DIVV] += dvx * runix + dvy * runiy + dvz * runiz;
+        v[S_DVXDX] += dvx * runix; v[S_DVXDY] += dvx * runiy; v[S_DVXDZ] += dvx * runiz;
+        v[S_DVYDX] += dvy * runix; v[S_DVYDY] += dvy * runiy; v[S_DVYDZ] += dvy * runiz;
+        v[S_DVZDX] += dvz * runix; v[S_DVZDY] += dvz * runiy; v[S_DVZDZ] += dvz * runiz;
+        if (use_da) {
+            const double dax = ai.x - aj[k].x, day = ai.y - aj[k].y, daz = ai.z - aj[k].z;
+            v[S_DAXDX] += dax * runix; v[S_DAXDY] += dax * runiy; v[S_DAXDZ] += dax * runiz;
+            v[S_DAYDX] += day * runix; v[S_DAYDY] += day * runiy; v[S_DAYDZ] += day * runiz;
+            v[S_DAZDX] += daz * runix; v[S_DAZDY] += daz * runiy; v[S_DAZDZ] += daz * runiz;
+        }
+        v[S_RXX] -= dx[k] * runix; v[S_RXY] -= dx[k] * runiy; v[S_RXZ] -= dx[k] * runiz;
+        v[S_RYY] -= dy[k] * runiy; v[S_RYZ] -= dy[k] * runiz; v[S_RZZ] -= dz[k] * runiz;
+        if (MHD) {
+            const double dBx = bi.x - bj[k].x, dBy = bi.y - bj[k].y, dBz = bi.z - bj[k].z;   // bi = (B/rho)_i rho(h_i) of this iteration (dens.F90:806-812)
+            w[B_DIVB] += dBx * runix + dBy * runiy + dBz * runiz;
+            w[B_CURLX] += dBz * runiy - dBy * runiz;          // dBz/dy - dBy/dz
+            w[B_CURLY] += dBx * runiz - dBz * runix;          // dBx/dz - dBz/dx
+            w[B_CURLZ] += dBy * runix - dBx * runiy;          // dBy/dx - dBx/dy
+        }
     }
 }
 
@@ -225,7 +245,7 @@ __device__ __forceinline__ void exactlinear_d(double &gx, double &gy, double &gz
 
 template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST>
 #ifndef DENS_MINB
-#define DENS_MINB 4
+#define DENS_MINB 3
 #endif
 #ifndef DENS_MHD_MINB
 #define DENS_MHD_MINB 3
@@ -239,6 +259,8 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
     __shared__ WarpShared wsh[4];
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     WarpShared &ws = wsh[wib];
+    const unsigned ws_s = ws_shared_addr(ws);
+    const unsigned hm_lane = ws_s + (unsigned)offsetof(WarpShared, hm) + 4u * lane, sidx_s = ws_s + (unsigned)offsetof(WarpShared, sidx);
     const int gwarp = blockIdx.x * 4 + wib;
     int *clist = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;      // cell list of the current group (the only global scratch)
     constexpr int DSTRIDE = MHD ? 4 : 3;                                 // double4 per packed record of the fast path
@@ -341,25 +363,17 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                 build_masks<false>(ws, nr, ft);
                 int c = -1; unsigned m = 0u;
                 if (FAST) {
-                    const int *idxlist = ws.sidx;
-                    while (true) {      // two neighbours per trip: independent dependency chains, both records in flight
-                        const int slot0 = conv ? -1 : next_hit(ws, lane, nchunk, c, m);
+                    int surv = 0;
+                    while (true) {      // two neighbours per trip; a lane with an odd number of hits pads with itself (weight 0)
+                        const int slot0 = conv ? -1 : next_hit_s(hm_lane, nchunk, c, m);
                         if (slot0 < 0) break;
-                        const int slot1 = next_hit(ws, lane, nchunk, c, m);
-                        const int j0 = idxlist[slot0], j1 = (slot1 >= 0) ? idxlist[slot1] : s;
-                        st_surv += 1 + (slot1 >= 0);
-#if DENS_NPAIR >= 3
-                        const int slot2 = (slot1 >= 0) ? next_hit(ws, lane, nchunk, c, m) : -1;
-                        const int j2 = (slot2 >= 0) ? idxlist[slot2] : s;
-                        st_surv += (slot2 >= 0);
-                        dens_pair_fast<K, PERIODIC, MHD, GRAV>(v, w, nneighi, j2, s, pi.x, pi.y, pi.z, h, hi1, hi21, vi, ai, bi, a.drec, pmassi,
-                                                               use_da, interior, Lx, Ly, Lz);
-#endif
-                        dens_pair_fast<K, PERIODIC, MHD, GRAV>(v, w, nneighi, j0, s, pi.x, pi.y, pi.z, h, hi1, hi21, vi, ai, bi, a.drec, pmassi,
-                                                               use_da, interior, Lx, Ly, Lz);
-                        dens_pair_fast<K, PERIODIC, MHD, GRAV>(v, w, nneighi, j1, s, pi.x, pi.y, pi.z, h, hi1, hi21, vi, ai, bi, a.drec, pmassi,
-                                                               use_da, interior, Lx, Ly, Lz);
+                        const int slot1 = next_hit_s(hm_lane, nchunk, c, m);
+                        const int j0 = (int)lds_u32(sidx_s + 4u * (unsigned)slot0), j1 = (slot1 >= 0) ? (int)lds_u32(sidx_s + 4u * (unsigned)slot1) : s;
+                        surv += 1 + (slot1 >= 0);
+                        dens_pair2_fast<K, PERIODIC, MHD, GRAV>(v, w, nneighi, j0, j1, s, pi.x, pi.y, pi.z, hi1, hi21, vi, ai, bi, a.drec, pmassi, use_da,
+                                                                interior, Lx, Ly, Lz);
                     }
+                    st_surv += surv;
                 } else
                 while (true) {      // two neighbours per trip: independent dependency chains, loads of both in flight
                     const int slot0 = conv ? -1 : next_hit(ws, lane, nchunk, c, m);

@@ -299,13 +299,12 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
 
 
 // ---- fast path: every particle is gas, no gravity / dust / individual timesteps / disc viscosity ---------------------------------
-// Same sums as force_pair above, restructured for instruction count: the exact membership test is a real branch (the FP32 prefilter
-// passes ~1% false candidates, so the warp stays converged), one packed 96/128/160-byte record per neighbour instead of five
-// gathers, the minimum-image wrap is skipped for target groups whose search region lies inside the box, and the j-side terms that
-// vanish with grad W_j (q2j >= R^2) are not masked separately.
+// Same sums as force_pair above, restructured for instruction count: one packed 96/128/160-byte record per neighbour instead of
+// five gathers, the minimum-image wrap is skipped for target groups whose search region lies inside the box, and terms that vanish
+// with grad W (q2 >= R^2) are not masked separately.
 template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS>
 #ifndef FORCE_MINB
-#define FORCE_MINB 5
+#define FORCE_MINB 4
 #endif
 #ifndef FORCE_NPAIR
 #define FORCE_NPAIR 2
@@ -316,6 +315,8 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : (INDTS ? 4 : FORCE_MI
     __shared__ WarpShared wsh[4];
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     WarpShared &ws = wsh[wib];
+    const unsigned ws_s = ws_shared_addr(ws);
+    const unsigned hm_lane = ws_s + (unsigned)offsetof(WarpShared, hm) + 4u * lane, sidx_s = ws_s + (unsigned)offsetof(WarpShared, sidx);
     const int gwarp = blockIdx.x * 4 + wib;
     int *clist = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;      // cell list of the current group (the only global scratch)
     const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
@@ -382,115 +383,125 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : (INDTS ? 4 : FORCE_MI
             const int nchunk = (nr + 31) >> 5;
             if (wide) build_masks<false>(ws, nr, ft);
             else build_masks<true>(ws, nr, ft);
-            const int *idxlist = ws.sidx;
             int c = -1; unsigned m = 0u;
-            // two neighbours per trip, branch-free (weights through ini/inj): two independent FP64 dependency chains and both
-            // records in flight; a lane that has run out of hits evaluates itself (j == s), which every weight zeroes
-            auto pair = [&](int slot) {
-                const int j = (slot >= 0) ? idxlist[slot] : s;
-                const double4 *rj = a.frec + FSTRIDE * (size_t)j;
-                const double4 R0 = rj[0], R1 = rj[1], R2 = rj[2];
-                double dx = xi - R0.x, dy = yi - R0.y, dz = zi - R0.z;
+            // Two neighbours per trip, written phase by phase over both so that two independent FP64 dependency chains and both
+            // records are in flight.  No branches: grad W is evaluated as truncated powers (zero beyond the support), r = 0 gives
+            // 1/r := 0, so a non-member (exact test fails, j == s, or the self padding of an odd hit count) adds exact zeros;
+            // only the pair count, the signal-speed maximum and the softened gravity need the membership flags.
+            auto pair2 = [&](int j0, int j1) {
+                const int jj[2] = {j0, j1};
+                double4 R0[2], R1[2], R2[2], R3[2], E[2];
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const double4 *rj = a.frec + FSTRIDE * (size_t)jj[k];
+                    R0[k] = rj[0]; R1[k] = rj[1]; R2[k] = rj[2];
+                    if (ADIA || GRAV) R3[k] = rj[3];
+                    if (MHD) E[k] = rj[4];
+                }
+                double dx[2], dy[2], dz[2];
+#pragma unroll
+                for (int k = 0; k < 2; k++) { dx[k] = xi - R0[k].x; dy[k] = yi - R0[k].y; dz[k] = zi - R0[k].z; }
                 if (PERIODIC && !interior) {                            // force.F90:1266-1270
-                    if (fabs(dx) > 0.5 * Lx) dx = dx - copysign(Lx, dx);
-                    if (fabs(dy) > 0.5 * Ly) dy = dy - copysign(Ly, dy);
-                    if (fabs(dz) > 0.5 * Lz) dz = dz - copysign(Lz, dz);
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        if (fabs(dx[k]) > 0.5 * Lx) dx[k] = dx[k] - copysign(Lx, dx[k]);
+                        if (fabs(dy[k]) > 0.5 * Ly) dy[k] = dy[k] - copysign(Ly, dy[k]);
+                        if (fabs(dz[k]) > 0.5 * Lz) dz[k] = dz[k] - copysign(Lz, dz[k]);
+                    }
                 }
-                const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                const double hj1 = R0.w;
-                const double q2i = __dmul_rn(r2, hi21), q2j = __dmul_rn(r2, __dmul_rn(hj1, hj1));         // force.F90:1272, :1285
-                const bool notself = (j != s);
-                const bool ini = (q2i < KF::radkern2) && notself, inj = (q2j < KF::radkern2) && notself;   // :1287, :1230 (exact membership)
-                const bool isn = ini || inj;
-                npair += isn ? 1 : 0;
-                if (indts && isn && abs((int)a.stype[j]) != IBOUNDARY) {        // j neighbours an active particle: wake flag, Saitoh-Makino input
-                    if (a.s_wake[j] < a.ibinnow_m1) atomicMax(&a.s_wake[j], a.ibinnow_m1);
-                    ibin_neigh = max(ibin_neigh, (int)a.s_ibinold[j]);
+                double r2[2], rij1[2], grkerni[2], grkernj[2];
+                bool ini[2], inj[2], isn[2];
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    r2[k] = __dadd_rn(__dadd_rn(__dmul_rn(dx[k], dx[k]), __dmul_rn(dy[k], dy[k])), __dmul_rn(dz[k], dz[k]));
+                    const double hj1 = R0[k].w;
+                    const double q2i = __dmul_rn(r2[k], hi21), q2j = __dmul_rn(r2[k], __dmul_rn(hj1, hj1));       // force.F90:1272, :1285
+                    const bool notself = (jj[k] != s);
+                    ini[k] = (q2i < KF::radkern2) && notself; inj[k] = (q2j < KF::radkern2) && notself;          // :1287, :1230 (exact membership)
+                    isn[k] = ini[k] || inj[k];
+                    npair += isn[k] ? 1 : 0;
+                    if (indts && isn[k] && abs((int)a.stype[jj[k]]) != IBOUNDARY) {   // j neighbours an active particle: wake flag, Saitoh-Makino input
+                        if (a.s_wake[jj[k]] < a.ibinnow_m1) atomicMax(&a.s_wake[jj[k]], a.ibinnow_m1);
+                        ibin_neigh = max(ibin_neigh, (int)a.s_ibinold[jj[k]]);
+                    }
                 }
-                const double r2s = isn ? r2 : 1.0;
-                const double rij1 = (r2s > DBL_MIN) ? rsqrt(r2s) : 0.;  // force.F90:1293-1299
-                const double rij = r2s * rij1;
-                const double grkerni = ini ? KF::grkern(q2i, rij * hi1) * gi : 0.;      // :1301-1302
-                const double grkernj = inj ? KF::grkern(q2j, rij * hj1) * R1.w : 0.;    // :1325-1327
-                const double runix = dx * rij1, runiy = dy * rij1, runiz = dz * rij1;
-                double fgrav = 0.;
-                if (GRAV) {                                            // softened gravity of SPH-neighbour pairs, force.F90:1303-1339, :1522
-                    const double4 G3 = rj[3];
-                    double phii = -rij1, fgravi = rij1 * rij1, fgravj = fgravi;
-                    if (ini) { double fmi; KF::softening(q2i, rij * hi1, phii, fmi); phii *= hi1; fgravi = fmi * hi21 + T3.z * grkerni; }
-                    if (inj) { double phij, fmj; KF::softening(q2j, rij * hj1, phij, fmj); fgravj = fmj * (hj1 * hj1) + G3.z * grkernj; }
-                    fgrav = isn ? 0.5 * pmass * (fgravi + fgravj) : 0.;
-                    fpot += isn ? pmass * phii : 0.;
+#pragma unroll
+                for (int k = 0; k < 2; k++) rij1[k] = rsqrt_pos(r2[k]);                 // force.F90:1293-1299
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const double rij = r2[k] * rij1[k];
+                    grkerni[k] = KF::grkern_bf(rij * hi1) * gi;                          // :1301-1302
+                    grkernj[k] = KF::grkern_bf(rij * R0[k].w) * R1[k].w;                 // :1325-1327
                 }
-                const double dvx = T1.x - R1.x, dvy = T1.y - R1.y, dvz = T1.z - R1.z;
-                const double projv = dvx * runix + dvy * runiy + dvz * runiz;
-                const double bp = beta * projv;
-                const double vwavej = R2.y;
-                // :1423-1426, :1501-1504: vsigmax >= 0 makes the clip at 0 implicit; j-side only when its terms are used (:1343-1345)
-                double vs = vwavei - bp;
-                if (USEJ || inj) vs = dmax(vs, vwavej - bp);
-                vsigmax = dmax(vsigmax, isn ? vs : 0.);
-                const double ap = (projv < 0.) ? projv : 0.;          // force.F90:1581-1592: approaching pairs only
-                const double qrho2i = hrho1i * dmax(avwi - bp, 0.) * ap;
-                const double rho1j = R2.w;
-                const double qrho2j = (-0.5 * rho1j) * dmax(R2.z - bp, 0.) * ap;
-                const double gradp = pmass * ((pro2i + qrho2i) * grkerni + (R2.x + qrho2j) * grkernj);
-                double projsx = 0., projsy = 0., projsz = 0.;
-                if (ADIA) {                                            // artificial conductivity, force.F90:1606-1624
-                    const double4 R3 = rj[3];
-                    const double denij = T3.y - R3.y;
-                    const double vsigu = GRAV ? fabs(projv) : sqrt(fabs(pri - R3.x) * (2. * rho1i * rho1j / (rho1i + rho1j)));
-                    const double auterm = 0.5 * pmass * rho1i * p.alphau, autermj = 0.5 * pmass * rho1j * p.alphau;
-                    dendtdiss += vsigu * denij * (auterm * grkerni + autermj * grkernj);
-                    dudtdiss += pmass * qrho2i * projv * grkerni;
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const double runix = dx[k] * rij1[k], runiy = dy[k] * rij1[k], runiz = dz[k] * rij1[k];
+                    double fgrav = 0.;
+                    if (GRAV) {                                            // softened gravity of SPH-neighbour pairs, force.F90:1303-1339, :1522
+                        const double hj1 = R0[k].w, rij = r2[k] * rij1[k];
+                        const double q2i = __dmul_rn(r2[k], hi21), q2j = __dmul_rn(r2[k], __dmul_rn(hj1, hj1));
+                        double phii = -rij1[k], fgravi = rij1[k] * rij1[k], fgravj = fgravi;
+                        if (ini[k]) { double fmi; KF::softening(q2i, rij * hi1, phii, fmi); phii *= hi1; fgravi = fmi * hi21 + T3.z * grkerni[k]; }
+                        if (inj[k]) { double phij, fmj; KF::softening(q2j, rij * hj1, phij, fmj); fgravj = fmj * (hj1 * hj1) + R3[k].z * grkernj[k]; }
+                        fgrav = isn[k] ? 0.5 * pmass * (fgravi + fgravj) : 0.;
+                        fpot += isn[k] ? pmass * phii : 0.;
+                    }
+                    const double dvx = T1.x - R1[k].x, dvy = T1.y - R1[k].y, dvz = T1.z - R1[k].z;
+                    const double projv = dvx * runix + dvy * runiy + dvz * runiz;
+                    const double bp = beta * projv;
+                    const double vwavej = R2[k].y;
+                    // :1423-1426, :1501-1504: vsigmax >= 0 makes the clip at 0 implicit; j-side only when its terms are used (:1343-1345)
+                    double vs = vwavei - bp;
+                    if (USEJ || inj[k]) vs = dmax(vs, vwavej - bp);
+                    vsigmax = dmax(vsigmax, isn[k] ? vs : 0.);
+                    const double ap = (projv < 0.) ? projv : 0.;          // force.F90:1581-1592: approaching pairs only
+                    const double qrho2i = hrho1i * dmax(avwi - bp, 0.) * ap;
+                    const double rho1j = R2[k].w;
+                    const double qrho2j = (-0.5 * rho1j) * dmax(R2[k].z - bp, 0.) * ap;
+                    const double gradp = pmass * ((pro2i + qrho2i) * grkerni[k] + (R2[k].x + qrho2j) * grkernj[k]);
+                    double projsx = 0., projsy = 0., projsz = 0.;
+                    if (ADIA) {                                            // artificial conductivity, force.F90:1606-1624
+                        const double denij = T3.y - R3[k].y;
+                        const double vsigu = GRAV ? fabs(projv) : sqrt(fabs(pri - R3[k].x) * (2. * rho1i * rho1j / (rho1i + rho1j)));
+                        const double auterm = 0.5 * pmass * rho1i * p.alphau, autermj = 0.5 * pmass * rho1j * p.alphau;
+                        dendtdiss += vsigu * denij * (auterm * grkerni[k] + autermj * grkernj[k]);
+                        dudtdiss += pmass * qrho2i * projv * grkerni[k];
+                    }
+                    if (MHD) {                                             // force.F90:1428-1444, :1626-1684, :2132-2150
+                        const double Bxi = T4.x, Byi = T4.y, Bzi = T4.z, psii = T4.w;
+                        const double dBxx = Bxi - E[k].x, dByy = Byi - E[k].y, dBzz = Bzi - E[k].z;
+                        const double projBi = Bxi * runix + Byi * runiy + Bzi * runiz;
+                        const double projBj = E[k].x * runix + E[k].y * runiy + E[k].z * runiz;
+                        const double projdB = dBxx * runix + dByy * runiy + dBzz * runiz;
+                        divBdiff += -pmass * projdB * grkerni[k];
+                        const double rho21i = rho1i * rho1i, rho21j = rho1j * rho1j;
+                        const double avBterm = 0.5 * pmass * rho1i * p.alphaB * rho1i, avBtermj = 0.5 * pmass * rho1j * p.alphaB * rho1j;
+                        const double tx = dvx - projv * runix, ty = dvy - projv * runiy, tz = dvz - projv * runiz;
+                        const double vsigB = sqrt(tx * tx + ty * ty + tz * tz);
+                        const double dBdissterm = (avBterm * grkerni[k] + avBtermj * grkernj[k]) * vsigB;
+                        if (ADIA && p.iresistive_heating > 0) dudtdiss += -0.5 * (dBxx * dBxx + dByy * dByy + dBzz * dBzz) * dBdissterm;
+                        const double pmjrho21grkerni = pmass * rho21i * grkerni[k], pmjrho21grkernj = pmass * rho21j * grkernj[k];
+                        const double termi = pmjrho21grkerni * projBi;
+                        divBsym += termi + pmjrho21grkernj * projBj;
+                        const double dpsiterm = p.overcleanfac * (pmjrho21grkerni * psii * vwavei + pmjrho21grkernj * E[k].w * vwavej);
+                        dBx += -termi * dvx + dBdissterm * dBxx - dpsiterm * runix;
+                        dBy += -termi * dvy + dBdissterm * dByy - dpsiterm * runiy;
+                        dBz += -termi * dvz + dBdissterm * dBzz - dpsiterm * runiz;
+                        const double si = -pmass * rho21i * projBi * grkerni[k], sj = -pmass * rho21j * projBj * grkernj[k];   // Maxwell stress, :1677-1684
+                        projsx = si * Bxi + sj * E[k].x; projsy = si * Byi + sj * E[k].y; projsz = si * Bzi + sj * E[k].z;
+                    }
+                    fx += -runix * (gradp + fgrav) - projsx;
+                    fy += -runiy * (gradp + fgrav) - projsy;
+                    fz += -runiz * (gradp + fgrav) - projsz;
+                    drhodt += projv * grkerni[k];
                 }
-                if (MHD) {                                             // force.F90:1428-1444, :1626-1684, :2132-2150
-                    const double4 E = rj[4];
-                    const double Bxi = T4.x, Byi = T4.y, Bzi = T4.z, psii = T4.w;
-                    const double dBxx = Bxi - E.x, dByy = Byi - E.y, dBzz = Bzi - E.z;
-                    const double projBi = Bxi * runix + Byi * runiy + Bzi * runiz;
-                    const double projBj = E.x * runix + E.y * runiy + E.z * runiz;
-                    const double projdB = dBxx * runix + dByy * runiy + dBzz * runiz;
-                    divBdiff += -pmass * projdB * grkerni;
-                    const double rho21i = rho1i * rho1i, rho21j = rho1j * rho1j;
-                    const double avBterm = 0.5 * pmass * rho1i * p.alphaB * rho1i, avBtermj = 0.5 * pmass * rho1j * p.alphaB * rho1j;
-                    const double tx = dvx - projv * runix, ty = dvy - projv * runiy, tz = dvz - projv * runiz;
-                    const double vsigB = sqrt(tx * tx + ty * ty + tz * tz);
-                    const double dBdissterm = (avBterm * grkerni + avBtermj * grkernj) * vsigB;
-                    if (ADIA && p.iresistive_heating > 0) dudtdiss += -0.5 * (dBxx * dBxx + dByy * dByy + dBzz * dBzz) * dBdissterm;
-                    const double pmjrho21grkerni = pmass * rho21i * grkerni, pmjrho21grkernj = pmass * rho21j * grkernj;
-                    const double termi = pmjrho21grkerni * projBi;
-                    divBsym += termi + pmjrho21grkernj * projBj;
-                    const double dpsiterm = p.overcleanfac * (pmjrho21grkerni * psii * vwavei + pmjrho21grkernj * E.w * vwavej);
-                    dBx += -termi * dvx + dBdissterm * dBxx - dpsiterm * runix;
-                    dBy += -termi * dvy + dBdissterm * dByy - dpsiterm * runiy;
-                    dBz += -termi * dvz + dBdissterm * dBzz - dpsiterm * runiz;
-                    const double si = -pmass * rho21i * projBi * grkerni, sj = -pmass * rho21j * projBj * grkernj;   // Maxwell stress, :1677-1684
-                    projsx = si * Bxi + sj * E.x; projsy = si * Byi + sj * E.y; projsz = si * Bzi + sj * E.z;
-                }
-                fx += -runix * (gradp + fgrav) - projsx;
-                fy += -runiy * (gradp + fgrav) - projsy;
-                fz += -runiz * (gradp + fgrav) - projsz;
-                drhodt += projv * grkerni;
             };
             while (true) {
-                const int slot0 = act ? next_hit(ws, lane, nchunk, c, m) : -1;
+                const int slot0 = act ? next_hit_s(hm_lane, nchunk, c, m) : -1;
                 if (slot0 < 0) break;
-                const int slot1 = next_hit(ws, lane, nchunk, c, m);
-#if FORCE_NPAIR >= 3
-                const int slot2 = (slot1 >= 0) ? next_hit(ws, lane, nchunk, c, m) : -1;
-#endif
-#if FORCE_NPAIR >= 4
-                const int slot3 = (slot2 >= 0) ? next_hit(ws, lane, nchunk, c, m) : -1;
-#endif
-                pair(slot0);
-                pair(slot1);
-#if FORCE_NPAIR >= 3
-                pair(slot2);
-#endif
-#if FORCE_NPAIR >= 4
-                pair(slot3);
-#endif
+                const int slot1 = next_hit_s(hm_lane, nchunk, c, m);
+                const int j0 = (int)lds_u32(sidx_s + 4u * (unsigned)slot0), j1 = (slot1 >= 0) ? (int)lds_u32(sidx_s + 4u * (unsigned)slot1) : s;
+                pair2(j0, j1);
             }
             __syncwarp();
         }

@@ -11,6 +11,12 @@ __device__ __forceinline__ double p2(double x) { return x * x; }
 __device__ __forceinline__ double p3(double x) { return x * x * x; }
 __device__ __forceinline__ double p4(double x) { double y = x * x; return y * y; }
 __device__ __forceinline__ double p5(double x) { double y = x * x; return y * y * x; }
+// max(x, 0) on the integer pipe (sign bit of the high word), keeping the FP64 pipe for the sums
+__device__ __forceinline__ double relu_d(double x)
+{
+    const int hi = __double2hiint(x), keep = ~(hi >> 31);
+    return __hiloint2double(hi & keep, __double2loint(x) & keep);
+}
 
 template <> struct SphKern<0> {
     static constexpr double radkern = 2.0, radkern2 = 4.0;
@@ -22,6 +28,19 @@ template <> struct SphKern<0> {
         if (q < 1.) { w = 0.75 * q2 * q - 1.5 * q2 + 1.; gr = q * (2.25 * q - 3.); }
         else if (q < 2.) { w = -0.25 * p3(q - 2.); gr = -0.75 * p2(q - 2.); }
         else { w = 0.; gr = 0.; }
+    }
+    // the same spline written as truncated powers, w = (2-q)+^3/4 - (1-q)+^3: no branches, zero beyond the support, any q >= 0
+    __device__ __forceinline__ static void get_kernel_bf(double q, double &w, double &gr)
+    {
+        const double a = relu_d(2. - q), b = relu_d(1. - q);
+        const double a2 = a * a, b2 = b * b;
+        w = fma(0.25 * a, a2, -(b2 * b));
+        gr = fma(-0.75, a2, 3. * b2);
+    }
+    __device__ __forceinline__ static double grkern_bf(double q)
+    {
+        const double a = relu_d(2. - q), b = relu_d(1. - q);
+        return fma(-0.75 * a, a, 3. * (b * b));
     }
     __device__ __forceinline__ static double grkern(double q2, double q)
     {
@@ -67,6 +86,21 @@ template <> struct SphKern<1> {
         else if (q < 2.) { w = -p5(q - 3.) + 6. * p5(q - 2.); gr = -5. * p4(q - 3.) + 30. * p4(q - 2.); }
         else if (q < 3.) { w = -p5(q - 3.); gr = -5. * p4(q - 3.); }
         else { w = 0.; gr = 0.; }
+    }
+    // truncated powers: w = (3-q)+^5 - 6 (2-q)+^5 + 15 (1-q)+^5
+    __device__ __forceinline__ static void get_kernel_bf(double q, double &w, double &gr)
+    {
+        const double a = relu_d(3. - q), b = relu_d(2. - q), c = relu_d(1. - q);
+        const double a2 = a * a, b2 = b * b, c2 = c * c;
+        const double a4 = a2 * a2, b4 = b2 * b2, c4 = c2 * c2;
+        w = fma(a4, a, fma(-6. * b4, b, 15. * c4 * c));
+        gr = fma(-5., a4, fma(30., b4, -75. * c4));
+    }
+    __device__ __forceinline__ static double grkern_bf(double q)
+    {
+        const double a = relu_d(3. - q), b = relu_d(2. - q), c = relu_d(1. - q);
+        const double a2 = a * a, b2 = b * b, c2 = c * c;
+        return fma(-5. * a2, a2, fma(30. * b2, b2, -75. * (c2 * c2)));
     }
     __device__ __forceinline__ static double grkern(double q2, double q)
     {

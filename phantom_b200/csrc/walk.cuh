@@ -247,6 +247,45 @@ __device__ __forceinline__ int next_hit(const WarpShared &ws, int lane, int nchu
     return c * 32 + bit;
 }
 
+// The same through an explicit 32-bit shared-window address.  The address is made opaque once per kernel so that the compiler keeps
+// it in a register; otherwise it re-derives it (S2R + LEA + IMAD) at every use inside the pair loop.
+__device__ __forceinline__ unsigned ws_shared_addr(const WarpShared &ws)
+{
+    unsigned a = (unsigned)__cvta_generic_to_shared(&ws);
+    asm volatile("mov.u32 %0, %0;" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// hm_lane = shared address of ws.hm[0][lane]
+__device__ __forceinline__ int next_hit_s(unsigned hm_lane, int nchunk, int &c, unsigned &m)
+{
+    while (m == 0u) {
+        if (++c >= nchunk) return -1;
+        m = lds_u32(hm_lane + 128u * (unsigned)c);
+    }
+    const int bit = __ffs(m) - 1;
+    m &= m - 1;
+    return c * 32 + bit;
+}
+
+// 1/sqrt(x) for a normal x > 0 (a third-order step on the hardware seed, as the CUDA library does, without its special-case branch);
+// returns 0 for x == 0 or subnormal: coincident particles, for which the reference takes rij1 = 1/(0 + epsilon) times zero separation
+__device__ __forceinline__ double rsqrt_pos(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    y = fma(p * e, y, y);
+    return (__double2hiint(x) >= 0x00100000) ? y : 0.;
+}
+
 // exact reference separation: dx = xi - xj, minimum image (dens.F90:666-670), rij2 = dx*dx + dy*dy + dz*dz evaluated
 // left to right without FMA contraction so that set membership is bit-identical to the gfortran build
 template <bool PERIODIC>
