@@ -153,6 +153,8 @@ struct sphgpu_ctx {
     DevBuf<TreeNode> nodes;
     DevBuf<TreeNodeF> nodesf;
     bool multitype = false;                 // any particle that is not plain gas (boundary, dust, ...)
+    DevBuf<int> wl_list, wl_ncl; DevBuf<float> wl_reach;   // cell lists prepared by k_walk_lists (walk.cuh)
+    int walk_cap = 192;             // cells per prepared list (longer lists are walked inside the pair kernel)
     DevBuf<int> stage_idx;                  // per-warp cell lists of the pair kernels (candidates themselves are staged in shared memory)
     DevBuf<int> nodeflag;
     DevBuf<char> cubtemp;

@@ -27,6 +27,7 @@ struct DensArgs {
     const double4 *pos4, *vel4, *acc4, *bev4; const int8_t *stype; const int *perm;
     const double4 *drec;     // fast path: 4 x 32 B per particle {x,y,z,h} {v,u} {f+fext} {B/rho,psi}
     int *stage_idx; int multitype; int max_leaf; double hmax_global;
+    WalkLists wl;       // cell lists prepared by k_walk_lists for the first pass of every group
     double *hnew; float *s_gradh, *s_divv, *s_dvdx, *s_alpha3, *s_divcurlB; int *s_nneigh; double *s_dustfrac;
     double *h_hist; int *h_its; int64_t npart;     // GRAV: per-particle h after every iteration, for the node-hmax replay of gravity.cu
     int scratch_per_warp; unsigned long long *cnt; double *dscal;
@@ -313,8 +314,11 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
         // target stays inside half a box length; otherwise every candidate goes to the exact test
         bool wide = PERIODIC && (halfext + rcut_list >= 0.999 * halfLmin);
         float reach = 0.f;
-        int ncl = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut_list), (float)radkern, fLx, fLy, fLz, ws, clist,
-                                             a.scratch_per_warp, reach);
+        const int *cl = clist;                                       // list in use: the prepared one, or this warp's slice after a walk in here
+        int ncl = a.wl.ncl[cellid];
+        if (ncl >= 0) { cl = a.wl.list + (size_t)cellid * a.wl.cap; reach = a.wl.reach[cellid]; }
+        else ncl = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut_list), (float)radkern, fLx, fLy, fLz, ws.stack,
+                                              clist, a.scratch_per_warp, reach);
         st_nwalk += (lane == 0);
         if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
         if (FAST && PERIODIC) {
@@ -331,8 +335,9 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                 hmax_list = hneed * a.margin * 1.01;
                 rcut_list = radkern * hmax_list;
                 wide = PERIODIC && (halfext + rcut_list >= 0.999 * halfLmin);
-                ncl = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut_list), (float)radkern, fLx, fLy, fLz, ws, clist,
-                                                 a.scratch_per_warp, reach);
+                ncl = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut_list), (float)radkern, fLx, fLy, fLz, ws.stack,
+                                                 clist, a.scratch_per_warp, reach);
+                cl = clist;
                 st_nwalk += (lane == 0);
                 if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); failed = true; }
                 if (FAST && PERIODIC) {
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
             if (FAST && MHD) { const double rhoi = rhoh_d(h, pmassi, dp.p.hfact); bi = make_double4(bevi.x * rhoi, bevi.y * rhoi, bevi.z * rhoi, bevi.w); }
             int nlist = 0;
             for (int cellpos = 0; cellpos < ncl;) {                  // rounds of <= ROUND candidates staged in shared memory
-                const int nr = stage_round<PERIODIC, false>(ws, clist, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf, fs);
+                const int nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf, fs);
                 nlist += nr;
                 const int nchunk = (nr + 31) >> 5;
                 build_masks<false>(ws, nr, ft);
@@ -586,6 +591,8 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     a.margin = c->list_margin; a.icall = icall;
     a.h_hist = c->h_hist.p; a.h_its = c->h_its.p; a.npart = n;
     c->grav_tree_valid = false;            // h changes below: the gravity tree caches h
+    TRY(walk_lists_run(c, false, (p.kernel == 0 ? SphKern<0>::radkern : SphKern<1>::radkern) * c->list_margin,
+                       (p.kernel == 0 ? SphKern<0>::radkern : SphKern<1>::radkern), a.wl));
     unsigned long long hc[16]; double hrhomax, hused, hgrow = 0.;
     for (int attempt = 0;; attempt++) {
         CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));

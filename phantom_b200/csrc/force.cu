@@ -19,6 +19,7 @@ namespace {
 struct ForceArgs {
     const TreeNodeF *nodes; const Cell *cells; int ncells; const Cell *groups; int ngroups;
     int *stage_idx; int multitype; int max_leaf;
+    WalkLists wl;       // cell lists prepared by k_walk_lists
     const double4 *pos4, *vel4, *recC, *recD, *recE; const double2 *hinv; const int8_t *stype; const int *perm;
     double4 *s_fxyzu, *s_dB; float *s_divvf, *s_divBsymm; int *s_done;
     int scratch_per_warp; unsigned long long *cnt; double *dscal;
@@ -352,8 +353,11 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : (INDTS ? 4 : FORCE_MI
         const bool interior = !PERIODIC || (cell.lo[0] - rreach > p.xmin && cell.hi[0] + rreach < p.xmax && cell.lo[1] - rreach > p.ymin &&
                                             cell.hi[1] + rreach < p.ymax && cell.lo[2] - rreach > p.zmin && cell.hi[2] + rreach < p.zmax);
         float reach = 0.f;
-        const int ncl = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut), __double2float_ru(KF::radkern * a.hscale),
-                                                  fLx, fLy, fLz, ws, clist, a.scratch_per_warp, reach);
+        const int *cl = clist;                                       // list in use: the prepared one, or this warp's slice after a walk in here
+        int ncl = a.wl.ncl[cellid];
+        if (ncl >= 0) { cl = a.wl.list + (size_t)cellid * a.wl.cap; reach = a.wl.reach[cellid]; }
+        else ncl = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut), __double2float_ru(KF::radkern * a.hscale),
+                                             fLx, fLy, fLz, ws.stack, clist, a.scratch_per_warp, reach);
         if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
         int nlist = 0;
         const FilterScale fs = filter_scale((float)halfext, reach);
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : (INDTS ? 4 : FORCE_MI
         double vsigmax = 0.;
         int npair = 0, ibin_neigh = 0;
         for (int cellpos = 0; cellpos < ncl;) {                     // rounds of <= ROUND candidates staged in shared memory
-            const int nr = stage_round<PERIODIC, true>(ws, clist, ncl, cellpos, a.frec, FSTRIDE, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs);
+            const int nr = stage_round<PERIODIC, true>(ws, cl, ncl, cellpos, a.frec, FSTRIDE, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs);
             nlist += nr;
             const int nchunk = (nr + 31) >> 5;
             if (wide) build_masks<false>(ws, nr, ft);
@@ -637,8 +641,11 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
         const double rcut = KF::radkern * cell.hmax * a.hscale;
         const bool wide = PERIODIC && (halfext + KF::radkern * fmax(cell.hmax, (double)hmax_global) * a.hscale >= 0.999 * halfLmin);
         float reach = 0.f;
-        const int ncl = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut), __double2float_ru(KF::radkern * a.hscale),
-                                                  fLx, fLy, fLz, ws, clist, a.scratch_per_warp, reach);
+        const int *cl = clist;                                       // list in use: the prepared one, or this warp's slice after a walk in here
+        int ncl = a.wl.ncl[cellid];
+        if (ncl >= 0) { cl = a.wl.list + (size_t)cellid * a.wl.cap; reach = a.wl.reach[cellid]; }
+        else ncl = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut), __double2float_ru(KF::radkern * a.hscale),
+                                             fLx, fLy, fLz, ws.stack, clist, a.scratch_per_warp, reach);
         if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
         int nlist = 0;
         const FilterScale fs = filter_scale((float)halfext, reach);
@@ -662,7 +669,7 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
         int npair = 0;
         XtraSums xs; xs.fdx = xs.fdy = xs.fdz = 0.; xs.tsmin = 1.e29; xs.ibin_neigh = 0;
         for (int cellpos = 0; cellpos < ncl;) {                     // rounds of <= ROUND candidates staged in shared memory
-            const int nr = stage_round<PERIODIC, false>(ws, clist, ncl, cellpos, a.pos4, 1, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs);
+            const int nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, a.pos4, 1, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs);
             nlist += nr;
             const int nchunk = (nr + 31) >> 5;
             if (wide) build_masks<false>(ws, nr, ft);
@@ -910,6 +917,8 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     a.s_ibinold = c->s_ibinold.p; a.s_ibin = c->s_ibin.p; a.s_wake = c->s_wake.p; a.s_ibinnew = c->s_ibinnew.p;
     a.hscale = c->hscale;
     a.nbinmax = c->nbinmax; a.ibinnow_m1 = c->ibinnow - 1; a.istepfrac = c->istepfrac;
+    TRY(walk_lists_run(c, true, (p.kernel == 0 ? SphKern<0>::radkern : SphKern<1>::radkern) * c->hscale,
+                       (p.kernel == 0 ? SphKern<0>::radkern : SphKern<1>::radkern) * c->hscale, a.wl));
     unsigned long long hc[16]; double hd[4];
     for (int attempt = 0;; attempt++) {
         CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));

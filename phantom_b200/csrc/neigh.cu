@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128) k_neigh(const TreeNodeF *nodes, const Cel
         const double cx = 0.5 * (cell.lo[0] + cell.hi[0]), cy = 0.5 * (cell.lo[1] + cell.hi[1]), cz = 0.5 * (cell.lo[2] + cell.hi[2]);
         float reach = 0.f;
         const int ncl = warp_walk<SYM, PERIODIC>(nodes, cells, ncells, tlo, thi, __double2float_ru(radkern * cell.hmax), (float)radkern, (float)Lx, (float)Ly,
-                                                 (float)Lz, ws, clist, scratch_per_warp, reach);
+                                                 (float)Lz, ws.stack, clist, scratch_per_warp, reach);
         if (ncl < 0) { if (lane == 0) atomicMax(&cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
         const FilterScale fs = filter_scale(0.f, reach);     // the FP16 filter words are staged but not used here: every candidate gets the exact test
         int nfound[32];                                      // per target of the cell (max_leaf <= 32), kept across rounds

@@ -73,7 +73,7 @@ __device__ __forceinline__ float box_gap2f(const float *tlo, const float *thi, f
 // group centre is bounded by halfext + reach (input of the FP32 error bound).
 template <bool SYM, bool PERIODIC>
 __device__ int warp_walk(const TreeNodeF *__restrict__ nodes, const Cell *__restrict__ cells, int ncells, const float *tlo, const float *thi, float rcut_t,
-                         float radkern, float fLx, float fLy, float fLz, WarpShared &ws, int *__restrict__ clist, int cap, float &reach)
+                         float radkern, float fLx, float fLy, float fLz, int *stack, int *__restrict__ clist, int cap, float &reach)
 {
     const int lane = lane_id();
     int ncl = 0;
@@ -85,14 +85,14 @@ __device__ int warp_walk(const TreeNodeF *__restrict__ nodes, const Cell *__rest
         ncl = 1;
     } else {
         int sp = 1;
-        if (lane == 0) ws.stack[0] = 0;
+        if (lane == 0) stack[0] = 0;
         __syncwarp();
         while (sp > 0) {
             int npop = min(16, sp);
             if (sp + npop > WALK_STACK - 2) npop = 1;
             const int slot = lane & 1, which = lane >> 1;
             int node = -1;
-            if (which < npop) node = ws.stack[sp - 1 - which];
+            if (which < npop) node = stack[sp - 1 - which];
             sp -= npop;
             __syncwarp();
             bool hit = false;
@@ -113,7 +113,7 @@ __device__ int warp_walk(const TreeNodeF *__restrict__ nodes, const Cell *__rest
             const unsigned mint = __ballot_sync(FULLMASK, hit && child >= 0);
             const unsigned mleaf = __ballot_sync(FULLMASK, leafhit);
             if (sp + __popc(mint) > WALK_STACK) return -1;
-            if (hit && child >= 0) ws.stack[sp + __popc(mint & ((1u << lane) - 1))] = child;
+            if (hit && child >= 0) stack[sp + __popc(mint & ((1u << lane) - 1))] = child;
             sp += __popc(mint);
             if (mleaf) {
                 const int nl = __popc(mleaf);
@@ -133,6 +133,57 @@ __device__ int warp_walk(const TreeNodeF *__restrict__ nodes, const Cell *__rest
     reach = rmax;
     __syncwarp();
     return ncl;
+}
+
+// ---- cell lists ahead of the pair kernels ----------------------------------------------------------------------------------------
+// The walk is a chain of dependent node reads (one L2 round trip per level) with almost no arithmetic: inside a pair kernel, at 12-16
+// warps per SM, it costs ~15 % of the time in scoreboard stalls.  k_walk_lists does it for every target group in a kernel of its own
+// (one warp per group, a 1 KB stack per warp, 48+ warps per SM hide the latency) and leaves the packed cell lists in global memory;
+// the pair kernels read them back coalesced.  A group whose list exceeds `cap` gets ncl = -1 and is walked by the pair kernel itself
+// into its per-warp slice, as is every re-walk of the density iteration.
+struct WalkLists {
+    int *list;          // [ngroups][cap] packed cells
+    int *ncl;           // [ngroups] cells in the list, -1: not prepared
+    float *reach;       // [ngroups] see warp_walk
+    int cap;
+};
+
+template <bool SYM, bool PERIODIC>
+__global__ void __launch_bounds__(256) k_walk_lists(const TreeNodeF *__restrict__ nodes, const Cell *__restrict__ cells, int ncells,
+                                                    const Cell *__restrict__ groups, int ngroups, double rfac, float radkern, float fLx, float fLy, float fLz,
+                                                    WalkLists wl)
+{
+    __shared__ int stacks[8][WALK_STACK];
+    const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= ngroups) return;
+    const int lane = lane_id();
+    const Cell &cell = groups[g];
+    if (cell.active == 0) { if (lane == 0) wl.ncl[g] = 0; return; }
+    float tlo[3], thi[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { tlo[k] = __double2float_rd(cell.lo[k]); thi[k] = __double2float_ru(cell.hi[k]); }
+    float reach = 0.f;
+    const int ncl = warp_walk<SYM, PERIODIC>(nodes, cells, ncells, tlo, thi, __double2float_ru(rfac * cell.hmax), radkern, fLx, fLy, fLz, stacks[threadIdx.x >> 5],
+                                             wl.list + (size_t)g * wl.cap, wl.cap, reach);
+    if (lane == 0) { wl.ncl[g] = ncl; wl.reach[g] = reach; }
+}
+
+// host side: prepare the lists of all target groups for search radius rfac * hmax(group) (SYM: or the candidates' own radius)
+static inline int walk_lists_run(sphgpu_ctx *c, bool sym, double rfac, double radkern_eff, WalkLists &wl)
+{
+    const int ng = (int)c->ngroups;
+    CUDA_TRY(c, c->wl_list.ensure((size_t)ng * c->walk_cap)); CUDA_TRY(c, c->wl_ncl.ensure(ng)); CUDA_TRY(c, c->wl_reach.ensure(ng));
+    wl.list = c->wl_list.p; wl.ncl = c->wl_ncl.p; wl.reach = c->wl_reach.p; wl.cap = c->walk_cap;
+    const float rk = nextafterf((float)radkern_eff, 3.0e38f);
+    const float fLx = (float)c->hp.dxbound, fLy = (float)c->hp.dybound, fLz = (float)c->hp.dzbound;
+    const int grid = (ng + 7) / 8;
+    const bool per = c->hp.p.periodic;
+#define WALK_LAUNCH(S, P) k_walk_lists<S, P><<<grid, 256, 0, c->stream>>>(c->nodesf.p, c->cells.p, (int)c->ncells, c->groups.p, ng, rfac, rk, fLx, fLy, fLz, wl)
+    if (sym) { if (per) WALK_LAUNCH(true, true); else WALK_LAUNCH(true, false); }
+    else { if (per) WALK_LAUNCH(false, true); else WALK_LAUNCH(false, false); }
+#undef WALK_LAUNCH
+    c->launches++;
+    return SPHGPU_OK;
 }
 
 // ---- FP16 prefilter -------------------------------------------------------------------------------------------------------
@@ -166,7 +217,9 @@ __device__ __forceinline__ FilterTarget filter_target(const FilterScale &fs, flo
     return t;
 }
 
-// Copy the particles of the next cells of the list into the shared-memory round buffer: 4 cells per step, 8 lanes per cell.
+// Copy the particles of the next cells of the list into the shared-memory round buffer.  Two passes so that no load waits on another:
+// (1) lane = cell, 32 cells per step: one coalesced read of the packed list, a warp scan of the counts, slot -> particle index;
+// (2) lane = slot: the position records of all slots are fetched independently, scaled to FP16 and stored.
 // posrec[j * stride] = {x, y, z, w} with w = h (WINV = false) or 1/h (WINV = true).  Returns the number staged; cellpos advances.
 template <bool PERIODIC, bool WINV>
 __device__ __forceinline__ int stage_round(WarpShared &ws, const int *__restrict__ clist, int ncl, int &cellpos, const double4 *__restrict__ posrec, int stride,
@@ -174,36 +227,39 @@ __device__ __forceinline__ int stage_round(WarpShared &ws, const int *__restrict
                                            const FilterScale &fs)
 {
     const int lane = lane_id();
-    const int sub = lane >> 3, l8 = lane & 7;
     int n = 0;
-    while (cellpos < ncl && n + 4 * maxleaf <= ROUND) {  // the next 4 cells (<= maxleaf particles each) always fit
+    while (cellpos < ncl) {
+        const int nb = min(32, min(ncl - cellpos, (ROUND - n) / maxleaf));      // cells (<= maxleaf particles each) that are sure to fit
+        if (nb <= 0) break;
         int start = 0, cnt = 0;
-        if (cellpos + sub < ncl) { const int pk = clist[cellpos + sub]; start = pk >> 5; cnt = (pk & 31) + 1; }
-        // exclusive offsets of the (up to) 4 cells of this step
-        const int c1 = __shfl_sync(FULLMASK, cnt, 0), c2 = __shfl_sync(FULLMASK, cnt, 8), c3 = __shfl_sync(FULLMASK, cnt, 16), c4 = __shfl_sync(FULLMASK, cnt, 24);
-        const int off = n + (sub > 0 ? c1 : 0) + (sub > 1 ? c2 : 0) + (sub > 2 ? c3 : 0);
-        for (int k = l8; k < cnt; k += 8) {
-            const int j = start + k;
-            const double4 p = posrec[(size_t)j * stride];
-            double rx = p.x - cx, ry = p.y - cy, rz = p.z - cz;
-            if (PERIODIC) {
-                if (rx > 0.5 * Lx) rx -= Lx; else if (rx < -0.5 * Lx) rx += Lx;
-                if (ry > 0.5 * Ly) ry -= Ly; else if (ry < -0.5 * Ly) ry += Ly;
-                if (rz > 0.5 * Lz) rz -= Lz; else if (rz < -0.5 * Lz) rz += Lz;
-            }
-            float rkh;
-            if (WINV) rkh = __fmul_ru(radkern, __frcp_ru(__double2float_rd(p.w)));   // >= radkern * h_j
-            else rkh = __double2float_ru((double)radkern * p.w);
-            // |u| <= 1 by construction; the clamp only keeps a stray value finite (it could not be a neighbour: limits are <= ~1)
-            const float ux = fminf(fmaxf((float)rx * fs.scale, -8.f), 8.f), uy = fminf(fmaxf((float)ry * fs.scale, -8.f), 8.f),
-                        uz = fminf(fmaxf((float)rz * fs.scale, -8.f), 8.f);
-            const int slot = off + k;
-            __half *w = reinterpret_cast<__half *>(&ws.hp[slot >> 5][slot & 15]) + ((slot >> 4) & 1);
-            w[0] = __float2half_rn(ux); w[2] = __float2half_rn(uy); w[4] = __float2half_rn(uz); w[6] = filter_limit(fs, rkh);
-            ws.sidx[slot] = j;
+        if (lane < nb) { const int pk = clist[cellpos + lane]; start = pk >> 5; cnt = (pk & 31) + 1; }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULLMASK, incl, d); if (lane >= d) incl += t; }
+        const int base = n + incl - cnt;
+        for (int k = 0; k < cnt; k++) ws.sidx[base + k] = start + k;
+        n += __shfl_sync(FULLMASK, incl, 31);
+        cellpos += nb;
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int slot = lane; slot < n; slot += 32) {
+        const int j = ws.sidx[slot];
+        const double4 p = posrec[(size_t)j * stride];
+        double rx = p.x - cx, ry = p.y - cy, rz = p.z - cz;
+        if (PERIODIC) {
+            if (rx > 0.5 * Lx) rx -= Lx; else if (rx < -0.5 * Lx) rx += Lx;
+            if (ry > 0.5 * Ly) ry -= Ly; else if (ry < -0.5 * Ly) ry += Ly;
+            if (rz > 0.5 * Lz) rz -= Lz; else if (rz < -0.5 * Lz) rz += Lz;
         }
-        n += c1 + c2 + c3 + c4;
-        cellpos += 4;
+        float rkh;
+        if (WINV) rkh = __fmul_ru(radkern, __frcp_ru(__double2float_rd(p.w)));   // >= radkern * h_j
+        else rkh = __double2float_ru((double)radkern * p.w);
+        // |u| <= 1 by construction; the clamp only keeps a stray value finite (it could not be a neighbour: limits are <= ~1)
+        const float ux = fminf(fmaxf((float)rx * fs.scale, -8.f), 8.f), uy = fminf(fmaxf((float)ry * fs.scale, -8.f), 8.f),
+                    uz = fminf(fmaxf((float)rz * fs.scale, -8.f), 8.f);
+        __half *w = reinterpret_cast<__half *>(&ws.hp[slot >> 5][slot & 15]) + ((slot >> 4) & 1);
+        w[0] = __float2half_rn(ux); w[2] = __float2half_rn(uy); w[4] = __float2half_rn(uz); w[6] = filter_limit(fs, rkh);
     }
     __syncwarp();
     return n;
