@@ -75,7 +75,7 @@ struct __align__(16) TreeNodeF {
     float lo[2][3];
     float hi[2][3];
     float hmax[2];
-    int child[2];
+    int child[2];      // >= 0: internal node id ; < 0: leaf, bits 0-30 = (first sorted slot << 5) | (count - 1)
 };
 
 struct Cell {          // leaf cell = run of <= max_cell Morton-consecutive particles
@@ -154,6 +154,8 @@ struct sphgpu_ctx {
     DevBuf<TreeNodeF> nodesf;
     bool multitype = false;                 // any particle that is not plain gas (boundary, dust, ...)
     DevBuf<int> wl_list, wl_ncl; DevBuf<float> wl_reach;   // cell lists prepared by k_walk_lists (walk.cuh)
+    bool wl_force_ok = false;       // the prepared lists are symmetric lists of the current groups ...
+    double wl_cover = 0.;           // ... and cover every h up to wl_cover x the tree's hmax (force pass reuses them while hscale <= wl_cover)
     int walk_cap = 192;             // cells per prepared list (longer lists are walked inside the pair kernel)
     DevBuf<int> stage_idx;                  // per-warp cell lists of the pair kernels (candidates themselves are staged in shared memory)
     DevBuf<int> nodeflag;

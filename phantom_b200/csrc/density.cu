@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
             if (FAST && MHD) { const double rhoi = rhoh_d(h, pmassi, dp.p.hfact); bi = make_double4(bevi.x * rhoi, bevi.y * rhoi, bevi.z * rhoi, bevi.w); }
             int nlist = 0;
             for (int cellpos = 0; cellpos < ncl;) {                  // rounds of <= ROUND candidates staged in shared memory
-                const int nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf, fs);
+                const int nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf, fs, interior);
                 nlist += nr;
                 const int nchunk = (nr + 31) >> 5;
                 build_masks<false>(ws, nr, ft);
@@ -591,8 +591,12 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     a.margin = c->list_margin; a.icall = icall;
     a.h_hist = c->h_hist.p; a.h_its = c->h_its.p; a.npart = n;
     c->grav_tree_valid = false;            // h changes below: the gravity tree caches h
-    TRY(walk_lists_run(c, false, (p.kernel == 0 ? SphKern<0>::radkern : SphKern<1>::radkern) * c->list_margin,
-                       (p.kernel == 0 ? SphKern<0>::radkern : SphKern<1>::radkern), a.wl));
+    {   // ONE symmetric walk serves both passes: with the list margin on every radius it holds the density candidates now and the force
+        // candidates as long as no h grows by more than the margin (force_run checks hscale against wl_cover)
+        const double R = (p.kernel == 0 ? SphKern<0>::radkern : SphKern<1>::radkern), hs0 = fmax(c->hscale, 1.);
+        TRY(walk_lists_run(c, true, R * c->list_margin * hs0, R * c->list_margin * hs0, a.wl));
+        c->wl_force_ok = true; c->wl_cover = hs0 * c->list_margin;
+    }
     unsigned long long hc[16]; double hrhomax, hused, hgrow = 0.;
     for (int attempt = 0;; attempt++) {
         CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));

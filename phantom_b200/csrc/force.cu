@@ -307,10 +307,10 @@ template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS>
 #ifndef FORCE_MINB
 #define FORCE_MINB 4
 #endif
-#ifndef FORCE_NPAIR
-#define FORCE_NPAIR 2
+#ifndef FORCE_MHD_MINB
+#define FORCE_MHD_MINB 3
 #endif
-__global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : (INDTS ? 4 : FORCE_MINB)) k_force_fast(const ForceArgs a, const __grid_constant__ DevParams dp)
+__global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_MINB)) k_force_fast(const ForceArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
     __shared__ WarpShared wsh[4];
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(128, (MHD || GRAV) ? 3 : (INDTS ? 4 : FORCE_MI
         double vsigmax = 0.;
         int npair = 0, ibin_neigh = 0;
         for (int cellpos = 0; cellpos < ncl;) {                     // rounds of <= ROUND candidates staged in shared memory
-            const int nr = stage_round<PERIODIC, true>(ws, cl, ncl, cellpos, a.frec, FSTRIDE, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs);
+            const int nr = stage_round<PERIODIC, true>(ws, cl, ncl, cellpos, a.frec, FSTRIDE, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs, PERIODIC && interior);
             nlist += nr;
             const int nchunk = (nr + 31) >> 5;
             if (wide) build_masks<false>(ws, nr, ft);
@@ -917,8 +917,13 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     a.s_ibinold = c->s_ibinold.p; a.s_ibin = c->s_ibin.p; a.s_wake = c->s_wake.p; a.s_ibinnew = c->s_ibinnew.p;
     a.hscale = c->hscale;
     a.nbinmax = c->nbinmax; a.ibinnow_m1 = c->ibinnow - 1; a.istepfrac = c->istepfrac;
-    TRY(walk_lists_run(c, true, (p.kernel == 0 ? SphKern<0>::radkern : SphKern<1>::radkern) * c->hscale,
-                       (p.kernel == 0 ? SphKern<0>::radkern : SphKern<1>::radkern) * c->hscale, a.wl));
+    if (c->wl_force_ok && c->hscale <= c->wl_cover) {                      // the lists of the density pass still cover every pair
+        a.wl.list = c->wl_list.p; a.wl.ncl = c->wl_ncl.p; a.wl.reach = c->wl_reach.p; a.wl.cap = c->walk_cap;
+    } else {
+        const double R = (p.kernel == 0 ? SphKern<0>::radkern : SphKern<1>::radkern);
+        TRY(walk_lists_run(c, true, R * c->hscale, R * c->hscale, a.wl));
+        c->wl_force_ok = true; c->wl_cover = c->hscale;
+    }
     unsigned long long hc[16]; double hd[4];
     for (int attempt = 0;; attempt++) {
         CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));

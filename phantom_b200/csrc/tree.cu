@@ -257,6 +257,8 @@ __global__ void k_refit(int M, const Cell *__restrict__ cells, TreeNode *nodes, 
         nd->hmax[slot] = hmax;
         nd->cnt[slot] = cnt; nd->start[slot] = start; nd->act[slot] = act;
         write_nodef(&nodesf[parent], slot, lo, hi, hmax);
+        // the walk's copy names a leaf child by its packed particle range, so that a leaf hit needs no second (dependent) read
+        if (me < 0) nodesf[parent].child[slot] = (int)(0x80000000u | ((unsigned)start << 5) | (unsigned)(cnt - 1));
         __threadfence();
         if (atomicAdd(&flags[parent], 1) == 0) return;     // first arrival: sibling not ready yet
         __threadfence();
@@ -343,7 +345,7 @@ static int build_groups(sphgpu_ctx *c)
 int tree_refit_hmax(sphgpu_ctx *c)
 {
     const int M = (int)c->ncells;
-    c->hscale = 1.;
+    c->hscale = 1.; c->wl_force_ok = false;
     LAUNCH(c, k_cell_hmax, nblk(M, 128), 128, M, c->cells.p, c->pos4.p);
     if (M > 1) {
         CUDA_TRY(c, cudaMemsetAsync(c->nodeflag.p, 0, sizeof(int) * (size_t)M, c->stream));
@@ -426,7 +428,7 @@ int tree_build(sphgpu_ctx *c)
         CUDA_TRY(c, c->h_build.ensure(n)); CUDA_TRY(c, c->h_its.ensure(n)); if (p.gravity) CUDA_TRY(c, c->h_hist.ensure((size_t)SPHGPU_HHIST * n));
         LAUNCH(c, k_hbuild, nblk(n, 256), 256, n, c->xyzh.p, c->h_build.p, c->h_its.p);
     }
-    c->grav_tree_valid = false; c->hscale = 1.;
+    c->grav_tree_valid = false; c->hscale = 1.; c->wl_force_ok = false;
     CUDA_TRY(c, cudaGetLastError());
     c->tree_valid = true;
     return SPHGPU_OK;

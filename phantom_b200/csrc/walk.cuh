@@ -119,8 +119,7 @@ __device__ int warp_walk(const TreeNodeF *__restrict__ nodes, const Cell *__rest
                 const int nl = __popc(mleaf);
                 if (ncl + nl > cap) return -1;
                 if (leafhit) {
-                    const Cell *cl = &cells[~child];
-                    clist[ncl + __popc(mleaf & ((1u << lane) - 1))] = (cl->start << 5) | (cl->count - 1);
+                    clist[ncl + __popc(mleaf & ((1u << lane) - 1))] = child & 0x7fffffff;
                     rmax = fmaxf(rmax, ext);
                 }
                 ncl += nl;
@@ -224,7 +223,7 @@ __device__ __forceinline__ FilterTarget filter_target(const FilterScale &fs, flo
 template <bool PERIODIC, bool WINV>
 __device__ __forceinline__ int stage_round(WarpShared &ws, const int *__restrict__ clist, int ncl, int &cellpos, const double4 *__restrict__ posrec, int stride,
                                            double cx, double cy, double cz, double Lx, double Ly, double Lz, float radkern, int maxleaf,
-                                           const FilterScale &fs)
+                                           const FilterScale &fs, bool interior = false)
 {
     const int lane = lane_id();
     int n = 0;
@@ -247,7 +246,7 @@ __device__ __forceinline__ int stage_round(WarpShared &ws, const int *__restrict
         const int j = ws.sidx[slot];
         const double4 p = posrec[(size_t)j * stride];
         double rx = p.x - cx, ry = p.y - cy, rz = p.z - cz;
-        if (PERIODIC) {
+        if (PERIODIC && !interior) {                  // interior: no candidate of this group lies across the periodic boundary
             if (rx > 0.5 * Lx) rx -= Lx; else if (rx < -0.5 * Lx) rx += Lx;
             if (ry > 0.5 * Ly) ry -= Ly; else if (ry < -0.5 * Ly) ry += Ly;
             if (rz > 0.5 * Lz) rz -= Lz; else if (rz < -0.5 * Lz) rz += Lz;
