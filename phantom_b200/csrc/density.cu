@@ -28,7 +28,8 @@ struct DensArgs {
     const double4 *drec;     // fast path: 4 x 32 B per particle {x,y,z,h} {v,u} {f+fext} {B/rho,psi}
     int *stage_idx; int multitype; int max_leaf; double hmax_global;
     WalkLists wl;       // cell lists prepared by k_walk_lists for the first pass of every group
-    double *hnew; float *s_gradh, *s_divv, *s_dvdx, *s_alpha3, *s_divcurlB; int *s_nneigh; double *s_dustfrac;
+    double *hnew; int *s_nneigh;                                   // sorted order: new h, neighbour count (< 0: not an active target)
+    float *gradh, *divcurlv, *dvdx, *alphaind, *divcurlB; double *dustfrac;   // caller's order, written directly by the pair kernel (index perm[s])
     double *h_hist; int *h_its; int64_t npart;     // GRAV: per-particle h after every iteration, for the node-hmax replay of gravity.cu
     int scratch_per_warp; unsigned long long *cnt; double *dscal;
     double margin; int icall;
@@ -69,27 +70,16 @@ __global__ void k_gather_dens(int64_t nlive, const int *__restrict__ perm, const
     s_nneigh[s] = -1;
 }
 
-__global__ void k_scatter_dens(int64_t nlive, const int *__restrict__ perm, const int *__restrict__ s_nneigh, const double *__restrict__ hnew,
-                               double4 *__restrict__ pos4, double *__restrict__ xyzh, const float *__restrict__ s_gradh, const float *__restrict__ s_divv,
-                               const float *__restrict__ s_dvdx, const float *__restrict__ s_alpha3, const float *__restrict__ s_divcurlB,
-                               float *__restrict__ gradh, float *__restrict__ divcurlv, float *__restrict__ dvdx, float *__restrict__ alphaind,
-                               float *__restrict__ divcurlB, int ngradh, int nalpha, int mhd, const double *__restrict__ s_dustfrac,
-                               double *__restrict__ dustfrac)
+// the new h of the active targets goes back only after the pass has succeeded (an overflow retry must start from the old h)
+__global__ void k_scatter_h(int64_t nlive, const int *__restrict__ perm, const int *__restrict__ s_nneigh, const double *__restrict__ hnew,
+                            double4 *__restrict__ pos4, double *__restrict__ xyzh)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nlive) return;
     if (s_nneigh[s] < 0) return;     // not an active target: keep stored values (test_derivs.f90:233-238)
-    const int i = perm[s];
     const double h = hnew[s];
     pos4[s].w = h;                                       // treecache(4,:) refresh (dens.F90:1596)
-    xyzh[4 * (size_t)i + 3] = h;
-    for (int k = 0; k < ngradh; k++) gradh[(size_t)ngradh * i + k] = s_gradh[(size_t)ngradh * s + k];
-    divcurlv[i] = s_divv[s];
-#pragma unroll
-    for (int k = 0; k < 9; k++) dvdx[9 * (size_t)i + k] = s_dvdx[9 * (size_t)s + k];
-    if (nalpha >= 3) alphaind[3 * (size_t)i + 2] = s_alpha3[s];
-    if (mhd) for (int k = 0; k < 4; k++) divcurlB[4 * (size_t)i + k] = s_divcurlB[4 * (size_t)s + k];
-    if (s_dustfrac) dustfrac[i] = s_dustfrac[s];
+    xyzh[4 * (size_t)perm[s] + 3] = h;
 }
 
 // pair body: lane = target, j = this lane's next neighbour candidate (slot < 0: none).  Branch-free so that two
@@ -435,17 +425,18 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
             gradhi = 1. / omegai;
             const double hfin = dp.p.hfact * pow(pmassi / fabs(rho), 1.0 / 3.0);    // hrho, part.F90:845
             a.hnew[s] = hfin;
+            const size_t io = (size_t)a.perm[s];                                      // results go straight to the caller's arrays
             st_hgrow = fmax(st_hgrow, hfin / h_old);
             const float gradh4 = (float)gradhi;
-            a.s_gradh[(size_t)dp.ngradh * s] = gradh4;
+            a.gradh[(size_t)dp.ngradh * io] = gradh4;
             if (GRAV) {
                 double gradsofti = (v[S_GRADSOFT] + KF::dphidh0 * pmassi) * hi21;
                 gradsofti = gradsofti * dhdrhoi;
-                a.s_gradh[(size_t)dp.ngradh * s + 1] = (float)gradsofti;
+                a.gradh[(size_t)dp.ngradh * io + 1] = (float)gradsofti;
             }
             gradhi = (double)gradh4;                                                  // dens.F90:1610
             const double rho1i = 1. / rho;
-            if (dp.p.dust) a.s_dustfrac[s] = gasi ? (KF::cnormk * dp.p.massoftype[IDUST] * v[S_RHODUST] * hi31) * rho1i : 0.;   // dens.F90:1612-1624
+            if (dp.p.dust) a.dustfrac[io] = gasi ? (KF::cnormk * dp.p.massoftype[IDUST] * v[S_RHODUST] * hi31) * rho1i : 0.;   // dens.F90:1612-1624
             const double term = KF::cnormk * gradhi * rho1i * hi41;
             const double rxx = v[S_RXX], rxy = v[S_RXY], rxz = v[S_RXZ], ryy = v[S_RYY], ryz = v[S_RYZ], rzz = v[S_RZZ];
             const double denom = rxx * ryy * rzz + 2. * rxy * rxz * ryz - rxx * ryz * ryz - ryy * rxz * rxz - rzz * rxy * rxy;
@@ -478,12 +469,12 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                     divcurlv5 = div_a - (dv[0] * dv[0] + dv[4] * dv[4] + dv[8] * dv[8] + 2. * (dv[1] * dv[3] + dv[2] * dv[6] + dv[5] * dv[7]));
                 }
             }
-            a.s_divv[s] = (float)divv;
-            a.s_alpha3[s] = (float)divcurlv5;
+            a.divcurlv[io] = (float)divv;
+            if (dp.nalpha >= 3) a.alphaind[3 * io + 2] = (float)divcurlv5;
 #pragma unroll
-            for (int k = 0; k < 9; k++) a.s_dvdx[9 * (size_t)s + k] = (float)dv[k];
+            for (int k = 0; k < 9; k++) a.dvdx[9 * io + k] = (float)dv[k];
             if (MHD) {
-                float *o = a.s_divcurlB + 4 * (size_t)s;
+                float *o = a.divcurlB + 4 * io;
                 if (gasi) {
                     o[0] = (float)(-w[B_DIVB] * term);
                     o[1] = (float)(-w[B_CURLX] * term);
@@ -569,9 +560,7 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     const int64_t n = c->npart, nl = c->nlive;
     const sphgpu_params &p = c->hp.p;
     CUDA_TRY(c, c->vel4.ensure(n)); CUDA_TRY(c, c->acc4.ensure(n)); if (p.mhd) CUDA_TRY(c, c->bev4.ensure(n));
-    CUDA_TRY(c, c->hnew.ensure(n)); CUDA_TRY(c, c->s_gradh.ensure(n * c->hp.ngradh)); CUDA_TRY(c, c->s_divv.ensure(n));
-    CUDA_TRY(c, c->s_dvdx.ensure(9 * n)); CUDA_TRY(c, c->s_alpha3.ensure(n)); CUDA_TRY(c, c->s_divcurlB.ensure(4 * n)); CUDA_TRY(c, c->s_nneigh.ensure(n));
-    if (p.dust) CUDA_TRY(c, c->s_dustfrac.ensure(n));
+    CUDA_TRY(c, c->hnew.ensure(n)); CUDA_TRY(c, c->s_nneigh.ensure(n));
     DensArgs a;
     memset(&a, 0, sizeof a);
     const int grid = c->numSMs * dispatch_density(c, a, -1);     // persistent grid = resident CTAs/SM x SMs
@@ -584,8 +573,8 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     a.drec = c->drec.p;
     a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.acc4 = c->acc4.p; a.bev4 = c->bev4.p; a.stype = c->stype.p; a.perm = c->perm.p;
-    a.hnew = c->hnew.p; a.s_gradh = c->s_gradh.p; a.s_divv = c->s_divv.p; a.s_dvdx = c->s_dvdx.p; a.s_alpha3 = c->s_alpha3.p;
-    a.s_divcurlB = c->s_divcurlB.p; a.s_nneigh = c->s_nneigh.p; a.s_dustfrac = c->s_dustfrac.p;
+    a.hnew = c->hnew.p; a.s_nneigh = c->s_nneigh.p;
+    a.gradh = c->gradh.p; a.divcurlv = c->divcurlv.p; a.dvdx = c->dvdx.p; a.alphaind = c->alphaind.p; a.divcurlB = c->divcurlB.p; a.dustfrac = c->dustfrac.p;
     a.multitype = c->multitype ? 1 : 0; a.max_leaf = c->max_leaf; a.hmax_global = 0.;
     a.cnt = c->counters.p; a.dscal = c->dscal.p;
     a.margin = c->list_margin; a.icall = icall;
@@ -626,9 +615,7 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
         c->err = buf; return SPHGPU_ERR_NOCONVERGE;
     }
     if (hc[CNT_ERR]) { c->err = "densityiterate: neighbour scratch overflow (raise scratch_per_warp)"; return (int)hc[CNT_ERR]; }
-    k_scatter_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->hnew.p, c->pos4.p, c->xyzh.p, c->s_gradh.p, c->s_divv.p, c->s_dvdx.p,
-                                                         c->s_alpha3.p, c->s_divcurlB.p, c->gradh.p, c->divcurlv.p, c->dvdx.p, c->alphaind.p, c->divcurlB.p,
-                                                         c->hp.ngradh, c->hp.nalpha, p.mhd, p.dust ? c->s_dustfrac.p : nullptr, c->dustfrac.p);
+    k_scatter_h<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->hnew.p, c->pos4.p, c->xyzh.p);
     c->launches++;
     sphgpu_scalars &sc = c->last_dens;
     memset(&sc, 0, sizeof sc);

@@ -106,6 +106,7 @@ __global__ void k_keys(int64_t n, const double *__restrict__ xyzh, double x0, do
         unsigned ix = (unsigned)ux, iy = (unsigned)uy, iz = (unsigned)uz;
         if (hilbert) hilbert_transpose(ix, iy, iz);
         key = (spread21((unsigned long long)ix) << 2) | (spread21((unsigned long long)iy) << 1) | spread21((unsigned long long)iz);
+        key &= ~0xFFFFull;            // 16/16/15 bits per axis decide the order (6 radix passes instead of 8); ties are split by index
     }
     keys[i] = key;
     idx[i] = (int)i;
@@ -391,14 +392,14 @@ int tree_build(sphgpu_ctx *c)
     scale *= 1.0000001;
     LAUNCH(c, k_keys, nblk(n, 256), 256, n, c->xyzh.p, lo[0], lo[1], lo[2], 1.0 / scale, c->keys_alt.p, c->perm_alt.p, c->hilbert ? 1 : 0);
     size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, c->keys_alt.p, c->keys.p, c->perm_alt.p, c->perm.p, (int)n, 0, 64, c->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, c->keys_alt.p, c->keys.p, c->perm_alt.p, c->perm.p, (int)n, 16, 64, c->stream);
     size_t tb2 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb2, c->cellflag.p, c->cellid_scan.p, (int)n, c->stream);
     tb = tb > tb2 ? tb : tb2;
     CUDA_TRY(c, c->cubtemp.ensure(tb));
     size_t tbb = c->cubtemp.cap;
-    CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(c->cubtemp.p, tbb, c->keys_alt.p, c->keys.p, c->perm_alt.p, c->perm.p, (int)n, 0, 64, c->stream));
-    c->launches += 8;
+    CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(c->cubtemp.p, tbb, c->keys_alt.p, c->keys.p, c->perm_alt.p, c->perm.p, (int)n, 16, 64, c->stream));
+    c->launches += 7;
     CUDA_TRY(c, c->pos4.ensure(n)); CUDA_TRY(c, c->stype.ensure(n)); CUDA_TRY(c, c->cpl.ensure(n));
     CUDA_TRY(c, c->cellflag.ensure(n)); CUDA_TRY(c, c->cellid_scan.ensure(n));
     LAUNCH(c, k_gather_pos, nblk(nlive, 256), 256, nlive, c->perm.p, c->xyzh.p, c->iphase.p, c->pos4.p, c->stype.p, c->keys.p, c->cpl.p, c->counters.p,
