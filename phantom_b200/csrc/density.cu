@@ -355,14 +355,14 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                 const int nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf, fs, interior);
                 nlist += nr;
                 const int nchunk = (nr + 31) >> 5;
-                build_masks<false>(ws, nr, ft);
+                unsigned nz = build_masks<false>(ws, nr, ft);
                 int c = -1; unsigned m = 0u;
                 if (FAST) {
                     int surv = 0;
                     while (true) {      // two neighbours per trip; a lane with an odd number of hits pads with itself (weight 0)
-                        const int slot0 = conv ? -1 : next_hit_s(hm_lane, nchunk, c, m);
+                        int slot0, slot1;
+                        next_hits2(hm_lane, nz, c, m, slot0, slot1);
                         if (slot0 < 0) break;
-                        const int slot1 = next_hit_s(hm_lane, nchunk, c, m);
                         const int j0 = (int)lds_u32(sidx_s + 4u * (unsigned)slot0), j1 = (slot1 >= 0) ? (int)lds_u32(sidx_s + 4u * (unsigned)slot1) : s;
                         surv += 1 + (slot1 >= 0);
                         dens_pair2_fast<K, PERIODIC, MHD, GRAV>(v, w, nneighi, j0, j1, s, pi.x, pi.y, pi.z, hi1, hi21, vi, ai, bi, a.drec, pmassi, use_da,

@@ -385,8 +385,7 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
             const int nr = stage_round<PERIODIC, true>(ws, cl, ncl, cellpos, a.frec, FSTRIDE, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs, PERIODIC && interior);
             nlist += nr;
             const int nchunk = (nr + 31) >> 5;
-            if (wide) build_masks<false>(ws, nr, ft);
-            else build_masks<true>(ws, nr, ft);
+            unsigned nz = wide ? build_masks<false>(ws, nr, ft) : build_masks<true>(ws, nr, ft);
             int c = -1; unsigned m = 0u;
             // Two neighbours per trip, written phase by phase over both so that two independent FP64 dependency chains and both
             // records are in flight.  No branches: grad W is evaluated as truncated powers (zero beyond the support), r = 0 gives
@@ -501,9 +500,9 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
                 }
             };
             while (true) {
-                const int slot0 = act ? next_hit_s(hm_lane, nchunk, c, m) : -1;
+                int slot0, slot1;
+                next_hits2(hm_lane, nz, c, m, slot0, slot1);
                 if (slot0 < 0) break;
-                const int slot1 = next_hit_s(hm_lane, nchunk, c, m);
                 const int j0 = (int)lds_u32(sidx_s + 4u * (unsigned)slot0), j1 = (slot1 >= 0) ? (int)lds_u32(sidx_s + 4u * (unsigned)slot1) : s;
                 pair2(j0, j1);
             }
