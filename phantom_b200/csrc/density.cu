@@ -25,7 +25,7 @@ namespace {
 struct DensArgs {
     const TreeNodeF *nodes; const Cell *cells; int ncells; const Cell *groups; int ngroups;
     const double4 *pos4, *vel4, *acc4, *bev4; const int8_t *stype; const int *perm;
-    const double4 *drec;     // fast path: 4 x 32 B per particle {x,y,z,h} {v,u} {f+fext} {B/rho,psi}
+    const double2 *drec;     // fast path: 5 (MHD: 7) x 16 B per particle {x,y} {z,h} {vx,vy} {vz,ax} {ay,az} [{Bx,By} {Bz,psi}], a = f + fext, B = (B/rho) rho(h)
     int *stage_idx; int multitype; int max_leaf; double hmax_global;
     WalkLists wl;       // cell lists prepared by k_walk_lists for the first pass of every group
     double *hnew; int *s_nneigh;                                   // sorted order: new h, neighbour count (< 0: not an active target)
@@ -45,7 +45,7 @@ enum { B_DIVB = 0, B_CURLX, B_CURLY, B_CURLZ, B_COUNT };
 __global__ void k_gather_dens(int64_t nlive, const int *__restrict__ perm, const double *__restrict__ vxyzu, const double *__restrict__ fxyzu,
                               const double *__restrict__ fext, const double *__restrict__ Bevol, int nvu, int mhd, const double4 *__restrict__ pos4,
                               double4 *__restrict__ vel4, double4 *__restrict__ acc4, double4 *__restrict__ bev4, double *__restrict__ hnew,
-                              int *__restrict__ s_nneigh, double4 *__restrict__ drec, double pmass, double hfact)
+                              int *__restrict__ s_nneigh, double2 *__restrict__ drec, double pmass, double hfact)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nlive) return;
@@ -53,15 +53,18 @@ __global__ void k_gather_dens(int64_t nlive, const int *__restrict__ perm, const
     const double *v = vxyzu + (size_t)nvu * i, *f = fxyzu + (size_t)nvu * i, *fe = fext + 3 * (size_t)i;
     const double4 vv = make_double4(v[0], v[1], v[2], nvu >= 4 ? v[3] : 0.);
     const double4 aa = make_double4(f[0] + fe[0], f[1] + fe[1], f[2] + fe[2], 0.);     // dens.F90:1353-1355
-    if (drec) {                                                  // packed record of the single-type fast path
-        double4 *r = drec + (mhd ? 4 : 3) * (size_t)s;
-        r[0] = pos4[s]; r[1] = vv; r[2] = aa;
+    if (drec) {                                                  // packed record of the single-type fast path (80 / 112 bytes)
+        double2 *r = drec + (mhd ? 7 : 5) * (size_t)s;
+        const double4 pp = pos4[s];
+        r[0] = make_double2(pp.x, pp.y); r[1] = make_double2(pp.z, pp.w); r[2] = make_double2(vv.x, vv.y); r[3] = make_double2(vv.z, aa.x);
+        r[4] = make_double2(aa.y, aa.z);
         if (mhd) {
             const double4 be = reinterpret_cast<const double4 *>(Bevol)[i];
-            const double rho = rhoh_d(pos4[s].w, pmass, hfact);             // rho_j of dens.F90:810, the same for every pair j enters
-            r[3] = make_double4(be.x * rho, be.y * rho, be.z * rho, be.w);
+            const double rho = rhoh_d(pp.w, pmass, hfact);                  // rho_j of dens.F90:810, the same for every pair j enters
+            r[5] = make_double2(be.x * rho, be.y * rho); r[6] = make_double2(be.z * rho, be.w);
             bev4[s] = be;
         }
+        vel4[s] = vv; acc4[s] = aa;                              // the targets read their own v, a from here
     } else {
         vel4[s] = vv; acc4[s] = aa;
         if (mhd) bev4[s] = reinterpret_cast<const double4 *>(Bevol)[i];
@@ -156,19 +159,26 @@ __device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[B_COUNT],
 // evaluated as truncated powers, a non-member (exact test fails, j == s, or the padding of an odd hit count) enters with weight 0
 // on m_j, through which every sum scales, and r = 0 gives 1/r := 0 (rsqrt_pos).  The neighbour comes as one packed record; the
 // minimum-image wrap is skipped for interior target groups.
-template <int K, bool PERIODIC, bool MHD, bool GRAV>
-__device__ __forceinline__ void dens_pair2_fast(double (&v)[29], double (&w)[B_COUNT], int &nneighi, int j0, int j1, int s, double xi, double yi, double zi,
-                                                double hi1, double hi21, const double4 &vi, const double4 &ai, const double4 &bi,
-                                                const double4 *__restrict__ drec, double pmass0, bool use_da, bool interior, double Lx, double Ly, double Lz)
+template <int K, bool PERIODIC, bool MHD, bool GRAV, int RND>
+__device__ __forceinline__ void dens_pair2_fast(double (&v)[29], double (&w)[B_COUNT], int &nneighi, int slot0, int slot1, int myslot, unsigned rec2_s,
+                                                unsigned rec1_s, unsigned sidx_s, double xi, double yi, double zi, double hi1, double hi21,
+                                                const double4 &vi, const double4 &ai, const double4 &bi, const double2 *__restrict__ drec, double pmass0,
+                                                bool use_da, bool interior, double Lx, double Ly, double Lz)
 {
     typedef SphKern<K> KF;
-    const int jj[2] = {j0, j1};
+    // a lane with an odd number of hits evaluates its first neighbour twice, the second time with weight 0
+    const int sl[2] = {slot0, slot1 >= 0 ? slot1 : slot0};
+    const bool live[2] = {slot0 != myslot, slot1 >= 0 && slot1 != myslot};
     double4 pj[2], vj[2], aj[2], bj[2];
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-        const double4 *rj = drec + (MHD ? 4 : 3) * (size_t)jj[k];
-        pj[k] = rj[0]; vj[k] = rj[1]; aj[k] = rj[2];
-        if (MHD) bj[k] = rj[3];                                              // B_j = (B/rho)_j rho(h_j), formed once per particle by k_gather_dens
+        // the position (head of the dependency chain) comes from the staging block, v and a from the packed record in global memory
+        const double2 XY = lds_d2(rec2_s + 16u * (unsigned)sl[k]);
+        pj[k] = make_double4(XY.x, XY.y, lds_d(rec1_s + 8u * (unsigned)sl[k]), 0.);
+        const double2 *rj = drec + (MHD ? 7 : 5) * (size_t)lds_u32(sidx_s + 4u * (unsigned)sl[k]);
+        const double2 B = rj[2], C = rj[3], D = rj[4];
+        vj[k] = make_double4(B.x, B.y, C.x, 0.); aj[k] = make_double4(C.y, D.x, D.y, 0.);
+        if (MHD) { const double2 E = rj[5]; bj[k] = make_double4(E.x, E.y, rj[6].x, 0.); }     // B_j = (B/rho)_j rho(h_j), formed by k_gather_dens
     }
     double dx[2], dy[2], dz[2];
 #pragma unroll
@@ -186,7 +196,7 @@ __device__ __forceinline__ void dens_pair2_fast(double (&v)[29], double (&w)[B_C
     for (int k = 0; k < 2; k++) {
         r2[k] = __dadd_rn(__dadd_rn(__dmul_rn(dx[k], dx[k]), __dmul_rn(dy[k], dy[k])), __dmul_rn(dz[k], dz[k]));
         q2i[k] = __dmul_rn(r2[k], hi21);                                      // dens.F90:675
-        const bool isn = (q2i[k] < KF::radkern2) && (jj[k] != s);             // :679, :650 (exact membership) -> 0/1 weight on m_j
+        const bool isn = (q2i[k] < KF::radkern2) && live[k];                  // :679, :650 (exact membership) -> 0/1 weight on m_j
         pmass[k] = isn ? pmass0 : 0.;
         nneighi += isn ? 1 : 0;
     }
@@ -234,6 +244,10 @@ __device__ __forceinline__ void exactlinear_d(double &gx, double &gy, double &gz
     gz = (dAx * rm[2] + dAy * rm[4] + dAz * rm[5]) * ddenom;
 }
 
+// staging block of the density kernel: the fast path keeps the candidates' FP64 positions in shared memory ({x,y} + z)
+template <bool FAST> struct DensShared { typedef WarpShared type; };
+template <> struct DensShared<true> { typedef WarpSharedT<ROUND_DEFAULT, 1, 1> type; };
+
 template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST>
 #ifndef DENS_MINB
 #define DENS_MINB 3
@@ -247,16 +261,18 @@ template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST>
 __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MHD) ? DENS_MHD_MINB : 3)) k_density(const DensArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
-    __shared__ WarpShared wsh[4];
+    typedef typename DensShared<FAST>::type WS;
+    extern __shared__ __align__(16) unsigned char dens_smem[];
     const int lane = lane_id(), wib = threadIdx.x >> 5;
-    WarpShared &ws = wsh[wib];
+    WS &ws = reinterpret_cast<WS *>(dens_smem)[wib];
     const unsigned ws_s = ws_shared_addr(ws);
-    const unsigned hm_lane = ws_s + (unsigned)offsetof(WarpShared, hm) + 4u * lane, sidx_s = ws_s + (unsigned)offsetof(WarpShared, sidx);
+    const unsigned hm_lane = ws_s + (unsigned)offsetof(WS, hm) + 4u * lane, sidx_s = ws_s + (unsigned)offsetof(WS, sidx);
+    const unsigned rec2_s = ws_s + (unsigned)offsetof(WS, rec2), rec1_s = ws_s + (unsigned)offsetof(WS, rec1);
     const int gwarp = blockIdx.x * 4 + wib;
     int *clist = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;      // cell list of the current group (the only global scratch)
-    constexpr int DSTRIDE = MHD ? 4 : 3;                                 // double4 per packed record of the fast path
-    const double4 *posrec = FAST ? a.drec : a.pos4;
-    const int pstride = FAST ? DSTRIDE : 1;
+    constexpr int DSTRIDE = MHD ? 7 : 5;                                 // double2 per packed record of the fast path
+    const double2 *posrec = FAST ? a.drec : reinterpret_cast<const double2 *>(a.pos4);
+    const int pstride = FAST ? DSTRIDE : 2;
     const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
     const float fLx = (float)Lx, fLy = (float)Ly, fLz = (float)Lz;
     const double radkern = KF::radkern;
@@ -286,7 +302,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
         const double4 pi = a.pos4[s];
         double4 vi, ai, bi = make_double4(0., 0., 0., 0.);
         double4 bevi = make_double4(0., 0., 0., 0.);            // (B/rho, psi) of the target; the fast pair body takes B = (B/rho) rho(h) of the current iterate
-        if (FAST) { const double4 *r = a.drec + DSTRIDE * (size_t)s; vi = r[1]; ai = r[2]; if (MHD && gasi) bevi = a.bev4[s]; }
+        if (FAST) { vi = a.vel4[s]; ai = a.acc4[s]; if (MHD && gasi) bevi = a.bev4[s]; }
         else { vi = a.vel4[s]; ai = a.acc4[s]; if (MHD && gasi) bi = a.bev4[s]; }
         const double pmassi = dp.p.massoftype[itypei];
         const float xif = (float)(pi.x - cx), yif = (float)(pi.y - cy), zif = (float)(pi.z - cz);
@@ -352,21 +368,25 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
             if (FAST && MHD) { const double rhoi = rhoh_d(h, pmassi, dp.p.hfact); bi = make_double4(bevi.x * rhoi, bevi.y * rhoi, bevi.z * rhoi, bevi.w); }
             int nlist = 0;
             for (int cellpos = 0; cellpos < ncl;) {                  // rounds of <= ROUND candidates staged in shared memory
-                const int nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf, fs, interior);
+                auto stage_rec = [&](int slot, int, const double2 &xy, const double2 &zw) {      // fast path: FP64 positions to shared memory
+                    if (FAST) { ws.rec2[0][slot] = xy; ws.rec1[0][slot] = zw.x; }
+                };
+                const int nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf, fs, interior,
+                                                            cell.start, stage_rec);
                 nlist += nr;
                 const int nchunk = (nr + 31) >> 5;
                 unsigned nz = build_masks<false>(ws, nr, ft);
                 int c = -1; unsigned m = 0u;
                 if (FAST) {
                     int surv = 0;
-                    while (true) {      // two neighbours per trip; a lane with an odd number of hits pads with itself (weight 0)
+                    const int myslot = ws.selfslot[lane];
+                    while (true) {      // two neighbours per trip
                         int slot0, slot1;
                         next_hits2(hm_lane, nz, c, m, slot0, slot1);
                         if (slot0 < 0) break;
-                        const int j0 = (int)lds_u32(sidx_s + 4u * (unsigned)slot0), j1 = (slot1 >= 0) ? (int)lds_u32(sidx_s + 4u * (unsigned)slot1) : s;
                         surv += 1 + (slot1 >= 0);
-                        dens_pair2_fast<K, PERIODIC, MHD, GRAV>(v, w, nneighi, j0, j1, s, pi.x, pi.y, pi.z, hi1, hi21, vi, ai, bi, a.drec, pmassi, use_da,
-                                                                interior, Lx, Ly, Lz);
+                        dens_pair2_fast<K, PERIODIC, MHD, GRAV, WS::ROUND>(v, w, nneighi, slot0, slot1, myslot, rec2_s, rec1_s, sidx_s, pi.x, pi.y, pi.z, hi1, hi21,
+                                                                           vi, ai, bi, a.drec, pmassi, use_da, interior, Lx, Ly, Lz);
                     }
                     st_surv += surv;
                 } else
@@ -515,12 +535,14 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
 template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST>
 int launch_density(sphgpu_ctx *c, const DensArgs &a, int grid)
 {
+    const size_t smem = 4 * sizeof(typename DensShared<FAST>::type);
+    cudaFuncSetAttribute(k_density<K, PERIODIC, MHD, GRAV, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (grid < 0) {
         int bps = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_density<K, PERIODIC, MHD, GRAV, FAST>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_density<K, PERIODIC, MHD, GRAV, FAST>, 128, smem);
         return bps < 1 ? 1 : bps;
     }
-    k_density<K, PERIODIC, MHD, GRAV, FAST><<<grid, 128, 0, c->stream>>>(a, c->hp);
+    k_density<K, PERIODIC, MHD, GRAV, FAST><<<grid, 128, smem, c->stream>>>(a, c->hp);
     c->launches++;
     return 0;
 }
@@ -568,9 +590,9 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     if (fast) CUDA_TRY(c, c->drec.ensure(4 * (size_t)n));
     CUDA_TRY(c, c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp));
     k_gather_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->vxyzu.p, c->fxyzu.p, c->fext.p, c->Bevol.p, c->hp.nvu, p.mhd, c->pos4.p, c->vel4.p,
-                                                        c->acc4.p, c->bev4.p, c->hnew.p, c->s_nneigh.p, fast ? c->drec.p : nullptr, p.massoftype[IGAS], p.hfact);
+                                                        c->acc4.p, c->bev4.p, c->hnew.p, c->s_nneigh.p, fast ? reinterpret_cast<double2 *>(c->drec.p) : nullptr, p.massoftype[IGAS], p.hfact);
     c->launches++;
-    a.drec = c->drec.p;
+    a.drec = reinterpret_cast<const double2 *>(c->drec.p);
     a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.acc4 = c->acc4.p; a.bev4 = c->bev4.p; a.stype = c->stype.p; a.perm = c->perm.p;
     a.hnew = c->hnew.p; a.s_nneigh = c->s_nneigh.p;

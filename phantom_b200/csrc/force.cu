@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
         double vsigmax = 0.;
         int npair = 0, ibin_neigh = 0;
         for (int cellpos = 0; cellpos < ncl;) {                     // rounds of <= ROUND candidates staged in shared memory
-            const int nr = stage_round<PERIODIC, true>(ws, cl, ncl, cellpos, a.frec, FSTRIDE, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs, PERIODIC && interior);
+            const int nr = stage_round<PERIODIC, true>(ws, cl, ncl, cellpos, reinterpret_cast<const double2 *>(a.frec), 2 * FSTRIDE, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs, PERIODIC && interior);
             nlist += nr;
             const int nchunk = (nr + 31) >> 5;
             unsigned nz = wide ? build_masks<false>(ws, nr, ft) : build_masks<true>(ws, nr, ft);
@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
         int npair = 0;
         XtraSums xs; xs.fdx = xs.fdy = xs.fdz = 0.; xs.tsmin = 1.e29; xs.ibin_neigh = 0;
         for (int cellpos = 0; cellpos < ncl;) {                     // rounds of <= ROUND candidates staged in shared memory
-            const int nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, a.pos4, 1, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs);
+            const int nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, reinterpret_cast<const double2 *>(a.pos4), 2, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs);
             nlist += nr;
             const int nchunk = (nr + 31) >> 5;
             if (wide) build_masks<false>(ws, nr, ft);

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(128) k_neigh(const TreeNodeF *nodes, const Cel
         int nfound[32];                                      // per target of the cell (max_leaf <= 32), kept across rounds
         for (int t = 0; t < 32; t++) nfound[t] = 0;
         for (int cellpos = 0; cellpos < ncl;) {
-          const int nlist = stage_round<PERIODIC, false>(ws, clist, ncl, cellpos, pos4, 1, cx, cy, cz, Lx, Ly, Lz, (float)radkern, max_leaf, fs);
+          const int nlist = stage_round<PERIODIC, false>(ws, clist, ncl, cellpos, reinterpret_cast<const double2 *>(pos4), 2, cx, cy, cz, Lx, Ly, Lz, (float)radkern, max_leaf, fs);
           const int *list = ws.sidx;
           for (int t = 0; t < cell.count; t++) {
             const int s = cell.start + t;

@@ -22,17 +22,25 @@
 #include <cuda_fp16.h>
 
 #define WALK_STACK 256
-#ifndef ROUND
-#define ROUND 384              // staged candidates per round
+#ifndef ROUND_DEFAULT
+#define ROUND_DEFAULT 384      // staged candidates per round
 #endif
-#define NCHUNK (ROUND / 32)
 
-struct WarpShared {
+// Per-warp staging block.  ROUND_ candidates per round; the fast kernels also keep P2_ double2 parts + P1_ double parts of each
+// candidate (its FP64 position) here: the L1 data pipe was the measured limiter of the pair loops (82-93 % busy with wavefronts,
+// one per lane and 16-byte load of a gathered record), and a shared-memory gather of 32 different addresses costs a few wavefronts.
+template <int ROUND_, int P2_, int P1_>
+struct __align__(16) WarpSharedT {
+    static constexpr int ROUND = ROUND_, NCHUNK = ROUND_ / 32, P2 = P2_, P1 = P1_;
     int stack[WALK_STACK];
     uint4 hp[NCHUNK][16];               // staged candidates, two per word: half2 {x, y, z, limit}; slot c*32+b sits in word b&15, half b>>4
-    int sidx[ROUND];                    // their sorted particle slots
+    int sidx[ROUND_];                   // their sorted particle slots
     unsigned hm[NCHUNK][32];            // hm[chunk][t] = candidates of the chunk inside target t's (FP16, conservative) radius
+    int selfslot[32];                   // slot at which target t itself is staged in this round, -1 if it is not
+    double2 rec2[P2_ > 0 ? P2_ : 1][P2_ > 0 ? ROUND_ : 1];     // structure of arrays: conflict-free staging stores
+    double rec1[P1_ > 0 ? P1_ : 1][P1_ > 0 ? ROUND_ : 1];
 };
+typedef WarpSharedT<ROUND_DEFAULT, 0, 0> WarpShared;     // general kernels: everything else is gathered from global memory
 
 // Scale of the FP16 filter of one target group: coordinates relative to the group centre times `scale` lie in [-1, 1].
 struct FilterScale { float scale, slack; };
@@ -219,12 +227,17 @@ __device__ __forceinline__ FilterTarget filter_target(const FilterScale &fs, flo
 // Copy the particles of the next cells of the list into the shared-memory round buffer.  Two passes so that no load waits on another:
 // (1) lane = cell, 32 cells per step: one coalesced read of the packed list, a warp scan of the counts, slot -> particle index;
 // (2) lane = slot: the position records of all slots are fetched independently, scaled to FP16 and stored.
-// posrec[j * stride] = {x, y, z, w} with w = h (WINV = false) or 1/h (WINV = true).  Returns the number staged; cellpos advances.
-template <bool PERIODIC, bool WINV>
-__device__ __forceinline__ int stage_round(WarpShared &ws, const int *__restrict__ clist, int ncl, int &cellpos, const double4 *__restrict__ posrec, int stride,
+// w = h (WINV = false) or 1/h (WINV = true).  Returns the number staged; cellpos advances.
+struct NoRecord { __device__ __forceinline__ void operator()(int, int, const double2 &, const double2 &) const {} };
+// posrec2[j * stride2] = {x, y}, [j * stride2 + 1] = {z, w}.  gstart: first sorted slot of the target group (selfslot bookkeeping);
+// stage_rec(slot, j, xy, zw): whatever else the caller wants staged.
+template <bool PERIODIC, bool WINV, class WS, class F = NoRecord>
+__device__ __forceinline__ int stage_round(WS &ws, const int *__restrict__ clist, int ncl, int &cellpos, const double2 *__restrict__ posrec2, int stride2,
                                            double cx, double cy, double cz, double Lx, double Ly, double Lz, float radkern, int maxleaf,
-                                           const FilterScale &fs, bool interior = false)
+                                           const FilterScale &fs, bool interior = false, int gstart = 0, F stage_rec = F())
 {
+    constexpr int ROUND = WS::ROUND;
+    ws.selfslot[lane_id()] = -1;
     const int lane = lane_id();
     int n = 0;
     while (cellpos < ncl) {
@@ -244,7 +257,8 @@ __device__ __forceinline__ int stage_round(WarpShared &ws, const int *__restrict
 #pragma unroll 4
     for (int slot = lane; slot < n; slot += 32) {
         const int j = ws.sidx[slot];
-        const double4 p = posrec[(size_t)j * stride];
+        const double2 pxy = posrec2[(size_t)j * stride2], pzw = posrec2[(size_t)j * stride2 + 1];
+        const double4 p = make_double4(pxy.x, pxy.y, pzw.x, pzw.y);
         double rx = p.x - cx, ry = p.y - cy, rz = p.z - cz;
         if (PERIODIC && !interior) {                  // interior: no candidate of this group lies across the periodic boundary
             if (rx > 0.5 * Lx) rx -= Lx; else if (rx < -0.5 * Lx) rx += Lx;
@@ -259,6 +273,9 @@ __device__ __forceinline__ int stage_round(WarpShared &ws, const int *__restrict
                     uz = fminf(fmaxf((float)rz * fs.scale, -8.f), 8.f);
         __half *w = reinterpret_cast<__half *>(&ws.hp[slot >> 5][slot & 15]) + ((slot >> 4) & 1);
         w[0] = __float2half_rn(ux); w[2] = __float2half_rn(uy); w[4] = __float2half_rn(uz); w[6] = filter_limit(fs, rkh);
+        const unsigned t = (unsigned)(j - gstart);
+        if (t < 32u) ws.selfslot[t] = slot;
+        stage_rec(slot, j, pxy, pzw);
     }
     __syncwarp();
     return n;
@@ -267,8 +284,8 @@ __device__ __forceinline__ int stage_round(WarpShared &ws, const int *__restrict
 // hit masks for the n staged candidates of the round: lane = target, loop over candidate pairs.  SYM: a pair passes when it is
 // inside the target's OR the candidate's radius (force pass); targets with limit 0 (inactive, converged) get empty masks.
 // Returns the lane's non-empty chunks as a bit mask (NCHUNK <= 32).
-template <bool SYM>
-__device__ __forceinline__ unsigned build_masks(WarpShared &ws, int n, const FilterTarget &t)
+template <bool SYM, class WS>
+__device__ __forceinline__ unsigned build_masks(WS &ws, int n, const FilterTarget &t)
 {
     unsigned nz = 0u;
     const int lane = lane_id();
@@ -296,7 +313,8 @@ __device__ __forceinline__ unsigned build_masks(WarpShared &ws, int n, const Fil
 }
 
 // advance this lane to its next hit; returns the staged slot or -1 when the lane has consumed all its hits of the round
-__device__ __forceinline__ int next_hit(const WarpShared &ws, int lane, int nchunk, int &c, unsigned &m)
+template <class WS>
+__device__ __forceinline__ int next_hit(const WS &ws, int lane, int nchunk, int &c, unsigned &m)
 {
     while (m == 0u) {
         if (++c >= nchunk) return -1;
@@ -309,11 +327,24 @@ __device__ __forceinline__ int next_hit(const WarpShared &ws, int lane, int nchu
 
 // The same through an explicit 32-bit shared-window address.  The address is made opaque once per kernel so that the compiler keeps
 // it in a register; otherwise it re-derives it (S2R + LEA + IMAD) at every use inside the pair loop.
-__device__ __forceinline__ unsigned ws_shared_addr(const WarpShared &ws)
+template <class WS>
+__device__ __forceinline__ unsigned ws_shared_addr(const WS &ws)
 {
     unsigned a = (unsigned)__cvta_generic_to_shared(&ws);
     asm volatile("mov.u32 %0, %0;" : "+r"(a));
     return a;
+}
+__device__ __forceinline__ double2 lds_d2(unsigned addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_d(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ unsigned lds_u32(unsigned addr)
 {
