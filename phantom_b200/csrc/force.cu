@@ -303,9 +303,15 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
 // Same sums as force_pair above, restructured for instruction count: one packed 96/128/160-byte record per neighbour instead of
 // five gathers, the minimum-image wrap is skipped for target groups whose search region lies inside the box, and terms that vanish
 // with grad W (q2 >= R^2) are not masked separately.
+// staging block of the fast force kernel: the candidates' {x, y} {z, 1/h} (first 32 bytes of the packed record) stay in shared memory.
+// Not with MHD: three resident CTAs of this block leave only ~28 KB of L1 for the 128 remaining bytes of each MHD record, which costs
+// more than the staged part saves (measured: mhdblast force 23.5 -> 29.1 ms).
+template <bool MHD> struct ForceFastSharedT { typedef WarpSharedT<ROUND_DEFAULT, 2, 0, false> type; };
+template <> struct ForceFastSharedT<true> { typedef WarpShared type; };
+
 template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS>
 #ifndef FORCE_MINB
-#define FORCE_MINB 4
+#define FORCE_MINB 3
 #endif
 #ifndef FORCE_MHD_MINB
 #define FORCE_MHD_MINB 3
@@ -313,11 +319,13 @@ template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS>
 __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_MINB)) k_force_fast(const ForceArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
-    __shared__ WarpShared wsh[4];
+    typedef typename ForceFastSharedT<MHD>::type WS;
+    extern __shared__ __align__(16) unsigned char force_smem[];
     const int lane = lane_id(), wib = threadIdx.x >> 5;
-    WarpShared &ws = wsh[wib];
+    WS &ws = reinterpret_cast<WS *>(force_smem)[wib];
     const unsigned ws_s = ws_shared_addr(ws);
-    const unsigned hm_lane = ws_s + (unsigned)offsetof(WarpShared, hm) + 4u * lane, sidx_s = ws_s + (unsigned)offsetof(WarpShared, sidx);
+    const unsigned hm_lane = ws_s + (unsigned)offsetof(WS, hm) + 4u * lane, sidx_s = ws_s + (unsigned)offsetof(WS, sidx);
+    const unsigned rec2_s = ws_s + (unsigned)offsetof(WS, rec2);
     const int gwarp = blockIdx.x * 4 + wib;
     int *clist = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;      // cell list of the current group (the only global scratch)
     const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
@@ -357,7 +365,7 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
         int ncl = a.wl.ncl[cellid];
         if (ncl >= 0) { cl = a.wl.list + (size_t)cellid * a.wl.cap; reach = a.wl.reach[cellid]; }
         else ncl = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut), __double2float_ru(KF::radkern * a.hscale),
-                                             fLx, fLy, fLz, ws.stack, clist, a.scratch_per_warp, reach);
+                                             fLx, fLy, fLz, ws.walk_stack(), clist, a.scratch_per_warp, reach);
         if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
         int nlist = 0;
         const FilterScale fs = filter_scale((float)halfext, reach);
@@ -382,7 +390,10 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
         double vsigmax = 0.;
         int npair = 0, ibin_neigh = 0;
         for (int cellpos = 0; cellpos < ncl;) {                     // rounds of <= ROUND candidates staged in shared memory
-            const int nr = stage_round<PERIODIC, true>(ws, cl, ncl, cellpos, reinterpret_cast<const double2 *>(a.frec), 2 * FSTRIDE, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs, PERIODIC && interior);
+            auto stage_rec = [&](int slot, int, const double2 &xy, const double2 &zw) { if (WS::P2 > 0) { ws.rec2[0][slot] = xy; ws.rec2[WS::P2 - 1][slot] = zw; } };
+            const int nr = stage_round<PERIODIC, true>(ws, cl, ncl, cellpos, reinterpret_cast<const double2 *>(a.frec), 2 * FSTRIDE, cx, cy, cz, Lx, Ly, Lz,
+                                                       (float)KF::radkern, a.max_leaf, fs, PERIODIC && interior, cell.start, stage_rec);
+            const int myslot = ws.selfslot[lane];
             nlist += nr;
             const int nchunk = (nr + 31) >> 5;
             unsigned nz = wide ? build_masks<false>(ws, nr, ft) : build_masks<true>(ws, nr, ft);
@@ -391,13 +402,22 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
             // records are in flight.  No branches: grad W is evaluated as truncated powers (zero beyond the support), r = 0 gives
             // 1/r := 0, so a non-member (exact test fails, j == s, or the self padding of an odd hit count) adds exact zeros;
             // only the pair count, the signal-speed maximum and the softened gravity need the membership flags.
-            auto pair2 = [&](int j0, int j1) {
-                const int jj[2] = {j0, j1};
+            auto pair2 = [&](int slot0, int slot1) {
+                // a lane with an odd number of hits evaluates its first neighbour twice, the second time as a non-member
+                const int sl[2] = {slot0, slot1 >= 0 ? slot1 : slot0};
+                const bool live[2] = {slot0 != myslot, slot1 >= 0 && slot1 != myslot};
+                int jj[2];
                 double4 R0[2], R1[2], R2[2], R3[2], E[2];
 #pragma unroll
                 for (int k = 0; k < 2; k++) {
+                    // {x,y,z,1/h} (head of the dependency chain) from the staging block, the rest of the packed record from global memory
+                    jj[k] = (int)lds_u32(sidx_s + 4u * (unsigned)sl[k]);
                     const double4 *rj = a.frec + FSTRIDE * (size_t)jj[k];
-                    R0[k] = rj[0]; R1[k] = rj[1]; R2[k] = rj[2];
+                    if (WS::P2 > 0) {
+                        const double2 XY = lds_d2(rec2_s + 16u * (unsigned)sl[k]), ZW = lds_d2(rec2_s + 16u * (unsigned)(WS::ROUND + sl[k]));
+                        R0[k] = make_double4(XY.x, XY.y, ZW.x, ZW.y);
+                    } else R0[k] = rj[0];
+                    R1[k] = rj[1]; R2[k] = rj[2];
                     if (ADIA || GRAV) R3[k] = rj[3];
                     if (MHD) E[k] = rj[4];
                 }
@@ -419,8 +439,7 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
                     r2[k] = __dadd_rn(__dadd_rn(__dmul_rn(dx[k], dx[k]), __dmul_rn(dy[k], dy[k])), __dmul_rn(dz[k], dz[k]));
                     const double hj1 = R0[k].w;
                     const double q2i = __dmul_rn(r2[k], hi21), q2j = __dmul_rn(r2[k], __dmul_rn(hj1, hj1));       // force.F90:1272, :1285
-                    const bool notself = (jj[k] != s);
-                    ini[k] = (q2i < KF::radkern2) && notself; inj[k] = (q2j < KF::radkern2) && notself;          // :1287, :1230 (exact membership)
+                    ini[k] = (q2i < KF::radkern2) && live[k]; inj[k] = (q2j < KF::radkern2) && live[k];          // :1287, :1230 (exact membership)
                     isn[k] = ini[k] || inj[k];
                     npair += isn[k] ? 1 : 0;
                     if (indts && isn[k] && abs((int)a.stype[jj[k]]) != IBOUNDARY) {   // j neighbours an active particle: wake flag, Saitoh-Makino input
@@ -433,8 +452,9 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
 #pragma unroll
                 for (int k = 0; k < 2; k++) {
                     const double rij = r2[k] * rij1[k];
-                    grkerni[k] = KF::grkern_bf(rij * hi1) * gi;                          // :1301-1302
-                    grkernj[k] = KF::grkern_bf(rij * R0[k].w) * R1[k].w;                 // :1325-1327
+                    // the padding repeats a real neighbour: it (and the self pair) enter with weight 0 on both gradients
+                    grkerni[k] = KF::grkern_bf(rij * hi1) * (live[k] ? gi : 0.);         // :1301-1302
+                    grkernj[k] = KF::grkern_bf(rij * R0[k].w) * (live[k] ? R1[k].w : 0.);   // :1325-1327
                 }
 #pragma unroll
                 for (int k = 0; k < 2; k++) {
@@ -503,8 +523,7 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
                 int slot0, slot1;
                 next_hits2(hm_lane, nz, c, m, slot0, slot1);
                 if (slot0 < 0) break;
-                const int j0 = (int)lds_u32(sidx_s + 4u * (unsigned)slot0), j1 = (slot1 >= 0) ? (int)lds_u32(sidx_s + 4u * (unsigned)slot1) : s;
-                pair2(j0, j1);
+                pair2(slot0, slot1);
             }
             __syncwarp();
         }
@@ -836,12 +855,14 @@ int launch_force_general(sphgpu_ctx *c, const ForceArgs &a, int grid)
 template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS>
 int launch_force_fast2(sphgpu_ctx *c, const ForceArgs &a, int grid)
 {
+    const size_t smem = 4 * sizeof(typename ForceFastSharedT<MHD>::type);
+    cudaFuncSetAttribute(k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (grid < 0) {
         int bps = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS>, 128, smem);
         return bps < 1 ? 1 : bps;
     }
-    k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS><<<grid, 128, 0, c->stream>>>(a, c->hp);
+    k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS><<<grid, 128, smem, c->stream>>>(a, c->hp);
     c->launches++;
     return 0;
 }

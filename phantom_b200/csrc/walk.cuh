@@ -29,10 +29,13 @@
 // Per-warp staging block.  ROUND_ candidates per round; the fast kernels also keep P2_ double2 parts + P1_ double parts of each
 // candidate (its FP64 position) here: the L1 data pipe was the measured limiter of the pair loops (82-93 % busy with wavefronts,
 // one per lane and 16-byte load of a gathered record), and a shared-memory gather of 32 different addresses costs a few wavefronts.
-template <int ROUND_, int P2_, int P1_>
+// OWNSTACK = false: the walk stack (only used by the rare in-kernel walk, before anything is staged) lives in the rec2 area.
+template <int ROUND_, int P2_, int P1_, bool OWNSTACK = true>
 struct __align__(16) WarpSharedT {
     static constexpr int ROUND = ROUND_, NCHUNK = ROUND_ / 32, P2 = P2_, P1 = P1_;
-    int stack[WALK_STACK];
+    static_assert(OWNSTACK || (size_t)P2_ * ROUND_ * 16 >= WALK_STACK * sizeof(int), "rec2 too small to hold the walk stack");
+    int stack[OWNSTACK ? WALK_STACK : 4];
+    __device__ __forceinline__ int *walk_stack() { return OWNSTACK ? stack : reinterpret_cast<int *>(&rec2[0][0]); }
     uint4 hp[NCHUNK][16];               // staged candidates, two per word: half2 {x, y, z, limit}; slot c*32+b sits in word b&15, half b>>4
     int sidx[ROUND_];                   // their sorted particle slots
     unsigned hm[NCHUNK][32];            // hm[chunk][t] = candidates of the chunk inside target t's (FP16, conservative) radius
