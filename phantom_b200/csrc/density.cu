@@ -25,7 +25,7 @@ namespace {
 struct DensArgs {
     const TreeNodeF *nodes; const Cell *cells; int ncells; const Cell *groups; int ngroups;
     const double4 *pos4, *vel4, *acc4, *bev4; const int8_t *stype; const int *perm;
-    const double2 *drec;     // fast path: 5 (MHD: 7) x 16 B per particle {x,y} {z,h} {vx,vy} {vz,ax} {ay,az} [{Bx,By} {Bz,psi}], a = f + fext, B = (B/rho) rho(h)
+    const double4 *drec;     // fast path: 3 (MHD: 4) x 32 B per particle {x,y,z,h} {vx,vy,vz,ax} {ay,az,Bx,By} [{Bz,psi,-,-}], a = f + fext, B = (B/rho) rho(h)
     int *stage_idx; int multitype; int max_leaf; double hmax_global;
     WalkLists wl;       // cell lists prepared by k_walk_lists for the first pass of every group
     double *hnew; int *s_nneigh;                                   // sorted order: new h, neighbour count (< 0: not an active target)
@@ -45,7 +45,7 @@ enum { B_DIVB = 0, B_CURLX, B_CURLY, B_CURLZ, B_COUNT };
 __global__ void k_gather_dens(int64_t nlive, const int *__restrict__ perm, const double *__restrict__ vxyzu, const double *__restrict__ fxyzu,
                               const double *__restrict__ fext, const double *__restrict__ Bevol, int nvu, int mhd, const double4 *__restrict__ pos4,
                               double4 *__restrict__ vel4, double4 *__restrict__ acc4, double4 *__restrict__ bev4, double *__restrict__ hnew,
-                              int *__restrict__ s_nneigh, double2 *__restrict__ drec, double pmass, double hfact)
+                              int *__restrict__ s_nneigh, double4 *__restrict__ drec, double pmass, double hfact)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nlive) return;
@@ -53,17 +53,18 @@ __global__ void k_gather_dens(int64_t nlive, const int *__restrict__ perm, const
     const double *v = vxyzu + (size_t)nvu * i, *f = fxyzu + (size_t)nvu * i, *fe = fext + 3 * (size_t)i;
     const double4 vv = make_double4(v[0], v[1], v[2], nvu >= 4 ? v[3] : 0.);
     const double4 aa = make_double4(f[0] + fe[0], f[1] + fe[1], f[2] + fe[2], 0.);     // dens.F90:1353-1355
-    if (drec) {                                                  // packed record of the single-type fast path (80 / 112 bytes)
-        double2 *r = drec + (mhd ? 7 : 5) * (size_t)s;
+    if (drec) {                                                  // packed record of the single-type fast path (96 / 128 bytes)
+        double4 *r = drec + (mhd ? 4 : 3) * (size_t)s;
         const double4 pp = pos4[s];
-        r[0] = make_double2(pp.x, pp.y); r[1] = make_double2(pp.z, pp.w); r[2] = make_double2(vv.x, vv.y); r[3] = make_double2(vv.z, aa.x);
-        r[4] = make_double2(aa.y, aa.z);
+        double4 be = make_double4(0., 0., 0., 0.);
+        double rho = 0.;
         if (mhd) {
-            const double4 be = reinterpret_cast<const double4 *>(Bevol)[i];
-            const double rho = rhoh_d(pp.w, pmass, hfact);                  // rho_j of dens.F90:810, the same for every pair j enters
-            r[5] = make_double2(be.x * rho, be.y * rho); r[6] = make_double2(be.z * rho, be.w);
+            be = reinterpret_cast<const double4 *>(Bevol)[i];
+            rho = rhoh_d(pp.w, pmass, hfact);                               // rho_j of dens.F90:810, the same for every pair j enters
             bev4[s] = be;
         }
+        r[0] = pp; r[1] = make_double4(vv.x, vv.y, vv.z, aa.x); r[2] = make_double4(aa.y, aa.z, be.x * rho, be.y * rho);
+        if (mhd) r[3] = make_double4(be.z * rho, be.w, 0., 0.);
         vel4[s] = vv; acc4[s] = aa;                              // the targets read their own v, a from here
     } else {
         vel4[s] = vv; acc4[s] = aa;
@@ -96,9 +97,9 @@ __device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[B_COUNT],
 {
     typedef SphKern<K> KF;
     const int j = (slot >= 0) ? idxlist[slot] : s;
-    const double4 pj = a.pos4[j];
-    const double4 vj = a.vel4[j];
-    const double4 aj = a.acc4[j];
+    const double4 pj = ldg256(a.pos4 + j);
+    const double4 vj = ldg256(a.vel4 + j);
+    const double4 aj = ldg256(a.acc4 + j);
     double dx, dy, dz;
     const double r2 = pair_r2<PERIODIC>(pi.x, pi.y, pi.z, pj, Lx, Ly, Lz, dx, dy, dz);
     const double q2i = __dmul_rn(r2, hi21);                                   // dens.F90:675
@@ -143,7 +144,7 @@ __device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[B_COUNT],
         const double pmassi = dp.p.massoftype[itypei];
         const double rhoi = rhoh_d(hi, pmassi, dp.p.hfact);
         const double rhoj = rhoh_d(pj.w, pmj, dp.p.hfact);
-        const double4 bj = a.bev4[j];
+        const double4 bj = ldg256(a.bev4 + j);
         const double dBx = (bi.x * rhoi - bj.x * rhoj) * g, dBy = (bi.y * rhoi - bj.y * rhoj) * g, dBz = (bi.z * rhoi - bj.z * rhoj) * g;
         w[B_DIVB] += dBx * runix + dBy * runiy + dBz * runiz;
         w[B_CURLX] += dBz * runiy - dBy * runiz;          // dBz/dy - dBy/dz
@@ -162,7 +163,7 @@ __device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[B_COUNT],
 template <int K, bool PERIODIC, bool MHD, bool GRAV, int RND>
 __device__ __forceinline__ void dens_pair2_fast(double (&v)[29], double (&w)[B_COUNT], int &nneighi, int slot0, int slot1, int myslot, unsigned rec2_s,
                                                 unsigned rec1_s, unsigned sidx_s, double xi, double yi, double zi, double hi1, double hi21,
-                                                const double4 &vi, const double4 &ai, const double4 &bi, const double2 *__restrict__ drec, double pmass0,
+                                                const double4 &vi, const double4 &ai, const double4 &bi, const double4 *__restrict__ drec, double pmass0,
                                                 bool use_da, bool interior, double Lx, double Ly, double Lz)
 {
     typedef SphKern<K> KF;
@@ -175,10 +176,16 @@ __device__ __forceinline__ void dens_pair2_fast(double (&v)[29], double (&w)[B_C
         // the position (head of the dependency chain) comes from the staging block, v and a from the packed record in global memory
         const double2 XY = lds_d2(rec2_s + 16u * (unsigned)sl[k]);
         pj[k] = make_double4(XY.x, XY.y, lds_d(rec1_s + 8u * (unsigned)sl[k]), 0.);
-        const double2 *rj = drec + (MHD ? 7 : 5) * (size_t)lds_u32(sidx_s + 4u * (unsigned)sl[k]);
-        const double2 B = rj[2], C = rj[3], D = rj[4];
-        vj[k] = make_double4(B.x, B.y, C.x, 0.); aj[k] = make_double4(C.y, D.x, D.y, 0.);
-        if (MHD) { const double2 E = rj[5]; bj[k] = make_double4(E.x, E.y, rj[6].x, 0.); }     // B_j = (B/rho)_j rho(h_j), formed by k_gather_dens
+        const double4 *rj = drec + (MHD ? 4 : 3) * (size_t)lds_u32(sidx_s + 4u * (unsigned)sl[k]);
+        const double4 B = ldg256(rj + 1);                                    // {vx,vy,vz,ax} in one 256-bit load
+        vj[k] = make_double4(B.x, B.y, B.z, 0.);
+        if (MHD) {
+            const double4 C = ldg256(rj + 2);                                // {ay,az,Bx,By}; B_j = (B/rho)_j rho(h_j), formed by k_gather_dens
+            aj[k] = make_double4(B.w, C.x, C.y, 0.); bj[k] = make_double4(C.z, C.w, rj[3].x, 0.);
+        } else {
+            const double2 C = *reinterpret_cast<const double2 *>(rj + 2);    // {ay,az}
+            aj[k] = make_double4(B.w, C.x, C.y, 0.);
+        }
     }
     double dx[2], dy[2], dz[2];
 #pragma unroll
@@ -270,8 +277,8 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
     const unsigned rec2_s = ws_s + (unsigned)offsetof(WS, rec2), rec1_s = ws_s + (unsigned)offsetof(WS, rec1);
     const int gwarp = blockIdx.x * 4 + wib;
     int *clist = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;      // cell list of the current group (the only global scratch)
-    constexpr int DSTRIDE = MHD ? 7 : 5;                                 // double2 per packed record of the fast path
-    const double2 *posrec = FAST ? a.drec : reinterpret_cast<const double2 *>(a.pos4);
+    constexpr int DSTRIDE = MHD ? 8 : 6;                                 // double2 per packed record of the fast path
+    const double2 *posrec = reinterpret_cast<const double2 *>(FAST ? a.drec : a.pos4);
     const int pstride = FAST ? DSTRIDE : 2;
     const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
     const float fLx = (float)Lx, fLy = (float)Ly, fLz = (float)Lz;
@@ -590,9 +597,9 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     if (fast) CUDA_TRY(c, c->drec.ensure(4 * (size_t)n));
     CUDA_TRY(c, c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp));
     k_gather_dens<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->vxyzu.p, c->fxyzu.p, c->fext.p, c->Bevol.p, c->hp.nvu, p.mhd, c->pos4.p, c->vel4.p,
-                                                        c->acc4.p, c->bev4.p, c->hnew.p, c->s_nneigh.p, fast ? reinterpret_cast<double2 *>(c->drec.p) : nullptr, p.massoftype[IGAS], p.hfact);
+                                                        c->acc4.p, c->bev4.p, c->hnew.p, c->s_nneigh.p, fast ? c->drec.p : nullptr, p.massoftype[IGAS], p.hfact);
     c->launches++;
-    a.drec = reinterpret_cast<const double2 *>(c->drec.p);
+    a.drec = c->drec.p;
     a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.acc4 = c->acc4.p; a.bev4 = c->bev4.p; a.stype = c->stype.p; a.perm = c->perm.p;
     a.hnew = c->hnew.p; a.s_nneigh = c->s_nneigh.p;

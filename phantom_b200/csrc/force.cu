@@ -155,10 +155,10 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
     typedef SphKern<K> KF;
     const sphgpu_params &p = dp.p;
     const int j = (slot >= 0) ? idxlist[slot] : s;
-    const double4 pj = a.pos4[j];
+    const double4 pj = ldg256(a.pos4 + j);
     const double2 hj = a.hinv[j];
-    const double4 Cj = a.recC[j], Dj = a.recD[j];
-    const double4 vj = a.vel4[j];
+    const double4 Cj = ldg256(a.recC + j), Dj = ldg256(a.recD + j);
+    const double4 vj = ldg256(a.vel4 + j);
     double dx, dy, dz;
     const double r2 = pair_r2<PERIODIC>(pi.x, pi.y, pi.z, pj, Lx, Ly, Lz, dx, dy, dz);
     const double hj1 = hj.x, hj21 = hj.y;
@@ -264,7 +264,7 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
         f[A_DENDTDISS] += vsigu * denij * (auterm * grkerni + autermj * grkernj);
     }
     if (MHD) {                                                                // force.F90:1428-1444, :1626-1672, :2132-2150
-        const double4 Ej = a.recE[j];
+        const double4 Ej = ldg256(a.recE + j);
         const double Bxi = Ei.x, Byi = Ei.y, Bzi = Ei.z, psii = Ei.w;
         const double Bxj = Ej.x, Byj = Ej.y, Bzj = Ej.z, psij = Ej.w;
         const double dBx = Bxi - Bxj, dBy = Byi - Byj, dBz = Bzi - Bzj;
@@ -416,10 +416,10 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
                     if (WS::P2 > 0) {
                         const double2 XY = lds_d2(rec2_s + 16u * (unsigned)sl[k]), ZW = lds_d2(rec2_s + 16u * (unsigned)(WS::ROUND + sl[k]));
                         R0[k] = make_double4(XY.x, XY.y, ZW.x, ZW.y);
-                    } else R0[k] = rj[0];
-                    R1[k] = rj[1]; R2[k] = rj[2];
-                    if (ADIA || GRAV) R3[k] = rj[3];
-                    if (MHD) E[k] = rj[4];
+                    } else R0[k] = ldg256(rj);
+                    R1[k] = ldg256(rj + 1); R2[k] = ldg256(rj + 2);
+                    if (ADIA || GRAV) R3[k] = ldg256(rj + 3);
+                    if (MHD) E[k] = ldg256(rj + 4);
                 }
                 double dx[2], dy[2], dz[2];
 #pragma unroll

@@ -337,6 +337,14 @@ __device__ __forceinline__ unsigned ws_shared_addr(const WS &ws)
     asm volatile("mov.u32 %0, %0;" : "+r"(a));
     return a;
 }
+// One 256-bit load (sm_100: LDG.E.256) of a 32-byte-aligned double4.  A gathered record costs the L1 data pipe one wavefront per lane
+// and load INSTRUCTION, so halving the instructions halves the load on the pipe that limits the pair loops.
+__device__ __forceinline__ double4 ldg256(const double4 *p)
+{
+    double4 v;
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ double2 lds_d2(unsigned addr)
 {
     double2 v;

@@ -12,7 +12,9 @@ METRICS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__gr
            "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
            "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
-           "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"] + \
+           "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+           "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+           "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"] + \
           ["smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % k for k in
            ("long_scoreboard", "short_scoreboard", "wait", "math_pipe_throttle", "not_selected", "branch_resolving", "no_instruction",
             "dispatch_stall", "mio_throttle", "lg_throttle", "barrier")]
