@@ -303,15 +303,18 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
 // Same sums as force_pair above, restructured for instruction count: one packed 96/128/160-byte record per neighbour instead of
 // five gathers, the minimum-image wrap is skipped for target groups whose search region lies inside the box, and terms that vanish
 // with grad W (q2 >= R^2) are not masked separately.
-// staging block of the fast force kernel: the candidates' {x, y} {z, 1/h} (first 32 bytes of the packed record) stay in shared memory.
-// Not with MHD: three resident CTAs of this block leave only ~28 KB of L1 for the 128 remaining bytes of each MHD record, which costs
-// more than the staged part saves (measured: mhdblast force 23.5 -> 29.1 ms).
-template <bool MHD> struct ForceFastSharedT { typedef WarpSharedT<ROUND_DEFAULT, 2, 0, false> type; };
+// staging block of the fast force kernel.  FORCE_STAGE = 1 keeps the candidates' {x, y} {z, 1/h} (first 32 bytes of the packed record) in
+// shared memory; measured slower than reading the whole record with 256-bit loads at four resident CTAs (turb 128^3: 1.45 vs 1.38 ms),
+// and much slower with MHD, where three resident CTAs of the staged block leave ~28 KB of L1 (mhdblast force 23.5 -> 29.1 ms).
+#ifndef FORCE_STAGE
+#define FORCE_STAGE 0
+#endif
+template <bool MHD> struct ForceFastSharedT { typedef WarpSharedT<ROUND_DEFAULT, FORCE_STAGE ? 2 : 0, 0, !FORCE_STAGE> type; };
 template <> struct ForceFastSharedT<true> { typedef WarpShared type; };
 
 template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS>
 #ifndef FORCE_MINB
-#define FORCE_MINB 3
+#define FORCE_MINB 4
 #endif
 #ifndef FORCE_MHD_MINB
 #define FORCE_MHD_MINB 3

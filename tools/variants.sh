@@ -2,7 +2,7 @@
 # A/B builds of the pair kernels with different launch bounds / pairs per trip: builds libsphgpu_<tag>.so variants (CPU side)
 # usage: tools/variants.sh build   |   tools/variants.sh run   (run = on the GPU box: times each variant with bench.py)
 cd "$(dirname "$0")/.."
-VARIANTS=("f4:-DFORCE_MINB=4" "f3:-DFORCE_MINB=3")
+VARIANTS=("d1:-DDENS_STAGE=1" "d0m3:-DDENS_STAGE=0 -DDENS_MINB=3" "d0m4:-DDENS_STAGE=0 -DDENS_MINB=4")
 if [ "$1" == "build" ]; then
   mkdir -p build/variants
   for v in "${VARIANTS[@]}"; do
