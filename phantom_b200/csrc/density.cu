@@ -24,11 +24,12 @@ namespace {
 
 struct DensArgs {
     const TreeNodeF *nodes; const Cell *cells; int ncells; const Cell *groups; int ngroups;
-    const double4 *pos4, *vel4, *acc4, *bev4; const int8_t *stype; const int *perm;
+    double4 *pos4; const double4 *vel4, *acc4, *bev4; const int8_t *stype; const int *perm;
     const double4 *drec;     // fast path: 3 (MHD: 4) x 32 B per particle {x,y,z,h} {vx,vy,vz,ax} {ay,az,Bx,By} [{Bz,psi,-,-}], a = f + fext, B = (B/rho) rho(h)
     int *stage_idx; int multitype; int max_leaf; double hmax_global;
     WalkLists wl;       // cell lists prepared by k_walk_lists for the first pass of every group
     double *hnew; int *s_nneigh;                                   // sorted order: new h, neighbour count (< 0: not an active target)
+    double *xyzh;                                                  // caller's order (fast path writes the new h directly)
     float *gradh, *divcurlv, *dvdx, *alphaind, *divcurlB; double *dustfrac;   // caller's order, written directly by the pair kernel (index perm[s])
     double *h_hist; int *h_its; int64_t npart;     // GRAV: per-particle h after every iteration, for the node-hmax replay of gravity.cu
     int scratch_per_warp; unsigned long long *cnt; double *dscal;
@@ -71,7 +72,6 @@ __global__ void k_gather_dens(int64_t nlive, const int *__restrict__ perm, const
         }
         r[0] = pp; r[1] = make_double4(vv.x, vv.y, vv.z, aa.x); r[2] = make_double4(aa.y, aa.z, be.x * rho, be.y * rho);
         if (mhd) r[3] = make_double4(be.z * rho, be.w, 0., 0.);
-        vel4[s] = vv; acc4[s] = aa;                              // the targets read their own v, a from here
     } else {
         vel4[s] = vv; acc4[s] = aa;
         if (mhd) bev4[s] = reinterpret_cast<const double4 *>(Bevol)[i];
@@ -90,6 +90,18 @@ __global__ void k_scatter_h(int64_t nlive, const int *__restrict__ perm, const i
     const double h = hnew[s];
     pos4[s].w = h;                                       // treecache(4,:) refresh (dens.F90:1596)
     xyzh[4 * (size_t)perm[s] + 3] = h;
+}
+
+// overflow retry of the fast path: back to the h the tree was built with (k_hbuild keeps it in caller order)
+__global__ void k_restore_h_sorted(int64_t nlive, const int *__restrict__ perm, const double *__restrict__ h_build, double4 *__restrict__ pos4,
+                                   double *__restrict__ xyzh)
+{
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nlive) return;
+    const int i = perm[s];
+    const double h = h_build[i];
+    pos4[s].w = h;
+    xyzh[4 * (size_t)i + 3] = h;
 }
 
 // pair body: lane = target, j = this lane's next neighbour candidate (slot < 0: none).  Branch-free so that two
@@ -317,7 +329,12 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
         const double4 pi = a.pos4[s];
         double4 vi, ai, bi = make_double4(0., 0., 0., 0.);
         double4 bevi = make_double4(0., 0., 0., 0.);            // (B/rho, psi) of the target; the fast pair body takes B = (B/rho) rho(h) of the current iterate
-        if (FAST) { vi = a.vel4[s]; ai = a.acc4[s]; if (MHD && gasi) bevi = a.bev4[s]; }
+        if (FAST) {
+            const double4 *r = a.drec + (MHD ? 4 : 3) * (size_t)s;
+            const double4 B = r[1], C = r[2];
+            vi = make_double4(B.x, B.y, B.z, 0.); ai = make_double4(B.w, C.x, C.y, 0.);
+            if (MHD && gasi) bevi = a.bev4[s];
+        }
         else { vi = a.vel4[s]; ai = a.acc4[s]; if (MHD && gasi) bi = a.bev4[s]; }
         const double pmassi = dp.p.massoftype[itypei];
         const float xif = (float)(pi.x - cx), yif = (float)(pi.y - cy), zif = (float)(pi.z - cz);
@@ -459,8 +476,11 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
             const double omegai = 1. - dhdrhoi * gradhi;
             gradhi = 1. / omegai;
             const double hfin = dp.p.hfact * pow(pmassi / fabs(rho), 1.0 / 3.0);    // hrho, part.F90:845
-            a.hnew[s] = hfin;
             const size_t io = (size_t)a.perm[s];                                      // results go straight to the caller's arrays
+            // the new h too in the fast path (nothing in this pass reads another particle's pos4.w or xyzh; an overflow retry restores
+            // the h of build_tree first); the general path reads h_j in its pair loop and keeps the new h aside until the pass is over
+            if (FAST) { a.pos4[s].w = hfin; a.xyzh[4 * io + 3] = hfin; }
+            else a.hnew[s] = hfin;
             st_hgrow = fmax(st_hgrow, hfin / h_old);
             const float gradh4 = (float)gradhi;
             a.gradh[(size_t)dp.ngradh * io] = gradh4;
@@ -610,7 +630,7 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     a.drec = c->drec.p;
     a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.acc4 = c->acc4.p; a.bev4 = c->bev4.p; a.stype = c->stype.p; a.perm = c->perm.p;
-    a.hnew = c->hnew.p; a.s_nneigh = c->s_nneigh.p;
+    a.hnew = c->hnew.p; a.s_nneigh = c->s_nneigh.p; a.xyzh = c->xyzh.p;
     a.gradh = c->gradh.p; a.divcurlv = c->divcurlv.p; a.dvdx = c->dvdx.p; a.alphaind = c->alphaind.p; a.divcurlB = c->divcurlB.p; a.dustfrac = c->dustfrac.p;
     a.multitype = c->multitype ? 1 : 0; a.max_leaf = c->max_leaf; a.hmax_global = 0.;
     a.cnt = c->counters.p; a.dscal = c->dscal.p;
@@ -642,6 +662,10 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
         if (hc[CNT_ERR] == SPHGPU_ERR_OVERFLOW && attempt < 3 && c->scratch_per_warp < (1 << 20)) {
             c->scratch_per_warp *= 8;
             CUDA_TRY(c, c->stage_idx.ensure((size_t)grid * 4 * c->scratch_per_warp));
+            if (fast) {                        // groups that finished have already stored their new h: start again from the tree's h
+                k_restore_h_sorted<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->h_build.p, c->pos4.p, c->xyzh.p);
+                c->launches++;
+            }
             continue;
         }
         break;
@@ -652,8 +676,10 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
         c->err = buf; return SPHGPU_ERR_NOCONVERGE;
     }
     if (hc[CNT_ERR]) { c->err = "densityiterate: neighbour scratch overflow (raise scratch_per_warp)"; return (int)hc[CNT_ERR]; }
-    k_scatter_h<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->hnew.p, c->pos4.p, c->xyzh.p);
-    c->launches++;
+    if (!fast) {
+        k_scatter_h<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->s_nneigh.p, c->hnew.p, c->pos4.p, c->xyzh.p);
+        c->launches++;
+    }
     sphgpu_scalars &sc = c->last_dens;
     memset(&sc, 0, sizeof sc);
     sc.rhomax = hrhomax; sc.np = (int64_t)hc[CNT_NP];

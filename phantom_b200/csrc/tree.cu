@@ -409,11 +409,13 @@ int tree_build(sphgpu_ctx *c)
     CUDA_TRY(c, cub::DeviceScan::ExclusiveSum(c->cubtemp.p, tbb, c->cellflag.p, c->cellid_scan.p, (int)nlive, c->stream));
     c->launches += 2;
     int lastflag, lastscan;
+    unsigned long long mt = 0;
     CUDA_TRY(c, cudaMemcpyAsync(&lastflag, c->cellflag.p + (nlive - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(&lastscan, c->cellid_scan.p + (nlive - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(&mt, c->counters.p + CNT_MULTITYPE, sizeof mt, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     const int64_t M = (int64_t)lastscan + lastflag;
-    { unsigned long long mt = 0; CUDA_TRY(c, cudaMemcpy(&mt, c->counters.p + CNT_MULTITYPE, sizeof mt, cudaMemcpyDeviceToHost)); c->multitype = mt != 0; }
+    c->multitype = mt != 0;
     c->ncells = M;
     CUDA_TRY(c, c->cells.ensure(M)); CUDA_TRY(c, c->cellkeys.ensure(M)); CUDA_TRY(c, c->nodes.ensure(M)); CUDA_TRY(c, c->nodesf.ensure(M)); CUDA_TRY(c, c->nodeflag.ensure(M));
     LAUNCH(c, k_cell_starts, nblk(nlive, 256), 256, nlive, c->cellflag.p, c->cellid_scan.p, c->cells.p);
