@@ -178,7 +178,7 @@ __device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[B_COUNT],
 // evaluated as truncated powers, a non-member (exact test fails, j == s, or the padding of an odd hit count) enters with weight 0
 // on m_j, through which every sum scales, and r = 0 gives 1/r := 0 (rsqrt_pos).  The neighbour comes as one packed record; the
 // minimum-image wrap is skipped for interior target groups.
-template <int K, bool PERIODIC, bool MHD, bool GRAV, int RND>
+template <int K, bool PERIODIC, bool MHD, bool GRAV, bool STAGED>
 __device__ __forceinline__ void dens_pair2_fast(double (&v)[29], double (&w)[B_COUNT], int &nneighi, int slot0, int slot1, int myslot, unsigned rec2_s,
                                                 unsigned rec1_s, unsigned sidx_s, double xi, double yi, double zi, double hi1, double hi21,
                                                 const double4 &vi, const double4 &ai, const double4 &bi, const double4 *__restrict__ drec, double pmass0,
@@ -193,7 +193,7 @@ __device__ __forceinline__ void dens_pair2_fast(double (&v)[29], double (&w)[B_C
     for (int k = 0; k < 2; k++) {
         // the position (head of the dependency chain) comes from the staging block, v and a from the packed record in global memory
         const double4 *rj = drec + (MHD ? 4 : 3) * (size_t)lds_u32(sidx_s + 4u * (unsigned)sl[k]);
-        if (DENS_STAGE) {
+        if (STAGED) {
             const double2 XY = lds_d2(rec2_s + 16u * (unsigned)sl[k]);
             pj[k] = make_double4(XY.x, XY.y, lds_d(rec1_s + 8u * (unsigned)sl[k]), 0.);
         } else pj[k] = ldg256(rj);
@@ -271,11 +271,21 @@ __device__ __forceinline__ void exactlinear_d(double &gx, double &gy, double &gz
     gz = (dAx * rm[2] + dAy * rm[4] + dAz * rm[5]) * ddenom;
 }
 
-// staging block of the density kernel: the fast path keeps the candidates' FP64 positions in shared memory ({x,y} + z)
-template <bool FAST> struct DensShared { typedef WarpShared type; };
-template <> struct DensShared<true> { typedef WarpSharedT<ROUND_DEFAULT, DENS_STAGE, DENS_STAGE> type; };
+// Staging block of the density kernel.  Two instantiations of the fast path, picked per call from the candidate counts of the previous
+// pass: up to 384 candidates per group (cubic lattices) fit one round WITH their FP64 positions in shared memory; larger candidate sets
+// (close-packed lattices ~510, glass-like and centrally condensed distributions ~700) take rounds of 768 without the staged positions,
+// because a second round costs more than the staging saves (its hits are lopsided over the lanes and the warp pays the maximum).
+#ifndef DENS_ROUND
+#define DENS_ROUND ROUND_DEFAULT
+#endif
+#ifndef DENS_ROUND_BIG
+#define DENS_ROUND_BIG 768
+#endif
+template <bool FAST, bool BIG> struct DensShared { typedef WarpShared type; };
+template <> struct DensShared<true, false> { typedef WarpSharedT<DENS_ROUND, DENS_STAGE, DENS_STAGE, !DENS_STAGE> type; };
+template <> struct DensShared<true, true> { typedef WarpSharedT<DENS_ROUND_BIG, 0, 0> type; };
 
-template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST>
+template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST, bool BIG>
 #ifndef DENS_MINB
 #define DENS_MINB 3
 #endif
@@ -288,7 +298,8 @@ template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST>
 __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MHD) ? DENS_MHD_MINB : 3)) k_density(const DensArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
-    typedef typename DensShared<FAST>::type WS;
+    typedef typename DensShared<FAST, BIG>::type WS;
+    constexpr bool STAGED = FAST && WS::P2 > 0;
     extern __shared__ __align__(16) unsigned char dens_smem[];
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     WS &ws = reinterpret_cast<WS *>(dens_smem)[wib];
@@ -355,7 +366,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
         const int *cl = clist;                                       // list in use: the prepared one, or this warp's slice after a walk in here
         int ncl = a.wl.ncl[cellid];
         if (ncl >= 0) { cl = a.wl.list + (size_t)cellid * a.wl.cap; reach = a.wl.reach[cellid]; }
-        else ncl = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut_list), (float)radkern, fLx, fLy, fLz, ws.stack,
+        else ncl = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut_list), (float)radkern, fLx, fLy, fLz, ws.walk_stack(),
                                               clist, a.scratch_per_warp, reach);
         st_nwalk += (lane == 0);
         if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
@@ -373,7 +384,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                 hmax_list = hneed * a.margin * 1.01;
                 rcut_list = radkern * hmax_list;
                 wide = PERIODIC && (halfext + rcut_list >= 0.999 * halfLmin);
-                ncl = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut_list), (float)radkern, fLx, fLy, fLz, ws.stack,
+                ncl = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut_list), (float)radkern, fLx, fLy, fLz, ws.walk_stack(),
                                                  clist, a.scratch_per_warp, reach);
                 cl = clist;
                 st_nwalk += (lane == 0);
@@ -401,7 +412,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
             int nlist = 0;
             for (int cellpos = 0; cellpos < ncl;) {                  // rounds of <= ROUND candidates staged in shared memory
                 auto stage_rec = [&](int slot, int, const double2 &xy, const double2 &zw) {      // fast path: FP64 positions to shared memory
-                    if (FAST && DENS_STAGE) { ws.rec2[0][slot] = xy; ws.rec1[0][slot] = zw.x; }
+                    if (STAGED) { ws.rec2[0][slot] = xy; ws.rec1[0][slot] = zw.x; }
                 };
                 const int nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf, fs, interior,
                                                             cell.start, stage_rec);
@@ -417,7 +428,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                         next_hits2(hm_lane, nz, c, m, slot0, slot1);
                         if (slot0 < 0) break;
                         surv += 1 + (slot1 >= 0);
-                        dens_pair2_fast<K, PERIODIC, MHD, GRAV, WS::ROUND>(v, w, nneighi, slot0, slot1, myslot, rec2_s, rec1_s, sidx_s, pi.x, pi.y, pi.z, hi1, hi21,
+                        dens_pair2_fast<K, PERIODIC, MHD, GRAV, STAGED>(v, w, nneighi, slot0, slot1, myslot, rec2_s, rec1_s, sidx_s, pi.x, pi.y, pi.z, hi1, hi21,
                                                                            vi, ai, bi, a.drec, pmassi, use_da, interior, Lx, Ly, Lz);
                     }
                     st_surv += surv;
@@ -567,19 +578,26 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
 }
 
 // grid < 0: only query the resident CTAs/SM of the instantiation; otherwise launch on `grid` CTAs
+template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST, bool BIG>
+int launch_density2(sphgpu_ctx *c, const DensArgs &a, int grid)
+{
+    const size_t smem = 4 * sizeof(typename DensShared<FAST, BIG>::type);
+    cudaFuncSetAttribute(k_density<K, PERIODIC, MHD, GRAV, FAST, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (grid < 0) {
+        int bps = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_density<K, PERIODIC, MHD, GRAV, FAST, BIG>, 128, smem);
+        return bps < 1 ? 1 : bps;
+    }
+    k_density<K, PERIODIC, MHD, GRAV, FAST, BIG><<<grid, 128, smem, c->stream>>>(a, c->hp);
+    c->launches++;
+    return 0;
+}
 template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST>
 int launch_density(sphgpu_ctx *c, const DensArgs &a, int grid)
 {
-    const size_t smem = 4 * sizeof(typename DensShared<FAST>::type);
-    cudaFuncSetAttribute(k_density<K, PERIODIC, MHD, GRAV, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (grid < 0) {
-        int bps = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_density<K, PERIODIC, MHD, GRAV, FAST>, 128, smem);
-        return bps < 1 ? 1 : bps;
-    }
-    k_density<K, PERIODIC, MHD, GRAV, FAST><<<grid, 128, smem, c->stream>>>(a, c->hp);
-    c->launches++;
-    return 0;
+    // the previous pass staged more candidates per group than one small round holds: take the big rounds
+    if (FAST && c->dens_trial_max > DENS_ROUND && c->dens_trial_hint > 0.8 * DENS_ROUND) return launch_density2<K, PERIODIC, MHD, GRAV, FAST, FAST>(c, a, grid);
+    return launch_density2<K, PERIODIC, MHD, GRAV, FAST, false>(c, a, grid);
 }
 
 template <int K, bool PERIODIC, bool FAST>
@@ -689,6 +707,7 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     if (hgrow <= 1.02 && !c->always_refit) c->hscale = fmax(c->hscale, 1.) * fmax(hgrow, 1.) * (1. + 1e-12);
     else TRY(tree_refit_hmax(c));
     sc.trialmean = sc.np ? (double)hc[CNT_NTRIAL] / (double)hc[CNT_NCALC] : -1.;
+    if (sc.np) { c->dens_trial_hint = sc.trialmean; c->dens_trial_max = (double)hc[CNT_MAXTRIAL]; }
     sc.actualmean = sc.np ? (double)hc[CNT_NACT] / (double)sc.np : -1.;
     sc.maxtrial = (int64_t)hc[CNT_MAXTRIAL]; sc.maxactual = (int64_t)hc[CNT_MAXACT]; sc.nrhocalc = (int64_t)hc[CNT_NCALC];
     sc.nactualtot = (int64_t)hc[CNT_NACT]; sc.ncalls_neigh = (int64_t)hc[CNT_NWALK]; sc.npairs_density = (int64_t)hc[CNT_NPAIRS];

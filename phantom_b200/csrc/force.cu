@@ -309,10 +309,17 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
 #ifndef FORCE_STAGE
 #define FORCE_STAGE 0
 #endif
-template <bool MHD> struct ForceFastSharedT { typedef WarpSharedT<ROUND_DEFAULT, FORCE_STAGE ? 2 : 0, 0, !FORCE_STAGE> type; };
-template <> struct ForceFastSharedT<true> { typedef WarpShared type; };
+// candidates per round: 384 hold every group of a cubic lattice in one round; close-packed / glass-like sets stage 500-700 per group and
+// take rounds of 768 (chosen per call from the candidate counts of the last density pass, like the density kernel)
+#ifndef FORCE_ROUND
+#define FORCE_ROUND ROUND_DEFAULT
+#endif
+#ifndef FORCE_ROUND_BIG
+#define FORCE_ROUND_BIG 768
+#endif
+template <bool MHD, bool BIG> struct ForceFastSharedT { typedef WarpSharedT<BIG ? FORCE_ROUND_BIG : FORCE_ROUND, (FORCE_STAGE && !MHD && !BIG) ? 2 : 0, 0, !(FORCE_STAGE && !MHD && !BIG)> type; };
 
-template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS>
+template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS, bool BIG>
 #ifndef FORCE_MINB
 #define FORCE_MINB 4
 #endif
@@ -322,7 +329,7 @@ template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS>
 __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_MINB)) k_force_fast(const ForceArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
-    typedef typename ForceFastSharedT<MHD>::type WS;
+    typedef typename ForceFastSharedT<MHD, BIG>::type WS;
     extern __shared__ __align__(16) unsigned char force_smem[];
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     WS &ws = reinterpret_cast<WS *>(force_smem)[wib];
@@ -855,19 +862,25 @@ int launch_force_general(sphgpu_ctx *c, const ForceArgs &a, int grid)
     c->launches++;
     return 0;
 }
+template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS, bool BIG>
+int launch_force_fast3(sphgpu_ctx *c, const ForceArgs &a, int grid)
+{
+    const size_t smem = 4 * sizeof(typename ForceFastSharedT<MHD, BIG>::type);
+    cudaFuncSetAttribute(k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (grid < 0) {
+        int bps = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS, BIG>, 128, smem);
+        return bps < 1 ? 1 : bps;
+    }
+    k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS, BIG><<<grid, 128, smem, c->stream>>>(a, c->hp);
+    c->launches++;
+    return 0;
+}
 template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS>
 int launch_force_fast2(sphgpu_ctx *c, const ForceArgs &a, int grid)
 {
-    const size_t smem = 4 * sizeof(typename ForceFastSharedT<MHD>::type);
-    cudaFuncSetAttribute(k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (grid < 0) {
-        int bps = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS>, 128, smem);
-        return bps < 1 ? 1 : bps;
-    }
-    k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS><<<grid, 128, smem, c->stream>>>(a, c->hp);
-    c->launches++;
-    return 0;
+    if (c->dens_trial_max > FORCE_ROUND && c->dens_trial_hint > 0.8 * FORCE_ROUND) return launch_force_fast3<K, PERIODIC, MHD, ADIA, GRAV, INDTS, true>(c, a, grid);
+    return launch_force_fast3<K, PERIODIC, MHD, ADIA, GRAV, INDTS, false>(c, a, grid);
 }
 template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV>
 int launch_force_fast(sphgpu_ctx *c, const ForceArgs &a, int grid)

@@ -44,5 +44,5 @@ for r in range(reps):
     nact = int(np.sum(part.iphase > 0))
     print(json.dumps(dict(config=name, npart=part.npart, setup_s=round(tsetup, 1), wall_ms=round(wall, 2), updates_per_s=round(nact / (wall * 1e-3)),
                           phases=g.timings_ms(), kernels=g.kernel_timings_ms(), gravity=g.gravity_timings_ms() if part.params.gravity else None,
-                          neigh_mean=sc.actualmean, neigh_max=sc.maxactual, its_mean=sc.nrhocalc / max(sc.np, 1), npairs_force=sc.npairs_force,
+                          neigh_mean=sc.actualmean, neigh_max=sc.maxactual, trial_mean=sc.trialmean, trial_max=sc.maxtrial, its_mean=sc.nrhocalc / max(sc.np, 1), npairs_force=sc.npairs_force,
                           npairs_gravity=sc.npairs_gravity, nm2l=sc.nm2l, dtcourant=sc.dtcourant, dtforce=sc.dtforce)), flush=True)

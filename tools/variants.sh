@@ -2,7 +2,7 @@
 # A/B builds of the pair kernels with different launch bounds / pairs per trip: builds libsphgpu_<tag>.so variants (CPU side)
 # usage: tools/variants.sh build   |   tools/variants.sh run   (run = on the GPU box: times each variant with bench.py)
 cd "$(dirname "$0")/.."
-VARIANTS=("d1:-DDENS_STAGE=1" "d0m3:-DDENS_STAGE=0 -DDENS_MINB=3" "d0m4:-DDENS_STAGE=0 -DDENS_MINB=4")
+VARIANTS=("v1:-DDENS_ROUND=384" "v2:-DDENS_ROUND=448 -DFORCE_ROUND=640" "v3:-DDENS_STAGE=0 -DDENS_ROUND=768 -DFORCE_ROUND=768" "v4:-DDENS_STAGE=0 -DDENS_ROUND=640 -DFORCE_ROUND=640")
 if [ "$1" == "build" ]; then
   mkdir -p build/variants
   for v in "${VARIANTS[@]}"; do
