@@ -281,7 +281,7 @@ __device__ __forceinline__ void exactlinear_d(double &gx, double &gy, double &gz
 #ifndef DENS_ROUND_BIG
 #define DENS_ROUND_BIG 768
 #endif
-template <bool FAST, bool BIG> struct DensShared { typedef WarpShared type; };
+template <bool FAST, bool BIG> struct DensShared { typedef WarpSharedGeneral type; };
 template <> struct DensShared<true, false> { typedef WarpSharedT<DENS_ROUND, DENS_STAGE, DENS_STAGE, !DENS_STAGE> type; };
 template <> struct DensShared<true, true> { typedef WarpSharedT<DENS_ROUND_BIG, 0, 0> type; };
 

@@ -640,9 +640,10 @@ template <int K, bool PERIODIC, bool MHD, bool XTRA>
 __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const ForceArgs a, const __grid_constant__ DevParams dp)
 {
     typedef SphKern<K> KF;
-    __shared__ WarpShared wsh[4];
+    typedef WarpSharedGeneral WS;
+    extern __shared__ __align__(16) unsigned char forceg_smem[];
     const int lane = lane_id(), wib = threadIdx.x >> 5;
-    WarpShared &ws = wsh[wib];
+    WS &ws = reinterpret_cast<WS *>(forceg_smem)[wib];
     const int gwarp = blockIdx.x * 4 + wib;
     int *clist = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;      // cell list of the current group (the only global scratch)
     const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
@@ -853,12 +854,14 @@ __global__ void k_scatter_force(int64_t nlive, const int *__restrict__ perm, con
 template <int K, bool PERIODIC, bool MHD>
 int launch_force_general(sphgpu_ctx *c, const ForceArgs &a, int grid)
 {
+    const size_t smem = 4 * sizeof(WarpSharedGeneral);
+    cudaFuncSetAttribute(k_force<K, PERIODIC, MHD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (grid < 0) {
         int bps = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force<K, PERIODIC, MHD, true>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force<K, PERIODIC, MHD, true>, 128, smem);
         return bps < 1 ? 1 : bps;
     }
-    k_force<K, PERIODIC, MHD, true><<<grid, 128, 0, c->stream>>>(a, c->hp);
+    k_force<K, PERIODIC, MHD, true><<<grid, 128, smem, c->stream>>>(a, c->hp);
     c->launches++;
     return 0;
 }

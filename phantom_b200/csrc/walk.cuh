@@ -43,7 +43,11 @@ struct __align__(16) WarpSharedT {
     double2 rec2[P2_ > 0 ? P2_ : 1][P2_ > 0 ? ROUND_ : 1];     // structure of arrays: conflict-free staging stores
     double rec1[P1_ > 0 ? P1_ : 1][P1_ > 0 ? ROUND_ : 1];
 };
-typedef WarpSharedT<ROUND_DEFAULT, 0, 0> WarpShared;     // general kernels: everything else is gathered from global memory
+typedef WarpSharedT<ROUND_DEFAULT, 0, 0> WarpShared;     // neighbour-list kernel (static shared memory)
+#ifndef ROUND_GENERAL
+#define ROUND_GENERAL 384
+#endif
+typedef WarpSharedT<ROUND_GENERAL, 0, 0> WarpSharedGeneral;   // general pair kernels (dynamic shared memory).  768 measured: two-fluid box 48.9 -> 45.9 ms but dusty disc 541 -> 583 ms (less L1 left for its five gathers per pair)
 
 // Scale of the FP16 filter of one target group: coordinates relative to the group centre times `scale` lie in [-1, 1].
 struct FilterScale { float scale, slack; };
