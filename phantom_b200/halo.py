@@ -213,6 +213,7 @@ class DistributedSph:
         mark("c2p+force")
         red = torch.tensor([sf.dtcourant, sf.dtforce, -sd.rhomax], dtype=torch.float64, device="cuda")
         dist.all_reduce(red, op=dist.ReduceOp.MIN)
+        red = red.cpu().numpy()                      # one device-to-host read for the three scalars
         sf.dtcourant, sf.dtforce, sf.rhomax = float(red[0]), float(red[1]), -float(red[2])
         sf.np, sf.nrhocalc, sf.npairs_density = sd.np, sd.nrhocalc, sd.npairs_density
         sf.actualmean, sf.maxactual, sf.trialmean, sf.nactualtot = sd.actualmean, sd.maxactual, sd.trialmean, sd.nactualtot
