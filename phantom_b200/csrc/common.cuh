@@ -154,6 +154,7 @@ struct sphgpu_ctx {
     DevBuf<TreeNodeF> nodesf;
     bool multitype = false;                 // any particle that is not plain gas (boundary, dust, ...)
     DevBuf<int> wl_list, wl_ncl; DevBuf<float> wl_reach;   // cell lists prepared by k_walk_lists (walk.cuh)
+    bool stream_blocking = false;   // the compute stream synchronises implicitly with the legacy default stream (option "legacy_stream")
     double dens_trial_hint = 0., dens_trial_max = 0.;   // mean / max candidates per target group in the last density pass (choose the round size of the next)
     bool wl_force_ok = false;       // the prepared lists are symmetric lists of the current groups ...
     double wl_cover = 0.;           // ... and cover every h up to wl_cover x the tree's hmax (force pass reuses them while hscale <= wl_cover)

@@ -209,7 +209,7 @@ int sphgpu_halo_select(sphgpu_ctx *c, int nranks, int myrank, const double *boxe
     k_halo_select<true><<<nblk(n, 256), 256, 0, c->stream>>>(n, c->xyzh.p, nranks, myrank, c->halo_boxes.p, dhalo, c->hp.dxbound, c->hp.dybound, c->hp.dzbound,
                                                              p.periodic, c->halo_cnt.p, doff, c->halo_sendidx.p);
     c->launches++;
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (!c->stream_blocking) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaGetLastError());
     return SPHGPU_OK;
 }
@@ -228,7 +228,7 @@ int sphgpu_halo_pack(sphgpu_ctx *c, int stage, void **sendptr, int *record_doubl
         else k_halo_pack2<<<nblk(tot, 256), 256, 0, c->stream>>>(tot, c->halo_sendidx.p, c->xyzh.p, c->gradh.p, c->alphaind.p, c->hp.ngradh, c->halo_sendbuf.p);
         c->launches++;
     }
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (!c->stream_blocking) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaGetLastError());
     *sendptr = c->halo_sendbuf.p; *record_doubles = rd;
     return SPHGPU_OK;
@@ -272,7 +272,7 @@ int sphgpu_halo_unpack(sphgpu_ctx *c, int stage, int64_t nghost)
             }
         }
     }
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (!c->stream_blocking) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaGetLastError());
     return SPHGPU_OK;
 }

@@ -156,6 +156,16 @@ int sphgpu_set_option(sphgpu_ctx *c, const char *name, double value)
     if (!strcmp(name, "always_refit")) { c->always_refit = value != 0.; return 0; }
     if (!strcmp(name, "force_general")) { c->force_general = value != 0.; return 0; }
     if (!strcmp(name, "grav_p2p_per_particle")) { c->grav_p2p_per_particle = (int)value < 8 ? 8 : (int)value; return 0; }
+    if (!strcmp(name, "legacy_stream")) {
+        // Multi-GPU plumbing (torch.distributed) issues its collectives relative to the legacy default stream.  A BLOCKING compute stream
+        // is implicitly ordered with it, so the halo pack / exchange / unpack sequence needs no host synchronisation in between.
+        if (value != 0. && !c->stream_blocking) {
+            cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream);
+            if (cudaStreamCreate(&c->stream) != cudaSuccess) return SPHGPU_ERR_CUDA;
+            c->stream_blocking = true;
+        }
+        return 0;
+    }
     if (!strcmp(name, "scratch_per_warp")) { c->scratch_per_warp = (int)value; c->stage_idx.release(); return 0; }
     return SPHGPU_ERR_ARG;
 }

@@ -120,6 +120,12 @@ class DistributedSph:
         self.nghost = 0
         self.nlocal = 0
         self._hu_prev = None
+        # the context's compute stream becomes a blocking stream: implicitly ordered with the legacy default stream that torch and its
+        # NCCL collectives work against, so pack -> all-to-all -> unpack needs no host synchronisation
+        self.sync_free = False
+        if torch.cuda.is_available() and torch.cuda.current_stream().cuda_stream == 0:
+            gpu.set_option("legacy_stream", 1)
+            self.sync_free = True
 
     def _alltoall(self, sendptr, rd, sendcounts, recvcounts, stage):
         torch, dist = self.torch, self.dist
@@ -128,7 +134,8 @@ class DistributedSph:
         send = torch.as_tensor(_DevArray(sendptr, max(ntot_s, 1) * rd), device="cuda")[: ntot_s * rd]
         recv = torch.as_tensor(_DevArray(recvptr, max(ntot_r, 1) * rd), device="cuda")[: ntot_r * rd]
         dist.all_to_all_single(recv, send, [int(c) * rd for c in recvcounts], [int(c) * rd for c in sendcounts])
-        torch.cuda.synchronize()
+        if not self.sync_free:
+            torch.cuda.synchronize()
         self.halo_bytes += 8 * rd * (ntot_s + ntot_r)
         return ntot_r
 
