@@ -133,10 +133,29 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": val, "unit": "particle-updates/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else written to fd 1 by libraries (NCCL prints its version there) goes to stderr"""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -356,7 +375,7 @@ def main():
         line["cpu_baseline"] = {"value": pc.npart / tc, "unit": "particle-updates/s", "cores": threads, "kind": "port",
                                 "sample": f"1 full derivs on {nxc}^3 = {pc.npart} particles ({tc:.1f} s)"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
