@@ -137,7 +137,11 @@ int  sphgpu_create(const sphgpu_params *params, int device, sphgpu_ctx **out);
 void sphgpu_destroy(sphgpu_ctx *ctx);
 int  sphgpu_set_params(sphgpu_ctx *ctx, const sphgpu_params *params);
 const char *sphgpu_last_error(sphgpu_ctx *ctx);
-/* tuning knobs: "max_cell" (particles per leaf cell, <=32), "list_margin" (x1e-4) ... ; returns 0 if known */
+/* tuning knobs: "max_cell" (particles per leaf cell, <=32), "list_margin" (x1e-4) ... ; returns 0 if known.
+ * "legacy_stream" = 1 replaces the context's non-blocking compute stream by a BLOCKING one, i.e. one implicitly ordered with the
+ * legacy default stream: a host that issues its NCCL collectives relative to the default stream (torch.distributed, or a Fortran
+ * MPI+NCCL driver doing the same) can then chain sphgpu_halo_select -> _pack -> all-to-all -> _unpack without any host
+ * synchronisation; the halo entry points skip their cudaStreamSynchronize in that mode. */
 int  sphgpu_set_option(sphgpu_ctx *ctx, const char *name, double value);
 /* per-phase device times of the last derivs (ms): tree, dens, cons2prim, force ; utils_timing.f90 labels */
 int  sphgpu_get_timings(sphgpu_ctx *ctx, double *ms4);
