@@ -374,7 +374,7 @@ def main():
         "phases_ms": {k: v / args.steps for k, v in phases.items()},
         "wall_ms_per_step": 1e3 * t_wall_max / args.steps,
         "e2e": {"value": e2e_val, "unit": "particle-updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "call": "sphgpu_derivs (literal C-ABI, pinned host buffers)"},
+                "call": "sphgpu_derivs (literal C-ABI, pinned host buffers)" if world == 1 else "sphgpu_upload(inputs) + DistributedSph.derivs (halo exchanges) + sphgpu_download(outputs), pinned host buffers"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": roofline,
