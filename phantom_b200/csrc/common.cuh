@@ -112,6 +112,7 @@ struct sphgpu_ctx {
     // tuning
     int max_cell = 32;       // target group: <= 32 particles (one lane per target)
     int max_leaf = 8;        // tree leaf (source granularity of the walk)
+    int group_pack = 0;      // > 0: target groups packed from whole leaf cells inside subtrees of <= group_pack particles (tree.cu k_groups_packed)
     double list_margin = 1.02;
     int scratch_per_warp = 4096;    // capacity (cells) of a warp's cell list
     // ---- canonical (original particle order) device arrays = device mirror of part.F90 ----

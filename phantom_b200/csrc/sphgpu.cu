@@ -1,5 +1,6 @@
 // sphgpu.cu -- the C ABI of include/sphgpu.h: context management, resident state transfers, and the literal-mode
 // wrappers mirroring build_tree / densityiterate / cons2prim_everything / force / derivs of the reference.
+#include <cstdlib>
 #include "common.cuh"
 #include <string.h>
 #include <new>
@@ -107,6 +108,7 @@ int sphgpu_create(const sphgpu_params *params, int device, sphgpu_ctx **out)
     c->numSMs = prop.multiProcessorCount;
     cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     for (int k = 0; k < 16; k++) cudaEventCreate(&c->ev[k]);
+    if (const char *e = getenv("SPHGPU_GROUP_PACK")) c->group_pack = atoi(e) < 0 ? 0 : (atoi(e) > 4096 ? 4096 : atoi(e));   // A/B switch for whole test runs
     set_params_internal(c, params);
     *out = c;
     return SPHGPU_OK;
@@ -149,6 +151,7 @@ int sphgpu_set_option(sphgpu_ctx *c, const char *name, double value)
 {
     if (!c || !name) return SPHGPU_ERR_ARG;
     if (!strcmp(name, "max_cell")) { int v = (int)value; c->max_cell = v < 1 ? 1 : (v > 32 ? 32 : v); c->tree_valid = false; return 0; }
+    if (!strcmp(name, "group_pack")) { int v = (int)value; c->group_pack = v < 0 ? 0 : (v > 4096 ? 4096 : v); c->tree_valid = false; return 0; }
     if (!strcmp(name, "max_leaf")) { int v = (int)value; c->max_leaf = v < 1 ? 1 : (v > 32 ? 32 : v); c->tree_valid = false; return 0; }
     if (!strcmp(name, "list_margin")) { c->list_margin = value < 1. ? 1. : value; return 0; }
     if (!strcmp(name, "hilbert")) { c->hilbert = value != 0.; c->tree_valid = false; return 0; }

@@ -301,6 +301,43 @@ __global__ void k_groups(int M, int gmax, const Cell *__restrict__ cells, const 
     groups[slotg] = g;
 }
 
+// target groups with better fill: inside every maximal subtree holding <= smax particles the Morton-consecutive leaf cells are packed
+// greedily into groups of <= gmax particles (a maximal <= gmax subtree holds 22.6 of 32 particles on average away from power-of-two
+// lattices, tools/group_fill.py).  A group is then a run of whole cells: box, hmax and active count are merged from its cells.
+// scan[s] = index of the cell that starts at sorted slot s (k_cell_starts).  One thread per subtree: two passes (count, then write into
+// a contiguous block of group slots so that consecutive groups stay spatial neighbours).
+__global__ void k_groups_packed(int M, int gmax, int smax, const Cell *__restrict__ cells, const TreeNode *__restrict__ nodes, const int *__restrict__ scan,
+                                Cell *__restrict__ groups, unsigned long long *ngroups)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * M - 1) return;
+    int parent, total, start;
+    if (t < M) { parent = cells[t].parent; total = cells[t].count; start = cells[t].start; }
+    else { const TreeNode &nd = nodes[t - M]; parent = nd.parent; total = nd.cnt[0] + nd.cnt[1]; start = min(nd.start[0], nd.start[1]); }
+    if (total > smax && t >= M) return;                     // (a single cell above smax cannot occur: cells hold <= 32 particles)
+    if (parent >= 0 && nodes[parent].cnt[0] + nodes[parent].cnt[1] <= smax) return;      // not maximal
+    const int c0 = (t < M) ? t : scan[start];
+    int ng = 0, acc = 0;
+    for (int cidx = c0, left = total; left > 0; cidx++) {   // pass 1: number of groups
+        const int cnt = cells[cidx].count;
+        if (acc == 0 || acc + cnt > gmax) { ng++; acc = 0; }
+        acc += cnt; left -= cnt;
+    }
+    unsigned long long slot = atomicAdd(ngroups, (unsigned long long)ng);
+    Cell g; g.count = 0;
+    for (int cidx = c0, left = total; left > 0; cidx++) {   // pass 2: merge and write
+        const Cell cc = cells[cidx];
+        if (g.count > 0 && g.count + cc.count > gmax) { groups[slot++] = g; g.count = 0; }
+        if (g.count == 0) { g = cc; g.parent = parent; }
+        else {
+            for (int k = 0; k < 3; k++) { g.lo[k] = fmin(g.lo[k], cc.lo[k]); g.hi[k] = fmax(g.hi[k], cc.hi[k]); }
+            g.hmax = fmax(g.hmax, cc.hmax); g.count += cc.count; g.active += cc.active;
+        }
+        left -= cc.count;
+    }
+    if (g.count > 0) groups[slot] = g;
+}
+
 // gravity: the reference's node hmax starts from the h the tree was built with (kdtree.F90:654-666)
 __global__ void k_hbuild(int64_t n, const double *__restrict__ xyzh, double *__restrict__ h_build, int *__restrict__ h_its)
 {
@@ -335,7 +372,10 @@ static int build_groups(sphgpu_ctx *c)
     CUDA_TRY(c, c->groups.ensure(M));
     unsigned long long *ng = c->counters.p + CNT_COUNT - 1;
     CUDA_TRY(c, cudaMemsetAsync(ng, 0, sizeof(unsigned long long), c->stream));
-    LAUNCH(c, k_groups, nblk(2 * M - 1, 128), 128, M, c->max_cell, c->cells.p, c->nodes.p, c->groups.p, ng);
+    if (c->group_pack > c->max_cell && c->max_leaf <= c->max_cell)
+        LAUNCH(c, k_groups_packed, nblk(2 * M - 1, 128), 128, M, c->max_cell, c->group_pack, c->cells.p, c->nodes.p, c->cellid_scan.p, c->groups.p, ng);
+    else
+        LAUNCH(c, k_groups, nblk(2 * M - 1, 128), 128, M, c->max_cell, c->cells.p, c->nodes.p, c->groups.p, ng);
     unsigned long long h = 0;
     CUDA_TRY(c, cudaMemcpyAsync(&h, ng, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
