@@ -95,6 +95,17 @@ def test_derivs_parity_adiabatic(lattice, nx):
     assert sg[1].npairs_force == so[1].npairs_force
 
 
+def test_derivs_parity_packed_target_groups():
+    # option group_pack: target groups are runs of whole leaf cells instead of subtrees (tree.cu k_groups_packed); grouping must not
+    # change neighbour sets or results beyond summation order
+    part, _ = setups.setup_test_derivs(nx=20, lattice="random")
+    part.alphaind[:, 0] = 0.5
+    po, pg, so, sg, g = run_both(part, group_pack=256)
+    check_hydro(po, pg)
+    assert sg[0].nactualtot == so[0].nactualtot and sg[0].maxactual == so[0].maxactual
+    assert sg[1].npairs_force == so[1].npairs_force
+
+
 def test_derivs_parity_isothermal_random_h():
     part, _ = setups.setup_test_derivs(nx=20, lattice="random", isothermal=True)
     rng = setups.Ran2(-24358)
