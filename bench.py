@@ -125,17 +125,22 @@ def run_reference(args, rank, world):
     part, _, wl = make_workload(args)
     o = Oracle(part.params)
     threads = o.max_threads()
-    # bounded sample: shrink the box until (steps+warmup) steps fit in ~150 s (cost is linear in N)
+    # bounded sample: one derivs at full size is timed first (it doubles as a warm-up step); the box is halved only if
+    # (steps + warmup) such steps would not fit in ~150 s (cost is linear in N)
     nx = args.nx
-    t_est = 9.0e-6 * part.npart * 8.0 / max(threads, 1)
-    while nx > 32 and t_est * (args.steps + args.warmup) > 150.0:
+    t1 = time.perf_counter()
+    o.derivs(part)
+    t_step = time.perf_counter() - t1
+    done_warm = 1
+    while nx > 32 and t_step * (args.steps + max(args.warmup - 1, 0)) > 150.0:
         nx //= 2
-        t_est /= 8.0
+        t_step /= 8.0
     if nx != args.nx:
         args.nx = nx
         part, _, _ = make_workload(args)
         o = Oracle(part.params)
-    for _ in range(args.warmup):
+        done_warm = 0
+    for _ in range(max(args.warmup - done_warm, 0)):
         o.derivs(part)
     t0 = time.perf_counter()
     for _ in range(args.steps):
