@@ -124,6 +124,11 @@ def run_reference(args, rank, world):
     from oraclelib import Oracle
     part, _, wl = make_workload(args)
     o = Oracle(part.params)
+    # all the host threads the box offers: torchrun exports OMP_NUM_THREADS=1 to its workers, which would otherwise leave the CPU arm
+    # on one core whenever N > 1
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if o.max_threads() < ncpu and (world > 1 or "TORCHELASTIC_RUN_ID" in os.environ):
+        o.set_threads(ncpu)
     threads = o.max_threads()
     # bounded sample: one derivs at full size is timed first (it doubles as a warm-up step); the box is halved only if
     # (steps + warmup) such steps would not fit in ~150 s (cost is linear in N)
