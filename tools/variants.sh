@@ -2,7 +2,7 @@
 # A/B builds of the pair kernels with different launch bounds / pairs per trip: builds libsphgpu_<tag>.so variants (CPU side)
 # usage: tools/variants.sh build   |   tools/variants.sh run   (run = on the GPU box: times each variant with bench.py)
 cd "$(dirname "$0")/.."
-VARIANTS=("v1:-DDENS_ROUND=384" "v2:-DDENS_ROUND=448 -DFORCE_ROUND=640" "v3:-DDENS_STAGE=0 -DDENS_ROUND=768 -DFORCE_ROUND=768" "v4:-DDENS_STAGE=0 -DDENS_ROUND=640 -DFORCE_ROUND=640")
+VARIANTS=("base:" "b512:-DDENS_ROUND_BIG=512 -DFORCE_ROUND_BIG=512" "b576:-DDENS_ROUND_BIG=576 -DFORCE_ROUND_BIG=576" "d512:-DDENS_ROUND_BIG=512")   # round 2: a big-round instantiation that keeps 3 density CTAs/SM
 if [ "$1" == "build" ]; then
   mkdir -p build/variants
   for v in "${VARIANTS[@]}"; do
@@ -17,7 +17,7 @@ else
     if [ -n "$VARIANT_CMD" ]; then
       echo -n "$tag "; SPHGPU_LIB=$PWD/build/variants/libsphgpu_$tag.so $VARIANT_CMD 2>&1 | tail -1 | cut -c1-400
     else
-    SPHGPU_LIB=$PWD/build/variants/libsphgpu_$tag.so python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); p=d['roofline']['passes']; print('$tag', round(d['ms_per_step'],3), 'dens', round(p['density']['ms'],3), 'force', round(p['force']['ms'],3))"
+    SPHGPU_LIB=$PWD/build/variants/libsphgpu_$tag.so python bench.py ${BENCH_ARGS:---nx 100} --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); p=d['roofline']['passes']; print('$tag', round(d['ms_per_step'],3), 'dens', round(p['density']['ms'],3), 'force', round(p['force']['ms'],3))"
     fi
   done
 fi
