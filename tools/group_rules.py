@@ -3,7 +3,7 @@ group (particles of the leaf cells whose box lies within 2h x 1.02 of the group'
 before spending GPU time on it.  Calibration against the B200 (100^3 lattice): plain subtrees 400.3 candidates, Morton-run packing
 inside 256-particle subtrees 572.7.
 
-usage: python tools/group_rules.py [nx] [lattice|random]"""
+usage: python tools/group_rules.py [nx] [lattice|random] [leafscan]     (leafscan: candidates per group against max_leaf)"""
 import sys
 import numpy as np
 from scipy.spatial import cKDTree
@@ -90,6 +90,15 @@ def main():
         cand = candidates(LO[smp], HI[smp], clo, chi, ccount, r)
         print(f"{name:34s} groups {len(S):7d}  fill {C.mean():5.2f}/32  candidates mean {cand.mean():6.1f}  p95 {np.percentile(cand, 95):6.1f}"
               f"  > 384: {100 * (cand > 384).mean():4.1f} %  > 512: {100 * (cand > 512).mean():4.1f} %  max {cand.max():.0f}")
+    if len(sys.argv) > 3 and sys.argv[3] == "leafscan":
+        smp = np.random.default_rng(2).choice(len(gs), size=min(2000, len(gs)), replace=False)
+        for leaf in (2, 4, 8, 16):
+            ls, lcount = runs(prefix_nodes(key, leaf))
+            llo, lhi = boxes(pos, ls)
+            cand = candidates(glo[smp], ghi[smp], llo, lhi, lcount, r)
+            print(f"max_leaf {leaf:2d}: cells {len(ls):7d} (mean {lcount.mean():5.2f} particles)  candidates mean {cand.mean():6.1f}  p95 {np.percentile(cand, 95):6.1f}"
+                  f"  cells per list {cand.mean() / lcount.mean():5.0f}  > 384: {100 * (cand > 384).mean():4.1f} %")
+        return
     report("plain (subtrees <= 32)", gs, gcount, glo, ghi)
     for grow in (1.3, 1e9):
         report(f"merge neighbours, volume x{grow:g}", *merge_rule(gs, gcount, glo, ghi, 32, r, grow))
