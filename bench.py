@@ -117,6 +117,32 @@ def make_workload(args, rank=0, world=1):
                          f"{part.npart * world} in total, cubic kernel, hydro+AV (Cullen-Dehnen), all active")
 
 
+def parity_block(SphGpu, pin, pcpu, sdo, sfo, device):
+    """GPU (C-ABI sphgpu_derivs on a fresh copy of the input) against the CPU arm's result on the same input, every particle."""
+    pg = pin.copy()
+    g = SphGpu(pg.params.copy(), device=device)
+    sg = g.derivs(pg, 1)
+
+    def relmax(a, b):
+        sc = float(np.sqrt(np.mean(b.astype(np.float64) ** 2))) + 1e-300
+        return float(np.max(np.abs(a - b) / (np.abs(b) + sc)))
+    out = {"particles": int(pin.npart),
+           "max_rel_h": float(np.max(np.abs(pg.xyzh[:, 3] - pcpu.xyzh[:, 3]) / pcpu.xyzh[:, 3])),
+           "max_rel_f": relmax(pg.fxyzu[:, :3], pcpu.fxyzu[:, :3]),
+           "nactualtot_equal": bool(sg.nactualtot == sdo.nactualtot and sg.maxactual == sdo.maxactual),
+           "npairs_force_equal": bool(sg.npairs_force == sfo.npairs_force),
+           "nactualtot": int(sg.nactualtot), "npairs_force": int(sg.npairs_force),
+           "dtcourant_rel": float(abs(sg.dtcourant - sfo.dtcourant) / sfo.dtcourant),
+           "tolerances": {"h": 1e-10, "f": 1e-8}}
+    if pin.params.maxvxyzu == 4:
+        out["max_rel_dudt"] = relmax(pg.fxyzu[:, 3], pcpu.fxyzu[:, 3])
+    if pin.params.mhd:
+        out["max_rel_dBdt"] = relmax(pg.dBevol, pcpu.dBevol)
+    out["ok"] = bool(out["max_rel_h"] < 1e-10 and out["max_rel_f"] < 1e-8 and out.get("max_rel_dudt", 0.) < 1e-8 and out.get("max_rel_dBdt", 0.) < 1e-8
+                     and out["nactualtot_equal"] and out["npairs_force_equal"])
+    return out
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle (port of the reference algorithm) on all host threads; rank 0 only."""
     if rank != 0:
@@ -406,15 +432,21 @@ def main():
             a2.nx = nxc
             pc, _, _ = make_workload(a2)
             o = Oracle(pc.params)
+        pin = pc.copy()
         t0 = time.perf_counter()
-        o.derivs(pc)
+        sdo, sfo = o.derivs(pc)
         tc = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": pc.npart / tc, "unit": "particle-updates/s", "cores": threads, "kind": "port",
                                 "sample": f"1 full derivs on {nxc}^3 = {pc.npart} particles ({tc:.1f} s)"}
+        # parity of the two arms on the SAME input (outside every timed region): the C-ABI derivs on a fresh copy of the CPU arm's
+        # initial state against the CPU arm's result, every particle, north_star tolerances (h 1e-10, a and du/dt 1e-8 relative)
+        line["parity"] = parity_block(SphGpu, pin, pc, sdo, sfo, local)
     if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and line.get("parity") and not line["parity"]["ok"]:
+        raise SystemExit("bench.py: GPU and CPU arms disagree beyond the north_star tolerances: %s" % json.dumps(line["parity"]))
 
 
 if __name__ == "__main__":

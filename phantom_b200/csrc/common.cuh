@@ -139,7 +139,6 @@ struct sphgpu_ctx {
     bool hilbert = false;                   // space-filling curve of the particle order: Morton (default) or Hilbert (option "hilbert" 1; measured equal on B200)
     bool always_refit = false;              // option: refit the tree's hmax after every density pass (A/B testing)
     bool force_general = false;             // option: route everything through the general force kernel (A/B testing)
-    bool pair_cta = false;                  // fast pair kernels: one CTA per target group with the records in shared memory (round 2); false = one warp per group (round 1)
     DevBuf<float> s_gradh, s_divv, s_dvdx, s_alpha3, s_divcurlB;   // sorted density outputs
     DevBuf<double4> s_fxyzu, s_dB;          // sorted force outputs
     DevBuf<float> s_divvf, s_poten, s_divBsymm;

@@ -577,416 +577,6 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
     }
 }
 
-
-// ---- round 2: one CTA per target group, whole neighbour records in shared memory (walk.cuh, "Round 2") -----------------------------
-// Same sums, same iteration, same stores as the FAST path of k_density above; what changes is who does what: the four warps of the CTA
-// hold the same 32 targets (lane = target), stage the group's candidates ONCE as 16-byte parts {x,y}{z,vx}{vy,vz}{ax,ay}{az,-}
-// [{Bx,By}{Bz,-}] and each take a quarter of every target's hits.  The pair loop touches shared memory only.
-#ifndef DENSC_ROUND
-#define DENSC_ROUND 512
-#endif
-#ifndef DENSC_ROUND_BIG
-#define DENSC_ROUND_BIG 768
-#endif
-#ifndef DENSC_MINB
-#define DENSC_MINB 3
-#endif
-#ifndef DENSC_MHD_MINB
-#define DENSC_MHD_MINB 2
-#endif
-
-template <int K, bool PERIODIC, bool MHD, bool GRAV, int ROUND>
-__device__ __forceinline__ void dens_pair2_cta(double (&v)[29], double (&w)[B_COUNT], int &nneighi, int slot0, int slot1, int myslot, unsigned rec_s, double xi,
-                                               double yi, double zi, double hi1, double hi21, const double4 &vi, const double4 &ai, const double4 &bi,
-                                               double pmass0, bool use_da, bool interior, double Lx, double Ly, double Lz)
-{
-    typedef SphKern<K> KF;
-    // a lane with an odd number of hits evaluates its first neighbour twice, the second time with weight 0
-    const int sl[2] = {slot0, slot1 >= 0 ? slot1 : slot0};
-    const bool live[2] = {slot0 != myslot, slot1 >= 0 && slot1 != myslot};
-    double2 P0[2], P1[2], P2[2], P3[2], P5[2];
-    double P4[2], P6[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const unsigned a0 = rec_s + 16u * (unsigned)sl[k];
-        P0[k] = lds_d2(a0); P1[k] = lds_d2(a0 + 16u * ROUND); P2[k] = lds_d2(a0 + 32u * ROUND);
-        if (use_da) { P3[k] = lds_d2(a0 + 48u * ROUND); P4[k] = lds_d(a0 + 64u * ROUND); }
-        if (MHD) { P5[k] = lds_d2(a0 + 80u * ROUND); P6[k] = lds_d(a0 + 96u * ROUND); }
-    }
-    double dx[2], dy[2], dz[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) { dx[k] = xi - P0[k].x; dy[k] = yi - P0[k].y; dz[k] = zi - P1[k].x; }
-    if (PERIODIC && !interior) {                                              // dens.F90:666-670
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            if (fabs(dx[k]) > 0.5 * Lx) dx[k] = dx[k] - copysign(Lx, dx[k]);
-            if (fabs(dy[k]) > 0.5 * Ly) dy[k] = dy[k] - copysign(Ly, dy[k]);
-            if (fabs(dz[k]) > 0.5 * Lz) dz[k] = dz[k] - copysign(Lz, dz[k]);
-        }
-    }
-    double r2[2], q2i[2], pmass[2], rinv[2], qi[2], wabi[2], grkerni[2], g[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        r2[k] = __dadd_rn(__dadd_rn(__dmul_rn(dx[k], dx[k]), __dmul_rn(dy[k], dy[k])), __dmul_rn(dz[k], dz[k]));
-        q2i[k] = __dmul_rn(r2[k], hi21);                                      // dens.F90:675
-        const bool isn = (q2i[k] < KF::radkern2) && live[k];                  // :679, :650 (exact membership) -> 0/1 weight on m_j
-        pmass[k] = isn ? pmass0 : 0.;
-        nneighi += isn ? 1 : 0;
-    }
-#pragma unroll
-    for (int k = 0; k < 2; k++) rinv[k] = rsqrt_pos(r2[k]);
-#pragma unroll
-    for (int k = 0; k < 2; k++) { qi[k] = (r2[k] * rinv[k]) * hi1; KF::get_kernel_bf(qi[k], wabi[k], grkerni[k]); }
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        v[S_RHO] += wabi[k] * pmass[k];
-        v[S_GRADH] += (-qi[k] * grkerni[k] - 3. * wabi[k]) * pmass[k];
-        if (GRAV) v[S_GRADSOFT] += KF::dphidh(fmin(q2i[k], KF::radkern2), fmin(qi[k], KF::radkern)) * pmass[k];
-        g[k] = fma(-DBL_EPSILON * rinv[k], rinv[k], rinv[k]) * (grkerni[k] * pmass[k]);   // rij1 = 1/(rij + epsilon) (dens.F90:746), times grkern m_j
-    }
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const double runix = dx[k] * g[k], runiy = dy[k] * g[k], runiz = dz[k] * g[k];
-        const double dvx = vi.x - P1[k].y, dvy = vi.y - P2[k].x, dvz = vi.z - P2[k].y;
-        v[S_DIVV] += dvx * runix + dvy * runiy + dvz * runiz;
-        v[S_DVXDX] += dvx * runix; v[S_DVXDY] += dvx * runiy; v[S_DVXDZ] += dvx * runiz;
-        v[S_DVYDX] += dvy * runix; v[S_DVYDY] += dvy * runiy; v[S_DVYDZ] += dvy * runiz;
-        v[S_DVZDX] += dvz * runix; v[S_DVZDY] += dvz * runiy; v[S_DVZDZ] += dvz * runiz;
-        if (use_da) {
-            const double dax = ai.x - P3[k].x, day = ai.y - P3[k].y, daz = ai.z - P4[k];
-            v[S_DAXDX] += dax * runix; v[S_DAXDY] += dax * runiy; v[S_DAXDZ] += dax * runiz;
-            v[S_DAYDX] += day * runix; v[S_DAYDY] += day * runiy; v[S_DAYDZ] += day * runiz;
-            v[S_DAZDX] += daz * runix; v[S_DAZDY] += daz * runiy; v[S_DAZDZ] += daz * runiz;
-        }
-        v[S_RXX] -= dx[k] * runix; v[S_RXY] -= dx[k] * runiy; v[S_RXZ] -= dx[k] * runiz;
-        v[S_RYY] -= dy[k] * runiy; v[S_RYZ] -= dy[k] * runiz; v[S_RZZ] -= dz[k] * runiz;
-        if (MHD) {
-            const double dBx = bi.x - P5[k].x, dBy = bi.y - P5[k].y, dBz = bi.z - P6[k];   // bi = (B/rho)_i rho(h_i) of this iteration (dens.F90:806-812)
-            w[B_DIVB] += dBx * runix + dBy * runiy + dBz * runiz;
-            w[B_CURLX] += dBz * runiy - dBy * runiz;          // dBz/dy - dBy/dz
-            w[B_CURLY] += dBx * runiz - dBz * runix;          // dBx/dz - dBz/dx
-            w[B_CURLZ] += dBy * runix - dBx * runiy;          // dBy/dx - dBx/dy
-        }
-    }
-}
-
-template <int K, bool PERIODIC, bool MHD, bool GRAV, int ROUND>
-__global__ void __launch_bounds__(CTA_THREADS, MHD ? DENSC_MHD_MINB : DENSC_MINB) k_density_cta(const DensArgs a, const __grid_constant__ DevParams dp)
-{
-    typedef SphKern<K> KF;
-    constexpr int NP = MHD ? 7 : 5;
-    typedef CtaSharedT<ROUND, NP> CS;
-    constexpr int NFIN = 28 + B_COUNT;                                    // sums reduced across the warps at the end
-    static_assert(sizeof(double) * (CTA_WARPS - 1) * NFIN * 32 <= sizeof(double2) * NP * ROUND, "record area too small for the final reduction");
-    extern __shared__ __align__(16) unsigned char densc_smem[];
-    CS &cs = *reinterpret_cast<CS *>(densc_smem);
-    double (*fin)[NFIN][32] = reinterpret_cast<double (*)[NFIN][32]>(&cs.rec[0][0]);
-    const int lane = lane_id(), wib = threadIdx.x >> 5;
-    const unsigned cs_s = ws_shared_addr(cs);
-    const unsigned hm_lane = cs_s + (unsigned)offsetof(CS, hm) + 4u * lane, rec_s = cs_s + (unsigned)offsetof(CS, rec);
-    int *clist = a.stage_idx + (size_t)blockIdx.x * a.scratch_per_warp;   // cell list of an in-kernel walk (the only global scratch)
-    constexpr int DSTRIDE = MHD ? 8 : 6;                                 // double2 per packed record
-    const double2 *posrec = reinterpret_cast<const double2 *>(a.drec);
-    const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
-    const float fLx = (float)Lx, fLy = (float)Ly, fLz = (float)Lz;
-    const double radkern = KF::radkern;
-    const double halfLmin = 0.5 * fmin(Lx, fmin(Ly, Lz));
-    const bool use_da = dp.nalpha > 1;
-    unsigned long long st_pairs = 0, st_trial = 0, st_ncalc = 0, st_nact = 0, st_np = 0, st_nwalk = 0, st_surv = 0;
-    int st_maxact = 0, st_maxtrial = 0;
-    double st_rhomax = 0., st_hused = 0., st_hgrow = 0.;
-
-    while (true) {
-        __syncthreads();                                             // the previous group's shared memory is no longer in use
-        if (threadIdx.x == 0) cs.ctl[0] = (int)atomicAdd(&a.cnt[CNT_WORK], 1ull);
-        __syncthreads();
-        const int cellid = cs.ctl[0];
-        if (cellid >= a.ngroups) break;
-        const Cell cell = a.groups[cellid];
-        if (cell.active == 0) continue;                              // dens.F90:302
-        const double cx = 0.5 * (cell.lo[0] + cell.hi[0]), cy = 0.5 * (cell.lo[1] + cell.hi[1]), cz = 0.5 * (cell.lo[2] + cell.hi[2]);
-        const double halfext = 0.5 * fmax(cell.hi[0] - cell.lo[0], fmax(cell.hi[1] - cell.lo[1], cell.hi[2] - cell.lo[2]));
-        float tlo[3], thi[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) { tlo[k] = __double2float_rd(cell.lo[k]); thi[k] = __double2float_ru(cell.hi[k]); }
-        // ---- lane = target in every warp: start_cell (dens.F90:1293-1378)
-        const int s = cell.start + min(lane, cell.count - 1);
-        bool act = false, gasi = true, dusti = false; int itypei = IGAS;
-        if (lane < cell.count) get_partinfo_d(a.stype[s], dp.p.set_boundaries_to_active, dp.p.dust, act, gasi, dusti, itypei);
-        const double4 pi = a.pos4[s];
-        double4 vi, ai, bi = make_double4(0., 0., 0., 0.), bevi = make_double4(0., 0., 0., 0.);
-        {
-            const double4 *r = a.drec + (MHD ? 4 : 3) * (size_t)s;
-            const double4 B = r[1], C = r[2];
-            vi = make_double4(B.x, B.y, B.z, 0.); ai = make_double4(B.w, C.x, C.y, 0.);
-            if (MHD && gasi) bevi = a.bev4[s];
-        }
-        const double pmassi = dp.p.massoftype[itypei];
-        const float xif = (float)(pi.x - cx), yif = (float)(pi.y - cy), zif = (float)(pi.z - cz);
-        double h = pi.w;
-        const double h_old = h;
-        bool conv = !act;                                            // inactive / boundary lanes take no part (dens.F90:1329)
-        bool failed = false;
-        double v[29], w[B_COUNT];
-        int nneighi = 0, its_lane = 0, nlist_last = 0;
-        double rhosum = 0., gradhsum = 0.;                           // this iteration's sums over all four warps
-
-        double hmax_list = cell.hmax * a.margin;
-        double rcut_list = radkern * hmax_list;
-        bool interior = false;
-        bool wide = PERIODIC && (halfext + rcut_list >= 0.999 * halfLmin);
-        float reach = 0.f;
-        const int *cl = clist;
-        int ncl = a.wl.ncl[cellid];
-        if (ncl >= 0) { cl = a.wl.list + (size_t)cellid * a.wl.cap; reach = a.wl.reach[cellid]; }
-        else ncl = cta_walk<false, PERIODIC>(cs, a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut_list), (float)radkern, fLx, fLy, fLz, clist,
-                                             a.scratch_per_warp, reach);
-        st_nwalk += (threadIdx.x == 0);
-        if (ncl < 0) { if (threadIdx.x == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
-        if (PERIODIC) {
-            const double rr = rcut_list * 1.0001;
-            interior = cell.lo[0] - rr > dp.p.xmin && cell.hi[0] + rr < dp.p.xmax && cell.lo[1] - rr > dp.p.ymin && cell.hi[1] + rr < dp.p.ymax &&
-                       cell.lo[2] - rr > dp.p.zmin && cell.hi[2] + rr < dp.p.zmax;
-        }
-
-        for (int its = 1;; its++) {                                  // local_its (dens.F90:338-373): the cell iterates until every particle converged
-            // compute_hmax / redo_neighbours (dens.F90:1275-1289, :343-347); every warp holds the same h, so the decisions are CTA-uniform
-            const double hneed = warp_max(conv ? 0. : h);
-            st_hused = fmax(st_hused, hneed);
-            if (radkern * hneed > rcut_list) {
-                hmax_list = hneed * a.margin * 1.01;
-                rcut_list = radkern * hmax_list;
-                wide = PERIODIC && (halfext + rcut_list >= 0.999 * halfLmin);
-                ncl = cta_walk<false, PERIODIC>(cs, a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut_list), (float)radkern, fLx, fLy, fLz, clist,
-                                                a.scratch_per_warp, reach);
-                cl = clist;
-                st_nwalk += (threadIdx.x == 0);
-                if (ncl < 0) { if (threadIdx.x == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); failed = true; }
-                if (PERIODIC) {
-                    const double rr = rcut_list * 1.0001;
-                    interior = cell.lo[0] - rr > dp.p.xmin && cell.hi[0] + rr < dp.p.xmax && cell.lo[1] - rr > dp.p.ymin && cell.hi[1] + rr < dp.p.ymax &&
-                               cell.lo[2] - rr > dp.p.zmin && cell.hi[2] + rr < dp.p.zmax;
-                }
-            }
-            if (__any_sync(FULLMASK, failed)) break;
-            const FilterScale fs = filter_scale((float)halfext, reach);
-            const FilterTarget ft = filter_target(fs, xif, yif, zif, conv ? 0.f : (wide ? -1.f : __double2float_ru(radkern * h)));
-            if (!conv) {
-#pragma unroll
-                for (int k = 0; k < 29; k++) v[k] = 0.;
-#pragma unroll
-                for (int k = 0; k < B_COUNT; k++) w[k] = 0.;
-                nneighi = 0;
-                its_lane = its;
-            }
-            const double hi1 = 1. / h, hi21 = hi1 * hi1;
-            if (MHD) { const double rhoi = rhoh_d(h, pmassi, dp.p.hfact); bi = make_double4(bevi.x * rhoi, bevi.y * rhoi, bevi.z * rhoi, bevi.w); }
-            int nlist = 0;
-            for (int cellpos = 0; cellpos < ncl;) {                  // rounds of <= ROUND candidates staged in shared memory
-                auto stage_rec = [&](int slot, int j, const double2 &xy, const double2 &zw) {
-                    const double4 *rj = a.drec + (MHD ? 4 : 3) * (size_t)j;
-                    const double4 B = ldg256(rj + 1);                // {vx,vy,vz,ax}
-                    cs.rec[0][slot] = xy; cs.rec[1][slot] = make_double2(zw.x, B.x); cs.rec[2][slot] = make_double2(B.y, B.z);
-                    if (MHD) {
-                        const double4 C = ldg256(rj + 2);            // {ay,az,Bx,By}
-                        cs.rec[3][slot] = make_double2(B.w, C.x); cs.rec[4][slot] = make_double2(C.y, 0.);
-                        cs.rec[5][slot] = make_double2(C.z, C.w); cs.rec[6][slot] = make_double2(rj[3].x, 0.);
-                    } else {
-                        const double2 C = *reinterpret_cast<const double2 *>(rj + 2);    // {ay,az}
-                        cs.rec[3][slot] = make_double2(B.w, C.x); cs.rec[4][slot] = make_double2(C.y, 0.);
-                    }
-                };
-                const int nr = cta_stage_round<PERIODIC, false>(cs, cl, ncl, cellpos, posrec, DSTRIDE, cx, cy, cz, Lx, Ly, Lz, (float)radkern, fs, interior,
-                                                                cell.start, stage_rec);
-                nlist += nr;
-                cta_build_masks<false>(cs, nr, ft);
-                HitRange hr = cta_split_hits(cs, (nr + 31) >> 5, hm_lane);
-                int c = -1; unsigned m = 0u;
-                int surv = 0;
-                const int myslot = cs.selfslot[lane];
-                while (true) {      // two neighbours per trip
-                    int slot0, slot1;
-                    next_hits2_r(hm_lane, hr, c, m, slot0, slot1);
-                    if (slot0 < 0) break;
-                    surv += 1 + (slot1 >= 0);
-                    dens_pair2_cta<K, PERIODIC, MHD, GRAV, ROUND>(v, w, nneighi, slot0, slot1, myslot, rec_s, pi.x, pi.y, pi.z, hi1, hi21, vi, ai, bi, pmassi,
-                                                                     use_da, interior, Lx, Ly, Lz);
-                }
-                st_surv += surv;
-                __syncthreads();                                     // the round's buffers are free again
-            }
-            nlist_last = nlist;
-            // this iteration's density and gradh sums over the four warps, added in the fixed order 0..3 by everybody
-            cs.red[wib][0][lane] = v[S_RHO]; cs.red[wib][1][lane] = v[S_GRADH];
-            __syncthreads();
-            if (!conv) {
-                rhosum = ((cs.red[0][0][lane] + cs.red[1][0][lane]) + cs.red[2][0][lane]) + cs.red[3][0][lane];
-                gradhsum = ((cs.red[0][1][lane] + cs.red[1][1][lane]) + cs.red[2][1][lane]) + cs.red[3][1][lane];
-                if (wib == 0) st_trial += (unsigned long long)nlist;
-                // finish_rhosum + finish_cell (dens.F90:1470-1507, :1401-1462)
-                const double hi31 = hi1 * hi21, hi41 = hi21 * hi21;
-                const double rhoi = KF::cnormk * (rhosum + KF::wab0 * pmassi) * hi31;
-                const double gradhi = KF::cnormk * (gradhsum + KF::gradh0 * pmassi) * hi41;
-                const double rhohi = rhoh_d(h, pmassi, dp.p.hfact);
-                const double dhdrhoi = -h / (3. * rhohi);
-                const double omegai = 1. - dhdrhoi * gradhi;
-                const double func = rhohi - rhoi;
-                double dfdh1;
-                if (omegai > DBL_MIN) dfdh1 = dhdrhoi / omegai;
-                else dfdh1 = dhdrhoi / fabs(omegai + DBL_EPSILON);
-                double hnew = h - func * dfdh1;
-                if (hnew > 1.2 * h) hnew = 1.2 * h;
-                else if (hnew < 0.8 * h) hnew = 0.8 * h;
-                conv = ((fabs(hnew - h) / h_old) < dp.p.tolh) && (omegai > 0.) && (h > 0.);
-                if (a.icall == 0) conv = true;
-                if (!conv) {
-                    if (its >= 100) {                               // maxdensits, dens.F90:1443-1456
-                        if (wib == 0) {
-                            atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_NOCONVERGE);
-                            atomicMax(&a.cnt[CNT_ERRID], (unsigned long long)(a.perm[s] + 1));
-                        }
-                        failed = true; conv = true;
-                    } else {
-                        h = hnew;
-                        if (GRAV && wib == 0 && its <= SPHGPU_HHIST) a.h_hist[(size_t)(its - 1) * a.npart + a.perm[s]] = hnew;
-                    }
-                }
-            }
-            if (__all_sync(FULLMASK, conv)) break;
-        }
-        // ---- the partial sums of warps 1..3 go to warp 0 through the (now free) record area; fixed order of addition
-        if (wib > 0) {
-#pragma unroll
-            for (int k = 0; k < 28; k++) fin[wib - 1][k][lane] = v[k];
-#pragma unroll
-            for (int k = 0; k < B_COUNT; k++) fin[wib - 1][28 + k][lane] = w[k];
-        }
-        cs.tot[wib][lane] = nneighi;
-        __syncthreads();
-        // ---- store_results (dens.F90:1511-1681), lane = target, warp 0 ----
-        if (wib == 0 && act && !failed) {
-#pragma unroll
-            for (int k = 0; k < 28; k++) v[k] = ((v[k] + fin[0][k][lane]) + fin[1][k][lane]) + fin[2][k][lane];
-#pragma unroll
-            for (int k = 0; k < B_COUNT; k++) w[k] = ((w[k] + fin[0][28 + k][lane]) + fin[1][28 + k][lane]) + fin[2][28 + k][lane];
-            nneighi = cs.tot[0][lane] + cs.tot[1][lane] + cs.tot[2][lane] + cs.tot[3][lane];
-            const double hi1 = 1. / h, hi21 = hi1 * hi1, hi31 = hi1 * hi21, hi41 = hi21 * hi21;
-            const double rho = KF::cnormk * (v[S_RHO] + KF::wab0 * pmassi) * hi31;
-            double gradhi = KF::cnormk * (v[S_GRADH] + KF::gradh0 * pmassi) * hi41;
-            const double rhohi = rhoh_d(h, pmassi, dp.p.hfact);
-            const double dhdrhoi = -h / (3. * rhohi);
-            const double omegai = 1. - dhdrhoi * gradhi;
-            gradhi = 1. / omegai;
-            const double hfin = dp.p.hfact * pow(pmassi / fabs(rho), 1.0 / 3.0);    // hrho, part.F90:845
-            const size_t io = (size_t)a.perm[s];                                      // results go straight to the caller's arrays
-            a.pos4[s].w = hfin; a.xyzh[4 * io + 3] = hfin;
-            st_hgrow = fmax(st_hgrow, hfin / h_old);
-            const float gradh4 = (float)gradhi;
-            a.gradh[(size_t)dp.ngradh * io] = gradh4;
-            if (GRAV) {
-                double gradsofti = (v[S_GRADSOFT] + KF::dphidh0 * pmassi) * hi21;
-                gradsofti = gradsofti * dhdrhoi;
-                a.gradh[(size_t)dp.ngradh * io + 1] = (float)gradsofti;
-            }
-            gradhi = (double)gradh4;                                                  // dens.F90:1610
-            const double rho1i = 1. / rho;
-            const double term = KF::cnormk * gradhi * rho1i * hi41;
-            const double rxx = v[S_RXX], rxy = v[S_RXY], rxz = v[S_RXZ], ryy = v[S_RYY], ryz = v[S_RYZ], rzz = v[S_RZZ];
-            const double denom = rxx * ryy * rzz + 2. * rxy * rxz * ryz - rxx * ryz * ryz - ryy * rxz * rxz - rzz * rxy * rxy;
-            double rm[6];
-            rm[0] = ryy * rzz - ryz * ryz; rm[1] = rxz * ryz - rzz * rxy; rm[2] = rxy * ryz - rxz * ryy;
-            rm[3] = rzz * rxx - rxz * rxz; rm[4] = rxy * rxz - rxx * ryz; rm[5] = rxx * ryy - rxy * rxy;
-            const double divv = -v[S_DIVV] * term;
-            double dv[9], divcurlv5 = 0.;
-            if (fabs(denom) > DBL_MIN) {
-                const double ddenom = 1. / denom;
-                exactlinear_d(dv[0], dv[1], dv[2], v[S_DVXDX], v[S_DVXDY], v[S_DVXDZ], rm, ddenom);
-                exactlinear_d(dv[3], dv[4], dv[5], v[S_DVYDX], v[S_DVYDY], v[S_DVYDZ], rm, ddenom);
-                exactlinear_d(dv[6], dv[7], dv[8], v[S_DVZDX], v[S_DVZDY], v[S_DVZDZ], rm, ddenom);
-#pragma unroll
-                for (int k = 0; k < 9; k++) dv[k] = -dv[k];
-                if (use_da) {
-                    double ax, ay, az, bx, by, bz, cxx, cyy, czz;
-                    exactlinear_d(ax, ay, az, v[S_DAXDX], v[S_DAXDY], v[S_DAXDZ], rm, ddenom);
-                    exactlinear_d(bx, by, bz, v[S_DAYDX], v[S_DAYDY], v[S_DAYDZ], rm, ddenom);
-                    exactlinear_d(cxx, cyy, czz, v[S_DAZDX], v[S_DAZDY], v[S_DAZDZ], rm, ddenom);
-                    const double div_a = -(ax + by + czz);
-                    divcurlv5 = div_a - (dv[0] * dv[0] + dv[4] * dv[4] + dv[8] * dv[8] + 2. * (dv[1] * dv[3] + dv[2] * dv[6] + dv[5] * dv[7]));
-                }
-            } else {
-                dv[0] = -term * v[S_DVXDX]; dv[1] = -term * v[S_DVXDY]; dv[2] = -term * v[S_DVXDZ];
-                dv[3] = -term * v[S_DVYDX]; dv[4] = -term * v[S_DVYDY]; dv[5] = -term * v[S_DVYDZ];
-                dv[6] = -term * v[S_DVZDX]; dv[7] = -term * v[S_DVZDY]; dv[8] = -term * v[S_DVZDZ];
-                if (use_da) {
-                    const double div_a = -term * (v[S_DAXDX] + v[S_DAYDY] + v[S_DAZDZ]);
-                    divcurlv5 = div_a - (dv[0] * dv[0] + dv[4] * dv[4] + dv[8] * dv[8] + 2. * (dv[1] * dv[3] + dv[2] * dv[6] + dv[5] * dv[7]));
-                }
-            }
-            a.divcurlv[io] = (float)divv;
-            if (dp.nalpha >= 3) a.alphaind[3 * io + 2] = (float)divcurlv5;
-#pragma unroll
-            for (int k = 0; k < 9; k++) a.dvdx[9 * io + k] = (float)dv[k];
-            if (MHD) {
-                float *o = a.divcurlB + 4 * io;
-                if (gasi) {
-                    o[0] = (float)(-w[B_DIVB] * term);
-                    o[1] = (float)(-w[B_CURLX] * term);
-                    o[2] = (float)(-w[B_CURLY] * term);
-                    o[3] = (float)(-w[B_CURLZ] * term);
-                } else { o[0] = o[1] = o[2] = o[3] = 0.f; }
-            }
-            const int nn = nneighi + 1;   // + self
-            a.s_nneigh[s] = nn;
-            if (GRAV) a.h_its[a.perm[s]] = its_lane;
-            st_rhomax = fmax(st_rhomax, rho);
-            st_pairs += (unsigned long long)nneighi * its_lane;
-            st_ncalc += its_lane; st_nact += nn; st_np += 1;
-            st_maxact = max(st_maxact, nn); st_maxtrial = max(st_maxtrial, nlist_last);
-        }
-    }
-    // ---- statistics: one atomic per warp
-    st_rhomax = warp_max(st_rhomax); st_hused = warp_max(st_hused); st_hgrow = warp_max(st_hgrow);
-#pragma unroll
-    for (int sft = 16; sft >= 1; sft >>= 1) {
-        st_pairs += __shfl_xor_sync(FULLMASK, st_pairs, sft); st_trial += __shfl_xor_sync(FULLMASK, st_trial, sft);
-        st_ncalc += __shfl_xor_sync(FULLMASK, st_ncalc, sft); st_nact += __shfl_xor_sync(FULLMASK, st_nact, sft);
-        st_np += __shfl_xor_sync(FULLMASK, st_np, sft); st_nwalk += __shfl_xor_sync(FULLMASK, st_nwalk, sft);
-        st_surv += __shfl_xor_sync(FULLMASK, st_surv, sft);
-        st_maxact = max(st_maxact, __shfl_xor_sync(FULLMASK, st_maxact, sft)); st_maxtrial = max(st_maxtrial, __shfl_xor_sync(FULLMASK, st_maxtrial, sft));
-    }
-    if (lane == 0) {
-        atomicAdd(&a.cnt[CNT_NSURV], st_surv);
-        if (wib == 0) {
-            atomicAdd(&a.cnt[CNT_NPAIRS], st_pairs); atomicAdd(&a.cnt[CNT_NTRIAL], st_trial); atomicAdd(&a.cnt[CNT_NCALC], st_ncalc);
-            atomicAdd(&a.cnt[CNT_NACT], st_nact); atomicAdd(&a.cnt[CNT_NP], st_np); atomicAdd(&a.cnt[CNT_NWALK], st_nwalk);
-            atomicMax(&a.cnt[CNT_MAXACT], (unsigned long long)st_maxact); atomicMax(&a.cnt[CNT_MAXTRIAL], (unsigned long long)st_maxtrial);
-            atomic_max_pos(&a.dscal[DS_RHOMAX], st_rhomax); atomic_max_pos(&a.dscal[DS_HUSED], st_hused); atomic_max_pos(&a.dscal[DS_HGROW], st_hgrow);
-        }
-    }
-}
-
-template <int K, bool PERIODIC, bool MHD, bool GRAV, int ROUND>
-int launch_density_cta2(sphgpu_ctx *c, const DensArgs &a, int grid)
-{
-    const size_t smem = sizeof(CtaSharedT<ROUND, MHD ? 7 : 5>);
-    cudaFuncSetAttribute(k_density_cta<K, PERIODIC, MHD, GRAV, ROUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (grid < 0) {
-        int bps = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_density_cta<K, PERIODIC, MHD, GRAV, ROUND>, CTA_THREADS, smem);
-        return bps < 1 ? 1 : bps;
-    }
-    k_density_cta<K, PERIODIC, MHD, GRAV, ROUND><<<grid, CTA_THREADS, smem, c->stream>>>(a, c->hp);
-    c->launches++;
-    return 0;
-}
-template <int K, bool PERIODIC, bool MHD, bool GRAV>
-int launch_density_cta(sphgpu_ctx *c, const DensArgs &a, int grid)
-{
-    // the previous pass staged more candidates per group than one small round holds: take the big rounds
-    if (c->dens_trial_max > DENSC_ROUND && c->dens_trial_hint > 0.8 * DENSC_ROUND) return launch_density_cta2<K, PERIODIC, MHD, GRAV, DENSC_ROUND_BIG>(c, a, grid);
-    return launch_density_cta2<K, PERIODIC, MHD, GRAV, DENSC_ROUND>(c, a, grid);
-}
-
 // grid < 0: only query the resident CTAs/SM of the instantiation; otherwise launch on `grid` CTAs
 template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST, bool BIG>
 int launch_density2(sphgpu_ctx *c, const DensArgs &a, int grid)
@@ -1014,12 +604,6 @@ template <int K, bool PERIODIC, bool FAST>
 int dispatch_density3(sphgpu_ctx *c, const DensArgs &a, int grid)
 {
     const bool mhd = c->hp.p.mhd, grav = c->hp.p.gravity;
-    if (FAST && c->pair_cta) {
-        if (mhd && grav) return launch_density_cta<K, PERIODIC, true, true>(c, a, grid);
-        if (mhd) return launch_density_cta<K, PERIODIC, true, false>(c, a, grid);
-        if (grav) return launch_density_cta<K, PERIODIC, false, true>(c, a, grid);
-        return launch_density_cta<K, PERIODIC, false, false>(c, a, grid);
-    }
     if (mhd && grav) return launch_density<K, PERIODIC, true, true, FAST>(c, a, grid);
     if (mhd) return launch_density<K, PERIODIC, true, false, FAST>(c, a, grid);
     if (grav) return launch_density<K, PERIODIC, false, true, FAST>(c, a, grid);

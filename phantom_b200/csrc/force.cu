@@ -633,348 +633,6 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
     }
 }
 
-// ---- round 2: one CTA per target group, whole neighbour records in shared memory (walk.cuh, "Round 2") -----------------------------
-// Same pair body and epilogue as k_force_fast; the four warps hold the same 32 targets, stage the group's candidates once as 16-byte
-// parts {x,y}{z,1/h}{vx,vy}{vz,gradW factor}{P/rho^2..,v_wave}{alpha v_wave,1/rho}[{P,u}{c_s|gradsoft,alpha}][{Bx,By}{Bz,psi}] and
-// each take a quarter of every target's hits; warp 0 adds the partial sums in a fixed order and runs finish_cell_and_store_results.
-#ifndef FORCEC_ROUND
-#define FORCEC_ROUND 384
-#endif
-#ifndef FORCEC_ROUND_BIG
-#define FORCEC_ROUND_BIG 768
-#endif
-#ifndef FORCEC_MINB
-#define FORCEC_MINB 4
-#endif
-#ifndef FORCEC_MHD_MINB
-#define FORCEC_MHD_MINB 2
-#endif
-template <bool MHD, bool ADIA, bool GRAV> struct ForceCtaParts { static constexpr int NP = 6 + ((ADIA || GRAV) ? 2 : 0) + (MHD ? 2 : 0); };
-
-template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS, int ROUND>
-__global__ void __launch_bounds__(CTA_THREADS, MHD ? FORCEC_MHD_MINB : (GRAV ? 3 : FORCEC_MINB)) k_force_cta(const ForceArgs a, const __grid_constant__ DevParams dp)
-{
-    typedef SphKern<K> KF;
-    constexpr int NP = ForceCtaParts<MHD, ADIA, GRAV>::NP;
-    constexpr unsigned OFF_D = 96u * ROUND, OFF_E = (96u + ((ADIA || GRAV) ? 32u : 0u)) * ROUND;   // byte offsets of the optional parts
-    typedef CtaSharedT<ROUND, NP> CS;
-    constexpr int NFIN = 13;
-    extern __shared__ __align__(16) unsigned char forcec_smem[];
-    CS &cs = *reinterpret_cast<CS *>(forcec_smem);
-    double (*fin)[NFIN][32] = reinterpret_cast<double (*)[NFIN][32]>(&cs.rec[0][0]);
-    const int lane = lane_id(), wib = threadIdx.x >> 5;
-    const unsigned cs_s = ws_shared_addr(cs);
-    const unsigned hm_lane = cs_s + (unsigned)offsetof(CS, hm) + 4u * lane, sidx_s = cs_s + (unsigned)offsetof(CS, sidx);
-    const unsigned rec_s = cs_s + (unsigned)offsetof(CS, rec);
-    int *clist = a.stage_idx + (size_t)blockIdx.x * a.scratch_per_warp;
-    const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
-    const float fLx = (float)Lx, fLy = (float)Ly, fLz = (float)Lz;
-    const double halfLmin = 0.5 * fmin(Lx, fmin(Ly, Lz));
-    const sphgpu_params &p = dp.p;
-    unsigned long long st_pairs = 0, st_trial = 0;
-    double st_dtc = 1.e29, st_dtf = 1.e29, st_dtmax = 0.;
-    int st_nbinmax = 0, st_ncheckbin = 0;
-    constexpr bool indts = INDTS;
-    const float hmax_global = (a.ncells > 1) ? fmaxf(a.nodes[0].hmax[0], a.nodes[0].hmax[1]) : 0.f;
-    const double pmass = p.massoftype[IGAS];
-    const double beta = p.beta;
-    constexpr bool USEJ = MHD || (ADIA && !GRAV);                    // force.F90:1343-1345 without dust
-    constexpr int FSTRIDE = MHD ? 5 : ((ADIA || GRAV) ? 4 : 3);     // double4 per packed record in global memory
-
-    while (true) {
-        __syncthreads();                                             // the previous group's shared memory is no longer in use
-        if (threadIdx.x == 0) cs.ctl[0] = (int)atomicAdd(&a.cnt[CNT_WORK], 1ull);
-        __syncthreads();
-        const int cellid = cs.ctl[0];
-        if (cellid >= a.ngroups) break;
-        const Cell cell = a.groups[cellid];
-        if (cell.active == 0) continue;                              // force.F90:509
-        const double cx = 0.5 * (cell.lo[0] + cell.hi[0]), cy = 0.5 * (cell.lo[1] + cell.hi[1]), cz = 0.5 * (cell.lo[2] + cell.hi[2]);
-        const double halfext = 0.5 * fmax(cell.hi[0] - cell.lo[0], fmax(cell.hi[1] - cell.lo[1], cell.hi[2] - cell.lo[2]));
-        float tlo[3], thi[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) { tlo[k] = __double2float_rd(cell.lo[k]); thi[k] = __double2float_ru(cell.hi[k]); }
-        const double rreach = KF::radkern * fmax(cell.hmax, (double)hmax_global) * a.hscale * 1.0001;
-        const double rcut = KF::radkern * cell.hmax * a.hscale;
-        const bool wide = PERIODIC && (halfext + rreach >= 0.999 * halfLmin);
-        const bool interior = !PERIODIC || (cell.lo[0] - rreach > p.xmin && cell.hi[0] + rreach < p.xmax && cell.lo[1] - rreach > p.ymin &&
-                                            cell.hi[1] + rreach < p.ymax && cell.lo[2] - rreach > p.zmin && cell.hi[2] + rreach < p.zmax);
-        float reach = 0.f;
-        const int *cl = clist;
-        int ncl = a.wl.ncl[cellid];
-        if (ncl >= 0) { cl = a.wl.list + (size_t)cellid * a.wl.cap; reach = a.wl.reach[cellid]; }
-        else ncl = cta_walk<true, PERIODIC>(cs, a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut), __double2float_ru(KF::radkern * a.hscale), fLx, fLy,
-                                            fLz, clist, a.scratch_per_warp, reach);
-        if (ncl < 0) { if (threadIdx.x == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
-        int nlist = 0;
-        const FilterScale fs = filter_scale((float)halfext, reach);
-        // ---- lane = target in every warp (start_cell, force.F90:2172-2514; per-particle part done by k_force_prep)
-        const int s = cell.start + min(lane, cell.count - 1);
-        bool act = false;
-        { bool g_, d_; int t_; if (lane < cell.count) get_partinfo_d(a.stype[s], p.set_boundaries_to_active, 0, act, g_, d_, t_); }
-        const double4 *ri = a.frec + FSTRIDE * (size_t)s;
-        const double4 T0 = ri[0], T1 = ri[1], T2 = ri[2];
-        double4 T3 = make_double4(0., 0., 0., 0.), T4 = T3;
-        if (ADIA || MHD || GRAV) T3 = ri[3];
-        if (MHD) T4 = ri[4];
-        const double xi = T0.x, yi = T0.y, zi = T0.z, hi1 = T0.w, hi21 = hi1 * hi1;
-        const double h = a.pos4[s].w;
-        const double gi = T1.w, pro2i = T2.x, vwavei = T2.y, avwi = T2.z, rho1i = T2.w, pri = T3.x;
-        const double hrho1i = -0.5 * rho1i;
-        const FilterTarget ft = filter_target(fs, (float)(xi - cx), (float)(yi - cy), (float)(zi - cz),
-                                              act ? (wide ? -1.f : __double2float_ru(KF::radkern * h)) : 0.f);
-        double fpot = 0.;
-        double fx = 0., fy = 0., fz = 0., drhodt = 0., dudtdiss = 0., dendtdiss = 0., divBsym = 0., dBx = 0., dBy = 0., dBz = 0., divBdiff = 0.;
-        double vsigmax = 0.;
-        int npair = 0, ibin_neigh = 0;
-        for (int cellpos = 0; cellpos < ncl;) {                     // rounds of <= ROUND candidates staged in shared memory
-            auto stage_rec = [&](int slot, int j, const double2 &xy, const double2 &zw) {
-                const double4 *rj = a.frec + FSTRIDE * (size_t)j;
-                const double4 B = ldg256(rj + 1), C = ldg256(rj + 2);
-                cs.rec[0][slot] = xy; cs.rec[1][slot] = zw;
-                cs.rec[2][slot] = make_double2(B.x, B.y); cs.rec[3][slot] = make_double2(B.z, B.w);
-                cs.rec[4][slot] = make_double2(C.x, C.y); cs.rec[5][slot] = make_double2(C.z, C.w);
-                if (ADIA || GRAV) { const double4 D = ldg256(rj + 3); cs.rec[6][slot] = make_double2(D.x, D.y); cs.rec[7][slot] = make_double2(D.z, D.w); }
-                if (MHD) { const double4 E = ldg256(rj + 4); cs.rec[NP - 2][slot] = make_double2(E.x, E.y); cs.rec[NP - 1][slot] = make_double2(E.z, E.w); }
-            };
-            const int nr = cta_stage_round<PERIODIC, true>(cs, cl, ncl, cellpos, reinterpret_cast<const double2 *>(a.frec), 2 * FSTRIDE, cx, cy, cz, Lx, Ly, Lz,
-                                                           (float)KF::radkern, fs, PERIODIC && interior, cell.start, stage_rec);
-            const int myslot = cs.selfslot[lane];
-            nlist += nr;
-            if (wide) cta_build_masks<false>(cs, nr, ft); else cta_build_masks<true>(cs, nr, ft);
-            HitRange hr = cta_split_hits(cs, (nr + 31) >> 5, hm_lane);
-            int c = -1; unsigned m = 0u;
-            auto pair2 = [&](int slot0, int slot1) {
-                const int sl[2] = {slot0, slot1 >= 0 ? slot1 : slot0};
-                const bool live[2] = {slot0 != myslot, slot1 >= 0 && slot1 != myslot};
-                double2 XY[2], ZW[2], V0[2], V1[2], C0[2], C1[2], D0[2], D1[2], E0[2], E1[2];
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    const unsigned a0 = rec_s + 16u * (unsigned)sl[k];
-                    XY[k] = lds_d2(a0); ZW[k] = lds_d2(a0 + 16u * ROUND);
-                    V0[k] = lds_d2(a0 + 32u * ROUND); V1[k] = lds_d2(a0 + 48u * ROUND);
-                    C0[k] = lds_d2(a0 + 64u * ROUND); C1[k] = lds_d2(a0 + 80u * ROUND);
-                    if (ADIA || GRAV) { D0[k] = lds_d2(a0 + OFF_D); D1[k] = lds_d2(a0 + OFF_D + 16u * ROUND); }
-                    if (MHD) { E0[k] = lds_d2(a0 + OFF_E); E1[k] = lds_d2(a0 + OFF_E + 16u * ROUND); }
-                }
-                double dx[2], dy[2], dz[2];
-#pragma unroll
-                for (int k = 0; k < 2; k++) { dx[k] = xi - XY[k].x; dy[k] = yi - XY[k].y; dz[k] = zi - ZW[k].x; }
-                if (PERIODIC && !interior) {                            // force.F90:1266-1270
-#pragma unroll
-                    for (int k = 0; k < 2; k++) {
-                        if (fabs(dx[k]) > 0.5 * Lx) dx[k] = dx[k] - copysign(Lx, dx[k]);
-                        if (fabs(dy[k]) > 0.5 * Ly) dy[k] = dy[k] - copysign(Ly, dy[k]);
-                        if (fabs(dz[k]) > 0.5 * Lz) dz[k] = dz[k] - copysign(Lz, dz[k]);
-                    }
-                }
-                double r2[2], rij1[2], grkerni[2], grkernj[2];
-                bool ini[2], inj[2], isn[2];
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    r2[k] = __dadd_rn(__dadd_rn(__dmul_rn(dx[k], dx[k]), __dmul_rn(dy[k], dy[k])), __dmul_rn(dz[k], dz[k]));
-                    const double hj1 = ZW[k].y;
-                    const double q2i = __dmul_rn(r2[k], hi21), q2j = __dmul_rn(r2[k], __dmul_rn(hj1, hj1));       // force.F90:1272, :1285
-                    ini[k] = (q2i < KF::radkern2) && live[k]; inj[k] = (q2j < KF::radkern2) && live[k];          // :1287, :1230 (exact membership)
-                    isn[k] = ini[k] || inj[k];
-                    npair += isn[k] ? 1 : 0;
-                    if (indts && isn[k]) {                               // j neighbours an active particle: wake flag, Saitoh-Makino input
-                        const int jj = (int)lds_u32(sidx_s + 4u * (unsigned)sl[k]);
-                        if (abs((int)a.stype[jj]) != IBOUNDARY) {
-                            if (a.s_wake[jj] < a.ibinnow_m1) atomicMax(&a.s_wake[jj], a.ibinnow_m1);
-                            ibin_neigh = max(ibin_neigh, (int)a.s_ibinold[jj]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 2; k++) rij1[k] = rsqrt_pos(r2[k]);                 // force.F90:1293-1299
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    const double rij = r2[k] * rij1[k];
-                    grkerni[k] = KF::grkern_bf(rij * hi1) * (live[k] ? gi : 0.);         // :1301-1302
-                    grkernj[k] = KF::grkern_bf(rij * ZW[k].y) * (live[k] ? V1[k].y : 0.);   // :1325-1327
-                }
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    const double runix = dx[k] * rij1[k], runiy = dy[k] * rij1[k], runiz = dz[k] * rij1[k];
-                    double fgrav = 0.;
-                    if (GRAV) {                                            // softened gravity of SPH-neighbour pairs, force.F90:1303-1339, :1522
-                        const double hj1 = ZW[k].y, rij = r2[k] * rij1[k];
-                        const double q2i = __dmul_rn(r2[k], hi21), q2j = __dmul_rn(r2[k], __dmul_rn(hj1, hj1));
-                        double phii = -rij1[k], fgravi = rij1[k] * rij1[k], fgravj = fgravi;
-                        if (ini[k]) { double fmi; KF::softening(q2i, rij * hi1, phii, fmi); phii *= hi1; fgravi = fmi * hi21 + T3.z * grkerni[k]; }
-                        if (inj[k]) { double phij, fmj; KF::softening(q2j, rij * hj1, phij, fmj); fgravj = fmj * (hj1 * hj1) + D1[k].x * grkernj[k]; }
-                        fgrav = isn[k] ? 0.5 * pmass * (fgravi + fgravj) : 0.;
-                        fpot += isn[k] ? pmass * phii : 0.;
-                    }
-                    const double dvx = T1.x - V0[k].x, dvy = T1.y - V0[k].y, dvz = T1.z - V1[k].x;
-                    const double projv = dvx * runix + dvy * runiy + dvz * runiz;
-                    const double bp = beta * projv;
-                    const double vwavej = C0[k].y;
-                    double vs = vwavei - bp;
-                    if (USEJ || inj[k]) vs = dmax(vs, vwavej - bp);
-                    vsigmax = dmax(vsigmax, isn[k] ? vs : 0.);
-                    const double ap = (projv < 0.) ? projv : 0.;          // force.F90:1581-1592: approaching pairs only
-                    const double qrho2i = hrho1i * dmax(avwi - bp, 0.) * ap;
-                    const double rho1j = C1[k].y;
-                    const double qrho2j = (-0.5 * rho1j) * dmax(C1[k].x - bp, 0.) * ap;
-                    const double gradp = pmass * ((pro2i + qrho2i) * grkerni[k] + (C0[k].x + qrho2j) * grkernj[k]);
-                    double projsx = 0., projsy = 0., projsz = 0.;
-                    if (ADIA) {                                            // artificial conductivity, force.F90:1606-1624
-                        const double denij = T3.y - D0[k].y;
-                        const double vsigu = GRAV ? fabs(projv) : sqrt(fabs(pri - D0[k].x) * (2. * rho1i * rho1j / (rho1i + rho1j)));
-                        const double auterm = 0.5 * pmass * rho1i * p.alphau, autermj = 0.5 * pmass * rho1j * p.alphau;
-                        dendtdiss += vsigu * denij * (auterm * grkerni[k] + autermj * grkernj[k]);
-                        dudtdiss += pmass * qrho2i * projv * grkerni[k];
-                    }
-                    if (MHD) {                                             // force.F90:1428-1444, :1626-1684, :2132-2150
-                        const double Bxi = T4.x, Byi = T4.y, Bzi = T4.z, psii = T4.w;
-                        const double Bxj = E0[k].x, Byj = E0[k].y, Bzj = E1[k].x, psij = E1[k].y;
-                        const double dBxx = Bxi - Bxj, dByy = Byi - Byj, dBzz = Bzi - Bzj;
-                        const double projBi = Bxi * runix + Byi * runiy + Bzi * runiz;
-                        const double projBj = Bxj * runix + Byj * runiy + Bzj * runiz;
-                        const double projdB = dBxx * runix + dByy * runiy + dBzz * runiz;
-                        divBdiff += -pmass * projdB * grkerni[k];
-                        const double rho21i = rho1i * rho1i, rho21j = rho1j * rho1j;
-                        const double avBterm = 0.5 * pmass * rho1i * p.alphaB * rho1i, avBtermj = 0.5 * pmass * rho1j * p.alphaB * rho1j;
-                        const double tx = dvx - projv * runix, ty = dvy - projv * runiy, tz = dvz - projv * runiz;
-                        const double vsigB = sqrt(tx * tx + ty * ty + tz * tz);
-                        const double dBdissterm = (avBterm * grkerni[k] + avBtermj * grkernj[k]) * vsigB;
-                        if (ADIA && p.iresistive_heating > 0) dudtdiss += -0.5 * (dBxx * dBxx + dByy * dByy + dBzz * dBzz) * dBdissterm;
-                        const double pmjrho21grkerni = pmass * rho21i * grkerni[k], pmjrho21grkernj = pmass * rho21j * grkernj[k];
-                        const double termi = pmjrho21grkerni * projBi;
-                        divBsym += termi + pmjrho21grkernj * projBj;
-                        const double dpsiterm = p.overcleanfac * (pmjrho21grkerni * psii * vwavei + pmjrho21grkernj * psij * vwavej);
-                        dBx += -termi * dvx + dBdissterm * dBxx - dpsiterm * runix;
-                        dBy += -termi * dvy + dBdissterm * dByy - dpsiterm * runiy;
-                        dBz += -termi * dvz + dBdissterm * dBzz - dpsiterm * runiz;
-                        const double si = -pmass * rho21i * projBi * grkerni[k], sj = -pmass * rho21j * projBj * grkernj[k];   // Maxwell stress, :1677-1684
-                        projsx = si * Bxi + sj * Bxj; projsy = si * Byi + sj * Byj; projsz = si * Bzi + sj * Bzj;
-                    }
-                    fx += -runix * (gradp + fgrav) - projsx;
-                    fy += -runiy * (gradp + fgrav) - projsy;
-                    fz += -runiz * (gradp + fgrav) - projsz;
-                    drhodt += projv * grkerni[k];
-                }
-            };
-            while (true) {
-                int slot0, slot1;
-                next_hits2_r(hm_lane, hr, c, m, slot0, slot1);
-                if (slot0 < 0) break;
-                pair2(slot0, slot1);
-            }
-            __syncthreads();                                         // the round's buffers are free again
-        }
-        // ---- the partial sums of warps 1..3 go to warp 0 through the (now free) record area; fixed order of addition
-        if (wib > 0) {
-            double (*o)[32] = fin[wib - 1];
-            o[0][lane] = fx; o[1][lane] = fy; o[2][lane] = fz; o[3][lane] = drhodt; o[4][lane] = dudtdiss; o[5][lane] = dendtdiss; o[6][lane] = divBsym;
-            o[7][lane] = dBx; o[8][lane] = dBy; o[9][lane] = dBz; o[10][lane] = divBdiff; o[11][lane] = fpot; o[12][lane] = vsigmax;
-        }
-        cs.tot[wib][lane] = npair; cs.cellincl[threadIdx.x] = ibin_neigh;
-        __syncthreads();
-        // ---- finish_cell_and_store_results (force.F90:2649-3330), lane = target, gas only, warp 0 ----
-        if (wib == 0 && act) {
-#define FSUM(x, k) x = ((x + fin[0][k][lane]) + fin[1][k][lane]) + fin[2][k][lane]
-            FSUM(fx, 0); FSUM(fy, 1); FSUM(fz, 2); FSUM(drhodt, 3); FSUM(dudtdiss, 4); FSUM(dendtdiss, 5); FSUM(divBsym, 6);
-            FSUM(dBx, 7); FSUM(dBy, 8); FSUM(dBz, 9); FSUM(divBdiff, 10); FSUM(fpot, 11);
-#undef FSUM
-            vsigmax = dmax(dmax(vsigmax, fin[0][12][lane]), dmax(fin[1][12][lane], fin[2][12][lane]));
-            npair = cs.tot[0][lane] + cs.tot[1][lane] + cs.tot[2][lane] + cs.tot[3][lane];
-            ibin_neigh = max(max(cs.cellincl[lane], cs.cellincl[32 + lane]), max(cs.cellincl[64 + lane], cs.cellincl[96 + lane]));
-            st_pairs += npair; st_trial += nlist;
-            double dtc = p.dtmax, dtf = 1.e29, dtclean = 1.e29;
-            double fxyz4 = 0.;
-            double4 dB = make_double4(0., 0., 0., 0.);
-            float divBsymm4 = 0.f;
-            const double rhoi = 1. / rho1i;
-            if (GRAV) {                                              // force.F90:2909-2927: far field (L2P + distant P2P) from gravity.cu
-                const double4 g = a.gacc[a.perm[s]];
-                double potensoft0, dum;
-                KF::softening(0., 0., potensoft0, dum);
-                fx += g.x; fy += g.y; fz += g.z;
-                a.s_poten[s] = (float)(0.5 * pmass * (fpot + pmass * potensoft0 * hi1) + 0.5 * pmass * g.w);
-            }
-            if (MHD) {                                               // force.F90:2939-2965
-                const double B2i = T4.x * T4.x + T4.y * T4.y + T4.z * T4.z;
-                double frac_divB = 0.;
-                if (B2i > 0.0) {
-                    const double betai = 2.0 * pri / B2i;
-                    if (betai < 2.0) frac_divB = 1.0;
-                    else if (betai < 10.0) frac_divB = (10.0 - betai) * 0.125;
-                }
-                fx -= T4.x * divBsym * frac_divB; fy -= T4.y * divBsym * frac_divB; fz -= T4.z * divBsym * frac_divB;
-                divBsymm4 = (float)(rhoi * divBsym);
-            }
-            const double drhodti = pmass * drhodt;
-            const double divvi = -drhodti * rho1i;
-            if (ADIA) {                                              // force.F90:3024-3095 (ien_type = energy, fac = 1)
-                const double pdv_work = pri * rho1i * rho1i * drhodti;
-                if (p.ipdv_heating > 0) fxyz4 += pdv_work;
-                if (p.ishock_heating > 0) fxyz4 += dudtdiss;
-                fxyz4 += dendtdiss;
-            }
-            if (MHD) {                                               // force.F90:3103-3125
-                dB.x = dBx; dB.y = dBy; dB.z = dBz;
-                if (p.psidecayfac > 0.) {
-                    const double vcleani = p.overcleanfac * vwavei;
-                    const double dtau = p.psidecayfac * vcleani * hi1;
-                    dB.w = -vcleani * divBdiff * rho1i - T4.w * dtau - 0.5 * T4.w * divvi;
-                    dtclean = p.C_cour * h / (vcleani + DBL_MIN);
-                }
-            }
-            const double vsigdtc = fmax(vsigmax, vwavei);
-            if (vsigdtc > DBL_MIN) dtc = p.C_cour * h / (vsigdtc * fmax(p.alpha, 1.0));          // force.F90:3138-3141
-            if (ADIA) {
-                const double eni = T3.y;
-                if (eni + dtc * fxyz4 < DBL_EPSILON && eni > DBL_EPSILON) fxyz4 = fxyz4 / (1. - dtc * fxyz4 / eni);       // :3144-3148
-            }
-            const double f2i = fx * fx + fy * fy + fz * fz;
-            if (fabs(f2i) > DBL_EPSILON) dtf = p.C_force * sqrt(h / sqrt(f2i));                  // force.F90:3217-3219
-            a.s_fxyzu[s] = make_double4(fx, fy, fz, fxyz4);
-            a.s_divvf[s] = (float)divvi;
-            if (MHD) { a.s_dB[s] = dB; a.s_divBsymm[s] = divBsymm4; }
-            a.s_done[s] = 2;
-            if (indts) {                                             // force.F90:3272-3310 + get_newbin (utils_indtimesteps.f90:230-287)
-                double dti = dtc;
-                const double dtitmp = fmin(dtf, dtclean);
-                if (dtitmp < dti + DBL_MIN && dtitmp < p.dtmax) dti = dtitmp;
-                const int ibin_oldi = (int)a.s_ibin[s];
-                int ibin_newi;
-                if (dti > p.dtmax) ibin_newi = 0;
-                else if (dti < DBL_MIN) ibin_newi = 30;
-                else ibin_newi = max((int)(log(2. * p.dtmax / dti) * 1.4426950408889634 - DBL_EPSILON), 0);
-                int ibini = ibin_oldi;
-                if (ibin_newi > ibin_oldi) ibini = ibin_newi;
-                else if (ibin_newi < ibin_oldi && ibin_oldi <= a.nbinmax && a.icall < 2) {
-                    if (a.istepfrac % (1 << (a.nbinmax - (ibin_oldi - 1))) == 0) ibini = ibini - 1;
-                }
-                ibini = max(ibini, ibin_neigh - 1);                  // Saitoh-Makino limiter
-                a.s_ibinnew[s] = (int8_t)ibini;
-                st_nbinmax = max(st_nbinmax, ibini); st_ncheckbin += 1;
-            } else {
-                st_dtc = fmin(st_dtc, dtc);
-                st_dtf = fmin(st_dtf, fmin(dtf, dtclean));
-                st_dtmax = fmax(st_dtmax, dtc);
-            }
-        }
-    }
-    if (wib != 0) return;                                            // the statistics live in warp 0
-    st_dtc = warp_min(st_dtc); st_dtf = warp_min(st_dtf); st_dtmax = warp_max(st_dtmax);
-#pragma unroll
-    for (int sft = 16; sft >= 1; sft >>= 1) { st_pairs += __shfl_xor_sync(FULLMASK, st_pairs, sft); st_trial += __shfl_xor_sync(FULLMASK, st_trial, sft); }
-    if (indts) {
-#pragma unroll
-        for (int sft = 16; sft >= 1; sft >>= 1) { st_nbinmax = max(st_nbinmax, __shfl_xor_sync(FULLMASK, st_nbinmax, sft)); st_ncheckbin += __shfl_xor_sync(FULLMASK, st_ncheckbin, sft); }
-        if (lane == 0 && st_ncheckbin) { atomicMax(&a.cnt[CNT_NBINMAX], (unsigned long long)st_nbinmax); atomicAdd(&a.cnt[CNT_NCHECKBIN], (unsigned long long)st_ncheckbin); }
-    }
-    if (lane == 0) {
-        atomicAdd(&a.cnt[CNT_NPAIRS], st_pairs); atomicAdd(&a.cnt[CNT_NTRIAL], st_trial);
-        atomic_min_pos(&a.dscal[DS_DTCOURANT], st_dtc); atomic_min_pos(&a.dscal[DS_DTFORCE], st_dtf);
-        atomic_min_pos(&a.dscal[DS_DTMINI], st_dtc); atomic_max_pos(&a.dscal[DS_DTMAXI], st_dtmax);
-    }
-}
-
 #ifndef XTRA_MINB
 #define XTRA_MINB 3
 #endif
@@ -1221,27 +879,9 @@ int launch_force_fast3(sphgpu_ctx *c, const ForceArgs &a, int grid)
     c->launches++;
     return 0;
 }
-template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS, int ROUND>
-int launch_force_cta(sphgpu_ctx *c, const ForceArgs &a, int grid)
-{
-    const size_t smem = sizeof(CtaSharedT<ROUND, ForceCtaParts<MHD, ADIA, GRAV>::NP>);
-    cudaFuncSetAttribute(k_force_cta<K, PERIODIC, MHD, ADIA, GRAV, INDTS, ROUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (grid < 0) {
-        int bps = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force_cta<K, PERIODIC, MHD, ADIA, GRAV, INDTS, ROUND>, CTA_THREADS, smem);
-        return bps < 1 ? 1 : bps;
-    }
-    k_force_cta<K, PERIODIC, MHD, ADIA, GRAV, INDTS, ROUND><<<grid, CTA_THREADS, smem, c->stream>>>(a, c->hp);
-    c->launches++;
-    return 0;
-}
 template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS>
 int launch_force_fast2(sphgpu_ctx *c, const ForceArgs &a, int grid)
 {
-    if (c->pair_cta) {
-        if (c->dens_trial_max > FORCEC_ROUND && c->dens_trial_hint > 0.8 * FORCEC_ROUND) return launch_force_cta<K, PERIODIC, MHD, ADIA, GRAV, INDTS, FORCEC_ROUND_BIG>(c, a, grid);
-        return launch_force_cta<K, PERIODIC, MHD, ADIA, GRAV, INDTS, FORCEC_ROUND>(c, a, grid);
-    }
     if (c->dens_trial_max > FORCE_ROUND && c->dens_trial_hint > 0.8 * FORCE_ROUND) return launch_force_fast3<K, PERIODIC, MHD, ADIA, GRAV, INDTS, true>(c, a, grid);
     return launch_force_fast3<K, PERIODIC, MHD, ADIA, GRAV, INDTS, false>(c, a, grid);
 }

@@ -109,7 +109,6 @@ int sphgpu_create(const sphgpu_params *params, int device, sphgpu_ctx **out)
     cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     for (int k = 0; k < 16; k++) cudaEventCreate(&c->ev[k]);
     if (const char *e = getenv("SPHGPU_GROUP_PACK")) c->group_pack = atoi(e) < 0 ? 0 : (atoi(e) > 4096 ? 4096 : atoi(e));   // A/B switch for whole test runs
-    if (const char *e = getenv("SPHGPU_PAIR_CTA")) c->pair_cta = atoi(e) != 0;                                               // A/B switch: 0 = round-1 kernels (one warp per target group)
     set_params_internal(c, params);
     *out = c;
     return SPHGPU_OK;
@@ -158,7 +157,6 @@ int sphgpu_set_option(sphgpu_ctx *c, const char *name, double value)
     if (!strcmp(name, "hilbert")) { c->hilbert = value != 0.; c->tree_valid = false; return 0; }
     if (!strcmp(name, "halo_hgrow")) { c->halo_hgrow = value; return 0; }
     if (!strcmp(name, "always_refit")) { c->always_refit = value != 0.; return 0; }
-    if (!strcmp(name, "pair_cta")) { c->pair_cta = value != 0.; return 0; }
     if (!strcmp(name, "force_general")) { c->force_general = value != 0.; return 0; }
     if (!strcmp(name, "grav_p2p_per_particle")) { c->grav_p2p_per_particle = (int)value < 8 ? 8 : (int)value; return 0; }
     if (!strcmp(name, "legacy_stream")) {

@@ -420,189 +420,3 @@ __device__ __forceinline__ double pair_r2(double xi, double yi, double zi, const
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-
-// =====================================================================================================================================
-// Round 2: one CTA (4 warps) per target group, whole neighbour records in shared memory.
-//
-// Why.  With one warp per group the pair loops gathered every neighbour's record per lane from global memory: 32 different 32-byte
-// sectors per load instruction = 32 wavefronts on the L1 data pipe, which ran 75-90 % busy while the FP64 pipe idled at 33-37 %
-// (profiles/r01_pair_kernels_ncu.txt).  A per-warp copy of the full records does not fit (384 x 80..160 B per warp), so the four warps
-// of a CTA now share ONE group: the candidates are staged once per CTA as structure-of-arrays of 16-byte parts, the pair loop reads
-// them with LDS.128 (consecutive slots -> consecutive bank groups; neighbouring targets read the same or adjacent slots), and no global
-// load is left in the loop.  Lane = target in every warp; each target's hits are split four ways BY RANK (warp w takes hits
-// [w q, (w+1) q) of the lane's hit list, q = ceil(hits/4) rounded up to even), so the trips per warp stay balanced whatever the spatial
-// order of the candidates; the partial sums are added in a fixed order (warp 0..3) through shared memory.
-// =====================================================================================================================================
-#define CTA_WARPS 4
-#define CTA_THREADS 128
-
-template <int ROUND_, int NP_>
-struct __align__(16) CtaSharedT {
-    static constexpr int ROUND = ROUND_, NCHUNK = ROUND_ / 32, NP = NP_;
-    double2 rec[NP_][ROUND_];           // staged neighbour records, part p of slot s at rec[p][s]
-    uint4 hp[NCHUNK][16];               // FP16 filter entries (as WarpSharedT)
-    unsigned hm[NCHUNK][32];            // hm[chunk][t]: hit mask of target t over the chunk's 32 candidates
-    int sidx[ROUND_];                   // sorted particle slot of every staged candidate
-    int cellincl[CTA_THREADS];          // inclusive candidate count up to each cell of the round
-    int selfslot[32];
-    int tot[CTA_WARPS][32];             // hits of target t inside the chunks whose masks warp w built; later: partial neighbour counts
-    double red[CTA_WARPS][4][32];       // per-iteration partial sums (density: rho, gradh)
-    int wtot[CTA_WARPS];
-    int ctl[8];                         // [0] group id  [1] ncl of an in-kernel walk
-    float fctl[4];                      // [0] reach of an in-kernel walk
-    __device__ __forceinline__ int *walk_stack() { return reinterpret_cast<int *>(&rec[0][0]); }
-    static_assert((size_t)NP_ * ROUND_ * 16 >= WALK_STACK * sizeof(int), "record area too small for the walk stack");
-};
-
-// in-kernel walk (groups whose prepared list overflowed, and re-walks of the density iteration): warp 0 walks, everybody gets the result
-template <bool SYM, bool PERIODIC, class CS>
-__device__ __forceinline__ int cta_walk(CS &cs, const TreeNodeF *__restrict__ nodes, const Cell *__restrict__ cells, int ncells, const float *tlo, const float *thi,
-                                        float rcut_t, float radkern, float fLx, float fLy, float fLz, int *__restrict__ clist, int cap, float &reach)
-{
-    __syncthreads();                                             // the record area (walk stack) is free
-    if (threadIdx.x < 32) {
-        float r = 0.f;
-        const int ncl = warp_walk<SYM, PERIODIC>(nodes, cells, ncells, tlo, thi, rcut_t, radkern, fLx, fLy, fLz, cs.walk_stack(), clist, cap, r);
-        if (threadIdx.x == 0) { cs.ctl[1] = ncl; cs.fctl[0] = r; }
-    }
-    __syncthreads();
-    reach = cs.fctl[0];
-    return cs.ctl[1];
-}
-
-// Copy the particles of the next cells of the list into the CTA's round buffer: the longest prefix of the next <= 128 cells that fits.
-// thread = cell for the scan of the counts, then thread = slot: position -> FP16 filter entry, stage_rec(slot, j, xy, zw) stages the
-// record.  Ends with a barrier; returns the number staged; cellpos advances.
-template <bool PERIODIC, bool WINV, class CS, class F>
-__device__ __forceinline__ int cta_stage_round(CS &cs, const int *__restrict__ clist, int ncl, int &cellpos, const double2 *__restrict__ posrec2, int stride2,
-                                               double cx, double cy, double cz, double Lx, double Ly, double Lz, float radkern, const FilterScale &fs,
-                                               bool interior, int gstart, F stage_rec)
-{
-    constexpr int ROUND = CS::ROUND;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid < 32) cs.selfslot[tid] = -1;
-    const int navail = min(CTA_THREADS, ncl - cellpos);
-    int start = 0, cnt = 0;
-    if (tid < navail) { const int pk = clist[cellpos + tid]; start = pk >> 5; cnt = (pk & 31) + 1; }
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULLMASK, incl, d); if (lane >= d) incl += t; }
-    if (lane == 31) cs.wtot[w] = incl;
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < CTA_WARPS - 1; k++) if (k < w) incl += cs.wtot[k];
-    const bool ok = tid < navail && incl <= ROUND;              // a prefix property: counts are positive
-    cs.cellincl[tid] = incl;
-    if (ok) { const int base = incl - cnt; for (int k = 0; k < cnt; k++) cs.sidx[base + k] = start + k; }
-    const int nb = __syncthreads_count(ok);
-    const int n = cs.cellincl[nb - 1];
-    cellpos += nb;
-#pragma unroll 2
-    for (int slot = tid; slot < n; slot += CTA_THREADS) {
-        const int j = cs.sidx[slot];
-        const double2 pxy = posrec2[(size_t)j * stride2], pzw = posrec2[(size_t)j * stride2 + 1];
-        double rx = pxy.x - cx, ry = pxy.y - cy, rz = pzw.x - cz;
-        if (PERIODIC && !interior) {                  // interior: no candidate of this group lies across the periodic boundary
-            if (rx > 0.5 * Lx) rx -= Lx; else if (rx < -0.5 * Lx) rx += Lx;
-            if (ry > 0.5 * Ly) ry -= Ly; else if (ry < -0.5 * Ly) ry += Ly;
-            if (rz > 0.5 * Lz) rz -= Lz; else if (rz < -0.5 * Lz) rz += Lz;
-        }
-        float rkh;
-        if (WINV) rkh = __fmul_ru(radkern, __frcp_ru(__double2float_rd(pzw.y)));   // >= radkern * h_j
-        else rkh = __double2float_ru((double)radkern * pzw.y);
-        const float ux = fminf(fmaxf((float)rx * fs.scale, -8.f), 8.f), uy = fminf(fmaxf((float)ry * fs.scale, -8.f), 8.f),
-                    uz = fminf(fmaxf((float)rz * fs.scale, -8.f), 8.f);
-        __half *hw = reinterpret_cast<__half *>(&cs.hp[slot >> 5][slot & 15]) + ((slot >> 4) & 1);
-        hw[0] = __float2half_rn(ux); hw[2] = __float2half_rn(uy); hw[4] = __float2half_rn(uz); hw[6] = filter_limit(fs, rkh);
-        const unsigned t = (unsigned)(j - gstart);
-        if (t < 32u) cs.selfslot[t] = slot;
-        stage_rec(slot, j, pxy, pzw);
-    }
-    __syncthreads();
-    return n;
-}
-
-// hit masks of the round: warp w builds the chunks c = w, w + 4, ... (lane = target, as build_masks); ends with a barrier
-template <bool SYM, class CS>
-__device__ __forceinline__ void cta_build_masks(CS &cs, int n, const FilterTarget &t)
-{
-    const int lane = lane_id(), w = threadIdx.x >> 5;
-    const int nchunk = (n + 31) >> 5;
-    const bool takes_part = __low2float(t.lim) > 0.f;
-    int mytot = 0;
-    for (int c = w; c < nchunk; c += CTA_WARPS) {
-        unsigned mine = 0u;
-#pragma unroll
-        for (int p = 0; p < 16; p++) {
-            const uint4 q = cs.hp[c][p];
-            const __half2 ax = __hsub2(t.x, *reinterpret_cast<const __half2 *>(&q.x)), ay = __hsub2(t.y, *reinterpret_cast<const __half2 *>(&q.y)),
-                          az = __hsub2(t.z, *reinterpret_cast<const __half2 *>(&q.z));
-            const __half2 r2 = __hfma2(az, az, __hfma2(ay, ay, __hmul2(ax, ax)));
-            const __half2 lim = SYM ? __hmax2(t.lim, *reinterpret_cast<const __half2 *>(&q.w)) : t.lim;
-            mine |= __hlt2_mask(r2, lim) & (0x00010001u << p);
-        }
-        const int left = n - c * 32;                          // slots beyond n hold stale data
-        if (left < 32) mine &= (1u << left) - 1u;
-        if (!takes_part) mine = 0u;
-        cs.hm[c][lane] = mine;
-        mytot += __popc(mine);
-    }
-    cs.tot[w][lane] = mytot;
-    __syncthreads();
-}
-
-// positions below the (k+1)-th set bit of m as a mask (0 <= k < popc(m)): the k lowest set bits of m are m & below_kth_bit(m, k)
-__device__ __forceinline__ unsigned below_kth_bit(unsigned m, int k)
-{
-    int pos = 0;
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) { const int t = pos + s; if (__popc(m & ((1u << t) - 1u)) <= k) pos = t; }
-    return (1u << pos) - 1u;
-}
-
-// this warp's share of the lane's hits: ranks [w q, (w+1) q) of the hit list.  nz = mask words with a share in it; the first and the
-// last of them are trimmed by keepfirst / keeplast when they are loaded.
-struct HitRange { unsigned nz; int cfirst, clast; unsigned keepfirst, keeplast; };
-template <class CS>
-__device__ __forceinline__ HitRange cta_split_hits(const CS &cs, int nchunk, unsigned hm_lane)
-{
-    const int lane = lane_id(), w = threadIdx.x >> 5;
-    const int tot = cs.tot[0][lane] + cs.tot[1][lane] + cs.tot[2][lane] + cs.tot[3][lane];
-    int q = (tot + CTA_WARPS - 1) / CTA_WARPS;
-    q += q & 1;                                             // even shares: only the last warp pads an odd hit count
-    const int r0 = w * q, r1 = min(r0 + q, tot);
-    HitRange hr; hr.nz = 0u; hr.cfirst = -1; hr.clast = -1; hr.keepfirst = ~0u; hr.keeplast = ~0u;
-    int lofirst = 0, hilast = 0, run = 0;
-    for (int c = 0; c < nchunk; c++) {
-        const int pc = __popc(lds_u32(hm_lane + 128u * (unsigned)c));
-        const int lo = max(r0 - run, 0), hi = min(r1 - run, pc);
-        if (lo < hi) {
-            hr.nz |= 1u << c;
-            if (lo > 0) { hr.cfirst = c; lofirst = lo; }
-            if (hi < pc) { hr.clast = c; hilast = hi; }
-        }
-        run += pc;
-    }
-    if (hr.cfirst >= 0) hr.keepfirst = ~below_kth_bit(lds_u32(hm_lane + 128u * (unsigned)hr.cfirst), lofirst);
-    if (hr.clast >= 0) hr.keeplast = below_kth_bit(lds_u32(hm_lane + 128u * (unsigned)hr.clast), hilast);
-    return hr;
-}
-
-// next_hits2 over the warp's share
-__device__ __forceinline__ void next_hits2_r(unsigned hm_lane, HitRange &hr, int &c, unsigned &m, int &slot0, int &slot1)
-{
-    if (m == 0u && hr.nz) {
-        c = __ffs(hr.nz) - 1; hr.nz &= hr.nz - 1u; m = lds_u32(hm_lane + 128u * (unsigned)c);
-        if (c == hr.cfirst) m &= hr.keepfirst;
-        if (c == hr.clast) m &= hr.keeplast;
-    }
-    slot0 = m ? c * 32 + (__ffs(m) - 1) : -1;
-    m &= m - 1u;
-    if (m == 0u && hr.nz) {
-        c = __ffs(hr.nz) - 1; hr.nz &= hr.nz - 1u; m = lds_u32(hm_lane + 128u * (unsigned)c);
-        if (c == hr.cfirst) m &= hr.keepfirst;
-        if (c == hr.clast) m &= hr.keeplast;
-    }
-    slot1 = m ? c * 32 + (__ffs(m) - 1) : -1;
-    m &= m - 1u;
-}

@@ -231,8 +231,8 @@ def setup_test_derivs(nx=100, rhozero=5.0, tolh=1.e-5, lattice="cubic", isotherm
                       dissipation=True, **kw):
     """test_derivs.f90:128-163; dissipation=False restates reset_dissipation_to_zero (:989-1003)."""
     if not dissipation:
-        kw = dict(alpha=0., alphau=0., alphaB=0., beta=0., **kw)
-    p = default_params(tolh=tolh, isothermal=int(isothermal), mhd=int(mhd), ieos=1 if isothermal else 2, **kw)
+        kw = {**dict(alpha=0., alphau=0., alphaB=0., beta=0.), **kw}
+    p = default_params(**{**dict(tolh=tolh, isothermal=int(isothermal), mhd=int(mhd), ieos=1 if isothermal else 2), **kw})
     if isothermal:
         p.polyk, p.gamma = 3.0, 1.0
     dxb = p.xmax - p.xmin
@@ -262,6 +262,64 @@ def setup_test_derivs(nx=100, rhozero=5.0, tolh=1.e-5, lattice="cubic", isotherm
         part.Bevol[:, 3] = 0.05 * np.sin(2 * pi * (x - p.xmin)) * np.cos(2 * pi * (y - p.ymin))
     hzero = p.hfact * (p.massoftype[IGAS] / rhozero) ** (1. / 3.)
     return part, hzero
+
+
+def unifdis_cubic_shell(xmin, xmax, ymin, ymax, zmin, zmax, delta, hfact, rmin=None, rmax=None):
+    """set_unifdis 'cubic' with the rmin/rmax mask (set_unifdis.f90:124-133, :181-233, in_range :615-620: both ends inclusive):
+    same loop order (x fastest), only the index range that can pass the mask is scanned."""
+    dxb, dyb, dzb = xmax - xmin, ymax - ymin, zmax - zmin
+    nx, ny, nz = _nint(dxb / delta), _nint(dyb / delta), _nint(dzb / delta)
+    dx, dy, dz = dxb / nx, dyb / ny, dzb / nz
+    rmin2 = rmin * rmin if rmin is not None else 0.
+    rmax2 = rmax * rmax if rmax is not None else np.finfo(np.float64).max
+
+    def axis(lo, d, n):
+        c = lo + (np.arange(1, n + 1) - 0.5) * d
+        if rmax is not None:
+            c = c[np.abs(c) <= rmax * (1. + 1e-12) + 1e-300]
+        return c
+    x, y, z = axis(xmin, dx, nx), axis(ymin, dy, ny), axis(zmin, dz, nz)
+    out = []
+    for zi in z:                                   # slabs keep the memory bounded (the blob lattice is 500^3)
+        rcyl2 = x[None, :] * x[None, :] + y[:, None] * y[:, None]
+        rr2 = rcyl2 + zi * zi
+        keep = (rmin2 <= rr2) & (rr2 <= rmax2)
+        jj, ii = np.nonzero(keep)                  # row-major: y slow, x fast = the reference's loop order
+        if len(ii):
+            slab = np.empty((len(ii), 4))
+            slab[:, 0], slab[:, 1], slab[:, 2], slab[:, 3] = x[ii], y[jj], zi, hfact * dx
+            out.append(slab)
+    return np.concatenate(out) if out else np.empty((0, 4))
+
+
+def setup_density_contrast(rhozero=5.0, tolh=1.e-5, isothermal=False):
+    """test_derivs.f90:651-713 (derivscontrast): a blob of 1000 x the density of the surrounding 50^3 medium, blob lattice spacing
+    psep/10, no dissipation.  Returns the particles, the number of test particles (r <= rblob - 2 hfact psep) and hblob.
+    Known answers held by the reference for the cubic kernel (:698-707): mean neighbours 57.466651861721814, max 988, total 37263216."""
+    p = default_params(tolh=tolh, isothermal=int(isothermal), ieos=1 if isothermal else 2, alpha=0., alphau=0., alphaB=0., beta=0.)
+    if isothermal:
+        p.polyk, p.gamma = 3.0, 1.0
+    dxb, dyb, dzb = p.xmax - p.xmin, p.ymax - p.ymin, p.zmax - p.zmin
+    psep = dxb / 50.
+    rblob = 0.1
+    rhoblob = 1000. * rhozero
+    psepblob = psep * (rhozero / rhoblob) ** (1. / 3.)
+    rtest = rblob - 2. * p.hfact * psep
+    box = (p.xmin, p.xmax, p.ymin, p.ymax, p.zmin, p.zmax)
+    inner = unifdis_cubic_shell(*box, psepblob, p.hfact, rmax=rtest)
+    shell = unifdis_cubic_shell(*box, psepblob, p.hfact, rmin=rtest, rmax=rblob)
+    medium = unifdis_cubic_shell(*box, psep, p.hfact, rmin=rblob)
+    xyzh = np.concatenate([inner, shell, medium])
+    nparttest, npartblob, npart = len(inner), len(inner) + len(shell), len(xyzh)
+    totvol = dxb * dyb * dzb - 4. / 3. * math.pi * rblob ** 3
+    p.massoftype[IGAS] = rhozero * totvol / (npart - npartblob)
+    part = Particles(p, xyzh)
+    vx, vy, vz, u = test_derivs_fields(xyzh, p)
+    part.vxyzu[:, 0], part.vxyzu[:, 1], part.vxyzu[:, 2] = vx, vy, vz
+    if not isothermal:
+        part.vxyzu[:, 3] = u
+    hblob = p.hfact * (p.massoftype[IGAS] / rhoblob) ** (1. / 3.)
+    return part, nparttest, hblob
 
 
 # ---------------------------------------------------------------------------------------------
