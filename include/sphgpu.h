@@ -73,7 +73,8 @@ typedef struct sphgpu_params {
     double tree_accuracy;                                      /* kdtree.F90:46 */
     double grainsize, graindens, K_code;                       /* dust.f90: grain size / intrinsic density (code units), K_code(1) */
     double seff;                                               /* dust.f90:96-99 init_drag: effective surface density for the mean free path (code units) */
-    double reserved_d[7];
+    double temp_coef_mu;                                       /* eos.f90:194,239,255: temperature_coef*gmw, eos_vars(itemp) = temp_coef_mu * P/rho ; 0 stores 0 */
+    double reserved_d[6];
 } sphgpu_params;
 
 /* module-variable outputs: timestep:dtcourant,dtforce,rhomaxnow ; dens.F90:104-106 statistics */
@@ -178,7 +179,10 @@ int sphgpu_densityiterate(sphgpu_ctx *ctx, int icall, int64_t npart, int64_t nac
 int sphgpu_cons2prim_everything(sphgpu_ctx *ctx, int64_t npart, const double *xyzh, const double *vxyzu,
                                 const float *dvdx, double *eos_vars, const double *Bevol, double *Bxyz,
                                 float *alphaind, const int8_t *iphase);
-/* force(icall,npart,xyzh,vxyzu,fxyzu,divcurlv,divcurlB,Bevol,dBevol,...,fext,...,dt,stressmax,eos_vars,...) */
+/* force(icall,npart,xyzh,vxyzu,fxyzu,divcurlv,divcurlB,Bevol,dBevol,...,fext,...,dt,stressmax,eos_vars,...)  (force.F90:193-196).
+ * Not carried: dustfrac (device-resident between the passes; host copy through sphgpu_host_arrays), fxyz_drag (implicit drag only),
+ * ddustevol/dustprop/dustgasprop/Vrel_disp (one-fluid dust, growth), ipart_rhomax (sink creation), rad/drad/radprop/dens/metrics/apr_level:
+ * all outside the scope of this path (INTEGRATION.md section 4 lists each). */
 int sphgpu_force(sphgpu_ctx *ctx, int icall, int64_t npart, const double *xyzh, const double *vxyzu, double *fxyzu,
                  float *divcurlv, const float *divcurlB, const double *Bevol, double *dBevol, const double *fext,
                  double dt, double stressmax, const double *eos_vars, const float *alphaind, const float *gradh,
@@ -226,6 +230,34 @@ int sphgpu_gravity_gather_pack(sphgpu_ctx *ctx, void **sendptr_device, int *reco
 int sphgpu_gravity_gather_recvbuf(sphgpu_ctx *ctx, int nranks, int64_t stride, void **recvptr_device);
 int sphgpu_gravity_gather_unpack(sphgpu_ctx *ctx, int nranks, int myrank, int64_t stride, const int64_t *counts);
 
+/* ---- the multi-GPU path behind the C ABI (dist.cu): one context per rank / GPU, NCCL over NVLink.  A Fortran host replaces
+ * balancedomains (mpi_balance.F90:82), the MPI cell export (mpi_derivs.F90:197-522) and reduceall_mpi with these calls; it only has
+ * to broadcast the 128-byte NCCL id that rank 0 obtains from sphgpu_dist_get_unique_id (MPI_Bcast, or a file).  NCCL is loaded with
+ * dlopen at sphgpu_dist_init, so a single-GPU user needs none.  Sequence: upload the OWNED particles -> sphgpu_dist_init ->
+ * sphgpu_dist_set_ids -> sphgpu_dist_set_boxes (or sphgpu_dist_rebalance) -> sphgpu_dist_derivs / sphgpu_dist_step ... -> download. */
+int sphgpu_dist_get_unique_id(void *id, int nbytes);                       /* nbytes >= 128 */
+int sphgpu_dist_init(sphgpu_ctx *ctx, const void *id, int nranks, int rank);
+int sphgpu_dist_finalize(sphgpu_ctx *ctx);
+/* boxes = 6 doubles per rank {lo xyz, hi xyz}, tiling the periodic box (or the bounding box of the set) */
+int sphgpu_dist_set_boxes(sphgpu_ctx *ctx, const double *boxes);
+int sphgpu_dist_get_boxes(sphgpu_ctx *ctx, double *boxes);
+/* global identities of the owned particles (they travel with a particle when it migrates); ids == NULL numbers them base, base+1, ... */
+int sphgpu_dist_set_ids(sphgpu_ctx *ctx, const int64_t *ids, int64_t base);
+int sphgpu_dist_get_ids(sphgpu_ctx *ctx, int64_t *ids, int64_t maxn);
+int64_t sphgpu_dist_nlocal(sphgpu_ctx *ctx);
+/* derivs(icall = 1 | 2) on the decomposed set; the scalars are reduced over the ranks (dtcourant, dtforce: min; rhomax: max; counts: sum) */
+int sphgpu_dist_derivs(sphgpu_ctx *ctx, int icall, double dt, sphgpu_scalars *out);
+/* balancedomains: hand every owned particle that left this rank's box to its new owner (whole record); returns the new owned count.
+ * in_step = 1 inside a leapfrog step (the evolved v, B travel too); a caller between steps passes 0 */
+int sphgpu_dist_migrate(sphgpu_ctx *ctx, int in_step, int64_t *nlocal_new);
+/* the reference's domain split (kdtree.F90:2098-2160, applied globally): bisection at the centre of mass along the longest axis,
+ * log2(nranks) levels, moments all-reduced; followed by a migration.  domain = {lo xyz, hi xyz} */
+int sphgpu_dist_rebalance(sphgpu_ctx *ctx, const double *domain, int64_t *nlocal_new);
+/* out8: [0] ghost capacity, [1] ghosts received, [2] bytes sent + received, [3] exchange rounds of the last dist_derivs,
+ * [4] particles handed over by the last migration, [5] largest trial h (halo width = radkern x this x 1.15 + overhang),
+ * [6] device time of the last dist_derivs in ms (CUDA events on the stream that also carries the NCCL transfers), [7] owned particles */
+int sphgpu_dist_stats(sphgpu_ctx *ctx, double *out8);
+
 /* ---- the callers either side of the path, resident on the device -------------------------------- */
 /* step (src/main/step_leapfrog.f90:95-760) with global timesteps and substep_sph (substepping.F90:241-264):
  * predictor, drift, predict_sph (h prediction, alpha decay), derivs(1), corrector iterated with derivs(2) until the velocity
@@ -245,6 +277,11 @@ typedef struct sphgpu_energies {
     int64_t np;
 } sphgpu_energies;
 int sphgpu_energies_resident(sphgpu_ctx *ctx, sphgpu_energies *out);
+/* sphgpu_step_resident on the decomposed set: migration, then the leapfrog step with ghost exchanges inside every derivs and the
+ * velocity-error norm reduced over the ranks */
+int sphgpu_dist_step(sphgpu_ctx *ctx, double dtsph, double tolv, sphgpu_step_out *out);
+/* compute_energies reduced over the ranks */
+int sphgpu_dist_energies(sphgpu_ctx *ctx, sphgpu_energies *out);
 
 /* turbulent driving: st_calcAccel (src/main/forcing.f90:728-830), called by derivs before force when
  * -DDRIVING (deriv.f90:178-182).  The host keeps the Ornstein-Uhlenbeck phases (st_ounoiseupdate / st_calcPhases use the Fortran

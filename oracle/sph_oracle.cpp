@@ -1158,7 +1158,7 @@ int oracle_cons2prim(oracle_ctx *cp, int64_t npart, const double *xyzh, const do
             spsoundi = std::sqrt(ponrhoi);
         }
         double *ev = eos_vars + 7 * i;
-        ev[0] = ponrhoi * rhogas; ev[1] = spsoundi; ev[2] = 0.; ev[6] = p.gamma;   // igasP, ics, itemp (code-unit T not used), igamma
+        ev[0] = ponrhoi * rhogas; ev[1] = spsoundi; ev[2] = p.temp_coef_mu * ponrhoi;   // igasP, ics, itemp (cons2prim.f90:390-392); the other rows are left alone
         if (c.nalpha() >= 2) {
             // xi_limiter (shock_capturing.f90:151-178)
             const float *d = dvdx + 9 * i;

@@ -64,7 +64,8 @@ typedef struct oracle_params {
     /* dust.f90 (two-fluid): grain size/density in code units, K_code */
     double grainsize, graindens, K_code;
     double seff;             /* dust.f90:96-99 (init_drag): effective surface density, code units */
-    double reserved_d[7];
+    double temp_coef_mu;     /* eos.f90:194: temperature_coef*gmw -> eos_vars(itemp) */
+    double reserved_d[6];
 } oracle_params;
 
 /* scalars the reference returns through module variables

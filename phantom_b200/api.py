@@ -36,6 +36,9 @@ EXPORTS = [
     "sphgpu_measure_fp64_peak", "sphgpu_measure_copy_bw", "sphgpu_local_hmax", "sphgpu_halo_select", "sphgpu_halo_pack",
     "sphgpu_halo_recvbuf", "sphgpu_halo_unpack", "sphgpu_nghost", "sphgpu_set_timestep_bins", "sphgpu_get_gravity_timings", "sphgpu_gravity_tree", "sphgpu_step_resident", "sphgpu_energies_resident", "sphgpu_gravity_gather_pack", "sphgpu_gravity_gather_recvbuf",
     "sphgpu_gravity_gather_unpack", "sphgpu_density_hmax_used", "sphgpu_halo_restore_h", "sphgpu_set_forcing_modes", "sphgpu_forcing_resident", "sphgpu_get_copy_bytes", "sphgpu_density_hgrow",
+    "sphgpu_dist_get_unique_id", "sphgpu_dist_init", "sphgpu_dist_finalize", "sphgpu_dist_set_boxes", "sphgpu_dist_get_boxes", "sphgpu_dist_set_ids",
+    "sphgpu_dist_get_ids", "sphgpu_dist_nlocal", "sphgpu_dist_derivs", "sphgpu_dist_migrate", "sphgpu_dist_rebalance", "sphgpu_dist_step",
+    "sphgpu_dist_energies", "sphgpu_dist_stats",
 ]
 
 
@@ -115,6 +118,21 @@ def load_library():
         L.sphgpu_gravity_gather_pack.argtypes = [vp, C.POINTER(vp), C.POINTER(i32)]
         L.sphgpu_gravity_gather_recvbuf.argtypes = [vp, i32, i64, C.POINTER(vp)]
         L.sphgpu_gravity_gather_unpack.argtypes = [vp, i32, i32, i64, vp]
+        L.sphgpu_dist_get_unique_id.argtypes = [vp, i32]
+        L.sphgpu_dist_init.argtypes = [vp, vp, i32, i32]
+        L.sphgpu_dist_finalize.argtypes = [vp]
+        L.sphgpu_dist_set_boxes.argtypes = [vp, vp]
+        L.sphgpu_dist_get_boxes.argtypes = [vp, vp]
+        L.sphgpu_dist_set_ids.argtypes = [vp, vp, i64]
+        L.sphgpu_dist_get_ids.argtypes = [vp, vp, i64]
+        L.sphgpu_dist_nlocal.argtypes = [vp]
+        L.sphgpu_dist_nlocal.restype = i64
+        L.sphgpu_dist_derivs.argtypes = [vp, i32, dbl, C.POINTER(SphScalars)]
+        L.sphgpu_dist_migrate.argtypes = [vp, i32, C.POINTER(i64)]
+        L.sphgpu_dist_rebalance.argtypes = [vp, vp, C.POINTER(i64)]
+        L.sphgpu_dist_step.argtypes = [vp, dbl, dbl, C.POINTER(SphStepOut)]
+        L.sphgpu_dist_energies.argtypes = [vp, C.POINTER(SphEnergies)]
+        L.sphgpu_dist_stats.argtypes = [vp, C.POINTER(dbl)]
         _lib = L
     return _lib
 
@@ -376,6 +394,78 @@ class SphGpu:
 
     def nghost(self):
         return self.L.sphgpu_nghost(self.h)
+
+    # ---- multi-GPU driver behind the C ABI (csrc/dist.cu; halo.DistSph wraps these) ---------------------
+    @staticmethod
+    def dist_unique_id():
+        """128-byte NCCL id (rank 0 calls this and broadcasts it)"""
+        buf = (C.c_ubyte * 128)()
+        rc = load_library().sphgpu_dist_get_unique_id(C.cast(buf, C.c_void_p), 128)
+        if rc != 0:
+            raise SphGpuError(rc, "sphgpu_dist_get_unique_id failed (NCCL not loadable?)")
+        return bytes(buf)
+
+    def dist_init(self, uid, nranks, rank):
+        buf = (C.c_ubyte * 128).from_buffer_copy(uid)
+        self._check(self.L.sphgpu_dist_init(self.h, C.cast(buf, C.c_void_p), int(nranks), int(rank)))
+
+    def dist_finalize(self):
+        self._check(self.L.sphgpu_dist_finalize(self.h))
+
+    def dist_set_boxes(self, boxes):
+        boxes = np.ascontiguousarray(boxes, dtype=np.float64)
+        self._check(self.L.sphgpu_dist_set_boxes(self.h, _p(boxes)))
+
+    def dist_get_boxes(self, nranks):
+        boxes = np.zeros((nranks, 6))
+        self._check(self.L.sphgpu_dist_get_boxes(self.h, _p(boxes)))
+        return boxes
+
+    def dist_set_ids(self, ids=None, base=0):
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+        self._check(self.L.sphgpu_dist_set_ids(self.h, _p(ids), int(base)))
+
+    def dist_get_ids(self):
+        n = self.dist_nlocal()
+        ids = np.zeros(n, dtype=np.int64)
+        self._check(self.L.sphgpu_dist_get_ids(self.h, _p(ids), n))
+        return ids
+
+    def dist_nlocal(self):
+        return int(self.L.sphgpu_dist_nlocal(self.h))
+
+    def dist_derivs(self, icall=1, dt=0.0):
+        sc = SphScalars()
+        self._check(self.L.sphgpu_dist_derivs(self.h, int(icall), float(dt), C.byref(sc)))
+        return sc
+
+    def dist_migrate(self, in_step=False):
+        n = C.c_int64()
+        self._check(self.L.sphgpu_dist_migrate(self.h, int(in_step), C.byref(n)))
+        return n.value
+
+    def dist_rebalance(self, domain):
+        domain = np.ascontiguousarray(domain, dtype=np.float64)
+        n = C.c_int64()
+        self._check(self.L.sphgpu_dist_rebalance(self.h, _p(domain), C.byref(n)))
+        return n.value
+
+    def dist_step(self, dtsph, tolv=1.e-2):
+        out = SphStepOut()
+        self._check(self.L.sphgpu_dist_step(self.h, float(dtsph), float(tolv), C.byref(out)))
+        return out
+
+    def dist_energies(self):
+        out = SphEnergies()
+        self._check(self.L.sphgpu_dist_energies(self.h, C.byref(out)))
+        return out
+
+    def dist_stats(self):
+        t = (C.c_double * 8)()
+        self._check(self.L.sphgpu_dist_stats(self.h, t))
+        return dict(ghost_capacity=int(t[0]), nghost=int(t[1]), halo_bytes=int(t[2]), rounds=int(t[3]), migrated=int(t[4]), hmax_used=t[5], ms=t[6],
+                    nlocal=int(t[7]))
 
     def measure_fp64_peak(self):
         return self.L.sphgpu_measure_fp64_peak(self.h)

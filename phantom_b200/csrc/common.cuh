@@ -178,6 +178,9 @@ struct sphgpu_ctx {
     DevBuf<int> halo_sendidx;
     DevBuf<unsigned long long> halo_cnt;
     DevBuf<double> halo_boxes, halo_sendbuf, halo_recvbuf;
+    // ---- multi-GPU driver behind the C ABI (dist.cu): NCCL communicator, domain boxes, exchange blocks; global particle ids
+    struct DistState *dist = nullptr;
+    DevBuf<long long> gid;
 };
 
 #define CUDA_TRY(ctx, call)                                                                           \
@@ -286,3 +289,5 @@ int64_t gravity_tree_dump(sphgpu_ctx *c, int64_t maxnodes, double *rec12, int32_
 int64_t neighbour_sets_run(sphgpu_ctx *c, int symmetric, int64_t *offsets, int32_t *list, int64_t maxlist);
 KernConsts make_kern_consts(int kernel);
 int ensure_all_keep(sphgpu_ctx *c, int64_t n, int64_t keep);
+int sphgpu_dist_hook_derivs(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out);
+int sphgpu_dist_hook_reduce_err(sphgpu_ctx *c, double *red3);

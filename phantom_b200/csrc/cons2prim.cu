@@ -37,7 +37,7 @@ __global__ void k_cons2prim(int64_t n, const double *__restrict__ xyzh, const do
         spsoundi = sqrt(ponrhoi);
     }
     double *ev = eos_vars + 7 * (size_t)i;
-    ev[0] = ponrhoi * rhogas; ev[1] = spsoundi; ev[2] = 0.; ev[6] = p.gamma;
+    ev[0] = ponrhoi * rhogas; ev[1] = spsoundi; ev[2] = p.temp_coef_mu * ponrhoi;   // igasP, ics, itemp (cons2prim.f90:390-392); imu, iX, iZ, igamma are not touched
     if (dp.nalpha >= 2) {
         const float *d = dvdx + 9 * (size_t)i;
         const double dvxdx = d[0], dvxdy = d[1], dvxdz = d[2], dvydx = d[3], dvydy = d[4], dvydz = d[5], dvzdx = d[6], dvzdy = d[7], dvzdz = d[8];

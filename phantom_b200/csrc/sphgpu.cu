@@ -119,6 +119,8 @@ void sphgpu_destroy(sphgpu_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    sphgpu_dist_finalize(c);
+    c->gid.release();
     c->xyzh.release(); c->vxyzu.release(); c->fxyzu.release(); c->fext.release(); c->Bevol.release(); c->dBevol.release(); c->eos_vars.release(); c->Bxyz.release();
     c->divcurlv.release(); c->divcurlB.release(); c->alphaind.release(); c->gradh.release(); c->dvdx.release(); c->poten.release(); c->divBsymm.release();
     c->iphase.release(); c->ibin.release(); c->ibin_old.release(); c->ibin_wake.release();
@@ -435,15 +437,23 @@ int sphgpu_derivs(sphgpu_ctx *c, int icall, sphgpu_host_arrays *h, double dt, sp
     H2D(c->vxyzu, h->vxyzu, (size_t)nvu * n); H2D(c->fxyzu, h->fxyzu, (size_t)nvu * n); H2D(c->fext, h->fext, 3 * n); H2D(c->alphaind, h->alphaind, 3 * n);
     if (p.mhd) { H2D(c->Bevol, h->Bevol, 4 * n); }
     if (p.ind_timesteps) { H2D(c->ibin, h->ibin, n); H2D(c->ibin_old, h->ibin_old, n); H2D(c->ibin_wake, h->ibin_wake, n); }
-    if (!all_active) {
-        H2D(c->gradh, h->gradh, (size_t)ng * n); H2D(c->divcurlv, h->divcurlv, n); H2D(c->dvdx, h->dvdx, 9 * n); H2D(c->eos_vars, h->eos_vars, 7 * n);
+    // eos_vars always travels: cons2prim writes the rows igasP, ics, itemp only, the host's imu, iX, iZ, igamma must survive the download
+    H2D(c->eos_vars, h->eos_vars, 7 * n);
+    auto upload_stored = [&]() -> int {      // arrays that keep their stored values for particles no pass writes
+        H2D(c->gradh, h->gradh, (size_t)ng * n); H2D(c->divcurlv, h->divcurlv, n); H2D(c->dvdx, h->dvdx, 9 * n);
         if (p.mhd) H2D(c->divcurlB, h->divcurlB, 4 * n);
-    }
+        return SPHGPU_OK;
+    };
+    if (!all_active) TRY(upload_stored());
     CUDA_TRY(c, cudaEventRecord(c->cev[1], si));
     // ---- passes
     cudaEventRecord(c->ev[0], c->stream);
     CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->cev[0], 0));
     if (icall == 1 || icall == 0) TRY(tree_build(c));
+    if (all_active && c->nlive < n) {        // dead / accreted particles (h <= 0) among "all gas": their stored values must survive too
+        TRY(upload_stored());
+        CUDA_TRY(c, cudaEventRecord(c->cev[1], si));
+    }
     cudaEventRecord(c->ev[1], c->stream);
     CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->cev[1], 0));
     if (icall == 1) {

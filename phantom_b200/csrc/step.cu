@@ -250,7 +250,9 @@ int sphgpu_step_resident(sphgpu_ctx *c, double dtsph, double tolv, sphgpu_step_o
     CUDA_TRY(c, cudaSetDevice(c->device));
     const sphgpu_params &p = c->hp.p;
     if (p.ind_timesteps) { c->err = "step: individual timesteps are integrated by the host (sphgpu_derivs); this routine is the global-timestep leapfrog"; return SPHGPU_ERR_ARG; }
-    const int64_t n = c->npart;
+    // a decomposed set (dist.cu) integrates its owned particles; the ghosts behind them are refreshed inside every derivs
+    if (c->nghost > 0 && !c->dist) { c->err = "step: the context holds ghost particles of a host-driven halo exchange; use sphgpu_dist_step"; return SPHGPU_ERR_STATE; }
+    const int64_t n = c->dist ? c->nlocal : c->npart;
     const int nvu = c->hp.nvu;
     if (n <= 0) return SPHGPU_ERR_STATE;
     cudaStream_t st = c->stream;
@@ -261,16 +263,24 @@ int sphgpu_step_resident(sphgpu_ctx *c, double dtsph, double tolv, sphgpu_step_o
     if (p.mhd) CUDA_TRY(c, cudaMemcpyAsync(c->B_true.p, c->Bevol.p, sizeof(double) * 4 * n, cudaMemcpyDeviceToDevice, st));
     StepArgs a; memset(&a, 0, sizeof a);
     a.n = n; a.nvu = nvu; a.mhd = p.mhd; a.nalpha = c->hp.nalpha; a.multitype = 1;
-    a.xyzh = c->xyzh.p; a.v = c->v_true.p; a.vpred = c->vxyzu.p; a.f = c->fxyzu.p; a.B = c->B_true.p; a.Bpred = c->Bevol.p; a.dB = c->dBevol.p;
-    a.eos_vars = c->eos_vars.p; a.divcurlv = c->divcurlv.p; a.alphaind = c->alphaind.p; a.iphase = c->iphase.p;
-    a.hfact = p.hfact; a.dt = dtsph; a.hdt = 0.5 * dtsph; a.red = c->dscal.p + 16;
+    a.hfact = p.hfact; a.dt = dtsph; a.hdt = 0.5 * dtsph;
     for (int k = 0; k < SPHGPU_MAXTYPES; k++) a.massoftype[k] = p.massoftype[k];
+    auto bind = [&]() {        // the canonical arrays may be reallocated when a derivs call appends more ghosts
+        a.xyzh = c->xyzh.p; a.v = c->v_true.p; a.vpred = c->vxyzu.p; a.f = c->fxyzu.p; a.B = c->B_true.p; a.Bpred = c->Bevol.p; a.dB = c->dBevol.p;
+        a.eos_vars = c->eos_vars.p; a.divcurlv = c->divcurlv.p; a.alphaind = c->alphaind.p; a.iphase = c->iphase.p; a.red = c->dscal.p + 16;
+    };
+    auto derivs = [&](int icall, sphgpu_scalars *sc) -> int {
+        const int r = c->dist ? sphgpu_dist_hook_derivs(c, icall, dtsph, sc) : sphgpu_derivs_resident(c, icall, dtsph, sc);
+        bind();
+        return r;
+    };
+    bind();
     SL(c, k_predict, a);
     SL(c, k_drift, a);
     SL(c, k_predict_sph, a);
     c->tree_valid = false;
     sphgpu_scalars sc;
-    TRY(sphgpu_derivs_resident(c, 1, dtsph, &sc));
+    TRY(derivs(1, &sc));
     int its = 0; bool converged = false;
     double errmax = 0., dterr = 1.e29;
     while (its < 30 && !converged) {                                  // step_leapfrog.f90:441-759
@@ -280,6 +290,7 @@ int sphgpu_step_resident(sphgpu_ctx *c, double dtsph, double tolv, sphgpu_step_o
         double red[3];
         CUDA_TRY(c, cudaMemcpyAsync(red, a.red, sizeof red, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
+        if (c->dist) TRY(sphgpu_dist_hook_reduce_err(c, red));        // reduceall_mpi of errmax, v2mean, np (step_leapfrog.f90:790-792)
         // check_velocity_error (step_leapfrog.f90:769-843)
         const double v2mean = red[2] > 0. ? red[1] / red[2] : 0.;
         errmax = v2mean > DBL_MIN ? red[0] / sqrt(v2mean) : 0.;
@@ -292,7 +303,7 @@ int sphgpu_step_resident(sphgpu_ctx *c, double dtsph, double tolv, sphgpu_step_o
         } else converged = true;
         if (!converged) {
             SL(c, k_unconverged, a);
-            TRY(sphgpu_derivs_resident(c, 2, dtsph, &sc));
+            TRY(derivs(2, &sc));
         }
     }
     CUDA_TRY(c, cudaMemcpyAsync(c->vxyzu.p, c->v_true.p, sizeof(double) * nvu * n, cudaMemcpyDeviceToDevice, st));

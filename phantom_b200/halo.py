@@ -229,3 +229,50 @@ class DistributedSph:
             print("halo timing (ms): " + " ".join(f"{n}={1e3 * (t - marks[k][1]):.3f}" for k, (n, t) in enumerate(marks[1:])) +
                   f" total={1e3 * (marks[-1][1] - marks[0][1]):.3f} nghost={self.nghost}", flush=True)
         return sf
+
+
+class DistSph:
+    """The decomposed particle set behind the C ABI (csrc/dist.cu): selection, packing, the NCCL exchanges, the migration of particles
+    that leave their box and the reductions all run inside the library; this class only bootstraps the communicator (the 128-byte NCCL
+    id travels over the existing torch.distributed group -- a Fortran host would MPI_Bcast it) and keeps the host-side slices."""
+
+    def __init__(self, gpu, rank, world, boxes=None, domain=None, ids=None):
+        import torch
+        import torch.distributed as dist
+        self.g, self.rank, self.world = gpu, rank, world
+        uid = [gpu.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        gpu.dist_init(uid[0], world, rank)
+        if ids is not None:
+            gpu.dist_set_ids(ids)
+        else:
+            n = torch.tensor([gpu.npart_uploaded], dtype=torch.int64, device="cuda")
+            alln = [torch.zeros_like(n) for _ in range(world)]
+            dist.all_gather(alln, n)
+            gpu.dist_set_ids(None, base=int(sum(int(a) for a in alln[:rank])))
+        if boxes is not None:
+            gpu.dist_set_boxes(boxes)
+        else:
+            gpu.dist_rebalance(domain)
+        self.halo_bytes, self.nghost = 0, 0
+
+    def derivs(self, icall=1, dt=0.0):
+        sc = self.g.dist_derivs(icall, dt)
+        st = self.g.dist_stats()
+        self.halo_bytes, self.nghost, self.halo_rounds, self.ms = st["halo_bytes"], st["nghost"], st["rounds"], st["ms"]
+        return sc
+
+    def step(self, dt, tolv=1.e-2):
+        return self.g.dist_step(dt, tolv)
+
+    def energies(self):
+        return self.g.dist_energies()
+
+    def download_owned(self, params, fields=("xyzh", "vxyzu", "fxyzu")):
+        """host copies of the owned particles' arrays and their global ids (the owned set changes as particles migrate)"""
+        from .setups import Particles
+        from . import api
+        n = self.g.dist_nlocal()
+        part = Particles(params, np.zeros((n, 4)))
+        self.g.download(part, api.F_ALL)
+        return part, self.g.dist_get_ids()

@@ -32,8 +32,8 @@ class SphParams(C.Structure):
         ("psidecayfac", C.c_double), ("overcleanfac", C.c_double),
         ("tree_accuracy", C.c_double),
         ("grainsize", C.c_double), ("graindens", C.c_double), ("K_code", C.c_double),
-        ("seff", C.c_double),
-        ("reserved_d", C.c_double * 7),
+        ("seff", C.c_double), ("temp_coef_mu", C.c_double),
+        ("reserved_d", C.c_double * 6),
     ]
 
     @property

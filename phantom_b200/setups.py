@@ -332,6 +332,7 @@ def _solenoidal_field(xyzh, box, seed, mach, cs, kmin=1, kmax=3):
     xmin, L = box
     x = (xyzh[:, :3] - xmin) / L
     v = np.zeros((len(xyzh), 3))
+    modes = []
     for kx in range(-kmax, kmax + 1):
         for ky in range(-kmax, kmax + 1):
             for kz in range(0, kmax + 1):
@@ -343,8 +344,22 @@ def _solenoidal_field(xyzh, box, seed, mach, cs, kmin=1, kmax=3):
                 b = rng.normal(size=3) * k2 ** (-1.0)
                 a -= kv * (a @ kv) / k2          # project out the compressive part
                 b -= kv * (b @ kv) / k2
-                ph = 2. * math.pi * (x @ kv)
-                v += np.outer(np.cos(ph), a) + np.outer(np.sin(ph), b)
+                modes.append((kv, a, b))
+
+    def fill(lo, hi):                            # the same operations per particle, whatever the chunking: results do not depend on it
+        xc, vc = x[lo:hi], v[lo:hi]
+        for kv, a, b in modes:
+            ph = 2. * math.pi * (xc @ kv)
+            vc += np.outer(np.cos(ph), a) + np.outer(np.sin(ph), b)
+    n = len(xyzh)
+    chunk = 1 << 17
+    if n <= chunk:
+        fill(0, n)
+    else:                                        # numpy releases the GIL inside the ufuncs: threads over particle chunks
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 8)) as ex:
+            list(ex.map(lambda lo: fill(lo, min(lo + chunk, n)), range(0, n, chunk)))
     vrms = math.sqrt(np.mean(np.sum(v * v, axis=1)))
     return v * (mach * cs / vrms)
 

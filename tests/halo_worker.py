@@ -17,6 +17,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def global_problem(nx, mhd=False):
     from phantom_b200 import setups
+    if nx < 0:              # turbulent box of (-nx)^3 particles (C2): the stepping test
+        part = setups.setup_turb(nx=-nx)
+        part.alphaind[:, 0] = 1.0
+        return part
     if nx >= 1000:          # self-gravitating sphere of nx particles (C5): exercises the gathered gravity set
         part = setups.setup_random_sphere(n=nx)
         rng = setups.Ran2(-97531)
@@ -53,17 +57,42 @@ def main():
     mine = np.nonzero(owner == rank)[0]
     loc = take(part, mine)
 
-    if backend == "nccl":
+    if backend.startswith("nccl"):
+        # the product path: everything behind the C ABI (csrc/dist.cu); only the NCCL id travels over torch.distributed
         torch.cuda.set_device(rank % torch.cuda.device_count())
         dist.init_process_group("nccl", device_id=torch.device("cuda", rank % torch.cuda.device_count()))
         from phantom_b200.api import SphGpu
         g = SphGpu(loc.params.copy(), device=rank % torch.cuda.device_count())
         g.upload(loc)
-        d = halo.DistributedSph(g, boxes, rank, world)
-        sc = d.derivs(1)
-        g.download(loc)
-        np.savez(os.path.join(outdir, f"rank{rank}.npz"), idx=mine, xyzh=loc.xyzh, fxyzu=loc.fxyzu, gradh=loc.gradh, divcurlv=loc.divcurlv,
-                 dtcourant=sc.dtcourant, dtforce=sc.dtforce, nghost=d.nghost, poten=loc.poten)
+        domain = [p.xmin, p.ymin, p.zmin, p.xmax, p.ymax, p.zmax]
+        if backend == "nccl_rebalance":       # boxes from the library's own bisection; the particles start on the WRONG ranks (round robin)
+            mine = np.arange(rank, part.npart, world)
+            loc = take(part, mine)
+            g.upload(loc)
+            d = halo.DistSph(g, rank, world, domain=domain, ids=mine)
+        else:
+            d = halo.DistSph(g, rank, world, boxes=boxes, ids=mine)
+        if backend == "nccl_step":
+            nsteps = int(sys.argv[4])
+            sc = d.derivs(1)
+            dt = min(sc.dtcourant, sc.dtforce)
+            hist, migrated = [], 0
+            for it in range(nsteps):
+                out = d.step(dt)
+                migrated += g.dist_stats()["migrated"]
+                e = d.energies()
+                hist.append([dt, out.its, e.ekin, e.etherm, e.emag, e.epot, e.etot, e.xmom, e.ymom, e.zmom, e.mtot, float(e.np)])
+                dt = min(out.dtcourant, out.dtforce, out.dterr)
+            own, ids = d.download_owned(loc.params)
+            np.savez(os.path.join(outdir, f"rank{rank}.npz"), idx=ids, xyzh=own.xyzh, vxyzu=own.vxyzu, hist=np.array(hist), migrated=migrated,
+                     nghost=d.nghost)
+        else:
+            sc = d.derivs(1)
+            own, ids = d.download_owned(loc.params)
+            np.savez(os.path.join(outdir, f"rank{rank}.npz"), idx=ids, xyzh=own.xyzh, fxyzu=own.fxyzu, gradh=own.gradh, divcurlv=own.divcurlv,
+                     dtcourant=sc.dtcourant, dtforce=sc.dtforce, nghost=d.nghost, poten=own.poten, nactualtot=sc.nactualtot, npairs_force=sc.npairs_force,
+                     boxes=g.dist_get_boxes(world))
+        g.dist_finalize()
         dist.destroy_process_group()
         return
 

@@ -11,10 +11,10 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def launch(backend, world, nx, outdir, port):
+def launch(backend, world, nx, outdir, port, *extra):
     env = dict(os.environ, OMP_NUM_THREADS="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tests", "halo_worker.py"), backend, str(nx), outdir]
+           "--master-port", str(port), os.path.join(ROOT, "tests", "halo_worker.py"), backend, str(nx), outdir] + [str(e) for e in extra]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
 
