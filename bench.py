@@ -357,13 +357,15 @@ def main():
     # ---------------- roofline of the dominant pair kernels ----------------
     fc = flop_constants()
     iso = bool(part.params.isothermal)
-    f_dens = fc["FLOP_DENS_PAIR_HYDRO"] * sc.npairs_density + fc["FLOP_DENS_EPILOGUE"] * sc.nrhocalc
-    f_force = (fc["FLOP_FORCE_PAIR_ISOTHERMAL"] if iso else fc["FLOP_FORCE_PAIR_ADIABATIC"]) * sc.npairs_force + fc["FLOP_FORCE_EPILOGUE"] * n
+    # N > 1: the scalars are sums over the ranks, the kernel times are per GPU: the roofline is that of ONE GPU's launch
+    npd, npf, nrc = sc.npairs_density / world, sc.npairs_force / world, sc.nrhocalc / world
+    f_dens = fc["FLOP_DENS_PAIR_HYDRO"] * npd + fc["FLOP_DENS_EPILOGUE"] * nrc
+    f_force = (fc["FLOP_FORCE_PAIR_ISOTHERMAL"] if iso else fc["FLOP_FORCE_PAIR_ADIABATIC"]) * npf + fc["FLOP_FORCE_EPILOGUE"] * n
     ms_d, ms_f = kern["density"] / args.steps, kern["force"] / args.steps
     passes = {
-        "density": {"flops_per_launch": f_dens, "ms": ms_d, "achieved_tflops": f_dens / (ms_d * 1e-3) / 1e12, "pairs": sc.npairs_density,
+        "density": {"flops_per_launch": f_dens, "ms": ms_d, "achieved_tflops": f_dens / (ms_d * 1e-3) / 1e12, "pairs": int(npd),
                     "its_mean": sc.nrhocalc / max(sc.np, 1)},
-        "force": {"flops_per_launch": f_force, "ms": ms_f, "achieved_tflops": f_force / (ms_f * 1e-3) / 1e12, "pairs": sc.npairs_force},
+        "force": {"flops_per_launch": f_force, "ms": ms_f, "achieved_tflops": f_force / (ms_f * 1e-3) / 1e12, "pairs": int(npf)},
     }
     for v in passes.values():
         v["frac_fp64"] = v["achieved_tflops"] / fp64_peak

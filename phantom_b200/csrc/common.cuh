@@ -217,7 +217,10 @@ __device__ __forceinline__ void get_partinfo_d(int8_t iphasei, int set_boundarie
     isgas = (itype == IGAS || itype == IBOUNDARY);
     isdust = use_dust ? (itype == IDUST) : false;
     if (itype == IBOUNDARY) {
-        if (set_boundaries_to_active) { isactive = true; itype = IGAS; }
+        // part.F90:1052-1060 activates every boundary particle while set_boundaries_to_active holds (the first density pass of a run, when
+        // all particles are active anyway).  One handed over with the inactive flag set stays inactive here: that is how the ghost copies
+        // of the multi-GPU halo arrive, and a ghost must never become a target.
+        if (set_boundaries_to_active && iphasei > 0) { isactive = true; itype = IGAS; }
         else isactive = false;
     }
 }

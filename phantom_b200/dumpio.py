@@ -95,24 +95,38 @@ def read_dump(path):
             for t, v in seen.items():
                 header[t] = v[0] if len(v) == 1 else np.array(v)       # repeated tags = arrays (npartoftype, massoftype, ...)
         nblockarrays, = struct.unpack("<i", _read_record(f))
-        nblocks = int(header.get("nblocks", 1))
-        heads = []
-        for _ in range(nblockarrays):
-            rec = _read_record(f)
-            number, = struct.unpack("<q", rec[:8])
-            nums = struct.unpack("<8i", rec[8:40])
-            heads.append((number, nums))
+        nblocks = max(int(header.get("nblocks", 1)), 1)
+        if nblockarrays % nblocks:
+            raise DumpFormatError("number of array lengths %d is not a multiple of nblocks %d" % (nblockarrays, nblocks))
+        narraylengths = nblockarrays // nblocks                          # readwrite_dumps.f90:579
+        # MPI dumps repeat {narraylengths block headers, then that block's arrays} once per process (:600-665); the pieces of one
+        # array length are concatenated in block order
+        per_block = []
+        for _ in range(nblocks):
+            heads = []
+            for _ in range(narraylengths):
+                rec = _read_record(f)
+                number, = struct.unpack("<q", rec[:8])
+                nums = struct.unpack("<8i", rec[8:40])
+                heads.append((number, nums))
+            parts = []
+            for number, nums in heads:
+                arrays = {}
+                for k in range(8):
+                    for _ in range(nums[k]):
+                        tag = _tags(_read_record(f))[0]
+                        arr = np.frombuffer(_read_record(f), dtype=dts[k]).copy()
+                        while tag in arrays:                               # repeated tags (e.g. several dust species): suffix them
+                            tag += "_"
+                        arrays[tag] = arr
+                parts.append(arrays)
+            per_block.append(parts)
         blocks = []
-        for number, nums in heads:
-            arrays = {}
-            for k in range(8):
-                for _ in range(nums[k]):
-                    tag = _tags(_read_record(f))[0]
-                    arr = np.frombuffer(_read_record(f), dtype=dts[k]).copy()
-                    while tag in arrays:                                   # repeated tags (e.g. several dust species): suffix them
-                        tag += "_"
-                    arrays[tag] = arr
-            blocks.append(arrays)
+        for k in range(narraylengths):
+            merged = {}
+            for tag in per_block[0][k]:
+                merged[tag] = per_block[0][k][tag] if nblocks == 1 else np.concatenate([pb[k][tag] for pb in per_block if tag in pb[k]])
+            blocks.append(merged)
     return dict(fileid=fileid, realsize=realsize, iversion=iversion, header=header, blocks=blocks, nblocks=nblocks)
 
 
@@ -146,8 +160,9 @@ def particles_from_dump(d, params):
     return part
 
 
-def write_dump(path, part, time=0.0, extra_header=None, small=False):
-    """write a full dump of the particle set in the layout of write_fulldump (readwrite_dumps.f90:85-330), default real = 8 bytes"""
+def write_dump(path, part, time=0.0, extra_header=None, small=False, nblocks=1):
+    """write a full dump of the particle set in the layout of write_fulldump (readwrite_dumps.f90:85-330), default real = 8 bytes.
+    nblocks > 1 writes it the way an MPI run of nblocks processes does: every process its block headers and arrays in turn (:170-172)"""
     p = part.params
     n = part.npart
     mhd = bool(p.mhd)
@@ -160,7 +175,7 @@ def write_dump(path, part, time=0.0, extra_header=None, small=False):
     def add(k, tag, vals):
         for v in np.atleast_1d(vals):
             hdr[k].append((tag, v))
-    add(I_INT, "nparttot", n); add(I_INT, "ntypes", ntypes); add(I_INT, "npartoftype", npartoftype); add(I_INT, "nblocks", 1)
+    add(I_INT, "nparttot", n); add(I_INT, "ntypes", ntypes); add(I_INT, "npartoftype", npartoftype); add(I_INT, "nblocks", nblocks)
     add(I_INT, "nptmass", 0); add(I_INT, "ndustlarge", 1 if npartoftype[6] else 0); add(I_INT, "ndustsmall", 0); add(I_INT, "idust", 7)
     add(I_INT, "majorv", 2026); add(I_INT, "minorv", 0); add(I_INT, "microv", 1)
     add(I_INT8, "nparttot", n); add(I_INT8, "ntypes", ntypes); add(I_INT8, "npartoftype", npartoftype)
@@ -210,12 +225,15 @@ def write_dump(path, part, time=0.0, extra_header=None, small=False):
             if hdr[k]:
                 _write_record(f, b"".join(_tag(t) for t, _ in hdr[k]))
                 _write_record(f, np.array([v for _, v in hdr[k]], dtype=dts[k]).tobytes())
-        _write_record(f, struct.pack("<i", len(blocks)))
-        for number, arrs in blocks:
-            _write_record(f, struct.pack("<q8i", number, *[len(a) for a in arrs]))
-        for number, arrs in blocks:
-            for k in range(8):
-                for tag, a in arrs[k]:
-                    _write_record(f, _tag(tag))
-                    _write_record(f, np.ascontiguousarray(a, dtype=dts[k]).tobytes())
+        _write_record(f, struct.pack("<i", len(blocks) * nblocks))
+        edges = [n * b // nblocks for b in range(nblocks + 1)]
+        for b in range(nblocks):
+            lo, hi = edges[b], edges[b + 1]
+            for number, arrs in blocks:
+                _write_record(f, struct.pack("<q8i", (hi - lo) if number else 0, *[len(a) for a in arrs]))
+            for number, arrs in blocks:
+                for k in range(8):
+                    for tag, a in arrs[k]:
+                        _write_record(f, _tag(tag))
+                        _write_record(f, np.ascontiguousarray(a[lo:hi], dtype=dts[k]).tobytes())
     return fileid

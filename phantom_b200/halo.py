@@ -13,9 +13,10 @@ for this path:
   reduceall_mpi('min'|'max')  src/main/force.F90:848-852, src/main/dens.F90:546-549
       -> one packed all_reduce for dtcourant / dtforce / rhomax.
 
-The selection, packing and unpacking run on the device (phantom_b200/csrc/halo.cu); the exchange is an all-to-all-v
-(`all_to_all_single`) issued directly on the library's device buffers.  With the gloo backend (CPU tests) the same
-host logic runs against numpy restatements of the device kernels.
+The product path is `DistSph` below: selection, packing, the grouped NCCL transfers, unpacking, the migration of particles that
+leave their box and the reductions all run inside the library (phantom_b200/csrc/dist.cu, `sphgpu_dist_*` of include/sphgpu.h).
+The numpy functions of this module restate the device kernels' rules (bisection, ownership, ghost selection) for the gloo tests,
+which run the same protocol on CPU with the oracle as the compute stand-in.
 """
 import math
 import numpy as np
@@ -95,140 +96,6 @@ def gather_padded(dist, torch, records):
     dist.all_gather(recv, padded)
     glob = np.concatenate([recv[r].numpy().reshape(stride, w)[: counts[r]] for r in range(world)])
     return glob, counts, int(counts[:rank].sum())
-
-
-class _DevArray:
-    """zero-copy view of a library-owned device buffer for torch (CUDA array interface)"""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
-
-
-class DistributedSph:
-    """derivs on a domain-decomposed particle set: one instance per rank, SphGpu context underneath."""
-
-    def __init__(self, gpu, boxes, rank, world, margin=1.15):
-        import torch
-        import torch.distributed as dist
-        self.torch, self.dist = torch, dist
-        self.g = gpu
-        self.boxes = np.ascontiguousarray(boxes, dtype=np.float64)
-        self.rank, self.world = rank, world
-        self.margin = margin
-        self.radkern = RADKERN[gpu.params.kernel]
-        self.halo_bytes = 0
-        self.nghost = 0
-        self.nlocal = 0
-        self._hu_prev = None
-        # the context's compute stream becomes a blocking stream: implicitly ordered with the legacy default stream that torch and its
-        # NCCL collectives work against, so pack -> all-to-all -> unpack needs no host synchronisation
-        self.sync_free = False
-        if torch.cuda.is_available() and torch.cuda.current_stream().cuda_stream == 0:
-            gpu.set_option("legacy_stream", 1)
-            self.sync_free = True
-
-    def _alltoall(self, sendptr, rd, sendcounts, recvcounts, stage):
-        torch, dist = self.torch, self.dist
-        ntot_s, ntot_r = int(sendcounts.sum()), int(recvcounts.sum())
-        recvptr = self.g.halo_recvbuf(ntot_r, rd)
-        send = torch.as_tensor(_DevArray(sendptr, max(ntot_s, 1) * rd), device="cuda")[: ntot_s * rd]
-        recv = torch.as_tensor(_DevArray(recvptr, max(ntot_r, 1) * rd), device="cuda")[: ntot_r * rd]
-        dist.all_to_all_single(recv, send, [int(c) * rd for c in recvcounts], [int(c) * rd for c in sendcounts])
-        if not self.sync_free:
-            torch.cuda.synchronize()
-        self.halo_bytes += 8 * rd * (ntot_s + ntot_r)
-        return ntot_r
-
-    def _gather_gravity_set(self):
-        """all-gather of the owned particles' positions and h history: the input of the self-gravity pass (see include/sphgpu.h)"""
-        torch, dist = self.torch, self.dist
-        g = self.g
-        nloc = torch.tensor([self.nlocal], dtype=torch.int64, device="cuda")
-        allc = torch.empty(self.world, dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(allc, nloc)
-        counts = allc.cpu().numpy()
-        stride = int(counts.max())
-        sendptr, rd = g.gravity_gather_pack()
-        recvptr = g.gravity_gather_recvbuf(self.world, stride)
-        send = torch.as_tensor(_DevArray(sendptr, max(self.nlocal, 1) * rd), device="cuda")[: self.nlocal * rd]
-        recv = torch.as_tensor(_DevArray(recvptr, self.world * stride * rd), device="cuda")
-        padded = torch.zeros(stride * rd, dtype=torch.float64, device="cuda")
-        padded[: self.nlocal * rd] = send
-        dist.all_gather_into_tensor(recv, padded)
-        torch.cuda.synchronize()
-        self.halo_bytes += 8 * rd * stride * self.world
-        g.gravity_gather_unpack(self.world, self.rank, stride, counts)
-
-    def derivs(self, icall=1, dt=0.0):
-        """tree + density + cons2prim + force with the two ghost exchanges; returns the reduced scalars"""
-        torch, dist = self.torch, self.dist
-        g = self.g
-        self.halo_bytes = 0
-        self.nlocal = int(g.npart_uploaded)
-        import os, time
-        timing = os.environ.get("SPHGPU_HALO_TIMING") and self.rank == 0
-        marks = []
-
-        def mark(name):
-            if timing:
-                torch.cuda.synchronize()
-                marks.append((name, time.perf_counter()))
-        mark("start")
-        # halo width from the global hmax: one tiny all_reduce on the first call; afterwards the largest trial h of the previous
-        # density pass (already reduced) -- the widening check below keeps this safe when h grows between steps
-        if self._hu_prev is None:
-            hm = torch.tensor([g.local_hmax()], dtype=torch.float64, device="cuda")
-            dist.all_reduce(hm, op=dist.ReduceOp.MAX)
-            self._hu_prev = float(hm[0])
-        dhalo = self.radkern * self._hu_prev * self.margin
-        self.halo_rounds = 0
-        while True:
-            self.halo_rounds += 1
-            sendcounts = g.halo_select(self.world, self.rank, self.boxes, dhalo)
-            sc = torch.from_numpy(sendcounts).cuda()
-            rc = torch.empty_like(sc)
-            dist.all_to_all_single(rc, sc)
-            recvcounts = rc.cpu().numpy()
-            ptr, rd = g.halo_pack(1)
-            self.nghost = self._alltoall(ptr, rd, sendcounts, recvcounts, 1)
-            g.halo_unpack(1, self.nghost)
-            mark("halo1")
-            g.build_tree_resident()
-            mark("tree")
-            sd = g.densityiterate_resident(1)
-            mark("density")
-            # widening round (the reference re-exports a cell whenever its h outgrows the search radius, dens.F90:343-365): if any
-            # particle anywhere iterated with 2h beyond the halo the ghosts were selected with, restore h and repeat with a wider halo
-            hu = torch.tensor([g.density_hmax_used(), g.density_hgrow()], dtype=torch.float64, device="cuda")
-            dist.all_reduce(hu, op=dist.ReduceOp.MAX)
-            hu = hu.cpu().numpy()
-            self._hu_prev = float(hu[0])
-            if self.radkern * float(hu[0]) <= dhalo or self.halo_rounds >= 8:
-                break
-            dhalo = self.radkern * float(hu[0]) * self.margin
-            g.halo_restore_h()
-        g.set_option("halo_hgrow", float(hu[1]))
-        g.params.set_boundaries_to_active = 0
-        ptr, rd = g.halo_pack(2)
-        self._alltoall(ptr, rd, sendcounts, recvcounts, 2)
-        g.halo_unpack(2, self.nghost)
-        mark("halo2")
-        g.cons2prim_resident()
-        if g.params.gravity:
-            self._gather_gravity_set()
-        sf = g.force_resident(icall, dt)
-        mark("c2p+force")
-        red = torch.tensor([sf.dtcourant, sf.dtforce, -sd.rhomax], dtype=torch.float64, device="cuda")
-        dist.all_reduce(red, op=dist.ReduceOp.MIN)
-        red = red.cpu().numpy()                      # one device-to-host read for the three scalars
-        sf.dtcourant, sf.dtforce, sf.rhomax = float(red[0]), float(red[1]), -float(red[2])
-        sf.np, sf.nrhocalc, sf.npairs_density = sd.np, sd.nrhocalc, sd.npairs_density
-        sf.actualmean, sf.maxactual, sf.trialmean, sf.nactualtot = sd.actualmean, sd.maxactual, sd.trialmean, sd.nactualtot
-        mark("reduce")
-        if timing:
-            print("halo timing (ms): " + " ".join(f"{n}={1e3 * (t - marks[k][1]):.3f}" for k, (n, t) in enumerate(marks[1:])) +
-                  f" total={1e3 * (marks[-1][1] - marks[0][1]):.3f} nghost={self.nghost}", flush=True)
-        return sf
 
 
 class DistSph:

@@ -3,7 +3,7 @@
 backend=gloo : host logic of the multi-GPU path (ORB boxes, ownership, ghost selection radius, the two-stage ghost
                protocol) exercised on CPU with the oracle standing in for the device kernels, result compared with the
                oracle on the undivided particle set.
-backend=nccl : the real thing -- SphGpu + DistributedSph on one GPU per rank, compared with the oracle on the whole set.
+backend=nccl : the real thing -- SphGpu + DistSph (csrc/dist.cu behind the C ABI) on one GPU per rank, compared with the oracle on the whole set.
 """
 import os
 import sys
@@ -19,6 +19,10 @@ def global_problem(nx, mhd=False):
     from phantom_b200 import setups
     if nx < 0:              # turbulent box of (-nx)^3 particles (C2): the stepping test
         part = setups.setup_turb(nx=-nx)
+        part.alphaind[:, 0] = 1.0
+        return part
+    if 500 <= nx < 1000:    # Sod shock tube (C1): boundary particles at the x ends (set_boundaries_to_active on the first pass), quintic kernel
+        part = setups.setup_shock(nx=nx - 500)
         part.alphaind[:, 0] = 1.0
         return part
     if nx >= 1000:          # self-gravitating sphere of nx particles (C5): exercises the gathered gravity set

@@ -64,3 +64,21 @@ def test_restart_from_dump_reproduces_derivs():
     Oracle(a.params).derivs(a)
     Oracle(b.params).derivs(b)
     assert np.array_equal(a.fxyzu, b.fxyzu) and np.array_equal(a.xyzh, b.xyzh)
+
+
+def test_multi_block_dump_of_an_mpi_run_reads_back():
+    # readwrite_dumps.f90:170-172, :600-665: nblocks processes each write {block headers, arrays}; the reader concatenates the pieces
+    part = setups.setup_orstang(nx=10)
+    with tempfile.TemporaryDirectory() as d:
+        one, three = os.path.join(d, "one_00000"), os.path.join(d, "three_00000")
+        dumpio.write_dump(one, part, time=0.5)
+        dumpio.write_dump(three, part, time=0.5, nblocks=3)
+        assert os.path.getsize(three) > os.path.getsize(one)
+        a, b = dumpio.read_dump(one), dumpio.read_dump(three)
+    assert b["nblocks"] == 3 and a["nblocks"] == 1 and len(b["blocks"]) == len(a["blocks"]) == 4
+    for ka, kb in zip(a["blocks"], b["blocks"]):
+        assert set(ka) == set(kb)
+        for tag in ka:
+            assert np.array_equal(ka[tag], kb[tag]), tag
+    pa = dumpio.particles_from_dump(b, part.params.copy())
+    assert np.array_equal(pa.xyzh[:, :3], part.xyzh[:, :3]) and np.array_equal(pa.vxyzu, part.vxyzu)

@@ -109,3 +109,15 @@ def test_two_gpu_step_with_migration_tracks_undivided_oracle():
         assert np.max(np.abs(o_["xyzh"][:, 3] - ref.xyzh[idx, 3]) / ref.xyzh[idx, 3]) < 1e-9
     assert np.all(seen == 1)
     assert sum(int(o_["migrated"]) for o_ in outs) > 0                 # particles did change owner during the run
+
+
+def test_two_gpu_shock_tube_with_boundary_particles():
+    """C1 on 2 GPUs: boundary particles are active on the first density pass (deriv.f90:146) on their owner and must stay neighbour-only
+    as ghosts on the other rank"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    from test_halo_gloo import launch, check_against_undivided
+    with tempfile.TemporaryDirectory() as d:
+        launch("nccl", 2, 516, d, 29619)
+        check_against_undivided(d, 2, 516)
