@@ -364,12 +364,16 @@ def _solenoidal_field(xyzh, box, seed, mach, cs, kmin=1, kmax=3):
     return v * (mach * cs / vrms)
 
 
-def setup_turb(nx=128, mach=5.0, seed=1234, ind_timesteps=False):
+def setup_turb(nx=128, mach=5.0, seed=1234, ind_timesteps=False, positions="lattice"):
     """C2: SETUP=turb -- isothermal periodic box [0,1]^3, cubic lattice nx^3, cs=1, rho0=1
-    (setup_turb.f90:101-176)."""
+    (setup_turb.f90:101-176).  positions="random": the same number of particles at uniformly random positions (set_unifdis 'random'),
+    a disordered state for benchmarks (target groups no longer align with the lattice)."""
     p = default_params(isothermal=1, ieos=1, polyk=1.0, gamma=1.0, ind_timesteps=int(ind_timesteps),
                        xmin=0., xmax=1., ymin=0., ymax=1., zmin=0., zmax=1., dtmax=0.025 if ind_timesteps else 1e29)
-    xyzh = unifdis_cubic(0., 1., 0., 1., 0., 1., 1.0 / nx, p.hfact)
+    if positions == "random":
+        xyzh = unifdis_random(0., 1., 0., 1., 0., 1., 1.0 / nx, p.hfact)
+    else:
+        xyzh = unifdis_cubic(0., 1., 0., 1., 0., 1., 1.0 / nx, p.hfact)
     p.massoftype[IGAS] = 1.0 / len(xyzh)
     part = Particles(p, xyzh)
     part.vxyzu[:, :3] = _solenoidal_field(xyzh, (0.0, 1.0), seed, mach, 1.0)

@@ -85,3 +85,41 @@ def test_turb_128_full_size_parity():
     sg = gpu(pg.params).derivs(pg)
     parity(po, pg, sdo, sfo, sg)
     assert np.array_equal(pg.alphaind[:, 1], po.alphaind[:, 1]) or np.max(np.abs(pg.alphaind[:, 1] - po.alphaind[:, 1])) < 1e-6
+
+
+def test_dustybox_on_the_device_matches_the_analytic_decay():
+    """DUSTYBOX (test_dust.f90:132-311) through sphgpu_step_resident: 100 steps, the reference's cubic-kernel tolerances on v and f of both
+    phases and on E_kin at every step"""
+    import math
+    from phantom_b200.params import default_params, IDUST
+    from phantom_b200.api import SphGpu
+    nx = 24
+    dz = 2. * math.sqrt(6.) / nx
+    p = default_params(dust=1, idrag=2, K_code=0.35, ieos=1, polyk=1., gamma=1., alpha=0., alphamax=0., alphau=0., alphaB=0., tolh=1.e-4,
+                       xmin=-0.5, xmax=0.5, ymin=-0.25, ymax=0.25, zmin=-dz, zmax=dz)
+    lat = setups.unifdis_closepacked(p.xmin, p.xmax, p.ymin, p.ymax, p.zmin, p.zmax, 1. / nx, p.hfact, periodic=True)
+    n1 = len(lat)
+    totmass = (p.xmax - p.xmin) * (p.ymax - p.ymin) * (p.zmax - p.zmin)
+    p.massoftype[IGAS] = totmass / n1
+    p.massoftype[IDUST] = totmass / n1
+    iphase = np.concatenate([np.full(n1, IGAS, dtype=np.int8), np.full(n1, IDUST, dtype=np.int8)])
+    part = setups.Particles(p, np.concatenate([lat, lat]), iphase)
+    dust = iphase == IDUST
+    part.vxyzu[dust, 0] = 1.
+    g = SphGpu(part.params.copy())
+    g.upload(part)
+    g.derivs_resident(1)
+    K, dt, t = 0.35, 1.e-3, 0.
+    for it in range(100):
+        t += dt
+        g.step_resident(dt)
+        dv = math.exp(-2. * K * t)
+        vg, vd = 0.5 * (1. - dv), 0.5 * (1. + dv)
+        fd = K * (vg - vd)
+        if it % 10 == 9 or it < 3:
+            g.download(part)
+            for x, val, tol in ((part.vxyzu[dust, 0], vd, 1.e-4), (part.fxyzu[dust, 0], fd, 3.e-3), (part.vxyzu[~dust, 0], vg, 1.e-4),
+                                (part.fxyzu[~dust, 0], -fd, 3.e-3)):
+                assert nfailed_v(x, val, tol)[0] == 0, it
+        ekin = g.energies_resident().ekin
+        assert nfailed_v(np.array([ekin]), 0.5 * totmass * (vd ** 2 + vg ** 2), 1.e-4)[0] == 0, it

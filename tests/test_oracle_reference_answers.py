@@ -288,3 +288,70 @@ def test_fmm_linear_momentum_conservation():
     fsum = p.massoftype[IGAS] * np.sum(part.fxyzu[:, :3], axis=0)
     assert np.all(np.abs(fsum) <= 2.e-16), fsum
     assert np.max(np.abs(part.fxyzu[:, :3])) > 1e-1                                 # G M / R^2 = 0.5 at the surface of each sphere
+
+
+# ---- two-fluid dust: test_dust.f90 -----------------------------------------------------------------------------------------------------
+def test_dustybox_analytic_decay():
+    """DUSTYBOX (test_dust.f90:132-311): gas and dust on the same close-packed lattice (nx = 24), dust drifting with v_x = 1 through gas at
+    rest, constant drag K = 0.35 (idrag = 2), isothermal EOS, no viscosity, 100 leapfrog steps of dt = 1e-3.  Exact solution
+    dv = exp(-2 K t), v_g = (1 - dv)/2, v_d = (1 + dv)/2, f_d = K (v_g - v_d); cubic-kernel tolerances 1e-4 (v, E_kin) and 3e-3 (f)."""
+    import steplib
+    from phantom_b200.params import default_params, IDUST
+    nx = 24
+    dz = 2. * math.sqrt(6.) / nx
+    p = default_params(dust=1, idrag=2, K_code=0.35, ieos=1, polyk=1., gamma=1., alpha=0., alphamax=0., alphau=0., alphaB=0., tolh=1.e-4,
+                       xmin=-0.5, xmax=0.5, ymin=-0.25, ymax=0.25, zmin=-dz, zmax=dz)
+    lat = setups.unifdis_closepacked(p.xmin, p.xmax, p.ymin, p.ymax, p.zmin, p.zmax, 1. / nx, p.hfact, periodic=True)
+    n1 = len(lat)
+    totmass = 1. * (p.xmax - p.xmin) * (p.ymax - p.ymin) * (p.zmax - p.zmin)
+    p.massoftype[IGAS] = totmass / n1
+    p.massoftype[IDUST] = totmass / n1
+    xyzh = np.concatenate([lat, lat])
+    iphase = np.concatenate([np.full(n1, IGAS, dtype=np.int8), np.full(n1, IDUST, dtype=np.int8)])
+    part = setups.Particles(p, xyzh, iphase)
+    dust = iphase == IDUST
+    part.vxyzu[dust, 0] = 1.
+    o = Oracle(part.params)
+    steplib.oracle_derivs(o, part, 1)
+    K, dt, t = 0.35, 1.e-3, 0.
+    for it in range(100):
+        t += dt
+        steplib.step_leapfrog(o, part, dt)
+        dv = math.exp(-2. * K * t)
+        vg, vd = 0.5 * (1. - dv), 0.5 * (1. + dv)
+        fd = K * (vg - vd)
+        for x, val, tol, what in ((part.vxyzu[dust, 0], vd, 1.e-4, "vd"), (part.fxyzu[dust, 0], fd, 3.e-3, "fd"),
+                                  (part.vxyzu[~dust, 0], vg, 1.e-4, "vg"), (part.fxyzu[~dust, 0], -fd, 3.e-3, "fg")):
+            nf, emax = nfailed_v(x, val, tol)
+            assert nf == 0, (it, what, emax)
+        ekin = steplib.energies(part)["ekin"]
+        ekin_exact = 0.5 * totmass * (vd ** 2 + vg ** 2)
+        assert nfailed_v(np.array([ekin]), ekin_exact, 1.e-4)[0] == 0, (it, ekin, ekin_exact)     # checkvalbuf (utils_testsuite.f90:662-685)
+
+
+def test_drag_conserves_momentum_and_energy():
+    """test_drag (test_dust.f90:501-641): 25^3 random gas particles + (25/3)^3 random dust particles with random velocities, Epstein/Stokes
+    drag (idrag = 1, unit grain size and density in cgs code units): sum m a = 0 to 1e-7 per component, sum m (v.a + du/dt) = 0 to 1e-6."""
+    from phantom_b200.params import default_params, IDUST
+    p = default_params(dust=1, idrag=1, ieos=2, grainsize=1., graindens=1.)
+    p.seff = math.pi / math.sqrt(2.) * 5. / 64. * (2. * 1.67262158e-24) / 2.367e-15      # init_drag (dust.f90:94-97) with umass = udist = 1
+    rhozero = 3.
+    totmass = rhozero * (p.xmax - p.xmin) * (p.ymax - p.ymin) * (p.zmax - p.zmin)
+    gas = setups.unifdis_random(p.xmin, p.xmax, p.ymin, p.ymax, p.zmin, p.zmax, 1. / 25, p.hfact, iseed=-14255)
+    dustp = setups.unifdis_random(p.xmin, p.xmax, p.ymin, p.ymax, p.zmin, p.zmax, 3. / 25, p.hfact, iseed=-14256)
+    p.massoftype[IGAS] = totmass / len(gas)
+    p.massoftype[IDUST] = totmass / len(dustp)
+    xyzh = np.concatenate([gas, dustp])
+    iphase = np.concatenate([np.full(len(gas), IGAS, dtype=np.int8), np.full(len(dustp), IDUST, dtype=np.int8)])
+    part = setups.Particles(p, xyzh, iphase)
+    rng = setups.Ran2(-14257)
+    part.vxyzu[:, :3] = rng.draw(3 * part.npart).reshape(-1, 3)
+    part.vxyzu[:len(gas), 3] = rng.draw(len(gas))
+    Oracle(part.params).derivs(part, dt=1.)
+    m = np.where(iphase == IDUST, p.massoftype[IDUST], p.massoftype[IGAS])
+    da = np.sum(m[:, None] * part.fxyzu[:, :3], axis=0)
+    assert np.all(np.abs(da) <= 1.e-7), da
+    dekin = np.sum(m * np.sum(part.vxyzu[:, :3] * part.fxyzu[:, :3], axis=1))
+    deint = np.sum(m * part.fxyzu[:, 3])
+    assert abs(dekin + deint) <= 1.e-6, (dekin, deint)
+    assert np.max(np.abs(part.fxyzu[iphase == IDUST, :3])) > 0.              # the dust does feel the drag
