@@ -78,6 +78,9 @@ struct __align__(16) TreeNodeF {
     int child[2];      // >= 0: internal node id ; < 0: leaf, bits 0-30 = (first sorted slot << 5) | (count - 1)
 };
 
+// node of the reference-topology kd-tree as the force pass of the reference-compatible neighbour mode needs it (gravity.cu builds it)
+struct __align__(16) RefNode { double xcen[3], size, hmax; int parent, pad; };
+
 struct Cell {          // leaf cell = run of <= max_cell Morton-consecutive particles
     double lo[3], hi[3];
     double hmax;
@@ -139,6 +142,15 @@ struct sphgpu_ctx {
     bool hilbert = false;                   // space-filling curve of the particle order: Morton (default) or Hilbert (option "hilbert" 1; measured equal on B200)
     bool always_refit = false;              // option: refit the tree's hmax after every density pass (A/B testing)
     bool force_general = false;             // option: route everything through the general force kernel (A/B testing)
+    // Individual timesteps: the reference's force walk can MISS a pair that only an inactive neighbour j reaches, because a leaf's hmax
+    // is overwritten by 1.01 max(h) over its ACTIVE members when the leaf re-walks during the h-rho iteration (dens.F90:343-345,
+    // :1275-1289; neigh_kdtree.f90:115-131) and the walk prunes on that (kdtree.F90:1288-1293).  refcompat = 1 (the default whenever
+    // ind_timesteps is set; option "refcompat_hmax") drops exactly those pairs: the reference's own tree is built (gravity.cu), its node
+    // hmax history replayed, and a pair with q2i >= R^2, q2j < R^2 is kept only if the reference's walk from i's leaf reaches j's leaf.
+    // refcompat = 0 evaluates the pair criterion q2i < R^2 .or. q2j < R^2 exactly (every pair, as an O(N^2) search would).
+    int refcompat = -1;                     // -1: follow ind_timesteps
+    DevBuf<RefNode> ref_nodes; DevBuf<int> ref_leaf, ref_leaf_sorted;   // reference tree nodes ; leaf of every particle (caller order / sorted slot)
+    bool ref_valid = false;
     DevBuf<float> s_gradh, s_divv, s_dvdx, s_alpha3, s_divcurlB;   // sorted density outputs
     DevBuf<double4> s_fxyzu, s_dB;          // sorted force outputs
     DevBuf<float> s_divvf, s_poten, s_divBsymm;
@@ -283,6 +295,8 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out);
 int cons2prim_run(sphgpu_ctx *c);
 int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out);
 int gravity_run(sphgpu_ctx *c);
+int refcompat_prepare(sphgpu_ctx *c);      // reference tree + node hmax history + leaf of every particle (gravity.cu)
+static inline bool refcompat_on(const sphgpu_ctx *c) { return c->refcompat < 0 ? c->hp.p.ind_timesteps != 0 : c->refcompat != 0; }
 void gravity_release(sphgpu_ctx *c);
 int gravity_gather_pack(sphgpu_ctx *c, void **sendptr, int *record_doubles);
 int gravity_gather_recvbuf(sphgpu_ctx *c, int nranks, int64_t stride, void **recvptr);

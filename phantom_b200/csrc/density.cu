@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                         failed = true; conv = true;
                     } else {
                         h = hnew;
-                        if (GRAV && its <= SPHGPU_HHIST) a.h_hist[(size_t)(its - 1) * a.npart + a.perm[s]] = hnew;
+                        if (a.h_hist && its <= SPHGPU_HHIST) a.h_hist[(size_t)(its - 1) * a.npart + a.perm[s]] = hnew;
                     }
                 }
             }
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
             }
             const int nn = nneighi + 1;   // + self
             a.s_nneigh[s] = nn;
-            if (GRAV) a.h_its[a.perm[s]] = its_lane;
+            if (a.h_hist) a.h_its[a.perm[s]] = its_lane;
             st_rhomax = fmax(st_rhomax, rho);
             st_pairs += (unsigned long long)nneighi * its_lane;
             st_ncalc += its_lane; st_nact += nn; st_np += 1;
@@ -653,7 +653,11 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     a.multitype = c->multitype ? 1 : 0; a.max_leaf = c->max_leaf; a.hmax_global = 0.;
     a.cnt = c->counters.p; a.dscal = c->dscal.p;
     a.margin = c->list_margin; a.icall = icall;
-    a.h_hist = c->h_hist.p; a.h_its = c->h_its.p; a.npart = n;
+    // the node-hmax replay of the reference tree (self-gravity, and the reference-compatible neighbour mode) needs every particle's h history
+    const bool loghist = p.gravity || refcompat_on(c);
+    if (loghist) CUDA_TRY(c, c->h_hist.ensure((size_t)SPHGPU_HHIST * n));
+    a.h_hist = loghist ? c->h_hist.p : nullptr; a.h_its = c->h_its.p; a.npart = n;
+    c->ref_valid = false;
     c->grav_tree_valid = false;            // h changes below: the gravity tree caches h
     {   // ONE symmetric walk serves both passes: with the list margin on every radius it holds the density candidates now and the force
         // candidates as long as no h grows by more than the margin (force_run checks hscale against wl_cover)

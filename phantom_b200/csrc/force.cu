@@ -30,6 +30,8 @@ struct ForceArgs {
     const double *gsoft; const float *dvdx9; const double4 *gacc; float *s_poten; double *s_tstop;
     const int8_t *s_ibinold, *s_ibin; int *s_wake; int8_t *s_ibinnew;
     int nbinmax, ibinnow_m1, istepfrac;
+    // reference-compatible neighbour mode (common.cuh: refcompat): reference tree nodes, leaf of every sorted slot; refnodes == NULL: exact mode
+    const RefNode *refnodes; const int *refleaf; double ref_radkern, ref_tree_acc2; int ref_gravity;
 };
 
 struct XtraSums { double fdx, fdy, fdz, tsmin; int ibin_neigh; };
@@ -143,6 +145,33 @@ __device__ __forceinline__ double recon_slope(const float *__restrict__ d, doubl
            dz * (rx * (double)d[2] + ry * (double)d[5] + rz * (double)d[8]);
 }
 
+// Would the reference's force walk from the leaf of i reach the leaf of j?  getneigh (kdtree.F90:1221-1347) opens a node when
+// r2 < (size_i + size_n + max(rcut_i, radkern hmax_n))^2 between the node centres (minimum image, get_sep :1468-1501), or by the
+// gravity opening criterion; j's leaf is reached iff every node on the path from the root down to it is opened.
+template <bool PERIODIC>
+__device__ __noinline__ bool ref_walk_reaches(const ForceArgs &a, int si, int sj, double Lx, double Ly, double Lz)
+{
+    const RefNode ci = a.refnodes[a.refleaf[si]];
+    const double rcuti = a.ref_radkern * ci.hmax;
+    int n = a.refleaf[sj];
+    while (n >= 0) {
+        const RefNode nd = a.refnodes[n];
+        double dx = ci.xcen[0] - nd.xcen[0], dy = ci.xcen[1] - nd.xcen[1], dz = ci.xcen[2] - nd.xcen[2];
+        if (PERIODIC) {
+            if (fabs(dx) > 0.5 * Lx) dx -= copysign(Lx, dx);
+            if (fabs(dy) > 0.5 * Ly) dy -= copysign(Ly, dy);
+            if (fabs(dz) > 0.5 * Lz) dz -= copysign(Lz, dz);
+        }
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        const double rcut = fmax(rcuti, a.ref_radkern * nd.hmax);
+        const double s = ci.size + nd.size;
+        const bool open = (r2 < (s + rcut) * (s + rcut)) || (a.ref_gravity && a.ref_tree_acc2 * r2 < s * s);
+        if (!open) return false;
+        n = nd.parent;
+    }
+    return true;
+}
+
 // pair body: lane = target, j = this lane's next neighbour candidate (slot < 0: none).  Branch-free: the exact membership
 // test (force.F90:1271-1287, :1230) and the gas-gas condition (:1539) become zero weights on grad W_i, grad W_j, through
 // which every sum of compute_forces scales; two calls per trip give two independent FP64 dependency chains.
@@ -163,7 +192,9 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
     const double r2 = pair_r2<PERIODIC>(pi.x, pi.y, pi.z, pj, Lx, Ly, Lz, dx, dy, dz);
     const double hj1 = hj.x, hj21 = hj.y;
     const double q2i = __dmul_rn(r2, hi21), q2j = __dmul_rn(r2, hj21);        // force.F90:1272, :1285
-    const bool isn = (q2i < KF::radkern2 || q2j < KF::radkern2) && (j != s);  // :1287, :1230
+    bool isn = (q2i < KF::radkern2 || q2j < KF::radkern2) && (j != s);        // :1287, :1230
+    // a pair that only j's kernel reaches exists for the reference only if its walk got to j's leaf (see ref_walk_reaches)
+    if (XTRA && a.refnodes && isn && !(q2i < KF::radkern2)) isn = ref_walk_reaches<PERIODIC>(a, s, j, Lx, Ly, Lz);
     npair += isn ? 1 : 0;
     int itypej = IGAS;
     if (a.multitype) itypej = abs((int)a.stype[j]);
@@ -443,13 +474,17 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
                     }
                 }
                 double r2[2], rij1[2], grkerni[2], grkernj[2];
-                bool ini[2], inj[2], isn[2];
+                bool ini[2], inj[2], isn[2], dropj[2] = {false, false};
 #pragma unroll
                 for (int k = 0; k < 2; k++) {
                     r2[k] = __dadd_rn(__dadd_rn(__dmul_rn(dx[k], dx[k]), __dmul_rn(dy[k], dy[k])), __dmul_rn(dz[k], dz[k]));
                     const double hj1 = R0[k].w;
                     const double q2i = __dmul_rn(r2[k], hi21), q2j = __dmul_rn(r2[k], __dmul_rn(hj1, hj1));       // force.F90:1272, :1285
                     ini[k] = (q2i < KF::radkern2) && live[k]; inj[k] = (q2j < KF::radkern2) && live[k];          // :1287, :1230 (exact membership)
+                    if (indts && a.refnodes && inj[k] && !ini[k]) {       // only j's kernel reaches: did the reference's walk find j's leaf?
+                        const int jj0 = (int)lds_u32(sidx_s + 4u * (unsigned)sl[k]);
+                        if (!ref_walk_reaches<PERIODIC>(a, s, jj0, Lx, Ly, Lz)) { inj[k] = false; dropj[k] = true; }
+                    }
                     isn[k] = ini[k] || inj[k];
                     npair += isn[k] ? 1 : 0;
                     if (indts && isn[k] && abs((int)a.stype[jj[k]]) != IBOUNDARY) {   // j neighbours an active particle: wake flag, Saitoh-Makino input
@@ -464,7 +499,7 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
                     const double rij = r2[k] * rij1[k];
                     // the padding repeats a real neighbour: it (and the self pair) enter with weight 0 on both gradients
                     grkerni[k] = KF::grkern_bf(rij * hi1) * (live[k] ? gi : 0.);         // :1301-1302
-                    grkernj[k] = KF::grkern_bf(rij * R0[k].w) * (live[k] ? R1[k].w : 0.);   // :1325-1327
+                    grkernj[k] = KF::grkern_bf(rij * R0[k].w) * ((live[k] && !(indts && dropj[k])) ? R1[k].w : 0.);   // :1325-1327
                 }
 #pragma unroll
                 for (int k = 0; k < 2; k++) {
@@ -956,6 +991,11 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     a.s_ibinold = c->s_ibinold.p; a.s_ibin = c->s_ibin.p; a.s_wake = c->s_wake.p; a.s_ibinnew = c->s_ibinnew.p;
     a.hscale = c->hscale;
     a.nbinmax = c->nbinmax; a.ibinnow_m1 = c->ibinnow - 1; a.istepfrac = c->istepfrac;
+    if (p.ind_timesteps && refcompat_on(c) && c->dens_valid) {           // reference-compatible neighbour sets (common.cuh: refcompat)
+        TRY(refcompat_prepare(c));
+        a.refnodes = c->ref_nodes.p; a.refleaf = c->ref_leaf_sorted.p; a.ref_radkern = c->hp.kc.radkern; a.ref_tree_acc2 = p.tree_accuracy * p.tree_accuracy;
+        a.ref_gravity = p.gravity;
+    }
     if (c->wl_force_ok && c->hscale <= c->wl_cover) {                      // the lists of the density pass still cover every pair
         a.wl.list = c->wl_list.p; a.wl.ncl = c->wl_ncl.p; a.wl.reach = c->wl_reach.p; a.wl.cap = c->walk_cap;
     } else {

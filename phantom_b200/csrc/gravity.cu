@@ -784,6 +784,49 @@ int gravity_run(sphgpu_ctx *c)
     return SPHGPU_OK;
 }
 
+// ---- reference-compatible neighbour mode (common.cuh: refcompat): the reference's tree with its node hmax at force time, compact ----
+__global__ void k_ref_export(int nn, const GNode *__restrict__ nodes, const int *__restrict__ gid, RefNode *__restrict__ out, int *__restrict__ leaf_of)
+{
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= nn) return;
+    const GNode &nd = nodes[d];
+    RefNode r;
+    r.xcen[0] = nd.xcen[0]; r.xcen[1] = nd.xcen[1]; r.xcen[2] = nd.xcen[2]; r.size = nd.size; r.hmax = nd.hmax; r.parent = nd.parent; r.pad = 0;
+    out[d] = r;
+    if (nd.left < 0) for (int s = nd.start; s < nd.start + nd.count; s++) leaf_of[gid[s]] = d;
+}
+__global__ void k_ref_leaf_sorted(int64_t nlive, const int *__restrict__ perm, const int *__restrict__ leaf_of, int *__restrict__ out)
+{
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s < nlive) out[s] = leaf_of[perm[s]];
+}
+
+int refcompat_prepare(sphgpu_ctx *c)
+{
+    if (c->ref_valid) return SPHGPU_OK;
+    if (!c->grav) c->grav = new GravState();
+    GravState &g = *c->grav;
+    const GravInput in = grav_input(c, g);
+    if (g.nglobal > 0) { c->err = "refcompat: not available together with the gathered multi-GPU gravity set"; return SPHGPU_ERR_STATE; }
+    CUDA_TRY(c, cudaMemsetAsync(c->counters.p + CNT_ERR, 0, 2 * sizeof(unsigned long long), c->stream));
+    if (!c->grav_tree_valid) { TRY(grav_build(c, g, in)); c->grav_tree_valid = true; }
+    const int nn = g.nn, cur = g.cur;
+    const int nlev = (int)g.level_start.size() - 1;
+    GL(c, k_g_hmax_leaf, nblk(nn, 128), 128, nn, g.nodes.p, g.gb.p, g.gid[cur].p, in.hbuild, in.hits, in.hhist, in.n, SPHGPU_HHIST, in.iphase,
+       c->hp.p.ind_timesteps, in.own_lo, in.own_hi);
+    for (int L = nlev - 1; L >= 0; L--) {
+        const int a0 = g.level_start[L], a1 = g.level_start[L + 1];
+        GL(c, k_g_hmax_up, nblk(a1 - a0, 128), 128, a0, a1, g.nodes.p, g.gb.p);
+    }
+    CUDA_TRY(c, c->ref_nodes.ensure(nn)); CUDA_TRY(c, c->ref_leaf.ensure(c->npart)); CUDA_TRY(c, c->ref_leaf_sorted.ensure(c->npart));
+    CUDA_TRY(c, cudaMemsetAsync(c->ref_leaf.p, 0, sizeof(int) * (size_t)c->npart, c->stream));
+    GL(c, k_ref_export, nblk(nn, 128), 128, nn, g.nodes.p, g.gid[cur].p, c->ref_nodes.p, c->ref_leaf.p);
+    GL(c, k_ref_leaf_sorted, nblk(c->nlive, 256), 256, c->nlive, c->perm.p, c->ref_leaf.p, c->ref_leaf_sorted.p);
+    CUDA_TRY(c, cudaGetLastError());
+    c->ref_valid = true;
+    return SPHGPU_OK;
+}
+
 // ---- multi-GPU: every rank evaluates the FMM for its own particles on the tree of the WHOLE particle set ---------------------------
 // (replaces the global tree + remote cell export of maketreeglobal / mpi_force for the gravity terms, kdtree.F90:2044-2300).
 // The ranks all-gather 13 doubles per owned particle {x,y,z,h, iphase, h at build_tree, iterations, h history(6)}; each rank then

@@ -133,7 +133,7 @@ void sphgpu_destroy(sphgpu_ctx *c)
     c->cubtemp.release(); c->scratch.release(); c->nodesf.release(); c->stage_idx.release(); c->counters.release(); c->dscal.release();
     for (int k = 0; k < 16; k++) cudaEventDestroy(c->ev[k]);
     if (c->copy_in) { cudaStreamDestroy(c->copy_in); cudaStreamDestroy(c->copy_out); for (int k = 0; k < 6; k++) cudaEventDestroy(c->cev[k]); }
-    gravity_release(c); c->h_build.release(); c->h_hist.release(); c->h_its.release();
+    gravity_release(c); c->h_build.release(); c->h_hist.release(); c->h_its.release(); c->ref_nodes.release(); c->ref_leaf.release(); c->ref_leaf_sorted.release();
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -159,6 +159,7 @@ int sphgpu_set_option(sphgpu_ctx *c, const char *name, double value)
     if (!strcmp(name, "hilbert")) { c->hilbert = value != 0.; c->tree_valid = false; return 0; }
     if (!strcmp(name, "halo_hgrow")) { c->halo_hgrow = value; return 0; }
     if (!strcmp(name, "always_refit")) { c->always_refit = value != 0.; return 0; }
+    if (!strcmp(name, "refcompat_hmax")) { c->refcompat = value < 0. ? -1 : (value != 0. ? 1 : 0); c->ref_valid = false; return 0; }
     if (!strcmp(name, "force_general")) { c->force_general = value != 0.; return 0; }
     if (!strcmp(name, "grav_p2p_per_particle")) { c->grav_p2p_per_particle = (int)value < 8 ? 8 : (int)value; return 0; }
     if (!strcmp(name, "legacy_stream")) {

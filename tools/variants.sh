@@ -8,7 +8,7 @@ if [ "$1" == "build" ]; then
   for v in "${VARIANTS[@]}"; do
     tag=${v%%:*}; flags=${v#*:}
     ( cd phantom_b200/csrc && for f in force density neigh; do /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -ccbin /usr/bin/g++ -Xcompiler -fPIC,-O2 --expt-relaxed-constexpr $flags -c $f.cu -o ../../build/variants/${f}_$tag.o & done; wait
-      /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -shared -o ../../build/variants/libsphgpu_$tag.so sphgpu.o tree.o ../../build/variants/density_$tag.o ../../build/variants/force_$tag.o cons2prim.o ../../build/variants/neigh_$tag.o halo.o gravity.o step.o )
+      /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -shared -o ../../build/variants/libsphgpu_$tag.so sphgpu.o tree.o ../../build/variants/density_$tag.o ../../build/variants/force_$tag.o cons2prim.o ../../build/variants/neigh_$tag.o halo.o gravity.o step.o dist.o -ldl )
     echo built $tag
   done
 else
