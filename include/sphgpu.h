@@ -268,6 +268,15 @@ typedef struct sphgpu_step_out {
     sphgpu_scalars scalars;     /* of the last derivs call of the step */
 } sphgpu_step_out;
 int sphgpu_step_resident(sphgpu_ctx *ctx, double dtsph, double tolv, sphgpu_step_out *out);
+/* the same step with -DIND_TIMESTEPS (step_leapfrog.f90:57-80, :157-164, :183-235, :470-560; utils_indtimesteps.f90): the host keeps
+ * time, istepfrac and nbinmax as evolve.f90 does and calls, per smallest timestep dtsph = dtmax / 2^nbinmax,
+ *   sphgpu_set_active_particles_resident (set_active_particles: the activity flags of this substep, ibinnow) and
+ *   sphgpu_step_ind_resident (predictor to every particle's own half step twas, drift, predict_sph, derivs, corrector of the active
+ *   particles into their new bins, synchronisation, wake-up of flagged neighbours); out->scalars.nbinmaxnew is the new nbinmax.
+ * sphgpu_init_step_resident is init_step: at time 0 every particle starts in bin nbinmax, twas = time + dt(ibin)/2. */
+int sphgpu_init_step_resident(sphgpu_ctx *ctx, double time, double dtmax, int nbinmax);
+int sphgpu_set_active_particles_resident(sphgpu_ctx *ctx, int nbinmax, int istepfrac, int64_t *nactive, int64_t *nalive);
+int sphgpu_step_ind_resident(sphgpu_ctx *ctx, double t, double dtsph, double dtmax, sphgpu_step_out *out);
 
 /* compute_energies (src/main/energies.f90:64-760): the conserved-quantity sums of the resident state */
 typedef struct sphgpu_energies {

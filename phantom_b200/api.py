@@ -38,7 +38,7 @@ EXPORTS = [
     "sphgpu_gravity_gather_unpack", "sphgpu_density_hmax_used", "sphgpu_halo_restore_h", "sphgpu_set_forcing_modes", "sphgpu_forcing_resident", "sphgpu_get_copy_bytes", "sphgpu_density_hgrow",
     "sphgpu_dist_get_unique_id", "sphgpu_dist_init", "sphgpu_dist_finalize", "sphgpu_dist_set_boxes", "sphgpu_dist_get_boxes", "sphgpu_dist_set_ids",
     "sphgpu_dist_get_ids", "sphgpu_dist_nlocal", "sphgpu_dist_derivs", "sphgpu_dist_migrate", "sphgpu_dist_rebalance", "sphgpu_dist_step",
-    "sphgpu_dist_energies", "sphgpu_dist_stats",
+    "sphgpu_dist_energies", "sphgpu_dist_stats", "sphgpu_init_step_resident", "sphgpu_set_active_particles_resident", "sphgpu_step_ind_resident",
 ]
 
 
@@ -133,6 +133,9 @@ def load_library():
         L.sphgpu_dist_step.argtypes = [vp, dbl, dbl, C.POINTER(SphStepOut)]
         L.sphgpu_dist_energies.argtypes = [vp, C.POINTER(SphEnergies)]
         L.sphgpu_dist_stats.argtypes = [vp, C.POINTER(dbl)]
+        L.sphgpu_init_step_resident.argtypes = [vp, dbl, dbl, i32]
+        L.sphgpu_set_active_particles_resident.argtypes = [vp, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+        L.sphgpu_step_ind_resident.argtypes = [vp, dbl, dbl, dbl, C.POINTER(SphStepOut)]
         _lib = L
     return _lib
 
@@ -284,6 +287,22 @@ class SphGpu:
         """one leapfrog step of the resident state (step_leapfrog.f90:95, global timesteps)"""
         out = SphStepOut()
         self._check(self.L.sphgpu_step_resident(self.h, float(dtsph), float(tolv), C.byref(out)))
+        return out
+
+    def init_step_resident(self, time, dtmax, nbinmax):
+        """init_step with individual timesteps (step_leapfrog.f90:57-80)"""
+        self._check(self.L.sphgpu_init_step_resident(self.h, float(time), float(dtmax), int(nbinmax)))
+
+    def set_active_particles_resident(self, nbinmax, istepfrac):
+        """set_active_particles (utils_indtimesteps.f90:114-178) -> (nactive, nalive)"""
+        na, nl = C.c_int64(), C.c_int64()
+        self._check(self.L.sphgpu_set_active_particles_resident(self.h, int(nbinmax), int(istepfrac), C.byref(na), C.byref(nl)))
+        return na.value, nl.value
+
+    def step_ind_resident(self, t, dtsph, dtmax):
+        """one call of step() with individual timesteps (dtsph = dtmax / 2^nbinmax)"""
+        out = SphStepOut()
+        self._check(self.L.sphgpu_step_ind_resident(self.h, float(t), float(dtsph), float(dtmax), C.byref(out)))
         return out
 
     def energies_resident(self):

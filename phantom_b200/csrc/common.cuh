@@ -126,6 +126,7 @@ struct sphgpu_ctx {
     DevBuf<double> dustfrac, tstop;
     DevBuf<double> forc_tab; int forc_nmodes = 0, forc_correct_mean = 0; double forc_fac = 0.;   // turbulent driving mode table (forcing.f90)
     DevBuf<double> v_true, B_true;          // step.cu: the evolved v, B/rho while vxyzu/Bevol hold the predicted values
+    DevBuf<double> twas;                    // step.cu, individual timesteps: the time each particle's v sits at (part.F90 twas)
     DevBuf<double4> gacc;                   // far-field gravity {fx,fy,fz,pot} per particle (gravity.cu -> force epilogue)
     // ---- sorted working set ----
     int64_t nlive = 0;

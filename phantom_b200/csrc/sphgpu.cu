@@ -125,7 +125,7 @@ void sphgpu_destroy(sphgpu_ctx *c)
     c->divcurlv.release(); c->divcurlB.release(); c->alphaind.release(); c->gradh.release(); c->dvdx.release(); c->poten.release(); c->divBsymm.release();
     c->iphase.release(); c->ibin.release(); c->ibin_old.release(); c->ibin_wake.release();
     c->keys.release(); c->keys_alt.release(); c->perm.release(); c->perm_alt.release(); c->pos4.release(); c->vel4.release(); c->acc4.release(); c->bev4.release();
-    c->stype.release(); c->hnew.release(); c->frecC.release(); c->frecD.release(); c->frecE.release(); c->frec.release(); c->drec.release(); c->v_true.release(); c->B_true.release(); c->forc_tab.release();
+    c->stype.release(); c->hnew.release(); c->frecC.release(); c->frecD.release(); c->frecE.release(); c->frec.release(); c->drec.release(); c->v_true.release(); c->B_true.release(); c->twas.release(); c->forc_tab.release();
     c->s_gradh.release(); c->s_divv.release(); c->s_dvdx.release(); c->s_alpha3.release(); c->s_divcurlB.release(); c->s_fxyzu.release(); c->s_dB.release();
     c->s_ibin.release(); c->s_ibinold.release(); c->s_wake.release(); c->s_ibinnew.release(); c->s_gsoft.release(); c->s_tstop.release(); c->s_dustfrac.release(); c->dustfrac.release(); c->tstop.release(); c->gacc.release(); c->s_divvf.release(); c->s_poten.release(); c->s_divBsymm.release(); c->s_nneigh.release();
     c->cpl.release(); c->cellflag.release(); c->cellid_scan.release(); c->cells.release(); c->groups.release(); c->cellkeys.release(); c->nodes.release(); c->nodeflag.release();

@@ -21,6 +21,9 @@ struct StepArgs {
     double *xyzh, *v, *vpred, *f, *B, *Bpred, *dB, *eos_vars; float *divcurlv, *alphaind; const int8_t *iphase;
     double hfact, dt, hdt; double massoftype[SPHGPU_MAXTYPES];
     double *red;       // [0] errmax (as ordered bits), [1] v2mean sum, [2] np
+    // individual timesteps (step_leapfrog.f90 with -DIND_TIMESTEPS): every particle sits at its own half step twas(i)
+    int ind; double timei; double *twas; int8_t *ibin, *ibin_old, *ibin_wake; int8_t *iphase_w;
+    int nbinmax; double thdt[32], ttwas[32];      // ibin_dts(ithdt,:) and ibin_dts(ittwas,:) (:74-79, :157-164)
 };
 
 __device__ __forceinline__ bool dead(double h) { return h < DBL_MIN; }     // isdead_or_accreted (part.F90:931)
@@ -31,9 +34,11 @@ __global__ void k_predict(const StepArgs a)
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
         if (dead(a.xyzh[4 * i + 3])) continue;
         const int itype = abs((int)a.iphase[i]);
+        if (a.ind && a.iphase[i] > 0) a.ibin_old[i] = a.ibin[i];                    // only required for ibin_neigh in force (:195)
         if (itype == IBOUNDARY) continue;
-        for (int k = 0; k < a.nvu; k++) a.v[a.nvu * i + k] += a.hdt * a.f[a.nvu * i + k];
-        if (a.mhd && itype == IGAS) for (int k = 0; k < 4; k++) a.B[4 * i + k] += a.hdt * a.dB[4 * i + k];
+        const double hdt = a.ind ? a.twas[i] - a.timei : a.hdt;                      // :199 synchronise to the particle's own half step
+        for (int k = 0; k < a.nvu; k++) a.v[a.nvu * i + k] += hdt * a.f[a.nvu * i + k];
+        if (a.mhd && itype == IGAS) for (int k = 0; k < 4; k++) a.B[4 * i + k] += hdt * a.dB[4 * i + k];
     }
 }
 
@@ -63,9 +68,10 @@ __global__ void k_predict_sph(const StepArgs a)
         const double dhdrhoi = -h / (3. * rhoi);                                        // part.F90:791
         const double hnew = h - a.dt * dhdrhoi * rhoi * (double)a.divcurlv[i];           // :332
         a.xyzh[4 * i + 3] = hnew;
-        for (int k = 0; k < a.nvu; k++) a.vpred[a.nvu * i + k] = a.v[a.nvu * i + k] + a.hdt * a.f[a.nvu * i + k];
+        const double hdt = a.ind ? a.timei - a.twas[i] : a.hdt;                      // :341 interpolate to the end time
+        for (int k = 0; k < a.nvu; k++) a.vpred[a.nvu * i + k] = a.v[a.nvu * i + k] + hdt * a.f[a.nvu * i + k];
         if (a.mhd) {
-            if (itype == IGAS) for (int k = 0; k < 4; k++) a.Bpred[4 * i + k] = a.B[4 * i + k] + a.hdt * a.dB[4 * i + k];
+            if (itype == IGAS) for (int k = 0; k < 4; k++) a.Bpred[4 * i + k] = a.B[4 * i + k] + hdt * a.dB[4 * i + k];
             else for (int k = 0; k < 4; k++) a.Bpred[4 * i + k] = a.B[4 * i + k];
         }
         if (a.nalpha >= 2) {                                                             // Cullen & Dehnen (2010) switch, :378-389
@@ -121,6 +127,62 @@ __global__ void k_correct(const StepArgs a)
     }
     errmax = block_max(errmax, sh); v2sum = block_sum(v2sum, sh); np = block_sum(np, sh);
     if (threadIdx.x == 0) { atomic_max_pos(&a.red[0], errmax); atomicAdd(&a.red[1], v2sum); atomicAdd(&a.red[2], np); }
+}
+
+// corrector with individual timesteps (step_leapfrog.f90:470-560): active particles finish their step and move to the half step of
+// their NEW bin, everybody is synchronised to the current time, flagged neighbours are woken into the bin of the particle that woke them
+__global__ void k_correct_ind(const StepArgs a)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (dead(a.xyzh[4 * i + 3])) continue;
+        const int itype = abs((int)a.iphase[i]);
+        if (itype == IBOUNDARY) continue;
+        double tw = a.twas[i];
+        if (a.iphase[i] > 0) {
+            a.ibin_wake[i] = 0;                                                      // cannot wake active particles
+            const double dti = (a.timei - tw) + a.thdt[a.ibin[i]];
+            for (int k = 0; k < a.nvu; k++) a.v[a.nvu * i + k] += dti * a.f[a.nvu * i + k];
+            if (a.mhd && itype == IGAS) for (int k = 0; k < 4; k++) a.B[4 * i + k] += dti * a.dB[4 * i + k];
+            tw += dti;
+        }
+        const double hdti = a.timei - tw;                                            // synchronise all particles
+        for (int k = 0; k < a.nvu; k++) a.v[a.nvu * i + k] += hdti * a.f[a.nvu * i + k];
+        if (a.mhd && itype == IGAS) for (int k = 0; k < 4; k++) a.B[4 * i + k] += hdti * a.dB[4 * i + k];
+        if (a.ibin_wake[i] > a.ibin[i]) {                                            // wake inactive particles for the next step
+            const int w = min(a.nbinmax, (int)a.ibin_wake[i]);
+            tw = a.ttwas[w];
+            a.ibin[i] = (int8_t)w;
+            a.ibin_wake[i] = 0;
+        }
+        a.twas[i] = tw;
+    }
+}
+
+// set_active_particles (utils_indtimesteps.f90:114-178): iphase carries the activity flag of this (sub)step
+__global__ void k_set_active(int64_t n, const double *__restrict__ xyzh, int8_t *__restrict__ iphase, int8_t *__restrict__ ibin, int nbinmax, int istepfrac,
+                             unsigned long long *cnt)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool alive = false, act = false;
+    if (i < n && !dead(xyzh[4 * i + 3])) {
+        alive = true;
+        const int itype = abs((int)iphase[i]);
+        if (itype == IBOUNDARY) ibin[i] = 0;                                        // boundary particles are never active
+        const int b = ibin[i];
+        if (b > nbinmax) atomicMax(&cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_STATE);
+        act = b <= nbinmax && (istepfrac % (1 << (nbinmax - b))) == 0;
+        iphase[i] = (int8_t)(act ? itype : -itype);
+    }
+    const unsigned ma = __ballot_sync(FULLMASK, act), ml = __ballot_sync(FULLMASK, alive);
+    if (lane_id() == 0) { if (ma) atomicAdd(&cnt[0], (unsigned long long)__popc(ma)); if (ml) atomicAdd(&cnt[1], (unsigned long long)__popc(ml)); }
+}
+__global__ void k_init_step(int64_t n, const int8_t *__restrict__ iphase, int8_t *__restrict__ ibin, double *__restrict__ twas, double time, double dtmax,
+                            int nbinmax, int reset)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (reset) ibin[i] = (abs((int)iphase[i]) == IBOUNDARY) ? (int8_t)0 : (int8_t)nbinmax;       // step_leapfrog.f90:58-64
+    twas[i] = time + 0.5 * dtmax / (double)(1 << ibin[i]);                                        // :69-72
 }
 
 // not converged (step_leapfrog.f90:651-701): the new v becomes the prediction, v goes back to the half step
@@ -249,7 +311,7 @@ int sphgpu_step_resident(sphgpu_ctx *c, double dtsph, double tolv, sphgpu_step_o
     if (!c || !(dtsph > 0.)) return SPHGPU_ERR_ARG;
     CUDA_TRY(c, cudaSetDevice(c->device));
     const sphgpu_params &p = c->hp.p;
-    if (p.ind_timesteps) { c->err = "step: individual timesteps are integrated by the host (sphgpu_derivs); this routine is the global-timestep leapfrog"; return SPHGPU_ERR_ARG; }
+    if (p.ind_timesteps) { c->err = "step: this is the global-timestep leapfrog; with ind_timesteps use sphgpu_step_ind_resident"; return SPHGPU_ERR_ARG; }
     // a decomposed set (dist.cu) integrates its owned particles; the ghosts behind them are refreshed inside every derivs
     if (c->nghost > 0 && !c->dist) { c->err = "step: the context holds ghost particles of a host-driven halo exchange; use sphgpu_dist_step"; return SPHGPU_ERR_STATE; }
     const int64_t n = c->dist ? c->nlocal : c->npart;
@@ -311,6 +373,100 @@ int sphgpu_step_resident(sphgpu_ctx *c, double dtsph, double tolv, sphgpu_step_o
     CUDA_TRY(c, cudaStreamSynchronize(st));
     CUDA_TRY(c, cudaGetLastError());
     if (out) { memset(out, 0, sizeof *out); out->dtcourant = sc.dtcourant; out->dtforce = sc.dtforce; out->dterr = dterr; out->errmax = errmax; out->its = its; out->scalars = sc; }
+    return SPHGPU_OK;
+}
+
+// ---- individual timesteps ---------------------------------------------------------------------------------------------------------
+// init_step (step_leapfrog.f90:57-80): at time 0 every particle starts in the finest bin; twas = the half step of each particle's bin
+int sphgpu_init_step_resident(sphgpu_ctx *c, double time, double dtmax, int nbinmax)
+{
+    if (!c || !(dtmax > 0.) || nbinmax < 0 || nbinmax > 30) return SPHGPU_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int64_t n = c->dist ? c->nlocal : c->npart;
+    if (n <= 0) return SPHGPU_ERR_STATE;
+    CUDA_TRY(c, c->twas.ensure(n));
+    k_init_step<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->iphase.p, c->ibin.p, c->twas.p, time, dtmax, nbinmax, time < DBL_MIN ? 1 : 0);
+    c->launches++;
+    c->nbinmax = nbinmax;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SPHGPU_OK;
+}
+
+// set_active_particles (utils_indtimesteps.f90:114-178) on the resident state; also hands nbinmax, istepfrac and the resulting ibinnow to
+// the force pass (what sphgpu_set_timestep_bins does for a host-driven run)
+int sphgpu_set_active_particles_resident(sphgpu_ctx *c, int nbinmax, int istepfrac, int64_t *nactive, int64_t *nalive)
+{
+    if (!c || nbinmax < 0 || nbinmax > 30 || istepfrac < 0) return SPHGPU_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int64_t n = c->dist ? c->nlocal : c->npart;
+    if (n <= 0) return SPHGPU_ERR_STATE;
+    CUDA_TRY(c, c->counters.ensure(CNT_COUNT));
+    CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    k_set_active<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->xyzh.p, c->iphase.p, c->ibin.p, nbinmax, istepfrac, c->counters.p);
+    c->launches++;
+    unsigned long long h[2];
+    CUDA_TRY(c, cudaMemcpyAsync(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long err = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&err, c->counters.p + CNT_ERR, sizeof err, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (err) { c->err = "set_active_particles: timestep bin exceeds max bins"; return SPHGPU_ERR_STATE; }
+    int ibinnow = nbinmax;
+    for (int i = 0; ibinnow == nbinmax && i < nbinmax; i++) if (istepfrac % (1 << (nbinmax - i)) == 0) ibinnow = i;
+    c->nbinmax = nbinmax; c->ibinnow = ibinnow; c->istepfrac = istepfrac;
+    c->tree_valid = false;                                           // the active counts of the cells changed
+    if (nactive) *nactive = (int64_t)h[0];
+    if (nalive) *nalive = (int64_t)h[1];
+    return SPHGPU_OK;
+}
+
+// step (step_leapfrog.f90:95-760) with -DIND_TIMESTEPS: dtsph is the smallest timestep dtmax / 2^nbinmax, t the time at the start of it.
+// The force pass moves active particles between bins; out->scalars.nbinmaxnew is the new nbinmax (timestep_ind module variable).
+int sphgpu_step_ind_resident(sphgpu_ctx *c, double t, double dtsph, double dtmax, sphgpu_step_out *out)
+{
+    if (!c || !(dtsph > 0.) || !(dtmax > 0.)) return SPHGPU_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const sphgpu_params &p = c->hp.p;
+    if (!p.ind_timesteps) { c->err = "step_ind: the context was not created with ind_timesteps"; return SPHGPU_ERR_ARG; }
+    if (c->nghost > 0 && !c->dist) { c->err = "step_ind: the context holds ghost particles of a host-driven halo exchange"; return SPHGPU_ERR_STATE; }
+    const int64_t n = c->dist ? c->nlocal : c->npart;
+    const int nvu = c->hp.nvu;
+    if (n <= 0 || c->twas.cap < (size_t)n) { c->err = "step_ind: sphgpu_init_step_resident has not been called"; return SPHGPU_ERR_STATE; }
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, c->v_true.ensure((size_t)nvu * n)); if (p.mhd) CUDA_TRY(c, c->B_true.ensure(4 * (size_t)n));
+    CUDA_TRY(c, cudaMemcpyAsync(c->v_true.p, c->vxyzu.p, sizeof(double) * nvu * n, cudaMemcpyDeviceToDevice, st));
+    if (p.mhd) CUDA_TRY(c, cudaMemcpyAsync(c->B_true.p, c->Bevol.p, sizeof(double) * 4 * n, cudaMemcpyDeviceToDevice, st));
+    StepArgs a; memset(&a, 0, sizeof a);
+    a.n = n; a.nvu = nvu; a.mhd = p.mhd; a.nalpha = c->hp.nalpha; a.multitype = 1;
+    a.hfact = p.hfact; a.dt = dtsph; a.hdt = 0.5 * dtsph; a.ind = 1; a.timei = t;
+    for (int k = 0; k < SPHGPU_MAXTYPES; k++) a.massoftype[k] = p.massoftype[k];
+    const double time_now = t + dtsph;
+    for (int b = 0; b <= 30; b++) {                                  // ibin_dts (:74-79, :157-164)
+        const double dtb = dtmax / (double)(1ull << b);
+        a.thdt[b] = 0.5 * dtb;
+        a.ttwas[b] = ((double)(long long)(time_now * (1.0 / dtb)) + 0.5) * dtb;
+    }
+    auto bind = [&]() {
+        a.xyzh = c->xyzh.p; a.v = c->v_true.p; a.vpred = c->vxyzu.p; a.f = c->fxyzu.p; a.B = c->B_true.p; a.Bpred = c->Bevol.p; a.dB = c->dBevol.p;
+        a.eos_vars = c->eos_vars.p; a.divcurlv = c->divcurlv.p; a.alphaind = c->alphaind.p; a.iphase = c->iphase.p; a.red = c->dscal.p + 16;
+        a.twas = c->twas.p; a.ibin = c->ibin.p; a.ibin_old = c->ibin_old.p; a.ibin_wake = c->ibin_wake.p;
+    };
+    bind();
+    SL(c, k_predict, a);
+    SL(c, k_drift, a);
+    a.timei = time_now;
+    SL(c, k_predict_sph, a);
+    c->tree_valid = false;
+    sphgpu_scalars sc;
+    TRY(c->dist ? sphgpu_dist_hook_derivs(c, 1, dtsph, &sc) : sphgpu_derivs_resident(c, 1, dtsph, &sc));
+    bind();
+    c->nbinmax = (int)sc.nbinmaxnew;                                 // force.F90:792
+    a.nbinmax = c->nbinmax;
+    SL(c, k_correct_ind, a);
+    CUDA_TRY(c, cudaMemcpyAsync(c->vxyzu.p, c->v_true.p, sizeof(double) * nvu * n, cudaMemcpyDeviceToDevice, st));
+    if (p.mhd) CUDA_TRY(c, cudaMemcpyAsync(c->Bevol.p, c->B_true.p, sizeof(double) * 4 * n, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    CUDA_TRY(c, cudaGetLastError());
+    if (out) { memset(out, 0, sizeof *out); out->dtcourant = sc.dtcourant; out->dtforce = sc.dtforce; out->dterr = 1.e29; out->errmax = 0.; out->its = 1; out->scalars = sc; }
     return SPHGPU_OK;
 }
 

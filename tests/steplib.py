@@ -119,3 +119,112 @@ def energies(part):
     out["mtot"] = float(np.sum(m))
     out["com"] = np.sum(m[:, None] * x[:, :3], axis=0) / out["mtot"]
     return out
+
+
+# ---- individual timesteps (-DIND_TIMESTEPS): step_leapfrog.f90:57-80, :157-164, :183-235, :307-400, :470-560 + utils_indtimesteps.f90 ----
+def get_dt(dtmax, ibin):
+    return dtmax / 2. ** np.asarray(ibin, dtype=np.float64)          # utils_indtimesteps.f90:45-51
+
+
+def init_step_ind(part, time, dtmax, nbinmax):
+    """init_step (step_leapfrog.f90:57-80): at t = 0 every particle starts in the finest bin (boundary particles in bin 0); twas =
+    the half step of the particle's own bin.  Returns twas."""
+    itype = np.abs(part.iphase.astype(np.int64))
+    if time < TINY:
+        part.ibin[:] = nbinmax
+        part.ibin[itype == IBOUNDARY] = 0
+    return time + 0.5 * get_dt(dtmax, part.ibin)
+
+
+def set_active_particles(part, nbinmax, istepfrac):
+    """utils_indtimesteps.f90:114-178: active iff mod(istepfrac, 2**(nbinmax - ibin)) == 0; returns (nactive, ibinnow)"""
+    itype = np.abs(part.iphase.astype(np.int64))
+    live = ~(part.xyzh[:, 3] < TINY)
+    part.ibin[live & (itype == IBOUNDARY)] = 0
+    act = (istepfrac % (2 ** (nbinmax - part.ibin.astype(np.int64)))) == 0
+    part.iphase[live] = np.where(act[live], itype[live], -itype[live]).astype(np.int8)
+    ibinnow, i = nbinmax, 0
+    while ibinnow == nbinmax and i < nbinmax:
+        if istepfrac % (2 ** (nbinmax - i)) == 0:
+            ibinnow = i
+        i += 1
+    return int(np.sum(act & live)), ibinnow
+
+
+def step_leapfrog_ind(o, part, twas, t, dtsph, dtmax, nbinmax, ibinnow, istepfrac):
+    """one call of step() with individual timesteps; returns (force scalars, new nbinmax).  part.iphase carries the activity flags
+    set_active_particles gave it; twas is updated in place."""
+    p = part.params
+    itype = np.abs(part.iphase.astype(np.int64))
+    live = ~(part.xyzh[:, 3] < TINY)
+    nb = live & (itype != IBOUNDARY)
+    gas = nb & (itype == IGAS)
+    active = part.iphase > 0
+    pm = np.array([p.massoftype[k] for k in range(8)])[itype]
+    v, f, B, dB = part.vxyzu, part.fxyzu, part.Bevol, part.dBevol
+    timei = t
+    # twas of every bin at the end of this step, for particles that are woken up (:157-164)
+    time_now = timei + dtsph
+    bins = np.arange(31)
+    tdt = get_dt(dtmax, bins)
+    ttwas = (np.floor(time_now * (1. / tdt)).astype(np.int64) + 0.5) * tdt
+    # predictor (:183-235): everybody goes to its own half step
+    part.ibin_old[live & active] = part.ibin[live & active]
+    hdti = twas - timei
+    v[nb] += hdti[nb, None] * f[nb]
+    if p.mhd:
+        B[gas] += hdti[gas, None] * dB[gas]
+    part.xyzh[live, :3] += dtsph * v[live, :3]                     # substep_sph
+    timei += dtsph
+    # predict_sph (:307-400)
+    vtrue, Btrue = v.copy(), B.copy()
+    h = part.xyzh[:, 3]
+    rho = pm * (p.hfact / np.abs(h)) ** 3
+    dhdrho = -h / (3. * rho)
+    hnew = h - dtsph * dhdrho * rho * part.divcurlv[:, 0].astype(np.float64)
+    part.xyzh[nb, 3] = hnew[nb]
+    hdti = timei - twas
+    vpred, Bpred = vtrue.copy(), Btrue.copy()
+    vpred[nb] = vtrue[nb] + hdti[nb, None] * f[nb]
+    if p.mhd:
+        Bpred[gas] = Btrue[gas] + hdti[gas, None] * dB[gas]
+    if not p.const_av:
+        cs = part.eos_vars[:, 1]
+        tdecay1 = 0.1 * cs / part.xyzh[:, 3]
+        ddenom = 1. / (1. + dtsph * tdecay1)
+        aloc = part.alphaind[:, 1].astype(np.float64)
+        a1 = part.alphaind[:, 0].astype(np.float64)
+        new = np.where(a1 < aloc, aloc, (a1 + dtsph * aloc * tdecay1) * ddenom).astype(np.float32)
+        part.alphaind[nb, 0] = new[nb]
+    part.vxyzu[:], part.Bevol[:] = vpred, Bpred
+    # derivs(1): the force pass moves the active particles between bins and flags the neighbours to wake (force.F90:1346-1358, :3272-3310)
+    o.build_tree(part)
+    o.densityiterate(part, 1)
+    part.params.set_boundaries_to_active = 0
+    o.set_params(part.params)
+    o.cons2prim(part)
+    sc = o.force(part, 1, dtsph, nbinmax=nbinmax, ibinnow=ibinnow, istepfrac=istepfrac)
+    nbinmax_new = int(sc.nbinmaxnew)
+    # corrector (:470-560)
+    f, dB = part.fxyzu, part.dBevol
+    act = nb & active
+    part.ibin_wake[act] = 0
+    hd = timei - twas
+    dti = hd + 0.5 * get_dt(dtmax, part.ibin)
+    vtrue[act] += dti[act, None] * f[act]
+    if p.mhd:
+        ga = act & (itype == IGAS)
+        Btrue[ga] += dti[ga, None] * dB[ga]
+    twas[act] += dti[act]
+    hd = timei - twas                                              # synchronise all particles
+    vtrue[nb] += hd[nb, None] * f[nb]
+    if p.mhd:
+        Btrue[gas] += hd[gas, None] * dB[gas]
+    wake = nb & (part.ibin_wake > part.ibin)
+    if np.any(wake):
+        w = np.minimum(part.ibin_wake[wake].astype(np.int64), nbinmax_new)
+        twas[wake] = ttwas[w]
+        part.ibin[wake] = w.astype(np.int8)
+        part.ibin_wake[wake] = 0
+    part.vxyzu[:], part.Bevol[:] = vtrue, Btrue
+    return sc, nbinmax_new

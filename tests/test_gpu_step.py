@@ -79,3 +79,102 @@ def test_selfgravitating_sphere_20_steps():
     po, pg, hist = run_pair(part, 20)
     check_hist(hist, tol=1e-9)
     assert hist[-1][1].epot < 0.
+
+
+# ---- individual timesteps -------------------------------------------------------------------------------------------------------------
+class _OracleInd:
+    """the evolve.f90 / step_leapfrog.f90 sequence with -DIND_TIMESTEPS on the CPU oracle (tests/steplib.py)"""
+
+    def __init__(self, part):
+        self.part = part
+        self.o = Oracle(part.params)
+
+    def first_derivs(self):
+        o, part = self.o, self.part
+        o.build_tree(part); o.densityiterate(part, 1); part.params.set_boundaries_to_active = 0; o.set_params(part.params); o.cons2prim(part)
+        return o.force(part, 1, 0.0, nbinmax=0, ibinnow=0, istepfrac=0)
+
+    def init_step(self, time, dtmax, nbinmax):
+        self.twas = steplib.init_step_ind(self.part, time, dtmax, nbinmax)
+
+    def substep(self, t, dt, dtmax, nbinmax, istepfrac):
+        nactive, ibinnow = steplib.set_active_particles(self.part, nbinmax, istepfrac)
+        sc, nbnew = steplib.step_leapfrog_ind(self.o, self.part, self.twas, t, dt, dtmax, nbinmax, ibinnow, istepfrac)
+        return nactive, nbnew, sc
+
+    def state(self):
+        return self.part
+
+
+class _GpuInd:
+    def __init__(self, part):
+        from phantom_b200.api import SphGpu
+        self.part = part
+        self.g = SphGpu(part.params.copy())
+        self.g.upload(part)
+
+    def first_derivs(self):
+        self.g.set_timestep_bins(0, 0, 0)
+        return self.g.derivs_resident(1)
+
+    def init_step(self, time, dtmax, nbinmax):
+        self.g.init_step_resident(time, dtmax, nbinmax)
+
+    def substep(self, t, dt, dtmax, nbinmax, istepfrac):
+        nactive, nalive = self.g.set_active_particles_resident(nbinmax, istepfrac)
+        out = self.g.step_ind_resident(t, dt, dtmax)
+        return nactive, int(out.scalars.nbinmaxnew), out.scalars
+
+    def state(self):
+        self.g.download(self.part)
+        return self.part
+
+
+def _evolve_ind(b, dtmax, nsub):
+    """evolve.f90:196-203 + evolve_utils.F90:65-87: istepfrac, time and nbinmax bookkeeping around step()"""
+    sc = b.first_derivs()
+    nbinmax = int(sc.nbinmaxnew)
+    b.init_step(0., dtmax, nbinmax)
+    istepfrac, t, log = 0, 0., []
+    for _ in range(nsub):
+        dt = dtmax / 2 ** nbinmax
+        istepfrac += 1
+        nactive, nbnew, sc = b.substep(t, dt, dtmax, nbinmax, istepfrac)
+        t = istepfrac / 2. ** nbinmax * dtmax
+        log.append((istepfrac, nbinmax, nactive, nbnew, int(sc.npairs_force)))
+        if nbnew != nbinmax:                                           # change_nbinmax (utils_indtimesteps.f90:186-222)
+            if nbnew < nbinmax:
+                assert istepfrac % 2 ** (nbinmax - nbnew) == 0
+                istepfrac //= 2 ** (nbinmax - nbnew)
+            else:
+                istepfrac *= 2 ** (nbnew - nbinmax)
+            nbinmax = nbnew
+        if istepfrac == 2 ** nbinmax:
+            break
+    return log, t
+
+
+def test_individual_timestep_stepping_matches_oracle():
+    """turbulent box with -DIND_TIMESTEPS: set_active_particles + step() per smallest timestep until the bins synchronise (or 24
+    substeps), on the device (sphgpu_set_active_particles_resident, sphgpu_step_ind_resident) and on the oracle: the same active counts,
+    bin populations and pair counts every substep, positions / velocities / h to 1e-10"""
+    part = setups.setup_turb(nx=14, ind_timesteps=True)
+    part.alphaind[:, 0] = 1.0
+    rng = setups.Ran2(-8642)
+    part.xyzh[:, :3] += 0.15 / 14 * (rng.draw(3 * part.npart).reshape(-1, 3) - 0.5)      # break the lattice: a spread of timesteps
+    dtmax = 0.02
+    part.params.dtmax = dtmax
+    po, pg = part.copy(), part.copy()
+    bo, bg = _OracleInd(po), _GpuInd(pg)
+    log_o, t_o = _evolve_ind(bo, dtmax, 24)
+    log_g, t_g = _evolve_ind(bg, dtmax, 24)
+    assert log_g == log_o, (log_g[:6], log_o[:6])
+    assert t_g == t_o and len(log_o) >= 4
+    assert len({l[2] for l in log_o}) > 1                                # the number of active particles does change between substeps
+    so, sg = bo.state(), bg.state()
+    assert np.array_equal(sg.ibin, so.ibin) and np.array_equal(sg.iphase, so.iphase)
+    dx = sg.xyzh[:, :3] - so.xyzh[:, :3]
+    assert np.max(np.abs(dx - np.round(dx))) < 1e-10
+    assert np.max(np.abs(sg.xyzh[:, 3] - so.xyzh[:, 3]) / so.xyzh[:, 3]) < 1e-9
+    vs = np.sqrt(np.mean(so.vxyzu[:, :3] ** 2))
+    assert np.max(np.abs(sg.vxyzu[:, :3] - so.vxyzu[:, :3])) < 1e-10 * vs
