@@ -174,7 +174,7 @@ __global__ void k_set_active(int64_t n, const double *__restrict__ xyzh, int8_t 
         iphase[i] = (int8_t)(act ? itype : -itype);
     }
     const unsigned ma = __ballot_sync(FULLMASK, act), ml = __ballot_sync(FULLMASK, alive);
-    if (lane_id() == 0) { if (ma) atomicAdd(&cnt[0], (unsigned long long)__popc(ma)); if (ml) atomicAdd(&cnt[1], (unsigned long long)__popc(ml)); }
+    if (lane_id() == 0) { if (ma) atomicAdd(&cnt[2], (unsigned long long)__popc(ma)); if (ml) atomicAdd(&cnt[3], (unsigned long long)__popc(ml)); }
 }
 __global__ void k_init_step(int64_t n, const int8_t *__restrict__ iphase, int8_t *__restrict__ ibin, double *__restrict__ twas, double time, double dtmax,
                             int nbinmax, int reset)
@@ -405,7 +405,7 @@ int sphgpu_set_active_particles_resident(sphgpu_ctx *c, int nbinmax, int istepfr
     k_set_active<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->xyzh.p, c->iphase.p, c->ibin.p, nbinmax, istepfrac, c->counters.p);
     c->launches++;
     unsigned long long h[2];
-    CUDA_TRY(c, cudaMemcpyAsync(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(h, c->counters.p + 2, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     unsigned long long err = 0;
     CUDA_TRY(c, cudaMemcpyAsync(&err, c->counters.p + CNT_ERR, sizeof err, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
