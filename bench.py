@@ -159,7 +159,7 @@ def run_reference(args, rank, world):
     threads = o.max_threads()
     # bounded sample: one derivs at full size is timed first (it doubles as a warm-up step); the box is halved only if
     # (steps + warmup) such steps would not fit in ~150 s (cost is linear in N)
-    nx = args.nx
+    nx = nx_asked = args.nx
     t1 = time.perf_counter()
     o.derivs(part)
     t_step = time.perf_counter() - t1
@@ -184,7 +184,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "particle-updates/s (tree+density+cons2prim+force)", "value": val, "unit": "particle-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl, "cpu_sample_nx": nx},
+        "config": dict({"workload": wl}, **({"cpu_sample_nx": nx} if nx != nx_asked else {})),
         "cpu_baseline": {"value": val, "unit": "particle-updates/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -470,6 +470,41 @@ def main():
             gb.dist_finalize()
         del gb, db, pb
 
+    # ---------------- N = 1 extras: an evolved (disordered) state, and parity on an MHD configuration ----------------
+    if args.extras and world == 1 and args.evolve == 0:
+        ge = SphGpu(part.params.copy(), device=local)
+        pe = part.copy()
+        ge.upload(pe)
+        sc0 = ge.derivs_resident(1)
+        dte = min(sc0.dtcourant, sc0.dtforce)
+        for _ in range(20):
+            oe = ge.step_resident(dte)
+            dte = min(oe.dtcourant, oe.dtforce, oe.dterr)
+        ge.download(pe)
+        pred = pe.copy()
+        pred.xyzh[:, 3] = pe.xyzh[:, 3] * (1. + dte * pe.divcurlv[:, 0].astype(np.float64) / 3.)
+        te, its = 0.0, 0.0
+        for it in range(2 + 5):
+            ge.upload(pred, F_XYZH)
+            sce = ge.derivs_resident(1)
+            if it >= 2:
+                te += sum(ge.timings_ms().values())
+                its = sce.nrhocalc / max(sce.np, 1)
+        line["evolved_state"] = {"what": "the same box after 20 leapfrog steps on the device (Mach 5), every timed derivs(1) starting from the h "
+                                         "predicted for the next step, so that the h-rho iteration does real work",
+                                 "ms_per_step": te / 5, "value": n * 5 / (te * 1e-3), "unit": "particle-updates/s", "its_mean": its,
+                                 "candidates_per_group": sce.trialmean, "neighbours_mean": sce.actualmean}
+        del ge
+        if not args.no_cpu_baseline:
+            from phantom_b200 import setups
+            from oraclelib import Oracle
+            pm = setups.setup_orstang(nx=48)
+            pm.alphaind[:, 0] = 1.0
+            pmc = pm.copy()
+            om = Oracle(pmc.params)
+            sdm, sfm = om.derivs(pmc)
+            line["parity_mhd"] = dict(parity_block(SphGpu, pm, pmc, sdm, sfm, local), workload="Orszag-Tang vortex, MHD + div-B cleaning (BASELINE configs[2] at reduced size)")
+
     # ---------------- CPU baseline (oracle port) beside it: rank 0, N=1 ----------------
     if world == 1 and not args.no_cpu_baseline and rank == 0:
         from oraclelib import Oracle
@@ -497,6 +532,8 @@ def main():
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and line.get("parity_mhd") and not line["parity_mhd"]["ok"]:
+        raise SystemExit("bench.py: GPU and CPU arms disagree on the MHD configuration: %s" % json.dumps(line["parity_mhd"]))
     if rank == 0 and line.get("parity") and not line["parity"]["ok"]:
         raise SystemExit("bench.py: GPU and CPU arms disagree beyond the north_star tolerances: %s" % json.dumps(line["parity"]))
 
