@@ -2,12 +2,12 @@
 # A/B builds of the pair kernels with different launch bounds / pairs per trip: builds libsphgpu_<tag>.so variants (CPU side)
 # usage: tools/variants.sh build   |   tools/variants.sh run   (run = on the GPU box: times each variant with bench.py)
 cd "$(dirname "$0")/.."
-VARIANTS=("base:" "b512:-DDENS_ROUND_BIG=512 -DFORCE_ROUND_BIG=512" "b576:-DDENS_ROUND_BIG=576 -DFORCE_ROUND_BIG=576" "d512:-DDENS_ROUND_BIG=512")   # round 2: a big-round instantiation that keeps 3 density CTAs/SM
+VARIANTS=("base:")   # add "tag:-Dflags" entries to A/B a build.  Round 2 sets, both measured and rejected: 512/576-candidate rounds (profiles/r02_disordered_states_ab.txt); next-trip prefetch of the force record head at 4 / 3 CTAs per SM (force 1.38 -> 1.68 / 1.52 ms)
 if [ "$1" == "build" ]; then
   mkdir -p build/variants
   for v in "${VARIANTS[@]}"; do
     tag=${v%%:*}; flags=${v#*:}
-    ( cd phantom_b200/csrc && for f in force density neigh; do /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -ccbin /usr/bin/g++ -Xcompiler -fPIC,-O2 --expt-relaxed-constexpr $flags -c $f.cu -o ../../build/variants/${f}_$tag.o & done; wait
+    ( cd phantom_b200/csrc && for f in ${VARIANT_FILES:-force density neigh}; do /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -ccbin /usr/bin/g++ -Xcompiler -fPIC,-O2 --expt-relaxed-constexpr $flags -c $f.cu -o ../../build/variants/${f}_$tag.o & done; wait
       /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -shared -o ../../build/variants/libsphgpu_$tag.so sphgpu.o tree.o ../../build/variants/density_$tag.o ../../build/variants/force_$tag.o cons2prim.o ../../build/variants/neigh_$tag.o halo.o gravity.o step.o dist.o -ldl )
     echo built $tag
   done
