@@ -12,6 +12,10 @@
 #define FLOP_FORCE_PAIR_ISOTHERMAL 110
 #define FLOP_FORCE_PAIR_MHD_EXTRA 150  /* force.F90:1428-1444,1626-1684 */
 #define FLOP_FORCE_EPILOGUE       150  /* finish_cell_and_store_results (force.F90:2939-3223) */
+#define FLOP_FORCE_PAIR_GRAV_EXTRA 30  /* softened gravity of SPH-neighbour pairs (force.F90:1303-1339) */
+#define FLOP_FORCE_PAIR_DRAG_EXTRA 80  /* two-fluid drag pair incl. reconstruct_dv and get_ts (force.F90:1864-1970) */
+#define FLOP_GRAV_P2P_PAIR         25  /* Newtonian m/r^2 pair outside both kernels (force.F90:1992-2053) */
+#define FLOP_GRAV_M2L             130  /* compute_M2L per accepted node pair (kdtree.F90:1702-1781) */
 #define BYTES_TREE_PER_PARTICLE   150  /* keys + sort passes + gather */
 #define BYTES_DENS_PER_PARTICLE   180  /* each array touched once */
 #define BYTES_DENS_MHD_EXTRA       48

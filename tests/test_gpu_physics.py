@@ -249,3 +249,26 @@ def test_turbulent_driving(correct_mean, ind_ts):
     g2.upload(p2); g2.forcing_resident(); g2.download(p2)
     scale = np.sqrt(np.mean(fdrive[active] ** 2))
     assert np.max(np.abs(p2.fxyzu[active, :3] - fdrive[active])) < 1e-12 * scale
+
+
+def test_gravity_pass_is_deterministic_and_tree_bitwise_repeatable():
+    """the level-synchronous gravity build accumulates node masses and centres of mass with double atomics, whose
+    order varies from run to run.  Two fresh contexts on the same sphere must still give the same tree topology, the same P2P / M2L
+    counts and forces equal to round-off (the pivots move by at most an ulp, which does not flip any particle across a split here)."""
+    part = setups.setup_random_sphere(n=6000)
+    part.alphaind[:, 0] = 0.5
+    runs = []
+    for _ in range(3):
+        pg = part.copy()
+        g = gpu(pg.params)
+        sc = g.derivs(pg)
+        rec, irec, ids = g.gravity_tree(pg.npart)
+        runs.append((pg, sc, rec, irec, ids))
+    p0, s0, r0, i0, d0 = runs[0]
+    fs = np.sqrt(np.mean(p0.fxyzu[:, :3] ** 2))
+    for pg, sc, rec, irec, ids in runs[1:]:
+        assert np.array_equal(irec, i0) and np.array_equal(ids, d0)                 # same topology, same particle order in the leaves
+        assert sc.npairs_gravity == s0.npairs_gravity and sc.nm2l == s0.nm2l and sc.npairs_force == s0.npairs_force
+        assert np.max(np.abs(rec - r0)) <= 1e-13 * np.max(np.abs(r0))               # node moments to round-off of the atomic sums
+        assert np.max(np.abs(pg.fxyzu[:, :3] - p0.fxyzu[:, :3])) <= 1e-12 * fs
+        assert np.array_equal(pg.xyzh, p0.xyzh)                                     # the SPH side has no atomics in its sums: bitwise

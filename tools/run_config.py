@@ -38,11 +38,28 @@ tsetup = time.time() - t0
 g = SphGpu(part.params.copy())
 if part.params.ind_timesteps:
     g.set_timestep_bins(0, 0, 0)
+peak = g.measure_fp64_peak()
+import re
+fc = {k: int(v) for k, v in re.findall(r"#define\s+(\w+)\s+(\d+)", open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "phantom_b200", "csrc",
+                                                                                      "roofline_constants.h")).read())}
+p = part.params
 g.upload(part)
 for r in range(reps):
     t = time.time(); sc = g.derivs_resident(1); wall = (time.time() - t) * 1e3
     nact = int(np.sum(part.iphase > 0))
+    kt, gt = g.kernel_timings_ms(), (g.gravity_timings_ms() if p.gravity else None)
+    # algorithmic flop of the pair kernels (roofline_constants.h x measured pair counts) against the FP64 peak measured on this device
+    fd = (fc["FLOP_DENS_PAIR_HYDRO"] + (fc["FLOP_DENS_PAIR_MHD_EXTRA"] if p.mhd else 0)) * sc.npairs_density + fc["FLOP_DENS_EPILOGUE"] * sc.nrhocalc
+    ff = ((fc["FLOP_FORCE_PAIR_ISOTHERMAL"] if p.isothermal else fc["FLOP_FORCE_PAIR_ADIABATIC"]) + (fc["FLOP_FORCE_PAIR_MHD_EXTRA"] if p.mhd else 0)
+          + (fc["FLOP_FORCE_PAIR_GRAV_EXTRA"] if p.gravity else 0)) * sc.npairs_force + fc["FLOP_FORCE_EPILOGUE"] * nact
+    roof = {"fp64_peak_tflops": round(peak, 2), "density_frac": round(fd / (kt["density"] * 1e-3) / 1e12 / peak, 4), "force_frac": round(ff / (kt["force"] * 1e-3) / 1e12 / peak, 4)}
+    if p.gravity and gt["p2p"] > 0:
+        roof["p2p_frac"] = round(fc["FLOP_GRAV_P2P_PAIR"] * sc.npairs_gravity / (gt["p2p"] * 1e-3) / 1e12 / peak, 4)
+        roof["tree_and_walk_ms"] = round(gt["total"] - gt["p2p"], 3)
+        roof["m2l_tflops_over_tree_and_walk"] = round(fc["FLOP_GRAV_M2L"] * sc.nm2l / ((gt["total"] - gt["p2p"]) * 1e-3) / 1e12, 3)
     print(json.dumps(dict(config=name, npart=part.npart, setup_s=round(tsetup, 1), wall_ms=round(wall, 2), updates_per_s=round(nact / (wall * 1e-3)),
-                          phases=g.timings_ms(), kernels=g.kernel_timings_ms(), gravity=g.gravity_timings_ms() if part.params.gravity else None,
-                          neigh_mean=sc.actualmean, neigh_max=sc.maxactual, trial_mean=sc.trialmean, trial_max=sc.maxtrial, its_mean=sc.nrhocalc / max(sc.np, 1), npairs_force=sc.npairs_force,
-                          npairs_gravity=sc.npairs_gravity, nm2l=sc.nm2l, dtcourant=sc.dtcourant, dtforce=sc.dtforce)), flush=True)
+                          phases={k: round(v, 3) for k, v in g.timings_ms().items()}, kernels={k: round(v, 3) for k, v in kt.items()},
+                          gravity={k: round(v, 3) for k, v in gt.items()} if gt else None, roofline=roof,
+                          neigh_mean=round(sc.actualmean, 2), neigh_max=sc.maxactual, trial_mean=round(sc.trialmean, 1), trial_max=sc.maxtrial,
+                          its_mean=round(sc.nrhocalc / max(sc.np, 1), 3), npairs_force=sc.npairs_force,
+                          npairs_gravity=sc.npairs_gravity, nm2l=sc.nm2l)), flush=True)
