@@ -285,7 +285,7 @@ __device__ __forceinline__ void atomic_max_pos(double *addr, double v) { atomicM
 
 // indices into ctx->counters (unsigned long long)
 enum { CNT_WORK = 0, CNT_ERR, CNT_ERRID, CNT_NPAIRS, CNT_NTRIAL, CNT_NCALC, CNT_NACT, CNT_MAXACT, CNT_MAXTRIAL, CNT_NP, CNT_NWALK, CNT_NLIVE, CNT_NBINMAX, CNT_NCHECKBIN, CNT_MULTITYPE, CNT_NSURV,
-       CNT_NGRAVPAIRS = 24, CNT_NM2L = 25, CNT_COUNT = 32 };
+       CNT_NGRAVPAIRS = 24, CNT_NM2L = 25, CNT_NCELLS = 26, CNT_CELLOVER = 27, CNT_COUNT = 32 };
 // indices into ctx->dscal (double)
 enum { DS_XMIN = 0, DS_YMIN, DS_ZMIN, DS_XMAX, DS_YMAX, DS_ZMAX, DS_DTCOURANT, DS_DTFORCE, DS_DTMINI, DS_DTMAXI, DS_RHOMAX, DS_HUSED, DS_HGROW, DS_COUNT = 32 };
 

@@ -434,12 +434,9 @@ int sphgpu_derivs(sphgpu_ctx *c, int icall, sphgpu_host_arrays *h, double dt, sp
     // ---- wave 1: what the tree needs
     if (icall != 2) { H2D(c->xyzh, h->xyzh, 4 * n); H2D(c->iphase, h->iphase, n); c->tree_valid = false; }
     CUDA_TRY(c, cudaEventRecord(c->cev[0], si));
-    // ---- wave 2: what density / cons2prim / force read
+    // ---- wave 2: what the density pass reads or writes (alphaind: it stores div a in the third column)
     H2D(c->vxyzu, h->vxyzu, (size_t)nvu * n); H2D(c->fxyzu, h->fxyzu, (size_t)nvu * n); H2D(c->fext, h->fext, 3 * n); H2D(c->alphaind, h->alphaind, 3 * n);
     if (p.mhd) { H2D(c->Bevol, h->Bevol, 4 * n); }
-    if (p.ind_timesteps) { H2D(c->ibin, h->ibin, n); H2D(c->ibin_old, h->ibin_old, n); H2D(c->ibin_wake, h->ibin_wake, n); }
-    // eos_vars always travels: cons2prim writes the rows igasP, ics, itemp only, the host's imu, iX, iZ, igamma must survive the download
-    H2D(c->eos_vars, h->eos_vars, 7 * n);
     auto upload_stored = [&]() -> int {      // arrays that keep their stored values for particles no pass writes
         H2D(c->gradh, h->gradh, (size_t)ng * n); H2D(c->divcurlv, h->divcurlv, n); H2D(c->dvdx, h->dvdx, 9 * n);
         if (p.mhd) H2D(c->divcurlB, h->divcurlB, 4 * n);
@@ -447,6 +444,11 @@ int sphgpu_derivs(sphgpu_ctx *c, int icall, sphgpu_host_arrays *h, double dt, sp
     };
     if (!all_active) TRY(upload_stored());
     CUDA_TRY(c, cudaEventRecord(c->cev[1], si));
+    // ---- wave 3: first read by cons2prim / force; travels while the density pass runs.
+    // eos_vars always goes: cons2prim writes the rows igasP, ics, itemp only, the host's imu, iX, iZ, igamma must survive the download
+    H2D(c->eos_vars, h->eos_vars, 7 * n);
+    if (p.ind_timesteps) { H2D(c->ibin, h->ibin, n); H2D(c->ibin_old, h->ibin_old, n); H2D(c->ibin_wake, h->ibin_wake, n); }
+    CUDA_TRY(c, cudaEventRecord(c->cev[5], si));
     // ---- passes
     cudaEventRecord(c->ev[0], c->stream);
     CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->cev[0], 0));
@@ -454,6 +456,7 @@ int sphgpu_derivs(sphgpu_ctx *c, int icall, sphgpu_host_arrays *h, double dt, sp
     if (all_active && c->nlive < n) {        // dead / accreted particles (h <= 0) among "all gas": their stored values must survive too
         TRY(upload_stored());
         CUDA_TRY(c, cudaEventRecord(c->cev[1], si));
+        CUDA_TRY(c, cudaEventRecord(c->cev[5], si));
     }
     cudaEventRecord(c->ev[1], c->stream);
     CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->cev[1], 0));
@@ -467,6 +470,7 @@ int sphgpu_derivs(sphgpu_ctx *c, int icall, sphgpu_host_arrays *h, double dt, sp
     D2H(c->xyzh, h->xyzh, 4 * n); D2H(c->gradh, h->gradh, (size_t)ng * n); D2H(c->dvdx, h->dvdx, 9 * n);
     if (p.mhd) D2H(c->divcurlB, h->divcurlB, 4 * n);
     if (p.dust) D2H(c->dustfrac, h->dustfrac, n);
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->cev[5], 0));
     TRY(cons2prim_run(c));
     cudaEventRecord(c->ev[3], c->stream);
     CUDA_TRY(c, cudaEventRecord(c->cev[3], c->stream));

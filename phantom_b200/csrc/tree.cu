@@ -90,11 +90,29 @@ __device__ __forceinline__ void hilbert_transpose(unsigned &x0, unsigned &x1, un
     x0 ^= t; x1 ^= t; x2 ^= t;
 }
 
-__global__ void k_keys(int64_t n, const double *__restrict__ xyzh, double x0, double y0, double z0, double inv_scale,
+// key normalisation computed per thread from the device bounding box (no host round trip): the periodic box when there is one
+// (stable across steps), else the particles' bounding box; cubic, slightly enlarged
+__device__ __forceinline__ void key_frame(const unsigned long long *bbox_enc, const DevParams &dp, double &x0, double &y0, double &z0, double &inv_scale)
+{
+    double lo[3], hi[3];
+    for (int k = 0; k < 3; k++) { lo[k] = dec_ordered(bbox_enc[k]); hi[k] = dec_ordered(bbox_enc[3 + k]); }
+    if (dp.p.periodic) {
+        lo[0] = fmin(lo[0], dp.p.xmin); lo[1] = fmin(lo[1], dp.p.ymin); lo[2] = fmin(lo[2], dp.p.zmin);
+        hi[0] = fmax(hi[0], dp.p.xmax); hi[1] = fmax(hi[1], dp.p.ymax); hi[2] = fmax(hi[2], dp.p.zmax);
+    }
+    double scale = fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    if (!(scale > 0.)) scale = 1.0;
+    scale *= 1.0000001;
+    x0 = lo[0]; y0 = lo[1]; z0 = lo[2]; inv_scale = 1.0 / scale;
+}
+
+__global__ void k_keys(int64_t n, const double *__restrict__ xyzh, const unsigned long long *__restrict__ bbox_enc, const __grid_constant__ DevParams dp,
                        unsigned long long *__restrict__ keys, int *__restrict__ idx, int hilbert)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    double x0, y0, z0, inv_scale;
+    key_frame(bbox_enc, dp, x0, y0, z0, inv_scale);
     const double4 x = reinterpret_cast<const double4 *>(xyzh)[i];
     unsigned long long key;
     if (x.w < DBL_MIN) key = ~0ull;   // dead/accreted particles sort to the end (part.F90:931)
@@ -112,12 +130,14 @@ __global__ void k_keys(int64_t n, const double *__restrict__ xyzh, double x0, do
     idx[i] = (int)i;
 }
 
-__global__ void k_gather_pos(int64_t nlive, const int *__restrict__ perm, const double *__restrict__ xyzh, const int8_t *__restrict__ iphase,
+__global__ void k_gather_pos(int64_t n, const int *__restrict__ perm, const double *__restrict__ xyzh, const int8_t *__restrict__ iphase,
                              double4 *__restrict__ pos4, int8_t *__restrict__ stype, const unsigned long long *__restrict__ keys,
                              unsigned char *__restrict__ cpl, unsigned long long *cnt, int boundary_is_gas)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (s >= nlive) return;
+    const int64_t nlive = (int64_t)cnt[CNT_NLIVE];
+    if (s >= n) return;
+    if (s >= nlive) { cpl[s] = 0; return; }
     const int i = perm[s];
     pos4[s] = reinterpret_cast<const double4 *>(xyzh)[i];
     const int8_t ph = iphase[i];
@@ -137,10 +157,12 @@ __global__ void k_gather_pos(int64_t nlive, const int *__restrict__ perm, const 
 
 // leaf-cell boundaries: particle s starts a cell iff its predecessor is not in the same maximal binary-radix node
 // (key prefix) holding <= tmax particles.  Prefix nodes of a Morton key are boxes (each bit halves one axis).
-__global__ void k_cell_flags(int64_t nlive, const unsigned char *__restrict__ cpl, int tmax, int *__restrict__ flag)
+__global__ void k_cell_flags(int64_t n, const unsigned long long *__restrict__ cnt, const unsigned char *__restrict__ cpl, int tmax, int *__restrict__ flag)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (s >= nlive) return;
+    const int64_t nlive = (int64_t)cnt[CNT_NLIVE];
+    if (s >= n) return;
+    if (s >= nlive) { flag[s] = 0; return; }
     unsigned char hist[66];
     for (int d = 0; d < 66; d++) hist[d] = 0;
     int m = 65;
@@ -166,18 +188,28 @@ __global__ void k_cell_flags(int64_t nlive, const unsigned char *__restrict__ cp
     flag[s] = f;
 }
 
-__global__ void k_cell_starts(int64_t nlive, const int *__restrict__ flag, const int *__restrict__ scan, Cell *__restrict__ cells)
+// M = number of leaf cells = scan[nlive-1] + flag[nlive-1], left on the device (CNT_NCELLS); M beyond the allocated capacity raises CNT_CELLOVER
+__global__ void k_cell_count(const int *__restrict__ flag, const int *__restrict__ scan, unsigned long long *cnt, long long cap)
+{
+    const long long nlive = (long long)cnt[CNT_NLIVE];
+    const unsigned long long M = nlive > 0 ? (unsigned long long)(scan[nlive - 1] + flag[nlive - 1]) : 0ull;
+    cnt[CNT_NCELLS] = M;
+    cnt[CNT_CELLOVER] = ((long long)M > cap) ? 1ull : 0ull;
+}
+
+__global__ void k_cell_starts(int64_t n, const unsigned long long *__restrict__ cnt, const int *__restrict__ flag, const int *__restrict__ scan, Cell *__restrict__ cells)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (s >= nlive) return;
+    if (s >= n || s >= (int64_t)cnt[CNT_NLIVE] || cnt[CNT_CELLOVER]) return;
     if (flag[s]) cells[scan[s]].start = (int)s;
 }
 
-__global__ void k_cell_props(int64_t ncells, int64_t nlive, Cell *__restrict__ cells, const double4 *__restrict__ pos4, const int8_t *__restrict__ stype,
+__global__ void k_cell_props(const unsigned long long *__restrict__ cnt, Cell *__restrict__ cells, const double4 *__restrict__ pos4, const int8_t *__restrict__ stype,
                              const unsigned long long *__restrict__ keys, unsigned long long *__restrict__ cellkeys, int sbta, int use_dust, int ind_ts)
 {
     int64_t cidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (cidx >= ncells) return;
+    const int64_t ncells = (int64_t)cnt[CNT_NCELLS], nlive = (int64_t)cnt[CNT_NLIVE];
+    if (cidx >= ncells || cnt[CNT_CELLOVER]) return;
     Cell c = cells[cidx];
     const int end = (cidx + 1 < ncells) ? cells[cidx + 1].start : (int)nlive;
     c.count = end - c.start;
@@ -208,10 +240,11 @@ __device__ __forceinline__ int delta_k(const unsigned long long *keys, int M, in
     return __clzll((long long)(a ^ b));
 }
 
-__global__ void k_radix_tree(int M, const unsigned long long *__restrict__ keys, TreeNode *__restrict__ nodes, TreeNodeF *__restrict__ nodesf, Cell *__restrict__ cells)
+__global__ void k_radix_tree(const unsigned long long *__restrict__ cnt, const unsigned long long *__restrict__ keys, TreeNode *__restrict__ nodes, TreeNodeF *__restrict__ nodesf, Cell *__restrict__ cells)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M - 1) return;
+    const int M = (int)cnt[CNT_NCELLS];
+    if (i >= M - 1 || cnt[CNT_CELLOVER]) return;
     const int d = (delta_k(keys, M, i, i + 1) - delta_k(keys, M, i, i - 1)) >= 0 ? 1 : -1;
     const int dmin = delta_k(keys, M, i, i - d);
     int lmax = 2;
@@ -243,10 +276,11 @@ __device__ __forceinline__ void write_nodef(TreeNodeF *nf, int slot, const doubl
     nf->hmax[slot] = __double2float_ru(hmax);
 }
 
-__global__ void k_refit(int M, const Cell *__restrict__ cells, TreeNode *nodes, TreeNodeF *nodesf, int *flags)
+__global__ void k_refit(const unsigned long long *__restrict__ tcnt, const Cell *__restrict__ cells, TreeNode *nodes, TreeNodeF *nodesf, int *flags)
 {
     int cidx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cidx >= M) return;
+    const int M = (int)tcnt[CNT_NCELLS];
+    if (cidx >= M || tcnt[CNT_CELLOVER]) return;
     const Cell c = cells[cidx];
     double lo[3] = {c.lo[0], c.lo[1], c.lo[2]}, hi[3] = {c.hi[0], c.hi[1], c.hi[2]}, hmax = c.hmax;
     int cnt = c.count, start = c.start, act = c.active;
@@ -274,11 +308,12 @@ __global__ void k_refit(int M, const Cell *__restrict__ cells, TreeNode *nodes, 
 }
 
 // target groups: maximal subtrees holding <= gmax particles (one lane per target in the pair kernels)
-__global__ void k_groups(int M, int gmax, const Cell *__restrict__ cells, const TreeNode *__restrict__ nodes, Cell *__restrict__ groups,
+__global__ void k_groups(const unsigned long long *__restrict__ cnt, int gmax, const Cell *__restrict__ cells, const TreeNode *__restrict__ nodes, Cell *__restrict__ groups,
                          unsigned long long *ngroups)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * M - 1) return;
+    const int M = (int)cnt[CNT_NCELLS];
+    if (t >= 2 * M - 1 || cnt[CNT_CELLOVER]) return;
     int me, parent, total;
     if (t < M) { me = ~t; parent = cells[t].parent; total = cells[t].count; }
     else { const int i = t - M; me = i; parent = nodes[i].parent; total = nodes[i].cnt[0] + nodes[i].cnt[1]; }
@@ -306,11 +341,12 @@ __global__ void k_groups(int M, int gmax, const Cell *__restrict__ cells, const 
 // lattices, tools/group_fill.py).  A group is then a run of whole cells: box, hmax and active count are merged from its cells.
 // scan[s] = index of the cell that starts at sorted slot s (k_cell_starts).  One thread per subtree: two passes (count, then write into
 // a contiguous block of group slots so that consecutive groups stay spatial neighbours).
-__global__ void k_groups_packed(int M, int gmax, int smax, const Cell *__restrict__ cells, const TreeNode *__restrict__ nodes, const int *__restrict__ scan,
+__global__ void k_groups_packed(const unsigned long long *__restrict__ cnt, int gmax, int smax, const Cell *__restrict__ cells, const TreeNode *__restrict__ nodes, const int *__restrict__ scan,
                                 Cell *__restrict__ groups, unsigned long long *ngroups)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * M - 1) return;
+    const int M = (int)cnt[CNT_NCELLS];
+    if (t >= 2 * M - 1 || cnt[CNT_CELLOVER]) return;
     int parent, total, start;
     if (t < M) { parent = cells[t].parent; total = cells[t].count; start = cells[t].start; }
     else { const TreeNode &nd = nodes[t - M]; parent = nd.parent; total = nd.cnt[0] + nd.cnt[1]; start = min(nd.start[0], nd.start[1]); }
@@ -366,20 +402,17 @@ __global__ void k_cell_hmax(int64_t ncells, Cell *__restrict__ cells, const doub
 
 static inline int nblk(int64_t n, int b) { return (int)((n + b - 1) / b); }
 
-static int build_groups(sphgpu_ctx *c)
+// groups of the current tree; cap = number of cells the grids are sized for (the kernels read the true count on the device).
+// The group count is left in counters[CNT_COUNT-1]: tree_build reads it with its other counts in ONE round trip.
+static int build_groups(sphgpu_ctx *c, int64_t cap)
 {
-    const int M = (int)c->ncells;
-    CUDA_TRY(c, c->groups.ensure(M));
+    CUDA_TRY(c, c->groups.ensure(cap));
     unsigned long long *ng = c->counters.p + CNT_COUNT - 1;
     CUDA_TRY(c, cudaMemsetAsync(ng, 0, sizeof(unsigned long long), c->stream));
     if (c->group_pack > c->max_cell && c->max_leaf <= c->max_cell)
-        LAUNCH(c, k_groups_packed, nblk(2 * M - 1, 128), 128, M, c->max_cell, c->group_pack, c->cells.p, c->nodes.p, c->cellid_scan.p, c->groups.p, ng);
+        LAUNCH(c, k_groups_packed, nblk(2 * cap - 1, 128), 128, c->counters.p, c->max_cell, c->group_pack, c->cells.p, c->nodes.p, c->cellid_scan.p, c->groups.p, ng);
     else
-        LAUNCH(c, k_groups, nblk(2 * M - 1, 128), 128, M, c->max_cell, c->cells.p, c->nodes.p, c->groups.p, ng);
-    unsigned long long h = 0;
-    CUDA_TRY(c, cudaMemcpyAsync(&h, ng, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    c->ngroups = (int64_t)h;
+        LAUNCH(c, k_groups, nblk(2 * cap - 1, 128), 128, c->counters.p, c->max_cell, c->cells.p, c->nodes.p, c->groups.p, ng);
     return SPHGPU_OK;
 }
 
@@ -390,87 +423,86 @@ int tree_refit_hmax(sphgpu_ctx *c)
     LAUNCH(c, k_cell_hmax, nblk(M, 128), 128, M, c->cells.p, c->pos4.p);
     if (M > 1) {
         CUDA_TRY(c, cudaMemsetAsync(c->nodeflag.p, 0, sizeof(int) * (size_t)M, c->stream));
-        LAUNCH(c, k_refit, nblk(M, 128), 128, M, c->cells.p, c->nodes.p, c->nodesf.p, c->nodeflag.p);
+        LAUNCH(c, k_refit, nblk(M, 128), 128, c->counters.p, c->cells.p, c->nodes.p, c->nodesf.p, c->nodeflag.p);
     }
-    TRY(build_groups(c));
+    // the structure is unchanged and grouping depends on particle counts only, so the number of groups is too: no read-back
+    // (the order of the groups may differ, which nothing depends on)
+    TRY(build_groups(c, M));
     CUDA_TRY(c, cudaGetLastError());
     return SPHGPU_OK;
 }
 
+// One host round trip per build. Everything that used to be read back mid-build (live count and bounding box for the key
+// frame, number of leaf cells for the allocation sizes) stays in c->counters; kernels are launched on grids sized from the
+// particle count / the cell capacity and read the true counts on the device. The single read at the end returns error
+// state, nlive, ncells, ngroups and the multi-type flag. The cell arrays are sized from the previous build (+25%) or
+// nlive/3; a build that finds more cells than that raises CNT_CELLOVER, skips the cell-indexed kernels and is repeated once
+// with the worst case (one cell per particle).
 int tree_build(sphgpu_ctx *c)
 {
     const int64_t n = c->npart;
     if (n <= 0) { c->err = "build_tree: no particles"; return SPHGPU_ERR_NOPART; }
     c->tree_valid = false; c->dens_valid = false;
+    const sphgpu_params &p = c->hp.p;
     CUDA_TRY(c, c->keys.ensure(n)); CUDA_TRY(c, c->keys_alt.ensure(n));
     CUDA_TRY(c, c->perm.ensure(n)); CUDA_TRY(c, c->perm_alt.ensure(n));
     CUDA_TRY(c, c->counters.ensure(CNT_COUNT)); CUDA_TRY(c, c->dscal.ensure(DS_COUNT));
-    CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * CNT_COUNT, c->stream));
-    // bbox accumulators (ordered encoding): min slots start at all-ones, max slots at zero
-    unsigned long long *bbox_enc = c->counters.p + 16;
-    CUDA_TRY(c, cudaMemsetAsync(bbox_enc, 0xff, sizeof(unsigned long long) * 3, c->stream));
-    LAUNCH(c, k_wrap_count, c->numSMs * 8, 256, n, c->xyzh.p, c->hp, c->counters.p, bbox_enc);
-    unsigned long long hc[CNT_COUNT];
-    CUDA_TRY(c, cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (hc[CNT_ERR]) {
-        char buf[128]; snprintf(buf, sizeof buf, "maketree: NaN in particle position, likely caused by NaN in force (particle %llu)", hc[CNT_ERRID]);
-        c->err = buf; return (int)hc[CNT_ERR];
-    }
-    const int64_t nlive = (int64_t)hc[CNT_NLIVE];
-    if (nlive == 0) { c->err = "maketree: no particles or all particles dead/accreted"; return SPHGPU_ERR_NOPART; }
-    c->nlive = nlive;
-    double lo[3], hi[3];
-    for (int k = 0; k < 3; k++) { lo[k] = dec_ordered(hc[16 + k]); hi[k] = dec_ordered(hc[19 + k]); }
-    const sphgpu_params &p = c->hp.p;
-    if (p.periodic) {   // stable normalisation across steps: the periodic box itself
-        lo[0] = fmin(lo[0], p.xmin); lo[1] = fmin(lo[1], p.ymin); lo[2] = fmin(lo[2], p.zmin);
-        hi[0] = fmax(hi[0], p.xmax); hi[1] = fmax(hi[1], p.ymax); hi[2] = fmax(hi[2], p.zmax);
-    }
-    double scale = fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
-    if (!(scale > 0.)) scale = 1.0;
-    scale *= 1.0000001;
-    LAUNCH(c, k_keys, nblk(n, 256), 256, n, c->xyzh.p, lo[0], lo[1], lo[2], 1.0 / scale, c->keys_alt.p, c->perm_alt.p, c->hilbert ? 1 : 0);
-    size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, c->keys_alt.p, c->keys.p, c->perm_alt.p, c->perm.p, (int)n, 16, 64, c->stream);
-    size_t tb2 = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb2, c->cellflag.p, c->cellid_scan.p, (int)n, c->stream);
-    tb = tb > tb2 ? tb : tb2;
-    CUDA_TRY(c, c->cubtemp.ensure(tb));
-    size_t tbb = c->cubtemp.cap;
-    CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(c->cubtemp.p, tbb, c->keys_alt.p, c->keys.p, c->perm_alt.p, c->perm.p, (int)n, 16, 64, c->stream));
-    c->launches += 7;
     CUDA_TRY(c, c->pos4.ensure(n)); CUDA_TRY(c, c->stype.ensure(n)); CUDA_TRY(c, c->cpl.ensure(n));
     CUDA_TRY(c, c->cellflag.ensure(n)); CUDA_TRY(c, c->cellid_scan.ensure(n));
-    LAUNCH(c, k_gather_pos, nblk(nlive, 256), 256, nlive, c->perm.p, c->xyzh.p, c->iphase.p, c->pos4.p, c->stype.p, c->keys.p, c->cpl.p, c->counters.p,
-           (p.massoftype[IBOUNDARY] == p.massoftype[IGAS]) ? 1 : 0);
-    LAUNCH(c, k_cell_flags, nblk(nlive, 128), 128, nlive, c->cpl.p, c->max_leaf, c->cellflag.p);
-    tbb = c->cubtemp.cap;
-    CUDA_TRY(c, cub::DeviceScan::ExclusiveSum(c->cubtemp.p, tbb, c->cellflag.p, c->cellid_scan.p, (int)nlive, c->stream));
-    c->launches += 2;
-    int lastflag, lastscan;
-    unsigned long long mt = 0;
-    CUDA_TRY(c, cudaMemcpyAsync(&lastflag, c->cellflag.p + (nlive - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(&lastscan, c->cellid_scan.p + (nlive - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(&mt, c->counters.p + CNT_MULTITYPE, sizeof mt, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    const int64_t M = (int64_t)lastscan + lastflag;
-    c->multitype = mt != 0;
-    c->ncells = M;
-    CUDA_TRY(c, c->cells.ensure(M)); CUDA_TRY(c, c->cellkeys.ensure(M)); CUDA_TRY(c, c->nodes.ensure(M)); CUDA_TRY(c, c->nodesf.ensure(M)); CUDA_TRY(c, c->nodeflag.ensure(M));
-    LAUNCH(c, k_cell_starts, nblk(nlive, 256), 256, nlive, c->cellflag.p, c->cellid_scan.p, c->cells.p);
-    LAUNCH(c, k_cell_props, nblk(M, 128), 128, M, nlive, c->cells.p, c->pos4.p, c->stype.p, c->keys.p, c->cellkeys.p,
-           p.set_boundaries_to_active, p.dust, p.ind_timesteps);
-    if (M > 1) {
-        LAUNCH(c, k_radix_tree, nblk(M - 1, 128), 128, (int)M, c->cellkeys.p, c->nodes.p, c->nodesf.p, c->cells.p);
-        CUDA_TRY(c, cudaMemsetAsync(c->nodeflag.p, 0, sizeof(int) * (size_t)M, c->stream));
-        LAUNCH(c, k_refit, nblk(M, 128), 128, (int)M, c->cells.p, c->nodes.p, c->nodesf.p, c->nodeflag.p);
-    }
-    TRY(build_groups(c));
-    {   // h as the tree was built with: start of the node-hmax history (gravity) and restore point of a halo-widening retry
-        CUDA_TRY(c, c->h_build.ensure(n)); CUDA_TRY(c, c->h_its.ensure(n)); if (p.gravity) CUDA_TRY(c, c->h_hist.ensure((size_t)SPHGPU_HHIST * n));
+    CUDA_TRY(c, c->h_build.ensure(n)); CUDA_TRY(c, c->h_its.ensure(n)); if (p.gravity) CUDA_TRY(c, c->h_hist.ensure((size_t)SPHGPU_HHIST * n));
+    size_t tb = 0, tb2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, c->keys_alt.p, c->keys.p, c->perm_alt.p, c->perm.p, (int)n, 16, 64, c->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb2, c->cellflag.p, c->cellid_scan.p, (int)n, c->stream);
+    CUDA_TRY(c, c->cubtemp.ensure(tb > tb2 ? tb : tb2));
+    int64_t cap = c->ncells > 0 ? c->ncells + c->ncells / 4 + 1024 : 0;
+    if (cap < n / 3 + 1024) cap = n / 3 + 1024;
+    if (cap > n) cap = n;
+    unsigned long long hc[CNT_COUNT];
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CUDA_TRY(c, c->cells.ensure(cap)); CUDA_TRY(c, c->cellkeys.ensure(cap)); CUDA_TRY(c, c->nodes.ensure(cap)); CUDA_TRY(c, c->nodesf.ensure(cap));
+        CUDA_TRY(c, c->nodeflag.ensure(cap));
+        CUDA_TRY(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * CNT_COUNT, c->stream));
+        // bbox accumulators (ordered encoding): min slots start at all-ones, max slots at zero
+        unsigned long long *bbox_enc = c->counters.p + 16;
+        CUDA_TRY(c, cudaMemsetAsync(bbox_enc, 0xff, sizeof(unsigned long long) * 3, c->stream));
+        LAUNCH(c, k_wrap_count, c->numSMs * 8, 256, n, c->xyzh.p, c->hp, c->counters.p, bbox_enc);
+        LAUNCH(c, k_keys, nblk(n, 256), 256, n, c->xyzh.p, bbox_enc, c->hp, c->keys_alt.p, c->perm_alt.p, c->hilbert ? 1 : 0);
+        size_t tbb = c->cubtemp.cap;
+        CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(c->cubtemp.p, tbb, c->keys_alt.p, c->keys.p, c->perm_alt.p, c->perm.p, (int)n, 16, 64, c->stream));
+        c->launches += 7;
+        LAUNCH(c, k_gather_pos, nblk(n, 256), 256, n, c->perm.p, c->xyzh.p, c->iphase.p, c->pos4.p, c->stype.p, c->keys.p, c->cpl.p, c->counters.p,
+               (p.massoftype[IBOUNDARY] == p.massoftype[IGAS]) ? 1 : 0);
+        LAUNCH(c, k_cell_flags, nblk(n, 128), 128, n, c->counters.p, c->cpl.p, c->max_leaf, c->cellflag.p);
+        tbb = c->cubtemp.cap;
+        CUDA_TRY(c, cub::DeviceScan::ExclusiveSum(c->cubtemp.p, tbb, c->cellflag.p, c->cellid_scan.p, (int)n, c->stream));
+        c->launches += 2;
+        LAUNCH(c, k_cell_count, 1, 1, c->cellflag.p, c->cellid_scan.p, c->counters.p, (long long)cap);
+        LAUNCH(c, k_cell_starts, nblk(n, 256), 256, n, c->counters.p, c->cellflag.p, c->cellid_scan.p, c->cells.p);
+        LAUNCH(c, k_cell_props, nblk(cap, 128), 128, c->counters.p, c->cells.p, c->pos4.p, c->stype.p, c->keys.p, c->cellkeys.p,
+               p.set_boundaries_to_active, p.dust, p.ind_timesteps);
+        if (cap > 1) {
+            LAUNCH(c, k_radix_tree, nblk(cap - 1, 128), 128, c->counters.p, c->cellkeys.p, c->nodes.p, c->nodesf.p, c->cells.p);
+            CUDA_TRY(c, cudaMemsetAsync(c->nodeflag.p, 0, sizeof(int) * (size_t)cap, c->stream));
+            LAUNCH(c, k_refit, nblk(cap, 128), 128, c->counters.p, c->cells.p, c->nodes.p, c->nodesf.p, c->nodeflag.p);
+        }
+        TRY(build_groups(c, cap));
+        // h as the tree was built with: start of the node-hmax history (gravity) and restore point of a halo-widening retry
         LAUNCH(c, k_hbuild, nblk(n, 256), 256, n, c->xyzh.p, c->h_build.p, c->h_its.p);
+        CUDA_TRY(c, cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        if (hc[CNT_ERR]) {
+            char buf[128]; snprintf(buf, sizeof buf, "maketree: NaN in particle position, likely caused by NaN in force (particle %llu)", hc[CNT_ERRID]);
+            c->err = buf; return (int)hc[CNT_ERR];
+        }
+        if (hc[CNT_NLIVE] == 0) { c->err = "maketree: no particles or all particles dead/accreted"; return SPHGPU_ERR_NOPART; }
+        if (!hc[CNT_CELLOVER]) break;
+        if (attempt == 1) { c->err = "build_tree: cell capacity exceeded twice"; return SPHGPU_ERR_ARG; }
+        cap = (int64_t)hc[CNT_NCELLS];
     }
+    c->nlive = (int64_t)hc[CNT_NLIVE];
+    c->ncells = (int64_t)hc[CNT_NCELLS];
+    c->ngroups = (int64_t)hc[CNT_COUNT - 1];
+    c->multitype = hc[CNT_MULTITYPE] != 0;
     c->grav_tree_valid = false; c->hscale = 1.; c->wl_force_ok = false;
     CUDA_TRY(c, cudaGetLastError());
     c->tree_valid = true;

@@ -251,10 +251,33 @@ def test_turbulent_driving(correct_mean, ind_ts):
     assert np.max(np.abs(p2.fxyzu[active, :3] - fdrive[active])) < 1e-12 * scale
 
 
+def _canonical_tree(rec, irec):
+    """node records relabelled in breadth-first order (left before right): the library numbers the two children of a split node from an
+    atomic counter, so the labels inside one level vary from run to run while the tree itself does not"""
+    order, q = [], [0]
+    while q:
+        nxt = []
+        for d in q:
+            order.append(d)
+            if irec[d, 0] >= 0:
+                nxt += [irec[d, 0], irec[d, 1]]
+        q = nxt
+    order = np.array(order)
+    new = np.full(len(irec), -1, dtype=np.int64)
+    new[order] = np.arange(len(order))
+    ir = irec[order].astype(np.int64)
+    for col in (0, 1, 2):
+        m = ir[:, col] >= 0
+        ir[m, col] = new[ir[m, col]]
+    return rec[order], ir
+
+
 def test_gravity_pass_is_deterministic_and_tree_bitwise_repeatable():
     """the level-synchronous gravity build accumulates node masses and centres of mass with double atomics, whose
-    order varies from run to run.  Two fresh contexts on the same sphere must still give the same tree topology, the same P2P / M2L
-    counts and forces equal to round-off (the pivots move by at most an ulp, which does not flip any particle across a split here)."""
+    order varies from run to run, and numbers child nodes from an atomic counter.  Fresh contexts on the same sphere must still give
+    the same tree (same splits, same particle order in the leaves, compared after relabelling the nodes breadth-first), the same
+    P2P / M2L counts and forces equal to round-off (the pivots move by at most an ulp, which does not flip any particle across a
+    split here)."""
     part = setups.setup_random_sphere(n=6000)
     part.alphaind[:, 0] = 0.5
     runs = []
@@ -263,11 +286,14 @@ def test_gravity_pass_is_deterministic_and_tree_bitwise_repeatable():
         g = gpu(pg.params)
         sc = g.derivs(pg)
         rec, irec, ids = g.gravity_tree(pg.npart)
+        rec, irec = _canonical_tree(rec, irec)
         runs.append((pg, sc, rec, irec, ids))
     p0, s0, r0, i0, d0 = runs[0]
+    assert len(i0) > 500 and np.all(i0[1:, 2] >= 0)
     fs = np.sqrt(np.mean(p0.fxyzu[:, :3] ** 2))
     for pg, sc, rec, irec, ids in runs[1:]:
-        assert np.array_equal(irec, i0) and np.array_equal(ids, d0)                 # same topology, same particle order in the leaves
+        assert np.array_equal(ids, d0)                                              # same particle order in the leaves
+        assert np.array_equal(irec, i0)                                             # same topology, slots, counts and levels
         assert sc.npairs_gravity == s0.npairs_gravity and sc.nm2l == s0.nm2l and sc.npairs_force == s0.npairs_force
         assert np.max(np.abs(rec - r0)) <= 1e-13 * np.max(np.abs(r0))               # node moments to round-off of the atomic sums
         assert np.max(np.abs(pg.fxyzu[:, :3] - p0.fxyzu[:, :3])) <= 1e-12 * fs
