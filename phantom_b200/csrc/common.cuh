@@ -167,6 +167,7 @@ struct sphgpu_ctx {
     DevBuf<TreeNode> nodes;
     DevBuf<TreeNodeF> nodesf;
     bool multitype = false;                 // any particle that is not plain gas (boundary, dust, ...)
+    int class_mask = 1;                     // sort classes present (bit 0 gas/boundary, 1 dust, 2 other): the class rounds of the general pair kernels
     DevBuf<int> wl_list, wl_ncl; DevBuf<float> wl_reach;   // cell lists prepared by k_walk_lists (walk.cuh)
     bool stream_blocking = false;   // the compute stream synchronises implicitly with the legacy default stream (option "legacy_stream")
     double dens_trial_hint = 0., dens_trial_max = 0.;   // mean / max candidates per target group in the last density pass (choose the round size of the next)
@@ -219,6 +220,16 @@ __device__ __forceinline__ double rhoh_d(double hi, double pmassi, double hfact)
 {
     double r = hfact / fabs(hi);
     return pmassi * (r * r * r);
+}
+
+// Sort class of a particle type: 0 = gas and boundary, 1 = dust, 2 = everything else.  The class is the top of the sort key, so every
+// leaf cell, every target group and every staged round of candidates holds ONE class and the pair kernels pick their pair body per
+// (class of the targets, class of the candidates) for the whole warp instead of branching per lane.  An all-gas set is class 0
+// throughout: same order as a plain Morton sort.
+__device__ __forceinline__ int sort_class(int8_t iphase)
+{
+    const int ta = iphase < 0 ? -iphase : iphase;
+    return (ta == IGAS || ta == IBOUNDARY) ? 0 : (ta == IDUST ? 1 : 2);
 }
 
 // decode iphase (part.F90:1026-1067), gas + boundary + one dust type
@@ -285,7 +296,7 @@ __device__ __forceinline__ void atomic_max_pos(double *addr, double v) { atomicM
 
 // indices into ctx->counters (unsigned long long)
 enum { CNT_WORK = 0, CNT_ERR, CNT_ERRID, CNT_NPAIRS, CNT_NTRIAL, CNT_NCALC, CNT_NACT, CNT_MAXACT, CNT_MAXTRIAL, CNT_NP, CNT_NWALK, CNT_NLIVE, CNT_NBINMAX, CNT_NCHECKBIN, CNT_MULTITYPE, CNT_NSURV,
-       CNT_NGRAVPAIRS = 24, CNT_NM2L = 25, CNT_NCELLS = 26, CNT_CELLOVER = 27, CNT_COUNT = 32 };
+       CNT_NGRAVPAIRS = 24, CNT_NM2L = 25, CNT_NCELLS = 26, CNT_CELLOVER = 27, CNT_CLASS1 = 28, CNT_CLASS2 = 29, CNT_COUNT = 32 };
 // indices into ctx->dscal (double)
 enum { DS_XMIN = 0, DS_YMIN, DS_ZMIN, DS_XMAX, DS_YMAX, DS_ZMAX, DS_DTCOURANT, DS_DTFORCE, DS_DTMINI, DS_DTMAXI, DS_RHOMAX, DS_HUSED, DS_HGROW, DS_COUNT = 32 };
 

@@ -26,7 +26,7 @@ struct DensArgs {
     const TreeNodeF *nodes; const Cell *cells; int ncells; const Cell *groups; int ngroups;
     double4 *pos4; const double4 *vel4, *acc4, *bev4; const int8_t *stype; const int *perm;
     const double4 *drec;     // fast path: 3 (MHD: 4) x 32 B per particle {x,y,z,h} {vx,vy,vz,ax} {ay,az,Bx,By} [{Bz,psi,-,-}], a = f + fext, B = (B/rho) rho(h)
-    int *stage_idx; int multitype; int max_leaf; double hmax_global;
+    int *stage_idx; int multitype; int max_leaf; int class_mask; double hmax_global;
     WalkLists wl;       // cell lists prepared by k_walk_lists for the first pass of every group
     double *hnew; int *s_nneigh;                                   // sorted order: new h, neighbour count (< 0: not an active target)
     double *xyzh;                                                  // caller's order (fast path writes the new h directly)
@@ -172,6 +172,27 @@ __device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[B_COUNT],
     if (dp.p.dust) v[S_RHODUST] += (isn && !same_type && gasi && itypej == IDUST) ? wabi : 0.;
 }
 
+
+// gas target, candidate of the dust class: the only density sum a pair of different classes enters is rho_dust (dens.F90:738-741);
+// W is evaluated exactly as in dens_pair
+template <int K, bool PERIODIC>
+__device__ __forceinline__ void dens_pair_rhodust(double &rhodust, int slot, const int *__restrict__ idxlist, int s, const double4 &pi, double hi1, double hi21,
+                                                  bool gasi, const DensArgs &a, double Lx, double Ly, double Lz)
+{
+    typedef SphKern<K> KF;
+    const int j = (slot >= 0) ? idxlist[slot] : s;
+    const double4 pj = ldg256(a.pos4 + j);
+    double dx, dy, dz;
+    const double r2 = pair_r2<PERIODIC>(pi.x, pi.y, pi.z, pj, Lx, Ly, Lz, dx, dy, dz);
+    const double q2i = __dmul_rn(r2, hi21);
+    const bool isn = (q2i < KF::radkern2) && (slot >= 0);
+    const double r2s = isn ? r2 : 1.0;
+    const double rinv = (r2s > 0.) ? rsqrt(r2s) : 0.;
+    const double qi = (r2s * rinv) * hi1;
+    double wabi, grkerni;
+    KF::get_kernel(isn ? q2i : 1.0, qi, wabi, grkerni);
+    rhodust += (isn && gasi && abs((int)a.stype[j]) == IDUST) ? wabi : 0.;
+}
 
 // fast path (every particle has the same type and mass, no dust): same sums as dens_pair for TWO neighbours of the lane at once,
 // written phase by phase over both so that two independent FP64 dependency chains are in flight.  No branches: the kernel is
@@ -410,14 +431,23 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
             const double hi1 = 1. / h, hi21 = hi1 * hi1;
             if (FAST && MHD) { const double rhoi = rhoh_d(h, pmassi, dp.p.hfact); bi = make_double4(bevi.x * rhoi, bevi.y * rhoi, bevi.z * rhoi, bevi.w); }
             int nlist = 0;
+            // General kernel: the candidates are taken one SORT CLASS at a time (cells, target groups and therefore rounds hold one
+            // class each), so the kind of pair is the same for the whole warp: same class -> the full sums; gas targets and dust
+            // candidates -> rho_dust alone; every other combination enters no density sum (dens.F90:717-741) and is not even staged.
+            const int ci = FAST ? 0 : sort_class(a.stype[cell.start]);
+            for (int cj = 0; cj < (FAST ? 1 : 3); cj++) {
+            if (!FAST) {
+                if (!((a.class_mask >> cj) & 1)) continue;
+                if (cj != ci && !(ci == 0 && cj == 1 && dp.p.dust)) continue;
+            }
             for (int cellpos = 0; cellpos < ncl;) {                  // rounds of <= ROUND candidates staged in shared memory
                 auto stage_rec = [&](int slot, int, const double2 &xy, const double2 &zw) {      // fast path: FP64 positions to shared memory
                     if (STAGED) { ws.rec2[0][slot] = xy; ws.rec1[0][slot] = zw.x; }
                 };
                 const int nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf, fs, interior,
-                                                            cell.start, stage_rec);
+                                                            cell.start, stage_rec, FAST ? -1 : cj, a.stype);
+                if (!FAST && nr == 0) continue;
                 nlist += nr;
-                const int nchunk = (nr + 31) >> 5;
                 unsigned nz = build_masks<false>(ws, nr, ft);
                 int c = -1; unsigned m = 0u;
                 if (FAST) {
@@ -432,18 +462,27 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                                                                            vi, ai, bi, a.drec, pmassi, use_da, interior, Lx, Ly, Lz);
                     }
                     st_surv += surv;
-                } else
-                while (true) {      // two neighbours per trip: independent dependency chains, loads of both in flight
-                    const int slot0 = conv ? -1 : next_hit(ws, lane, nchunk, c, m);
-                    const int slot1 = (slot0 < 0) ? -1 : next_hit(ws, lane, nchunk, c, m);
-                    if (!__any_sync(FULLMASK, slot0 >= 0)) break;
-                    if (slot0 >= 0) {
+                } else if (cj == ci) {
+                    while (true) {      // two neighbours per trip: independent dependency chains, loads of both in flight
+                        int slot0, slot1;
+                        next_hits2(hm_lane, nz, c, m, slot0, slot1);
+                        if (slot0 < 0) break;
                         st_surv += 1 + (slot1 >= 0);
                         dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, slot0, ws.sidx, s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp, use_da, Lx, Ly, Lz);
                         dens_pair<K, PERIODIC, MHD, GRAV>(v, w, nneighi, slot1, ws.sidx, s, pi, h, hi1, hi21, itypei, gasi, vi, ai, bi, a, dp, use_da, Lx, Ly, Lz);
                     }
+                } else {
+                    while (true) {
+                        int slot0, slot1;
+                        next_hits2(hm_lane, nz, c, m, slot0, slot1);
+                        if (slot0 < 0) break;
+                        st_surv += 1 + (slot1 >= 0);
+                        dens_pair_rhodust<K, PERIODIC>(v[S_RHODUST], slot0, ws.sidx, s, pi, hi1, hi21, gasi, a, Lx, Ly, Lz);
+                        dens_pair_rhodust<K, PERIODIC>(v[S_RHODUST], slot1, ws.sidx, s, pi, hi1, hi21, gasi, a, Lx, Ly, Lz);
+                    }
                 }
                 __syncwarp();
+            }
             }
             nlist_last = nlist;
             if (!conv) {
@@ -650,7 +689,7 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.acc4 = c->acc4.p; a.bev4 = c->bev4.p; a.stype = c->stype.p; a.perm = c->perm.p;
     a.hnew = c->hnew.p; a.s_nneigh = c->s_nneigh.p; a.xyzh = c->xyzh.p;
     a.gradh = c->gradh.p; a.divcurlv = c->divcurlv.p; a.dvdx = c->dvdx.p; a.alphaind = c->alphaind.p; a.divcurlB = c->divcurlB.p; a.dustfrac = c->dustfrac.p;
-    a.multitype = c->multitype ? 1 : 0; a.max_leaf = c->max_leaf; a.hmax_global = 0.;
+    a.multitype = c->multitype ? 1 : 0; a.max_leaf = c->max_leaf; a.class_mask = c->class_mask; a.hmax_global = 0.;
     a.cnt = c->counters.p; a.dscal = c->dscal.p;
     a.margin = c->list_margin; a.icall = icall;
     // the node-hmax replay of the reference tree (self-gravity, and the reference-compatible neighbour mode) needs every particle's h history

@@ -18,7 +18,7 @@ namespace {
 
 struct ForceArgs {
     const TreeNodeF *nodes; const Cell *cells; int ncells; const Cell *groups; int ngroups;
-    int *stage_idx; int multitype; int max_leaf;
+    int *stage_idx; int multitype; int max_leaf; int class_mask;
     WalkLists wl;       // cell lists prepared by k_walk_lists
     const double4 *pos4, *vel4, *recC, *recD, *recE; const double2 *hinv; const int8_t *stype; const int *perm;
     double4 *s_fxyzu, *s_dB; float *s_divvf, *s_divBsymm; int *s_done;
@@ -175,7 +175,10 @@ __device__ __noinline__ bool ref_walk_reaches(const ForceArgs &a, int si, int sj
 // pair body: lane = target, j = this lane's next neighbour candidate (slot < 0: none).  Branch-free: the exact membership
 // test (force.F90:1271-1287, :1230) and the gas-gas condition (:1539) become zero weights on grad W_i, grad W_j, through
 // which every sum of compute_forces scales; two calls per trip give two independent FP64 dependency chains.
-template <int K, bool PERIODIC, bool MHD, bool XTRA>
+// CP = kind of pair, the same for the whole warp because target groups and staged rounds hold one sort class each (tree.cu):
+// 0 gas-gas (hydro, MHD, conductivity), 1 gas-dust or dust-gas (drag), 2 anything else; gravity, the wake-up of individual-timestep
+// neighbours, the pair count and the signal speed are common to all three.
+template <int K, bool PERIODIC, bool MHD, bool XTRA, int CP>
 __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int &npair, int slot, const int *__restrict__ idxlist, int s,
                                            const double4 &pi, double hi, double hi1, double hi21, bool gasi, const double4 &vi, const double4 &Ci,
                                            const double4 &Di, const double4 &Ei, const ForceArgs &a, const DevParams &dp, double Lx, double Ly, double Lz,
@@ -186,7 +189,9 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
     const int j = (slot >= 0) ? idxlist[slot] : s;
     const double4 pj = ldg256(a.pos4 + j);
     const double2 hj = a.hinv[j];
-    const double4 Cj = ldg256(a.recC + j), Dj = ldg256(a.recD + j);
+    const double4 Dj = ldg256(a.recD + j);
+    double4 Cj = make_double4(0., 0., 0., 0.);
+    if (CP == 0) Cj = ldg256(a.recC + j);
     const double4 vj = ldg256(a.vel4 + j);
     double dx, dy, dz;
     const double r2 = pair_r2<PERIODIC>(pi.x, pi.y, pi.z, pj, Lx, Ly, Lz, dx, dy, dz);
@@ -198,8 +203,7 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
     npair += isn ? 1 : 0;
     int itypej = IGAS;
     if (a.multitype) itypej = abs((int)a.stype[j]);
-    const bool gasj = (itypej == IGAS || itypej == IBOUNDARY);
-    const bool gg = isn && gasi && gasj;
+    const bool gg = isn && (CP == 0);                                         // gas-gas condition (force.F90:1539)
     const double r2s = isn ? r2 : 1.0;
     const double rij1 = (r2s > DBL_MIN) ? rsqrt(r2s) : 0.;                    // force.F90:1293-1299
     const double rij = r2s * rij1;
@@ -224,10 +228,9 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
             f[A_FX] -= dx * rij1 * fgrav; f[A_FY] -= dy * rij1 * fgrav; f[A_FZ] -= dz * rij1 * fgrav;
             f[A_POT] += Dj.z * phii;
         }
-        if (p.dust && p.idrag > 0 && isn) {                                   // force.F90:1864-1970 (explicit drag, large grains)
-            const bool dusti = (itypei == IDUST), dustj = (itypej == IDUST);
-            const bool gas_dust = gasi && dustj, dust_gas = dusti && gasj;
-            if (gas_dust || dust_gas) {
+        if (CP == 1 && p.dust && p.idrag > 0 && isn) {                        // force.F90:1864-1970 (explicit drag, large grains)
+            const bool gas_dust = gasi;                                       // else dust-gas: the warp's targets are of one class
+            {
                 const double rx = dx * rij1, ry = dy * rij1, rz = dz * rij1;
                 const double pv = (vi.x - vj.x) * rx + (vi.y - vj.y) * ry + (vi.z - vj.z) * rz;
                 const double sl = recon_slope(a.dvdx9 + 9 * (size_t)s, dx, dy, dz, rx, ry, rz);
@@ -251,13 +254,17 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
         grkerni = ini ? KF::grkern(q2i, qi) * Di.y : 0.;                      // :1301-1302
         grkernj = inj ? KF::grkern(q2j, qj) * Dj.y : 0.;                      // :1325-1327
     }
+    const double runix = dx * rij1, runiy = dy * rij1, runiz = dz * rij1;
+    const double dvx = vi.x - vj.x, dvy = vi.y - vj.y, dvz = vi.z - vj.z;
+    const double projv = dvx * runix + dvy * runiy + dvz * runiz;
+    if (CP != 0) {                                                            // force.F90:1446-1448: signal speed of a pair that is not gas-gas
+        vsigmax = fmax(vsigmax, isn ? fmax(-projv, 0.) : 0.);
+        return;
+    }
     bool usej = (q2j < KF::radkern2);
     if (MHD) usej = true;
     if (p.dust) usej = true;
     if (dp.nvu >= 4 && !p.gravity) usej = true;                               // :1343-1345
-    const double runix = dx * rij1, runiy = dy * rij1, runiz = dz * rij1;
-    const double dvx = vi.x - vj.x, dvy = vi.y - vj.y, dvz = vi.z - vj.z;
-    const double projv = dvx * runix + dvy * runiy + dvz * runiz;
     const double rho1i = Di.x, rho1j = usej ? Dj.x : 0.;
     const double vwavei = Ci.y, alphai = Ci.z, pri = Ci.w, pro2i = Ci.x;
     const double beta = p.beta;
@@ -267,8 +274,7 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
     const double alphaj = (usej && !p.const_av) ? Cj.z : alphai;
     const double vsigj = usej ? fmax(vwavej - beta * projv, 0.) : 0.;         // :1501-1504
     const double vsigavj = usej ? fmax(alphaj * vwavej - beta * projv, 0.) : 0.;
-    const double vs_gg = fmax(vsigi, vsigj), vs_other = fmax(-projv, 0.);     // :1446-1448 for non gas-gas pairs
-    vsigmax = fmax(vsigmax, isn ? ((gasi && gasj) ? vs_gg : vs_other) : 0.);
+    vsigmax = fmax(vsigmax, isn ? fmax(vsigi, vsigj) : 0.);
     double qrho2i = 0., qrho2j = 0., dudtdissi;
     if (p.disc_viscosity) {                                                   // force.F90:1555-1579
         const double hjv = 1. / hj1, csi = Di.w, csj = Dj.w;
@@ -679,6 +685,7 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
     extern __shared__ __align__(16) unsigned char forceg_smem[];
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     WS &ws = reinterpret_cast<WS *>(forceg_smem)[wib];
+    const unsigned hm_lane = ws_shared_addr(ws) + (unsigned)offsetof(WS, hm) + 4u * lane;
     const int gwarp = blockIdx.x * 4 + wib;
     int *clist = a.stage_idx + (size_t)gwarp * a.scratch_per_warp;      // cell list of the current group (the only global scratch)
     const double Lx = dp.dxbound, Ly = dp.dybound, Lz = dp.dzbound;
@@ -732,23 +739,31 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
         double vsigmax = 0.;
         int npair = 0;
         XtraSums xs; xs.fdx = xs.fdy = xs.fdz = 0.; xs.tsmin = 1.e29; xs.ibin_neigh = 0;
-        for (int cellpos = 0; cellpos < ncl;) {                     // rounds of <= ROUND candidates staged in shared memory
-            const int nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, reinterpret_cast<const double2 *>(a.pos4), 2, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern, a.max_leaf, fs);
-            nlist += nr;
-            const int nchunk = (nr + 31) >> 5;
-            if (wide) build_masks<false>(ws, nr, ft);
-            else build_masks<true>(ws, nr, ft);
-            int c = -1; unsigned m = 0u;
-            while (true) {      // two neighbours per trip
-                const int slot0 = act ? next_hit(ws, lane, nchunk, c, m) : -1;
-                const int slot1 = (slot0 < 0) ? -1 : next_hit(ws, lane, nchunk, c, m);
-                if (!__any_sync(FULLMASK, slot0 >= 0)) break;
-                if (slot0 >= 0) {
-                    force_pair<K, PERIODIC, MHD, XTRA>(f, vsigmax, npair, slot0, ws.sidx, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei);
-                    force_pair<K, PERIODIC, MHD, XTRA>(f, vsigmax, npair, slot1, ws.sidx, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei);
+        // The candidates are taken one SORT CLASS at a time (cells, target groups and therefore rounds hold one class each, tree.cu), so
+        // the kind of pair -- gas-gas, gas-dust, other -- is the same for the whole warp and each kind has its own branch-free body.
+        const int ci = sort_class(a.stype[cell.start]);
+        for (int cj = 0; cj < 3; cj++) {
+            if (!((a.class_mask >> cj) & 1)) continue;
+            const int cp = (ci == 0 && cj == 0) ? 0 : ((ci + cj == 1) ? 1 : 2);
+            for (int cellpos = 0; cellpos < ncl;) {                 // rounds of <= ROUND candidates staged in shared memory
+                const int nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, reinterpret_cast<const double2 *>(a.pos4), 2, cx, cy, cz, Lx, Ly, Lz, (float)KF::radkern,
+                                                            a.max_leaf, fs, false, 0, NoRecord(), cj, a.stype);
+                if (nr == 0) continue;
+                nlist += nr;
+                unsigned nz = wide ? build_masks<false>(ws, nr, ft) : build_masks<true>(ws, nr, ft);
+                int c = -1; unsigned m = 0u;
+#define FORCE_PAIR_LOOP(CP)                                                                                                                                          \
+                while (true) {      /* two neighbours per trip, every lane on the same path */                                                                      \
+                    int slot0, slot1;                                                                                                                                \
+                    next_hits2(hm_lane, nz, c, m, slot0, slot1);                                                                                                     \
+                    if (slot0 < 0) break;                                                                                                                            \
+                    force_pair<K, PERIODIC, MHD, XTRA, CP>(f, vsigmax, npair, slot0, ws.sidx, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei); \
+                    force_pair<K, PERIODIC, MHD, XTRA, CP>(f, vsigmax, npair, slot1, ws.sidx, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei); \
                 }
+                if (cp == 0) { FORCE_PAIR_LOOP(0) } else if (cp == 1) { FORCE_PAIR_LOOP(1) } else { FORCE_PAIR_LOOP(2) }
+#undef FORCE_PAIR_LOOP
+                __syncwarp();
             }
-            __syncwarp();
         }
         // ---- finish_cell_and_store_results (force.F90:2649-3330), lane = target ----
         if (act) {
@@ -984,7 +999,7 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     a.nodes = c->nodesf.p; a.cells = c->cells.p; a.ncells = (int)c->ncells; a.groups = c->groups.p; a.ngroups = (int)c->ngroups;
     a.pos4 = c->pos4.p; a.vel4 = c->vel4.p; a.recC = c->frecC.p; a.recD = c->frecD.p; a.recE = c->frecE.p; a.hinv = hinv; a.stype = c->stype.p; a.perm = c->perm.p;
     a.s_fxyzu = c->s_fxyzu.p; a.s_dB = c->s_dB.p; a.s_divvf = c->s_divvf.p; a.s_divBsymm = c->s_divBsymm.p; a.s_done = c->s_nneigh.p;
-    a.multitype = c->multitype ? 1 : 0; a.max_leaf = c->max_leaf;
+    a.multitype = c->multitype ? 1 : 0; a.max_leaf = c->max_leaf; a.class_mask = c->class_mask;
     a.cnt = c->counters.p; a.dscal = c->dscal.p; a.icall = icall;
     a.frec = c->frec.p;
     a.gsoft = c->s_gsoft.p; a.dvdx9 = c->s_dvdx.p; a.gacc = c->gacc.p; a.s_poten = c->s_poten.p; a.s_tstop = c->s_tstop.p;

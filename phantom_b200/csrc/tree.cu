@@ -106,8 +106,8 @@ __device__ __forceinline__ void key_frame(const unsigned long long *bbox_enc, co
     x0 = lo[0]; y0 = lo[1]; z0 = lo[2]; inv_scale = 1.0 / scale;
 }
 
-__global__ void k_keys(int64_t n, const double *__restrict__ xyzh, const unsigned long long *__restrict__ bbox_enc, const __grid_constant__ DevParams dp,
-                       unsigned long long *__restrict__ keys, int *__restrict__ idx, int hilbert)
+__global__ void k_keys(int64_t n, const double *__restrict__ xyzh, const int8_t *__restrict__ iphase, const unsigned long long *__restrict__ bbox_enc,
+                       const __grid_constant__ DevParams dp, unsigned long long *__restrict__ keys, int *__restrict__ idx, int hilbert)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -124,7 +124,8 @@ __global__ void k_keys(int64_t n, const double *__restrict__ xyzh, const unsigne
         unsigned ix = (unsigned)ux, iy = (unsigned)uy, iz = (unsigned)uz;
         if (hilbert) hilbert_transpose(ix, iy, iz);
         key = (spread21((unsigned long long)ix) << 2) | (spread21((unsigned long long)iy) << 1) | spread21((unsigned long long)iz);
-        key &= ~0xFFFFull;            // 16/16/15 bits per axis decide the order (6 radix passes instead of 8); ties are split by index
+        key = ((unsigned long long)sort_class(iphase[i]) << 61) | (key >> 2);     // bit 63 stays clear (cpl counts 63 key bits)
+        key &= ~0xFFFFull;            // 15 bits per axis decide the order (6 radix passes instead of 8); ties are split by index
     }
     keys[i] = key;
     idx[i] = (int)i;
@@ -146,6 +147,7 @@ __global__ void k_gather_pos(int64_t n, const int *__restrict__ perm, const doub
     // (dens.F90:717-723, force.F90:1539) and differ only in being inactive, which the fast kernels honour through get_partinfo
     const int ta = ph < 0 ? -ph : ph;
     if (!(ta == IGAS || (boundary_is_gas && ta == IBOUNDARY))) cnt[CNT_MULTITYPE] = 1ull;
+    { const int sc = sort_class(ph); if (sc == 1) cnt[CNT_CLASS1] = 1ull; else if (sc == 2) cnt[CNT_CLASS2] = 1ull; }
     // common leading bits (of the 63 key bits) with the previous key: 0..63
     unsigned char c = 0;
     if (s > 0) {
@@ -181,6 +183,7 @@ __global__ void k_cell_flags(int64_t n, const unsigned long long *__restrict__ c
     int count = 1, depth = 64;
     for (int d = 65; d >= 0; d--) { count += hist[d]; if (count <= tmax) depth = d; }
     if (depth > 64) depth = 64;
+    if (depth < 2) depth = 2;                   // the two class bits: a cell never holds two sort classes
     int f;
     if (s == 0) f = 1;
     else if (depth == 64) f = (cpl[s] < 63) || (s % tmax == 0);   // > tmax identical keys: split the run arbitrarily
@@ -308,20 +311,28 @@ __global__ void k_refit(const unsigned long long *__restrict__ tcnt, const Cell 
 }
 
 // target groups: maximal subtrees holding <= gmax particles (one lane per target in the pair kernels)
-__global__ void k_groups(const unsigned long long *__restrict__ cnt, int gmax, const Cell *__restrict__ cells, const TreeNode *__restrict__ nodes, Cell *__restrict__ groups,
-                         unsigned long long *ngroups)
+// (a subtree that spans two sort classes is never a group: the classes are key prefixes, so it is one of the top nodes of the tree)
+__device__ __forceinline__ bool mixed_classes(const int8_t *__restrict__ stype, int start, int count)
+{
+    return sort_class(stype[start]) != sort_class(stype[start + count - 1]);
+}
+
+__global__ void k_groups(const unsigned long long *__restrict__ cnt, int gmax, const Cell *__restrict__ cells, const TreeNode *__restrict__ nodes, const int8_t *__restrict__ stype,
+                         Cell *__restrict__ groups, unsigned long long *ngroups)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int M = (int)cnt[CNT_NCELLS];
     if (t >= 2 * M - 1 || cnt[CNT_CELLOVER]) return;
-    int me, parent, total;
-    if (t < M) { me = ~t; parent = cells[t].parent; total = cells[t].count; }
-    else { const int i = t - M; me = i; parent = nodes[i].parent; total = nodes[i].cnt[0] + nodes[i].cnt[1]; }
+    int me, parent, total, start;
+    if (t < M) { me = ~t; parent = cells[t].parent; total = cells[t].count; start = cells[t].start; }
+    else { const int i = t - M; me = i; parent = nodes[i].parent; total = nodes[i].cnt[0] + nodes[i].cnt[1]; start = min(nodes[i].start[0], nodes[i].start[1]); }
     if (total > gmax) return;
+    if (t >= M && mixed_classes(stype, start, total)) return;
     Cell g;
     if (parent >= 0) {
         const TreeNode &pn = nodes[parent];
-        if (pn.cnt[0] + pn.cnt[1] <= gmax) return;          // the parent is (inside) a group already
+        const int ptotal = pn.cnt[0] + pn.cnt[1];
+        if (ptotal <= gmax && !mixed_classes(stype, min(pn.start[0], pn.start[1]), ptotal)) return;          // the parent is (inside) a group already
         const int slot = (pn.child[0] == me) ? 0 : 1;
         for (int k = 0; k < 3; k++) { g.lo[k] = pn.lo[slot][k]; g.hi[k] = pn.hi[slot][k]; }
         g.hmax = pn.hmax[slot]; g.start = pn.start[slot]; g.count = pn.cnt[slot]; g.active = pn.act[slot]; g.parent = parent;
@@ -342,7 +353,7 @@ __global__ void k_groups(const unsigned long long *__restrict__ cnt, int gmax, c
 // scan[s] = index of the cell that starts at sorted slot s (k_cell_starts).  One thread per subtree: two passes (count, then write into
 // a contiguous block of group slots so that consecutive groups stay spatial neighbours).
 __global__ void k_groups_packed(const unsigned long long *__restrict__ cnt, int gmax, int smax, const Cell *__restrict__ cells, const TreeNode *__restrict__ nodes, const int *__restrict__ scan,
-                                Cell *__restrict__ groups, unsigned long long *ngroups)
+                                const int8_t *__restrict__ stype, Cell *__restrict__ groups, unsigned long long *ngroups)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int M = (int)cnt[CNT_NCELLS];
@@ -351,7 +362,11 @@ __global__ void k_groups_packed(const unsigned long long *__restrict__ cnt, int 
     if (t < M) { parent = cells[t].parent; total = cells[t].count; start = cells[t].start; }
     else { const TreeNode &nd = nodes[t - M]; parent = nd.parent; total = nd.cnt[0] + nd.cnt[1]; start = min(nd.start[0], nd.start[1]); }
     if (total > smax && t >= M) return;                     // (a single cell above smax cannot occur: cells hold <= 32 particles)
-    if (parent >= 0 && nodes[parent].cnt[0] + nodes[parent].cnt[1] <= smax) return;      // not maximal
+    if (t >= M && mixed_classes(stype, start, total)) return;
+    if (parent >= 0) {
+        const int ptotal = nodes[parent].cnt[0] + nodes[parent].cnt[1];
+        if (ptotal <= smax && !mixed_classes(stype, min(nodes[parent].start[0], nodes[parent].start[1]), ptotal)) return;      // not maximal
+    }
     const int c0 = (t < M) ? t : scan[start];
     int ng = 0, acc = 0;
     for (int cidx = c0, left = total; left > 0; cidx++) {   // pass 1: number of groups
@@ -410,9 +425,9 @@ static int build_groups(sphgpu_ctx *c, int64_t cap)
     unsigned long long *ng = c->counters.p + CNT_COUNT - 1;
     CUDA_TRY(c, cudaMemsetAsync(ng, 0, sizeof(unsigned long long), c->stream));
     if (c->group_pack > c->max_cell && c->max_leaf <= c->max_cell)
-        LAUNCH(c, k_groups_packed, nblk(2 * cap - 1, 128), 128, c->counters.p, c->max_cell, c->group_pack, c->cells.p, c->nodes.p, c->cellid_scan.p, c->groups.p, ng);
+        LAUNCH(c, k_groups_packed, nblk(2 * cap - 1, 128), 128, c->counters.p, c->max_cell, c->group_pack, c->cells.p, c->nodes.p, c->cellid_scan.p, c->stype.p, c->groups.p, ng);
     else
-        LAUNCH(c, k_groups, nblk(2 * cap - 1, 128), 128, c->counters.p, c->max_cell, c->cells.p, c->nodes.p, c->groups.p, ng);
+        LAUNCH(c, k_groups, nblk(2 * cap - 1, 128), 128, c->counters.p, c->max_cell, c->cells.p, c->nodes.p, c->stype.p, c->groups.p, ng);
     return SPHGPU_OK;
 }
 
@@ -466,7 +481,7 @@ int tree_build(sphgpu_ctx *c)
         unsigned long long *bbox_enc = c->counters.p + 16;
         CUDA_TRY(c, cudaMemsetAsync(bbox_enc, 0xff, sizeof(unsigned long long) * 3, c->stream));
         LAUNCH(c, k_wrap_count, c->numSMs * 8, 256, n, c->xyzh.p, c->hp, c->counters.p, bbox_enc);
-        LAUNCH(c, k_keys, nblk(n, 256), 256, n, c->xyzh.p, bbox_enc, c->hp, c->keys_alt.p, c->perm_alt.p, c->hilbert ? 1 : 0);
+        LAUNCH(c, k_keys, nblk(n, 256), 256, n, c->xyzh.p, c->iphase.p, bbox_enc, c->hp, c->keys_alt.p, c->perm_alt.p, c->hilbert ? 1 : 0);
         size_t tbb = c->cubtemp.cap;
         CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(c->cubtemp.p, tbb, c->keys_alt.p, c->keys.p, c->perm_alt.p, c->perm.p, (int)n, 16, 64, c->stream));
         c->launches += 7;
@@ -503,6 +518,7 @@ int tree_build(sphgpu_ctx *c)
     c->ncells = (int64_t)hc[CNT_NCELLS];
     c->ngroups = (int64_t)hc[CNT_COUNT - 1];
     c->multitype = hc[CNT_MULTITYPE] != 0;
+    c->class_mask = 1 | (hc[CNT_CLASS1] ? 2 : 0) | (hc[CNT_CLASS2] ? 4 : 0);
     c->grav_tree_valid = false; c->hscale = 1.; c->wl_force_ok = false;
     CUDA_TRY(c, cudaGetLastError());
     c->tree_valid = true;

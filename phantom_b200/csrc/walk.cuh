@@ -234,14 +234,16 @@ __device__ __forceinline__ FilterTarget filter_target(const FilterScale &fs, flo
 // Copy the particles of the next cells of the list into the shared-memory round buffer.  Two passes so that no load waits on another:
 // (1) lane = cell, 32 cells per step: one coalesced read of the packed list, a warp scan of the counts, slot -> particle index;
 // (2) lane = slot: the position records of all slots are fetched independently, scaled to FP16 and stored.
-// w = h (WINV = false) or 1/h (WINV = true).  Returns the number staged; cellpos advances.
+// w = h (WINV = false) or 1/h (WINV = true).  Returns the number staged; cellpos advances.  cls >= 0: only the cells of that sort
+// class are staged (general kernels: one pair body per class pair for the whole warp); a round may then come back empty.
 struct NoRecord { __device__ __forceinline__ void operator()(int, int, const double2 &, const double2 &) const {} };
 // posrec2[j * stride2] = {x, y}, [j * stride2 + 1] = {z, w}.  gstart: first sorted slot of the target group (selfslot bookkeeping);
 // stage_rec(slot, j, xy, zw): whatever else the caller wants staged.
 template <bool PERIODIC, bool WINV, class WS, class F = NoRecord>
 __device__ __forceinline__ int stage_round(WS &ws, const int *__restrict__ clist, int ncl, int &cellpos, const double2 *__restrict__ posrec2, int stride2,
                                            double cx, double cy, double cz, double Lx, double Ly, double Lz, float radkern, int maxleaf,
-                                           const FilterScale &fs, bool interior = false, int gstart = 0, F stage_rec = F())
+                                           const FilterScale &fs, bool interior = false, int gstart = 0, F stage_rec = F(), int cls = -1,
+                                           const int8_t *__restrict__ stype = nullptr)
 {
     constexpr int ROUND = WS::ROUND;
     ws.selfslot[lane_id()] = -1;
@@ -252,6 +254,7 @@ __device__ __forceinline__ int stage_round(WS &ws, const int *__restrict__ clist
         if (nb <= 0) break;
         int start = 0, cnt = 0;
         if (lane < nb) { const int pk = clist[cellpos + lane]; start = pk >> 5; cnt = (pk & 31) + 1; }
+        if (cls >= 0 && cnt > 0 && sort_class(stype[start]) != cls) cnt = 0;     // rounds of one sort class (cells never mix classes)
         int incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULLMASK, incl, d); if (lane >= d) incl += t; }

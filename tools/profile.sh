@@ -5,9 +5,9 @@
 #   gravity kernels : launch list + --set full capture of k_g_p2p / k_g_walk (C5, 1M)  -> gpurun_out/launches_grav.csv, prof_grav.ncu-rep
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_under_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k_density|k_force' -s 2 -c 2 -o gpurun_out/prof_pair -f \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/prof.log 2>&1
 if [ "$1" == "gravity" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_grav.csv \
     python tools/bench_gravity.py 1e6 2 > /dev/null 2>&1
