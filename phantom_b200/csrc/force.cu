@@ -109,7 +109,8 @@ __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const 
 }
 
 // get_ts (dust.f90:161-276): stopping time of a gas-dust pair
-__device__ __forceinline__ double get_ts_d(const sphgpu_params &p, double rhogas, double rhodust, double spsoundgas, double dv2)
+// (not inlined: the Stokes branch carries a pow(); one copy keeps the general kernel's pair loops inside the instruction cache)
+__device__ __noinline__ double get_ts_d(const sphgpu_params &p, double rhogas, double rhodust, double spsoundgas, double dv2)
 {
     const double pi = 3.14159265358979323846264338327950288;
     const double rhosum = rhogas + rhodust;
@@ -241,7 +242,7 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
                 const double dv2 = projvstar * projvstar;
                 const double wdrag = (q2i < q2j) ? KF::wdrag(q2i, qi) * hi21 * hi1 * KF::cnormk_drag : KF::wdrag(q2j, qj) * hj21 * hj1 * KF::cnormk_drag;
                 const double rhoi = 1. / Di.x, rhoj = 1. / Dj.x;
-                const double ts = gas_dust ? get_ts_d(p, rhoi, rhoj, Di.w, dv2) : get_ts_d(p, rhoj, rhoi, Dj.w, dv2);
+                const double ts = get_ts_d(p, gas_dust ? rhoi : rhoj, gas_dust ? rhoj : rhoi, gas_dust ? Di.w : Dj.w, dv2);
                 const double dragterm = 3. * Dj.z / ((rhoi + rhoj) * ts) * projvstar * wdrag;
                 xs.tsmin = fmin(xs.tsmin, ts);
                 xs.fdx -= dragterm * rx; xs.fdy -= dragterm * ry; xs.fdz -= dragterm * rz;
@@ -754,11 +755,17 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
                 int c = -1; unsigned m = 0u;
 #define FORCE_PAIR_LOOP(CP)                                                                                                                                          \
                 while (true) {      /* two neighbours per trip, every lane on the same path */                                                                      \
-                    int slot0, slot1;                                                                                                                                \
-                    next_hits2(hm_lane, nz, c, m, slot0, slot1);                                                                                                     \
-                    if (slot0 < 0) break;                                                                                                                            \
-                    force_pair<K, PERIODIC, MHD, XTRA, CP>(f, vsigmax, npair, slot0, ws.sidx, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei); \
-                    force_pair<K, PERIODIC, MHD, XTRA, CP>(f, vsigmax, npair, slot1, ws.sidx, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei); \
+                    int sl[2];                                                                                                                                       \
+                    next_hits2(hm_lane, nz, c, m, sl[0], sl[1]);                                                                                                     \
+                    if (sl[0] < 0) break;                                                                                                                            \
+                    if (CP == 0) {  /* gas-gas: both bodies inlined side by side, two independent FP64 chains */                                                    \
+                        force_pair<K, PERIODIC, MHD, XTRA, CP>(f, vsigmax, npair, sl[0], ws.sidx, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei); \
+                        force_pair<K, PERIODIC, MHD, XTRA, CP>(f, vsigmax, npair, sl[1], ws.sidx, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei); \
+                    } else {        /* one copy of the body: the general kernel is bound by instruction fetch, not by the FP64 pipe */                              \
+                        _Pragma("unroll 1")                                                                                                                          \
+                        for (int k = 0; k < 2; k++)                                                                                                                  \
+                            force_pair<K, PERIODIC, MHD, XTRA, CP>(f, vsigmax, npair, sl[k], ws.sidx, s, pi, h, hi1, hi21, gasi, vi, Ci, Di, Ei, a, dp, Lx, Ly, Lz, xs, itypei); \
+                    }                                                                                                                                                \
                 }
                 if (cp == 0) { FORCE_PAIR_LOOP(0) } else if (cp == 1) { FORCE_PAIR_LOOP(1) } else { FORCE_PAIR_LOOP(2) }
 #undef FORCE_PAIR_LOOP
