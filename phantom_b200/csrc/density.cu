@@ -92,7 +92,7 @@ __global__ void k_scatter_h(int64_t nlive, const int *__restrict__ perm, const i
     xyzh[4 * (size_t)perm[s] + 3] = h;
 }
 
-// overflow retry of the fast path: back to the h the tree was built with (k_hbuild keeps it in caller order)
+// overflow retry of the fast path: back to the h the tree was built with (k_wrap_count keeps it in caller order)
 __global__ void k_restore_h_sorted(int64_t nlive, const int *__restrict__ perm, const double *__restrict__ h_build, double4 *__restrict__ pos4,
                                    double *__restrict__ xyzh)
 {

@@ -30,12 +30,15 @@ __host__ __device__ __forceinline__ double dec_ordered(unsigned long long b)
 }
 
 // periodic wrap (boundary.f90:123-157), NaN check (kdtree.F90:391), live count, bounding box
-__global__ void k_wrap_count(int64_t n, double *__restrict__ xyzh, DevParams dp, unsigned long long *cnt, unsigned long long *bbox_enc)
+// (+ h as the tree is built with: start of the node-hmax history of the gravity tree and restore point of a halo-widening retry)
+__global__ void k_wrap_count(int64_t n, double *__restrict__ xyzh, DevParams dp, unsigned long long *cnt, unsigned long long *bbox_enc,
+                             double *__restrict__ h_build, int *__restrict__ h_its)
 {
     double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
     int nlive = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double4 x = reinterpret_cast<double4 *>(xyzh)[i];
+        h_build[i] = x.w; h_its[i] = 0;
         if (!(x.w < DBL_MIN)) {
             if (dp.p.periodic) {
                 bool ch = false;
@@ -165,23 +168,24 @@ __global__ void k_cell_flags(int64_t n, const unsigned long long *__restrict__ c
     const int64_t nlive = (int64_t)cnt[CNT_NLIVE];
     if (s >= n) return;
     if (s >= nlive) { flag[s] = 0; return; }
-    unsigned char hist[66];
-    for (int d = 0; d < 66; d++) hist[d] = 0;
-    int m = 65;
-    for (int k = 1; k <= tmax; k++) {           // to the left: m_k = min cpl over (s-k+1 .. s)
-        if (s - k < 0) break;
-        m = min(m, (int)cpl[s - k + 1]);
-        hist[m]++;
+    // depth = shallowest d at which at most tmax particles share their first d key bits with s.  Particle s-k shares
+    // mL_k = min cpl(s-k+1..s) bits with s, particle s+k shares mR_k = min cpl(s+1..s+k); both sequences fall with k, so the tmax-th
+    // largest of all of them comes out of a merge of at most tmax steps, and depth is one more than it (0 if there are fewer).
+    int kL = 1, kR = 1;
+    int curL = (s - 1 >= 0) ? (int)cpl[s] : -1, curR = (s + 1 < nlive) ? (int)cpl[s + 1] : -1;
+    int depth = 0;
+    for (int t = 1; t <= tmax; t++) {
+        if (curL < 0 && curR < 0) break;                     // fewer than tmax others in reach: everything fits at depth 0
+        if (curL >= curR) {
+            if (t == tmax) depth = curL + 1;
+            kL++;
+            curL = (kL <= tmax && s - kL >= 0) ? min(curL, (int)cpl[s - kL + 1]) : -1;
+        } else {
+            if (t == tmax) depth = curR + 1;
+            kR++;
+            curR = (kR <= tmax && s + kR < nlive) ? min(curR, (int)cpl[s + kR]) : -1;
+        }
     }
-    m = 65;
-    for (int k = 1; k <= tmax; k++) {           // to the right: min cpl over (s+1 .. s+k)
-        if (s + k >= nlive) break;
-        m = min(m, (int)cpl[s + k]);
-        hist[m]++;
-    }
-    // count(d) = particles sharing the first d bits with s (inside the window) ; depth = shallowest d with count <= tmax
-    int count = 1, depth = 64;
-    for (int d = 65; d >= 0; d--) { count += hist[d]; if (count <= tmax) depth = d; }
     if (depth > 64) depth = 64;
     if (depth < 2) depth = 2;                   // the two class bits: a cell never holds two sort classes
     int f;
@@ -389,14 +393,6 @@ __global__ void k_groups_packed(const unsigned long long *__restrict__ cnt, int 
     if (g.count > 0) groups[slot] = g;
 }
 
-// gravity: the reference's node hmax starts from the h the tree was built with (kdtree.F90:654-666)
-__global__ void k_hbuild(int64_t n, const double *__restrict__ xyzh, double *__restrict__ h_build, int *__restrict__ h_its)
-{
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    h_build[i] = xyzh[4 * i + 3]; h_its[i] = 0;
-}
-
 __global__ void k_cell_hmax(int64_t ncells, Cell *__restrict__ cells, const double4 *__restrict__ pos4)
 {
     int64_t cidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -480,7 +476,7 @@ int tree_build(sphgpu_ctx *c)
         // bbox accumulators (ordered encoding): min slots start at all-ones, max slots at zero
         unsigned long long *bbox_enc = c->counters.p + 16;
         CUDA_TRY(c, cudaMemsetAsync(bbox_enc, 0xff, sizeof(unsigned long long) * 3, c->stream));
-        LAUNCH(c, k_wrap_count, c->numSMs * 8, 256, n, c->xyzh.p, c->hp, c->counters.p, bbox_enc);
+        LAUNCH(c, k_wrap_count, c->numSMs * 8, 256, n, c->xyzh.p, c->hp, c->counters.p, bbox_enc, c->h_build.p, c->h_its.p);
         LAUNCH(c, k_keys, nblk(n, 256), 256, n, c->xyzh.p, c->iphase.p, bbox_enc, c->hp, c->keys_alt.p, c->perm_alt.p, c->hilbert ? 1 : 0);
         size_t tbb = c->cubtemp.cap;
         CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(c->cubtemp.p, tbb, c->keys_alt.p, c->keys.p, c->perm_alt.p, c->perm.p, (int)n, 16, 64, c->stream));
@@ -501,8 +497,6 @@ int tree_build(sphgpu_ctx *c)
             LAUNCH(c, k_refit, nblk(cap, 128), 128, c->counters.p, c->cells.p, c->nodes.p, c->nodesf.p, c->nodeflag.p);
         }
         TRY(build_groups(c, cap));
-        // h as the tree was built with: start of the node-hmax history (gravity) and restore point of a halo-widening retry
-        LAUNCH(c, k_hbuild, nblk(n, 256), 256, n, c->xyzh.p, c->h_build.p, c->h_its.p);
         CUDA_TRY(c, cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         if (hc[CNT_ERR]) {
