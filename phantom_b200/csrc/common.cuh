@@ -167,6 +167,7 @@ struct sphgpu_ctx {
     DevBuf<TreeNode> nodes;
     DevBuf<TreeNodeF> nodesf;
     bool multitype = false;                 // any particle that is not plain gas (boundary, dust, ...)
+    bool dens_reuse = false;                // the last density pass iterated: keep staged rounds and masks over the h-rho iterations
     int class_mask = 1;                     // sort classes present (bit 0 gas/boundary, 1 dust, 2 other): the class rounds of the general pair kernels
     DevBuf<int> wl_list, wl_ncl; DevBuf<float> wl_reach;   // cell lists prepared by k_walk_lists (walk.cuh)
     bool stream_blocking = false;   // the compute stream synchronises implicitly with the legacy default stream (option "legacy_stream")

@@ -34,6 +34,7 @@ struct DensArgs {
     double *h_hist; int *h_its; int64_t npart;     // GRAV: per-particle h after every iteration, for the node-hmax replay of gravity.cu
     int scratch_per_warp; unsigned long long *cnt; double *dscal;
     double margin; int icall;
+    double mask_margin;   // > 0: the FP16 hit masks are built for radkern h (1 + mask_margin) so that the next h-rho iteration can reuse them
 };
 
 // DENS_STAGE = 1: the fast kernel keeps the candidates' FP64 positions in shared memory (measured 1.53 vs 1.64 ms on turb 128^3 against
@@ -306,7 +307,7 @@ template <bool FAST, bool BIG> struct DensShared { typedef WarpSharedGeneral typ
 template <> struct DensShared<true, false> { typedef WarpSharedT<DENS_ROUND, DENS_STAGE, DENS_STAGE, !DENS_STAGE> type; };
 template <> struct DensShared<true, true> { typedef WarpSharedT<DENS_ROUND_BIG, 0, 0> type; };
 
-template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST, bool BIG>
+template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST, bool BIG, bool REUSE>
 #ifndef DENS_MINB
 #define DENS_MINB 3
 #endif
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
     typedef SphKern<K> KF;
     typedef typename DensShared<FAST, BIG>::type WS;
     constexpr bool STAGED = FAST && WS::P2 > 0;
+    constexpr bool RU = FAST && REUSE;          // keep the staged round and its masks over the h-rho iterations (see below)
     extern __shared__ __align__(16) unsigned char dens_smem[];
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     WS &ws = reinterpret_cast<WS *>(dens_smem)[wib];
@@ -397,6 +399,10 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                        cell.lo[2] - rr > dp.p.zmin && cell.hi[2] + rr < dp.p.zmax;
         }
 
+        // fast path, group staged in ONE round: the staged candidates stay in shared memory over the h-rho iterations, and so do the hit
+        // masks while every unconverged target's kernel radius stays inside the radius its mask was built for (the exact FP64 test in
+        // the pair body decides membership with the current h either way)
+        bool staged_all = false; int nr_saved = 0;
         for (int its = 1;; its++) {                                  // local_its (dens.F90:338-373): the cell iterates until every particle converged
             // compute_hmax / redo_neighbours (dens.F90:1275-1289, :343-347)
             const double hneed = warp_max(conv ? 0. : h);
@@ -408,6 +414,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                 ncl = warp_walk<false, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut_list), (float)radkern, fLx, fLy, fLz, ws.walk_stack(),
                                                  clist, a.scratch_per_warp, reach);
                 cl = clist;
+                staged_all = false;
                 st_nwalk += (lane == 0);
                 if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); failed = true; }
                 if (FAST && PERIODIC) {
@@ -419,7 +426,9 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
             if (__any_sync(FULLMASK, failed)) break;
             const FilterScale fs = filter_scale((float)halfext, reach);
             // converged / inactive targets get an empty mask; a wide periodic search switches the filter off
-            const FilterTarget ft = filter_target(fs, xif, yif, zif, conv ? 0.f : (wide ? -1.f : __double2float_ru(radkern * h)));
+            const double rfilt = RU ? radkern * h * (1. + a.mask_margin) : radkern * h;
+            const FilterTarget ft = filter_target(fs, xif, yif, zif, conv ? 0.f : (wide ? -1.f : __double2float_ru(rfilt)));
+            const bool masks_ok = RU && staged_all && its > 1 && __all_sync(FULLMASK, conv || radkern * h <= (double)ws.rmask[lane]);
             if (!conv) {
 #pragma unroll
                 for (int k = 0; k < 29; k++) v[k] = 0.;
@@ -444,11 +453,23 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                 auto stage_rec = [&](int slot, int, const double2 &xy, const double2 &zw) {      // fast path: FP64 positions to shared memory
                     if (STAGED) { ws.rec2[0][slot] = xy; ws.rec1[0][slot] = zw.x; }
                 };
-                const int nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf, fs, interior,
-                                                            cell.start, stage_rec, FAST ? -1 : cj, a.stype);
+                int nr;
+                bool reuse = false;
+                if (RU && staged_all) { nr = nr_saved; cellpos = ncl; reuse = masks_ok; }
+                else {
+                    const int cp0 = cellpos;
+                    nr = stage_round<PERIODIC, false>(ws, cl, ncl, cellpos, posrec, pstride, cx, cy, cz, Lx, Ly, Lz, (float)radkern, a.max_leaf, fs, interior,
+                                                      cell.start, stage_rec, FAST ? -1 : cj, a.stype);
+                    if (RU) { staged_all = (cp0 == 0 && cellpos >= ncl); nr_saved = nr; }
+                }
                 if (!FAST && nr == 0) continue;
                 nlist += nr;
-                unsigned nz = build_masks<false>(ws, nr, ft);
+                unsigned nz;
+                if (RU && reuse) nz = conv ? 0u : ws.nzsave[lane];
+                else {
+                    nz = build_masks<false>(ws, nr, ft);
+                    if (RU) { ws.nzsave[lane] = nz; ws.rmask[lane] = conv ? 0.f : (wide ? 3.0e38f : __double2float_rd(rfilt)); }
+                }
                 int c = -1; unsigned m = 0u;
                 if (FAST) {
                     int surv = 0;
@@ -617,17 +638,17 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
 }
 
 // grid < 0: only query the resident CTAs/SM of the instantiation; otherwise launch on `grid` CTAs
-template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST, bool BIG>
+template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST, bool BIG, bool REUSE>
 int launch_density2(sphgpu_ctx *c, const DensArgs &a, int grid)
 {
     const size_t smem = 4 * sizeof(typename DensShared<FAST, BIG>::type);
-    cudaFuncSetAttribute(k_density<K, PERIODIC, MHD, GRAV, FAST, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_density<K, PERIODIC, MHD, GRAV, FAST, BIG, REUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (grid < 0) {
         int bps = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_density<K, PERIODIC, MHD, GRAV, FAST, BIG>, 128, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_density<K, PERIODIC, MHD, GRAV, FAST, BIG, REUSE>, 128, smem);
         return bps < 1 ? 1 : bps;
     }
-    k_density<K, PERIODIC, MHD, GRAV, FAST, BIG><<<grid, 128, smem, c->stream>>>(a, c->hp);
+    k_density<K, PERIODIC, MHD, GRAV, FAST, BIG, REUSE><<<grid, 128, smem, c->stream>>>(a, c->hp);
     c->launches++;
     return 0;
 }
@@ -635,8 +656,13 @@ template <int K, bool PERIODIC, bool MHD, bool GRAV, bool FAST>
 int launch_density(sphgpu_ctx *c, const DensArgs &a, int grid)
 {
     // the previous pass staged more candidates per group than one small round holds: take the big rounds
-    if (FAST && c->dens_trial_max > DENS_ROUND && c->dens_trial_hint > 0.8 * DENS_ROUND) return launch_density2<K, PERIODIC, MHD, GRAV, FAST, FAST>(c, a, grid);
-    return launch_density2<K, PERIODIC, MHD, GRAV, FAST, false>(c, a, grid);
+    // (and a set that iterated last time -- a.mask_margin > 0 -- takes the instantiation that keeps round and masks over the iterations;
+    // it exists with the big rounds only: disordered sets are the ones that iterate, and the extra state costs the lattice kernel spills)
+    if (FAST && c->dens_trial_max > DENS_ROUND && c->dens_trial_hint > 0.8 * DENS_ROUND) {
+        if (c->dens_reuse) return launch_density2<K, PERIODIC, MHD, GRAV, FAST, FAST, FAST>(c, a, grid);
+        return launch_density2<K, PERIODIC, MHD, GRAV, FAST, FAST, false>(c, a, grid);
+    }
+    return launch_density2<K, PERIODIC, MHD, GRAV, FAST, false, false>(c, a, grid);
 }
 
 template <int K, bool PERIODIC, bool FAST>
@@ -677,6 +703,7 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     CUDA_TRY(c, c->hnew.ensure(n)); CUDA_TRY(c, c->s_nneigh.ensure(n));
     DensArgs a;
     memset(&a, 0, sizeof a);
+    c->dens_reuse = c->last_dens.np > 0 && (double)c->last_dens.nrhocalc > 1.2 * (double)c->last_dens.np;
     const int grid = c->numSMs * dispatch_density(c, a, -1);     // persistent grid = resident CTAs/SM x SMs
     const bool fast = !density_is_general(c);
     if (fast) CUDA_TRY(c, c->drec.ensure(4 * (size_t)n));
@@ -692,6 +719,8 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
     a.multitype = c->multitype ? 1 : 0; a.max_leaf = c->max_leaf; a.class_mask = c->class_mask; a.hmax_global = 0.;
     a.cnt = c->counters.p; a.dscal = c->dscal.p;
     a.margin = c->list_margin; a.icall = icall;
+    // a set that needed a second h-rho iteration last time will need one again: build the masks a little wide and keep them
+    a.mask_margin = c->dens_reuse ? 0.005 : 0.;
     // the node-hmax replay of the reference tree (self-gravity, and the reference-compatible neighbour mode) needs every particle's h history
     const bool loghist = p.gravity || refcompat_on(c);
     if (loghist) CUDA_TRY(c, c->h_hist.ensure((size_t)SPHGPU_HHIST * n));

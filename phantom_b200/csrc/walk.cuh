@@ -40,6 +40,8 @@ struct __align__(16) WarpSharedT {
     int sidx[ROUND_];                   // their sorted particle slots
     unsigned hm[NCHUNK][32];            // hm[chunk][t] = candidates of the chunk inside target t's (FP16, conservative) radius
     int selfslot[32];                   // slot at which target t itself is staged in this round, -1 if it is not
+    unsigned nzsave[32];                // density pass: the lane's non-empty mask words and the radius its masks were built for, kept
+    float rmask[32];                    // over the h-rho iterations of a group that was staged in one round (out of the registers)
     double2 rec2[P2_ > 0 ? P2_ : 1][P2_ > 0 ? ROUND_ : 1];     // structure of arrays: conflict-free staging stores
     double rec1[P1_ > 0 ? P1_ : 1][P1_ > 0 ? ROUND_ : 1];
 };

@@ -116,6 +116,39 @@ def test_derivs_parity_isothermal_random_h():
     assert sg[0].nactualtot == so[0].nactualtot
 
 
+@pytest.mark.parametrize("mhd,gravity", [(False, False), (True, False)])
+def test_derivs_parity_iterating_set_second_call(mhd, gravity):
+    """A set whose h-rho iteration did real work in the previous call takes the density instantiation that keeps the staged round and
+    its hit masks over the iterations (density.cu: REUSE; masks built 0.5 % wide, the exact FP64 test decides).  Same state handed
+    over twice: the second call must give the oracle's h, forces and neighbour totals and the iteration counts of the plain
+    instantiation, whether a particle needs one, two or more iterations."""
+    part, _ = setups.setup_test_derivs(nx=22, lattice="random", mhd=mhd)
+    rng = setups.Ran2(-9753)
+    fac = 0.9 + 0.25 * rng.draw(part.npart)
+    fac[::7] = 1.0                                   # some particles start converged
+    part.alphaind[:, 0] = 0.5
+    po = part.copy()
+    o = Oracle(po.params)
+    o.derivs(po)                                     # converged h
+    start = part.copy()
+    start.xyzh[:, 3] = po.xyzh[:, 3] * fac
+    po2 = start.copy()
+    o2 = Oracle(po2.params)
+    sdo, sfo = o2.derivs(po2)
+    assert sdo.nrhocalc > 1.5 * sdo.np               # the set iterates
+    g = gpu(start.params)
+    warm = start.copy()
+    sw = g.derivs(warm)                              # first call: plain instantiation, sets the hint
+    pg = start.copy()
+    sg = g.derivs(pg)
+    check_hydro(po2, pg, mhd=mhd)
+    assert rel_err(pg.xyzh[:, 3], warm.xyzh[:, 3], 0.) < 1e-13                               # and so does the plain instantiation
+    assert sg.nactualtot == sdo.nactualtot and sg.maxactual == sdo.maxactual and sg.npairs_force == sfo.npairs_force
+    # iteration counts: per particle here, per leaf cell of its own tree in the oracle -- the two instantiations must agree with each other
+    assert sg.nrhocalc == sw.nrhocalc and sg.nrhocalc > 1.5 * sg.np, (sg.nrhocalc, sw.nrhocalc, sdo.nrhocalc, sg.np)
+    assert sg.npairs_density == sw.npairs_density
+
+
 def test_derivs_parity_quintic():
     part, _ = setups.setup_test_derivs(nx=18, lattice="random", kernel=1, hfact=1.0)
     part.alphaind[:, 0] = 0.3
