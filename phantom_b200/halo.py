@@ -16,7 +16,7 @@ for this path:
 The product path is `DistSph` below: selection, packing, the grouped NCCL transfers, unpacking, the migration of particles that
 leave their box and the reductions all run inside the library (phantom_b200/csrc/dist.cu, `sphgpu_dist_*` of include/sphgpu.h).
 The numpy functions of this module restate the device kernels' rules (bisection, ownership, ghost selection) for the gloo tests,
-which run the same protocol on CPU with the oracle as the compute stand-in.
+which run the same protocol on CPU with the test suite's CPU restatement as the compute stand-in.
 """
 import math
 import numpy as np
