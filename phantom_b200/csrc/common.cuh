@@ -167,6 +167,8 @@ struct sphgpu_ctx {
     DevBuf<TreeNode> nodes;
     DevBuf<TreeNodeF> nodesf;
     bool multitype = false;                 // any particle that is not plain gas (boundary, dust, ...)
+    bool eos_on_device = false;             // eos_vars (P, c_s) were written by cons2prim_run after the last upload of that array
+    bool no_iso1 = false;                   // option: keep the three-sector force records for isothermal sets too (A/B, tests)
     bool dens_reuse = false;                // the last density pass iterated: keep staged rounds and masks over the h-rho iterations
     int class_mask = 1;                     // sort classes present (bit 0 gas/boundary, 1 dust, 2 other): the class rounds of the general pair kernels
     DevBuf<int> wl_list, wl_ncl; DevBuf<float> wl_reach;   // cell lists prepared by k_walk_lists (walk.cuh)

@@ -72,6 +72,7 @@ int cons2prim_run(sphgpu_ctx *c)
     k_cons2prim<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(n, c->xyzh.p, c->vxyzu.p, c->dvdx.p, c->Bevol.p, c->iphase.p, c->eos_vars.p, c->alphaind.p,
                                                                  c->hp.p.mhd ? c->Bxyz.p : nullptr, c->hp, c->counters.p);
     c->launches++;
+    c->eos_on_device = true;
     CUDA_TRY(c, cudaGetLastError());
     return SPHGPU_OK;
 }

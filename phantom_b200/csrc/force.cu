@@ -19,6 +19,7 @@ namespace {
 struct ForceArgs {
     const TreeNodeF *nodes; const Cell *cells; int ncells; const Cell *groups; int ngroups;
     int *stage_idx; int multitype; int max_leaf; int class_mask;
+    int iso1; double iso_pmass, iso_hfact, iso_polyk, iso_cs, iso_cnormk, iso_alpha;   // two-sector records of the isothermal fast path (iso1_derive)
     WalkLists wl;       // cell lists prepared by k_walk_lists
     const double4 *pos4, *vel4, *recC, *recD, *recE; const double2 *hinv; const int8_t *stype; const int *perm;
     double4 *s_fxyzu, *s_dB; float *s_divvf, *s_divBsymm; int *s_done;
@@ -46,7 +47,7 @@ __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const 
                              const __grid_constant__ DevParams dp, unsigned long long *cnt, double *__restrict__ gsoft, const float *__restrict__ dvdx,
                              float *__restrict__ dvdx9, const int8_t *__restrict__ ibin, const int8_t *__restrict__ ibin_old,
                              const int8_t *__restrict__ ibin_wake, int8_t *__restrict__ s_ibin, int8_t *__restrict__ s_ibinold, int *__restrict__ s_wake,
-                             double4 *__restrict__ frec)
+                             double4 *__restrict__ frec, int iso1)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nlive) return;
@@ -92,13 +93,19 @@ __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const 
     s_done[s] = 0;
     if (frec) {                                                  // packed j-records of the all-gas fast path
         const double4 x = pos4[s];
-        const int fstride = p.mhd ? 5 : ((dp.nvu >= 4 || p.gravity) ? 4 : 3);
+        const int fstride = iso1 ? 2 : (p.mhd ? 5 : ((dp.nvu >= 4 || p.gravity) ? 4 : 3));
         double4 *r = frec + fstride * (size_t)s;
         r[0] = make_double4(x.x, x.y, x.z, h1);
-        r[1] = make_double4(v[0], v[1], v[2], gradhfac);
-        r[2] = make_double4(pro2, vwave, alpha * vwave, rho1);
-        if (fstride >= 4) r[3] = make_double4(pr, dp.nvu >= 4 ? v[3] : 0., p.gravity ? (double)gradh[(size_t)dp.ngradh * i + 1] : cs, alpha);
-        if (fstride >= 5) r[4] = E;
+        if (iso1) {          // gradh and alpha as the real*4 the reference stores; everything else of the record follows from h (iso1_derive)
+            const float ghf = gradh[(size_t)dp.ngradh * i];
+            const float alf = p.const_av ? 0.f : alphaind[3 * (size_t)i];
+            r[1] = make_double4(v[0], v[1], v[2], __hiloint2double(__float_as_int(alf), __float_as_int(ghf > 0.f ? ghf : 1.f)));
+        } else {
+            r[1] = make_double4(v[0], v[1], v[2], gradhfac);
+            r[2] = make_double4(pro2, vwave, alpha * vwave, rho1);
+            if (fstride >= 4) r[3] = make_double4(pr, dp.nvu >= 4 ? v[3] : 0., p.gravity ? (double)gradh[(size_t)dp.ngradh * i + 1] : cs, alpha);
+            if (fstride >= 5) r[4] = E;
+        }
     }
     if (p.gravity) gsoft[s] = (double)gradh[(size_t)dp.ngradh * i + 1];
     if (p.dust) {
@@ -355,9 +362,36 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
 #ifndef FORCE_ROUND_BIG
 #define FORCE_ROUND_BIG 768
 #endif
+// Isothermal (ieos = 1) hydro without self-gravity: P = polyk rho and c_s = sqrt(polyk) (eos.f90, cons2prim.cu) make every entry of
+// the third sector a function of h, so the neighbour record shrinks from three 32-byte sectors to two -- {x, y, z, 1/h} {v, (gradh,
+// alpha) as the two real*4 the reference stores} -- and the L1 data pipe, which bounds this kernel, carries a third less.  Target
+// and neighbour side go through the same function.  1/rho by a branch-free reciprocal (two Newton steps on the hardware seed).
+struct Iso1 { double gradhfac, pro2, avw, rho1; };
+__device__ __forceinline__ double rcp_pos(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ Iso1 iso1_derive(double h1, double packed, const ForceArgs &a)
+{
+    Iso1 r;
+    const double gh = (double)__int_as_float(__double2loint(packed));
+    const double al = a.iso1 == 2 ? a.iso_alpha : (double)__int_as_float(__double2hiint(packed));     // iso1 == 2: constant alpha
+    const double h21 = h1 * h1, hf = a.iso_hfact * h1;
+    r.gradhfac = h21 * h21 * a.iso_cnormk * gh;                  // force.F90:1327, as k_force_prep
+    r.rho1 = rcp_pos(a.iso_pmass * (hf * hf * hf));              // rhoanddhdrho (part.F90:805-817)
+    r.pro2 = a.iso_polyk * r.rho1;                               // P / rho^2
+    r.avw = al * a.iso_cs;
+    return r;
+}
+
 template <bool MHD, bool BIG> struct ForceFastSharedT { typedef WarpSharedT<BIG ? FORCE_ROUND_BIG : FORCE_ROUND, (FORCE_STAGE && !MHD && !BIG) ? 2 : 0, 0, !(FORCE_STAGE && !MHD && !BIG)> type; };
 
-template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS, bool BIG>
+template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS, bool BIG, bool ISO1>
 #ifndef FORCE_MINB
 #define FORCE_MINB 4
 #endif
@@ -388,7 +422,8 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
     const double pmass = p.massoftype[IGAS];
     const double beta = p.beta;
     constexpr bool USEJ = MHD || (ADIA && !GRAV);                    // force.F90:1343-1345 without dust
-    constexpr int FSTRIDE = MHD ? 5 : ((ADIA || GRAV) ? 4 : 3);     // double4 per packed record
+    static_assert(!ISO1 || (!MHD && !ADIA && !GRAV), "two-sector records: isothermal hydro only");
+    constexpr int FSTRIDE = ISO1 ? 2 : (MHD ? 5 : ((ADIA || GRAV) ? 4 : 3));     // double4 per packed record
 
     while (true) {
         int cellid = 0;
@@ -422,7 +457,10 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
         bool act = false;
         { bool g_, d_; int t_; if (lane < cell.count) get_partinfo_d(a.stype[s], p.set_boundaries_to_active, 0, act, g_, d_, t_); }
         const double4 *ri = a.frec + FSTRIDE * (size_t)s;
-        const double4 T0 = ri[0], T1 = ri[1], T2 = ri[2];
+        const double4 T0 = ri[0];
+        double4 T1 = ri[1], T2;
+        if (ISO1) { const Iso1 di = iso1_derive(T0.w, T1.w, a); T1.w = di.gradhfac; T2 = make_double4(di.pro2, a.iso_cs, di.avw, di.rho1); }
+        else T2 = ri[2];
         double4 T3 = make_double4(0., 0., 0., 0.), T4 = T3;
         if (ADIA || MHD || GRAV) T3 = ri[3];
         if (MHD) T4 = ri[4];
@@ -465,9 +503,17 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
                         const double2 XY = lds_d2(rec2_s + 16u * (unsigned)sl[k]), ZW = lds_d2(rec2_s + 16u * (unsigned)(WS::ROUND + sl[k]));
                         R0[k] = make_double4(XY.x, XY.y, ZW.x, ZW.y);
                     } else R0[k] = ldg256(rj);
-                    R1[k] = ldg256(rj + 1); R2[k] = ldg256(rj + 2);
+                    R1[k] = ldg256(rj + 1);
+                    if (!ISO1) R2[k] = ldg256(rj + 2);
                     if (ADIA || GRAV) R3[k] = ldg256(rj + 3);
                     if (MHD) E[k] = ldg256(rj + 4);
+                }
+                if (ISO1) {
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const Iso1 dj = iso1_derive(R0[k].w, R1[k].w, a);
+                        R1[k].w = dj.gradhfac; R2[k] = make_double4(dj.pro2, a.iso_cs, dj.avw, dj.rho1);
+                    }
                 }
                 double dx[2], dy[2], dz[2];
 #pragma unroll
@@ -907,6 +953,14 @@ __global__ void k_scatter_force(int64_t nlive, const int *__restrict__ perm, con
     }
 }
 
+// two-sector records (iso1_derive): isothermal equation of state whose P and c_s this library computed itself (cons2prim_run since
+// the last upload of eos_vars), energy not evolved, no MHD, no self-gravity
+static bool force_iso1(const sphgpu_ctx *c)
+{
+    const sphgpu_params &p = c->hp.p;
+    return c->eos_on_device && p.ieos == 1 && c->hp.nvu < 4 && !p.mhd && !p.gravity && !c->no_iso1;
+}
+
 // grid < 0: only query the resident CTAs/SM of the instantiation; otherwise launch on `grid` CTAs
 template <int K, bool PERIODIC, bool MHD>
 int launch_force_general(sphgpu_ctx *c, const ForceArgs &a, int grid)
@@ -922,19 +976,25 @@ int launch_force_general(sphgpu_ctx *c, const ForceArgs &a, int grid)
     c->launches++;
     return 0;
 }
+template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS, bool BIG, bool ISO1>
+int launch_force_fast4(sphgpu_ctx *c, const ForceArgs &a, int grid)
+{
+    const size_t smem = 4 * sizeof(typename ForceFastSharedT<MHD, BIG>::type);
+    cudaFuncSetAttribute(k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS, BIG, ISO1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (grid < 0) {
+        int bps = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS, BIG, ISO1>, 128, smem);
+        return bps < 1 ? 1 : bps;
+    }
+    k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS, BIG, ISO1><<<grid, 128, smem, c->stream>>>(a, c->hp);
+    c->launches++;
+    return 0;
+}
 template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS, bool BIG>
 int launch_force_fast3(sphgpu_ctx *c, const ForceArgs &a, int grid)
 {
-    const size_t smem = 4 * sizeof(typename ForceFastSharedT<MHD, BIG>::type);
-    cudaFuncSetAttribute(k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (grid < 0) {
-        int bps = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS, BIG>, 128, smem);
-        return bps < 1 ? 1 : bps;
-    }
-    k_force_fast<K, PERIODIC, MHD, ADIA, GRAV, INDTS, BIG><<<grid, 128, smem, c->stream>>>(a, c->hp);
-    c->launches++;
-    return 0;
+    if (!MHD && !ADIA && !GRAV && force_iso1(c)) return launch_force_fast4<K, PERIODIC, MHD, ADIA, GRAV, INDTS, BIG, !MHD && !ADIA && !GRAV>(c, a, grid);
+    return launch_force_fast4<K, PERIODIC, MHD, ADIA, GRAV, INDTS, BIG, false>(c, a, grid);
 }
 template <int K, bool PERIODIC, bool MHD, bool ADIA, bool GRAV, bool INDTS>
 int launch_force_fast2(sphgpu_ctx *c, const ForceArgs &a, int grid)
@@ -1012,6 +1072,8 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     a.gsoft = c->s_gsoft.p; a.dvdx9 = c->s_dvdx.p; a.gacc = c->gacc.p; a.s_poten = c->s_poten.p; a.s_tstop = c->s_tstop.p;
     a.s_ibinold = c->s_ibinold.p; a.s_ibin = c->s_ibin.p; a.s_wake = c->s_wake.p; a.s_ibinnew = c->s_ibinnew.p;
     a.hscale = c->hscale;
+    a.iso1 = (fast && force_iso1(c)) ? (p.const_av ? 2 : 1) : 0;
+    a.iso_pmass = p.massoftype[IGAS]; a.iso_hfact = p.hfact; a.iso_polyk = p.polyk; a.iso_cs = sqrt(p.polyk); a.iso_cnormk = c->hp.kc.cnormk; a.iso_alpha = p.alpha;
     a.nbinmax = c->nbinmax; a.ibinnow_m1 = c->ibinnow - 1; a.istepfrac = c->istepfrac;
     if (p.ind_timesteps && refcompat_on(c) && c->dens_valid) {           // reference-compatible neighbour sets (common.cuh: refcompat)
         TRY(refcompat_prepare(c));
@@ -1033,7 +1095,7 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
         k_force_prep<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, c->perm.p, c->pos4.p, c->stype.p, c->vxyzu.p, c->Bevol.p, c->eos_vars.p, c->alphaind.p, c->gradh.p,
                                                            c->vel4.p, c->frecC.p, c->frecD.p, c->frecE.p, hinv, c->s_nneigh.p, c->hp, c->counters.p,
                                                            c->s_gsoft.p, c->dvdx.p, c->s_dvdx.p, c->ibin.p, c->ibin_old.p, c->ibin_wake.p, c->s_ibin.p,
-                                                           c->s_ibinold.p, c->s_wake.p, fast ? c->frec.p : nullptr);
+                                                           c->s_ibinold.p, c->s_wake.p, fast ? c->frec.p : nullptr, a.iso1);
         c->launches++;
         a.stage_idx = c->stage_idx.p; a.scratch_per_warp = c->scratch_per_warp;
         cudaEventRecord(c->ev[10], c->stream);

@@ -155,6 +155,7 @@ int sphgpu_set_option(sphgpu_ctx *c, const char *name, double value)
     if (!strcmp(name, "max_cell")) { int v = (int)value; c->max_cell = v < 1 ? 1 : (v > 32 ? 32 : v); c->tree_valid = false; return 0; }
     if (!strcmp(name, "group_pack")) { int v = (int)value; c->group_pack = v < 0 ? 0 : (v > 4096 ? 4096 : v); c->tree_valid = false; return 0; }
     if (!strcmp(name, "max_leaf")) { int v = (int)value; c->max_leaf = v < 1 ? 1 : (v > 32 ? 32 : v); c->tree_valid = false; return 0; }
+    if (!strcmp(name, "no_iso1")) { c->no_iso1 = value != 0.; return 0; }
     if (!strcmp(name, "list_margin")) { c->list_margin = value < 1. ? 1. : value; return 0; }
     if (!strcmp(name, "hilbert")) { c->hilbert = value != 0.; c->tree_valid = false; return 0; }
     if (!strcmp(name, "halo_hgrow")) { c->halo_hgrow = value; return 0; }
@@ -242,7 +243,7 @@ int sphgpu_upload(sphgpu_ctx *c, const sphgpu_host_arrays *h, uint64_t mask)
     if (mask & SPHGPU_F_FEXT) TRY(upload_arr(c, c->fext, h->fext, 3 * n));
     if (mask & SPHGPU_F_BEVOL) TRY(upload_arr(c, c->Bevol, h->Bevol, 4 * n));
     if (mask & SPHGPU_F_DBEVOL) TRY(upload_arr(c, c->dBevol, h->dBevol, 4 * n));
-    if (mask & SPHGPU_F_EOSVARS) TRY(upload_arr(c, c->eos_vars, h->eos_vars, 7 * n));
+    if (mask & SPHGPU_F_EOSVARS) { TRY(upload_arr(c, c->eos_vars, h->eos_vars, 7 * n)); c->eos_on_device = false; }
     if (mask & SPHGPU_F_DIVCURLV) TRY(upload_arr(c, c->divcurlv, h->divcurlv, n));
     if (mask & SPHGPU_F_DIVCURLB) TRY(upload_arr(c, c->divcurlB, h->divcurlB, 4 * n));
     if (mask & SPHGPU_F_ALPHAIND) TRY(upload_arr(c, c->alphaind, h->alphaind, 3 * n));

@@ -149,6 +149,35 @@ def test_derivs_parity_iterating_set_second_call(mhd, gravity):
     assert sg.npairs_density == sw.npairs_density
 
 
+@pytest.mark.parametrize("const_av", [False, True])
+def test_derivs_parity_isothermal_two_sector_records(const_av):
+    """ieos = 1 without energy, MHD or self-gravity: full derivs on the device take the force instantiation whose neighbour records
+    are two sectors wide, P/rho^2, rho and the gradW factor derived from h per pair (force.cu: iso1_derive).  Against the oracle, and
+    against the three-sector instantiation (option no_iso1) of the same library."""
+    part, _ = setups.setup_test_derivs(nx=22, lattice="random", isothermal=True)
+    rng = setups.Ran2(-1357)
+    part.xyzh[:, 3] *= (0.9 + 0.2 * rng.draw(part.npart))
+    part.alphaind[:, 0] = 0.1 + 0.9 * rng.draw(part.npart)
+    if const_av:
+        part.params.const_av = 1
+        part.params.alpha = 0.7
+    po, pg, so, sg, g = run_both(part)
+    if const_av:      # (the reference does not fill dvdx / alpha_loc with constant alpha; h and forces are what this test is about)
+        fso = np.sqrt(np.mean(po.fxyzu[:, :3] ** 2))
+        assert rel_err(pg.xyzh[:, 3], po.xyzh[:, 3], 0.) < TOL_H
+        assert np.max(np.abs(pg.fxyzu[:, :3] - po.fxyzu[:, :3]) / (np.abs(po.fxyzu[:, :3]) + fso)) < TOL_F
+    else:
+        check_hydro(po, pg)
+    assert sg[1].npairs_force == so[1].npairs_force
+    p3 = part.copy()
+    s3 = gpu(p3.params, no_iso1=1).derivs(p3)
+    fs = np.sqrt(np.mean(p3.fxyzu[:, :3] ** 2))
+    assert np.array_equal(p3.xyzh, pg.xyzh)
+    d = np.max(np.abs(p3.fxyzu[:, :3] - pg.fxyzu[:, :3]))
+    assert 0. < d < 1e-12 * fs                                   # different instantiations (not bitwise), same forces
+    assert abs(s3.dtcourant - sg[1].dtcourant) <= 1e-13 * s3.dtcourant and s3.npairs_force == sg[1].npairs_force
+
+
 def test_derivs_parity_quintic():
     part, _ = setups.setup_test_derivs(nx=18, lattice="random", kernel=1, hfact=1.0)
     part.alphaind[:, 0] = 0.3
