@@ -2,7 +2,7 @@
 # A/B builds of the pair kernels with different launch bounds / pairs per trip: builds libsphgpu_<tag>.so variants (CPU side)
 # usage: tools/variants.sh build   |   tools/variants.sh run   (run = on the GPU box: times each variant with bench.py)
 cd "$(dirname "$0")/.."
-VARIANTS=("base:" "x2:-DXTRA_MINB=2")   # add "tag:-Dflags" entries to A/B a build.  Round 2 sets, both measured and rejected: 512/576-candidate rounds (profiles/r02_disordered_states_ab.txt); next-trip prefetch of the force record head at 4 / 3 CTAs per SM (force 1.38 -> 1.68 / 1.52 ms)
+VARIANTS=("base:")   # add "tag:-Dflags" entries to A/B a build.  Round 2 sets, all measured and rejected: 512/576-candidate rounds (profiles/r02_disordered_states_ab.txt); next-trip prefetch of the force record head (three-sector records: 1.38 -> 1.68 / 1.52 ms at 4 / 3 CTAs per SM; two-sector records: 1.297 -> 1.302 ms); XTRA_MINB=2 (two-fluid box 50.3 -> 55.2 ms); FORCE_MINB=5 with the two-sector records (1.298 -> 1.355 ms)
 if [ "$1" == "build" ]; then
   mkdir -p build/variants
   for v in "${VARIANTS[@]}"; do
