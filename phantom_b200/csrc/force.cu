@@ -439,10 +439,6 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
         for (int k = 0; k < 3; k++) { tlo[k] = __double2float_rd(cell.lo[k]); thi[k] = __double2float_ru(cell.hi[k]); }
         const double rreach = KF::radkern * fmax(cell.hmax, (double)hmax_global) * a.hscale * 1.0001;
         const double rcut = KF::radkern * cell.hmax * a.hscale;
-        const bool wide = PERIODIC && (halfext + rreach >= 0.999 * halfLmin);
-        // no pair of this group can straddle the periodic boundary: |xi - xj| <= L/2 for every candidate that survives the prefilter
-        const bool interior = !PERIODIC || (cell.lo[0] - rreach > p.xmin && cell.hi[0] + rreach < p.xmax && cell.lo[1] - rreach > p.ymin &&
-                                            cell.hi[1] + rreach < p.ymax && cell.lo[2] - rreach > p.zmin && cell.hi[2] + rreach < p.zmax);
         float reach = 0.f;
         const int *cl = clist;                                       // list in use: the prepared one, or this warp's slice after a walk in here
         int ncl = a.wl.ncl[cellid];
@@ -450,6 +446,15 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
         else ncl = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut), __double2float_ru(KF::radkern * a.hscale),
                                              fLx, fLy, fLz, ws.walk_stack(), clist, a.scratch_per_warp, reach);
         if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+        // Largest kernel radius of any target or candidate of THIS group: the walk's reach (search radius + extent over the cells it
+        // hit) bounds it locally, radkern x the global hmax bounds it anyway.  The FP16 filter, which works on nearest images relative
+        // to the group centre, is valid while halfext + that radius < L/2; a thin periodic box (the shock tube's y, z) whose large-h
+        // side would fail this must not switch the filter off for the groups of the small-h side.
+        const double rloc = fmin(rreach, (double)reach * 1.0001);
+        const bool wide = PERIODIC && (halfext + rloc >= 0.999 * halfLmin);
+        // no pair of this group can straddle the periodic boundary: |xi - xj| <= L/2 for every candidate that survives the prefilter
+        const bool interior = !PERIODIC || (cell.lo[0] - rloc > p.xmin && cell.hi[0] + rloc < p.xmax && cell.lo[1] - rloc > p.ymin &&
+                                            cell.hi[1] + rloc < p.ymax && cell.lo[2] - rloc > p.zmin && cell.hi[2] + rloc < p.zmax);
         int nlist = 0;
         const FilterScale fs = filter_scale((float)halfext, reach);
         // ---- lane = target (start_cell, force.F90:2172-2514; per-particle part done by k_force_prep)
@@ -757,7 +762,6 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
 #pragma unroll
         for (int k = 0; k < 3; k++) { tlo[k] = __double2float_rd(cell.lo[k]); thi[k] = __double2float_ru(cell.hi[k]); }
         const double rcut = KF::radkern * cell.hmax * a.hscale;
-        const bool wide = PERIODIC && (halfext + KF::radkern * fmax(cell.hmax, (double)hmax_global) * a.hscale >= 0.999 * halfLmin);
         float reach = 0.f;
         const int *cl = clist;                                       // list in use: the prepared one, or this warp's slice after a walk in here
         int ncl = a.wl.ncl[cellid];
@@ -765,6 +769,8 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
         else ncl = warp_walk<true, PERIODIC>(a.nodes, a.cells, a.ncells, tlo, thi, __double2float_ru(rcut), __double2float_ru(KF::radkern * a.hscale),
                                              fLx, fLy, fLz, ws.stack, clist, a.scratch_per_warp, reach);
         if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
+        // (largest kernel radius of this group's targets and candidates: bounded locally by the walk's reach, see k_force_fast)
+        const bool wide = PERIODIC && (halfext + fmin(KF::radkern * fmax(cell.hmax, (double)hmax_global) * a.hscale, (double)reach) * 1.0001 >= 0.999 * halfLmin);
         int nlist = 0;
         const FilterScale fs = filter_scale((float)halfext, reach);
         // ---- lane = target: start_cell (force.F90:2172-2514); the per-particle part was done by k_force_prep
