@@ -167,11 +167,13 @@ struct sphgpu_ctx {
     DevBuf<TreeNode> nodes;
     DevBuf<TreeNodeF> nodesf;
     bool multitype = false;                 // any particle that is not plain gas (boundary, dust, ...)
+    bool wl_ordered = false;                // wl_order holds the groups of the current lists by falling length
     bool eos_on_device = false;             // eos_vars (P, c_s) were written by cons2prim_run after the last upload of that array
     bool no_iso1 = false;                   // option: keep the three-sector force records for isothermal sets too (A/B, tests)
     bool dens_reuse = false;                // the last density pass iterated: keep staged rounds and masks over the h-rho iterations
     int class_mask = 1;                     // sort classes present (bit 0 gas/boundary, 1 dust, 2 other): the class rounds of the general pair kernels
     DevBuf<int> wl_list, wl_ncl; DevBuf<float> wl_reach;   // cell lists prepared by k_walk_lists (walk.cuh)
+    DevBuf<int> wl_key, wl_key2, wl_iota, wl_order;        // target groups by falling list length (walk.cuh: walk_order_run)
     bool stream_blocking = false;   // the compute stream synchronises implicitly with the legacy default stream (option "legacy_stream")
     double dens_trial_hint = 0., dens_trial_max = 0.;   // mean / max candidates per target group in the last density pass (choose the round size of the next)
     bool wl_force_ok = false;       // the prepared lists are symmetric lists of the current groups ...

@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
         if (lane == 0) cellid = (int)atomicAdd(&a.cnt[CNT_WORK], 1ull);
         cellid = __shfl_sync(FULLMASK, cellid, 0);
         if (cellid >= a.ngroups) break;
+        if (a.wl.order) cellid = a.wl.order[cellid];
         const Cell cell = a.groups[cellid];
         if (cell.active == 0) continue;                              // dens.F90:302
         const double cx = 0.5 * (cell.lo[0] + cell.hi[0]), cy = 0.5 * (cell.lo[1] + cell.hi[1]), cz = 0.5 * (cell.lo[2] + cell.hi[2]);
@@ -731,7 +732,8 @@ int density_run(sphgpu_ctx *c, int icall, sphgpu_scalars *out)
         // candidates as long as no h grows by more than the margin (force_run checks hscale against wl_cover)
         const double R = (p.kernel == 0 ? SphKern<0>::radkern : SphKern<1>::radkern), hs0 = fmax(c->hscale, 1.);
         TRY(walk_lists_run(c, true, R * c->list_margin * hs0, R * c->list_margin * hs0, a.wl));
-        c->wl_force_ok = true; c->wl_cover = hs0 * c->list_margin;
+        TRY(walk_order_run(c, a.wl));
+        c->wl_force_ok = true; c->wl_cover = hs0 * c->list_margin; c->wl_ordered = a.wl.order != nullptr;
     }
     unsigned long long hc[16]; double hrhomax, hused, hgrow = 0.;
     for (int attempt = 0;; attempt++) {

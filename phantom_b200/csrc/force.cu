@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
         if (lane == 0) cellid = (int)atomicAdd(&a.cnt[CNT_WORK], 1ull);
         cellid = __shfl_sync(FULLMASK, cellid, 0);
         if (cellid >= a.ngroups) break;
+        if (a.wl.order) cellid = a.wl.order[cellid];
         const Cell cell = a.groups[cellid];
         if (cell.active == 0) continue;                              // force.F90:509
         const double cx = 0.5 * (cell.lo[0] + cell.hi[0]), cy = 0.5 * (cell.lo[1] + cell.hi[1]), cz = 0.5 * (cell.lo[2] + cell.hi[2]);
@@ -754,6 +755,7 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
         if (lane == 0) cellid = (int)atomicAdd(&a.cnt[CNT_WORK], 1ull);
         cellid = __shfl_sync(FULLMASK, cellid, 0);
         if (cellid >= a.ngroups) break;
+        if (a.wl.order) cellid = a.wl.order[cellid];
         const Cell cell = a.groups[cellid];
         if (cell.active == 0) continue;                              // force.F90:509
         const double cx = 0.5 * (cell.lo[0] + cell.hi[0]), cy = 0.5 * (cell.lo[1] + cell.hi[1]), cz = 0.5 * (cell.lo[2] + cell.hi[2]);
@@ -1088,10 +1090,12 @@ int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     }
     if (c->wl_force_ok && c->hscale <= c->wl_cover) {                      // the lists of the density pass still cover every pair
         a.wl.list = c->wl_list.p; a.wl.ncl = c->wl_ncl.p; a.wl.reach = c->wl_reach.p; a.wl.cap = c->walk_cap;
+        a.wl.order = c->wl_ordered ? c->wl_order.p : nullptr;
     } else {
         const double R = (p.kernel == 0 ? SphKern<0>::radkern : SphKern<1>::radkern);
         TRY(walk_lists_run(c, true, R * c->hscale, R * c->hscale, a.wl));
-        c->wl_force_ok = true; c->wl_cover = c->hscale;
+        TRY(walk_order_run(c, a.wl));
+        c->wl_force_ok = true; c->wl_cover = c->hscale; c->wl_ordered = a.wl.order != nullptr;
     }
     unsigned long long hc[16]; double hd[4];
     for (int attempt = 0;; attempt++) {
