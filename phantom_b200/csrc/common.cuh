@@ -167,6 +167,7 @@ struct sphgpu_ctx {
     DevBuf<TreeNode> nodes;
     DevBuf<TreeNodeF> nodesf;
     bool multitype = false;                 // any particle that is not plain gas (boundary, dust, ...)
+    bool any_inactive = true;               // some live particle carries the inactive flag (tree build); false: every particle is a target
     bool wl_ordered = false;                // wl_order holds the groups of the current lists by falling length
     bool eos_on_device = false;             // eos_vars (P, c_s) were written by cons2prim_run after the last upload of that array
     bool no_iso1 = false;                   // option: keep the three-sector force records for isothermal sets too (A/B, tests)
@@ -301,7 +302,7 @@ __device__ __forceinline__ void atomic_max_pos(double *addr, double v) { atomicM
 
 // indices into ctx->counters (unsigned long long)
 enum { CNT_WORK = 0, CNT_ERR, CNT_ERRID, CNT_NPAIRS, CNT_NTRIAL, CNT_NCALC, CNT_NACT, CNT_MAXACT, CNT_MAXTRIAL, CNT_NP, CNT_NWALK, CNT_NLIVE, CNT_NBINMAX, CNT_NCHECKBIN, CNT_MULTITYPE, CNT_NSURV,
-       CNT_NGRAVPAIRS = 24, CNT_NM2L = 25, CNT_NCELLS = 26, CNT_CELLOVER = 27, CNT_CLASS1 = 28, CNT_CLASS2 = 29, CNT_COUNT = 32 };
+       CNT_NGRAVPAIRS = 24, CNT_NM2L = 25, CNT_NCELLS = 26, CNT_CELLOVER = 27, CNT_CLASS1 = 28, CNT_CLASS2 = 29, CNT_ANYINACTIVE = 30, CNT_COUNT = 32 };
 // indices into ctx->dscal (double)
 enum { DS_XMIN = 0, DS_YMIN, DS_ZMIN, DS_XMAX, DS_YMAX, DS_ZMAX, DS_DTCOURANT, DS_DTFORCE, DS_DTMINI, DS_DTMAXI, DS_RHOMAX, DS_HUSED, DS_HGROW, DS_COUNT = 32 };
 
@@ -313,7 +314,8 @@ int cons2prim_run(sphgpu_ctx *c);
 int force_run(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out);
 int gravity_run(sphgpu_ctx *c);
 int refcompat_prepare(sphgpu_ctx *c);      // reference tree + node hmax history + leaf of every particle (gravity.cu)
-static inline bool refcompat_on(const sphgpu_ctx *c) { return c->refcompat < 0 ? c->hp.p.ind_timesteps != 0 : c->refcompat != 0; }
+// (with every particle active the reference's leaf hmax cover every member's kernel, as with global timesteps: nothing to replicate)
+static inline bool refcompat_on(const sphgpu_ctx *c) { return (c->refcompat < 0 ? c->hp.p.ind_timesteps != 0 : c->refcompat != 0) && c->any_inactive; }
 void gravity_release(sphgpu_ctx *c);
 int gravity_gather_pack(sphgpu_ctx *c, void **sendptr, int *record_doubles);
 int gravity_gather_recvbuf(sphgpu_ctx *c, int nranks, int64_t stride, void **recvptr);

@@ -151,6 +151,7 @@ __global__ void k_gather_pos(int64_t n, const int *__restrict__ perm, const doub
     const int ta = ph < 0 ? -ph : ph;
     if (!(ta == IGAS || (boundary_is_gas && ta == IBOUNDARY))) cnt[CNT_MULTITYPE] = 1ull;
     { const int sc = sort_class(ph); if (sc == 1) cnt[CNT_CLASS1] = 1ull; else if (sc == 2) cnt[CNT_CLASS2] = 1ull; }
+    if (ph <= 0) cnt[CNT_ANYINACTIVE] = 1ull;
     // common leading bits (of the 63 key bits) with the previous key: 0..63
     unsigned char c = 0;
     if (s > 0) {
@@ -513,6 +514,7 @@ int tree_build(sphgpu_ctx *c)
     c->ngroups = (int64_t)hc[CNT_COUNT - 1];
     c->multitype = hc[CNT_MULTITYPE] != 0;
     c->class_mask = 1 | (hc[CNT_CLASS1] ? 2 : 0) | (hc[CNT_CLASS2] ? 4 : 0);
+    c->any_inactive = hc[CNT_ANYINACTIVE] != 0;
     c->grav_tree_valid = false; c->hscale = 1.; c->wl_force_ok = false;
     CUDA_TRY(c, cudaGetLastError());
     c->tree_valid = true;
