@@ -326,4 +326,5 @@ int64_t neighbour_sets_run(sphgpu_ctx *c, int symmetric, int64_t *offsets, int32
 KernConsts make_kern_consts(int kernel);
 int ensure_all_keep(sphgpu_ctx *c, int64_t n, int64_t keep);
 int sphgpu_dist_hook_derivs(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out);
+void sphgpu_dist_mark_dirty(sphgpu_ctx *c);     // positions, h or boxes of a distributed context changed (upload, step, migration)
 int sphgpu_dist_hook_reduce_err(sphgpu_ctx *c, double *red3);

@@ -79,6 +79,7 @@ struct DistState {
     DevBuf<double> sendbuf, recvbuf;
     DevBuf<double> red, red_out;               // all-reduce staging
     double hu_prev = -1., overhang = 0., margin = 1.15;
+    bool geom_dirty = true;                    // owned positions / h / boxes changed since the halo width inputs were last reduced
     long long ncap_ghost = 0;
     int64_t halo_bytes = 0;
     int rounds = 0;
@@ -629,6 +630,7 @@ int sphgpu_dist_finalize(sphgpu_ctx *c)
 // boxes: 6 doubles per rank {lo xyz, hi xyz} tiling the domain [glo, ghi] (the periodic box, or the bounding box of the set)
 int sphgpu_dist_set_boxes(sphgpu_ctx *c, const double *boxes)
 {
+    sphgpu_dist_mark_dirty(c);
     if (!c || !c->dist || !boxes) return SPHGPU_ERR_ARG;
     DistState *d = c->dist;
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -652,6 +654,7 @@ int sphgpu_dist_get_boxes(sphgpu_ctx *c, double *boxes)
 // global particle identities of the owned particles (they travel with the particles when these migrate); ids == NULL: base + position
 int sphgpu_dist_set_ids(sphgpu_ctx *c, const int64_t *ids, int64_t base)
 {
+    sphgpu_dist_mark_dirty(c);
     if (!c || c->nlocal <= 0) return SPHGPU_ERR_ARG;
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, c->gid.ensure(c->nlocal));
@@ -700,7 +703,7 @@ int sphgpu_dist_derivs(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
     if (icall == 1) {
         // halo width: radkern x (largest trial h of the previous density pass, all ranks) x margin + how far owned particles stick out of
         // their boxes; both come out of ONE all-reduce (the first call measures h directly)
-        {
+        if (d->geom_dirty || d->hu_prev < 0.) {   // (a repeated derivs on an unchanged state has nothing new to reduce)
             const double want = (double)d->mig_want;
             CUDA_TRY(c, cudaMemsetAsync(d->red.p, 0, 2 * sizeof(double), c->stream));
             CUDA_TRY(c, cudaMemcpyAsync(d->red.p + 2, &want, sizeof want, cudaMemcpyHostToDevice, c->stream));
@@ -716,6 +719,7 @@ int sphgpu_dist_derivs(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
             d->overhang = glob[1];
             if ((long long)glob[2] > d->mig_cap / 2) d->mig_cap = 4 * (long long)glob[2];      // the same decision on every rank
             d->mig_want = 0;
+            d->geom_dirty = false;
         }
         double dhalo = radkern * d->hu_prev * d->margin + 2. * d->overhang;
         while (true) {
@@ -794,6 +798,7 @@ int sphgpu_dist_derivs(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out)
 // travel too.  Returns the new number of owned particles.
 int sphgpu_dist_migrate(sphgpu_ctx *c, int in_step, int64_t *nlocal_new)
 {
+    sphgpu_dist_mark_dirty(c);
     if (!c || !c->dist) return SPHGPU_ERR_ARG;
     DistState *d = c->dist;
     if (d->boxes.empty()) { c->err = "dist_migrate: no domain boxes"; return SPHGPU_ERR_STATE; }
@@ -865,6 +870,7 @@ int sphgpu_dist_migrate(sphgpu_ctx *c, int in_step, int64_t *nlocal_new)
 // longest axis, the moments of every level all-reduced; followed by a migration.  domain = {lo xyz, hi xyz} to be tiled.
 int sphgpu_dist_rebalance(sphgpu_ctx *c, const double *domain, int64_t *nlocal_new)
 {
+    sphgpu_dist_mark_dirty(c);
     if (!c || !c->dist || !domain) return SPHGPU_ERR_ARG;
     DistState *d = c->dist;
     const int P = d->nranks;
@@ -964,7 +970,8 @@ int sphgpu_dist_energies(sphgpu_ctx *c, sphgpu_energies *out)
 }  // extern "C"
 
 // ---- hooks used by step.cu -----------------------------------------------------------------------------------------------------------
-int sphgpu_dist_hook_derivs(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out) { return sphgpu_dist_derivs(c, icall, dt, out); }
+int sphgpu_dist_hook_derivs(sphgpu_ctx *c, int icall, double dt, sphgpu_scalars *out) { if (c && c->dist) c->dist->geom_dirty = true; return sphgpu_dist_derivs(c, icall, dt, out); }
+void sphgpu_dist_mark_dirty(sphgpu_ctx *c) { if (c && c->dist) c->dist->geom_dirty = true; }
 int sphgpu_dist_hook_reduce_err(sphgpu_ctx *c, double *red3)
 {
     DistState *d = c->dist;

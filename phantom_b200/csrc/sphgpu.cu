@@ -230,6 +230,7 @@ int sphgpu_get_kernel_timings(sphgpu_ctx *c, double *ms2)
 
 int sphgpu_upload(sphgpu_ctx *c, const sphgpu_host_arrays *h, uint64_t mask)
 {
+    sphgpu_dist_mark_dirty(c);
     if (!c || !h || h->npart <= 0) return SPHGPU_ERR_ARG;
     CUDA_TRY(c, cudaSetDevice(c->device));
     const int64_t n = h->npart;
