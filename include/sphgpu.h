@@ -138,7 +138,11 @@ int  sphgpu_create(const sphgpu_params *params, int device, sphgpu_ctx **out);
 void sphgpu_destroy(sphgpu_ctx *ctx);
 int  sphgpu_set_params(sphgpu_ctx *ctx, const sphgpu_params *params);
 const char *sphgpu_last_error(sphgpu_ctx *ctx);
-/* tuning knobs: "max_cell" (particles per leaf cell, <=32), "list_margin" (x1e-4) ... ; returns 0 if known.
+/* Options by name; returns 0 if known.  Tuning: "max_cell" (targets per group, <= 32), "max_leaf" (particles per leaf cell),
+ * "group_pack", "list_margin", "hilbert", "scratch_per_warp", "always_refit", "grav_p2p_per_particle".
+ * Behaviour: "refcompat_hmax" (1/0; default = on with individual timesteps: neighbour sets pruned exactly as the reference's walk
+ * prunes them while some particle is inactive), "force_general" (1 = general pair kernels even for an all-gas set), "no_iso1"
+ * (1 = keep the three-sector force records for an isothermal set instead of deriving P, rho and c_s from h per pair).
  * "legacy_stream" = 1 replaces the context's non-blocking compute stream by a BLOCKING one, i.e. one implicitly ordered with the
  * legacy default stream: a host that issues its NCCL collectives relative to the default stream (torch.distributed, or a Fortran
  * MPI+NCCL driver doing the same) can then chain sphgpu_halo_select -> _pack -> all-to-all -> _unpack without any host
