@@ -541,10 +541,15 @@ __global__ void __launch_bounds__(128, 4) k_g_p2p(const P2PArgs a)
     const int *lst = a.p2p + a.p2poff[d];
     const int nl = a.p2pcnt[d];
     unsigned long long npairs = 0;
+    // particle range of this lane's source leaf in the NEXT batch: list entry -> node -> range are two of the three dependent reads of
+    // the staging, fetched while the current batch is being summed
+    int nstart = 0, ncount = 0;
+    if (lane < nl) { const GNode &ns = a.nodes[lst[lane]]; nstart = ns.start; ncount = ns.count; }
     for (int base = 0; base < nl; base += P2P_BATCH) {
         // ---- stage: lane = source leaf
-        int sstart = 0, scount = 0;
-        if (base + lane < nl) { const GNode &ns = a.nodes[lst[base + lane]]; sstart = ns.start; scount = ns.count; }
+        const int sstart = nstart, scount = ncount;
+        nstart = 0; ncount = 0;
+        if (base + P2P_BATCH + lane < nl) { const GNode &ns = a.nodes[lst[base + P2P_BATCH + lane]]; nstart = ns.start; ncount = ns.count; }
         int off = scount;                                     // inclusive warp scan of the counts
 #pragma unroll
         for (int sft = 1; sft < 32; sft <<= 1) { const int o = __shfl_up_sync(FULLMASK, off, sft); if (lane >= sft) off += o; }
