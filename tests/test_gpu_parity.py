@@ -231,6 +231,46 @@ def test_boundary_and_inactive_particles():
     assert np.array_equal(pg.xyzh[b, 3], part.xyzh[b, 3]) and np.all(pg.fxyzu[b] == 0.)
 
 
+@pytest.mark.parametrize("max_leaf", [1, 3])
+def test_tree_cell_capacity_retry(max_leaf):
+    """The tree is built with ONE host round trip on cell arrays sized from n/3 (or the previous build); a set that makes more leaf
+    cells than that -- one particle per cell here -- raises the overflow flag on the device and the build is repeated at the true
+    size (tree.cu).  Results must not depend on it."""
+    part, _ = setups.setup_test_derivs(nx=16, lattice="random")
+    part.alphaind[:, 0] = 0.5
+    po, pg, so, sg, g = run_both(part, max_leaf=max_leaf)
+    check_hydro(po, pg)
+    assert sg[0].nactualtot == so[0].nactualtot and sg[1].npairs_force == so[1].npairs_force
+    pg2 = part.copy()
+    sg2 = g.derivs(pg2)                              # second build on the same context: capacity remembered from the first
+    assert np.array_equal(pg2.xyzh, pg.xyzh) and np.array_equal(pg2.fxyzu, pg.fxyzu)
+
+
+def test_three_sort_classes_mixed_types():
+    """Gas, dust and a third kind (star-type particles) in one set: the sort key carries the class, so leaf cells, target groups and
+    staged rounds are single-class and the general kernels choose the pair body per class pair.  Every class gets the density of its
+    own kind, gas alone gets hydro forces (dens.F90:717-741, force.F90:1539)."""
+    from phantom_b200.params import IDUST
+    part, _ = setups.setup_dustybox(nx=14, idrag=2, lattice="random")
+    ISTAR = 4
+    rng = setups.Ran2(-4242)
+    star = (rng.draw(part.npart) < 0.1) & (part.iphase == IGAS)
+    part.iphase[star] = ISTAR
+    part.params.massoftype[ISTAR] = 0.3 * part.params.massoftype[IGAS]
+    part.xyzh[star, 3] *= 2.0
+    po, pg = part.copy(), part.copy()
+    o = Oracle(po.params)
+    sdo, sfo = o.derivs(po)
+    g = gpu(pg.params)
+    sg = g.derivs(pg)
+    assert rel_err(pg.xyzh[:, 3], po.xyzh[:, 3], 0.) < TOL_H
+    fs = np.sqrt(np.mean(po.fxyzu[:, :3] ** 2))
+    assert np.max(np.abs(pg.fxyzu[:, :3] - po.fxyzu[:, :3]) / (np.abs(po.fxyzu[:, :3]) + fs)) < TOL_F
+    assert np.all(pg.fxyzu[star, :3] == po.fxyzu[star, :3])
+    assert sg.nactualtot == sdo.nactualtot and sg.npairs_force == sfo.npairs_force
+    assert np.max(np.abs(pg.dustfrac - po.dustfrac)) <= 1e-12 * (np.max(np.abs(po.dustfrac)) + 1e-300)
+
+
 def test_periodic_wrap_and_errors():
     from phantom_b200.api import SphGpuError
     part, _ = setups.setup_test_derivs(nx=10, lattice="random")
