@@ -495,6 +495,57 @@ def main():
                                  "ms_per_step": te / 5, "value": n * 5 / (te * 1e-3), "unit": "particle-updates/s", "its_mean": its,
                                  "candidates_per_group": sce.trialmean, "neighbours_mean": sce.actualmean}
         del ge
+        # ---- the same evolved box with individual timesteps (BASELINE configs[1]: "IND_TIMESTEPS on/off both reported"): one dtmax of
+        # substeps on the device -- set_active_particles + step() per smallest timestep, the bin bookkeeping of evolve.F90 on the host
+        try:
+            import time as _time
+
+            def _ind_cycle(refcompat):
+                pi_ = pe.copy()
+                pi_.params.ind_timesteps = 1
+                dtmax_i = 8. * dte
+                pi_.params.dtmax = dtmax_i
+                gi = SphGpu(pi_.params.copy(), device=local)
+                if refcompat is not None:
+                    gi.set_option("refcompat_hmax", float(refcompat))
+                gi.upload(pi_)
+                gi.set_timestep_bins(0, 0, 0)
+                sci = gi.derivs_resident(1)
+                nbinmax = int(sci.nbinmaxnew)
+                gi.init_step_resident(0., dtmax_i, nbinmax)
+                istepfrac, ti, nsub, nact_tot, nb0 = 0, 0., 0, 0, nbinmax
+                torch.cuda.synchronize()
+                t0 = _time.perf_counter()
+                while nsub < 256:
+                    dti = dtmax_i / 2 ** nbinmax
+                    istepfrac += 1
+                    nactive, _nalive = gi.set_active_particles_resident(nbinmax, istepfrac)
+                    outi = gi.step_ind_resident(ti, dti, dtmax_i)
+                    nsub += 1; nact_tot += int(nactive)
+                    ti = istepfrac / 2. ** nbinmax * dtmax_i
+                    nbnew = int(outi.scalars.nbinmaxnew)
+                    if nbnew != nbinmax:                               # change_nbinmax (utils_indtimesteps.f90:186-222)
+                        istepfrac = istepfrac // 2 ** (nbinmax - nbnew) if nbnew < nbinmax else istepfrac * 2 ** (nbnew - nbinmax)
+                        nbinmax = nbnew
+                    if istepfrac == 2 ** nbinmax:
+                        break
+                torch.cuda.synchronize()
+                wall_i = _time.perf_counter() - t0
+                del gi
+                return dict(nbinmax_start=nb0, nbinmax_end=nbinmax, substeps=nsub, active_updates=nact_tot, mean_active_fraction=nact_tot / max(nsub * n, 1),
+                            ms_total=wall_i * 1e3, ms_per_substep=wall_i * 1e3 / max(nsub, 1), value=nact_tot / wall_i, unit="active-particle-updates/s",
+                            synchronised=bool(istepfrac == 2 ** nbinmax))
+            blk = _ind_cycle(None)
+            exact = _ind_cycle(0)
+            blk["what"] = ("the evolved box stepped through one dtmax = 8 x its global timestep with individual timestep bins "
+                           "(sphgpu_set_active_particles_resident + sphgpu_step_ind_resident per smallest timestep, host wall clock around the loop); "
+                           "default = neighbour sets pruned as the reference's tree walk prunes them (option refcompat_hmax, needs the reference-"
+                           "topology tree every substep)")
+            blk["global_equivalent_ms"] = blk["substeps"] * (te / 5)
+            blk["exact_neighbour_sets"] = {"ms_per_substep": exact["ms_per_substep"], "value": exact["value"], "substeps": exact["substeps"]}
+            line["ind_timesteps"] = blk
+        except Exception as e:      # an extra, never the reason for a missing bench line
+            line["ind_timesteps"] = {"error": str(e)[:200]}
         if not args.no_cpu_baseline:
             from phantom_b200 import setups
             from oraclelib import Oracle
