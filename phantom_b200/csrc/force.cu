@@ -159,9 +159,11 @@ __device__ __forceinline__ double recon_slope(const float *__restrict__ d, doubl
 template <bool PERIODIC>
 __device__ __noinline__ bool ref_walk_reaches(const ForceArgs &a, int si, int sj, double Lx, double Ly, double Lz)
 {
-    const RefNode ci = a.refnodes[a.refleaf[si]];
-    const double rcuti = a.ref_radkern * ci.hmax;
     int n = a.refleaf[sj];
+    if (n < 0) return true;                                  // j's leaf hmax covers h_j (k_ref_leaf_sorted): every node on its path opens
+    const int li = a.refleaf[si];
+    const RefNode ci = a.refnodes[li < 0 ? ~li : li];
+    const double rcuti = a.ref_radkern * ci.hmax;
     while (n >= 0) {
         const RefNode nd = a.refnodes[n];
         double dx = ci.xcen[0] - nd.xcen[0], dy = ci.xcen[1] - nd.xcen[1], dz = ci.xcen[2] - nd.xcen[2];

@@ -800,10 +800,17 @@ __global__ void k_ref_export(int nn, const GNode *__restrict__ nodes, const int 
     out[d] = r;
     if (nd.left < 0) for (int s = nd.start; s < nd.start + nd.count; s++) leaf_of[gid[s]] = d;
 }
-__global__ void k_ref_leaf_sorted(int64_t nlive, const int *__restrict__ perm, const int *__restrict__ leaf_of, int *__restrict__ out)
+// leaf of every sorted slot; stored as ~leaf when the leaf's hmax covers the particle's own h: every node on its path to the root then
+// has hmax >= h_j (hmax only grows upwards), so any i inside j's kernel opens them all (|x_i - c_i| <= size_i, |x_j - c_n| <= size_n,
+// r_ij < radkern h_j <= radkern hmax_n) and ref_walk_reaches need not walk.  Only the particles a leaf's hmax does NOT cover -- inactive
+// members above 1.01 x the active members' h, members that converged before the others -- can be missed by the reference.
+__global__ void k_ref_leaf_sorted(int64_t nlive, const int *__restrict__ perm, const int *__restrict__ leaf_of, const RefNode *__restrict__ nodes,
+                                  const double4 *__restrict__ pos4, int *__restrict__ out)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (s < nlive) out[s] = leaf_of[perm[s]];
+    if (s >= nlive) return;
+    const int leaf = leaf_of[perm[s]];
+    out[s] = (fabs(pos4[s].w) <= nodes[leaf].hmax) ? ~leaf : leaf;
 }
 
 int refcompat_prepare(sphgpu_ctx *c)
@@ -826,7 +833,7 @@ int refcompat_prepare(sphgpu_ctx *c)
     CUDA_TRY(c, c->ref_nodes.ensure(nn)); CUDA_TRY(c, c->ref_leaf.ensure(c->npart)); CUDA_TRY(c, c->ref_leaf_sorted.ensure(c->npart));
     CUDA_TRY(c, cudaMemsetAsync(c->ref_leaf.p, 0, sizeof(int) * (size_t)c->npart, c->stream));
     GL(c, k_ref_export, nblk(nn, 128), 128, nn, g.nodes.p, g.gid[cur].p, c->ref_nodes.p, c->ref_leaf.p);
-    GL(c, k_ref_leaf_sorted, nblk(c->nlive, 256), 256, c->nlive, c->perm.p, c->ref_leaf.p, c->ref_leaf_sorted.p);
+    GL(c, k_ref_leaf_sorted, nblk(c->nlive, 256), 256, c->nlive, c->perm.p, c->ref_leaf.p, c->ref_nodes.p, c->pos4.p, c->ref_leaf_sorted.p);
     CUDA_TRY(c, cudaGetLastError());
     c->ref_valid = true;
     return SPHGPU_OK;
