@@ -103,8 +103,11 @@ __global__ void k_g_liveflag(int64_t n, const double *__restrict__ xyzh, int *__
     flag[i] = (xyzh[4 * i + 3] < DBL_MIN) ? 0 : 1;
 }
 
-__global__ void k_g_node_reset(int n0, int n1, GBuild *__restrict__ gb)
+// (the node range [lvl[L], lvl[L+1]) of the level being built is read from the device: the host does not wait for it, grids are sized
+// for the largest range the level can have)
+__global__ void k_g_node_reset(const int *__restrict__ lvl, int L, GBuild *__restrict__ gb)
 {
+    const int n0 = lvl[L], n1 = lvl[L + 1];
     const int d = n0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n1) return;
     GBuild b; memset(&b, 0, sizeof b);
@@ -162,8 +165,9 @@ __global__ void __launch_bounds__(256) k_g_sums(int nlive, const int *__restrict
 }
 
 // node kernel A: centre of mass, split decision, axis = first longest bbox axis, pivot = COM on that axis (kdtree.F90:668-700, :792-818)
-__global__ void k_g_nodes_a(int n0, int n1, GNode *__restrict__ nodes, GBuild *__restrict__ gb, double dfac, unsigned long long *cnt)
+__global__ void k_g_nodes_a(const int *__restrict__ lvl, int L, GNode *__restrict__ nodes, GBuild *__restrict__ gb, double dfac, unsigned long long *cnt)
 {
+    const int n0 = lvl[L], n1 = lvl[L + 1];
     const int d = n0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n1) return;
     GBuild &b = gb[d];
@@ -217,9 +221,10 @@ __global__ void __launch_bounds__(256) k_g_moments(int nlive, const int *__restr
 }
 
 // node kernel B: finish the node record; split nodes get two children appended after the current level
-__global__ void k_g_nodes_b(int n0, int n1, GNode *__restrict__ nodes, GBuild *__restrict__ gb, const int *__restrict__ flag, const int *__restrict__ scan,
+__global__ void k_g_nodes_b(const int *__restrict__ lvl, int L, GNode *__restrict__ nodes, GBuild *__restrict__ gb, const int *__restrict__ flag, const int *__restrict__ scan,
                             int *nnodes, int maxnodes, unsigned long long *cnt)
 {
+    const int n0 = lvl[L], n1 = lvl[L + 1];
     const int d = n0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n1) return;
     GBuild &b = gb[d];
@@ -241,6 +246,9 @@ __global__ void k_g_nodes_b(int n0, int n1, GNode *__restrict__ nodes, GBuild *_
     l.start = nd.start; l.count = nl; r.start = nd.start + nl; r.count = nd.count - nl;
     nodes[base] = l; nodes[base + 1] = r;
 }
+
+// end of level L: the nodes allocated during it are level L + 1
+__global__ void k_g_level_end(const int *__restrict__ nnodes, int *__restrict__ lvl, int L) { lvl[L + 2] = *nnodes; }
 
 // pass 3: stable partition of every split node; particles of finished leaves keep their slot
 __global__ void k_g_scatter(int nlive, const int *__restrict__ pnode, const double4 *__restrict__ pos, const double *__restrict__ mass,
@@ -622,6 +630,8 @@ struct GravState {
     DevBuf<unsigned long long> ptrs;          // [0] list pool pointer, [1] P2P pool pointer, [2] need, [3] nnodes (as int)
     DevBuf<char> cubtmp;
     std::vector<int> level_start;              // nodes of level L are [level_start[L], level_start[L+1])
+    DevBuf<int> lvl;                           // the same on the device while the tree is being built (grav_build)
+    int levels_prev = 0;                       // depth of the previous build: from where on the host watches for the last level
     int nn = 0, cur = 0, nlive = 0;
     // multi-GPU: the gathered particle set of all ranks (positions, h history) in rank order; this rank owns [own_lo, own_hi)
     int64_t nglobal = 0, own_lo = 0;
@@ -685,29 +695,43 @@ static int grav_build(sphgpu_ctx *c, GravState &g, const GravInput &in)
     int *nnodes_d = reinterpret_cast<int *>(g.ptrs.p + 3);
     int one = 1;
     CUDA_TRY(c, cudaMemcpyAsync(nnodes_d, &one, sizeof(int), cudaMemcpyHostToDevice, st));
-    g.level_start.clear(); g.level_start.push_back(0);
-    int n0 = 0, n1 = 1, cur = 0;
+    // level table on the device: lvl[L] = first node of level L.  The host reads it (and the error flag) only from the depth of the
+    // previous build on: a tree of the same particles a step later is as deep, give or take a level, and the levels above that are
+    // enqueued without a round trip each.  Levels enqueued beyond the last one find an empty node range and sweep finished leaves.
+    CUDA_TRY(c, g.lvl.ensure(132));
+    { const int init[2] = {0, 1}; CUDA_TRY(c, cudaMemcpyAsync(g.lvl.p, init, sizeof init, cudaMemcpyHostToDevice, st)); }
+    g.level_start.clear();
+    const int first_check = g.levels_prev > 3 ? g.levels_prev - 2 : 0;
+    int cur = 0, nlevels = -1;
+    std::vector<int> hl(132, 0);
     for (int level = 0; level < 128; level++) {
-        GL(c, k_g_node_reset, nblk(n1 - n0, 128), 128, n0, n1, g.gb.p);
+        // most nodes a level can hold: 2^level, and no more than there are nodes at all
+        const long long ub = level < 30 ? std::min<long long>(1ll << level, maxnodes) : maxnodes;
+        GL(c, k_g_node_reset, nblk(ub, 128), 128, g.lvl.p, level, g.gb.p);
         GL(c, k_g_sums, nblk(nlive, 256), 256, nlive, g.pnode[cur].p, g.pos[cur].p, g.mass[cur].p, dfac, g.gb.p);
-        GL(c, k_g_nodes_a, nblk(n1 - n0, 128), 128, n0, n1, g.nodes.p, g.gb.p, dfac, c->counters.p);
+        GL(c, k_g_nodes_a, nblk(ub, 128), 128, g.lvl.p, level, g.nodes.p, g.gb.p, dfac, c->counters.p);
         GL(c, k_g_moments, nblk(nlive, 256), 256, nlive, g.pnode[cur].p, g.pos[cur].p, g.mass[cur].p, g.nodes.p, g.gb.p, g.flag.p);
         tbb = g.cubtmp.cap;
         CUDA_TRY(c, cub::DeviceScan::ExclusiveSum(g.cubtmp.p, tbb, g.flag.p, g.scan.p, nlive, st));
         c->launches++;
-        GL(c, k_g_nodes_b, nblk(n1 - n0, 128), 128, n0, n1, g.nodes.p, g.gb.p, g.flag.p, g.scan.p, nnodes_d, maxnodes, c->counters.p);
+        GL(c, k_g_nodes_b, nblk(ub, 128), 128, g.lvl.p, level, g.nodes.p, g.gb.p, g.flag.p, g.scan.p, nnodes_d, maxnodes, c->counters.p);
         GL(c, k_g_scatter, nblk(nlive, 256), 256, nlive, g.pnode[cur].p, g.pos[cur].p, g.mass[cur].p, g.gid[cur].p, g.nodes.p, g.gb.p, g.flag.p, g.scan.p,
            g.pnode[1 - cur].p, g.pos[1 - cur].p, g.mass[1 - cur].p, g.gid[1 - cur].p);
+        GL(c, k_g_level_end, 1, 1, nnodes_d, g.lvl.p, level);
         cur = 1 - cur;
-        int nn = 0; unsigned long long err = 0;
-        CUDA_TRY(c, cudaMemcpyAsync(&nn, nnodes_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (level < first_check) continue;
+        unsigned long long err = 0;
+        CUDA_TRY(c, cudaMemcpyAsync(hl.data(), g.lvl.p, sizeof(int) * (level + 3), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(c, cudaMemcpyAsync(&err, c->counters.p + CNT_ERR, sizeof err, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
         if (err) { c->err = err == SPHGPU_ERR_OVERFLOW ? "gravity tree: number of nodes exceeds array dimensions" : "gravity tree: totmass_node==0"; return (int)err; }
-        g.level_start.push_back(n1);
-        if (nn == n1) break;                     // nothing was split
-        n0 = n1; n1 = nn;
+        for (int L = 0; L <= level; L++) if (hl[L + 2] == hl[L + 1]) { nlevels = L + 1; break; }      // level L split nothing: it is the last one
+        if (nlevels > 0) break;
     }
+    if (nlevels <= 0) { c->err = "gravity tree: more than 128 levels"; return SPHGPU_ERR_OVERFLOW; }
+    for (int L = 0; L <= nlevels; L++) g.level_start.push_back(hl[L]);
+    g.levels_prev = nlevels;
+    const int n1 = hl[nlevels];
     g.nn = n1; g.cur = cur;
     return SPHGPU_OK;
 }
