@@ -184,6 +184,8 @@ __global__ void k_g_nodes_a(const int *__restrict__ lvl, int L, GNode *__restric
 }
 
 // pass 2: size^2 = max |x - xcen|^2, quadrupole moments (kdtree.F90:734-752) and the left/right flag of sort_particles_in_cell (:937-1001)
+// (QUADS = false: the tree is built for the reference-compatible neighbour mode alone, which needs centres, sizes and topology)
+template <bool QUADS>
 __global__ void __launch_bounds__(256) k_g_moments(int nlive, const int *__restrict__ pnode, const double4 *__restrict__ pos, const double *__restrict__ mass,
                             const GNode *__restrict__ nodes, GBuild *__restrict__ gb, int *__restrict__ flag)
 {
@@ -202,8 +204,11 @@ __global__ void __launch_bounds__(256) k_g_moments(int nlive, const int *__restr
     int last; const bool head = seg_bounds(key, last);
     const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     double r2m = seg_max(r2, last);
-    double v[7] = {seg_sum(m * (dx * dx), last), seg_sum(m * (dx * dy), last), seg_sum(m * (dx * dz), last), seg_sum(m * (dy * dy), last),
-                   seg_sum(m * (dy * dz), last), seg_sum(m * (dz * dz), last), 0.};
+    double v[7] = {0., 0., 0., 0., 0., 0., 0.};
+    if (QUADS) {
+        v[0] = seg_sum(m * (dx * dx), last); v[1] = seg_sum(m * (dx * dy), last); v[2] = seg_sum(m * (dx * dz), last);
+        v[3] = seg_sum(m * (dy * dy), last); v[4] = seg_sum(m * (dy * dz), last); v[5] = seg_sum(m * (dz * dz), last);
+    }
     const bool buni = block_uniform_sum<7>(key, head, v, sh, shkey);
     if (buni) {                                   // block maximum of r2 through slot 6
         const int w = threadIdx.x >> 5;
@@ -215,8 +220,10 @@ __global__ void __launch_bounds__(256) k_g_moments(int nlive, const int *__restr
     if ((buni && threadIdx.x == 0) || (!buni && head && key >= 0)) {
         GBuild *b = &gb[key];
         atomicMax(&b->r2max, (unsigned long long)__double_as_longlong(r2m));
-        atomicAdd(&b->q[0], v[0]); atomicAdd(&b->q[1], v[1]); atomicAdd(&b->q[2], v[2]);
-        atomicAdd(&b->q[3], v[3]); atomicAdd(&b->q[4], v[4]); atomicAdd(&b->q[5], v[5]);
+        if (QUADS) {
+            atomicAdd(&b->q[0], v[0]); atomicAdd(&b->q[1], v[1]); atomicAdd(&b->q[2], v[2]);
+            atomicAdd(&b->q[3], v[3]); atomicAdd(&b->q[4], v[4]); atomicAdd(&b->q[5], v[5]);
+        }
     }
 }
 
@@ -710,7 +717,8 @@ static int grav_build(sphgpu_ctx *c, GravState &g, const GravInput &in)
         GL(c, k_g_node_reset, nblk(ub, 128), 128, g.lvl.p, level, g.gb.p);
         GL(c, k_g_sums, nblk(nlive, 256), 256, nlive, g.pnode[cur].p, g.pos[cur].p, g.mass[cur].p, dfac, g.gb.p);
         GL(c, k_g_nodes_a, nblk(ub, 128), 128, g.lvl.p, level, g.nodes.p, g.gb.p, dfac, c->counters.p);
-        GL(c, k_g_moments, nblk(nlive, 256), 256, nlive, g.pnode[cur].p, g.pos[cur].p, g.mass[cur].p, g.nodes.p, g.gb.p, g.flag.p);
+        if (p.gravity) GL(c, k_g_moments<true>, nblk(nlive, 256), 256, nlive, g.pnode[cur].p, g.pos[cur].p, g.mass[cur].p, g.nodes.p, g.gb.p, g.flag.p);
+        else GL(c, k_g_moments<false>, nblk(nlive, 256), 256, nlive, g.pnode[cur].p, g.pos[cur].p, g.mass[cur].p, g.nodes.p, g.gb.p, g.flag.p);
         tbb = g.cubtmp.cap;
         CUDA_TRY(c, cub::DeviceScan::ExclusiveSum(g.cubtmp.p, tbb, g.flag.p, g.scan.p, nlive, st));
         c->launches++;
