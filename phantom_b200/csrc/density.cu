@@ -425,10 +425,12 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                 }
             }
             if (__any_sync(FULLMASK, failed)) break;
-            const FilterScale fs = filter_scale((float)halfext, reach);
-            // converged / inactive targets get an empty mask; a wide periodic search switches the filter off
+            const bool wrapf = wide && rcut_list < 0.9 * halfLmin;      // thin periodic box: the filter takes the minimum image per pair (walk.cuh)
+            FilterScale fs = filter_scale((float)halfext, reach);
+            if (wrapf) filter_scale_wrap(fs);
+            // converged / inactive targets get an empty mask; a wide periodic search beyond that switches the filter off
             const double rfilt = RU ? radkern * h * (1. + a.mask_margin) : radkern * h;
-            const FilterTarget ft = filter_target(fs, xif, yif, zif, conv ? 0.f : (wide ? -1.f : __double2float_ru(rfilt)));
+            const FilterTarget ft = filter_target(fs, xif, yif, zif, conv ? 0.f : ((wide && !wrapf) ? -1.f : __double2float_ru(rfilt)));
             const bool masks_ok = RU && staged_all && its > 1 && __all_sync(FULLMASK, conv || radkern * h <= (double)ws.rmask[lane]);
             if (!conv) {
 #pragma unroll
@@ -468,8 +470,9 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                 unsigned nz;
                 if (RU && reuse) nz = conv ? 0u : ws.nzsave[lane];
                 else {
-                    nz = build_masks<false>(ws, nr, ft);
-                    if (RU) { ws.nzsave[lane] = nz; ws.rmask[lane] = conv ? 0.f : (wide ? 3.0e38f : __double2float_rd(rfilt)); }
+                    if (wrapf) { const FilterWrap fw = filter_wrap(fs, fLx, fLy, fLz); nz = build_masks<false, true>(ws, nr, ft, &fw); }
+                    else nz = build_masks<false>(ws, nr, ft);
+                    if (RU) { ws.nzsave[lane] = nz; ws.rmask[lane] = conv ? 0.f : ((wide && !wrapf) ? 3.0e38f : __double2float_rd(rfilt)); }
                 }
                 int c = -1; unsigned m = 0u;
                 if (FAST) {

@@ -455,11 +455,13 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
         // side would fail this must not switch the filter off for the groups of the small-h side.
         const double rloc = fmin(rreach, (double)reach * 1.0001);
         const bool wide = PERIODIC && (halfext + rloc >= 0.999 * halfLmin);
+        const bool wrapf = wide && rloc < 0.9 * halfLmin;           // kernel radii well below half the box: the filter wraps per pair (walk.cuh)
         // no pair of this group can straddle the periodic boundary: |xi - xj| <= L/2 for every candidate that survives the prefilter
         const bool interior = !PERIODIC || (cell.lo[0] - rloc > p.xmin && cell.hi[0] + rloc < p.xmax && cell.lo[1] - rloc > p.ymin &&
                                             cell.hi[1] + rloc < p.ymax && cell.lo[2] - rloc > p.zmin && cell.hi[2] + rloc < p.zmax);
         int nlist = 0;
-        const FilterScale fs = filter_scale((float)halfext, reach);
+        FilterScale fs = filter_scale((float)halfext, reach);
+        if (wrapf) filter_scale_wrap(fs);
         // ---- lane = target (start_cell, force.F90:2172-2514; per-particle part done by k_force_prep)
         const int s = cell.start + min(lane, cell.count - 1);
         bool act = false;
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
         const double hrho1i = -0.5 * rho1i;
         // force.F90:2255: inactive targets skipped (empty masks); a wide periodic search switches the filter off
         const FilterTarget ft = filter_target(fs, (float)(xi - cx), (float)(yi - cy), (float)(zi - cz),
-                                              act ? (wide ? -1.f : __double2float_ru(KF::radkern * h)) : 0.f);
+                                              act ? ((wide && !wrapf) ? -1.f : __double2float_ru(KF::radkern * h)) : 0.f);
         double fpot = 0.;
         double fx = 0., fy = 0., fz = 0., drhodt = 0., dudtdiss = 0., dendtdiss = 0., divBsym = 0., dBx = 0., dBy = 0., dBz = 0., divBdiff = 0.;
         double vsigmax = 0.;
@@ -490,7 +492,9 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
             const int myslot = ws.selfslot[lane];
             nlist += nr;
             const int nchunk = (nr + 31) >> 5;
-            unsigned nz = wide ? build_masks<false>(ws, nr, ft) : build_masks<true>(ws, nr, ft);
+            unsigned nz;
+            if (wrapf) { const FilterWrap fw = filter_wrap(fs, fLx, fLy, fLz); nz = build_masks<true, true>(ws, nr, ft, &fw); }
+            else nz = wide ? build_masks<false>(ws, nr, ft) : build_masks<true>(ws, nr, ft);
             int c = -1; unsigned m = 0u;
             // Two neighbours per trip, written phase by phase over both so that two independent FP64 dependency chains and both
             // records are in flight.  No branches: grad W is evaluated as truncated powers (zero beyond the support), r = 0 gives
@@ -774,9 +778,12 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
                                              fLx, fLy, fLz, ws.stack, clist, a.scratch_per_warp, reach);
         if (ncl < 0) { if (lane == 0) atomicMax(&a.cnt[CNT_ERR], (unsigned long long)SPHGPU_ERR_OVERFLOW); break; }
         // (largest kernel radius of this group's targets and candidates: bounded locally by the walk's reach, see k_force_fast)
-        const bool wide = PERIODIC && (halfext + fmin(KF::radkern * fmax(cell.hmax, (double)hmax_global) * a.hscale, (double)reach) * 1.0001 >= 0.999 * halfLmin);
+        const double rloc = fmin(KF::radkern * fmax(cell.hmax, (double)hmax_global) * a.hscale, (double)reach) * 1.0001;
+        const bool wide = PERIODIC && (halfext + rloc >= 0.999 * halfLmin);
+        const bool wrapf = wide && rloc < 0.9 * halfLmin;
         int nlist = 0;
-        const FilterScale fs = filter_scale((float)halfext, reach);
+        FilterScale fs = filter_scale((float)halfext, reach);
+        if (wrapf) filter_scale_wrap(fs);
         // ---- lane = target: start_cell (force.F90:2172-2514); the per-particle part was done by k_force_prep
         const int s = cell.start + min(lane, cell.count - 1);
         bool act = false, gasi = true, dusti = false; int itypei = IGAS;
@@ -789,7 +796,7 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
         const double hi1 = hv.x, hi21 = hv.y;
         // force.F90:2255: inactive targets skipped (empty masks); a wide periodic search switches the filter off
         const FilterTarget ft = filter_target(fs, (float)(pi.x - cx), (float)(pi.y - cy), (float)(pi.z - cz),
-                                              act ? (wide ? -1.f : __double2float_ru(KF::radkern * h)) : 0.f);
+                                              act ? ((wide && !wrapf) ? -1.f : __double2float_ru(KF::radkern * h)) : 0.f);
         double f[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) f[k] = 0.;
@@ -807,7 +814,9 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
                                                             a.max_leaf, fs, false, 0, NoRecord(), cj, a.stype);
                 if (nr == 0) continue;
                 nlist += nr;
-                unsigned nz = wide ? build_masks<false>(ws, nr, ft) : build_masks<true>(ws, nr, ft);
+                unsigned nz;
+            if (wrapf) { const FilterWrap fw = filter_wrap(fs, fLx, fLy, fLz); nz = build_masks<true, true>(ws, nr, ft, &fw); }
+            else nz = wide ? build_masks<false>(ws, nr, ft) : build_masks<true>(ws, nr, ft);
                 int c = -1; unsigned m = 0u;
 #define FORCE_PAIR_LOOP(CP)                                                                                                                                          \
                 while (true) {      /* two neighbours per trip, every lane on the same path */                                                                      \

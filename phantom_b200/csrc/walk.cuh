@@ -250,6 +250,26 @@ __device__ __forceinline__ FilterScale filter_scale(float halfext, float reach)
     fs.slack = 1.7321f * 9.77e-4f * (halfext * 1.0001f * __frcp_rd(ext) * 1.0001f + 1.f) + 1e-6f;
     return fs;
 }
+// Thin periodic boxes (the shock tube's y and z): a target group whose search sphere reaches beyond half a box length cannot use the
+// nearest image relative to the group CENTRE for every target.  While the kernel radii stay well below half the box (0.45 L) the
+// filter takes the minimum image per pair itself, a' = a - L rint(a / L) in the scaled FP16 coordinates (three more half2 operations
+// per axis), instead of being switched off and leaving every candidate to the FP64 test.  Error: the rounding of L to FP16 and of the
+// fused multiply-add add <= 2^-11 (L_s + |a'|) per axis with L_s = L x scale <= ~2.2 here; filter_scale_wrap widens the slack for it.
+struct FilterWrap { __half2 L[3], iL[3]; };
+__device__ __forceinline__ FilterWrap filter_wrap(const FilterScale &fs, float Lx, float Ly, float Lz)
+{
+    FilterWrap w;
+    const float L[3] = {Lx, Ly, Lz};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const __half l = __float2half_rn(fminf(L[k] * fs.scale, 3.0e4f));       // a direction without a (near) image: n = rint(a / 3e4) = 0
+        w.L[k] = __half2half2(l);
+        w.iL[k] = __float2half2_rn(1.f / __half2float(l));
+    }
+    return w;
+}
+__device__ __forceinline__ void filter_scale_wrap(FilterScale &fs) { fs.slack = 3.f * fs.slack + 2.0e-3f; }
+
 // limit on the scaled, FP16-evaluated r^2 for a kernel radius rc (>= the exact one); rc < 0: pass everything
 __device__ __forceinline__ __half filter_limit(const FilterScale &fs, float rc)
 {
@@ -329,8 +349,8 @@ __device__ __forceinline__ int stage_round(WS &ws, const int *__restrict__ clist
 // hit masks for the n staged candidates of the round: lane = target, loop over candidate pairs.  SYM: a pair passes when it is
 // inside the target's OR the candidate's radius (force pass); targets with limit 0 (inactive, converged) get empty masks.
 // Returns the lane's non-empty chunks as a bit mask (NCHUNK <= 32).
-template <bool SYM, class WS>
-__device__ __forceinline__ unsigned build_masks(WS &ws, int n, const FilterTarget &t)
+template <bool SYM, bool WRAP = false, class WS>
+__device__ __forceinline__ unsigned build_masks(WS &ws, int n, const FilterTarget &t, const FilterWrap *fw = nullptr)
 {
     unsigned nz = 0u;
     const int lane = lane_id();
@@ -341,8 +361,13 @@ __device__ __forceinline__ unsigned build_masks(WS &ws, int n, const FilterTarge
 #pragma unroll
         for (int p = 0; p < 16; p++) {
             const uint4 q = ws.hp[c][p];
-            const __half2 ax = __hsub2(t.x, *reinterpret_cast<const __half2 *>(&q.x)), ay = __hsub2(t.y, *reinterpret_cast<const __half2 *>(&q.y)),
-                          az = __hsub2(t.z, *reinterpret_cast<const __half2 *>(&q.z));
+            __half2 ax = __hsub2(t.x, *reinterpret_cast<const __half2 *>(&q.x)), ay = __hsub2(t.y, *reinterpret_cast<const __half2 *>(&q.y)),
+                    az = __hsub2(t.z, *reinterpret_cast<const __half2 *>(&q.z));
+            if (WRAP) {                                       // minimum image per pair (thin periodic box)
+                ax = __hfma2(__hneg2(h2rint(__hmul2(ax, fw->iL[0]))), fw->L[0], ax);
+                ay = __hfma2(__hneg2(h2rint(__hmul2(ay, fw->iL[1]))), fw->L[1], ay);
+                az = __hfma2(__hneg2(h2rint(__hmul2(az, fw->iL[2]))), fw->L[2], az);
+            }
             const __half2 r2 = __hfma2(az, az, __hfma2(ay, ay, __hmul2(ax, ax)));
             const __half2 lim = SYM ? __hmax2(t.lim, *reinterpret_cast<const __half2 *>(&q.w)) : t.lim;
             mine |= __hlt2_mask(r2, lim) & (0x00010001u << p);

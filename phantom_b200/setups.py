@@ -410,7 +410,7 @@ def setup_turb_block(nx, world, rank, mach=5.0, seed=1234):
     return part, boxes
 
 
-def setup_shock(nx=256, gamma=5. / 3.):
+def setup_shock(nx=256, gamma=5. / 3., width=1):
     """C1: SETUP=shock -- 3D Sod tube, quintic kernel, adiabatic, closepacked, periodic in y,z
     (setup_shock.f90:497-499 states; set_shock.f90:35-140; adjust_shock_boundaries :180-209)."""
     rhoL, rhoR, prL, prR = 1.0, 0.125, 1.0, 0.1
@@ -418,7 +418,7 @@ def setup_shock(nx=256, gamma=5. / 3.):
     xleft, xright, xshock = -0.5, 0.5, 0.0
     dxleft = (xshock - xleft) / nx          # nx particles across the left half (nx=256 -> 1/512)
     dxright = dxleft * (rhoL / rhoR) ** (1. / 3.)
-    fac = -6. * (int(1.99 * radkern / 6.) + 1) * max(dxleft, dxright)
+    fac = -6. * width * (int(1.99 * radkern / 6.) + 1) * max(dxleft, dxright)      # width > 1: a thicker tube than adjust_shock_boundaries makes (measurements)
     ymin, zmin = fac * math.sqrt(0.75), fac * math.sqrt(6.) / 3.
     ymax, zmax = -ymin, -zmin
     p = default_params(kernel=KERNEL_QUINTIC, hfact=hfact, gamma=gamma, ieos=2, isothermal=0,

@@ -59,6 +59,23 @@ def test_c1_sod_shock_tube():
     assert np.all(pg.fxyzu[b] == 0.)          # boundary particles take part in the first density pass (deriv.f90:146) but never in force
 
 
+def test_thin_periodic_tube_disordered():
+    """The shock tube's y, z extent is a few kernel radii: target groups whose search sphere reaches beyond half the box take the
+    FP16 filter that wraps every pair to its minimum image (walk.cuh: build_masks<.., WRAP>).  Particles shaken off the lattice and
+    given a spread of h so that nothing about the filter is aligned: neighbour totals, h and forces against the oracle."""
+    part = setups.setup_shock(nx=20)
+    rng = setups.Ran2(-777)
+    dx = 0.5 / 20
+    part.xyzh[:, :3] += 0.35 * dx * (rng.draw(3 * part.npart).reshape(-1, 3) - 0.5)
+    part.xyzh[:, 3] *= 0.92 + 0.16 * rng.draw(part.npart)
+    part.vxyzu[:, :3] = 0.3 * (rng.draw(3 * part.npart).reshape(-1, 3) - 0.5)
+    part.alphaind[:, 0] = 0.7
+    po, pg, sdo, sfo, sg = both(part)
+    gas = part.iphase == IGAS
+    check_common(po, pg, sdo, sfo, sg, active=gas)
+    assert sg.nactualtot == sdo.nactualtot and sg.npairs_force == sfo.npairs_force
+
+
 @pytest.mark.parametrize("ind_ts", [False, True])
 def test_c2_turbulent_box(ind_ts):
     # SETUP=turb: isothermal periodic box, cubic lattice, Mach 5 solenoidal velocity field

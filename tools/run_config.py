@@ -11,7 +11,7 @@ name, size = sys.argv[1], int(float(sys.argv[2]))
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 t0 = time.time()
 if name == "shock":
-    part = setups.setup_shock(nx=size)
+    part = setups.setup_shock(nx=size, width=int(os.environ.get("SHOCK_WIDTH", "1")))
 elif name == "turb":
     part = setups.setup_turb(nx=size)
 elif name == "mhdblast":
