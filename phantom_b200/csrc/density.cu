@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                 unsigned nz;
                 if (RU && reuse) nz = conv ? 0u : ws.nzsave[lane];
                 else {
-                    if (wrapf) { const FilterWrap fw = filter_wrap(fs, fLx, fLy, fLz); nz = build_masks<false, true>(ws, nr, ft, &fw); }
+                    if (wrapf) { const FilterWrap fw = filter_wrap(fs, (float)dp.dxbound, (float)dp.dybound, (float)dp.dzbound); nz = build_masks<false, true>(ws, nr, ft, &fw); }
                     else nz = build_masks<false>(ws, nr, ft);
                     if (RU) { ws.nzsave[lane] = nz; ws.rmask[lane] = conv ? 0.f : ((wide && !wrapf) ? 3.0e38f : __double2float_rd(rfilt)); }
                 }

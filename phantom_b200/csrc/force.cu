@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
             nlist += nr;
             const int nchunk = (nr + 31) >> 5;
             unsigned nz;
-            if (wrapf) { const FilterWrap fw = filter_wrap(fs, fLx, fLy, fLz); nz = build_masks<true, true>(ws, nr, ft, &fw); }
+            if (wrapf) { const FilterWrap fw = filter_wrap(fs, (float)dp.dxbound, (float)dp.dybound, (float)dp.dzbound); nz = build_masks<true, true>(ws, nr, ft, &fw); }
             else nz = wide ? build_masks<false>(ws, nr, ft) : build_masks<true>(ws, nr, ft);
             int c = -1; unsigned m = 0u;
             // Two neighbours per trip, written phase by phase over both so that two independent FP64 dependency chains and both
@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
                 if (nr == 0) continue;
                 nlist += nr;
                 unsigned nz;
-            if (wrapf) { const FilterWrap fw = filter_wrap(fs, fLx, fLy, fLz); nz = build_masks<true, true>(ws, nr, ft, &fw); }
+            if (wrapf) { const FilterWrap fw = filter_wrap(fs, (float)dp.dxbound, (float)dp.dybound, (float)dp.dzbound); nz = build_masks<true, true>(ws, nr, ft, &fw); }
             else nz = wide ? build_masks<false>(ws, nr, ft) : build_masks<true>(ws, nr, ft);
                 int c = -1; unsigned m = 0u;
 #define FORCE_PAIR_LOOP(CP)                                                                                                                                          \
