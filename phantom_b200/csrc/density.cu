@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(128, (FAST && !MHD) ? DENS_MINB : ((FAST && MH
                 }
             }
             if (__any_sync(FULLMASK, failed)) break;
-            const bool wrapf = wide && rcut_list < 0.9 * halfLmin;      // thin periodic box: the filter takes the minimum image per pair (walk.cuh)
+            const bool wrapf = FAST && wide && rcut_list < 0.9 * halfLmin;      // thin periodic box: the filter takes the minimum image per pair (walk.cuh)
             FilterScale fs = filter_scale((float)halfext, reach);
             if (wrapf) filter_scale_wrap(fs);
             // converged / inactive targets get an empty mask; a wide periodic search beyond that switches the filter off

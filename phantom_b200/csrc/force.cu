@@ -780,10 +780,8 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
         // (largest kernel radius of this group's targets and candidates: bounded locally by the walk's reach, see k_force_fast)
         const double rloc = fmin(KF::radkern * fmax(cell.hmax, (double)hmax_global) * a.hscale, (double)reach) * 1.0001;
         const bool wide = PERIODIC && (halfext + rloc >= 0.999 * halfLmin);
-        const bool wrapf = wide && rloc < 0.9 * halfLmin;
         int nlist = 0;
-        FilterScale fs = filter_scale((float)halfext, reach);
-        if (wrapf) filter_scale_wrap(fs);
+        const FilterScale fs = filter_scale((float)halfext, reach);
         // ---- lane = target: start_cell (force.F90:2172-2514); the per-particle part was done by k_force_prep
         const int s = cell.start + min(lane, cell.count - 1);
         bool act = false, gasi = true, dusti = false; int itypei = IGAS;
@@ -796,7 +794,7 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
         const double hi1 = hv.x, hi21 = hv.y;
         // force.F90:2255: inactive targets skipped (empty masks); a wide periodic search switches the filter off
         const FilterTarget ft = filter_target(fs, (float)(pi.x - cx), (float)(pi.y - cy), (float)(pi.z - cz),
-                                              act ? ((wide && !wrapf) ? -1.f : __double2float_ru(KF::radkern * h)) : 0.f);
+                                              act ? (wide ? -1.f : __double2float_ru(KF::radkern * h)) : 0.f);
         double f[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) f[k] = 0.;
@@ -814,9 +812,7 @@ __global__ void __launch_bounds__(128, XTRA ? XTRA_MINB : 4) k_force(const Force
                                                             a.max_leaf, fs, false, 0, NoRecord(), cj, a.stype);
                 if (nr == 0) continue;
                 nlist += nr;
-                unsigned nz;
-            if (wrapf) { const FilterWrap fw = filter_wrap(fs, (float)dp.dxbound, (float)dp.dybound, (float)dp.dzbound); nz = build_masks<true, true>(ws, nr, ft, &fw); }
-            else nz = wide ? build_masks<false>(ws, nr, ft) : build_masks<true>(ws, nr, ft);
+                unsigned nz = wide ? build_masks<false>(ws, nr, ft) : build_masks<true>(ws, nr, ft);     // (no per-pair wrap here: this kernel is instruction-fetch bound)
                 int c = -1; unsigned m = 0u;
 #define FORCE_PAIR_LOOP(CP)                                                                                                                                          \
                 while (true) {      /* two neighbours per trip, every lane on the same path */                                                                      \
