@@ -573,9 +573,14 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
                     if (GRAV) {                                            // softened gravity of SPH-neighbour pairs, force.F90:1303-1339, :1522
                         const double hj1 = R0[k].w, rij = r2[k] * rij1[k];
                         const double q2i = __dmul_rn(r2[k], hi21), q2j = __dmul_rn(r2[k], __dmul_rn(hj1, hj1));
-                        double phii = -rij1[k], fgravi = rij1[k] * rij1[k], fgravj = fgravi;
-                        if (ini[k]) { double fmi; KF::softening(q2i, rij * hi1, phii, fmi); phii *= hi1; fgravi = fmi * hi21 + T3.z * grkerni[k]; }
-                        if (inj[k]) { double phij, fmj; KF::softening(q2j, rij * hj1, phij, fmj); fgravj = fmj * (hj1 * hj1) + R3[k].z * grkernj[k]; }
+                        // both sides evaluated and selected (no branch between lanes that are inside one kernel, the other, both or none)
+                        double phis, fmi, phij, fmj;
+                        KF::softening_in(fmin(q2i, KF::radkern2), fmin(rij * hi1, KF::radkern), rij1[k] * h, phis, fmi);
+                        KF::softening_in(fmin(q2j, KF::radkern2), fmin(rij * hj1, KF::radkern), rij1[k] * rcp_pos(hj1), phij, fmj);
+                        const double newt = rij1[k] * rij1[k];
+                        const double phii = ini[k] ? phis * hi1 : -rij1[k];
+                        const double fgravi = ini[k] ? fmi * hi21 + T3.z * grkerni[k] : newt;
+                        const double fgravj = inj[k] ? fmj * (hj1 * hj1) + R3[k].z * grkernj[k] : newt;
                         fgrav = isn[k] ? 0.5 * pmass * (fgravi + fgravj) : 0.;
                         fpot += isn[k] ? pmass * phii : 0.;
                     }

@@ -67,6 +67,20 @@ template <> struct SphKern<0> {
             fs = (-5. * q6 + 36. * q4 * q - 90. * q4 + 80. * q2 * q - 2.) / (30. * q2);
         } else { pot = -1. / q; fs = 1. / q2; }
     }
+    // the same inside the support (q < 2), both pieces evaluated and selected: no branch between lanes on different pieces, no divisions
+    // (qinv = 1/q from the caller's 1/r); force.F90:1303-1339 calls it only for q2 < radkern2
+    __device__ __forceinline__ static void softening_in(double q2, double q, double qinv, double &pot, double &fs)
+    {
+        const double potA = fma(q2, fma(q2, fma(q, 0.1, -0.3), 2. / 3.), -1.4);
+        const double fsA = q * fma(q2, fma(q, 0.5, -1.2), 4. / 3.);
+        const double polB = fma(q2, fma(q, fma(q, 9. - q, -30.), 40.), -48.);
+        const double potB = fma(polB, 1. / 30., qinv * (1. / 15.));
+        const double pfB = fma(q2 * q, fma(q, fma(q, fma(q, -5., 36.), -90.), 80.), -2.);
+        const double fsB = pfB * (qinv * qinv) * (1. / 30.);
+        const bool inner = q < 1.;
+        pot = inner ? potA : potB;
+        fs = inner ? fsA : fsB;
+    }
     __device__ __forceinline__ static double wdrag(double q2, double q)
     {
         if (q < 1.) return q2 * (0.75 * q2 * q - 1.5 * q2 + 1.);
@@ -133,6 +147,7 @@ template <> struct SphKern<1> {
             fs = (-7. * q8 + 120. * q6 * q - 840. * q6 + 3024. * q4 * q - 5670. * q4 + 4536. * q2 * q - 507.) / (1680. * q2);
         } else { pot = -1. / q; fs = 1. / q2; }
     }
+    __device__ __forceinline__ static void softening_in(double q2, double q, double, double &pot, double &fs) { softening(q2, q, pot, fs); }
     __device__ __forceinline__ static double wdrag(double q2, double q)
     {
         if (q < 1.) { const double q4 = q2 * q2; return q2 * (-10. * q4 * q + 30. * q4 - 60. * q2 + 66.); }
