@@ -600,7 +600,9 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
                     double projsx = 0., projsy = 0., projsz = 0.;
                     if (ADIA) {                                            // artificial conductivity, force.F90:1606-1624
                         const double denij = T3.y - R3[k].y;
-                        const double vsigu = GRAV ? fabs(projv) : sqrt(fabs(pri - R3[k].x) * (2. * rho1i * rho1j / (rho1i + rho1j)));
+                        // sqrt(|dP| 2/(rho_i + rho_j)) without the library's division and square root (branch-free reciprocal and rsqrt)
+                        const double xu = fabs(pri - R3[k].x) * (2. * rho1i * rho1j) * rcp_pos(rho1i + rho1j);
+                        const double vsigu = GRAV ? fabs(projv) : xu * rsqrt_pos(xu);
                         const double auterm = 0.5 * pmass * rho1i * p.alphau, autermj = 0.5 * pmass * rho1j * p.alphau;
                         dendtdiss += vsigu * denij * (auterm * grkerni[k] + autermj * grkernj[k]);
                         dudtdiss += pmass * qrho2i * projv * grkerni[k];
