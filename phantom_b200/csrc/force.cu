@@ -115,6 +115,17 @@ __global__ void k_force_prep(int64_t nlive, const int *__restrict__ perm, const 
     if (p.ind_timesteps) { s_ibin[s] = ibin[i]; s_ibinold[s] = ibin_old[i]; s_wake[s] = (int)ibin_wake[i]; }
 }
 
+// 1/x for a normal x > 0: two Newton steps on the hardware seed, no special-case branch
+__device__ __forceinline__ double rcp_pos(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
 // get_ts (dust.f90:161-276): stopping time of a gas-dust pair
 // (not inlined: the Stokes branch carries a pow(); one copy keeps the general kernel's pair loops inside the instruction cache)
 __device__ __noinline__ double get_ts_d(const sphgpu_params &p, double rhogas, double rhodust, double spsoundgas, double dv2)
@@ -215,7 +226,7 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
     if (a.multitype) itypej = abs((int)a.stype[j]);
     const bool gg = isn && (CP == 0);                                         // gas-gas condition (force.F90:1539)
     const double r2s = isn ? r2 : 1.0;
-    const double rij1 = (r2s > DBL_MIN) ? rsqrt(r2s) : 0.;                    // force.F90:1293-1299
+    const double rij1 = rsqrt_pos(r2s);                                        // force.F90:1293-1299 (0 for a vanishing separation)
     const double rij = r2s * rij1;
     const double qi = rij * hi1, qj = rij * hj1;
     const double pmassj = Dj.z, pmassi = Di.z;
@@ -306,7 +317,7 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
         const double denij = vi.w - vj.w;
         double vsigu;
         if (p.gravity) vsigu = fabs(projv);
-        else vsigu = sqrt(fabs(pri - prj) * (2. * rho1i * Dj.x / (rho1i + Dj.x)));      // 2/(rho_i + rho_j)
+        else { const double xu = fabs(pri - prj) * (2. * rho1i * Dj.x) * rcp_pos(rho1i + Dj.x); vsigu = xu * rsqrt_pos(xu); }      // sqrt(|dP| 2/(rho_i + rho_j))
         const double auterm = 0.5 * pmassi * rho1i * p.alphau, autermj = 0.5 * pmassj * rho1j * p.alphau;
         f[A_DENDTDISS] += vsigu * denij * (auterm * grkerni + autermj * grkernj);
     }
@@ -323,7 +334,8 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
         const double rho21i = rho1i * rho1i, rho21j = rho1j * rho1j;
         const double avBterm = 0.5 * pmassi * rho1i * p.alphaB * rho1i, avBtermj = 0.5 * pmassj * rho1j * p.alphaB * rho1j;
         const double tx = dvx - projv * runix, ty = dvy - projv * runiy, tz = dvz - projv * runiz;
-        const double vsigB = sqrt(tx * tx + ty * ty + tz * tz);
+        const double t2 = tx * tx + ty * ty + tz * tz;
+        const double vsigB = t2 * rsqrt_pos(t2);
         const double dBdissterm = (avBterm * grkerni + avBtermj * grkernj) * vsigB;
         if (p.iresistive_heating > 0) dudtresist = -0.5 * dB2 * dBdissterm;
         const double pmjrho21grkerni = pmassj * rho21i * grkerni, pmjrho21grkernj = pmassj * rho21j * grkernj;
@@ -369,15 +381,6 @@ __device__ __forceinline__ void force_pair(double (&f)[12], double &vsigmax, int
 // alpha) as the two real*4 the reference stores} -- and the L1 data pipe, which bounds this kernel, carries a third less.  Target
 // and neighbour side go through the same function.  1/rho by a branch-free reciprocal (two Newton steps on the hardware seed).
 struct Iso1 { double gradhfac, pro2, avw, rho1; };
-__device__ __forceinline__ double rcp_pos(double x)
-{
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
-}
 __device__ __forceinline__ Iso1 iso1_derive(double h1, double packed, const ForceArgs &a)
 {
     Iso1 r;
@@ -617,7 +620,8 @@ __global__ void __launch_bounds__(128, MHD ? FORCE_MHD_MINB : (GRAV ? 3 : FORCE_
                         const double rho21i = rho1i * rho1i, rho21j = rho1j * rho1j;
                         const double avBterm = 0.5 * pmass * rho1i * p.alphaB * rho1i, avBtermj = 0.5 * pmass * rho1j * p.alphaB * rho1j;
                         const double tx = dvx - projv * runix, ty = dvy - projv * runiy, tz = dvz - projv * runiz;
-                        const double vsigB = sqrt(tx * tx + ty * ty + tz * tz);
+                        const double t2 = tx * tx + ty * ty + tz * tz;
+                        const double vsigB = t2 * rsqrt_pos(t2);                 // |v_ij x r|, branch-free
                         const double dBdissterm = (avBterm * grkerni[k] + avBtermj * grkernj[k]) * vsigB;
                         if (ADIA && p.iresistive_heating > 0) dudtdiss += -0.5 * (dBxx * dBxx + dByy * dByy + dBzz * dBzz) * dBdissterm;
                         const double pmjrho21grkerni = pmass * rho21i * grkerni[k], pmjrho21grkernj = pmass * rho21j * grkernj[k];
