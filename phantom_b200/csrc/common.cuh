@@ -255,6 +255,19 @@ __device__ __forceinline__ void get_partinfo_d(int8_t iphasei, int set_boundarie
     }
 }
 
+// 1/sqrt(x) for a normal x > 0 (a third-order step on the hardware seed, as the CUDA library does, without its special-case branch);
+// returns 0 for x == 0 or subnormal: coincident particles, for which the reference takes rij1 = 1/(0 + epsilon) times zero separation
+__device__ __forceinline__ double rsqrt_pos(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    y = fma(p * e, y, y);
+    return (__double2hiint(x) >= 0x00100000) ? y : 0.;
+}
+
 // max/min without the NaN canonicalisation of fmax/fmin (3 instructions instead of ~7); operands here are never NaN
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }

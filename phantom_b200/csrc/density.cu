@@ -125,7 +125,7 @@ __device__ __forceinline__ void dens_pair(double (&v)[29], double (&w)[B_COUNT],
     const bool isn = (q2i < KF::radkern2) && (j != s);                        // :679, :650 (exact membership)
     // rij = sqrt(rij2), rij1 = 1/(rij + epsilon) (dens.F90:688,:746) from one reciprocal square root
     const double r2s = isn ? r2 : 1.0;
-    const double rinv = (r2s > 0.) ? rsqrt(r2s) : 0.;
+    const double rinv = rsqrt_pos(r2s);
     const double rij = r2s * rinv;
     const double qi = rij * hi1;
     double wabi, grkerni;
@@ -188,7 +188,7 @@ __device__ __forceinline__ void dens_pair_rhodust(double &rhodust, int slot, con
     const double q2i = __dmul_rn(r2, hi21);
     const bool isn = (q2i < KF::radkern2) && (slot >= 0);
     const double r2s = isn ? r2 : 1.0;
-    const double rinv = (r2s > 0.) ? rsqrt(r2s) : 0.;
+    const double rinv = rsqrt_pos(r2s);
     const double qi = (r2s * rinv) * hi1;
     double wabi, grkerni;
     KF::get_kernel(isn ? q2i : 1.0, qi, wabi, grkerni);

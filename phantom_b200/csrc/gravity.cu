@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(128, 4) k_g_p2p(const P2PArgs a)
                     const double q2i = __dmul_rn(r2, ti.w), q2j = __dmul_rn(r2, pj.w);
                     const bool sph = (q2i < KF::radkern2) || (q2j < KF::radkern2);       // force.F90:1287: handled by k_force
                     const bool use = !sph && (t != tself);
-                    const double rinv = use ? rsqrt(r2) : 0.;
+                    const double rinv = use ? rsqrt_pos(r2) : 0.;
                     const double mr3 = mj * rinv * rinv * rinv;                            // force.F90:2020-2043
                     fx[t] -= dx * mr3; fy[t] -= dy * mr3; fz[t] -= dz * mr3;
                     ph[t] -= mj * rinv;

@@ -455,19 +455,6 @@ __device__ __forceinline__ void next_hits2(unsigned hm_lane, unsigned &nz, int &
     m &= m - 1u;
 }
 
-// 1/sqrt(x) for a normal x > 0 (a third-order step on the hardware seed, as the CUDA library does, without its special-case branch);
-// returns 0 for x == 0 or subnormal: coincident particles, for which the reference takes rij1 = 1/(0 + epsilon) times zero separation
-__device__ __forceinline__ double rsqrt_pos(double x)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double t = x * y;
-    const double e = fma(-t, y, 1.0);
-    const double p = fma(e, 0.375, 0.5);
-    y = fma(p * e, y, y);
-    return (__double2hiint(x) >= 0x00100000) ? y : 0.;
-}
-
 // exact reference separation: dx = xi - xj, minimum image (dens.F90:666-670), rij2 = dx*dx + dy*dy + dz*dz evaluated
 // left to right without FMA contraction so that set membership is bit-identical to the gfortran build
 template <bool PERIODIC>
