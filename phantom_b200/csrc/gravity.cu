@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(128) k_g_walk(const WalkArgs a)
                 else {
                     double dx, dy, dz, r2;
                     verdict = mac(nd, ns, a.tree_acc2, a.radkern, dx, dy, dz, r2);
-                    if (verdict == 0 && final_pass) { m2l(dx, dy, dz, 1. / sqrt(r2), ns.mass, ns.quads, f); nm2l++; }
+                    if (verdict == 0 && final_pass) { m2l(dx, dy, dz, rsqrt_pos(r2), ns.mass, ns.quads, f); nm2l++; }
                 }
             }
             const unsigned mleaf = __ballot_sync(FULLMASK, verdict == 1 && sleaf);
